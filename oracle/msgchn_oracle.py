@@ -1,0 +1,498 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (plain PyTorch fp32) of ProxyTTA's per-frame
+adaptation step for the MSG-CHN back-end.  It is the checker for the CUDA path, never the
+thing shipped or measured: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import it.
+
+Parity pinning: the reference ships no golden vectors and no runnable tests, so
+this restatement is pinned against *outputs of the reference itself run in the build container*
+(`oracle/gen_golden.py` imports /root/reference through `oracle/ref_shims.py`, feeds it the same
+seeded synthetic checkpoint and frames, and commits the results under tests/golden/).
+tests/test_oracle_golden.py checks this file against those fixtures (and, when /root/reference is
+present, against the live reference).
+
+Everything is functional over a flat state dict whose keys and shapes are exactly those of the
+reference's `network_adapt.state_dict()` after `_prepare_head(mode)` (132 entries for
+`meta_selfsup_seq_2layers_ema`), so the same `{'net': state_dict}` checkpoint feeds both.
+
+Reference files restated here (paths relative to the reference root):
+  N  = external_src/MSG_CHN/workspace/exp_msg_chn/network_exp_msg_chn_adapt.py
+  W  = src/msg_chn_model_adapt.py
+  E  = src/external_model_adapt.py
+  L  = src/loss_utils.py
+  U  = src/net_utils.py
+  T  = src/tta_main.py
+  V  = src/eval_utils.py
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------------------------
+# precision emulation hook (used only for tolerance studies: rounds a tensor to bf16 and back)
+# ----------------------------------------------------------------------------------------------
+class Precision:
+    """`act(x)` is applied to every 32/128-channel activation and head matrix, `wgt(w)` to every
+    conv / linear weight.  Identity in the fp32 oracle."""
+
+    def __init__(self, emulate=None):
+        self.emulate = emulate
+
+    def act(self, x):
+        if self.emulate == 'bf16':
+            return x.to(torch.bfloat16).to(torch.float32)
+        return x
+
+    def wgt(self, w):
+        if self.emulate == 'bf16':
+            return w.to(torch.bfloat16).to(torch.float32)
+        return w
+
+
+FP32 = Precision(None)
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic checkpoint / frames
+# ----------------------------------------------------------------------------------------------
+def _conv_entry(sd, g, name, cout, cin, bias=True, transposed=False):
+    # N:188-194  xavier_normal_ weights, bias 0.01 (encoders / decoders)
+    shape = (cin, cout, 3, 3) if transposed else (cout, cin, 3, 3)
+    fan_in, fan_out = cin * 9, cout * 9
+    if transposed:
+        fan_in, fan_out = cout * 9, cin * 9
+    std = math.sqrt(2.0 / (fan_in + fan_out))
+    sd[name + '.weight'] = torch.randn(shape, generator=g) * std
+    if bias:
+        sd[name + '.bias'] = torch.full((cout,), 0.01)
+
+
+def _bn_entry(sd, g, name, c):
+    # affine / running stats perturbed away from the (1, 0, 0, 1) init so that tests see them
+    sd[name + '.weight'] = 1.0 + 0.1 * torch.randn(c, generator=g)
+    sd[name + '.bias'] = 0.05 * torch.randn(c, generator=g)
+    sd[name + '.running_mean'] = 0.05 * torch.randn(c, generator=g)
+    sd[name + '.running_var'] = 1.0 + 0.1 * torch.rand(c, generator=g)
+    sd[name + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+
+
+def _linear_entry(sd, g, name, cout, cin):
+    bound = 1.0 / math.sqrt(cin)       # nn.Linear default: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+    sd[name + '.weight'] = (torch.rand((cout, cin), generator=g) * 2 - 1) * bound
+    sd[name + '.bias'] = (torch.rand((cout,), generator=g) * 2 - 1) * bound
+
+
+def _mlp_entries(sd, g, name, dim, out, hidden):
+    # N:1089-1098  Linear -> BatchNorm1d -> ReLU -> Linear
+    _linear_entry(sd, g, name + '.0', hidden, dim)
+    _bn_entry(sd, g, name + '.1', hidden)
+    _linear_entry(sd, g, name + '.3', out, hidden)
+
+
+def make_synthetic_checkpoint(seed=0, prepare_mode='meta_selfsup_seq_2layers_ema'):
+    """Seeded stand-in for the Google-Drive checkpoints (none is in the reference tree).  Key set
+    and shapes follow N:166-335 (network) and N:1022-1087 (`_prepare_head`)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+
+    def encoder(prefix, cin, n_enc):
+        _conv_entry(sd, g, prefix + '.init.0', 32, cin)
+        _conv_entry(sd, g, prefix + '.init.2', 32, 32)
+        for k in range(1, n_enc + 1):
+            _conv_entry(sd, g, '%s.enc%d.1' % (prefix, k), 32, 32)
+            _conv_entry(sd, g, '%s.enc%d.3' % (prefix, k), 32, 32)
+
+    def decoder(prefix):
+        for blk in ('dec2', 'dec1'):
+            _conv_entry(sd, g, '%s.%s.1' % (prefix, blk), 32, 32, transposed=True)
+            _conv_entry(sd, g, '%s.%s.3' % (prefix, blk), 32, 32)
+        _conv_entry(sd, g, prefix + '.prdct.1', 32, 32)
+        _conv_entry(sd, g, prefix + '.prdct.3', 1, 32)
+
+    encoder('rgb_encoder', 3, 4)
+    encoder('depth_encoder1', 1, 2)
+    decoder('depth_decoder1')
+    encoder('depth_encoder2', 2, 2)
+    decoder('depth_decoder2')
+    encoder('depth_encoder3', 2, 2)
+    decoder('depth_decoder3')
+    if 'selfsup' in prepare_mode:
+        _mlp_entries(sd, g, 'proj', 32, 512, 512)
+        if 'ema' in prepare_mode:
+            for k in [k for k in sd if k.startswith('proj.')]:
+                sd['proj_t.' + k[5:]] = sd[k].clone()
+        _mlp_entries(sd, g, 'pred', 512, 512, 512)
+    if 'meta' in prepare_mode and 'seq' in prepare_mode:
+        if '1layer' in prepare_mode:
+            # N:1066-1068  Conv2d(32,32,3,1,1), kaiming_normal fan_out
+            sd['conv1_rgb_meta.weight'] = torch.randn((32, 32, 3, 3), generator=g) * math.sqrt(2.0 / (32 * 9))
+            sd['conv1_rgb_meta.bias'] = (torch.rand((32,), generator=g) * 2 - 1) / math.sqrt(32 * 9)
+        elif '2layers' in prepare_mode:
+            # N:28-36, 1073  Res_Conv(32,128,3,1,1)
+            p = 'conv1_rgb_meta.conv1_meta'
+            bound = 1.0 / math.sqrt(32 * 9)
+            sd[p + '.0.0.weight'] = (torch.rand((128, 32, 3, 3), generator=g) * 2 - 1) * bound
+            _bn_entry(sd, g, p + '.0.1', 128)
+            bound = 1.0 / math.sqrt(128 * 9)
+            sd[p + '.1.weight'] = (torch.rand((32, 128, 3, 3), generator=g) * 2 - 1) * bound
+            sd[p + '.1.bias'] = (torch.rand((32,), generator=g) * 2 - 1) * bound
+            _bn_entry(sd, g, p + '.2', 32)
+        else:
+            raise NotImplementedError(prepare_mode)
+    return sd
+
+
+def checkpoint_digest(sd):
+    """Order-independent fingerprint of a state dict (guards the 'same seed -> same checkpoint on
+    the GPU box' assumption the fixtures rely on)."""
+    tot = 0.0
+    for k in sorted(sd):
+        v = sd[k].double()
+        tot += float(v.sum()) + 0.5 * float(v.abs().sum()) + 1e-3 * v.numel()
+    return tot
+
+
+DATASETS = {
+    # name: (sampling density, depth cap, dense depth surface)  -- SURVEY.md §8d
+    'kitti': (0.05, 80.0),
+    'void': (0.005, 8.0),
+}
+
+
+def synthetic_frame(seq_seed, t, n, h, w, dataset='kitti', outlier_fraction=0.01):
+    """Frame t of synthetic sequence `seq_seed`: image in [0,255]; sparse depth = smooth
+    surface x Bernoulli(p), with ~1 % of the samples pushed +5 m so the outlier filter has work."""
+    p, cap = DATASETS[dataset]
+    g = torch.Generator().manual_seed(1000 * seq_seed + t)
+    yy = torch.arange(h, dtype=torch.float32).view(1, 1, h, 1)
+    xx = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w)
+    # smooth texture + +-4 grey levels of noise: i.i.d. uniform [0,255] pixels would make the
+    # edge-aware weights exp(-|dI|) underflow to 0 and the smoothness loss vanish
+    ph = torch.tensor([0.0, 1.3, 2.1]).view(1, 3, 1, 1)
+    image = 127.0 + 100.0 * torch.sin(xx / 31.0 + ph + 0.05 * t) * torch.cos(yy / 17.0 + 0.5 * ph)
+    image = image + 8.0 * (torch.rand((n, 3, h, w), generator=g) - 0.5)
+    image = image.clamp(0.0, 255.0).contiguous()
+    if dataset == 'kitti':
+        dense = 5.0 + 70.0 * (1.0 - yy / h) + 2.0 * torch.sin((xx + 3.0 * t) / 97.0)
+    else:
+        dense = 0.5 + 4.0 * (yy / h) + 0.3 * torch.sin((xx + 3.0 * t) / 53.0)
+    dense = dense.expand(n, 1, h, w).contiguous()
+    mask = (torch.rand((n, 1, h, w), generator=g) < p).float()
+    out = (torch.rand((n, 1, h, w), generator=g) < outlier_fraction).float()
+    sparse = (dense + 5.0 * out * (cap / 80.0)) * mask
+    return image, sparse, dense
+
+
+# ----------------------------------------------------------------------------------------------
+# pre-processing (driver side): T:583-590, U:766-811
+# ----------------------------------------------------------------------------------------------
+def validity_map(sparse_depth):
+    # T:583-586
+    return torch.where(sparse_depth > 0, torch.ones_like(sparse_depth), sparse_depth)
+
+
+def remove_outliers(sparse_depth, validity, kernel_size=7, threshold=1.5):
+    # U:766-811
+    max_value = 10 * torch.max(sparse_depth)
+    filled = torch.where(validity <= 0, torch.full_like(sparse_depth, float(max_value)), sparse_depth)
+    pad = kernel_size // 2
+    filled = F.pad(filled, (pad, pad, pad, pad), mode='constant', value=float(max_value))
+    min_values = -F.max_pool2d(-filled, kernel_size=kernel_size, stride=1, padding=0)
+    clean = torch.where(min_values < sparse_depth - threshold,
+                        torch.zeros_like(validity), torch.ones_like(validity))
+    clean = validity * clean
+    return sparse_depth * clean, clean
+
+
+# ----------------------------------------------------------------------------------------------
+# network (N:166-311, 463-557)
+# ----------------------------------------------------------------------------------------------
+def _conv(sd, name, x, pr, stride=1):
+    return F.conv2d(x, pr.wgt(sd[name + '.weight']), sd.get(name + '.bias'), stride=stride, padding=1)
+
+
+def _convT(sd, name, x, pr):
+    return F.conv_transpose2d(x, pr.wgt(sd[name + '.weight']), sd[name + '.bias'], stride=2, padding=1,
+                              output_padding=1)
+
+
+def _up2(x):
+    # Appendix B: align_corners=True
+    return F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True)
+
+
+def _enc_block(sd, prefix, x, pr):
+    # ReLU, conv s2, ReLU, conv  (N:175-186)
+    x = pr.act(_conv(sd, prefix + '.1', F.relu(x), pr, stride=2))
+    return pr.act(_conv(sd, prefix + '.3', F.relu(x), pr))
+
+
+def _init_block(sd, prefix, x, pr):
+    # conv, ReLU, conv (N:171-173)
+    x = pr.act(_conv(sd, prefix + '.0', x, pr))
+    return pr.act(_conv(sd, prefix + '.2', F.relu(x), pr))
+
+
+def rgb_encoder(sd, rgb, pr=FP32):
+    # N:256-264
+    x0 = _init_block(sd, 'rgb_encoder.init', rgb, pr)
+    outs = [x0]
+    for k in range(1, 5):
+        outs.append(_enc_block(sd, 'rgb_encoder.enc%d' % k, outs[-1], pr))
+    return outs
+
+
+def depth_encoder(sd, prefix, inp, pre_x2=None, pre_x3=None, pre_x4=None, pr=FP32):
+    # N:196-211
+    x0 = _init_block(sd, prefix + '.init', inp, pr)
+    if pre_x4 is not None:
+        x0 = pr.act(x0 + _up2(pre_x4))
+    x1 = _enc_block(sd, prefix + '.enc1', x0, pr)
+    if pre_x3 is not None:
+        x1 = pr.act(x1 + _up2(pre_x3))
+    x2 = _enc_block(sd, prefix + '.enc2', x1, pr)
+    if pre_x2 is not None:
+        x2 = pr.act(x2 + _up2(pre_x2))
+    return x0, x1, x2
+
+
+def _dec_block(sd, prefix, x, pr):
+    # ReLU, convT s2, ReLU, conv (N:271-283)
+    x = pr.act(_convT(sd, prefix + '.1', F.relu(x), pr))
+    return pr.act(_conv(sd, prefix + '.3', F.relu(x), pr))
+
+
+def depth_decoder(sd, prefix, pre_dx, pre_cx, pr=FP32):
+    # N:297-311
+    x2 = pr.act(pre_dx[2] + pre_cx[2])
+    x1 = pr.act(pre_dx[1] + pre_cx[1])
+    x0 = pr.act(pre_dx[0] + pre_cx[0])
+    x3 = _dec_block(sd, prefix + '.dec2', x2, pr)
+    x4 = _dec_block(sd, prefix + '.dec1', pr.act(x1 + x3), pr)
+    h = pr.act(_conv(sd, prefix + '.prdct.1', F.relu(pr.act(x4 + x0)), pr))
+    out = _conv(sd, prefix + '.prdct.3', F.relu(h), pr)
+    return x2, x3, x4, out
+
+
+def _bn_train(sd, name, x, training, momentum=0.1, eps=1e-5):
+    """BatchNorm in the module's current mode; in train mode the running statistics in `sd` are
+    updated in place, exactly as nn.BatchNorm does (this is what makes the reference update them
+    twice per step, SURVEY.md gotcha 8)."""
+    rm, rv = sd[name + '.running_mean'], sd[name + '.running_var']
+    y = F.batch_norm(x, rm, rv, sd[name + '.weight'], sd[name + '.bias'], training, momentum, eps)
+    if training:
+        sd[name + '.num_batches_tracked'] += 1
+    return y
+
+
+def meta_layer(sd, x, training, pr=FP32):
+    """conv1_rgb_meta: N:28-36 (Res_Conv, '2layers') or a plain Conv2d ('1layer', N:1066)."""
+    if 'conv1_rgb_meta.weight' in sd:
+        return pr.act(_conv(sd, 'conv1_rgb_meta', x, pr))
+    p = 'conv1_rgb_meta.conv1_meta'
+    h = pr.act(F.conv2d(x, pr.wgt(sd[p + '.0.0.weight']), None, padding=1))
+    h = pr.act(F.leaky_relu(_bn_train(sd, p + '.0.1', h, training), 0.2))
+    h = pr.act(_conv(sd, p + '.1', h, pr))
+    h = _bn_train(sd, p + '.2', h, training)
+    return pr.act(h + x)
+
+
+def pyramid(d):
+    # N:479,487,492  validity-normalised average pooling
+    c = (d > 0).float()
+    d14 = F.avg_pool2d(d, 4, 4) / (F.avg_pool2d(c, 4, 4) + 0.0001)
+    d12 = F.avg_pool2d(d, 2, 2) / (F.avg_pool2d(c, 2, 2) + 0.0001)
+    return d12, d14
+
+
+def _cascade(sd, enc_c, d, d12, d14, with_decoder3, pr):
+    # N:487-506 (real branch) / N:515-532 (zero branch, stops after depth_encoder3)
+    enc14 = depth_encoder(sd, 'depth_encoder1', d14, pr=pr)
+    dcd14 = depth_decoder(sd, 'depth_decoder1', enc14, enc_c[2:5], pr)
+    p12 = _up2(dcd14[3])
+    enc12 = depth_encoder(sd, 'depth_encoder2', torch.cat((d12, p12), 1), dcd14[0], dcd14[1], dcd14[2], pr)
+    dcd12 = depth_decoder(sd, 'depth_decoder2', enc12, enc_c[1:4], pr)
+    p11 = _up2(dcd12[3] + p12)
+    enc11 = depth_encoder(sd, 'depth_encoder3', torch.cat((d, p11), 1), dcd12[0], dcd12[1], dcd12[2], pr)
+    if not with_decoder3:
+        return None, enc11
+    dcd11 = depth_decoder(sd, 'depth_decoder3', enc11, enc_c[0:3], pr)
+    return dcd11[3] + p11, enc11
+
+
+def _mlp(sd, name, x, training, pr):
+    # N:1089-1098
+    h = pr.act(F.linear(x, pr.wgt(sd[name + '.0.weight']), sd[name + '.0.bias']))
+    h = pr.act(F.relu(_bn_train(sd, name + '.1', h, training)))
+    return pr.act(F.linear(h, pr.wgt(sd[name + '.3.weight']), sd[name + '.3.bias']))
+
+
+def network_forward(sd, image, sparse_depth, training, pr=FP32):
+    """network_adapt._rgbd_meta_contrast with mode = [adapt, reverse, seq, ema] (N:463-557), i.e.
+    loss_type 'adapt_meta_selfsup_seq_ema_reverse'.  Train mode returns (output, emb, ref); eval mode
+    returns output only."""
+    d12, d14 = pyramid(sparse_depth)
+    enc_c = rgb_encoder(sd, image, pr)
+    enc_c[2] = meta_layer(sd, enc_c[2], training, pr)
+    output, enc11 = _cascade(sd, enc_c, sparse_depth, d12, d14, True, pr)
+    if not training:
+        return output
+    with torch.no_grad():
+        enc_z = rgb_encoder(sd, torch.zeros_like(image), pr)
+        enc_z[2] = meta_layer(sd, enc_z[2], training, pr)
+        _, enc11_zero = _cascade(sd, enc_z, sparse_depth, d12, d14, False, pr)
+    # N:551-554 ('ema', 'reverse', 'adapt'): rows are pixels of the /4 map in NHWC order
+    z_zero = enc11_zero[2].permute(0, 2, 3, 1).reshape(-1, 32).detach()
+    z_real = enc11[2].permute(0, 2, 3, 1).reshape(-1, 32)
+    emb = _mlp(sd, 'pred', _mlp(sd, 'proj', z_zero, training, pr), training, pr)
+    ref = _mlp(sd, 'proj', z_real, training, pr)
+    return output, emb, ref
+
+
+def model_forward(sd, image, sparse_depth, training, max_input_depth, pr=FP32):
+    """ExternalModel_Adapt.forward (E:103-108: clamp) -> MsgChnModel_Adapt.forward (W:54-125).
+    The pad-to-/16 + flip-pad ensembling (W:58-125) is restated for completeness."""
+    if max_input_depth is not None:
+        sparse_depth = torch.clamp(sparse_depth, 0, max_input_depth)
+    h, w = image.shape[-2:]
+    pt = (16 - h % 16) % 16
+    prt = (16 - w % 16) % 16
+    if pt == 0 and prt == 0:
+        return network_forward(sd, image, sparse_depth, training, pr)
+    image0 = F.pad(image, (0, prt, pt, 0, 0, 0)); sparse0 = F.pad(sparse_depth, (0, prt, pt, 0, 0, 0))
+    image1 = F.pad(image, (prt, 0, 0, pt, 0, 0)); sparse1 = F.pad(sparse_depth, (prt, 0, 0, pt, 0, 0))
+    out = network_forward(sd, torch.cat([image0, image1], 0), torch.cat([sparse0, sparse1], 0), training, pr)
+    output = out[0] if training else out
+    o0, o1 = torch.chunk(output, 2, 0)
+    hh, ww = o0.shape[-2:]
+    o0 = o0[:, :, pt:, :ww - prt]
+    o1 = o1[:, :, :hh - pt, prt:]
+    output = 0.5 * (o0 + o1)
+    if training:
+        return output, out[1], out[2]
+    return output
+
+
+# ----------------------------------------------------------------------------------------------
+# losses: L:116-169, 624-638; E:371-441
+# ----------------------------------------------------------------------------------------------
+def smoothness_loss(predict, image):
+    # L:139-169 with gradient_yx L:624-638
+    pdx = predict[:, :, :, :-1] - predict[:, :, :, 1:]
+    pdy = predict[:, :, :-1, :] - predict[:, :, 1:, :]
+    idx = image[:, :, :, :-1] - image[:, :, :, 1:]
+    idy = image[:, :, :-1, :] - image[:, :, 1:, :]
+    wx = torch.exp(-torch.mean(torch.abs(idx), dim=1, keepdim=True))
+    wy = torch.exp(-torch.mean(torch.abs(idy), dim=1, keepdim=True))
+    return torch.mean(wx * torch.abs(pdx)) + torch.mean(wy * torch.abs(pdy))
+
+
+def sparse_depth_loss(src, tgt, w):
+    # L:116-137 (no epsilon: an empty frame gives NaN in the reference too)
+    delta = torch.abs(tgt - src)
+    loss = torch.sum(w * delta, dim=[1, 2, 3])
+    return torch.mean(loss / torch.sum(w, dim=[1, 2, 3]))
+
+
+def adapt_loss(input_rgb, output_depth, sparse_depth, validity, embedding, reference,
+               w_sd, w_sm, w_cos, max_input_depth=None):
+    # E:191-203 (clamp) + E:371-441
+    if max_input_depth is not None:
+        sparse_depth = torch.clamp(sparse_depth, 0, max_input_depth)
+    l_sm = smoothness_loss(output_depth, input_rgb)
+    l_sd = sparse_depth_loss(output_depth, sparse_depth, validity)
+    e = F.normalize(embedding, dim=-1, p=2)
+    r = F.normalize(reference, dim=-1, p=2)
+    l_cos = (2 - 2 * (e * r).sum(dim=-1)).mean()
+    if l_cos < 0.3:           # E:424 (a host sync in the reference)
+        w_cos = 0
+    loss = w_sd * l_sd + w_sm * l_sm + w_cos * l_cos
+    return loss, {'loss': loss, 'loss_smooth': l_sm, 'loss_sparse_depth': l_sd, 'loss_cos': l_cos}
+
+
+# ----------------------------------------------------------------------------------------------
+# adapted parameters + Adam: W:392-396; T:341-346,633 (torch.optim.Adam, amsgrad False, wd 0)
+# ----------------------------------------------------------------------------------------------
+_FLOAT_STATE = ('weight', 'bias')
+
+
+def adapt_parameter_names(sd, mode='meta'):
+    # W:392-396: every *parameter* (not buffer) whose name contains 'meta'
+    if mode != 'meta':
+        raise NotImplementedError(mode)
+    return [k for k in sd if 'meta' in k and k.rsplit('.', 1)[-1] in _FLOAT_STATE]
+
+
+class AdamState:
+    def __init__(self, names, sd):
+        self.step = 0
+        self.m = {k: torch.zeros_like(sd[k]) for k in names}
+        self.v = {k: torch.zeros_like(sd[k]) for k in names}
+
+
+def adam_update(sd, grads, state, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """torch.optim.Adam single-tensor formulation."""
+    state.step += 1
+    b1, b2 = betas
+    bc1 = 1 - b1 ** state.step
+    bc2 = 1 - b2 ** state.step
+    for k, g in grads.items():
+        p = sd[k]
+        if weight_decay != 0:
+            g = g + weight_decay * p
+        state.m[k].mul_(b1).add_(g, alpha=1 - b1)
+        state.v[k].mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (state.v[k].sqrt() / math.sqrt(bc2)).add_(eps)
+        p.data.addcdiv_(state.m[k], denom, value=-(lr / bc1))
+
+
+# ----------------------------------------------------------------------------------------------
+# one full TTA step: T:583-633
+# ----------------------------------------------------------------------------------------------
+def tta_step(sd, state, image, sparse_depth, *, lr, w_sd=1.0, w_sm=1.0, w_cos=0.1,
+             max_input_depth=80.0, normalize=lambda im: im / 255.0, pr=FP32, return_grads=False):
+    """`image` is the raw [0,255] image; the network sees `normalize(image)` (T:595-604, 610), the
+    smoothness loss sees the raw one (T:620; SURVEY.md gotcha 7).  Mutates `sd` (adapted tensors,
+    BN buffers) and `state`.  Returns a dict of everything the parity tests compare."""
+    names = list(state.m.keys())
+    v = validity_map(sparse_depth)
+    d_f, v_f = remove_outliers(sparse_depth, v)
+    work = dict(sd)
+    leaves = {}
+    for k in names:
+        leaves[k] = sd[k].detach().clone().requires_grad_(True)
+        work[k] = leaves[k]
+    out, emb, ref = model_forward(work, normalize(image), d_f, True, max_input_depth, pr)
+    loss, info = adapt_loss(image, out, d_f, v_f, emb, ref, w_sd, w_sm, w_cos, max_input_depth)
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(names, grads)}
+    adam_update(sd, grads, state, lr)
+    res = {
+        'validity': v_f, 'sparse_depth': d_f, 'output_depth': out.detach(),
+        'loss': float(loss), 'loss_smooth': float(info['loss_smooth']),
+        'loss_sparse_depth': float(info['loss_sparse_depth']), 'loss_cos': float(info['loss_cos']),
+    }
+    if return_grads:
+        res['grads'] = grads
+        res['emb'] = emb.detach()
+        res['ref'] = ref.detach()
+    return res
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluation metrics: V:117-175 (torch variants used by T:760-798), after the depth-range mask
+# ----------------------------------------------------------------------------------------------
+def eval_metrics(output_depth, ground_truth, min_depth, max_depth):
+    """T:773-798 with V:117-175: mask = gt>0 and min<=gt<=max; MAE / RMSE on 1000*depth (mm),
+    iMAE / iRMSE on 0.001*depth (1/km), eps 1e-9 (V:24)."""
+    eps = 1e-9
+    mask = (ground_truth > 0) & ~(ground_truth < min_depth) & ~(ground_truth > max_depth)
+    o = output_depth[mask]
+    g = ground_truth[mask]
+    mae = torch.mean(torch.abs(1000.0 * g - 1000.0 * o))
+    rmse = torch.sqrt(torch.mean((1000.0 * g - 1000.0 * o) ** 2))
+    imae = torch.mean(torch.abs(1.0 / (0.001 * g + eps) - 1.0 / (0.001 * o + eps)))
+    irmse = torch.sqrt(torch.mean((1.0 / (0.001 * g + eps) - 1.0 / (0.001 * o + eps)) ** 2))
+    return {'mae': float(mae), 'rmse': float(rmse), 'imae': float(imae), 'irmse': float(irmse)}
