@@ -1,0 +1,125 @@
+/* ptta_b200.h -- C ABI of the B200-native ProxyTTA adaptation step (libptta_b200.so).
+ *
+ * Drop-in boundary for seobbro/TTA-depth-completion's per-frame TTA step.  The reference has no C
+ * FFI of its own for MSG-CHN (it is PyTorch eager: src/external_model_adapt.py:82-237,371-441,
+ * src/msg_chn_model_adapt.py:32-125, external_src/MSG_CHN/workspace/exp_msg_chn/
+ * network_exp_msg_chn_adapt.py:337-557) and one pybind11 module for NLSPN's deformable conv
+ * (external_src/NLSPN/src/model/deformconv/src/vision.cpp:6-13).  Every entry point below names the
+ * reference code it replaces.  Conventions:
+ *   - plain C: raw DEVICE pointers, ints, floats, a cudaStream_t passed as void*; no torch types;
+ *   - every function returns 0 on success; on failure a message is available from ptta_last_error();
+ *   - nothing allocates device memory behind the caller's back: the engine reports the workspace it
+ *     needs (ptta_msgchn_workspace_bytes) and the caller binds a buffer of that size;
+ *   - all work is enqueued on the given stream; nothing synchronises unless stated;
+ *   - 32-channel feature maps are NHWC bf16, single-channel maps fp32 [N,H,W], images fp32 NCHW.
+ */
+#ifndef PTTA_B200_H
+#define PTTA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ptta_stream_t;            /* cudaStream_t */
+typedef struct ptta_msgchn ptta_msgchn; /* opaque engine */
+
+const char* ptta_last_error(void);
+int ptta_version(void);
+
+/* ---- stand-alone operators (also the units the parity tests exercise) ------------------------- */
+
+/* src/tta_main.py:583-586 (validity map) + src/net_utils.py:766-811 (OutlierRemoval.remove_outliers) */
+int ptta_outlier_removal(const float* sparse_depth, float* filtered_depth, float* filtered_validity,
+                         int n, int h, int w, int kernel_size, float threshold, ptta_stream_t stream);
+/* src/external_model_adapt.py:103-108 (clamp) + network_exp_msg_chn_adapt.py:479,487,492 (pyramid) */
+int ptta_pyramid(const float* depth, float* depth_clamped, float* depth_half, float* depth_quarter,
+                 int n, int h, int w, float max_input_depth, int do_clamp, ptta_stream_t stream);
+/* fp32 conv weight -> bf16 [tap][O][I] operand; strides in elements, flip reverses the 3x3 taps */
+int ptta_pack_conv_weight(const float* src, void* dst_bf16, int o, int i, int stride_o, int stride_i, int flip,
+                          ptta_stream_t stream);
+/* F.conv2d / F.conv_transpose2d 3x3 (network_exp_msg_chn_adapt.py:166-311) and their data gradients.
+ * mode: 0 stride 1, 1 stride 2, 2 transposed stride 2.  prologue: 0 none, 1 ReLU, 2 BN-affine+LeakyReLU.
+ * mask_mode: 0 none, 1 [mask>0], 2 LeakyReLU'(mask*mask_scale+mask_shift).  out = add + mask*(conv+bias). */
+int ptta_conv3x3(const void* in_bf16, void* out_bf16, const void* wpack_bf16, const float* bias,
+                 int n, int hin, int win, int cin, int cout, int mode,
+                 int prologue, const float* pro_scale, const float* pro_shift, float slope,
+                 const void* mask_bf16, int mask_mode, const float* mask_scale, const float* mask_shift,
+                 const void* add_bf16, ptta_stream_t stream);
+/* weight gradient of a 3x3 stride-1 conv (autograd of the meta layer, network_exp_msg_chn_adapt.py:28-36) */
+size_t ptta_conv3x3_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout);
+int ptta_conv3x3_wgrad(const void* in_bf16, const void* gout_bf16, float* dw, void* workspace,
+                       int n, int h, int w, int cin, int cout,
+                       int prologue, const float* pro_scale, const float* pro_shift, float slope, ptta_stream_t stream);
+/* {1,2,3}-plane fp32 -> 32-channel stem conv (init.0 layers, :172,220), optional ReLU mask */
+int ptta_stem_conv(const float* const* planes, const long long* batch_strides, const float* scale, const float* shift,
+                   int cin, const float* weight, const float* bias, const void* mask_bf16, void* out_bf16,
+                   int n, int h, int w, ptta_stream_t stream);
+/* 32 -> 1 conv (prdct.3, :289); weight is [9][32] fp32 */
+int ptta_head_conv(const void* in_bf16, const float* weight_9x32, float bias, const float* add, float* out,
+                   int n, int h, int w, int relu_in, int accumulate, ptta_stream_t stream);
+/* F.interpolate(scale_factor=2, bilinear, align_corners=True) (:201-209,493,500) and adjoints */
+int ptta_up2_1ch(const float* a, const float* b, const float* c, float* out, int n, int h, int w, ptta_stream_t stream);
+int ptta_up2_1ch_adjoint(const float* g_hi, float* g_lo, int n, int h, int w, int accumulate, ptta_stream_t stream);
+int ptta_add_up2_c32(const void* x_bf16, const void* half_bf16, void* out_bf16, int n, int h, int w, ptta_stream_t stream);
+int ptta_up2_c32_adjoint(const void* g_hi_bf16, void* g_lo_bf16, int n, int h, int w, int accumulate, ptta_stream_t stream);
+/* nn.Linear (:1089-1098): C[M][N] = A[M][K] * B[N][K]^T + bias */
+int ptta_gemm_bf16(const void* a, const void* b, void* c, const float* bias, long long m, int n, int k, ptta_stream_t stream);
+/* torch.optim.Adam over one flat fp32 buffer (src/tta_main.py:341-346,633); step is 1-based */
+int ptta_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, ptta_stream_t stream);
+
+/* ---- MSG-CHN ProxyTTA engine ------------------------------------------------------------------- */
+/* prepare_mode: the reference's string, e.g. "meta_selfsup_seq_2layers_ema" (network_exp_msg_chn_adapt.py:1022-1087) */
+int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepare_mode);
+void ptta_msgchn_destroy(ptta_msgchn* e);
+size_t ptta_msgchn_workspace_bytes(const ptta_msgchn* e);
+int ptta_msgchn_bind_workspace(ptta_msgchn* e, void* workspace, size_t bytes, ptta_stream_t stream);
+/* bind one state-dict entry (fp32, or int64 for num_batches_tracked) by its reference key; also
+ * "grad/<key>", "adam_m/<key>", "adam_v/<key>" for the adapted tensors. Pointers are not owned. */
+int ptta_msgchn_set_tensor(ptta_msgchn* e, const char* key, void* device_ptr, long long numel);
+/* number / names of state-dict keys the engine requires (for error reporting and tests) */
+int ptta_msgchn_num_keys(const ptta_msgchn* e);
+const char* ptta_msgchn_key(const ptta_msgchn* e, int i);
+/* (re)build the bf16 operand copies: all layers (+ cached zero-image rgb_encoder features) or only the adapted meta layer */
+int ptta_msgchn_pack_weights(ptta_msgchn* e, ptta_stream_t stream);
+int ptta_msgchn_pack_adapted(ptta_msgchn* e, ptta_stream_t stream);
+/* ExternalModel_Adapt.forward (src/external_model_adapt.py:82-114) -> network_adapt.forward
+ * (network_exp_msg_chn_adapt.py:337-557).  image: fp32 NCHW; the network sees image*img_scale[c]+img_shift[c].
+ * img_scale / img_shift are HOST arrays of 3 floats.  training != 0 also runs the zero-image branch and the proxy heads. */
+int ptta_msgchn_forward(ptta_msgchn* e, const float* image, const float* img_scale, const float* img_shift,
+                        const float* sparse_depth, float max_input_depth, int training, ptta_stream_t stream);
+/* ExternalModel_Adapt.compute_loss(loss_type='adapt') -> adapt_loss (src/external_model_adapt.py:371-441) on the
+ * outputs of the last training forward; results stay on the device (ptta_msgchn_read_losses syncs). */
+int ptta_msgchn_loss(ptta_msgchn* e, const float* image_raw, const float* sparse_depth, const float* validity,
+                     float max_input_depth, float w_sparse_depth, float w_smoothness, float w_cos, ptta_stream_t stream);
+int ptta_msgchn_read_losses(ptta_msgchn* e, float* out5 /* loss, sparse, smooth, cos, w_cos_eff */, ptta_stream_t stream);
+/* loss.backward() restricted to what the adapted tensors need (src/tta_main.py:631-632) */
+int ptta_msgchn_backward(ptta_msgchn* e, float grad_scale, ptta_stream_t stream);
+/* the same in two halves, for autograd integration: loss -> ("g_output" fp32 [N,H,W], "g_ref" bf16 [R,512]),
+ * then ("g_output", "g_ref") -> gradients of the adapted tensors ("grad/<key>" buffers) */
+int ptta_msgchn_loss_backward(ptta_msgchn* e, float grad_scale, ptta_stream_t stream);
+int ptta_msgchn_network_backward(ptta_msgchn* e, ptta_stream_t stream);
+/* optimizer.step() (src/tta_main.py:633) + repack of the adapted bf16 operands */
+int ptta_msgchn_set_adam(ptta_msgchn* e, float lr, float beta1, float beta2, float eps, float weight_decay, int step_count, ptta_stream_t stream);
+int ptta_msgchn_adam_step(ptta_msgchn* e, ptta_stream_t stream);
+/* the whole per-frame step, src/tta_main.py:583-633: outlier removal, forward, loss, backward, Adam */
+int ptta_msgchn_tta_step(ptta_msgchn* e, const float* image_raw, const float* img_scale, const float* img_shift,
+                         const float* sparse_depth, float max_input_depth,
+                         float w_sparse_depth, float w_smoothness, float w_cos, ptta_stream_t stream);
+/* same step captured once into a CUDA graph and replayed (inputs are read from the same device buffers each launch) */
+int ptta_msgchn_tta_step_graph(ptta_msgchn* e, const float* image_raw, const float* img_scale, const float* img_shift,
+                               const float* sparse_depth, float max_input_depth,
+                               float w_sparse_depth, float w_smoothness, float w_cos, ptta_stream_t stream);
+/* named access to engine-owned tensors ("output", "emb", "ref", "filtered_depth", "filtered_validity", any
+ * activation by its debug name). dtype: 0 fp32, 1 bf16. dims: up to 4 (NHWC for maps). */
+int ptta_msgchn_get_tensor(ptta_msgchn* e, const char* name, void** ptr, int* dtype, long long* dims4);
+int ptta_msgchn_num_tensors(const ptta_msgchn* e);
+const char* ptta_msgchn_tensor_name(const ptta_msgchn* e, int i);
+/* number of kernels launched by this engine since creation (for bench.py's gpu_launches) */
+long long ptta_msgchn_launch_count(const ptta_msgchn* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

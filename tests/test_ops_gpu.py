@@ -1,0 +1,261 @@
+"""Per-operator parity of the CUDA kernels (through the C ABI) against plain PyTorch fp32 on the same inputs.
+
+Tolerances: integer-valued outputs (validity mask, filtered sparse depth) bit-exact; fp32 kernels 1e-5;
+bf16-storage kernels are compared after rounding the fp32 reference to bf16, within a few bf16 ulps
+(the kernels accumulate in fp32, so the only differences are summation order and the final rounding)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import msgchn_oracle as O
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from tta_depth_completion_b200 import ops as _ops
+    return _ops
+
+
+DEV = 'cuda'
+
+
+def nhwc(x):      # NCHW float -> NHWC bf16 cuda
+    return x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)
+
+
+def nchw(x):      # NHWC bf16 cuda -> NCHW float cpu
+    return x.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def assert_close_bf16(got, want, what, ulps=4.0):
+    """|got - want| <= ulps * 2^-8 * max(|want|, scale) elementwise, scale = rms of want"""
+    scale = float(want.pow(2).mean().sqrt())
+    tol = ulps * 2.0 ** -8 * torch.maximum(want.abs(), torch.full_like(want, scale))
+    err = (got - want).abs()
+    bad = err > tol
+    assert not bool(bad.any()), '%s: %d / %d elements off, max err %.4g (rms %.4g)' % (what, int(bad.sum()), bad.numel(),
+                                                                                       float(err.max()), scale)
+
+
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(1, 64, 128), (2, 48, 80), (1, 37, 53), (1, 352, 1216)])
+def test_outlier_removal_bit_exact(ops, shape):
+    n, h, w = shape
+    _, sparse, _ = O.synthetic_frame(3, 1, n, h, w, 'kitti')
+    want_d, want_v = O.remove_outliers(sparse, O.validity_map(sparse))
+    d, v = ops.outlier_removal(sparse.to(DEV))
+    assert torch.equal(v.cpu(), want_v) and torch.equal(d.cpu(), want_d)
+    assert int(want_v.sum()) < int((sparse > 0).sum()) or h < 40      # the filter really removed something
+
+
+def test_outlier_removal_edge_cases(ops):
+    z = torch.zeros(1, 1, 32, 32)
+    d, v = ops.outlier_removal(z.to(DEV))                     # empty frame
+    assert float(d.abs().sum()) == 0 and float(v.sum()) == 0
+    full = torch.full((1, 1, 32, 32), 5.0)
+    full[0, 0, 10, 10] = 20.0                                  # one gross outlier in a dense map
+    want_d, want_v = O.remove_outliers(full, O.validity_map(full))
+    d, v = ops.outlier_removal(full.to(DEV))
+    assert torch.equal(v.cpu(), want_v) and torch.equal(d.cpu(), want_d) and float(v[0, 0, 10, 10]) == 0.0
+
+
+@pytest.mark.parametrize('shape', [(1, 64, 128), (2, 48, 80), (1, 352, 1216)])
+def test_pyramid(ops, shape):
+    n, h, w = shape
+    _, sparse, _ = O.synthetic_frame(2, 0, n, h, w, 'kitti')
+    sparse = sparse * 1.5                                       # some values above the 80 m cap
+    dc, d2, d4 = ops.pyramid(sparse.to(DEV), 80.0)
+    want = torch.clamp(sparse, 0, 80.0)
+    w2, w4 = O.pyramid(want)
+    assert torch.equal(dc.cpu(), want)
+    assert torch.allclose(d2.cpu(), w2, rtol=1e-5, atol=1e-6) and torch.allclose(d4.cpu(), w4, rtol=1e-5, atol=1e-6)
+    assert torch.equal((d2.cpu() > 0), (w2 > 0)) and torch.equal((d4.cpu() > 0), (w4 > 0))
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _conv_case(n, h, w, cin, cout, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = bf(torch.randn((n, cin, h, w), generator=g))
+    wt = bf(torch.randn((cout, cin, 3, 3), generator=g) * (2.0 / (9 * cin)) ** 0.5)
+    b = torch.randn((cout,), generator=g) * 0.1
+    return x, wt, b
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout', [(1, 32, 48, 32, 32), (2, 19, 37, 32, 32), (1, 16, 32, 32, 128), (1, 16, 32, 128, 32),
+                                            (1, 3, 5, 32, 32), (1, 88, 304, 32, 32)])
+def test_conv_s1_forward_relu_prologue(ops, n, h, w, cin, cout):
+    x, wt, b = _conv_case(n, h, w, cin, cout, 1)
+    want = bf(F.conv2d(F.relu(x), wt, b, padding=1))
+    got = ops.conv3x3(nhwc(x), ops.pack_conv_weight(wt.to(DEV), 'conv_fwd'), b.to(DEV), ops.MODE_S1, ops.PRO_RELU)
+    assert_close_bf16(nchw(got), want, 'conv s1')
+
+
+@pytest.mark.parametrize('n,h,w', [(1, 32, 48), (2, 18, 38), (1, 6, 10), (1, 176, 608)])
+def test_conv_s2_forward(ops, n, h, w):
+    x, wt, b = _conv_case(n, h, w, 32, 32, 2)
+    want = bf(F.conv2d(F.relu(x), wt, b, stride=2, padding=1))
+    got = ops.conv3x3(nhwc(x), ops.pack_conv_weight(wt.to(DEV), 'conv_fwd'), b.to(DEV), ops.MODE_S2, ops.PRO_RELU)
+    assert_close_bf16(nchw(got), want, 'conv s2')
+
+
+@pytest.mark.parametrize('n,h,w', [(1, 16, 24), (2, 9, 19), (1, 3, 5), (1, 88, 304)])
+def test_conv_transposed_forward(ops, n, h, w):
+    g = torch.Generator().manual_seed(3)
+    x = bf(torch.randn((n, 32, h, w), generator=g))
+    wt = bf(torch.randn((32, 32, 3, 3), generator=g) * (2.0 / 288) ** 0.5)          # [Cin, Cout, 3, 3]
+    b = torch.randn((32,), generator=g) * 0.1
+    want = bf(F.conv_transpose2d(F.relu(x), wt, b, stride=2, padding=1, output_padding=1))
+    got = ops.conv3x3(nhwc(x), ops.pack_conv_weight(wt.to(DEV), 'convT_fwd'), b.to(DEV), ops.MODE_T2, ops.PRO_RELU)
+    assert_close_bf16(nchw(got), want, 'convT')
+
+
+def test_conv_data_gradients(ops):
+    """dgrad of conv s1 / conv s2 / convT against autograd, with ReLU mask and accumulate."""
+    g = torch.Generator().manual_seed(4)
+    n, h, w = 2, 16, 24
+    wt = bf(torch.randn((32, 32, 3, 3), generator=g) * (2.0 / 288) ** 0.5)
+    pre = bf(torch.randn((n, 32, h, w), generator=g))                                # saved pre-activation (mask source)
+    extra = bf(torch.randn((n, 32, h, w), generator=g))
+    # stride 1: y = conv(relu(pre))
+    x = pre.clone().requires_grad_(True)
+    y = F.conv2d(F.relu(x), wt, None, padding=1)
+    gy = bf(torch.randn(y.shape, generator=g))
+    y.backward(gy)
+    want = bf(x.grad + extra)
+    got = ops.conv3x3(nhwc(gy), ops.pack_conv_weight(wt.to(DEV), 'conv_dgrad_s1'), None, ops.MODE_S1, ops.PRO_NONE,
+                      mask=nhwc(pre), mask_mode=ops.MASK_RELU, add=nhwc(extra))
+    assert_close_bf16(nchw(got), want, 'dgrad s1')
+    # stride 2: y = conv_s2(relu(pre)) -> data gradient is a transposed conv
+    x = pre.clone().requires_grad_(True)
+    y = F.conv2d(F.relu(x), wt, None, stride=2, padding=1)
+    gy = bf(torch.randn(y.shape, generator=g))
+    y.backward(gy)
+    got = ops.conv3x3(nhwc(gy), ops.pack_conv_weight(wt.to(DEV), 'conv_dgrad_s2'), None, ops.MODE_T2, ops.PRO_NONE,
+                      mask=nhwc(pre), mask_mode=ops.MASK_RELU)
+    assert_close_bf16(nchw(got), bf(x.grad), 'dgrad s2')
+    # transposed: y = convT(relu(pre)) -> data gradient is a stride-2 conv
+    x = pre.clone().requires_grad_(True)
+    y = F.conv_transpose2d(F.relu(x), wt, None, stride=2, padding=1, output_padding=1)
+    gy = bf(torch.randn(y.shape, generator=g))
+    y.backward(gy)
+    got = ops.conv3x3(nhwc(gy), ops.pack_conv_weight(wt.to(DEV), 'convT_dgrad'), None, ops.MODE_S2, ops.PRO_NONE,
+                      mask=nhwc(pre), mask_mode=ops.MASK_RELU)
+    assert_close_bf16(nchw(got), bf(x.grad), 'dgrad convT')
+
+
+def test_conv_bn_leaky_prologue_and_mask(ops):
+    g = torch.Generator().manual_seed(5)
+    n, h, w = 1, 16, 32
+    hraw = bf(torch.randn((n, 128, h, w), generator=g))
+    scale = torch.rand((128,), generator=g) + 0.5
+    shift = torch.randn((128,), generator=g) * 0.3
+    wt = bf(torch.randn((32, 128, 3, 3), generator=g) * (2.0 / 1152) ** 0.5)
+    b = torch.randn((32,), generator=g) * 0.1
+    x = hraw.clone().requires_grad_(True)
+    act = F.leaky_relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), 0.2)
+    y = F.conv2d(bf(act.detach()) + (act - act.detach()), wt, b, padding=1)       # forward sees the bf16-rounded activation
+    got = ops.conv3x3(nhwc(hraw), ops.pack_conv_weight(wt.to(DEV), 'conv_fwd'), b.to(DEV), ops.MODE_S1, ops.PRO_BN_LEAKY,
+                      pro_scale=scale.to(DEV), pro_shift=shift.to(DEV))
+    assert_close_bf16(nchw(got), bf(y.detach()), 'conv bn+leaky prologue')
+    # data gradient down to the BN output: g * leaky'(bn(h))
+    gy = bf(torch.randn(y.shape, generator=g))
+    act2 = F.leaky_relu(hraw * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), 0.2).requires_grad_(True)
+    F.conv2d(act2, wt, b, padding=1).backward(gy)
+    pre = hraw * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    want = bf(act2.grad * torch.where(pre > 0, torch.ones_like(pre), torch.full_like(pre, 0.2)))
+    got = ops.conv3x3(nhwc(gy), ops.pack_conv_weight(wt.to(DEV), 'conv_dgrad_s1'), None, ops.MODE_S1, ops.PRO_NONE,
+                      mask=nhwc(hraw), mask_mode=ops.MASK_BN_LEAKY, mask_scale=scale.to(DEV), mask_shift=shift.to(DEV))
+    assert_close_bf16(nchw(got), want, 'dgrad with leaky-bn mask')
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout', [(1, 16, 32, 32, 128), (2, 19, 21, 128, 32), (1, 22, 76, 32, 32)])
+def test_conv_wgrad(ops, n, h, w, cin, cout):
+    g = torch.Generator().manual_seed(6)
+    x = bf(torch.randn((n, cin, h, w), generator=g))
+    gy = bf(torch.randn((n, cout, h, w), generator=g))
+    wt = torch.zeros((cout, cin, 3, 3), requires_grad=True)
+    F.conv2d(x, wt, None, padding=1).backward(gy)
+    got = ops.conv3x3_wgrad(nhwc(x), nhwc(gy)).cpu()
+    rel = float((got - wt.grad).norm() / wt.grad.norm())
+    assert rel < 2e-5, rel
+
+
+def test_stem_and_head_conv(ops):
+    g = torch.Generator().manual_seed(7)
+    n, h, w = 2, 24, 40
+    for cin in (1, 2, 3):
+        x = torch.randn((n, cin, h, w), generator=g)
+        wt = torch.randn((32, cin, 3, 3), generator=g) * 0.3
+        b = torch.randn((32,), generator=g) * 0.1
+        want = bf(F.conv2d(x, wt, b, padding=1))
+        planes = [x[:, c].contiguous().to(DEV) for c in range(cin)]
+        got = ops.stem_conv(planes, wt.to(DEV), b.to(DEV))
+        assert_close_bf16(nchw(got), want, 'stem cin=%d' % cin, ulps=2.0)
+    x = bf(torch.randn((n, 32, h, w), generator=g))
+    wt = torch.randn((1, 32, 3, 3), generator=g) * 0.1
+    add = torch.randn((n, h, w), generator=g)
+    want = F.conv2d(F.relu(x), wt, torch.tensor([0.25]), padding=1)[:, 0] + add
+    w9 = wt[0].reshape(32, 9).t().contiguous()               # [tap][c]
+    got = ops.head_conv(nhwc(x), w9.to(DEV), 0.25, add.to(DEV), relu_in=True)
+    assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('n,h,w', [(1, 8, 12), (2, 11, 19), (1, 88, 304)])
+def test_up2_and_adjoints(ops, n, h, w):
+    g = torch.Generator().manual_seed(8)
+    a = torch.randn((n, h, w), generator=g)
+    b = torch.randn((n, h, w), generator=g)
+    c = torch.randn((n, 2 * h, 2 * w), generator=g)
+    want = F.interpolate((a + b).unsqueeze(1), scale_factor=2, mode='bilinear', align_corners=True)[:, 0] + c
+    got = ops.up2_1ch(a.to(DEV), b.to(DEV), c.to(DEV))
+    assert torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-5)
+    # adjoint against autograd
+    al = a.clone().requires_grad_(True)
+    F.interpolate(al.unsqueeze(1), scale_factor=2, mode='bilinear', align_corners=True).backward(c.unsqueeze(1))
+    got = ops.up2_1ch_adjoint(c.to(DEV))
+    assert torch.allclose(got.cpu(), al.grad, rtol=1e-4, atol=1e-5)
+    # 32-channel bf16 variants
+    x = bf(torch.randn((n, 32, 2 * h, 2 * w), generator=g))
+    half = bf(torch.randn((n, 32, h, w), generator=g))
+    want = bf(x + F.interpolate(half, scale_factor=2, mode='bilinear', align_corners=True))
+    got = ops.add_up2_c32(nhwc(x), nhwc(half))
+    assert_close_bf16(nchw(got), want, 'add_up2_c32', ulps=2.0)
+    hl = half.clone().requires_grad_(True)
+    F.interpolate(hl, scale_factor=2, mode='bilinear', align_corners=True).backward(x)
+    got = ops.up2_c32_adjoint(nhwc(x))
+    assert_close_bf16(nchw(got), bf(hl.grad), 'up2_c32_adjoint', ulps=2.0)
+
+
+@pytest.mark.parametrize('m,n,k', [(300, 512, 32), (1000, 512, 512), (513, 32, 512), (26752, 512, 512)])
+def test_gemm(ops, m, n, k):
+    g = torch.Generator().manual_seed(9)
+    a = bf(torch.randn((m, k), generator=g))
+    b = bf(torch.randn((n, k), generator=g) / k ** 0.5)
+    bias = torch.randn((n,), generator=g)
+    want = bf(a.to(DEV) @ b.to(DEV).t() + bias.to(DEV)).cpu()      # fp32 matmul of bf16-exact inputs (TF32 off by default)
+    got = ops.gemm_bf16(a.to(DEV, torch.bfloat16), b.to(DEV, torch.bfloat16), bias.to(DEV)).float().cpu()
+    assert_close_bf16(got, want, 'gemm %dx%dx%d' % (m, n, k))
+
+
+def test_adam_matches_torch(ops):
+    g = torch.Generator().manual_seed(10)
+    p0 = torch.randn((5000,), generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    p = p0.clone().to(DEV)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 6):
+        grad = torch.randn((5000,), generator=g) * 10.0 ** float(torch.randint(-6, 1, (1,), generator=g))
+        ref.grad = grad.clone()
+        opt.step()
+        ops.adam_flat(p, grad.to(DEV), m, v, 1e-3, step)
+    assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(m.cpu(), opt.state[ref]['exp_avg'], rtol=1e-6, atol=1e-12)
+    assert torch.allclose(v.cpu(), opt.state[ref]['exp_avg_sq'], rtol=1e-6, atol=1e-20)

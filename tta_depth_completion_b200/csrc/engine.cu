@@ -1,0 +1,1161 @@
+// MSG-CHN ProxyTTA engine: the whole per-frame adaptation step (src/tta_main.py:583-633 of the
+// reference) as a fixed sequence of sm_100a kernels over an engine-owned activation arena.
+//
+// Graph restated from external_src/MSG_CHN/workspace/exp_msg_chn/network_exp_msg_chn_adapt.py
+// (RGBEncoder :214-264, DepthEncoder :166-211, DepthDecoder :267-311, Res_Conv :28-36,
+// _rgbd_meta_contrast :463-557, heads :1022-1098).  The backward pass is hand-derived and only
+// visits what the adapted ("meta") tensors need: the proxy head on the real
+// rows, decoder3/encoder3/decoder2/encoder2, decoder1's prediction layers and the meta layer.
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <atomic>
+
+#include "common.cuh"
+#include "conv_mma.cuh"
+#include "gemm_mma.cuh"
+#include "small_kernels.cuh"
+#include "../../include/ptta_b200.h"
+
+namespace ptta {
+
+static thread_local std::string g_error;
+static std::atomic<long long> g_launches(0);
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("kernel launch %s failed: %s", what, cudaGetErrorString(e));
+        return 3;
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+struct Map32 { bf16* p = nullptr; int n = 0, h = 0, w = 0, c = 32; size_t numel() const { return (size_t)n * h * w * c; } };
+struct Map1 { float* p = nullptr; int n = 0, h = 0, w = 0; size_t numel() const { return (size_t)n * h * w; } };
+struct TensorInfo { void* p; int dtype; long long d[4]; };
+
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0;
+    void* take(size_t bytes) {
+        size_t o = (off + 255) & ~(size_t)255;
+        off = o + bytes;
+        return base ? base + o : nullptr;
+    }
+};
+
+struct ConvLayer {
+    std::string name;
+    int cin = 32, cout = 32;
+    bool transposed = false, has_bias = true;
+    const float* w = nullptr; const float* b = nullptr;
+    bf16* pack_fwd = nullptr; bf16* pack_dgrad = nullptr;
+    int mode_fwd = MODE_S1, mode_dgrad = MODE_S1;
+};
+struct StemLayer {   // init.0: {1,2,3} -> 32
+    std::string name; int cin = 1;
+    const float* w = nullptr; const float* b = nullptr;
+    float* dgrad_ch1 = nullptr;   // [9][32] flipped weights of input plane 1 (cascade encoders)
+};
+struct HeadLayer {   // prdct.3: 32 -> 1
+    std::string name;
+    const float* w = nullptr; const float* b = nullptr;
+    float* w_fwd = nullptr;       // [9][32]
+    float* w_dgrad = nullptr;     // [32][1][3][3] flipped, stem-shaped
+    float bias_host = 0.f;
+};
+struct BnState {     // per call-site statistics
+    float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr;
+};
+struct BnLayer {
+    std::string name; int c = 0;
+    float *gamma = nullptr, *beta = nullptr, *rm = nullptr, *rv = nullptr; long long* nbt = nullptr;
+};
+struct LinearLayer {
+    std::string name; int in = 0, out = 0;
+    const float* w = nullptr; const float* b = nullptr;
+    bf16* pack = nullptr;     // [out][in]
+    bf16* pack_t = nullptr;   // [in][out]  (data gradient)
+};
+
+struct EncW { StemLayer init0; ConvLayer init2, e1a, e1b, e2a, e2b, e3a, e3b, e4a, e4b; int nenc = 2; };
+struct DecW { ConvLayer d2a, d2b, d1a, d1b, p1; HeadLayer p3; };
+
+struct EncAct { Map32 a0, x0, t1, x1, t2, x2; };
+struct DecAct { Map32 x2, x1, x0, u2, x3, s1, u1, x4, s0, h; Map1 out; };
+struct Branch {
+    Map32 c[5];            // rgb features (c[2] after the meta layer)
+    Map32 c2raw;           // rgb x2 before the meta layer
+    Map32 mh, mg;          // meta: conv1 output (128 ch), conv2 output (32 ch), both pre-BN
+    BnState bn1, bn2;
+    EncAct e1, e2, e3;
+    DecAct d1, d2, d3;
+    Map1 p12, p11;
+    Map1 output;
+};
+
+}  // namespace ptta
+
+using namespace ptta;
+
+struct ptta_msgchn {
+    int N, H, W;
+    bool two_layers, has_heads;
+    std::string prepare_mode;
+    cudaStream_t st = nullptr;      // stream of the call in flight
+    Arena arena;
+    size_t ws_bytes = 0;
+    bool bound = false, packed = false;
+    std::map<std::string, std::pair<void*, long long>> ext;   // façade-owned tensors by key
+    std::vector<std::string> keys;                            // required keys
+    std::map<std::string, TensorInfo> named;
+    std::vector<std::string> named_order;
+
+    // weights
+    EncW rgbW, enc1W, enc2W, enc3W;
+    DecW dec1W, dec2W, dec3W;
+    ConvLayer meta1, meta2;          // 2layers: 32->128 (no bias), 128->32 ; 1layer: meta1 = 32->32
+    BnLayer metaBn1, metaBn2;
+    LinearLayer proj0, proj3, pred0, pred3;
+    BnLayer projBn, predBn;
+    std::vector<std::string> adapt_names;
+
+    // activations
+    Branch real, zero;
+    Map32 rgbT[5];                   // rgb encoder temporaries (a0 / t_k), per resolution
+    Map32 zc[5];                     // cached rgb_encoder(0) features
+    Map1 fd, fv, dcl, d12, d14;      // filtered depth / validity, clamped depth, pyramid
+    // heads
+    long long R = 0;
+    bf16 *h_a0z = nullptr, *h_a0r = nullptr, *h_an = nullptr, *h_pz = nullptr, *h_q0 = nullptr, *emb = nullptr, *ref = nullptr;
+    bf16 *g_ref = nullptr, *g_a3 = nullptr, *g_a0 = nullptr;
+    BnState bnProjZ, bnProjR, bnPred;
+    float* rowstat = nullptr;
+    // backward scratch
+    Map32 T1a, T1b, T2a, T2b, D2, G4a, G4b, D4, GC2, D8, E8, M128a, M128b;
+    Map1 g_out, g_p11, g_q, g_p12, g_o14;
+    float *k0 = nullptr, *k1 = nullptr, *k2 = nullptr;
+    double* partial = nullptr; size_t partial_doubles = 0;
+    float* wgrad_ws = nullptr;
+    LossScalars* losses = nullptr;
+    double *loss_map_partial = nullptr, *loss_cos_partial = nullptr;
+    int loss_map_blocks = 0, loss_cos_blocks = 0;
+    AdamHyper* adam_hyper = nullptr;
+    AdamChunk* adam_chunks = nullptr; int n_adam_chunks = 0;
+    float* zero_bias = nullptr;
+    // loss inputs remembered for backward
+    const float *l_img = nullptr, *l_d = nullptr, *l_v = nullptr; float l_cap = 0, l_wsd = 0, l_wsm = 0;
+    // graph
+    cudaGraphExec_t graph_exec = nullptr;
+    const void* graph_key[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    // ---------------------------------------------------------------------------------------------
+    Map32 alloc32(const char* name, int h, int w, int c = 32) {
+        Map32 m; m.n = N; m.h = h; m.w = w; m.c = c;
+        m.p = (bf16*)arena.take(m.numel() * sizeof(bf16));
+        if (name) reg(name, m.p, 1, N, h, w, c);
+        return m;
+    }
+    Map1 alloc1(const char* name, int h, int w) {
+        Map1 m; m.n = N; m.h = h; m.w = w;
+        m.p = (float*)arena.take(m.numel() * sizeof(float));
+        if (name) reg(name, m.p, 0, N, h, w, 1);
+        return m;
+    }
+    template <typename T> T* allocv(size_t count) { return (T*)arena.take(count * sizeof(T)); }
+    void reg(const std::string& name, void* p, int dtype, long long a, long long b, long long c, long long d) {
+        if (!named.count(name)) named_order.push_back(name);
+        TensorInfo t; t.p = p; t.dtype = dtype; t.d[0] = a; t.d[1] = b; t.d[2] = c; t.d[3] = d;
+        named[name] = t;
+    }
+    BnState alloc_bn(int c) {
+        BnState s; s.mean = allocv<float>(c); s.invstd = allocv<float>(c); s.scale = allocv<float>(c); s.shift = allocv<float>(c);
+        return s;
+    }
+    void need(const std::string& k) { keys.push_back(k); }
+
+    void def_conv(ConvLayer& L, const std::string& name, int cin, int cout, bool transposed, bool bias) {
+        L.name = name; L.cin = cin; L.cout = cout; L.transposed = transposed; L.has_bias = bias;
+        need(name + ".weight");
+        if (bias) need(name + ".bias");
+    }
+    void def_enc(EncW& E, const std::string& prefix, int cin, int nenc) {
+        E.nenc = nenc;
+        E.init0.name = prefix + ".init.0"; E.init0.cin = cin;
+        need(E.init0.name + ".weight"); need(E.init0.name + ".bias");
+        def_conv(E.init2, prefix + ".init.2", 32, 32, false, true);
+        ConvLayer* ls[8] = {&E.e1a, &E.e1b, &E.e2a, &E.e2b, &E.e3a, &E.e3b, &E.e4a, &E.e4b};
+        for (int k = 0; k < nenc; ++k) {
+            def_conv(*ls[2 * k], prefix + ".enc" + std::to_string(k + 1) + ".1", 32, 32, false, true);
+            ls[2 * k]->mode_fwd = MODE_S2; ls[2 * k]->mode_dgrad = MODE_T2;
+            def_conv(*ls[2 * k + 1], prefix + ".enc" + std::to_string(k + 1) + ".3", 32, 32, false, true);
+        }
+    }
+    void def_dec(DecW& D, const std::string& prefix) {
+        def_conv(D.d2a, prefix + ".dec2.1", 32, 32, true, true); D.d2a.mode_fwd = MODE_T2; D.d2a.mode_dgrad = MODE_S2;
+        def_conv(D.d2b, prefix + ".dec2.3", 32, 32, false, true);
+        def_conv(D.d1a, prefix + ".dec1.1", 32, 32, true, true); D.d1a.mode_fwd = MODE_T2; D.d1a.mode_dgrad = MODE_S2;
+        def_conv(D.d1b, prefix + ".dec1.3", 32, 32, false, true);
+        def_conv(D.p1, prefix + ".prdct.1", 32, 32, false, true);
+        D.p3.name = prefix + ".prdct.3";
+        need(D.p3.name + ".weight"); need(D.p3.name + ".bias");
+    }
+    void def_bn(BnLayer& B, const std::string& name, int c) {
+        B.name = name; B.c = c;
+        need(name + ".weight"); need(name + ".bias"); need(name + ".running_mean"); need(name + ".running_var");
+        need(name + ".num_batches_tracked");
+    }
+    void def_linear(LinearLayer& L, const std::string& name, int in, int out) {
+        L.name = name; L.in = in; L.out = out;
+        need(name + ".weight"); need(name + ".bias");
+    }
+
+    int define_model() {
+        def_enc(rgbW, "rgb_encoder", 3, 4);
+        def_enc(enc1W, "depth_encoder1", 1, 2); def_dec(dec1W, "depth_decoder1");
+        def_enc(enc2W, "depth_encoder2", 2, 2); def_dec(dec2W, "depth_decoder2");
+        def_enc(enc3W, "depth_encoder3", 2, 2); def_dec(dec3W, "depth_decoder3");
+        if (two_layers) {
+            const std::string p = "conv1_rgb_meta.conv1_meta";
+            def_conv(meta1, p + ".0.0", 32, 128, false, false);
+            def_bn(metaBn1, p + ".0.1", 128);
+            def_conv(meta2, p + ".1", 128, 32, false, true);
+            def_bn(metaBn2, p + ".2", 32);
+            adapt_names = {p + ".0.0.weight", p + ".0.1.weight", p + ".0.1.bias", p + ".1.weight", p + ".1.bias",
+                           p + ".2.weight", p + ".2.bias"};
+        } else {
+            def_conv(meta1, "conv1_rgb_meta", 32, 32, false, true);
+            adapt_names = {"conv1_rgb_meta.weight", "conv1_rgb_meta.bias"};
+        }
+        if (has_heads) {
+            def_linear(proj0, "proj.0", 32, 512); def_bn(projBn, "proj.1", 512); def_linear(proj3, "proj.3", 512, 512);
+            def_linear(pred0, "pred.0", 512, 512); def_bn(predBn, "pred.1", 512); def_linear(pred3, "pred.3", 512, 512);
+        }
+        return 0;
+    }
+
+    // ---- arena plan (run twice: sizing pass with base == nullptr, then with the bound workspace) ----
+    void plan_conv(ConvLayer& L) {
+        L.pack_fwd = allocv<bf16>((size_t)9 * L.cin * L.cout);
+        L.pack_dgrad = allocv<bf16>((size_t)9 * L.cin * L.cout);
+    }
+    void plan_enc_w(EncW& E) {
+        E.init0.dgrad_ch1 = allocv<float>(288);
+        plan_conv(E.init2);
+        ConvLayer* ls[8] = {&E.e1a, &E.e1b, &E.e2a, &E.e2b, &E.e3a, &E.e3b, &E.e4a, &E.e4b};
+        for (int k = 0; k < 2 * E.nenc; ++k) plan_conv(*ls[k]);
+    }
+    void plan_dec_w(DecW& D) {
+        plan_conv(D.d2a); plan_conv(D.d2b); plan_conv(D.d1a); plan_conv(D.d1b); plan_conv(D.p1);
+        D.p3.w_fwd = allocv<float>(288); D.p3.w_dgrad = allocv<float>(288);
+    }
+    void plan_enc_act(EncAct& A, const std::string& tag, int h, int w) {
+        A.a0 = alloc32((tag + ".a0").c_str(), h, w); A.x0 = alloc32((tag + ".x0").c_str(), h, w);
+        A.t1 = alloc32((tag + ".t1").c_str(), h / 2, w / 2); A.x1 = alloc32((tag + ".x1").c_str(), h / 2, w / 2);
+        A.t2 = alloc32((tag + ".t2").c_str(), h / 4, w / 4); A.x2 = alloc32((tag + ".x2").c_str(), h / 4, w / 4);
+    }
+    void plan_dec_act(DecAct& A, const std::string& tag, int h, int w) {   // h,w = resolution of x0 / out
+        A.x2 = alloc32((tag + ".x2").c_str(), h / 4, w / 4); A.x1 = alloc32((tag + ".x1").c_str(), h / 2, w / 2);
+        A.x0 = alloc32((tag + ".x0").c_str(), h, w);
+        A.u2 = alloc32((tag + ".u2").c_str(), h / 2, w / 2); A.x3 = alloc32((tag + ".x3").c_str(), h / 2, w / 2);
+        A.s1 = alloc32((tag + ".s1").c_str(), h / 2, w / 2);
+        A.u1 = alloc32((tag + ".u1").c_str(), h, w); A.x4 = alloc32((tag + ".x4").c_str(), h, w);
+        A.s0 = alloc32((tag + ".s0").c_str(), h, w); A.h = alloc32((tag + ".h").c_str(), h, w);
+        A.out = alloc1((tag + ".out").c_str(), h, w);
+    }
+    void plan_branch(Branch& B, const std::string& tag, bool is_real) {
+        if (is_real) {
+            for (int k = 0; k < 5; ++k) B.c[k] = alloc32((tag + ".c" + std::to_string(k)).c_str(), H >> k, W >> k);
+            B.c2raw = alloc32((tag + ".c2raw").c_str(), H / 4, W / 4);
+        } else {
+            // zero-image branch: rgb features are the cached rgb_encoder(0) maps; only the meta output is its own
+            for (int k = 0; k < 5; ++k) B.c[k] = zc[k];
+            B.c2raw = zc[2];
+            B.c[2] = alloc32((tag + ".c2").c_str(), H / 4, W / 4);
+        }
+        if (two_layers) {
+            B.mh = alloc32((tag + ".mh").c_str(), H / 4, W / 4, 128);
+            B.mg = alloc32((tag + ".mg").c_str(), H / 4, W / 4);
+            B.bn1 = alloc_bn(128); B.bn2 = alloc_bn(32);
+        }
+        if (is_real) plan_enc_act(B.e1, tag + ".e1", H / 4, W / 4); else B.e1 = real.e1;   // identical input -> shared
+        plan_dec_act(B.d1, tag + ".d1", H / 4, W / 4);
+        B.p12 = alloc1((tag + ".p12").c_str(), H / 2, W / 2);
+        plan_enc_act(B.e2, tag + ".e2", H / 2, W / 2);
+        plan_dec_act(B.d2, tag + ".d2", H / 2, W / 2);
+        B.p11 = alloc1((tag + ".p11").c_str(), H, W);
+        plan_enc_act(B.e3, tag + ".e3", H, W);
+        if (is_real) {
+            plan_dec_act(B.d3, tag + ".d3", H, W);
+            B.output = alloc1((tag + ".output").c_str(), H, W);
+        }
+    }
+    void plan() {
+        arena.off = 0;
+        named.clear(); named_order.clear();
+        plan_enc_w(rgbW); plan_enc_w(enc1W); plan_enc_w(enc2W); plan_enc_w(enc3W);
+        plan_dec_w(dec1W); plan_dec_w(dec2W); plan_dec_w(dec3W);
+        plan_conv(meta1);
+        if (two_layers) plan_conv(meta2);
+        zero_bias = allocv<float>(512);
+        fd = alloc1("filtered_depth", H, W); fv = alloc1("filtered_validity", H, W);
+        dcl = alloc1("depth_clamped", H, W); d12 = alloc1("d12", H / 2, W / 2); d14 = alloc1("d14", H / 4, W / 4);
+        for (int k = 0; k < 5; ++k) rgbT[k] = alloc32(("rgbT" + std::to_string(k)).c_str(), H >> k, W >> k);
+        plan_branch(real, "real", true);
+        reg("output", real.output.p, 0, N, H, W, 1);
+        R = (long long)N * (H / 4) * (W / 4);
+        if (has_heads) {
+            for (int k = 0; k < 5; ++k) zc[k] = alloc32(("zc" + std::to_string(k)).c_str(), H >> k, W >> k);
+            plan_branch(zero, "zero", false);
+            auto lin = [&](LinearLayer& L) { L.pack = allocv<bf16>((size_t)L.in * L.out); L.pack_t = allocv<bf16>((size_t)L.in * L.out); };
+            lin(proj0); lin(proj3); lin(pred0); lin(pred3);
+            size_t rm = (size_t)R * 512;
+            h_a0z = allocv<bf16>(rm); h_a0r = allocv<bf16>(rm); h_an = allocv<bf16>(rm); h_pz = allocv<bf16>(rm); h_q0 = allocv<bf16>(rm);
+            emb = allocv<bf16>(rm); ref = allocv<bf16>(rm);
+            reg("emb", emb, 1, R, 512, 1, 1); reg("ref", ref, 1, R, 512, 1, 1);
+            reg("heads.a0_real", h_a0r, 1, R, 512, 1, 1);
+            g_ref = allocv<bf16>(rm); g_a3 = allocv<bf16>(rm); g_a0 = allocv<bf16>(rm);
+            reg("g_ref", g_ref, 1, R, 512, 1, 1);
+            bnProjZ = alloc_bn(512); bnProjR = alloc_bn(512); bnPred = alloc_bn(512);
+            rowstat = allocv<float>((size_t)R * 3);
+        }
+        // backward scratch
+        T1a = alloc32("T1a", H, W); T1b = alloc32("T1b", H, W);
+        T2a = alloc32("T2a", H / 2, W / 2); T2b = alloc32("T2b", H / 2, W / 2); D2 = alloc32("D2", H / 2, W / 2);
+        G4a = alloc32("G4a", H / 4, W / 4); G4b = alloc32("G4b", H / 4, W / 4); D4 = alloc32("D4", H / 4, W / 4);
+        GC2 = alloc32("g_c2", H / 4, W / 4);
+        D8 = alloc32("D8", H / 8, W / 8); E8 = alloc32("E8", H / 8, W / 8);
+        if (two_layers) { M128a = alloc32("M128a", H / 4, W / 4, 128); M128b = alloc32("M128b", H / 4, W / 4, 128); }
+        g_out = alloc1("g_output", H, W); g_p11 = alloc1("g_p11", H, W);
+        g_q = alloc1("g_q", H / 2, W / 2); g_p12 = alloc1("g_p12", H / 2, W / 2); g_o14 = alloc1("g_out14", H / 4, W / 4);
+        k0 = allocv<float>(512); k1 = allocv<float>(512); k2 = allocv<float>(512);
+        long long max_rows = std::max<long long>(R, 1);
+        partial_doubles = (size_t)cdiv(max_rows, STATS_ROWS_PER_BLOCK) * 2 * 512;
+        partial = allocv<double>(partial_doubles);
+        size_t wg = std::max(wgrad_partial_bytes(N, H / 4, W / 4, 32, 128), wgrad_partial_bytes(N, H / 4, W / 4, 128, 32));
+        wgrad_ws = (float*)arena.take(wg);
+        losses = (LossScalars*)arena.take(sizeof(LossScalars));
+        reg("losses", losses, 0, 5, 1, 1, 1);
+        loss_map_blocks = std::min(cdiv((long long)H * W, LOSS_BLOCK * 4), 256);
+        loss_cos_blocks = (int)std::min<long long>(std::max<long long>(cdiv(R, 8), 1), 1184);
+        loss_map_partial = allocv<double>((size_t)N * loss_map_blocks * 4);
+        loss_cos_partial = allocv<double>(loss_cos_blocks);
+        adam_hyper = (AdamHyper*)arena.take(sizeof(AdamHyper));
+        adam_chunks = (AdamChunk*)arena.take(sizeof(AdamChunk) * 256);
+        ws_bytes = arena.off + 256;
+    }
+
+    // ---- tensor lookup ------------------------------------------------------------------------------
+    template <typename T> int get(const std::string& key, T*& out, long long numel) {
+        auto it = ext.find(key);
+        PTTA_CHECK(it != ext.end(), "state-dict entry '%s' was not bound (ptta_msgchn_set_tensor)", key.c_str());
+        PTTA_CHECK(numel < 0 || it->second.second == numel, "state-dict entry '%s' has %lld elements, expected %lld", key.c_str(),
+                   it->second.second, numel);
+        out = (T*)it->second.first;
+        return 0;
+    }
+    int bind_conv(ConvLayer& L) {
+        float* w; PTTA_TRY(get(L.name + ".weight", w, (long long)9 * L.cin * L.cout)); L.w = w;
+        if (L.has_bias) { float* b; PTTA_TRY(get(L.name + ".bias", b, L.cout)); L.b = b; }
+        return 0;
+    }
+    int bind_enc(EncW& E) {
+        float* w; PTTA_TRY(get(E.init0.name + ".weight", w, 32LL * E.init0.cin * 9)); E.init0.w = w;
+        float* b; PTTA_TRY(get(E.init0.name + ".bias", b, 32)); E.init0.b = b;
+        PTTA_TRY(bind_conv(E.init2));
+        ConvLayer* ls[8] = {&E.e1a, &E.e1b, &E.e2a, &E.e2b, &E.e3a, &E.e3b, &E.e4a, &E.e4b};
+        for (int k = 0; k < 2 * E.nenc; ++k) PTTA_TRY(bind_conv(*ls[k]));
+        return 0;
+    }
+    int bind_dec(DecW& D) {
+        PTTA_TRY(bind_conv(D.d2a)); PTTA_TRY(bind_conv(D.d2b)); PTTA_TRY(bind_conv(D.d1a)); PTTA_TRY(bind_conv(D.d1b));
+        PTTA_TRY(bind_conv(D.p1));
+        float* w; PTTA_TRY(get(D.p3.name + ".weight", w, 288)); D.p3.w = w;
+        float* b; PTTA_TRY(get(D.p3.name + ".bias", b, 1)); D.p3.b = b;
+        return 0;
+    }
+    int bind_bn(BnLayer& B) {
+        PTTA_TRY(get(B.name + ".weight", B.gamma, B.c)); PTTA_TRY(get(B.name + ".bias", B.beta, B.c));
+        PTTA_TRY(get(B.name + ".running_mean", B.rm, B.c)); PTTA_TRY(get(B.name + ".running_var", B.rv, B.c));
+        PTTA_TRY(get(B.name + ".num_batches_tracked", B.nbt, 1));
+        return 0;
+    }
+    int bind_linear(LinearLayer& L) {
+        float* w; PTTA_TRY(get(L.name + ".weight", w, (long long)L.in * L.out)); L.w = w;
+        float* b; PTTA_TRY(get(L.name + ".bias", b, L.out)); L.b = b;
+        return 0;
+    }
+    int bind_all() {
+        PTTA_TRY(bind_enc(rgbW)); PTTA_TRY(bind_enc(enc1W)); PTTA_TRY(bind_enc(enc2W)); PTTA_TRY(bind_enc(enc3W));
+        PTTA_TRY(bind_dec(dec1W)); PTTA_TRY(bind_dec(dec2W)); PTTA_TRY(bind_dec(dec3W));
+        PTTA_TRY(bind_conv(meta1));
+        if (two_layers) { PTTA_TRY(bind_conv(meta2)); PTTA_TRY(bind_bn(metaBn1)); PTTA_TRY(bind_bn(metaBn2)); }
+        if (has_heads) {
+            PTTA_TRY(bind_linear(proj0)); PTTA_TRY(bind_linear(proj3)); PTTA_TRY(bind_linear(pred0)); PTTA_TRY(bind_linear(pred3));
+            PTTA_TRY(bind_bn(projBn)); PTTA_TRY(bind_bn(predBn));
+        }
+        return 0;
+    }
+
+    // ---- weight packing -------------------------------------------------------------------------------
+    int pack_conv(const ConvLayer& L) {
+        const int tot = 9 * L.cin * L.cout;
+        const int blocks = cdiv(tot, 256);
+        if (!L.transposed) {
+            // Conv2d weight [cout][cin][3][3]
+            pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(L.w, L.pack_fwd, L.cout, L.cin, L.cin * 9, 9, 0);
+            PTTA_TRY(check_launch("pack_fwd"));
+            // data gradient: output channel = cin, input channel = cout; stride-1 layers flip the taps,
+            // stride-2 layers run as a transposed conv with the taps as they are
+            pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(L.w, L.pack_dgrad, L.cin, L.cout, 9, L.cin * 9, L.mode_fwd == MODE_S1 ? 1 : 0);
+            PTTA_TRY(check_launch("pack_dgrad"));
+        } else {
+            // ConvTranspose2d weight [cin][cout][3][3]
+            pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(L.w, L.pack_fwd, L.cout, L.cin, 9, L.cout * 9, 0);
+            PTTA_TRY(check_launch("pack_fwd_t"));
+            pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(L.w, L.pack_dgrad, L.cin, L.cout, L.cout * 9, 9, 0);
+            PTTA_TRY(check_launch("pack_dgrad_t"));
+        }
+        return 0;
+    }
+    int pack_enc(EncW& E) {
+        if (E.init0.cin == 2) {
+            pack_head_weight_kernel<<<2, 256, 0, st>>>(E.init0.w + 9, E.init0.dgrad_ch1, 18, 1);
+            PTTA_TRY(check_launch("pack_stem_dgrad"));
+        }
+        PTTA_TRY(pack_conv(E.init2));
+        ConvLayer* ls[8] = {&E.e1a, &E.e1b, &E.e2a, &E.e2b, &E.e3a, &E.e3b, &E.e4a, &E.e4b};
+        for (int k = 0; k < 2 * E.nenc; ++k) PTTA_TRY(pack_conv(*ls[k]));
+        return 0;
+    }
+    int pack_dec(DecW& D) {
+        PTTA_TRY(pack_conv(D.d2a)); PTTA_TRY(pack_conv(D.d2b)); PTTA_TRY(pack_conv(D.d1a)); PTTA_TRY(pack_conv(D.d1b));
+        PTTA_TRY(pack_conv(D.p1));
+        pack_head_weight_kernel<<<2, 256, 0, st>>>(D.p3.w, D.p3.w_fwd, 9, 0);
+        PTTA_TRY(check_launch("pack_head"));
+        pack_flip9_kernel<<<2, 256, 0, st>>>(D.p3.w, D.p3.w_dgrad, 32);
+        PTTA_TRY(check_launch("pack_head_dgrad"));
+        PTTA_CUDA(cudaMemcpyAsync(&D.p3.bias_host, D.p3.b, sizeof(float), cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+    int pack_linear(LinearLayer& L) {
+        int tot = L.in * L.out;
+        pack_matrix_kernel<<<cdiv(tot, 256), 256, 0, st>>>(L.w, L.pack, L.out, L.in, L.in, 1);
+        PTTA_TRY(check_launch("pack_linear"));
+        pack_matrix_kernel<<<cdiv(tot, 256), 256, 0, st>>>(L.w, L.pack_t, L.in, L.out, 1, L.in);
+        PTTA_TRY(check_launch("pack_linear_t"));
+        return 0;
+    }
+    int pack_adapted() {
+        PTTA_TRY(pack_conv(meta1));
+        if (two_layers) PTTA_TRY(pack_conv(meta2));
+        return 0;
+    }
+    int pack_all() {
+        PTTA_TRY(bind_all());
+        PTTA_CUDA(cudaMemsetAsync(zero_bias, 0, 512 * sizeof(float), st));
+        PTTA_TRY(pack_enc(rgbW)); PTTA_TRY(pack_enc(enc1W)); PTTA_TRY(pack_enc(enc2W)); PTTA_TRY(pack_enc(enc3W));
+        PTTA_TRY(pack_dec(dec1W)); PTTA_TRY(pack_dec(dec2W)); PTTA_TRY(pack_dec(dec3W));
+        PTTA_TRY(pack_adapted());
+        if (has_heads) {
+            PTTA_TRY(pack_linear(proj0)); PTTA_TRY(pack_linear(proj3)); PTTA_TRY(pack_linear(pred0)); PTTA_TRY(pack_linear(pred3));
+        }
+        PTTA_CUDA(cudaStreamSynchronize(st));   // bias_host copies
+        // Adam chunk table over the adapted tensors
+        std::vector<AdamChunk> chunks;
+        for (const std::string& k : adapt_names) {
+            auto it = ext.find(k);
+            PTTA_CHECK(it != ext.end(), "adapted tensor '%s' not bound", k.c_str());
+            long long n = it->second.second;
+            float *p = (float*)it->second.first, *g = nullptr, *m = nullptr, *v = nullptr;
+            if (ext.count("grad/" + k)) g = (float*)ext["grad/" + k].first;
+            if (ext.count("adam_m/" + k)) m = (float*)ext["adam_m/" + k].first;
+            if (ext.count("adam_v/" + k)) v = (float*)ext["adam_v/" + k].first;
+            if (!g || !m || !v) { chunks.clear(); break; }
+            for (long long o = 0; o < n; o += ADAM_CHUNK) {
+                AdamChunk c; c.p = p + o; c.g = g + o; c.m = m + o; c.v = v + o; c.n = (int)std::min<long long>(ADAM_CHUNK, n - o);
+                chunks.push_back(c);
+            }
+        }
+        PTTA_CHECK(chunks.size() <= 256, "too many Adam chunks (%zu)", chunks.size());
+        n_adam_chunks = (int)chunks.size();
+        if (n_adam_chunks) PTTA_CUDA(cudaMemcpyAsync(adam_chunks, chunks.data(), sizeof(AdamChunk) * chunks.size(), cudaMemcpyHostToDevice, st));
+        if (has_heads) {
+            // rgb_encoder(0): constant while the encoder is frozen ('meta' adapt mode never touches it)
+            PTTA_TRY(run_rgb_encoder(nullptr, nullptr, nullptr, zc));
+        }
+        PTTA_CUDA(cudaStreamSynchronize(st));
+        packed = true;
+        if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+        return 0;
+    }
+
+    // ---- layer helpers ----------------------------------------------------------------------------------
+    int conv_fwd(const ConvLayer& L, const Map32& in, const Map32& out, int pro, const BnState* probn = nullptr) {
+        ConvParams p; memset(&p, 0, sizeof(p));
+        p.in = in.p; p.out = out.p; p.w = L.pack_fwd; p.bias = L.has_bias ? L.b : nullptr;
+        p.N = in.n; p.Hin = in.h; p.Win = in.w; p.pro = pro; p.slope = 0.2f;
+        if (probn) { p.pro_scale = probn->scale; p.pro_shift = probn->shift; }
+        return launch_conv3x3(p, L.cin, L.cout, L.mode_fwd, st);
+    }
+    // gin = [add +] mask * dgrad(gout)
+    int conv_dgrad(const ConvLayer& L, const Map32& gout, const Map32& gin, const bf16* mask, const bf16* add,
+                   int mask_mode = MASK_RELU, const BnState* maskbn = nullptr) {
+        ConvParams p; memset(&p, 0, sizeof(p));
+        p.in = gout.p; p.out = gin.p; p.w = L.pack_dgrad; p.bias = nullptr;
+        p.N = gout.n; p.Hin = gout.h; p.Win = gout.w; p.pro = PRO_NONE; p.slope = 0.2f;
+        p.mask = mask; p.mask_mode = mask ? mask_mode : MASK_NONE; p.add = add;
+        if (maskbn) { p.mask_scale = maskbn->scale; p.mask_shift = maskbn->shift; }
+        return launch_conv3x3(p, L.cout, L.cin, L.mode_dgrad, st);
+    }
+    int add32(const Map32& a, const Map32& b, const Map32& out) {
+        long long n8 = (long long)a.numel() / 8;
+        ew_add_kernel<<<cdiv(n8, 256), 256, 0, st>>>(a.p, b.p, out.p, n8);
+        return check_launch("ew_add");
+    }
+    int add_up2(const Map32& x, const Map32& half) {   // x += up2(half)
+        long long tot = (long long)x.n * x.h * x.w * 4;
+        add_up2_c32_kernel<<<cdiv(tot, 256), 256, 0, st>>>(x.p, half.p, x.p, x.n, half.h, half.w);
+        return check_launch("add_up2_c32");
+    }
+    int up2_adj32(const Map32& ghi, const Map32& glo, int accumulate) {
+        long long tot = (long long)glo.n * glo.h * glo.w * 4;
+        up2_c32_adj_kernel<<<cdiv(tot, 256), 256, 0, st>>>(ghi.p, glo.p, glo.n, glo.h, glo.w, accumulate);
+        return check_launch("up2_c32_adj");
+    }
+    int up2_1(const Map1& a, const float* b, const float* c, const Map1& out) {
+        long long tot = (long long)out.numel();
+        up2_1ch_kernel<<<cdiv(tot, 256), 256, 0, st>>>(a.p, b, c, out.p, a.n, a.h, a.w);
+        return check_launch("up2_1ch");
+    }
+    int up2_adj1(const Map1& ghi, const Map1& glo) {
+        long long tot = (long long)glo.numel();
+        up2_1ch_adj_kernel<<<cdiv(tot, 256), 256, 0, st>>>(ghi.p, glo.p, glo.n, glo.h, glo.w, 0);
+        return check_launch("up2_1ch_adj");
+    }
+    int stem(const StemLayer& S, const float* p0, long long s0, float sc0, float sh0, const float* p1, long long s1, float sc1,
+             float sh1, const float* p2, long long s2, float sc2, float sh2, const Map32& out) {
+        StemParams p; memset(&p, 0, sizeof(p));
+        p.plane[0] = p0; p.plane[1] = p1; p.plane[2] = p2;
+        p.batch_stride[0] = s0; p.batch_stride[1] = s1; p.batch_stride[2] = s2;
+        p.scale[0] = sc0; p.scale[1] = sc1; p.scale[2] = sc2; p.shift[0] = sh0; p.shift[1] = sh1; p.shift[2] = sh2;
+        p.w = S.w; p.bias = S.b; p.mask = nullptr; p.out = out.p; p.N = out.n; p.H = out.h; p.W = out.w;
+        long long tot = (long long)out.n * out.h * out.w;
+        if (S.cin == 1) stem_conv_kernel<1><<<cdiv(tot, 128), 128, 0, st>>>(p);
+        else if (S.cin == 2) stem_conv_kernel<2><<<cdiv(tot, 128), 128, 0, st>>>(p);
+        else stem_conv_kernel<3><<<cdiv(tot, 128), 128, 0, st>>>(p);
+        return check_launch("stem_conv");
+    }
+    // prediction layer: out = conv32->1(relu(h)) + bias [+ add]
+    int head_fwd(const HeadLayer& Hd, const Map32& h, const float* add, const Map1& out) {
+        long long tot = (long long)out.numel();
+        head_conv_kernel<<<cdiv(tot, 128), 128, 0, st>>>(h.p, Hd.w_fwd, Hd.bias_host, add, out.p, out.n, out.h, out.w, 1, 0);
+        return check_launch("head_conv");
+    }
+    // g_h = dgrad_{1->32}(g_out) * [h > 0]
+    int head_dgrad(const HeadLayer& Hd, const Map1& gout, const Map32& hmask, const Map32& gh) {
+        StemParams p; memset(&p, 0, sizeof(p));
+        p.plane[0] = gout.p; p.batch_stride[0] = (long long)gout.h * gout.w; p.scale[0] = 1.f;
+        p.w = Hd.w_dgrad; p.bias = nullptr; p.mask = hmask.p; p.out = gh.p; p.N = gh.n; p.H = gh.h; p.W = gh.w;
+        long long tot = (long long)gh.n * gh.h * gh.w;
+        stem_conv_kernel<1><<<cdiv(tot, 128), 128, 0, st>>>(p);
+        return check_launch("head_dgrad");
+    }
+    // gradient wrt input plane 1 of a 2-plane stem: out = conv32->1(g_a0; flipped plane-1 weights) + add
+    int stem_dgrad_ch1(const StemLayer& S, const Map32& ga0, const float* add, const Map1& out) {
+        long long tot = (long long)out.numel();
+        head_conv_kernel<<<cdiv(tot, 128), 128, 0, st>>>(ga0.p, S.dgrad_ch1, 0.f, add, out.p, out.n, out.h, out.w, 0, 0);
+        return check_launch("stem_dgrad");
+    }
+    int stats(const bf16* x, const bf16* dy, long long rows, int C, int mode, const BnState* s, int relu_mask, int& nblk) {
+        nblk = cdiv(rows, STATS_ROWS_PER_BLOCK);
+        PTTA_CHECK((size_t)nblk * 2 * C <= partial_doubles, "stats partial buffer too small");
+        col_stats_kernel<<<nblk, 256, 2 * 2048 * sizeof(double), st>>>(x, dy, partial, rows, C, mode, s ? s->mean : nullptr,
+                                                                      s ? s->invstd : nullptr, s ? s->scale : nullptr,
+                                                                      s ? s->shift : nullptr, relu_mask);
+        return check_launch("col_stats");
+    }
+    int bn_forward_stats(const BnLayer& L, const BnState& s, const bf16* x, long long rows, bool training) {
+        int nblk = 0;
+        if (training) PTTA_TRY(stats(x, nullptr, rows, L.c, 0, nullptr, 0, nblk));
+        BnParams p; p.gamma = L.gamma; p.beta = L.beta; p.running_mean = L.rm; p.running_var = L.rv; p.num_batches_tracked = L.nbt;
+        p.mean = s.mean; p.invstd = s.invstd; p.scale = s.scale; p.shift = s.shift; p.momentum = 0.1f; p.eps = 1e-5f;
+        bn_finalize_kernel<<<cdiv(L.c, 128), 128, 0, st>>>(partial, nblk, rows, L.c, p, training ? 1 : 0);
+        return check_launch("bn_finalize");
+    }
+    int bn_apply(const bf16* x, const bf16* res, bf16* y, long long rows, int C, const BnState& s, int act) {
+        long long tot = rows * (C / 8);
+        bn_apply_kernel<<<cdiv(tot, 256), 256, 0, st>>>(x, res, y, rows, C, s.scale, s.shift, act);
+        return check_launch("bn_apply");
+    }
+    // dx = BN-backward(dy [* relu mask]); optionally writes dgamma / dbeta
+    int bn_backward(const BnLayer& L, const BnState& s, const bf16* dy, const bf16* x, bf16* dx, long long rows, int relu_mask,
+                    float* dgamma, float* dbeta) {
+        int nblk = 0;
+        PTTA_TRY(stats(x, dy, rows, L.c, 1, &s, relu_mask, nblk));
+        bn_bwd_finalize_kernel<<<cdiv(L.c, 128), 128, 0, st>>>(partial, nblk, rows, L.c, L.gamma, s.invstd, dgamma, dbeta, k0, k1, k2);
+        PTTA_TRY(check_launch("bn_bwd_finalize"));
+        long long tot = rows * (L.c / 8);
+        bn_bwd_apply_kernel<<<cdiv(tot, 256), 256, 0, st>>>(dy, x, dx, rows, L.c, s.mean, s.invstd, k0, k1, k2, s.scale, s.shift, relu_mask);
+        return check_launch("bn_bwd_apply");
+    }
+    int gemm(const bf16* A, const bf16* B, bf16* C, const float* bias, long long M, int Nn, int K) {
+        GemmParams p; p.A = A; p.B = B; p.C = C; p.bias = bias; p.M = M; p.N = Nn; p.K = K;
+        return launch_gemm(p, st);
+    }
+
+    // ---- network pieces -------------------------------------------------------------------------------
+    // image == nullptr -> zero image (constant planes: scale 0, shift 0)
+    int run_rgb_encoder(const float* image, const float* isc, const float* ish, Map32* c) {
+        const long long hw = (long long)H * W;
+        const float* base = image ? image : fd.p;   // any valid pointer; scale 0 makes the value irrelevant
+        float s[3], b[3];
+        for (int k = 0; k < 3; ++k) { s[k] = image ? isc[k] : 0.f; b[k] = image ? ish[k] : 0.f; }
+        if (image)
+            PTTA_TRY(stem(rgbW.init0, base, 3 * hw, s[0], b[0], base + hw, 3 * hw, s[1], b[1], base + 2 * hw, 3 * hw, s[2], b[2], rgbT[0]));
+        else
+            PTTA_TRY(stem(rgbW.init0, base, hw, 0.f, 0.f, base, hw, 0.f, 0.f, base, hw, 0.f, 0.f, rgbT[0]));
+        PTTA_TRY(conv_fwd(rgbW.init2, rgbT[0], c[0], PRO_RELU));
+        const ConvLayer* ls[8] = {&rgbW.e1a, &rgbW.e1b, &rgbW.e2a, &rgbW.e2b, &rgbW.e3a, &rgbW.e3b, &rgbW.e4a, &rgbW.e4b};
+        for (int k = 1; k <= 4; ++k) {
+            PTTA_TRY(conv_fwd(*ls[2 * (k - 1)], c[k - 1], rgbT[k], PRO_RELU));
+            PTTA_TRY(conv_fwd(*ls[2 * (k - 1) + 1], rgbT[k], c[k], PRO_RELU));
+        }
+        return 0;
+    }
+    // c2 = meta(c2raw)
+    int run_meta(Branch& B, bool training) {
+        if (!two_layers) return conv_fwd(meta1, B.c2raw, B.c[2], PRO_NONE);
+        const long long rows = (long long)N * (H / 4) * (W / 4);
+        PTTA_TRY(conv_fwd(meta1, B.c2raw, B.mh, PRO_NONE));
+        PTTA_TRY(bn_forward_stats(metaBn1, B.bn1, B.mh.p, rows, training));
+        PTTA_TRY(conv_fwd(meta2, B.mh, B.mg, PRO_BN_LEAKY, &B.bn1));
+        PTTA_TRY(bn_forward_stats(metaBn2, B.bn2, B.mg.p, rows, training));
+        return bn_apply(B.mg.p, B.c2raw.p, B.c[2].p, rows, 32, B.bn2, 0);
+    }
+    int run_encoder(const EncW& Wt, EncAct& A, const float* p0, const float* p1, const Map32* pre_x4, const Map32* pre_x3,
+                    const Map32* pre_x2) {
+        const long long hw = (long long)A.a0.h * A.a0.w;
+        PTTA_TRY(stem(Wt.init0, p0, hw, 1.f, 0.f, p1 ? p1 : p0, hw, 1.f, 0.f, p0, hw, 0.f, 0.f, A.a0));
+        PTTA_TRY(conv_fwd(Wt.init2, A.a0, A.x0, PRO_RELU));
+        if (pre_x4) PTTA_TRY(add_up2(A.x0, *pre_x4));
+        PTTA_TRY(conv_fwd(Wt.e1a, A.x0, A.t1, PRO_RELU));
+        PTTA_TRY(conv_fwd(Wt.e1b, A.t1, A.x1, PRO_RELU));
+        if (pre_x3) PTTA_TRY(add_up2(A.x1, *pre_x3));
+        PTTA_TRY(conv_fwd(Wt.e2a, A.x1, A.t2, PRO_RELU));
+        PTTA_TRY(conv_fwd(Wt.e2b, A.t2, A.x2, PRO_RELU));
+        if (pre_x2) PTTA_TRY(add_up2(A.x2, *pre_x2));
+        return 0;
+    }
+    // cx0/cx1/cx2: rgb features at the resolutions of x0/x1/x2; out = prediction [+ add]
+    int run_decoder(const DecW& Wt, DecAct& A, const EncAct& E, const Map32& cx0, const Map32& cx1, const Map32& cx2,
+                    const float* add, const Map1& out) {
+        PTTA_TRY(add32(E.x2, cx2, A.x2));
+        PTTA_TRY(add32(E.x1, cx1, A.x1));
+        PTTA_TRY(add32(E.x0, cx0, A.x0));
+        PTTA_TRY(conv_fwd(Wt.d2a, A.x2, A.u2, PRO_RELU));
+        PTTA_TRY(conv_fwd(Wt.d2b, A.u2, A.x3, PRO_RELU));
+        PTTA_TRY(add32(A.x1, A.x3, A.s1));
+        PTTA_TRY(conv_fwd(Wt.d1a, A.s1, A.u1, PRO_RELU));
+        PTTA_TRY(conv_fwd(Wt.d1b, A.u1, A.x4, PRO_RELU));
+        PTTA_TRY(add32(A.x4, A.x0, A.s0));
+        PTTA_TRY(conv_fwd(Wt.p1, A.s0, A.h, PRO_RELU));
+        return head_fwd(Wt.p3, A.h, add, out);
+    }
+    int run_cascade(Branch& B, bool is_real) {
+        if (is_real) PTTA_TRY(run_encoder(enc1W, B.e1, d14.p, nullptr, nullptr, nullptr, nullptr));
+        PTTA_TRY(run_decoder(dec1W, B.d1, B.e1, B.c[2], B.c[3], B.c[4], nullptr, B.d1.out));
+        PTTA_TRY(up2_1(B.d1.out, nullptr, nullptr, B.p12));                        // p12 = up2(out14)
+        PTTA_TRY(run_encoder(enc2W, B.e2, d12.p, B.p12.p, &B.d1.x4, &B.d1.x3, &B.d1.x2));
+        PTTA_TRY(run_decoder(dec2W, B.d2, B.e2, B.c[1], B.c[2], B.c[3], nullptr, B.d2.out));
+        PTTA_TRY(up2_1(B.d2.out, B.p12.p, nullptr, B.p11));                        // p11 = up2(out12 + p12)
+        PTTA_TRY(run_encoder(enc3W, B.e3, dcl.p, B.p11.p, &B.d2.x4, &B.d2.x3, &B.d2.x2));
+        if (!is_real) return 0;                                                    // zero branch stops after encoder 3
+        return run_decoder(dec3W, B.d3, B.e3, B.c[0], B.c[1], B.c[2], B.p11.p, B.output);   // output = out11 + p11
+    }
+    int mlp(const LinearLayer& L0, const BnLayer& bn, const BnState& s, const LinearLayer& L3, const bf16* x, int in_dim, bf16* a0, bf16* out,
+            bool training) {
+        PTTA_TRY(gemm(x, L0.pack, a0, L0.b, R, L0.out, in_dim));
+        PTTA_TRY(bn_forward_stats(bn, s, a0, R, training));
+        PTTA_TRY(bn_apply(a0, nullptr, h_an, R, L0.out, s, 1));
+        return gemm(h_an, L3.pack, out, L3.b, R, L3.out, L3.in);
+    }
+
+    int forward(const float* image, const float* isc, const float* ish, const float* sparse, float cap, bool training) {
+        PTTA_CHECK(bound && packed, "engine not ready: bind a workspace and pack weights first");
+        PTTA_CHECK(!training || has_heads, "training forward needs the proxy heads ('selfsup' prepare mode)");
+        {
+            long long tot = (long long)N * (H / 4) * (W / 4);
+            pyramid_kernel<<<cdiv(tot, 128), 128, 0, st>>>(sparse, dcl.p, d12.p, d14.p, N, H, W, cap, cap > 0.f ? 1 : 0);
+            PTTA_TRY(check_launch("pyramid"));
+        }
+        Map32 rc[5] = {real.c[0], real.c[1], real.c2raw, real.c[3], real.c[4]};
+        PTTA_TRY(run_rgb_encoder(image, isc, ish, rc));
+        PTTA_TRY(run_meta(real, training));
+        PTTA_TRY(run_cascade(real, true));
+        if (!training) return 0;
+        // zero-image branch (no_grad in the reference, network_exp_msg_chn_adapt.py:508-532); BN running statistics
+        // are updated a second time here, exactly as the reference does
+        PTTA_TRY(run_meta(zero, true));
+        PTTA_TRY(run_cascade(zero, false));
+        // heads (:551-554): emb = pred(proj(z_zero)), ref = proj(z_real); rows = pixels of the /4 map (NHWC)
+        PTTA_TRY(mlp(proj0, projBn, bnProjZ, proj3, zero.e3.x2.p, 32, h_a0z, h_pz, true));
+        PTTA_TRY(mlp(pred0, predBn, bnPred, pred3, h_pz, 512, h_q0, emb, true));
+        PTTA_TRY(mlp(proj0, projBn, bnProjR, proj3, real.e3.x2.p, 32, h_a0r, ref, true));
+        return 0;
+    }
+
+    // ---- losses (src/external_model_adapt.py:371-441) ----------------------------------------------------
+    int loss(const float* image_raw, const float* sparse, const float* validity, float cap, float w_sd, float w_sm, float w_cos) {
+        PTTA_CHECK(N <= 64, "loss: batch size %d > 64 not supported", N);
+        l_img = image_raw; l_d = sparse; l_v = validity; l_cap = cap; l_wsd = w_sd; l_wsm = w_sm;
+        dim3 grid(loss_map_blocks, N);
+        loss_map_reduce_kernel<<<grid, LOSS_BLOCK, 0, st>>>(real.output.p, sparse, validity, image_raw, loss_map_partial, H, W, cap,
+                                                           cap > 0.f ? 1 : 0);
+        PTTA_TRY(check_launch("loss_map_reduce"));
+        loss_cos_rows_kernel<<<loss_cos_blocks, 256, 0, st>>>(emb, ref, rowstat, loss_cos_partial, R, 512);
+        PTTA_TRY(check_launch("loss_cos_rows"));
+        loss_finalize_kernel<<<1, 32, 0, st>>>(loss_map_partial, loss_map_blocks, loss_cos_partial, loss_cos_blocks, N, H, W, R, w_sd, w_sm,
+                                              w_cos, 0.3f, losses);
+        return check_launch("loss_finalize");
+    }
+
+    // ---- backward -----------------------------------------------------------------------------------------
+    float* grad_of(const std::string& key) {
+        auto it = ext.find("grad/" + key);
+        return it == ext.end() ? nullptr : (float*)it->second.first;
+    }
+    // prediction layers of a decoder: gs0 = [add +] dgrad(prdct.1)(dgrad(prdct.3)(gout) * [h>0]) * [s0>0]
+    int dec_pred_backward(const DecW& Wt, const DecAct& A, const Map1& gout, const Map32& tmp, const Map32& gs0, const bf16* add) {
+        PTTA_TRY(head_dgrad(Wt.p3, gout, A.h, tmp));
+        return conv_dgrad(Wt.p1, tmp, gs0, A.s0.p, add);
+    }
+    // d loss / d output (g_out) and d loss / d ref (g_ref)
+    int loss_backward(float gscale) {
+        PTTA_CHECK(l_img != nullptr, "backward called before loss");
+        const Branch& B = real;
+        {
+            long long tot = (long long)N * H * W;
+            loss_map_grad_kernel<<<cdiv(tot, 256), 256, 0, st>>>(B.output.p, l_d, l_v, l_img, g_out.p, losses, N, H, W, l_cap,
+                                                               l_cap > 0.f ? 1 : 0, l_wsd, l_wsm, gscale);
+            PTTA_TRY(check_launch("loss_map_grad"));
+            loss_cos_grad_kernel<<<loss_cos_blocks, 256, 0, st>>>(emb, ref, rowstat, losses, g_ref, R, 512, gscale);
+            PTTA_TRY(check_launch("loss_cos_grad"));
+        }
+        return 0;
+    }
+    // from (g_out, g_ref) to the gradients of the adapted tensors
+    int network_backward() {
+        for (const std::string& k : adapt_names) PTTA_CHECK(grad_of(k) != nullptr, "gradient buffer 'grad/%s' not bound", k.c_str());
+        const Branch& B = real;
+        // proxy head on the real rows: ref = L3(relu(bn(L0(z))))
+        PTTA_TRY(gemm(g_ref, proj3.pack_t, g_a3, nullptr, R, 512, 512));
+        PTTA_TRY(bn_backward(projBn, bnProjR, g_a3, h_a0r, g_a0, R, 1, nullptr, nullptr));
+        PTTA_TRY(gemm(g_a0, proj0.pack_t, G4a.p, nullptr, R, 32, 512));     // g_z -> G4a  (grad wrt e3.x2 from the heads)
+
+        // ---- decoder 3 ----
+        PTTA_TRY(dec_pred_backward(dec3W, B.d3, g_out, T1a, T1b, nullptr));                 // T1b = g_s0 (= g_x4 = g_e3x0)
+        PTTA_TRY(conv_dgrad(dec3W.d1b, T1b, T1a, B.d3.u1.p, nullptr));                      // T1a = g_u1
+        PTTA_TRY(conv_dgrad(dec3W.d1a, T1a, T2a, B.d3.s1.p, nullptr));                      // T2a = g_s1 (= g_e3x1 = g_x3)
+        PTTA_TRY(conv_dgrad(dec3W.d2b, T2a, T2b, B.d3.u2.p, nullptr));                      // T2b = g_u2
+        PTTA_TRY(conv_dgrad(dec3W.d2a, T2b, GC2, B.d3.x2.p, nullptr));                      // GC2 = grad of d3.x2 (meta contribution #1)
+        PTTA_TRY(add32(GC2, G4a, G4b));                                                     // G4b = g_e3x2 = GC2 + g_z
+        // ---- encoder 3 ----
+        PTTA_TRY(up2_adj32(G4b, D8, 0));                                                    // D8 = grad of d2.x2 (skip)
+        PTTA_TRY(conv_dgrad(enc3W.e2b, G4b, G4a, B.e3.t2.p, nullptr));                      // G4a = g_t2
+        PTTA_TRY(conv_dgrad(enc3W.e2a, G4a, T2b, B.e3.x1.p, T2a.p));                        // T2b = g_x1 total
+        PTTA_TRY(up2_adj32(T2b, D4, 0));                                                    // D4 = grad of d2.x3 (skip)
+        PTTA_TRY(conv_dgrad(enc3W.e1b, T2b, T2a, B.e3.t1.p, nullptr));                      // T2a = g_t1
+        PTTA_TRY(conv_dgrad(enc3W.e1a, T2a, T1a, B.e3.x0.p, T1b.p));                        // T1a = g_x0 total
+        PTTA_TRY(up2_adj32(T1a, D2, 0));                                                    // D2 = grad of d2.x4 (skip)
+        PTTA_TRY(conv_dgrad(enc3W.init2, T1a, T1b, B.e3.a0.p, nullptr));                    // T1b = g_a0
+        PTTA_TRY(stem_dgrad_ch1(enc3W.init0, T1b, g_out.p, g_p11));                         // g_p11 = g_output + stem grad
+        PTTA_TRY(up2_adj1(g_p11, g_q));                                                     // g_q = g_out12 = g_p12 (part)
+        // ---- decoder 2 ----
+        PTTA_TRY(dec_pred_backward(dec2W, B.d2, g_q, T2a, T2b, nullptr));                   // T2b = g_s0 (= g_e2x0)
+        PTTA_TRY(add32(D2, T2b, T2a));                                                      // T2a = g_x4 total
+        PTTA_TRY(conv_dgrad(dec2W.d1b, T2a, D2, B.d2.u1.p, nullptr));                       // D2 = g_u1
+        PTTA_TRY(conv_dgrad(dec2W.d1a, D2, G4a, B.d2.s1.p, nullptr));                       // G4a = g_s1 (= g_e2x1; meta contribution #2)
+        PTTA_TRY(add32(GC2, G4a, GC2));
+        PTTA_TRY(add32(D4, G4a, D4));                                                       // D4 = g_x3 total
+        PTTA_TRY(conv_dgrad(dec2W.d2b, D4, G4b, B.d2.u2.p, nullptr));                       // G4b = g_u2
+        PTTA_TRY(conv_dgrad(dec2W.d2a, G4b, E8, B.d2.x2.p, D8.p));                          // E8 = g_e2x2
+        // ---- encoder 2 ----
+        PTTA_TRY(conv_dgrad(enc2W.e2b, E8, D8, B.e2.t2.p, nullptr));                        // D8 = g_t2
+        PTTA_TRY(conv_dgrad(enc2W.e2a, D8, G4b, B.e2.x1.p, G4a.p));                         // G4b = g_x1 total
+        PTTA_TRY(conv_dgrad(enc2W.e1b, G4b, D4, B.e2.t1.p, nullptr));                       // D4 = g_t1
+        PTTA_TRY(conv_dgrad(enc2W.e1a, D4, T2a, B.e2.x0.p, T2b.p));                         // T2a = g_x0 total
+        PTTA_TRY(conv_dgrad(enc2W.init2, T2a, D2, B.e2.a0.p, nullptr));                     // D2 = g_a0
+        PTTA_TRY(stem_dgrad_ch1(enc2W.init0, D2, g_q.p, g_p12));                            // g_p12 = g_q + stem grad
+        PTTA_TRY(up2_adj1(g_p12, g_o14));                                                   // g_out14
+        // ---- decoder 1 (prediction layers only) ----
+        PTTA_TRY(dec_pred_backward(dec1W, B.d1, g_o14, G4a, GC2, GC2.p));                   // GC2 += g_s0 (meta contribution #3)
+
+        // ---- meta layer ----
+        const long long rows = (long long)N * (H / 4) * (W / 4);
+        if (!two_layers) {
+            WgradParams wp; memset(&wp, 0, sizeof(wp));
+            wp.in = B.c2raw.p; wp.gout = GC2.p; wp.partial = wgrad_ws; wp.N = N; wp.H = H / 4; wp.W = W / 4; wp.pro = PRO_NONE;
+            PTTA_TRY(launch_wgrad(wp, grad_of("conv1_rgb_meta.weight"), 32, 32, st));
+            int nblk = 0;
+            PTTA_TRY(stats(GC2.p, nullptr, rows, 32, 0, nullptr, 0, nblk));
+            colsum_finalize_kernel<<<1, 32, 0, st>>>(partial, nblk, 32, grad_of("conv1_rgb_meta.bias"));
+            return check_launch("colsum_finalize");
+        }
+        const std::string p = "conv1_rgb_meta.conv1_meta";
+        // BN2: c2 = bn2(mg) + c2raw
+        PTTA_TRY(bn_backward(metaBn2, B.bn2, GC2.p, B.mg.p, G4a.p, rows, 0, grad_of(p + ".2.weight"), grad_of(p + ".2.bias")));   // G4a = g_mg
+        {
+            int nblk = 0;
+            PTTA_TRY(stats(G4a.p, nullptr, rows, 32, 0, nullptr, 0, nblk));
+            colsum_finalize_kernel<<<1, 32, 0, st>>>(partial, nblk, 32, grad_of(p + ".1.bias"));
+            PTTA_TRY(check_launch("colsum_finalize"));
+        }
+        {   // conv2 wgrad: input = leaky(bn1(mh))
+            WgradParams wp; memset(&wp, 0, sizeof(wp));
+            wp.in = B.mh.p; wp.gout = G4a.p; wp.partial = wgrad_ws; wp.N = N; wp.H = H / 4; wp.W = W / 4;
+            wp.pro = PRO_BN_LEAKY; wp.pro_scale = B.bn1.scale; wp.pro_shift = B.bn1.shift; wp.slope = 0.2f;
+            PTTA_TRY(launch_wgrad(wp, grad_of(p + ".1.weight"), 128, 32, st));
+        }
+        PTTA_TRY(conv_dgrad(meta2, G4a, M128a, B.mh.p, nullptr, MASK_BN_LEAKY, &B.bn1));    // M128a = grad wrt bn1 output
+        PTTA_TRY(bn_backward(metaBn1, B.bn1, M128a.p, B.mh.p, M128b.p, rows, 0, grad_of(p + ".0.1.weight"), grad_of(p + ".0.1.bias")));
+        {   // conv1 wgrad: input = c2raw
+            WgradParams wp; memset(&wp, 0, sizeof(wp));
+            wp.in = B.c2raw.p; wp.gout = M128b.p; wp.partial = wgrad_ws; wp.N = N; wp.H = H / 4; wp.W = W / 4; wp.pro = PRO_NONE;
+            PTTA_TRY(launch_wgrad(wp, grad_of(p + ".0.0.weight"), 32, 128, st));
+        }
+        return 0;
+    }
+
+    int backward(float gscale) {
+        PTTA_TRY(loss_backward(gscale));
+        return network_backward();
+    }
+
+    int adam_step() {
+        PTTA_CHECK(n_adam_chunks > 0, "Adam state not bound (grad/, adam_m/, adam_v/ entries for every adapted tensor)");
+        adam_kernel<<<n_adam_chunks, 256, 0, st>>>(adam_chunks, adam_hyper);
+        PTTA_TRY(check_launch("adam"));
+        adam_advance_kernel<<<1, 1, 0, st>>>(adam_hyper);
+        PTTA_TRY(check_launch("adam_advance"));
+        return pack_adapted();
+    }
+
+    int outlier(const float* sparse) {
+        dim3 grid(cdiv(W, OR_TX), cdiv(H, OR_TY), N), block(OR_TX, OR_TY);
+        size_t sm = (size_t)(OR_TX + 6) * (OR_TY + 6) * sizeof(float);
+        outlier_removal_kernel<<<grid, block, sm, st>>>(sparse, fd.p, fv.p, H, W, 7, 1.5f);
+        return check_launch("outlier_removal");
+    }
+
+    int tta_step(const float* image_raw, const float* isc, const float* ish, const float* sparse, float cap, float w_sd, float w_sm,
+                 float w_cos) {
+        PTTA_TRY(outlier(sparse));                                               // src/tta_main.py:583-590
+        PTTA_TRY(forward(image_raw, isc, ish, fd.p, cap, true));                 // :610-614
+        PTTA_TRY(loss(image_raw, fd.p, fv.p, cap, w_sd, w_sm, w_cos));           // :619-629
+        PTTA_TRY(backward(1.f));                                                 // :631-632
+        return adam_step();                                                      // :633
+    }
+};
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* ptta_last_error(void) { return g_error.c_str(); }
+int ptta_version(void) { return 100; }
+
+int ptta_outlier_removal(const float* d, float* d_out, float* v_out, int n, int h, int w, int ksize, float thr, ptta_stream_t stream) {
+    PTTA_CHECK(ksize >= 1 && ksize <= 15 && (ksize & 1), "outlier_removal: kernel_size %d must be odd and <= 15", ksize);
+    int pad = ksize / 2;
+    dim3 grid(cdiv(w, OR_TX), cdiv(h, OR_TY), n), block(OR_TX, OR_TY);
+    size_t sm = (size_t)(OR_TX + 2 * pad) * (OR_TY + 2 * pad) * sizeof(float);
+    outlier_removal_kernel<<<grid, block, sm, (cudaStream_t)stream>>>(d, d_out, v_out, h, w, ksize, thr);
+    return check_launch("outlier_removal");
+}
+
+int ptta_pyramid(const float* d, float* dc, float* d2, float* d4, int n, int h, int w, float cap, int do_clamp, ptta_stream_t stream) {
+    PTTA_CHECK(h % 4 == 0 && w % 4 == 0, "pyramid: %dx%d must be multiples of 4", h, w);
+    long long tot = (long long)n * (h / 4) * (w / 4);
+    pyramid_kernel<<<cdiv(tot, 128), 128, 0, (cudaStream_t)stream>>>(d, dc, d2, d4, n, h, w, cap, do_clamp);
+    return check_launch("pyramid");
+}
+
+int ptta_pack_conv_weight(const float* src, void* dst, int o, int i, int s_o, int s_i, int flip, ptta_stream_t stream) {
+    pack_conv_weight_kernel<<<cdiv(9 * o * i, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, o, i, s_o, s_i, flip);
+    return check_launch("pack_conv_weight");
+}
+
+int ptta_conv3x3(const void* in, void* out, const void* wpack, const float* bias, int n, int hin, int win, int cin, int cout, int mode,
+                 int prologue, const float* pro_scale, const float* pro_shift, float slope, const void* mask, int mask_mode,
+                 const float* mask_scale, const float* mask_shift, const void* add, ptta_stream_t stream) {
+    ConvParams p; memset(&p, 0, sizeof(p));
+    p.in = (const bf16*)in; p.out = (bf16*)out; p.w = (const bf16*)wpack; p.bias = bias;
+    p.N = n; p.Hin = hin; p.Win = win; p.pro = prologue; p.pro_scale = pro_scale; p.pro_shift = pro_shift; p.slope = slope;
+    p.mask = (const bf16*)mask; p.mask_mode = mask ? mask_mode : MASK_NONE; p.mask_scale = mask_scale; p.mask_shift = mask_shift;
+    p.add = (const bf16*)add;
+    PTTA_CHECK(prologue != PRO_BN_LEAKY || (pro_scale && pro_shift), "conv3x3: BN prologue needs scale and shift");
+    PTTA_CHECK(p.mask_mode != MASK_BN_LEAKY || (mask_scale && mask_shift), "conv3x3: BN mask needs scale and shift");
+    return launch_conv3x3(p, cin, cout, mode, (cudaStream_t)stream);
+}
+
+size_t ptta_conv3x3_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout) { return wgrad_partial_bytes(n, h, w, cin, cout); }
+
+int ptta_conv3x3_wgrad(const void* in, const void* gout, float* dw, void* workspace, int n, int h, int w, int cin, int cout, int prologue,
+                       const float* pro_scale, const float* pro_shift, float slope, ptta_stream_t stream) {
+    WgradParams p; memset(&p, 0, sizeof(p));
+    p.in = (const bf16*)in; p.gout = (const bf16*)gout; p.partial = (float*)workspace; p.N = n; p.H = h; p.W = w;
+    p.pro = prologue; p.pro_scale = pro_scale; p.pro_shift = pro_shift; p.slope = slope;
+    return launch_wgrad(p, dw, cin, cout, (cudaStream_t)stream);
+}
+
+int ptta_stem_conv(const float* const* planes, const long long* strides, const float* scale, const float* shift, int cin,
+                   const float* weight, const float* bias, const void* mask, void* out, int n, int h, int w, ptta_stream_t stream) {
+    PTTA_CHECK(cin >= 1 && cin <= 3, "stem_conv: cin=%d", cin);
+    StemParams p; memset(&p, 0, sizeof(p));
+    for (int k = 0; k < 3; ++k) {
+        int s = k < cin ? k : 0;
+        p.plane[k] = planes[s]; p.batch_stride[k] = strides[s]; p.scale[k] = scale[s]; p.shift[k] = shift[s];
+    }
+    p.w = weight; p.bias = bias; p.mask = (const bf16*)mask; p.out = (bf16*)out; p.N = n; p.H = h; p.W = w;
+    long long tot = (long long)n * h * w;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cin == 1) stem_conv_kernel<1><<<cdiv(tot, 128), 128, 0, st>>>(p);
+    else if (cin == 2) stem_conv_kernel<2><<<cdiv(tot, 128), 128, 0, st>>>(p);
+    else stem_conv_kernel<3><<<cdiv(tot, 128), 128, 0, st>>>(p);
+    return check_launch("stem_conv");
+}
+
+int ptta_head_conv(const void* in, const float* w, float bias, const float* add, float* out, int n, int h, int ww, int relu_in,
+                   int accumulate, ptta_stream_t stream) {
+    long long tot = (long long)n * h * ww;
+    head_conv_kernel<<<cdiv(tot, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)in, w, bias, add, out, n, h, ww, relu_in, accumulate);
+    return check_launch("head_conv");
+}
+
+int ptta_up2_1ch(const float* a, const float* b, const float* c, float* out, int n, int h, int w, ptta_stream_t stream) {
+    long long tot = (long long)n * h * w * 4;
+    up2_1ch_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(a, b, c, out, n, h, w);
+    return check_launch("up2_1ch");
+}
+int ptta_up2_1ch_adjoint(const float* ghi, float* glo, int n, int h, int w, int accumulate, ptta_stream_t stream) {
+    long long tot = (long long)n * h * w;
+    up2_1ch_adj_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(ghi, glo, n, h, w, accumulate);
+    return check_launch("up2_1ch_adj");
+}
+int ptta_add_up2_c32(const void* x, const void* half, void* out, int n, int h, int w, ptta_stream_t stream) {
+    long long tot = (long long)n * h * w * 4 * 4;
+    add_up2_c32_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)half, (bf16*)out, n, h, w);
+    return check_launch("add_up2_c32");
+}
+int ptta_up2_c32_adjoint(const void* ghi, void* glo, int n, int h, int w, int accumulate, ptta_stream_t stream) {
+    long long tot = (long long)n * h * w * 4;
+    up2_c32_adj_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)ghi, (bf16*)glo, n, h, w, accumulate);
+    return check_launch("up2_c32_adj");
+}
+
+int ptta_gemm_bf16(const void* a, const void* b, void* c, const float* bias, long long m, int n, int k, ptta_stream_t stream) {
+    GemmParams p; p.A = (const bf16*)a; p.B = (const bf16*)b; p.C = (bf16*)c; p.bias = bias; p.M = m; p.N = n; p.K = k;
+    return launch_gemm(p, (cudaStream_t)stream);
+}
+
+__global__ void adam_flat_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                                 float wd, int step) {
+    const double bc1 = 1.0 - pow((double)b1, (double)step);
+    const double bc2 = 1.0 - pow((double)b2, (double)step);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gg = g[i], pp = p[i];
+        if (wd != 0.f) gg = fmaf(wd, pp, gg);
+        float mm = b1 * m[i] + (1.f - b1) * gg;
+        float vv = b2 * v[i] + (1.f - b2) * gg * gg;
+        m[i] = mm; v[i] = vv;
+        p[i] = pp - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+    }
+}
+int ptta_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd, int step,
+                   ptta_stream_t stream) {
+    PTTA_CHECK(step >= 1, "adam: step must be >= 1");
+    if (n <= 0) return 0;
+    int blocks = (int)std::min<long long>(cdiv(n, 256), 1184);
+    adam_flat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, step);
+    return check_launch("adam_flat");
+}
+
+// ---- engine ---------------------------------------------------------------------------------------
+int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepare_mode) {
+    PTTA_CHECK(out != nullptr, "create: null out pointer");
+    PTTA_CHECK(n >= 1 && h >= 16 && w >= 16, "create: bad shape %dx%dx%d", n, h, w);
+    PTTA_CHECK(h % 16 == 0 && w % 16 == 0, "create: H=%d, W=%d must be multiples of 16 (pad first, src/msg_chn_model_adapt.py:58-102)", h, w);
+    std::string mode = prepare_mode ? prepare_mode : "";
+    PTTA_CHECK(mode.find("meta") != std::string::npos && mode.find("seq") != std::string::npos,
+               "create: prepare_mode '%s' has no sequential meta layer (network_exp_msg_chn_adapt.py:1063-1077)", mode.c_str());
+    bool two = mode.find("2layers") != std::string::npos, one = mode.find("1layer") != std::string::npos;
+    PTTA_CHECK(two || one, "create: prepare_mode '%s' must contain '1layer' or '2layers'", mode.c_str());
+    ptta_msgchn* e = new ptta_msgchn();
+    e->N = n; e->H = h; e->W = w; e->two_layers = two; e->prepare_mode = mode;
+    e->has_heads = mode.find("selfsup") != std::string::npos;
+    e->define_model();
+    e->plan();
+    *out = e;
+    return 0;
+}
+void ptta_msgchn_destroy(ptta_msgchn* e) {
+    if (!e) return;
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    delete e;
+}
+size_t ptta_msgchn_workspace_bytes(const ptta_msgchn* e) { return e ? e->ws_bytes : 0; }
+
+int ptta_msgchn_bind_workspace(ptta_msgchn* e, void* ws, size_t bytes, ptta_stream_t stream) {
+    PTTA_CHECK(e && ws, "bind_workspace: null argument");
+    PTTA_CHECK(bytes >= e->ws_bytes, "bind_workspace: %zu bytes given, %zu needed", bytes, e->ws_bytes);
+    PTTA_CHECK(((uintptr_t)ws & 255) == 0, "bind_workspace: pointer must be 256-byte aligned");
+    e->arena.base = (char*)ws;
+    e->plan();
+    e->bound = true; e->packed = false;
+    PTTA_CUDA(cudaMemsetAsync(ws, 0, e->ws_bytes, (cudaStream_t)stream));
+    AdamHyper hy; hy.lr = 1e-4f; hy.beta1 = 0.9f; hy.beta2 = 0.999f; hy.eps = 1e-8f; hy.weight_decay = 0.f; hy.step = 0;
+    PTTA_CUDA(cudaMemcpyAsync(e->adam_hyper, &hy, sizeof(hy), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    PTTA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+int ptta_msgchn_set_tensor(ptta_msgchn* e, const char* key, void* ptr, long long numel) {
+    PTTA_CHECK(e && key && ptr, "set_tensor: null argument");
+    e->ext[key] = std::make_pair(ptr, numel);
+    e->packed = false;
+    return 0;
+}
+int ptta_msgchn_num_keys(const ptta_msgchn* e) { return e ? (int)e->keys.size() : 0; }
+const char* ptta_msgchn_key(const ptta_msgchn* e, int i) { return (e && i >= 0 && i < (int)e->keys.size()) ? e->keys[i].c_str() : nullptr; }
+
+int ptta_msgchn_pack_weights(ptta_msgchn* e, ptta_stream_t stream) {
+    PTTA_CHECK(e && e->bound, "pack_weights: bind a workspace first");
+    e->st = (cudaStream_t)stream;
+    return e->pack_all();
+}
+int ptta_msgchn_pack_adapted(ptta_msgchn* e, ptta_stream_t stream) {
+    PTTA_CHECK(e && e->bound && e->packed, "pack_adapted: engine not ready");
+    e->st = (cudaStream_t)stream;
+    return e->pack_adapted();
+}
+
+int ptta_msgchn_forward(ptta_msgchn* e, const float* image, const float* isc, const float* ish, const float* sparse, float cap,
+                        int training, ptta_stream_t stream) {
+    PTTA_CHECK(e && image && sparse && isc && ish, "forward: null argument");
+    e->st = (cudaStream_t)stream;
+    return e->forward(image, isc, ish, sparse, cap, training != 0);
+}
+int ptta_msgchn_loss(ptta_msgchn* e, const float* image_raw, const float* sparse, const float* validity, float cap, float w_sd, float w_sm,
+                     float w_cos, ptta_stream_t stream) {
+    PTTA_CHECK(e && image_raw && sparse && validity, "loss: null argument");
+    PTTA_CHECK(e->has_heads, "loss: engine has no proxy heads");
+    e->st = (cudaStream_t)stream;
+    return e->loss(image_raw, sparse, validity, cap, w_sd, w_sm, w_cos);
+}
+int ptta_msgchn_read_losses(ptta_msgchn* e, float* out5, ptta_stream_t stream) {
+    PTTA_CHECK(e && out5, "read_losses: null argument");
+    PTTA_CUDA(cudaMemcpyAsync(out5, e->losses, 5 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PTTA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int ptta_msgchn_backward(ptta_msgchn* e, float gscale, ptta_stream_t stream) {
+    PTTA_CHECK(e, "backward: null engine");
+    e->st = (cudaStream_t)stream;
+    return e->backward(gscale);
+}
+int ptta_msgchn_loss_backward(ptta_msgchn* e, float gscale, ptta_stream_t stream) {
+    PTTA_CHECK(e, "loss_backward: null engine");
+    e->st = (cudaStream_t)stream;
+    return e->loss_backward(gscale);
+}
+int ptta_msgchn_network_backward(ptta_msgchn* e, ptta_stream_t stream) {
+    PTTA_CHECK(e && e->bound && e->packed, "network_backward: engine not ready");
+    e->st = (cudaStream_t)stream;
+    return e->network_backward();
+}
+int ptta_msgchn_set_adam(ptta_msgchn* e, float lr, float b1, float b2, float eps, float wd, int step_count, ptta_stream_t stream) {
+    PTTA_CHECK(e && e->bound, "set_adam: engine not bound");
+    AdamHyper hy; hy.lr = lr; hy.beta1 = b1; hy.beta2 = b2; hy.eps = eps; hy.weight_decay = wd; hy.step = step_count;
+    if (step_count < 0) {   // keep the device-side step count, update the rest
+        PTTA_CUDA(cudaMemcpyAsync(e->adam_hyper, &hy, offsetof(AdamHyper, step), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    } else {
+        PTTA_CUDA(cudaMemcpyAsync(e->adam_hyper, &hy, sizeof(hy), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    }
+    PTTA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));   // hy is a stack object
+    return 0;
+}
+int ptta_msgchn_adam_step(ptta_msgchn* e, ptta_stream_t stream) {
+    PTTA_CHECK(e && e->bound && e->packed, "adam_step: engine not ready");
+    e->st = (cudaStream_t)stream;
+    return e->adam_step();
+}
+int ptta_msgchn_tta_step(ptta_msgchn* e, const float* image_raw, const float* isc, const float* ish, const float* sparse, float cap,
+                         float w_sd, float w_sm, float w_cos, ptta_stream_t stream) {
+    PTTA_CHECK(e && image_raw && sparse && isc && ish, "tta_step: null argument");
+    e->st = (cudaStream_t)stream;
+    return e->tta_step(image_raw, isc, ish, sparse, cap, w_sd, w_sm, w_cos);
+}
+int ptta_msgchn_tta_step_graph(ptta_msgchn* e, const float* image_raw, const float* isc, const float* ish, const float* sparse, float cap,
+                               float w_sd, float w_sm, float w_cos, ptta_stream_t stream) {
+    PTTA_CHECK(e && image_raw && sparse && isc && ish, "tta_step_graph: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    PTTA_CHECK(st != nullptr, "tta_step_graph: needs a non-default stream (legacy stream 0 cannot be captured)");
+    const void* key[4] = {image_raw, sparse, isc, ish};
+    if (e->graph_exec && memcmp(key, e->graph_key, sizeof(key)) != 0) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    if (!e->graph_exec) {
+        // one eager step first: sets every cudaFuncAttribute (not capturable) and validates the arguments
+        e->st = st;
+        PTTA_TRY(e->tta_step(image_raw, isc, ish, sparse, cap, w_sd, w_sm, w_cos));
+        PTTA_CUDA(cudaStreamSynchronize(st));
+        // capture a second pass WITHOUT executing it
+        cudaGraph_t graph = nullptr;
+        PTTA_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = e->tta_step(image_raw, isc, ish, sparse, cap, w_sd, w_sm, w_cos);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        PTTA_CHECK(ce == cudaSuccess, "graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        PTTA_CHECK(ce == cudaSuccess, "graph instantiate failed: %s", cudaGetErrorString(ce));
+        memcpy(e->graph_key, key, sizeof(key));
+        return 0;   // the eager step above WAS this call's step
+    }
+    PTTA_CUDA(cudaGraphLaunch(e->graph_exec, st));
+    return 0;
+}
+
+int ptta_msgchn_get_tensor(ptta_msgchn* e, const char* name, void** ptr, int* dtype, long long* dims4) {
+    PTTA_CHECK(e && name && ptr, "get_tensor: null argument");
+    PTTA_CHECK(e->bound, "get_tensor: no workspace bound");
+    auto it = e->named.find(name);
+    PTTA_CHECK(it != e->named.end(), "get_tensor: unknown tensor '%s'", name);
+    *ptr = it->second.p;
+    if (dtype) *dtype = it->second.dtype;
+    if (dims4) for (int k = 0; k < 4; ++k) dims4[k] = it->second.d[k];
+    return 0;
+}
+int ptta_msgchn_num_tensors(const ptta_msgchn* e) { return e ? (int)e->named_order.size() : 0; }
+const char* ptta_msgchn_tensor_name(const ptta_msgchn* e, int i) {
+    return (e && i >= 0 && i < (int)e->named_order.size()) ? e->named_order[i].c_str() : nullptr;
+}
+long long ptta_msgchn_launch_count(const ptta_msgchn*) { return g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,868 @@
+// Memory-bound kernels of the ProxyTTA step: pre-processing, pyramid, 1<->32 channel stems, bilinear
+// x2 (and its adjoint), BatchNorm pieces, losses, Adam.  All fp32 arithmetic; 32-channel maps are
+// NHWC bf16, single-channel maps fp32 [N,H,W].
+#pragma once
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace ptta {
+
+// -------------------------------------------------------------------------------------------------
+// a1 + a2: validity map (src/tta_main.py:583-586) and OutlierRemoval(7, 1.5)
+// (src/net_utils.py:766-811).  Invalid / out-of-image samples are +inf in the 7x7 min window, which
+// gives bit-identical results to the reference's 10*max(d) fill without its global reduction.
+// -------------------------------------------------------------------------------------------------
+#define OR_TX 32
+#define OR_TY 8
+__global__ void __launch_bounds__(OR_TX * OR_TY) outlier_removal_kernel(const float* __restrict__ d, float* __restrict__ d_out,
+                                                                        float* __restrict__ v_out, int H, int W, int ksize, float thr) {
+    extern __shared__ float s_or[];
+    const int pad = ksize / 2;
+    const int SW = OR_TX + 2 * pad, SH = OR_TY + 2 * pad;
+    const int n = blockIdx.z;
+    const int x0 = blockIdx.x * OR_TX, y0 = blockIdx.y * OR_TY;
+    const float* dn = d + (size_t)n * H * W;
+    const int tid = threadIdx.y * OR_TX + threadIdx.x;
+    for (int i = tid; i < SW * SH; i += OR_TX * OR_TY) {
+        int sy = i / SW, sx = i - sy * SW;
+        int gy = y0 - pad + sy, gx = x0 - pad + sx;
+        float f = CUDART_INF_F;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            float val = dn[(size_t)gy * W + gx];
+            float vm = val > 0.f ? 1.f : val;          // validity map
+            f = vm <= 0.f ? CUDART_INF_F : val;
+        }
+        s_or[i] = f;
+    }
+    __syncthreads();
+    int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float val = dn[(size_t)y * W + x];
+    float vm = val > 0.f ? 1.f : val;
+    float keep = 1.f;
+    if (vm != 0.f) {
+        float m = CUDART_INF_F;
+        for (int j = 0; j < ksize; ++j)
+            for (int i = 0; i < ksize; ++i) m = fminf(m, s_or[(threadIdx.y + j) * SW + threadIdx.x + i]);
+        keep = (m < val - thr) ? 0.f : 1.f;
+    }
+    float vo = vm * keep;
+    size_t o = (size_t)n * H * W + (size_t)y * W + x;
+    v_out[o] = vo;
+    d_out[o] = val * vo;
+}
+
+// -------------------------------------------------------------------------------------------------
+// a3 + a6: clamp(d, 0, cap) (src/external_model_adapt.py:103-108) and the validity-normalised
+// average-pool pyramid (network_exp_msg_chn_adapt.py:479,487,492).  One thread per /4 cell.
+// -------------------------------------------------------------------------------------------------
+__global__ void pyramid_kernel(const float* __restrict__ d, float* __restrict__ dc, float* __restrict__ d2, float* __restrict__ d4,
+                               int N, int H, int W, float cap, int do_clamp) {
+    int H4 = H / 4, W4 = W / 4;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * H4 * W4) return;
+    int x4 = idx % W4;
+    int y4 = (idx / W4) % H4;
+    int n = idx / ((long long)W4 * H4);
+    const float* dn = d + (size_t)n * H * W;
+    float* dcn = dc + (size_t)n * H * W;
+    float v[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float4 r = *reinterpret_cast<const float4*>(dn + (size_t)(y4 * 4 + j) * W + x4 * 4);
+        if (do_clamp) {
+            r.x = fminf(fmaxf(r.x, 0.f), cap); r.y = fminf(fmaxf(r.y, 0.f), cap);
+            r.z = fminf(fmaxf(r.z, 0.f), cap); r.w = fminf(fmaxf(r.w, 0.f), cap);
+        }
+        *reinterpret_cast<float4*>(dcn + (size_t)(y4 * 4 + j) * W + x4 * 4) = r;
+        v[j][0] = r.x; v[j][1] = r.y; v[j][2] = r.z; v[j][3] = r.w;
+    }
+    float s4 = 0.f, c4 = 0.f;
+    int H2 = H / 2, W2 = W / 2;
+#pragma unroll
+    for (int by = 0; by < 2; ++by)
+#pragma unroll
+        for (int bx = 0; bx < 2; ++bx) {
+            float s = 0.f, c = 0.f;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    float t = v[by * 2 + j][bx * 2 + i];
+                    s += t;
+                    c += t > 0.f ? 1.f : 0.f;
+                }
+            s4 += s; c4 += c;
+            d2[(size_t)n * H2 * W2 + (size_t)(y4 * 2 + by) * W2 + x4 * 2 + bx] = (s * 0.25f) / (c * 0.25f + 0.0001f);
+        }
+    d4[(size_t)n * H4 * W4 + (size_t)y4 * W4 + x4] = (s4 * 0.0625f) / (c4 * 0.0625f + 0.0001f);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Stem: {1,2,3} fp32 planes -> 32 channels bf16 NHWC, 3x3 s1 p1 (init.0 of every encoder,
+// network_exp_msg_chn_adapt.py:172,220).  Each plane has its own pointer / batch stride and an
+// affine (x*scale + shift) so that image normalisation (src/transforms.py:669-712) and the
+// cat((d, up2(pred))) of the cascade (network_exp_msg_chn_adapt.py:494,501) need no extra pass.
+// With CIN=1, pre-flipped weights and a ReLU mask it is also the data-gradient of the 32->1
+// prediction conv.
+// -------------------------------------------------------------------------------------------------
+struct StemParams {
+    const float* plane[3];
+    long long batch_stride[3];
+    float scale[3], shift[3];
+    const float* w;      // [32][CIN][3][3]
+    const float* bias;   // [32] or null
+    const bf16* mask;    // relu mask (NHWC 32) or null
+    bf16* out;
+    int N, H, W;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams p) {
+    __shared__ float s_w[CIN * 9 * 32];   // [ci][tap][co]
+    __shared__ float s_b[32];
+    for (int i = threadIdx.x; i < CIN * 9 * 32; i += blockDim.x) {
+        int co = i & 31, r = i >> 5;       // r = ci*9 + tap
+        s_w[i] = p.w[(size_t)co * CIN * 9 + r];
+    }
+    if (threadIdx.x < 32) s_b[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+    __syncthreads();
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)p.N * p.H * p.W;
+    if (idx >= total) return;
+    int x = idx % p.W;
+    int y = (idx / p.W) % p.H;
+    int n = idx / ((long long)p.W * p.H);
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = s_b[c];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+        const float* pl = p.plane[ci] + (size_t)n * p.batch_stride[ci];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            int gy = y + ky - 1;
+            if (gy < 0 || gy >= p.H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                int gx = x + kx - 1;
+                if (gx < 0 || gx >= p.W) continue;
+                float v = __ldg(pl + (size_t)gy * p.W + gx) * p.scale[ci] + p.shift[ci];
+                const float* wr = s_w + (ci * 9 + ky * 3 + kx) * 32;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+            }
+        }
+    }
+    size_t o = (size_t)idx * 32;
+    if (p.mask) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 mv = *reinterpret_cast<const uint4*>(p.mask + o + q * 8);
+            const uint32_t* mu = reinterpret_cast<const uint32_t*>(&mv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 m = unpack_bf162(mu[j]);
+                if (!(m.x > 0.f)) acc[q * 8 + j * 2] = 0.f;
+                if (!(m.y > 0.f)) acc[q * 8 + j * 2 + 1] = 0.f;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint4 ov;
+        ov.x = pack_bf162(acc[q * 8 + 0], acc[q * 8 + 1]);
+        ov.y = pack_bf162(acc[q * 8 + 2], acc[q * 8 + 3]);
+        ov.z = pack_bf162(acc[q * 8 + 4], acc[q * 8 + 5]);
+        ov.w = pack_bf162(acc[q * 8 + 6], acc[q * 8 + 7]);
+        *reinterpret_cast<uint4*>(p.out + o + q * 8) = ov;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// 32 -> 1 channel 3x3 s1 p1 conv: the prediction layer prdct.3 (network_exp_msg_chn_adapt.py:289)
+// with ReLU-on-load, and -- with pre-flipped weights, no ReLU, accumulate -- the data-gradient of a
+// stem with respect to one of its input planes.  out = [acc_prev +] conv(in) + bias [+ add].
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) head_conv_kernel(const bf16* __restrict__ in, const float* __restrict__ w /*[9][32]*/,
+                                                        float bias, const float* __restrict__ add, float* __restrict__ out,
+                                                        int N, int H, int W, int relu_in, int accumulate) {
+    __shared__ float s_w[9 * 32];
+    for (int i = threadIdx.x; i < 288; i += blockDim.x) s_w[i] = w[i];
+    __syncthreads();
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * H * W;
+    if (idx >= total) return;
+    int x = idx % W;
+    int y = (idx / W) % H;
+    int n = idx / ((long long)W * H);
+    const bf16* inn = in + (size_t)n * H * W * 32;
+    float acc = bias;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        int gy = y + ky - 1;
+        if (gy < 0 || gy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            int gx = x + kx - 1;
+            if (gx < 0 || gx >= W) continue;
+            const uint4* src = reinterpret_cast<const uint4*>(inn + ((size_t)gy * W + gx) * 32);
+            const float* wr = s_w + (ky * 3 + kx) * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 v = __ldg(src + q);
+                const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 f = unpack_bf162(u[j]);
+                    if (relu_in) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+                    acc = fmaf(f.x, wr[q * 8 + j * 2], acc);
+                    acc = fmaf(f.y, wr[q * 8 + j * 2 + 1], acc);
+                }
+            }
+        }
+    }
+    if (add) acc += add[idx];
+    if (accumulate) acc += out[idx];
+    out[idx] = acc;
+}
+
+// -------------------------------------------------------------------------------------------------
+// bilinear x2, align_corners=True (F.interpolate), fp32 coordinates as ATen's
+// upsample_bilinear2d: scale = (in-1)/(out-1), src = scale*dst, i0 = int(src), lambda = src - i0.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void up2_coord(int dst, int in_size, float scale, int& i0, int& i1, float& l0, float& l1) {
+    float src = scale * (float)dst;
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.f - l1;
+}
+__host__ __device__ __forceinline__ float up2_scale(int in_size) {
+    int out_size = 2 * in_size;
+    return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+}
+
+// out[y][x] = up2(a [+ b])[y][x] [+ c[y][x]]     (a, b: [N,h,w]; out, c: [N,2h,2w])
+__global__ void up2_1ch_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                               float* __restrict__ out, int N, int h, int w) {
+    int H = 2 * h, W = 2 * w;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * H * W) return;
+    int x = idx % W;
+    int y = (idx / W) % H;
+    int n = idx / ((long long)W * H);
+    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+    up2_coord(y, h, up2_scale(h), y0, y1, ly0, ly1);
+    up2_coord(x, w, up2_scale(w), x0, x1, lx0, lx1);
+    size_t base = (size_t)n * h * w;
+    float v00 = a[base + (size_t)y0 * w + x0], v01 = a[base + (size_t)y0 * w + x1];
+    float v10 = a[base + (size_t)y1 * w + x0], v11 = a[base + (size_t)y1 * w + x1];
+    if (b) {
+        v00 += b[base + (size_t)y0 * w + x0]; v01 += b[base + (size_t)y0 * w + x1];
+        v10 += b[base + (size_t)y1 * w + x0]; v11 += b[base + (size_t)y1 * w + x1];
+    }
+    float r = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+    if (c) r += c[idx];
+    out[idx] = r;
+}
+
+// weight with which destination index t reads source index s along one axis
+__device__ __forceinline__ float up2_adj_weight(int t, int s, int in_size, float scale) {
+    int i0, i1; float l0, l1;
+    up2_coord(t, in_size, scale, i0, i1, l0, l1);
+    float wgt = 0.f;
+    if (i0 == s) wgt += l0;
+    if (i1 == s) wgt += l1;
+    return wgt;
+}
+
+// adjoint: gl[s] [+]= sum_t w(t,s) * gh[t]        (gh: [N,2h,2w] -> gl: [N,h,w])
+__global__ void up2_1ch_adj_kernel(const float* __restrict__ gh, float* __restrict__ gl, int N, int h, int w, int accumulate) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * h * w) return;
+    int x = idx % w;
+    int y = (idx / w) % h;
+    int n = idx / ((long long)w * h);
+    int H = 2 * h, W = 2 * w;
+    float sy = up2_scale(h), sx = up2_scale(w);
+    float wy[6], wx[6];
+    int ty0 = 2 * y - 2, tx0 = 2 * x - 2;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        int t = ty0 + j;
+        wy[j] = (t >= 0 && t < H) ? up2_adj_weight(t, y, h, sy) : 0.f;
+        t = tx0 + j;
+        wx[j] = (t >= 0 && t < W) ? up2_adj_weight(t, x, w, sx) : 0.f;
+    }
+    const float* g = gh + (size_t)n * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        if (wy[j] == 0.f) continue;
+        float row = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            if (wx[i] != 0.f) row += wx[i] * g[(size_t)(ty0 + j) * W + tx0 + i];
+        acc += wy[j] * row;
+    }
+    if (accumulate) acc += gl[idx];
+    gl[idx] = acc;
+}
+
+// 32-channel NHWC bf16: out[p] = x[p] + up2(half)[p]   (thread = pixel x 8 channels)
+__global__ void add_up2_c32_kernel(const bf16* __restrict__ x, const bf16* __restrict__ half, bf16* __restrict__ out, int N, int h, int w) {
+    int H = 2 * h, W = 2 * w;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * H * W * 4) return;
+    int q = idx & 3;
+    long long pix = idx >> 2;
+    int xx = pix % W;
+    int yy = (pix / W) % H;
+    int n = pix / ((long long)W * H);
+    int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+    up2_coord(yy, h, up2_scale(h), y0, y1, ly0, ly1);
+    up2_coord(xx, w, up2_scale(w), x0, x1, lx0, lx1);
+    const bf16* hb = half + (size_t)n * h * w * 32 + q * 8;
+    uint4 a00 = __ldg(reinterpret_cast<const uint4*>(hb + ((size_t)y0 * w + x0) * 32));
+    uint4 a01 = __ldg(reinterpret_cast<const uint4*>(hb + ((size_t)y0 * w + x1) * 32));
+    uint4 a10 = __ldg(reinterpret_cast<const uint4*>(hb + ((size_t)y1 * w + x0) * 32));
+    uint4 a11 = __ldg(reinterpret_cast<const uint4*>(hb + ((size_t)y1 * w + x1) * 32));
+    uint4 xv = *reinterpret_cast<const uint4*>(x + (size_t)pix * 32 + q * 8);
+    const uint32_t *u00 = reinterpret_cast<const uint32_t*>(&a00), *u01 = reinterpret_cast<const uint32_t*>(&a01);
+    const uint32_t *u10 = reinterpret_cast<const uint32_t*>(&a10), *u11 = reinterpret_cast<const uint32_t*>(&a11);
+    const uint32_t* ux = reinterpret_cast<const uint32_t*>(&xv);
+    uint4 ov; uint32_t* uo = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float2 f00 = unpack_bf162(u00[j]), f01 = unpack_bf162(u01[j]), f10 = unpack_bf162(u10[j]), f11 = unpack_bf162(u11[j]);
+        float2 fx = unpack_bf162(ux[j]);
+        float r0 = ly0 * (lx0 * f00.x + lx1 * f01.x) + ly1 * (lx0 * f10.x + lx1 * f11.x);
+        float r1 = ly0 * (lx0 * f00.y + lx1 * f01.y) + ly1 * (lx0 * f10.y + lx1 * f11.y);
+        uo[j] = pack_bf162(fx.x + r0, fx.y + r1);
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)pix * 32 + q * 8) = ov;
+}
+
+// adjoint for 32-channel maps: gl[s] [+]= sum_t w(t,s) gh[t]
+__global__ void up2_c32_adj_kernel(const bf16* __restrict__ gh, bf16* __restrict__ gl, int N, int h, int w, int accumulate) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * h * w * 4) return;
+    int q = idx & 3;
+    long long pix = idx >> 2;
+    int x = pix % w;
+    int y = (pix / w) % h;
+    int n = pix / ((long long)w * h);
+    int H = 2 * h, W = 2 * w;
+    float sy = up2_scale(h), sx = up2_scale(w);
+    float wy[6], wx[6];
+    int ty0 = 2 * y - 2, tx0 = 2 * x - 2;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        int t = ty0 + j;
+        wy[j] = (t >= 0 && t < H) ? up2_adj_weight(t, y, h, sy) : 0.f;
+        t = tx0 + j;
+        wx[j] = (t >= 0 && t < W) ? up2_adj_weight(t, x, w, sx) : 0.f;
+    }
+    const bf16* g = gh + (size_t)n * H * W * 32 + q * 8;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        if (wy[j] == 0.f) continue;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            float wgt = wy[j] * wx[i];
+            if (wgt == 0.f) continue;
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(g + ((size_t)(ty0 + j) * W + tx0 + i) * 32));
+            const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float2 f = unpack_bf162(u[k]);
+                acc[k * 2] = fmaf(wgt, f.x, acc[k * 2]);
+                acc[k * 2 + 1] = fmaf(wgt, f.y, acc[k * 2 + 1]);
+            }
+        }
+    }
+    bf16* o = gl + (size_t)pix * 32 + q * 8;
+    if (accumulate) {
+        uint4 v = *reinterpret_cast<const uint4*>(o);
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 f = unpack_bf162(u[k]);
+            acc[k * 2] += f.x; acc[k * 2 + 1] += f.y;
+        }
+    }
+    uint4 ov;
+    ov.x = pack_bf162(acc[0], acc[1]); ov.y = pack_bf162(acc[2], acc[3]);
+    ov.z = pack_bf162(acc[4], acc[5]); ov.w = pack_bf162(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(o) = ov;
+}
+
+// out = a + b (bf16, n multiple of 8)
+__global__ void ew_add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, long long n8) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    uint4 av = reinterpret_cast<const uint4*>(a)[i], bv = reinterpret_cast<const uint4*>(b)[i];
+    const uint32_t *ua = reinterpret_cast<const uint32_t*>(&av), *ub = reinterpret_cast<const uint32_t*>(&bv);
+    uint4 ov; uint32_t* uo = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float2 fa = unpack_bf162(ua[j]), fb = unpack_bf162(ub[j]);
+        uo[j] = pack_bf162(fa.x + fb.x, fa.y + fb.y);
+    }
+    reinterpret_cast<uint4*>(out)[i] = ov;
+}
+
+// -------------------------------------------------------------------------------------------------
+// BatchNorm (train mode: batch statistics, biased variance for normalisation, unbiased for the
+// running estimate, momentum 0.1 -- nn.BatchNorm2d/1d as used at network_exp_msg_chn_adapt.py:28-36
+// and :1089-1098).  Tensors are [rows][C] bf16 (NHWC maps or the R x 512 head matrices).
+//   col_stats        : per-block partial sums, double:  mode 0: (sum x, sum x^2)
+//                                                       mode 1: (sum dy, sum dy*xhat)  [BN backward]
+//   bn_finalize      : partials -> mean/invstd/scale/shift (+ running-stat update)
+//   bn_apply         : y = act(x*scale + shift) [+ residual]
+//   bn_bwd_finalize  : partials -> dgamma, dbeta, and the three coefficient vectors of dx
+//   bn_bwd_apply     : dx = k0[c]*dy - k1[c] - xhat*k2[c]
+// `relu_mask`: the incoming dy is first multiplied by [x*scale+shift > 0] (the ReLU that follows BN
+// in the MLP heads), so no masked copy of dy is ever written.
+// -------------------------------------------------------------------------------------------------
+#define STATS_ROWS_PER_BLOCK 1024
+__global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, double* __restrict__ partial,
+                                                        long long rows, int C, int mode, const float* __restrict__ mean,
+                                                        const float* __restrict__ invstd, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, int relu_mask) {
+    extern __shared__ double s_red[];   // [256][2]... reduced per chunk below
+    const int CH = C / 8;
+    const int step = 256 / CH;
+    const int c = threadIdx.x % CH, r0 = threadIdx.x / CH;
+    long long row_begin = (long long)blockIdx.x * STATS_ROWS_PER_BLOCK;
+    long long row_end = row_begin + STATS_ROWS_PER_BLOCK;
+    if (row_end > rows) row_end = rows;
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
+    float mu[8], is[8], sc[8], sh[8];
+    if (mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mu[j] = mean[c * 8 + j]; is[j] = invstd[c * 8 + j];
+            sc[j] = relu_mask ? scale[c * 8 + j] : 0.f; sh[j] = relu_mask ? shift[c * 8 + j] : 0.f;
+        }
+    }
+    for (long long r = row_begin + r0; r < row_end; r += step) {
+        uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r * C + c * 8));
+        const uint32_t* ux = reinterpret_cast<const uint32_t*>(&xv);
+        if (mode == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_bf162(ux[j]);
+                s0[j * 2] += f.x; s0[j * 2 + 1] += f.y;
+                s1[j * 2] = fmaf(f.x, f.x, s1[j * 2]); s1[j * 2 + 1] = fmaf(f.y, f.y, s1[j * 2 + 1]);
+            }
+        } else {
+            uint4 gv = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)r * C + c * 8));
+            const uint32_t* ug = reinterpret_cast<const uint32_t*>(&gv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_bf162(ux[j]), g = unpack_bf162(ug[j]);
+                if (relu_mask) {
+                    if (!(f.x * sc[j * 2] + sh[j * 2] > 0.f)) g.x = 0.f;
+                    if (!(f.y * sc[j * 2 + 1] + sh[j * 2 + 1] > 0.f)) g.y = 0.f;
+                }
+                float xh0 = (f.x - mu[j * 2]) * is[j * 2], xh1 = (f.y - mu[j * 2 + 1]) * is[j * 2 + 1];
+                s0[j * 2] += g.x; s0[j * 2 + 1] += g.y;
+                s1[j * 2] = fmaf(g.x, xh0, s1[j * 2]); s1[j * 2 + 1] = fmaf(g.y, xh1, s1[j * 2 + 1]);
+            }
+        }
+    }
+    // reduce over the `step` threads that share a channel chunk
+    double* sh0 = s_red;                 // [step][C]
+    double* sh1 = s_red + (size_t)step * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sh0[(size_t)r0 * C + c * 8 + j] = (double)s0[j];
+        sh1[(size_t)r0 * C + c * 8 + j] = (double)s1[j];
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < C; ch += 256) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < step; ++k) { a += sh0[(size_t)k * C + ch]; b += sh1[(size_t)k * C + ch]; }
+        partial[((size_t)blockIdx.x * 2 + 0) * C + ch] = a;
+        partial[((size_t)blockIdx.x * 2 + 1) * C + ch] = b;
+    }
+}
+
+struct BnParams {
+    const float* gamma; const float* beta;
+    float* running_mean; float* running_var; long long* num_batches_tracked;
+    float* mean; float* invstd; float* scale; float* shift;
+    float momentum, eps;
+};
+
+__global__ void bn_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C, BnParams p, int training) {
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= C) return;
+    if (training) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < nblk; ++k) { a += partial[((size_t)k * 2 + 0) * C + ch]; b += partial[((size_t)k * 2 + 1) * C + ch]; }
+        double m = a / (double)count;
+        double var = b / (double)count - m * m;
+        if (var < 0.0) var = 0.0;
+        float invstd = (float)(1.0 / sqrt(var + (double)p.eps));
+        p.mean[ch] = (float)m;
+        p.invstd[ch] = invstd;
+        float sc = p.gamma[ch] * invstd;
+        p.scale[ch] = sc;
+        p.shift[ch] = p.beta[ch] - (float)m * sc;
+        if (p.running_mean) {
+            double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+            p.running_mean[ch] = (1.f - p.momentum) * p.running_mean[ch] + p.momentum * (float)m;
+            p.running_var[ch] = (1.f - p.momentum) * p.running_var[ch] + p.momentum * (float)unbiased;
+        }
+        if (ch == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+    } else {
+        float invstd = 1.f / sqrtf(p.running_var[ch] + p.eps);
+        p.mean[ch] = p.running_mean[ch];
+        p.invstd[ch] = invstd;
+        float sc = p.gamma[ch] * invstd;
+        p.scale[ch] = sc;
+        p.shift[ch] = p.beta[ch] - p.running_mean[ch] * sc;
+    }
+}
+
+// y = act(x*scale+shift) [+ res];  act: 0 none, 1 relu
+__global__ void bn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res, bf16* __restrict__ y, long long rows, int C,
+                                const float* __restrict__ scale, const float* __restrict__ shift, int act) {
+    const int CH = C / 8;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * CH) return;
+    int c = i % CH;
+    uint4 xv = reinterpret_cast<const uint4*>(x)[i];
+    const uint32_t* ux = reinterpret_cast<const uint32_t*>(&xv);
+    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+    if (res) rv = reinterpret_cast<const uint4*>(res)[i];
+    const uint32_t* ur = reinterpret_cast<const uint32_t*>(&rv);
+    uint4 ov; uint32_t* uo = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float2 f = unpack_bf162(ux[j]);
+        int ch = c * 8 + j * 2;
+        f.x = f.x * scale[ch] + shift[ch];
+        f.y = f.y * scale[ch + 1] + shift[ch + 1];
+        if (act == 1) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+        if (res) { float2 r = unpack_bf162(ur[j]); f.x += r.x; f.y += r.y; }
+        uo[j] = pack_bf162(f.x, f.y);
+    }
+    reinterpret_cast<uint4*>(y)[i] = ov;
+}
+
+// dgamma = sum dy*xhat, dbeta = sum dy;  dx = k0*dy - k1 - xhat*k2 with
+//   k0 = gamma*invstd, k1 = k0*mean(dy), k2 = k0*mean(dy*xhat)
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C,
+                                       const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ k0, float* __restrict__ k1, float* __restrict__ k2) {
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= C) return;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < nblk; ++k) { a += partial[((size_t)k * 2 + 0) * C + ch]; b += partial[((size_t)k * 2 + 1) * C + ch]; }
+    if (dbeta) dbeta[ch] = (float)a;
+    if (dgamma) dgamma[ch] = (float)b;
+    float g = gamma[ch] * invstd[ch];
+    k0[ch] = g;
+    k1[ch] = (float)((double)g * a / (double)count);
+    k2[ch] = (float)((double)g * b / (double)count);
+}
+
+__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, long long rows, int C,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ k0,
+                                    const float* __restrict__ k1, const float* __restrict__ k2, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int relu_mask) {
+    const int CH = C / 8;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * CH) return;
+    int c = i % CH;
+    uint4 xv = reinterpret_cast<const uint4*>(x)[i], gv = reinterpret_cast<const uint4*>(dy)[i];
+    const uint32_t *ux = reinterpret_cast<const uint32_t*>(&xv), *ug = reinterpret_cast<const uint32_t*>(&gv);
+    uint4 ov; uint32_t* uo = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float2 f = unpack_bf162(ux[j]), g = unpack_bf162(ug[j]);
+        int ch = c * 8 + j * 2;
+        if (relu_mask) {
+            if (!(f.x * scale[ch] + shift[ch] > 0.f)) g.x = 0.f;
+            if (!(f.y * scale[ch + 1] + shift[ch + 1] > 0.f)) g.y = 0.f;
+        }
+        float xh0 = (f.x - mean[ch]) * invstd[ch], xh1 = (f.y - mean[ch + 1]) * invstd[ch + 1];
+        float o0 = k0[ch] * g.x - k1[ch] - xh0 * k2[ch];
+        float o1 = k0[ch + 1] * g.y - k1[ch + 1] - xh1 * k2[ch + 1];
+        uo[j] = pack_bf162(o0, o1);
+    }
+    reinterpret_cast<uint4*>(dx)[i] = ov;
+}
+
+// column sums of a [rows][C] bf16 matrix into fp32 (bias gradients): out[c] = sum_r x[r][c]; uses col_stats partials (mode 0, slot 0)
+__global__ void colsum_finalize_kernel(const double* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= C) return;
+    double a = 0.0;
+    for (int k = 0; k < nblk; ++k) a += partial[((size_t)k * 2 + 0) * C + ch];
+    out[ch] = (float)a;
+}
+
+// -------------------------------------------------------------------------------------------------
+// a13-a15: the three TTA losses (src/loss_utils.py:116-169,624-638; src/external_model_adapt.py:371-441)
+//   map part : masked sparse-depth L1 (per-image normalisation, no epsilon) + edge-aware smoothness on
+//              the RAW [0,255] image; one reduction pass + one gradient pass over the full-res maps
+//   cos part : mean_r(2 - 2 <e/|e|, r/|r|>) over the two R x 512 head outputs, warp per row
+//   finalize : device-side `if loss_cos < 0.3: w_cos = 0` gate (a host sync in the reference)
+// Partial layout (doubles): map: [N][nblk][4] = {sum v|d-p|, sum v, sum wx|dx|, sum wy|dy|}; cos: [nblk]
+// -------------------------------------------------------------------------------------------------
+#define LOSS_BLOCK 256
+__global__ void __launch_bounds__(LOSS_BLOCK) loss_map_reduce_kernel(const float* __restrict__ pred, const float* __restrict__ d,
+                                                                     const float* __restrict__ v, const float* __restrict__ img,
+                                                                     double* __restrict__ partial, int H, int W, float cap, int do_clamp) {
+    __shared__ double sh[32];
+    const int n = blockIdx.y;
+    const long long HW = (long long)H * W;
+    const float* pn = pred + n * HW; const float* dn = d + n * HW; const float* vn = v + n * HW;
+    const float* in = img + n * HW * 3;
+    double s_sd = 0.0, s_v = 0.0, s_x = 0.0, s_y = 0.0;
+    for (long long i = (long long)blockIdx.x * LOSS_BLOCK + threadIdx.x; i < HW; i += (long long)gridDim.x * LOSS_BLOCK) {
+        int x = i % W, y = i / W;
+        float p0 = pn[i];
+        float dd = dn[i];
+        if (do_clamp) dd = fminf(fmaxf(dd, 0.f), cap);
+        float vv = vn[i];
+        s_sd += (double)(vv * fabsf(dd - p0));
+        s_v += (double)vv;
+        if (x < W - 1) {
+            float g = fabsf(in[i] - in[i + 1]) + fabsf(in[HW + i] - in[HW + i + 1]) + fabsf(in[2 * HW + i] - in[2 * HW + i + 1]);
+            s_x += (double)(expf(-g / 3.f) * fabsf(p0 - pn[i + 1]));
+        }
+        if (y < H - 1) {
+            float g = fabsf(in[i] - in[i + W]) + fabsf(in[HW + i] - in[HW + i + W]) + fabsf(in[2 * HW + i] - in[2 * HW + i + W]);
+            s_y += (double)(expf(-g / 3.f) * fabsf(p0 - pn[i + W]));
+        }
+    }
+    double r0 = block_sum_d(s_sd, sh), r1 = block_sum_d(s_v, sh), r2 = block_sum_d(s_x, sh), r3 = block_sum_d(s_y, sh);
+    if (threadIdx.x == 0) {
+        double* o = partial + ((size_t)n * gridDim.x + blockIdx.x) * 4;
+        o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3;
+    }
+}
+
+// rowstat[r] = {dot, |e|^2, |r|^2}; partial[blk] = sum over its rows of (2 - 2 cos)
+__global__ void __launch_bounds__(256) loss_cos_rows_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ ref, float* __restrict__ rowstat,
+                                                            double* __restrict__ partial, long long R, int D) {
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double local = 0.0;
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < R; r += (long long)gridDim.x * 8) {
+        const bf16* e = emb + (size_t)r * D; const bf16* f = ref + (size_t)r * D;
+        float dot = 0.f, ne = 0.f, nr = 0.f;
+        for (int c = lane * 8; c < D; c += 256) {
+            uint4 ev = __ldg(reinterpret_cast<const uint4*>(e + c)), fv = __ldg(reinterpret_cast<const uint4*>(f + c));
+            const uint32_t *ue = reinterpret_cast<const uint32_t*>(&ev), *uf = reinterpret_cast<const uint32_t*>(&fv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 a = unpack_bf162(ue[j]), b = unpack_bf162(uf[j]);
+                dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot);
+                ne = fmaf(a.x, a.x, ne); ne = fmaf(a.y, a.y, ne);
+                nr = fmaf(b.x, b.x, nr); nr = fmaf(b.y, b.y, nr);
+            }
+        }
+        dot = warp_sum(dot); ne = warp_sum(ne); nr = warp_sum(nr);
+        if (lane == 0) {
+            rowstat[r * 3 + 0] = dot; rowstat[r * 3 + 1] = ne; rowstat[r * 3 + 2] = nr;
+            float den = fmaxf(sqrtf(ne), 1e-12f) * fmaxf(sqrtf(nr), 1e-12f);
+            local += (double)(2.f - 2.f * dot / den);
+        }
+    }
+    double tot = block_sum_d(local, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+struct LossScalars {   // device-resident result block
+    float loss, loss_sparse_depth, loss_smooth, loss_cos, w_cos_eff;
+    float inv_count[64];   // 1 / sum(v) per image (N <= 64)
+};
+
+__global__ void loss_finalize_kernel(const double* __restrict__ map_partial, int map_blocks, const double* __restrict__ cos_partial,
+                                     int cos_blocks, int N, int H, int W, long long R, float w_sd, float w_sm, float w_cos,
+                                     float cos_gate, LossScalars* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double sd = 0.0, sx = 0.0, sy = 0.0;
+    for (int n = 0; n < N; ++n) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < map_blocks; ++k) {
+            const double* p = map_partial + ((size_t)n * map_blocks + k) * 4;
+            a += p[0]; b += p[1]; sx += p[2]; sy += p[3];
+        }
+        float fa = (float)a, fb = (float)b;
+        sd += (double)(fa / fb);                 // no epsilon: an empty frame yields NaN, as in the reference
+        if (n < 64) out->inv_count[n] = 1.f / fb;
+    }
+    float l_sd = (float)(sd / N);
+    float l_sm = (float)(sx / ((double)N * H * (W - 1))) + (float)(sy / ((double)N * (H - 1) * W));
+    double c = 0.0;
+    for (int k = 0; k < cos_blocks; ++k) c += cos_partial[k];
+    float l_cos = R > 0 ? (float)(c / (double)R) : 0.f;
+    float w_eff = (l_cos < cos_gate) ? 0.f : w_cos;
+    out->loss_sparse_depth = l_sd;
+    out->loss_smooth = l_sm;
+    out->loss_cos = l_cos;
+    out->w_cos_eff = w_eff;
+    out->loss = w_sd * l_sd + w_sm * l_sm + w_eff * l_cos;
+}
+
+// d loss / d pred  (upstream gradient `gscale` of the scalar loss, 1 for plain backward())
+__global__ void loss_map_grad_kernel(const float* __restrict__ pred, const float* __restrict__ d, const float* __restrict__ v,
+                                     const float* __restrict__ img, float* __restrict__ gpred, const LossScalars* __restrict__ ls,
+                                     int N, int H, int W, float cap, int do_clamp, float w_sd, float w_sm, float gscale) {
+    const long long HW = (long long)H * W;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * HW) return;
+    int n = idx / HW;
+    long long i = idx - n * HW;
+    int x = i % W, y = i / W;
+    const float* pn = pred + n * HW; const float* in = img + n * HW * 3;
+    float p0 = pn[i];
+    float dd = d[idx];
+    if (do_clamp) dd = fminf(fmaxf(dd, 0.f), cap);
+    float diff = p0 - dd;
+    float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    float g = w_sd * v[idx] * sgn * ls->inv_count[n] / (float)N;
+    float cx = w_sm / ((float)N * H * (W - 1)), cy = w_sm / ((float)N * (H - 1) * W);
+    if (x < W - 1) {
+        float e = fabsf(in[i] - in[i + 1]) + fabsf(in[HW + i] - in[HW + i + 1]) + fabsf(in[2 * HW + i] - in[2 * HW + i + 1]);
+        float dx = p0 - pn[i + 1];
+        g += cx * expf(-e / 3.f) * (dx > 0.f ? 1.f : (dx < 0.f ? -1.f : 0.f));
+    }
+    if (x > 0) {
+        float e = fabsf(in[i - 1] - in[i]) + fabsf(in[HW + i - 1] - in[HW + i]) + fabsf(in[2 * HW + i - 1] - in[2 * HW + i]);
+        float dx = pn[i - 1] - p0;
+        g -= cx * expf(-e / 3.f) * (dx > 0.f ? 1.f : (dx < 0.f ? -1.f : 0.f));
+    }
+    if (y < H - 1) {
+        float e = fabsf(in[i] - in[i + W]) + fabsf(in[HW + i] - in[HW + i + W]) + fabsf(in[2 * HW + i] - in[2 * HW + i + W]);
+        float dy = p0 - pn[i + W];
+        g += cy * expf(-e / 3.f) * (dy > 0.f ? 1.f : (dy < 0.f ? -1.f : 0.f));
+    }
+    if (y > 0) {
+        float e = fabsf(in[i - W] - in[i]) + fabsf(in[HW + i - W] - in[HW + i]) + fabsf(in[2 * HW + i - W] - in[2 * HW + i]);
+        float dy = pn[i - W] - p0;
+        g -= cy * expf(-e / 3.f) * (dy > 0.f ? 1.f : (dy < 0.f ? -1.f : 0.f));
+    }
+    gpred[idx] = g * gscale;
+}
+
+// d loss / d ref = w_eff * (-2/R) * (ehat - cos*rhat) / max(|r|, eps)
+__global__ void __launch_bounds__(256) loss_cos_grad_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ ref, const float* __restrict__ rowstat,
+                                                            const LossScalars* __restrict__ ls, bf16* __restrict__ gref, long long R, int D, float gscale) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float coef = ls->w_cos_eff * (-2.f / (float)R) * gscale;
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < R; r += (long long)gridDim.x * 8) {
+        float dot = rowstat[r * 3], ne = fmaxf(sqrtf(rowstat[r * 3 + 1]), 1e-12f), nr = fmaxf(sqrtf(rowstat[r * 3 + 2]), 1e-12f);
+        float cs = dot / (ne * nr);
+        float a = coef / (ne * nr), b = coef * cs / (nr * nr);
+        const bf16* e = emb + (size_t)r * D; const bf16* f = ref + (size_t)r * D;
+        bf16* o = gref + (size_t)r * D;
+        for (int c = lane * 8; c < D; c += 256) {
+            uint4 ev = __ldg(reinterpret_cast<const uint4*>(e + c)), fv = __ldg(reinterpret_cast<const uint4*>(f + c));
+            const uint32_t *ue = reinterpret_cast<const uint32_t*>(&ev), *uf = reinterpret_cast<const uint32_t*>(&fv);
+            uint4 ov; uint32_t* uo = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 x = unpack_bf162(ue[j]), y = unpack_bf162(uf[j]);
+                uo[j] = pack_bf162(a * x.x - b * y.x, a * x.y - b * y.y);
+            }
+            *reinterpret_cast<uint4*>(o + c) = ov;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// a17: fused multi-tensor Adam (torch.optim.Adam, amsgrad=False; src/tta_main.py:341-346,633).
+// One launch over a chunk table covering every adapted tensor; hyper-parameters and the step count
+// live on the device so the launch is CUDA-graph friendly.
+// -------------------------------------------------------------------------------------------------
+struct AdamHyper { float lr, beta1, beta2, eps, weight_decay; int step; };
+struct AdamChunk { float* p; const float* g; float* m; float* v; int n; };
+#define ADAM_CHUNK 2048
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__ chunks, const AdamHyper* __restrict__ hy) {
+    const AdamChunk ck = chunks[blockIdx.x];
+    const int t = hy->step + 1;
+    const float b1 = hy->beta1, b2 = hy->beta2;
+    const double bc1 = 1.0 - pow((double)b1, (double)t);
+    const double bc2 = 1.0 - pow((double)b2, (double)t);
+    const float step_size = (float)((double)hy->lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float eps = hy->eps, wd = hy->weight_decay;
+    for (int i = threadIdx.x; i < ck.n; i += 256) {
+        float g = ck.g[i], p = ck.p[i];
+        if (wd != 0.f) g = fmaf(wd, p, g);
+        float m = b1 * ck.m[i] + (1.f - b1) * g;
+        float v = b2 * ck.v[i] + (1.f - b2) * g * g;
+        ck.m[i] = m; ck.v[i] = v;
+        float denom = sqrtf(v) / bc2_sqrt + eps;
+        ck.p[i] = p - step_size * (m / denom);
+    }
+}
+__global__ void adam_advance_kernel(AdamHyper* hy) { hy->step += 1; }
+
+// -------------------------------------------------------------------------------------------------
+// weight packing: fp32 parameter -> bf16 [tap][O][I] operand of conv3x3_mma
+//   dst[(tap*O + o)*I + i] = src[o*s_o + i*s_i + tap']   tap' = flip ? 8 - tap : tap
+// -------------------------------------------------------------------------------------------------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I, int s_o, int s_i, int flip) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 9 * O * I) return;
+    int i = idx % I;
+    int o = (idx / I) % O;
+    int tap = idx / (I * O);
+    int ts = flip ? 8 - tap : tap;
+    dst[idx] = __float2bfloat16_rn(src[(size_t)o * s_o + (size_t)i * s_i + ts]);
+}
+// generic 2-D cast with optional transpose: dst[r][c] = src[r*s_r + c*s_c]
+__global__ void pack_matrix_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int rows, int cols, int s_r, int s_c) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    int c = idx % cols, r = idx / cols;
+    dst[idx] = __float2bfloat16_rn(src[(size_t)r * s_r + (size_t)c * s_c]);
+}
+// head conv weights: dst[tap][c] = src[c*s_c + tap'] (fp32)
+__global__ void pack_head_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int s_c, int flip) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 288) return;
+    int c = idx & 31, tap = idx >> 5;
+    dst[idx] = src[(size_t)c * s_c + (flip ? 8 - tap : tap)];
+}
+// stem-shaped fp32 weights for the 1->32 data gradient of prdct.3: dst[c][tap] = src[c*9 + (8 - tap)]
+__global__ void pack_flip9_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 9) return;
+    int tap = idx % 9, c = idx / 9;
+    dst[idx] = src[(size_t)c * 9 + (8 - tap)];
+}
+
+// misc
+__global__ void fill_kernel(float* p, float v, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ s, float* __restrict__ d, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = __bfloat162float(s[i]);
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = __float2bfloat16_rn(s[i]);
+}
+
+}  // namespace ptta

@@ -1,0 +1,433 @@
+"""Drop-in mirror of the reference's model facade for the TTA path, backed by the native engine.
+
+Mirrors (same names, argument meaning and error behaviour):
+  * `ExternalModel_Adapt`  -- src/external_model_adapt.py:29-660
+  * `MsgChnModel_Adapt`    -- src/msg_chn_model_adapt.py:12-556
+  * `OutlierRemoval`       -- src/net_utils.py:750-811
+The reference driver's call sequence (src/tta_main.py:309-354, 583-633) works unchanged:
+
+    model = ExternalModel_Adapt('msg_chn', min_predict_depth, max_predict_depth, max_input_depth, device=...)
+    model._prepare_head('meta_selfsup_seq_2layers_ema'); model.restore_model(ckpt)
+    optimizer = torch.optim.Adam(model.adapt_parameters('meta'), lr=...)
+    out, emb, ref = model.forward(image=..., sparse_depth=..., loss_type='adapt_meta_selfsup_seq_ema_reverse')
+    loss, info = model.compute_loss(input_rgb=..., output_depth=out, ..., loss_type='adapt')
+    optimizer.zero_grad(); loss.backward(); optimizer.step()
+
+plus one extension, `tta_step(...)`, which runs the whole per-frame step (outlier removal, forward,
+losses, backward, Adam) inside the library without returning to Python.  All arithmetic is done by
+libptta_b200.so; torch supplies device memory, streams and the autograd glue only."""
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+from .engine import MsgChnEngine
+
+ADAPT_LOSS_TYPE = 'adapt_meta_selfsup_seq_ema_reverse'
+
+
+class OutlierRemoval(object):
+    """src/net_utils.py:750-811 -- 7x7 min-filter outlier rejection on the sparse depth."""
+
+    def __init__(self, kernel_size=7, threshold=1.5):
+        self.kernel_size = kernel_size
+        self.threshold = threshold
+
+    def remove_outliers(self, sparse_depth, validity_map=None):
+        # the validity map is a function of the sparse depth (src/tta_main.py:583-586); it is recomputed in-kernel
+        return ops.outlier_removal(sparse_depth.contiguous(), self.kernel_size, self.threshold)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parameter construction (shapes / initialisers of network_exp_msg_chn_adapt.py:166-335, 1022-1098)
+# ---------------------------------------------------------------------------------------------------------
+def _conv_init(sd, name, cout, cin, transposed=False):
+    w = torch.empty((cin, cout, 3, 3) if transposed else (cout, cin, 3, 3))
+    torch.nn.init.xavier_normal_(w)                      # :188-194
+    sd[name + '.weight'] = w
+    sd[name + '.bias'] = torch.full((cout,), 0.01)
+
+
+def _bn_init(sd, name, c):
+    sd[name + '.weight'] = torch.ones(c)
+    sd[name + '.bias'] = torch.zeros(c)
+    sd[name + '.running_mean'] = torch.zeros(c)
+    sd[name + '.running_var'] = torch.ones(c)
+    sd[name + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+
+
+def _default_conv_init(w):
+    torch.nn.init.kaiming_uniform_(w, a=math.sqrt(5))    # nn.Conv2d / nn.Linear default
+    return w
+
+
+def _linear_init(sd, name, cout, cin):
+    sd[name + '.weight'] = _default_conv_init(torch.empty(cout, cin))
+    bound = 1.0 / math.sqrt(cin)
+    sd[name + '.bias'] = torch.empty(cout).uniform_(-bound, bound)
+
+
+def _mlp_init(sd, name, dim, out, hidden):
+    _linear_init(sd, name + '.0', hidden, dim)
+    _bn_init(sd, name + '.1', hidden)
+    _linear_init(sd, name + '.3', out, hidden)
+
+
+def build_base_state():
+    """network_adapt.__init__ (network_exp_msg_chn_adapt.py:313-335): three depth encoder/decoder pairs + RGB encoder."""
+    sd = OrderedDict()
+
+    def encoder(prefix, cin, n_enc):
+        _conv_init(sd, prefix + '.init.0', 32, cin)
+        _conv_init(sd, prefix + '.init.2', 32, 32)
+        for k in range(1, n_enc + 1):
+            _conv_init(sd, '%s.enc%d.1' % (prefix, k), 32, 32)
+            _conv_init(sd, '%s.enc%d.3' % (prefix, k), 32, 32)
+
+    def decoder(prefix):
+        for blk in ('dec2', 'dec1'):
+            _conv_init(sd, '%s.%s.1' % (prefix, blk), 32, 32, transposed=True)
+            _conv_init(sd, '%s.%s.3' % (prefix, blk), 32, 32)
+        _conv_init(sd, prefix + '.prdct.1', 32, 32)
+        _conv_init(sd, prefix + '.prdct.3', 1, 32)
+
+    encoder('rgb_encoder', 3, 4)
+    encoder('depth_encoder1', 1, 2); decoder('depth_decoder1')
+    encoder('depth_encoder2', 2, 2); decoder('depth_decoder2')
+    encoder('depth_encoder3', 2, 2); decoder('depth_decoder3')
+    return sd
+
+
+def add_head_state(sd, mode):
+    """network_adapt._prepare_head (network_exp_msg_chn_adapt.py:1022-1087)."""
+    if 'selfsup' in mode:
+        _mlp_init(sd, 'proj', 32, 512, 512)
+        if 'ema' in mode:
+            for k in [k for k in sd if k.startswith('proj.')]:
+                sd['proj_t.' + k[5:]] = sd[k].clone()
+        _mlp_init(sd, 'pred', 512, 512, 512)
+    if 'meta' in mode:
+        if 'seq' not in mode:
+            raise NotImplementedError('only the sequential ("seq") meta layer is implemented: %s' % mode)
+        if '1layer' in mode:
+            w = torch.empty(32, 32, 3, 3)
+            torch.nn.init.kaiming_normal_(w, mode='fan_out', nonlinearity='relu')
+            sd['conv1_rgb_meta.weight'] = w
+            sd['conv1_rgb_meta.bias'] = torch.empty(32).uniform_(-1.0 / math.sqrt(288), 1.0 / math.sqrt(288))
+        elif '2layers' in mode:
+            p = 'conv1_rgb_meta.conv1_meta'
+            sd[p + '.0.0.weight'] = _default_conv_init(torch.empty(128, 32, 3, 3))
+            _bn_init(sd, p + '.0.1', 128)
+            sd[p + '.1.weight'] = _default_conv_init(torch.empty(32, 128, 3, 3))
+            sd[p + '.1.bias'] = torch.empty(32).uniform_(-1.0 / math.sqrt(1152), 1.0 / math.sqrt(1152))
+            _bn_init(sd, p + '.2', 32)
+        else:
+            raise NotImplementedError(mode)
+    return sd
+
+
+_PARAM_SUFFIX = ('.weight', '.bias')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# autograd glue: the engine computes every gradient; these Functions only route them
+# ---------------------------------------------------------------------------------------------------------
+class _ForwardFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wrapper, image, sparse_depth, *params):
+        eng = wrapper._engine_for(image)
+        eng.pack_adapted()                     # the optimizer may have stepped the fp32 masters since the last call
+        eng.forward(image, sparse_depth, None, True)     # the facade already clamped the sparse depth
+        ctx.wrapper, ctx.eng, ctx.n_params = wrapper, eng, len(params)
+        n, h, w = eng.n, eng.h, eng.w
+        out = eng.tensor('output').view(n, 1, h, w).clone()
+        emb, ref = eng.tensor('emb').view(-1, 512), eng.tensor('ref').view(-1, 512)
+        ctx.mark_non_differentiable(emb)       # emb = pred(proj(z_zero.detach())): no path to the adapted tensors
+        return out, emb, ref
+
+    @staticmethod
+    def backward(ctx, g_out, g_emb, g_ref):
+        eng, wrapper = ctx.eng, ctx.wrapper
+        go, gr = eng.tensor('g_output'), eng.tensor('g_ref')
+        if g_out is not None and g_out.data_ptr() != go.data_ptr():
+            go.view(-1).copy_(g_out.reshape(-1))
+        if g_ref is not None and g_ref.data_ptr() != gr.data_ptr():
+            gr.view(-1).copy_(g_ref.reshape(-1))
+        eng.network_backward()
+        grads = [wrapper._grad_views[k].clone() for k in wrapper._adapt_names]
+        return (None, None, None) + tuple(grads)
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, output_depth, embedding, reference, image_raw, sparse_depth, validity_map, cap, w_sd, w_sm, w_cos):
+        # the engine evaluates the loss on its own copies of (output, emb, ref) from the forward that produced them
+        eng.loss(image_raw, sparse_depth, validity_map, cap, w_sd, w_sm, w_cos)
+        ctx.eng = eng
+        scal = eng.tensor('losses').view(-1)
+        loss, parts = scal[0].clone(), scal[1:4].clone()
+        ctx.mark_non_differentiable(parts)
+        return loss, parts
+
+    @staticmethod
+    def backward(ctx, g_loss, g_parts):
+        eng = ctx.eng
+        eng.loss_backward(float(g_loss))       # a host read of the upstream scalar (1.0 for loss.backward())
+        n, h, w = eng.n, eng.h, eng.w
+        return (None, eng.tensor('g_output').view(n, 1, h, w), None, eng.tensor('g_ref').view(-1, 512),
+                None, None, None, None, None, None, None)
+
+
+class MsgChnModel_Adapt(object):
+    """src/msg_chn_model_adapt.py -- MSG-CHN wrapper (state dict, adapted-parameter selection, checkpoints)."""
+
+    def __init__(self, max_predict_depth=100.0, device=torch.device('cuda')):
+        self.max_predict_depth = max_predict_depth
+        self.device = torch.device(device)
+        self.training = True
+        self.prepare_mode = None
+        self._sd = build_base_state()
+        self._engines = {}
+        self._adapt_names = []
+        self._params = None
+        self._grad_views = {}
+        self._flat = {}
+        self.img_scale = (1.0, 1.0, 1.0)
+        self.img_shift = (0.0, 0.0, 0.0)
+        self._adam_step = 0
+
+    # -- construction ---------------------------------------------------------------------------------
+    def _prepare_head(self, mode=''):
+        self.prepare_mode = mode
+        add_head_state(self._sd, mode)
+        self._materialise()
+
+    def _materialise(self):
+        """Move the state to the device; adapted tensors become views of one flat fp32 buffer (as do their
+        gradients and Adam moments) so that the fused Adam kernel covers them in one launch."""
+        if self.device.type != 'cuda':
+            raise RuntimeError('the TTA step runs on CUDA only (no CPU fallback); got device %s' % self.device)
+        for k, v in list(self._sd.items()):
+            want = torch.int64 if k.endswith('num_batches_tracked') else torch.float32
+            self._sd[k] = v.detach().to(self.device, want).contiguous()
+        self._adapt_names = [k for k in self._sd if 'meta' in k and k.endswith(_PARAM_SUFFIX)]   # msg_chn_model_adapt.py:392-396
+        total = sum(self._sd[k].numel() for k in self._adapt_names)
+        self._flat = {name: torch.zeros(total, dtype=torch.float32, device=self.device) for name in ('param', 'grad', 'm', 'v')}
+        self._grad_views, self._m_views, self._v_views = {}, {}, {}
+        self._param_objs = OrderedDict()
+        off = 0
+        for k in self._adapt_names:
+            t = self._sd[k]
+            n = t.numel()
+            view = self._flat['param'][off:off + n].view(t.shape)
+            view.copy_(t)
+            p = torch.nn.Parameter(view, requires_grad=True)
+            self._param_objs[k] = p
+            self._sd[k] = p.data
+            self._grad_views[k] = self._flat['grad'][off:off + n].view(t.shape)
+            self._m_views[k] = self._flat['m'][off:off + n].view(t.shape)
+            self._v_views[k] = self._flat['v'][off:off + n].view(t.shape)
+            off += n
+        for e in self._engines.values():
+            e.close()
+        self._engines = {}
+
+    def _engine_for(self, image):
+        if self.prepare_mode is None:
+            raise RuntimeError('_prepare_head(mode) must be called before forward (src/tta_main.py:322)')
+        key = (image.shape[0], image.shape[2], image.shape[3])
+        eng = self._engines.get(key)
+        if eng is None:
+            n, h, w = key
+            if h % 16 or w % 16:
+                raise NotImplementedError('H, W must be multiples of 16: the pad + flip ensembling of '
+                                          'src/msg_chn_model_adapt.py:58-125 is not implemented on the native path yet')
+            state = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in self._sd.items()}
+            eng = MsgChnEngine(n, h, w, self.prepare_mode, state, self._grad_views, self._m_views, self._v_views)
+            self._engines[key] = eng
+        return eng
+
+    # -- reference API ----------------------------------------------------------------------------------
+    def forward(self, image, sparse_depth, intrinsics=None, crop_mask=None, loss_type='pretrain'):
+        image = image.contiguous()
+        sparse_depth = sparse_depth.contiguous()
+        if self.training and 'adapt' in loss_type:
+            out, emb, ref = _ForwardFn.apply(self, image, sparse_depth, *self._param_objs.values())
+            return out, emb, ref
+        eng = self._engine_for(image)
+        eng.pack_adapted()
+        with torch.no_grad():
+            eng.forward(image, sparse_depth, None, False)
+            return eng.tensor('output').view(eng.n, 1, eng.h, eng.w).clone()
+
+    def parameters(self):
+        return [torch.nn.Parameter(v, requires_grad=False) if k not in self._param_objs else self._param_objs[k]
+                for k, v in self._sd.items() if k.endswith(_PARAM_SUFFIX)]
+
+    def adapt_parameters(self, mode=''):
+        if mode != 'meta':
+            raise NotImplementedError('adapt mode %r: only "meta" is on the native path (msg_chn_model_adapt.py:392-396)' % mode)
+        return torch.nn.ParameterList(list(self._param_objs.values()))
+
+    def train(self):
+        self.training = True
+
+    def eval(self):
+        self.training = False
+
+    def state_dict(self):
+        return OrderedDict((k, (v.detach() if isinstance(v, torch.Tensor) else v)) for k, v in self._sd.items())
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [k for k in self._sd if k not in sd]
+        unexpected = [k for k in sd if k not in self._sd]
+        if strict and (missing or unexpected):
+            raise RuntimeError('Error(s) in loading state_dict: missing %s, unexpected %s' % (missing[:5], unexpected[:5]))
+        for k in self._sd:
+            if k in sd:
+                src = sd[k]
+                if tuple(src.shape) != tuple(self._sd[k].shape):
+                    raise RuntimeError('size mismatch for %s: %s vs %s' % (k, tuple(src.shape), tuple(self._sd[k].shape)))
+                self._sd[k].copy_(src.to(self._sd[k].device, self._sd[k].dtype))
+        for e in self._engines.values():
+            e.rebind()
+
+    def restore_model(self, restore_path, optimizer=None):
+        ckpt = torch.load(restore_path, map_location=self.device, weights_only=False)
+        self.load_state_dict(ckpt['net'])
+        if optimizer is not None and 'optimizer' in ckpt:
+            optimizer.load_state_dict(ckpt['optimizer'])
+        return optimizer, ckpt.get('train_step', 0)
+
+    def save_model(self, checkpoint_path, step, optimizer, meanvar=None):
+        ckpt = {'net': OrderedDict((k, v.clone()) for k, v in self.state_dict().items()), 'train_step': step}
+        if optimizer is not None:
+            ckpt['optimizer'] = optimizer.state_dict()
+        torch.save(ckpt, checkpoint_path)
+
+    def convert_syncbn(self, apex=False):
+        # single process per model: BatchNorm statistics are local (the reference's SyncBN is numerically plain BN at world size 1)
+        return None
+
+    def distributed_data_parallel(self, rank=0):
+        return None
+
+    def data_parallel(self):
+        return None
+
+    def to(self, device):
+        self.device = torch.device(device)
+        if self.prepare_mode is not None:
+            self._materialise()
+
+
+class ExternalModel_Adapt(object):
+    """src/external_model_adapt.py:29-660, restricted to the TTA hot path (MSG-CHN; 'adapt' losses)."""
+
+    def __init__(self, model_name, min_predict_depth, max_predict_depth, max_input_depth=None, offset=False, from_scratch=False,
+                 dataset_name=None, device=torch.device('cuda')):
+        self.model_name = model_name
+        self.dataset_name = dataset_name
+        self.device = torch.device(device)
+        self.max_predict_depth = max_predict_depth
+        self.max_input_depth = max_input_depth
+        if model_name == 'msg_chn':
+            self.model = MsgChnModel_Adapt(device=self.device, max_predict_depth=max_predict_depth)
+        elif model_name == 'nlspn' or 'costdcnet' in model_name:
+            raise NotImplementedError('%s has no native back-end yet (DESIGN.md, scope table)' % model_name)
+        else:
+            raise ValueError('Unsupported depth completion model: {}'.format(model_name))
+
+    def forward(self, image, sparse_depth, crop_mask=None, intrinsics=None, loss_type='pretrain'):
+        if self.max_input_depth is not None:
+            sparse_depth = torch.clamp(sparse_depth, 0, self.max_input_depth)     # src/external_model_adapt.py:103-108
+        return self.model.forward(image=image, sparse_depth=sparse_depth, intrinsics=intrinsics, crop_mask=crop_mask,
+                                  loss_type=loss_type)
+
+    def compute_loss(self, input_rgb, output_depth=None, output_depth_ref=None, ground_truth=None, intrinsincs=None,
+                     sparse_depth=None, reference_depth=None, validity_map=None, embedding=None, reference=None, epoch=0,
+                     max_input_depth=None, max_predict_depth=100.0, w_loss_sparse_depth=0.0, w_loss_smoothness=0.0,
+                     w_loss_robust=1.0, w_loss_cos=1.0, dataset_name=None, loss_type='pretrain'):
+        if 'adapt' in loss_type and not any(s in loss_type for s in ('prepare', 'cotta', 'init', '_bn')):
+            return self.adapt_loss(input_rgb=input_rgb, output_depth=output_depth, sparse_depth=sparse_depth,
+                                   validity_map=validity_map, embedding=embedding, reference=reference,
+                                   w_loss_sparse_depth=w_loss_sparse_depth, w_loss_smoothness=w_loss_smoothness,
+                                   w_loss_cos=w_loss_cos)
+        raise NotImplementedError('loss_type %r is outside the TTA hot path (DESIGN.md, scope table)' % loss_type)
+
+    def adapt_loss(self, input_rgb, output_depth, sparse_depth, validity_map, embedding, reference, w_loss_sparse_depth=1.0,
+                   w_loss_smoothness=1.0, w_loss_cos=1.0):
+        """src/external_model_adapt.py:371-441 (the clamp of :191-193 is applied inside the loss kernel)."""
+        eng = self.model._engine_for(input_rgb)
+        loss, parts = _LossFn.apply(eng, output_depth, embedding, reference, input_rgb.contiguous(), sparse_depth.contiguous(),
+                                    validity_map.contiguous(), self.max_input_depth, float(w_loss_sparse_depth),
+                                    float(w_loss_smoothness), float(w_loss_cos))
+        info = {'loss': loss.detach(), 'loss_sparse_depth': parts[0], 'loss_smooth': parts[1], 'loss_cos': parts[2]}
+        return loss, info
+
+    # -- the fused fast path (extension) ---------------------------------------------------------------------
+    def set_image_normalization(self, scale, shift):
+        """network input = raw_image * scale[c] + shift[c]  (src/transforms.py:669-712; (1/255, 0) for range [0,1])."""
+        self.model.img_scale, self.model.img_shift = tuple(scale), tuple(shift)
+
+    def tta_step(self, image_raw, sparse_depth, learning_rate, w_loss_sparse_depth=1.0, w_loss_smoothness=1.0, w_loss_cos=1.0,
+                 betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, graph=False):
+        """One whole adaptation step (src/tta_main.py:583-633) in a single library call; returns nothing -- read
+        `last_losses()` when the values are needed (that read synchronises)."""
+        eng = self.model._engine_for(image_raw)
+        hyper = (learning_rate, betas, eps, weight_decay)
+        if getattr(eng, '_hyper', None) != hyper:
+            eng.set_adam(learning_rate, betas, eps, weight_decay, step_count=-1)
+            eng._hyper = hyper
+        eng.tta_step(image_raw, sparse_depth, self.max_input_depth, w_loss_sparse_depth, w_loss_smoothness, w_loss_cos,
+                     self.model.img_scale, self.model.img_shift, graph=graph)
+        self._last_engine = eng
+
+    def last_losses(self):
+        return self._last_engine.read_losses()
+
+    def last_output(self):
+        e = self._last_engine
+        return e.tensor('output').view(e.n, 1, e.h, e.w)
+
+    # -- plumbing identical to the reference ---------------------------------------------------------------------
+    def parameters(self):
+        return self.model.parameters()
+
+    def _prepare_head(self, mode=''):
+        self.model._prepare_head(mode=mode)
+
+    def adapt_parameters(self, mode=''):
+        return self.model.adapt_parameters(mode=mode)
+
+    def train(self, meta=False, prepare=False):
+        self.model.train()
+
+    def eval(self):
+        self.model.eval()
+
+    def to(self, device):
+        self.device = torch.device(device)
+        self.model.to(device)
+
+    def data_parallel(self):
+        self.model.data_parallel()
+
+    def distributed_data_parallel(self, rank):
+        self.model.distributed_data_parallel(rank)
+
+    def restore_model(self, restore_path, optimizer=None, learning_schedule=None, learning_rates=None, n_step_per_epoch=None):
+        return self.model.restore_model(restore_path=restore_path, optimizer=optimizer)
+
+    def save_model(self, checkpoint_path, step, optimizer, meanvar=None):
+        self.model.save_model(checkpoint_path, step, optimizer, meanvar)
+
+    def convert_syncbn(self, apex=False):
+        self.model.convert_syncbn(apex)
+
+    def state_dict(self):
+        return self.model.state_dict()
+
+    def load_state_dict(self, sd, strict=True):
+        self.model.load_state_dict(sd, strict)

@@ -1,0 +1,183 @@
+"""Thin torch-tensor wrappers over the stand-alone operators of libptta_b200.so.
+
+Layouts: feature maps are NHWC bf16 tensors [N,H,W,C]; single-channel maps fp32 [N,H,W] (or [N,1,H,W]);
+images fp32 NCHW.  No operator here has a PyTorch fallback."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, c_void_p
+
+MODE_S1, MODE_S2, MODE_T2 = 0, 1, 2
+PRO_NONE, PRO_RELU, PRO_BN_LEAKY = 0, 1, 2
+MASK_NONE, MASK_RELU, MASK_BN_LEAKY = 0, 1, 2
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need(t, dtype, name):
+    if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+        raise TypeError('%s must be a contiguous CUDA %s tensor' % (name, dtype))
+
+
+def outlier_removal(sparse_depth, kernel_size=7, threshold=1.5):
+    """validity map + OutlierRemoval.remove_outliers (src/tta_main.py:583-586, src/net_utils.py:766-811).
+    Returns (filtered_sparse_depth, filtered_validity_map), same shape as the input."""
+    _need(sparse_depth, torch.float32, 'sparse_depth')
+    n = sparse_depth.shape[0]
+    h, w = sparse_depth.shape[-2:]
+    d = torch.empty_like(sparse_depth)
+    v = torch.empty_like(sparse_depth)
+    check(_lib.lib().ptta_outlier_removal(ptr(sparse_depth), ptr(d), ptr(v), n, h, w, kernel_size, threshold, _stream()), 'outlier_removal')
+    return d, v
+
+
+def pyramid(depth, max_input_depth=None):
+    """clamp + validity-normalised /2 and /4 average pooling (network_exp_msg_chn_adapt.py:479,487,492)."""
+    _need(depth, torch.float32, 'depth')
+    n = depth.shape[0]
+    h, w = depth.shape[-2:]
+    dc = torch.empty_like(depth)
+    d2 = torch.empty((n, 1, h // 2, w // 2), dtype=torch.float32, device=depth.device)
+    d4 = torch.empty((n, 1, h // 4, w // 4), dtype=torch.float32, device=depth.device)
+    cap = -1.0 if max_input_depth is None else float(max_input_depth)
+    check(_lib.lib().ptta_pyramid(ptr(depth), ptr(dc), ptr(d2), ptr(d4), n, h, w, cap, 0 if max_input_depth is None else 1, _stream()),
+          'pyramid')
+    return dc, d2, d4
+
+
+def pack_conv_weight(weight, role):
+    """fp32 Conv2d [Cout,Cin,3,3] / ConvTranspose2d [Cin,Cout,3,3] weight -> bf16 [9][O][I] operand.
+    role: 'conv_fwd', 'conv_dgrad_s1', 'conv_dgrad_s2', 'convT_fwd', 'convT_dgrad'."""
+    _need(weight, torch.float32, 'weight')
+    a, b = weight.shape[0], weight.shape[1]
+    if role == 'conv_fwd':
+        o, i, so, si, flip = a, b, b * 9, 9, 0
+    elif role == 'conv_dgrad_s1':
+        o, i, so, si, flip = b, a, 9, b * 9, 1
+    elif role == 'conv_dgrad_s2':
+        o, i, so, si, flip = b, a, 9, b * 9, 0
+    elif role == 'convT_fwd':          # weight [Cin, Cout, 3, 3]
+        o, i, so, si, flip = b, a, 9, b * 9, 0
+    elif role == 'convT_dgrad':
+        o, i, so, si, flip = a, b, b * 9, 9, 0
+    else:
+        raise ValueError(role)
+    out = torch.empty((9, o, i), dtype=torch.bfloat16, device=weight.device)
+    check(_lib.lib().ptta_pack_conv_weight(ptr(weight), ptr(out), o, i, so, si, flip, _stream()), 'pack_conv_weight')
+    return out
+
+
+def conv3x3(x, wpack, bias=None, mode=MODE_S1, prologue=PRO_NONE, pro_scale=None, pro_shift=None, slope=0.2,
+            mask=None, mask_mode=MASK_NONE, mask_scale=None, mask_shift=None, add=None):
+    _need(x, torch.bfloat16, 'x')
+    _need(wpack, torch.bfloat16, 'wpack')
+    n, h, w, cin = x.shape
+    cout = wpack.shape[1]
+    if wpack.shape[2] != cin:
+        raise ValueError('weight operand expects %d input channels, x has %d' % (wpack.shape[2], cin))
+    if mode == MODE_S1:
+        ho, wo = h, w
+    elif mode == MODE_S2:
+        ho, wo = (h + 1) // 2, (w + 1) // 2
+    else:
+        ho, wo = 2 * h, 2 * w
+    out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().ptta_conv3x3(ptr(x), ptr(out), ptr(wpack), ptr(bias), n, h, w, cin, cout, mode, prologue, ptr(pro_scale),
+                                  ptr(pro_shift), slope, ptr(mask), mask_mode, ptr(mask_scale), ptr(mask_shift), ptr(add), _stream()),
+          'conv3x3')
+    return out
+
+
+def conv3x3_wgrad(x, gout, prologue=PRO_NONE, pro_scale=None, pro_shift=None, slope=0.2):
+    _need(x, torch.bfloat16, 'x')
+    _need(gout, torch.bfloat16, 'gout')
+    n, h, w, cin = x.shape
+    cout = gout.shape[3]
+    L = _lib.lib()
+    ws = torch.empty(L.ptta_conv3x3_wgrad_workspace_bytes(n, h, w, cin, cout), dtype=torch.uint8, device=x.device)
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=x.device)
+    check(L.ptta_conv3x3_wgrad(ptr(x), ptr(gout), ptr(dw), ptr(ws), n, h, w, cin, cout, prologue, ptr(pro_scale), ptr(pro_shift), slope,
+                               _stream()), 'conv3x3_wgrad')
+    return dw
+
+
+def stem_conv(planes, weight, bias=None, scale=None, shift=None, mask=None):
+    """planes: list of 1..3 fp32 tensors [N,H,W] (each contiguous) -> NHWC bf16 [N,H,W,32]."""
+    cin = len(planes)
+    n, h, w = planes[0].shape
+    for p in planes:
+        _need(p, torch.float32, 'plane')
+    _need(weight, torch.float32, 'weight')
+    pl = (ctypes.c_void_p * 3)(*[planes[min(k, cin - 1)].data_ptr() for k in range(3)])
+    st = (ctypes.c_longlong * 3)(*[h * w] * 3)
+    sc = (ctypes.c_float * 3)(*(list(scale) if scale is not None else [1.0] * cin) + [1.0] * (3 - cin))
+    sh = (ctypes.c_float * 3)(*(list(shift) if shift is not None else [0.0] * cin) + [0.0] * (3 - cin))
+    out = torch.empty((n, h, w, 32), dtype=torch.bfloat16, device=weight.device)
+    check(_lib.lib().ptta_stem_conv(pl, st, sc, sh, cin, ptr(weight), ptr(bias), ptr(mask), ptr(out), n, h, w, _stream()), 'stem_conv')
+    return out
+
+
+def head_conv(x, weight_9x32, bias=0.0, add=None, relu_in=True, out=None, accumulate=False):
+    _need(x, torch.bfloat16, 'x')
+    _need(weight_9x32, torch.float32, 'weight')
+    n, h, w, _ = x.shape
+    if out is None:
+        out = torch.empty((n, h, w), dtype=torch.float32, device=x.device)
+    check(_lib.lib().ptta_head_conv(ptr(x), ptr(weight_9x32), float(bias), ptr(add), ptr(out), n, h, w, 1 if relu_in else 0,
+                                    1 if accumulate else 0, _stream()), 'head_conv')
+    return out
+
+
+def up2_1ch(a, b=None, c=None):
+    _need(a, torch.float32, 'a')
+    n, h, w = a.shape
+    out = torch.empty((n, 2 * h, 2 * w), dtype=torch.float32, device=a.device)
+    check(_lib.lib().ptta_up2_1ch(ptr(a), ptr(b), ptr(c), ptr(out), n, h, w, _stream()), 'up2_1ch')
+    return out
+
+
+def up2_1ch_adjoint(g_hi):
+    _need(g_hi, torch.float32, 'g_hi')
+    n, H, W = g_hi.shape
+    out = torch.empty((n, H // 2, W // 2), dtype=torch.float32, device=g_hi.device)
+    check(_lib.lib().ptta_up2_1ch_adjoint(ptr(g_hi), ptr(out), n, H // 2, W // 2, 0, _stream()), 'up2_1ch_adjoint')
+    return out
+
+
+def add_up2_c32(x, half):
+    _need(x, torch.bfloat16, 'x')
+    _need(half, torch.bfloat16, 'half')
+    n, h, w, _ = half.shape
+    out = torch.empty_like(x)
+    check(_lib.lib().ptta_add_up2_c32(ptr(x), ptr(half), ptr(out), n, h, w, _stream()), 'add_up2_c32')
+    return out
+
+
+def up2_c32_adjoint(g_hi):
+    _need(g_hi, torch.bfloat16, 'g_hi')
+    n, H, W, c = g_hi.shape
+    out = torch.empty((n, H // 2, W // 2, c), dtype=torch.bfloat16, device=g_hi.device)
+    check(_lib.lib().ptta_up2_c32_adjoint(ptr(g_hi), ptr(out), n, H // 2, W // 2, 0, _stream()), 'up2_c32_adjoint')
+    return out
+
+
+def gemm_bf16(a, b, bias=None):
+    """a [M,K] bf16, b [N,K] bf16 (nn.Linear weight layout) -> [M,N] bf16"""
+    _need(a, torch.bfloat16, 'a')
+    _need(b, torch.bfloat16, 'b')
+    m, k = a.shape
+    n = b.shape[0]
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    check(_lib.lib().ptta_gemm_bf16(ptr(a), ptr(b), ptr(out), ptr(bias), m, n, k, _stream()), 'gemm_bf16')
+    return out
+
+
+def adam_flat(param, grad, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        _need(t, torch.float32, 'adam tensor')
+    check(_lib.lib().ptta_adam_flat(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, betas[0], betas[1], eps,
+                                    weight_decay, step, _stream()), 'adam_flat')
