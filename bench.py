@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the ProxyTTA per-frame adaptation step (BASELINE.json: adapted frames/s, fwd+bwd+update, 352x1216).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload kitti|void] [--batch B]
+
+One "step" = src/tta_main.py:583-633 of the reference for one batch: outlier removal, forward (real + zero-image
+branch + proxy heads), the three losses, backward to the adapted meta layer, Adam.  Workload at N=1 = BASELINE.json
+configs[1]: MSG-CHN `meta_selfsup_seq_2layers_ema`, batch 1, synthetic KITTI-shape 3x352x1216 frames, ~5 % sparse depth,
+continual adaptation over consecutive frames of one synthetic sequence.  With N GPUs every rank adapts its own model on
+its own sequence shard (no collective; "scaling": "weak").
+
+Printed JSON (rank 0, one line): the contract keys + `roofline` (dominant kernel, timed alone with CUDA events inside
+this script), `cpu_baseline` (the oracle port on the host cores, bounded sample), `e2e` (same metric through the
+facade with HOST pinned inputs, H2D inside the timed region, loss read back D2H every step) and `clocks`.
+
+`--impl reference`: the reference's own CPU path -- here the oracle port of it (the reference is PyTorch-eager Python
+that cannot travel to the GPU box; oracle/msgchn_oracle.py is pinned against its outputs, tests/golden/) -- timed on
+all host cores on the same workload."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+WORKLOADS = {
+    # name: (H, W, dataset, prepare_mode, lr, max_input_depth)
+    'kitti': (352, 1216, 'kitti', 'meta_selfsup_seq_2layers_ema', 1e-4, 80.0),
+    'void': (480, 640, 'void', 'meta_selfsup_seq_1layer_ema', 3e-3, 8.0),
+}
+W_SD, W_SM, W_COS = 1.0, 1.0, 0.1
+RING = 8                      # distinct frames cycled through (device-resident for `value`, pinned host for `e2e`)
+CONV_GFLOP_R1 = 2 * 9 * 32 * 32 * 352 * 1216 / 1e9      # 32->32 3x3 s1 @352x1216: SURVEY.md section 8(d) / Appendix A
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return {'hbm_gbs': p['hbm_gbs'], 'bf16_tflops': p['bf16_tflops'], 'bf16_tflops_sustained': p.get('bf16_tflops_sustained'),
+                'source': 'measured (MEASURED_PEAKS.json)'}
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.samples[0][1]), 'reasons': sorted(reasons),
+                'samples': len(self.samples)}
+
+
+def make_frames(workload, batch, count, seq_seed):
+    from oracle import msgchn_oracle as O          # synthetic-input generator only
+    h, w, dataset = WORKLOADS[workload][:3]
+    frames = []
+    for t in range(count):
+        image, sparse, _ = O.synthetic_frame(seq_seed, t, batch, h, w, dataset)
+        frames.append((image.contiguous(), sparse.contiguous()))
+    return frames
+
+
+def make_checkpoint(workload):
+    from oracle import msgchn_oracle as O
+    return O.make_synthetic_checkpoint(0, WORKLOADS[workload][3])
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port of the reference step on all host cores."""
+    from oracle import msgchn_oracle as O
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = make_checkpoint(args.workload)
+    names = O.adapt_parameter_names(sd, 'meta')
+    state = O.AdamState(names, sd)
+    frames = make_frames(args.workload, args.batch, min(RING, args.steps + args.warmup), 1)
+    for i in range(args.warmup):
+        O.tta_step(sd, state, *frames[i % len(frames)], lr=lr, w_sd=W_SD, w_sm=W_SM, w_cos=W_COS, max_input_depth=cap)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        O.tta_step(sd, state, *frames[(args.warmup + i) % len(frames)], lr=lr, w_sd=W_SD, w_sm=W_SM, w_cos=W_COS, max_input_depth=cap)
+    dt = time.perf_counter() - t0
+    value = args.batch * args.steps / dt
+    line = {
+        'impl': 'reference', 'metric': 'adapted_frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args),
+        'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d full-size TTA steps (%dx%dx%d) of the oracle port, torch %s CPU fp32, after %d warm-up' % (
+                             args.steps, args.batch, h, w, torch.__version__, args.warmup)},
+        'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
+    return {'workload': 'MSG-CHN ProxyTTA continual adaptation, synthetic %s-shape %dx3x%dx%d frames, prepare_mode %s, adapt_mode meta, '
+                        'lr %g, w_sd/w_smooth/w_cos %g/%g/%g, Adam(0.9,0.999,1e-8)' % (dataset.upper(), args.batch, h, w, mode, lr, W_SD, W_SM,
+                                                                                       W_COS),
+            'batch_per_gpu': args.batch, 'parallelism': 'independent sequence shard per GPU (no collective)',
+            'l2': 'ring of %d distinct frames; per-step working set (~1.5 GB of activations) exceeds the 126 MB L2' % RING}
+
+
+def cpu_baseline_sample(args, budget_s=25.0):
+    """oracle port on the host cores, bounded sample (1 warm-up + up to 3 timed full-size steps)"""
+    from oracle import msgchn_oracle as O
+    h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = make_checkpoint(args.workload)
+    names = O.adapt_parameter_names(sd, 'meta')
+    state = O.AdamState(names, sd)
+    frames = make_frames(args.workload, args.batch, 2, 1)
+    O.tta_step(sd, state, *frames[0], lr=lr, w_sd=W_SD, w_sm=W_SM, w_cos=W_COS, max_input_depth=cap)
+    n, t0 = 0, time.perf_counter()
+    while n < 3 and (n == 0 or time.perf_counter() - t0 < budget_s):
+        O.tta_step(sd, state, *frames[n % 2], lr=lr, w_sd=W_SD, w_sm=W_SM, w_cos=W_COS, max_input_depth=cap)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {'value': args.batch * n / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d full-size TTA step(s) (%dx3x%dx%d) of oracle/msgchn_oracle.py (torch %s CPU fp32) after 1 warm-up, %.1f s/step' % (
+                n, args.batch, h, w, torch.__version__, dt / n)}
+
+
+def time_dominant_kernel(dev, peaks, iters=40):
+    """The 32->32 3x3 stride-1 conv at full resolution (the layer shape that carries most FLOPs and most bytes of the step),
+    timed alone with CUDA events on its launch stream; inputs rotate over 8 x 27 MB maps (> L2)."""
+    from tta_depth_completion_b200 import ops
+    h, w = 352, 1216
+    g = torch.Generator().manual_seed(0)
+    wt = (torch.randn((32, 32, 3, 3), generator=g) * (2.0 / 288) ** 0.5).to(dev)
+    wp = ops.pack_conv_weight(wt, 'conv_fwd')
+    bias = torch.zeros(32, device=dev)
+    xs = [torch.randn((1, h, w, 32), device=dev).to(torch.bfloat16) for _ in range(8)]
+    for i in range(5):
+        ops.conv3x3(xs[i % 8], wp, bias, ops.MODE_S1, ops.PRO_RELU)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        ops.conv3x3(xs[i % 8], wp, bias, ops.MODE_S1, ops.PRO_RELU)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    tflops = CONV_GFLOP_R1 / ms          # GFLOP / ms == TFLOP/s
+    alg_bytes = 2 * h * w * 32 * 2 + 9 * 32 * 32 * 2 + 128
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')) as f:
+            traffic = json.load(f).get('dram_bytes_per_launch')
+    except Exception:
+        pass
+    return {'kernel': 'conv3x3 32->32 s1 @352x1216 (NHWC bf16, fp32 accumulate, ReLU prologue + bias epilogue)',
+            'bound': 'tensor', 'achieved': tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': tflops / peaks['bf16_tflops'],
+            'traffic': traffic, 'us_per_launch': 1e3 * ms, 'gflop_per_launch': CONV_GFLOP_R1,
+            'hbm_gbs_achieved': alg_bytes / ms / 1e6, 'hbm_frac': alg_bytes / ms / 1e6 / peaks['hbm_gbs'],
+            'peak_source': peaks['source'] + ', burst figure (kernel timed alone)'}
+
+
+def run_native(args):
+    from tta_depth_completion_b200 import ExternalModel_Adapt
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the TTA step has no CPU fallback (use --impl reference for the CPU arm)')
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
+    peaks = load_peaks()
+
+    model = ExternalModel_Adapt('msg_chn', 0.0, 100.0, max_input_depth=cap, device=dev)
+    model._prepare_head(mode)
+    model.load_state_dict(make_checkpoint(args.workload))
+    model.set_image_normalization((1 / 255.0,) * 3, (0.0,) * 3)
+    model.train()
+    frames = make_frames(args.workload, args.batch, RING, seq_seed=1 + rank)          # rank r adapts on sequence shard r
+    dev_frames = [(i.to(dev), s.to(dev)) for i, s in frames]
+    pinned = [(i.pin_memory(), s.pin_memory()) for i, s in frames]
+    stream = torch.cuda.Stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput (`value`) -------------------------------------------------------------------
+    eng = None
+    with torch.cuda.stream(stream):
+        launches0 = 0
+        for i in range(args.warmup):
+            img, sp = dev_frames[i % RING]
+            if eng is not None and i == args.warmup - 1:
+                launches0 = eng.launch_count()
+            model.tta_step(img, sp, lr, W_SD, W_SM, W_COS)
+            eng = model._last_engine
+        launches_per_step = eng.launch_count() - launches0 if launches0 else None
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            img, sp = dev_frames[(args.warmup + i) % RING]
+            model.tta_step(img, sp, lr, W_SD, W_SM, W_COS)
+        e1.record(stream)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        sampler.stop_flag = True
+        losses = model.last_losses()
+
+        # ---- end to end: host pinned inputs -> H2D -> step -> D2H loss read, every step -------------------------------
+        img_d = torch.empty_like(dev_frames[0][0])
+        sp_d = torch.empty_like(dev_frames[0][1])
+        for i in range(max(3, args.warmup)):
+            img_d.copy_(pinned[i % RING][0], non_blocking=True)
+            sp_d.copy_(pinned[i % RING][1], non_blocking=True)
+            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS)
+            model.last_losses()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for i in range(args.steps):
+            img_d.copy_(pinned[i % RING][0], non_blocking=True)
+            sp_d.copy_(pinned[i % RING][1], non_blocking=True)
+            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS)
+            e2e_losses = model.last_losses()            # D2H + sync (the driver reads the loss every step, src/tta_main.py:801)
+        f1.record(stream)
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    frames_total = world * args.batch * args.steps
+    h2d = frames[0][0].numel() * 4 + frames[0][1].numel() * 4
+    line = {
+        'metric': 'adapted_frames_per_sec', 'value': frames_total / (ms_total / 1e3), 'unit': 'frames/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(args),
+        'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 20,
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': (launches_per_step or 0) * args.steps,
+        'launches_per_step': launches_per_step,
+        'clocks': sampler.summary(),
+        'last_losses': losses,
+    }
+    gflop_step = {'kitti': 210.5, 'void': 152.8}[args.workload] * args.batch
+    line['step_tflops'] = gflop_step / (ms_total / args.steps)
+    line['step_tflops_note'] = 'work performed per step (%.1f GFLOP: fwd + required dgrad/wgrad, rgb_encoder(0) cached, SURVEY.md 8d) / ms_per_step' % gflop_step
+    if world == 1 and not args.no_extras:
+        line['roofline'] = time_dominant_kernel(dev, peaks)
+        line['cpu_baseline'] = cpu_baseline_sample(args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--workload', default='kitti', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=1)
+    ap.add_argument('--no-extras', action='store_true', help='skip the roofline / cpu_baseline legs (profiling runs)')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.steps is None:
+        args.steps = 10 if args.impl == 'reference' else 200
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == '__main__':
+    main()

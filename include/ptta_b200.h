@@ -67,7 +67,7 @@ int ptta_up2_c32_adjoint(const void* g_hi_bf16, void* g_lo_bf16, int n, int h, i
 int ptta_gemm_bf16(const void* a, const void* b, void* c, const float* bias, long long m, int n, int k, ptta_stream_t stream);
 /* torch.optim.Adam over one flat fp32 buffer (src/tta_main.py:341-346,633); step is 1-based */
 int ptta_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
-                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, ptta_stream_t stream);
+                   double lr, double beta1, double beta2, double eps, double weight_decay, int step, ptta_stream_t stream);
 
 /* ---- MSG-CHN ProxyTTA engine ------------------------------------------------------------------- */
 /* prepare_mode: the reference's string, e.g. "meta_selfsup_seq_2layers_ema" (network_exp_msg_chn_adapt.py:1022-1087) */
@@ -101,7 +101,8 @@ int ptta_msgchn_backward(ptta_msgchn* e, float grad_scale, ptta_stream_t stream)
 int ptta_msgchn_loss_backward(ptta_msgchn* e, float grad_scale, ptta_stream_t stream);
 int ptta_msgchn_network_backward(ptta_msgchn* e, ptta_stream_t stream);
 /* optimizer.step() (src/tta_main.py:633) + repack of the adapted bf16 operands */
-int ptta_msgchn_set_adam(ptta_msgchn* e, float lr, float beta1, float beta2, float eps, float weight_decay, int step_count, ptta_stream_t stream);
+/* hyper-parameters are doubles (torch derives 1-beta and the bias corrections in double); step_count < 0 keeps the device-side count */
+int ptta_msgchn_set_adam(ptta_msgchn* e, double lr, double beta1, double beta2, double eps, double weight_decay, int step_count, ptta_stream_t stream);
 int ptta_msgchn_adam_step(ptta_msgchn* e, ptta_stream_t stream);
 /* the whole per-frame step, src/tta_main.py:583-633: outlier removal, forward, loss, backward, Adam */
 int ptta_msgchn_tta_step(ptta_msgchn* e, const float* image_raw, const float* img_scale, const float* img_shift,

@@ -12,7 +12,7 @@ c_void_p, c_int, c_float, c_ll, c_size_t, c_char_p = (ctypes.c_void_p, ctypes.c_
 HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'ptta_b200.h')
 
 _CTYPE = {
-    'int': c_int, 'float': c_float, 'long long': c_ll, 'size_t': c_size_t, 'ptta_stream_t': c_void_p,
+    'int': c_int, 'float': c_float, 'double': ctypes.c_double, 'long long': c_ll, 'size_t': c_size_t, 'ptta_stream_t': c_void_p,
     'const char*': c_char_p, 'void': None,
 }
 

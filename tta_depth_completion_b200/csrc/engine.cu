@@ -974,27 +974,25 @@ int ptta_gemm_bf16(const void* a, const void* b, void* c, const float* bias, lon
     return launch_gemm(p, (cudaStream_t)stream);
 }
 
-__global__ void adam_flat_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+__global__ void adam_flat_kernel(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, float eps,
                                  float wd, int step) {
-    const double bc1 = 1.0 - pow((double)b1, (double)step);
-    const double bc2 = 1.0 - pow((double)b2, (double)step);
-    const float step_size = (float)((double)lr / bc1);
+    const double bc1 = 1.0 - pow(b1, (double)step);
+    const double bc2 = 1.0 - pow(b2, (double)step);
+    const float step_size = (float)(lr / bc1);
     const float bc2_sqrt = (float)sqrt(bc2);
+    const float fb2 = (float)b2, omb1 = (float)(1.0 - b1), omb2 = (float)(1.0 - b2);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float gg = g[i], pp = p[i];
-        if (wd != 0.f) gg = fmaf(wd, pp, gg);
-        float mm = b1 * m[i] + (1.f - b1) * gg;
-        float vv = b2 * v[i] + (1.f - b2) * gg * gg;
-        m[i] = mm; v[i] = vv;
-        p[i] = pp - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+        float pp = p[i], mm = m[i], vv = v[i];
+        adam_update(pp, g[i], mm, vv, fb2, omb1, omb2, eps, wd, step_size, bc2_sqrt);
+        p[i] = pp; m[i] = mm; v[i] = vv;
     }
 }
-int ptta_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd, int step,
+int ptta_adam_flat(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps, double wd, int step,
                    ptta_stream_t stream) {
     PTTA_CHECK(step >= 1, "adam: step must be >= 1");
     if (n <= 0) return 0;
     int blocks = (int)std::min<long long>(cdiv(n, 256), 1184);
-    adam_flat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, step);
+    adam_flat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, (float)eps, (float)wd, step);
     return check_launch("adam_flat");
 }
 
@@ -1031,7 +1029,12 @@ int ptta_msgchn_bind_workspace(ptta_msgchn* e, void* ws, size_t bytes, ptta_stre
     e->plan();
     e->bound = true; e->packed = false;
     PTTA_CUDA(cudaMemsetAsync(ws, 0, e->ws_bytes, (cudaStream_t)stream));
-    AdamHyper hy; hy.lr = 1e-4f; hy.beta1 = 0.9f; hy.beta2 = 0.999f; hy.eps = 1e-8f; hy.weight_decay = 0.f; hy.step = 0;
+    AdamHyper hy;
+    {
+        hy.lr = 1e-4f; hy.beta1 = 0.9f; hy.beta2 = 0.999f; hy.eps = 1e-8f; hy.weight_decay = 0.f;
+        hy.one_minus_beta1 = (float)(1.0 - 0.9); hy.one_minus_beta2 = (float)(1.0 - 0.999);
+        hy.step = 0; hy.beta1_d = 0.9; hy.beta2_d = 0.999; hy.lr_d = 1e-4;
+    }
     PTTA_CUDA(cudaMemcpyAsync(e->adam_hyper, &hy, sizeof(hy), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     PTTA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
@@ -1091,15 +1094,24 @@ int ptta_msgchn_network_backward(ptta_msgchn* e, ptta_stream_t stream) {
     e->st = (cudaStream_t)stream;
     return e->network_backward();
 }
-int ptta_msgchn_set_adam(ptta_msgchn* e, float lr, float b1, float b2, float eps, float wd, int step_count, ptta_stream_t stream) {
+static AdamHyper make_hyper(double lr, double b1, double b2, double eps, double wd, int step) {
+    AdamHyper hy;
+    hy.lr = (float)lr; hy.beta1 = (float)b1; hy.beta2 = (float)b2; hy.eps = (float)eps; hy.weight_decay = (float)wd;
+    hy.one_minus_beta1 = (float)(1.0 - b1); hy.one_minus_beta2 = (float)(1.0 - b2);
+    hy.step = step; hy.beta1_d = b1; hy.beta2_d = b2; hy.lr_d = lr;
+    return hy;
+}
+int ptta_msgchn_set_adam(ptta_msgchn* e, double lr, double b1, double b2, double eps, double wd, int step_count, ptta_stream_t stream) {
     PTTA_CHECK(e && e->bound, "set_adam: engine not bound");
-    AdamHyper hy; hy.lr = lr; hy.beta1 = b1; hy.beta2 = b2; hy.eps = eps; hy.weight_decay = wd; hy.step = step_count;
+    cudaStream_t st = (cudaStream_t)stream;
+    AdamHyper hy = make_hyper(lr, b1, b2, eps, wd, step_count);
     if (step_count < 0) {   // keep the device-side step count, update the rest
-        PTTA_CUDA(cudaMemcpyAsync(e->adam_hyper, &hy, offsetof(AdamHyper, step), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        PTTA_CUDA(cudaMemcpyAsync(e->adam_hyper, &hy, offsetof(AdamHyper, step), cudaMemcpyHostToDevice, st));
+        PTTA_CUDA(cudaMemcpyAsync(&e->adam_hyper->beta1_d, &hy.beta1_d, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     } else {
-        PTTA_CUDA(cudaMemcpyAsync(e->adam_hyper, &hy, sizeof(hy), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        PTTA_CUDA(cudaMemcpyAsync(e->adam_hyper, &hy, sizeof(hy), cudaMemcpyHostToDevice, st));
     }
-    PTTA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));   // hy is a stack object
+    PTTA_CUDA(cudaStreamSynchronize(st));   // hy is a stack object
     return 0;
 }
 int ptta_msgchn_adam_step(ptta_msgchn* e, ptta_stream_t stream) {

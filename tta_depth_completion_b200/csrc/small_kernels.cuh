@@ -791,27 +791,33 @@ __global__ void __launch_bounds__(256) loss_cos_grad_kernel(const bf16* __restri
 // One launch over a chunk table covering every adapted tensor; hyper-parameters and the step count
 // live on the device so the launch is CUDA-graph friendly.
 // -------------------------------------------------------------------------------------------------
-struct AdamHyper { float lr, beta1, beta2, eps, weight_decay; int step; };
+struct AdamHyper { float lr, beta1, beta2, eps, weight_decay, one_minus_beta1, one_minus_beta2; int step; double beta1_d, beta2_d, lr_d; };
 struct AdamChunk { float* p; const float* g; float* m; float* v; int n; };
 #define ADAM_CHUNK 2048
+
+// torch's single-tensor formulation: exp_avg.lerp_(g, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g, g, value=1-b2);
+// denom = sqrt(v)/sqrt(bc2) + eps; p.addcdiv_(m, denom, value=-lr/bc1)   (1-b computed in double, as torch does)
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float b2, float omb1, float omb2, float eps, float wd,
+                                            float step_size, float bc2_sqrt) {
+    if (wd != 0.f) g = fmaf(wd, p, g);
+    m = fmaf(omb1, g - m, m);
+    v = b2 * v + omb2 * g * g;
+    float denom = sqrtf(v) / bc2_sqrt + eps;
+    p = p - step_size * (m / denom);
+}
 
 __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__ chunks, const AdamHyper* __restrict__ hy) {
     const AdamChunk ck = chunks[blockIdx.x];
     const int t = hy->step + 1;
-    const float b1 = hy->beta1, b2 = hy->beta2;
-    const double bc1 = 1.0 - pow((double)b1, (double)t);
-    const double bc2 = 1.0 - pow((double)b2, (double)t);
-    const float step_size = (float)((double)hy->lr / bc1);
+    const double bc1 = 1.0 - pow(hy->beta1_d, (double)t);
+    const double bc2 = 1.0 - pow(hy->beta2_d, (double)t);
+    const float step_size = (float)(hy->lr_d / bc1);
     const float bc2_sqrt = (float)sqrt(bc2);
-    const float eps = hy->eps, wd = hy->weight_decay;
+    const float b2 = hy->beta2, omb1 = hy->one_minus_beta1, omb2 = hy->one_minus_beta2, eps = hy->eps, wd = hy->weight_decay;
     for (int i = threadIdx.x; i < ck.n; i += 256) {
-        float g = ck.g[i], p = ck.p[i];
-        if (wd != 0.f) g = fmaf(wd, p, g);
-        float m = b1 * ck.m[i] + (1.f - b1) * g;
-        float v = b2 * ck.v[i] + (1.f - b2) * g * g;
-        ck.m[i] = m; ck.v[i] = v;
-        float denom = sqrtf(v) / bc2_sqrt + eps;
-        ck.p[i] = p - step_size * (m / denom);
+        float p = ck.p[i], m = ck.m[i], v = ck.v[i];
+        adam_update(p, ck.g[i], m, v, b2, omb1, omb2, eps, wd, step_size, bc2_sqrt);
+        ck.p[i] = p; ck.m[i] = m; ck.v[i] = v;
     }
 }
 __global__ void adam_advance_kernel(AdamHyper* hy) { hy->step += 1; }

@@ -250,6 +250,8 @@ class MsgChnModel_Adapt(object):
 
     # -- reference API ----------------------------------------------------------------------------------
     def forward(self, image, sparse_depth, intrinsics=None, crop_mask=None, loss_type='pretrain'):
+        if self.prepare_mode is None:
+            raise RuntimeError('_prepare_head(mode) must be called before forward (src/tta_main.py:322)')
         image = image.contiguous()
         sparse_depth = sparse_depth.contiguous()
         if self.training and 'adapt' in loss_type:
