@@ -441,16 +441,24 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const WgradParams p)
     }
 }
 
-// dW[co][ci][ky][kx] (PyTorch Conv2d layout) = sum over partial blocks, fixed order
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nblocks, int cout, int cin) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = 9 * cout * cin;
-    if (i >= total) return;
+// dW[co][ci][ky][kx] (PyTorch Conv2d layout) = sum over partial blocks.  Block = 32 outputs x 8 slices of the partial
+// list; slices are combined through shared memory in a fixed order (deterministic, coalesced 128 B reads).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nblocks, int cout, int cin) {
+    __shared__ float sh[8][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int total = 9 * cout * cin;
+    const int i = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (i < total)
+        for (int b = slice; b < nblocks; b += 8) s += partial[(size_t)b * total + i];
+    sh[slice][lane] = s;
+    __syncthreads();
+    if (slice != 0 || i >= total) return;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += sh[k][lane];
     int tap = i / (cout * cin);
     int rem = i - tap * cout * cin;
     int co = rem / cin, ci = rem - co * cin;
-    float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * total + i];
     dw[((size_t)co * cin + ci) * 9 + tap] = s;
 }
 
@@ -468,7 +476,7 @@ int launch_wgrad_t(WgradParams p, float* dw, cudaStream_t st) {
     conv3x3_wgrad_kernel<CIN, COUT><<<grid, 256, S::TOTAL, st>>>(p);
     PTTA_TRY(check_launch("conv3x3_wgrad"));
     int total = 9 * COUT * CIN;
-    wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.partial, dw, p.tiles_x * p.tiles_y * p.N, COUT, CIN);
+    wgrad_reduce_kernel<<<cdiv(total, 32), 256, 0, st>>>(p.partial, dw, p.tiles_x * p.tiles_y * p.N, COUT, CIN);
     return check_launch("wgrad_reduce");
 }
 

@@ -594,7 +594,7 @@ struct ptta_msgchn {
         if (training) PTTA_TRY(stats(x, nullptr, rows, L.c, 0, nullptr, 0, nblk));
         BnParams p; p.gamma = L.gamma; p.beta = L.beta; p.running_mean = L.rm; p.running_var = L.rv; p.num_batches_tracked = L.nbt;
         p.mean = s.mean; p.invstd = s.invstd; p.scale = s.scale; p.shift = s.shift; p.momentum = 0.1f; p.eps = 1e-5f;
-        bn_finalize_kernel<<<cdiv(L.c, 128), 128, 0, st>>>(partial, nblk, rows, L.c, p, training ? 1 : 0);
+        bn_finalize_kernel<<<cdiv(L.c, 4), 128, 0, st>>>(partial, nblk, rows, L.c, p, training ? 1 : 0);
         return check_launch("bn_finalize");
     }
     int bn_apply(const bf16* x, const bf16* res, bf16* y, long long rows, int C, const BnState& s, int act) {
@@ -607,7 +607,7 @@ struct ptta_msgchn {
                     float* dgamma, float* dbeta) {
         int nblk = 0;
         PTTA_TRY(stats(x, dy, rows, L.c, 1, &s, relu_mask, nblk));
-        bn_bwd_finalize_kernel<<<cdiv(L.c, 128), 128, 0, st>>>(partial, nblk, rows, L.c, L.gamma, s.invstd, dgamma, dbeta, k0, k1, k2);
+        bn_bwd_finalize_kernel<<<cdiv(L.c, 4), 128, 0, st>>>(partial, nblk, rows, L.c, L.gamma, s.invstd, dgamma, dbeta, k0, k1, k2);
         PTTA_TRY(check_launch("bn_bwd_finalize"));
         long long tot = rows * (L.c / 8);
         bn_bwd_apply_kernel<<<cdiv(tot, 256), 256, 0, st>>>(dy, x, dx, rows, L.c, s.mean, s.invstd, k0, k1, k2, s.scale, s.shift, relu_mask);
@@ -729,7 +729,7 @@ struct ptta_msgchn {
         PTTA_TRY(check_launch("loss_map_reduce"));
         loss_cos_rows_kernel<<<loss_cos_blocks, 256, 0, st>>>(emb, ref, rowstat, loss_cos_partial, R, 512);
         PTTA_TRY(check_launch("loss_cos_rows"));
-        loss_finalize_kernel<<<1, 32, 0, st>>>(loss_map_partial, loss_map_blocks, loss_cos_partial, loss_cos_blocks, N, H, W, R, w_sd, w_sm,
+        loss_finalize_kernel<<<1, 256, 0, st>>>(loss_map_partial, loss_map_blocks, loss_cos_partial, loss_cos_blocks, N, H, W, R, w_sd, w_sm,
                                               w_cos, 0.3f, losses);
         return check_launch("loss_finalize");
     }
@@ -813,7 +813,7 @@ struct ptta_msgchn {
             PTTA_TRY(launch_wgrad(wp, grad_of("conv1_rgb_meta.weight"), 32, 32, st));
             int nblk = 0;
             PTTA_TRY(stats(GC2.p, nullptr, rows, 32, 0, nullptr, 0, nblk));
-            colsum_finalize_kernel<<<1, 32, 0, st>>>(partial, nblk, 32, grad_of("conv1_rgb_meta.bias"));
+            colsum_finalize_kernel<<<8, 128, 0, st>>>(partial, nblk, 32, grad_of("conv1_rgb_meta.bias"));
             return check_launch("colsum_finalize");
         }
         const std::string p = "conv1_rgb_meta.conv1_meta";
@@ -822,7 +822,7 @@ struct ptta_msgchn {
         {
             int nblk = 0;
             PTTA_TRY(stats(G4a.p, nullptr, rows, 32, 0, nullptr, 0, nblk));
-            colsum_finalize_kernel<<<1, 32, 0, st>>>(partial, nblk, 32, grad_of(p + ".1.bias"));
+            colsum_finalize_kernel<<<8, 128, 0, st>>>(partial, nblk, 32, grad_of(p + ".1.bias"));
             PTTA_TRY(check_launch("colsum_finalize"));
         }
         {   // conv2 wgrad: input = leaky(bn1(mh))

@@ -430,7 +430,7 @@ __global__ void ew_add_kernel(const bf16* __restrict__ a, const bf16* __restrict
 // `relu_mask`: the incoming dy is first multiplied by [x*scale+shift > 0] (the ReLU that follows BN
 // in the MLP heads), so no masked copy of dy is ever written.
 // -------------------------------------------------------------------------------------------------
-#define STATS_ROWS_PER_BLOCK 1024
+#define STATS_ROWS_PER_BLOCK 128
 __global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, double* __restrict__ partial,
                                                         long long rows, int C, int mode, const float* __restrict__ mean,
                                                         const float* __restrict__ invstd, const float* __restrict__ scale,
@@ -503,12 +503,21 @@ struct BnParams {
     float momentum, eps;
 };
 
-__global__ void bn_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C, BnParams p, int training) {
-    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+// sum of partial[k][slot][ch] over k, one warp per channel (fixed lane assignment + butterfly -> deterministic)
+__device__ __forceinline__ double warp_reduce_partials(const double* __restrict__ partial, int nblk, int C, int slot, int ch, int lane) {
+    double a = 0.0;
+    for (int k = lane; k < nblk; k += 32) a += partial[((size_t)k * 2 + slot) * C + ch];
+    return warp_sum_d(a);
+}
+
+__global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C, BnParams p, int training) {
+    const int lane = threadIdx.x & 31;
+    const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (ch >= C) return;
     if (training) {
-        double a = 0.0, b = 0.0;
-        for (int k = 0; k < nblk; ++k) { a += partial[((size_t)k * 2 + 0) * C + ch]; b += partial[((size_t)k * 2 + 1) * C + ch]; }
+        double a = warp_reduce_partials(partial, nblk, C, 0, ch, lane);
+        double b = warp_reduce_partials(partial, nblk, C, 1, ch, lane);
+        if (lane != 0) return;
         double m = a / (double)count;
         double var = b / (double)count - m * m;
         if (var < 0.0) var = 0.0;
@@ -525,6 +534,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partial, int nblk,
         }
         if (ch == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
     } else {
+        if (lane != 0) return;
         float invstd = 1.f / sqrtf(p.running_var[ch] + p.eps);
         p.mean[ch] = p.running_mean[ch];
         p.invstd[ch] = invstd;
@@ -562,14 +572,16 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, const bf16* __restri
 
 // dgamma = sum dy*xhat, dbeta = sum dy;  dx = k0*dy - k1 - xhat*k2 with
 //   k0 = gamma*invstd, k1 = k0*mean(dy), k2 = k0*mean(dy*xhat)
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C,
+__global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ k0, float* __restrict__ k1, float* __restrict__ k2) {
-    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (ch >= C) return;
-    double a = 0.0, b = 0.0;
-    for (int k = 0; k < nblk; ++k) { a += partial[((size_t)k * 2 + 0) * C + ch]; b += partial[((size_t)k * 2 + 1) * C + ch]; }
+    double a = warp_reduce_partials(partial, nblk, C, 0, ch, lane);
+    double b = warp_reduce_partials(partial, nblk, C, 1, ch, lane);
+    if (lane != 0) return;
     if (dbeta) dbeta[ch] = (float)a;
     if (dgamma) dgamma[ch] = (float)b;
     float g = gamma[ch] * invstd[ch];
@@ -606,12 +618,12 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
 }
 
 // column sums of a [rows][C] bf16 matrix into fp32 (bias gradients): out[c] = sum_r x[r][c]; uses col_stats partials (mode 0, slot 0)
-__global__ void colsum_finalize_kernel(const double* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
-    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) colsum_finalize_kernel(const double* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (ch >= C) return;
-    double a = 0.0;
-    for (int k = 0; k < nblk; ++k) a += partial[((size_t)k * 2 + 0) * C + ch];
-    out[ch] = (float)a;
+    double a = warp_reduce_partials(partial, nblk, C, 0, ch, lane);
+    if (lane == 0) out[ch] = (float)a;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -692,25 +704,33 @@ struct LossScalars {   // device-resident result block
     float inv_count[64];   // 1 / sum(v) per image (N <= 64)
 };
 
-__global__ void loss_finalize_kernel(const double* __restrict__ map_partial, int map_blocks, const double* __restrict__ cos_partial,
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const double* __restrict__ map_partial, int map_blocks, const double* __restrict__ cos_partial,
                                      int cos_blocks, int N, int H, int W, long long R, float w_sd, float w_sm, float w_cos,
                                      float cos_gate, LossScalars* out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double sd = 0.0, sx = 0.0, sy = 0.0;
+    __shared__ double sh[32];
+    __shared__ double s_sd;
+    double sx = 0.0, sy = 0.0;
+    if (threadIdx.x == 0) s_sd = 0.0;
     for (int n = 0; n < N; ++n) {
-        double a = 0.0, b = 0.0;
-        for (int k = 0; k < map_blocks; ++k) {
+        double a = 0.0, b = 0.0, cx = 0.0, cy = 0.0;
+        for (int k = threadIdx.x; k < map_blocks; k += 256) {
             const double* p = map_partial + ((size_t)n * map_blocks + k) * 4;
-            a += p[0]; b += p[1]; sx += p[2]; sy += p[3];
+            a += p[0]; b += p[1]; cx += p[2]; cy += p[3];
         }
-        float fa = (float)a, fb = (float)b;
-        sd += (double)(fa / fb);                 // no epsilon: an empty frame yields NaN, as in the reference
-        if (n < 64) out->inv_count[n] = 1.f / fb;
+        a = block_sum_d(a, sh); b = block_sum_d(b, sh); cx = block_sum_d(cx, sh); cy = block_sum_d(cy, sh);
+        if (threadIdx.x == 0) {
+            float fa = (float)a, fb = (float)b;
+            s_sd += (double)(fa / fb);               // no epsilon: an empty frame yields NaN, as in the reference
+            if (n < 64) out->inv_count[n] = 1.f / fb;
+            sx += cx; sy += cy;
+        }
     }
-    float l_sd = (float)(sd / N);
-    float l_sm = (float)(sx / ((double)N * H * (W - 1))) + (float)(sy / ((double)N * (H - 1) * W));
     double c = 0.0;
-    for (int k = 0; k < cos_blocks; ++k) c += cos_partial[k];
+    for (int k = threadIdx.x; k < cos_blocks; k += 256) c += cos_partial[k];
+    c = block_sum_d(c, sh);
+    if (threadIdx.x != 0) return;
+    float l_sd = (float)(s_sd / N);
+    float l_sm = (float)(sx / ((double)N * H * (W - 1))) + (float)(sy / ((double)N * (H - 1) * W));
     float l_cos = R > 0 ? (float)(c / (double)R) : 0.f;
     float w_eff = (l_cos < cos_gate) ? 0.f : w_cos;
     out->loss_sparse_depth = l_sd;
