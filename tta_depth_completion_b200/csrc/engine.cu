@@ -17,6 +17,7 @@
 #include "conv_mma.cuh"
 #include "gemm_mma.cuh"
 #include "small_kernels.cuh"
+#include "conv_tc.cuh"
 #include "../../include/ptta_b200.h"
 
 namespace ptta {
@@ -912,6 +913,20 @@ int ptta_conv3x3(const void* in, void* out, const void* wpack, const float* bias
     PTTA_CHECK(prologue != PRO_BN_LEAKY || (pro_scale && pro_shift), "conv3x3: BN prologue needs scale and shift");
     PTTA_CHECK(p.mask_mode != MASK_BN_LEAKY || (mask_scale && mask_shift), "conv3x3: BN mask needs scale and shift");
     return launch_conv3x3(p, cin, cout, mode, (cudaStream_t)stream);
+}
+
+int ptta_conv3x3_tc(const void* in, void* out, const void* wpack, const float* bias, int n, int h, int w, int relu_in, int relu_out,
+                    const void* mask, const void* add, ptta_stream_t stream) {
+    PTTA_CHECK(in && out && wpack, "conv3x3_tc: null argument");
+    ConvTcParams p; memset(&p, 0, sizeof(p));
+    p.w = (const bf16*)wpack; p.bias = bias; p.out = (bf16*)out; p.mask = (const bf16*)mask; p.add = (const bf16*)add;
+    p.N = n; p.H = h; p.W = w; p.relu_in = relu_in; p.relu_out = relu_out;
+    return launch_conv_tc((const bf16*)in, p, (cudaStream_t)stream);
+}
+
+int ptta_debug_set(int v) {
+    PTTA_CUDA(cudaMemcpyToSymbol(g_tc_dbg, &v, sizeof(int)));
+    return 0;
 }
 
 size_t ptta_conv3x3_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout) { return wgrad_partial_bytes(n, h, w, cin, cout); }

@@ -92,6 +92,19 @@ def conv3x3(x, wpack, bias=None, mode=MODE_S1, prologue=PRO_NONE, pro_scale=None
     return out
 
 
+def conv3x3_tc(x, wpack, bias=None, relu_in=True, relu_out=False, mask=None, add=None, variant=0):  # variant: unused
+    """32->32 stride-1 conv on tcgen05 (same operand conventions as conv3x3 with MODE_S1)."""
+    _need(x, torch.bfloat16, 'x')
+    _need(wpack, torch.bfloat16, 'wpack')
+    n, h, w, cin = x.shape
+    if cin != 32 or tuple(wpack.shape) != (9, 32, 32):
+        raise ValueError('conv3x3_tc handles 32->32 channels only')
+    out = torch.empty_like(x)
+    check(_lib.lib().ptta_conv3x3_tc(ptr(x), ptr(out), ptr(wpack), ptr(bias), n, h, w, 1 if relu_in else 0, 1 if relu_out else 0,
+                                     ptr(mask), ptr(add), _stream()), 'conv3x3_tc')
+    return out
+
+
 def conv3x3_wgrad(x, gout, prologue=PRO_NONE, pro_scale=None, pro_shift=None, slope=0.2):
     _need(x, torch.bfloat16, 'x')
     _need(gout, torch.bfloat16, 'gout')
