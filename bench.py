@@ -228,16 +228,24 @@ def run_native(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput (`value`) -------------------------------------------------------------------
+    # every step: D2D copy of the next ring frame into the step's fixed input buffers, then the whole step replayed from
+    # its CUDA graph (--no-graph: the same kernels launched eagerly)
+    use_graph = args.graph
+    img_d = torch.empty_like(dev_frames[0][0])
+    sp_d = torch.empty_like(dev_frames[0][1])
     eng = None
     with torch.cuda.stream(stream):
-        launches0 = 0
+        # launches per step are counted on one eager step (graph replays do not pass through the launch counter)
+        img_d.copy_(dev_frames[0][0]); sp_d.copy_(dev_frames[0][1])
+        model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS)
+        eng = model._last_engine
+        l0 = eng.launch_count()
+        model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS)
+        launches_per_step = eng.launch_count() - l0
         for i in range(args.warmup):
             img, sp = dev_frames[i % RING]
-            if eng is not None and i == args.warmup - 1:
-                launches0 = eng.launch_count()
-            model.tta_step(img, sp, lr, W_SD, W_SM, W_COS)
-            eng = model._last_engine
-        launches_per_step = eng.launch_count() - launches0 if launches0 else None
+            img_d.copy_(img, non_blocking=True); sp_d.copy_(sp, non_blocking=True)
+            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS, graph=use_graph)
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -245,7 +253,8 @@ def run_native(args):
         e0.record(stream)
         for i in range(args.steps):
             img, sp = dev_frames[(args.warmup + i) % RING]
-            model.tta_step(img, sp, lr, W_SD, W_SM, W_COS)
+            img_d.copy_(img, non_blocking=True); sp_d.copy_(sp, non_blocking=True)
+            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS, graph=use_graph)
         e1.record(stream)
         barrier()
         ms_total = e0.elapsed_time(e1)
@@ -253,12 +262,10 @@ def run_native(args):
         losses = model.last_losses()
 
         # ---- end to end: host pinned inputs -> H2D -> step -> D2H loss read, every step -------------------------------
-        img_d = torch.empty_like(dev_frames[0][0])
-        sp_d = torch.empty_like(dev_frames[0][1])
         for i in range(max(3, args.warmup)):
             img_d.copy_(pinned[i % RING][0], non_blocking=True)
             sp_d.copy_(pinned[i % RING][1], non_blocking=True)
-            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS)
+            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS, graph=use_graph)
             model.last_losses()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -266,7 +273,7 @@ def run_native(args):
         for i in range(args.steps):
             img_d.copy_(pinned[i % RING][0], non_blocking=True)
             sp_d.copy_(pinned[i % RING][1], non_blocking=True)
-            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS)
+            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS, graph=use_graph)
             e2e_losses = model.last_losses()            # D2H + sync (the driver reads the loss every step, src/tta_main.py:801)
         f1.record(stream)
         barrier()
@@ -289,7 +296,7 @@ def run_native(args):
         'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 20,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': (launches_per_step or 0) * args.steps,
-        'launches_per_step': launches_per_step,
+        'launches_per_step': launches_per_step, 'cuda_graph': use_graph,
         'clocks': sampler.summary(),
         'last_losses': losses,
     }
@@ -312,6 +319,7 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--workload', default='kitti', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=1)
+    ap.add_argument('--graph', action='store_true', help='replay the step from its CUDA graph (measured slower than eager launches: DESIGN.md)')
     ap.add_argument('--no-extras', action='store_true', help='skip the roofline / cpu_baseline legs (profiling runs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

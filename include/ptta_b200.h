@@ -70,6 +70,8 @@ int ptta_add_up2_c32(const void* x_bf16, const void* half_bf16, void* out_bf16, 
 int ptta_up2_c32_adjoint(const void* g_hi_bf16, void* g_lo_bf16, int n, int h, int w, int accumulate, ptta_stream_t stream);
 /* nn.Linear (:1089-1098): C[M][N] = A[M][K] * B[N][K]^T + bias */
 int ptta_gemm_bf16(const void* a, const void* b, void* c, const float* bias, long long m, int n, int k, ptta_stream_t stream);
+/* the same on the tcgen05 tensor cores (TMA-fed, TMEM accumulators); needs N % 256 == 0 and K % 64 == 0 */
+int ptta_gemm_bf16_tc(const void* a, const void* b, void* c, const float* bias, long long m, int n, int k, ptta_stream_t stream);
 /* torch.optim.Adam over one flat fp32 buffer (src/tta_main.py:341-346,633); step is 1-based */
 int ptta_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                    double lr, double beta1, double beta2, double eps, double weight_decay, int step, ptta_stream_t stream);

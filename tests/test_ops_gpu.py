@@ -243,6 +243,37 @@ def test_gemm(ops, m, n, k):
     assert_close_bf16(got, want, 'gemm %dx%dx%d' % (m, n, k))
 
 
+@pytest.mark.parametrize('m,n,k', [(300, 256, 64), (1000, 512, 512), (26752, 512, 512), (129, 768, 128)])
+def test_gemm_tcgen05(ops, m, n, k):
+    g = torch.Generator().manual_seed(11)
+    a = bf(torch.randn((m, k), generator=g))
+    b = bf(torch.randn((n, k), generator=g) / k ** 0.5)
+    bias = torch.randn((n,), generator=g)
+    want = bf(a.to(DEV) @ b.to(DEV).t() + bias.to(DEV)).cpu()
+    got = ops.gemm_bf16_tc(a.to(DEV, torch.bfloat16), b.to(DEV, torch.bfloat16), bias.to(DEV)).float().cpu()
+    assert_close_bf16(got, want, 'gemm_tc %dx%dx%d' % (m, n, k))
+    got2 = ops.gemm_bf16(a.to(DEV, torch.bfloat16), b.to(DEV, torch.bfloat16), bias.to(DEV)).float().cpu()
+    assert float((got - got2).abs().max()) <= 2.0 ** -6 * float(want.abs().max())     # both accumulate in fp32
+
+
+@pytest.mark.parametrize('n,h,w', [(1, 16, 128), (1, 24, 300), (2, 19, 37), (1, 88, 304), (1, 352, 1216)])
+def test_conv_tcgen05_matches_mma(ops, n, h, w):
+    """the tcgen05 conv is bit-identical to the mma.sync kernel (same bf16 products, fp32 accumulation of 288 terms)"""
+    g = torch.Generator().manual_seed(12)
+    wt = (torch.randn((32, 32, 3, 3), generator=g) * (2.0 / 288) ** 0.5).to(DEV)
+    wp = ops.pack_conv_weight(wt, 'conv_fwd')
+    bias = (torch.randn(32, generator=g) * 0.1).to(DEV)
+    x = torch.randn((n, h, w, 32), generator=g).to(DEV).to(torch.bfloat16)
+    m = torch.randn((n, h, w, 32), generator=g).to(DEV).to(torch.bfloat16)
+    a = torch.randn((n, h, w, 32), generator=g).to(DEV).to(torch.bfloat16)
+    want = ops.conv3x3(x, wp, bias, ops.MODE_S1, ops.PRO_RELU)
+    got = ops.conv3x3_tc(x, wp, bias, relu_in=True)
+    assert_close_bf16(got.float().cpu(), want.float().cpu(), 'conv_tc relu', ulps=1.0)
+    want = ops.conv3x3(x, wp, None, ops.MODE_S1, ops.PRO_NONE, mask=m, mask_mode=ops.MASK_RELU, add=a)
+    got = ops.conv3x3_tc(x, wp, None, relu_in=False, mask=m, add=a)
+    assert_close_bf16(got.float().cpu(), want.float().cpu(), 'conv_tc mask+add', ulps=1.0)
+
+
 def test_adam_matches_torch(ops):
     g = torch.Generator().manual_seed(10)
     p0 = torch.randn((5000,), generator=g)

@@ -18,6 +18,7 @@
 #include "gemm_mma.cuh"
 #include "small_kernels.cuh"
 #include "conv_tc.cuh"
+#include "gemm_tc.cuh"
 #include "../../include/ptta_b200.h"
 
 namespace ptta {
@@ -615,6 +616,7 @@ struct ptta_msgchn {
         return check_launch("bn_bwd_apply");
     }
     int gemm(const bf16* A, const bf16* B, bf16* C, const float* bias, long long M, int Nn, int K) {
+        if (gemm_tc_supported(M, Nn, K)) return launch_gemm_tc(A, B, C, bias, M, Nn, K, st);
         GemmParams p; p.A = A; p.B = B; p.C = C; p.bias = bias; p.M = M; p.N = Nn; p.K = K;
         return launch_gemm(p, st);
     }
@@ -987,6 +989,11 @@ int ptta_up2_c32_adjoint(const void* ghi, void* glo, int n, int h, int w, int ac
 int ptta_gemm_bf16(const void* a, const void* b, void* c, const float* bias, long long m, int n, int k, ptta_stream_t stream) {
     GemmParams p; p.A = (const bf16*)a; p.B = (const bf16*)b; p.C = (bf16*)c; p.bias = bias; p.M = m; p.N = n; p.K = k;
     return launch_gemm(p, (cudaStream_t)stream);
+}
+
+int ptta_gemm_bf16_tc(const void* a, const void* b, void* c, const float* bias, long long m, int n, int k, ptta_stream_t stream) {
+    PTTA_CHECK(a && b && c, "gemm_bf16_tc: null argument");
+    return launch_gemm_tc((const bf16*)a, (const bf16*)b, (bf16*)c, bias, m, n, k, (cudaStream_t)stream);
 }
 
 __global__ void adam_flat_kernel(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, float eps,

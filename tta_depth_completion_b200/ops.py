@@ -189,6 +189,17 @@ def gemm_bf16(a, b, bias=None):
     return out
 
 
+def gemm_bf16_tc(a, b, bias=None):
+    """tcgen05 variant of gemm_bf16 (N % 256 == 0, K % 64 == 0)"""
+    _need(a, torch.bfloat16, 'a')
+    _need(b, torch.bfloat16, 'b')
+    m, k = a.shape
+    n = b.shape[0]
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    check(_lib.lib().ptta_gemm_bf16_tc(ptr(a), ptr(b), ptr(out), ptr(bias), m, n, k, _stream()), 'gemm_bf16_tc')
+    return out
+
+
 def adam_flat(param, grad, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
     for t in (param, grad, exp_avg, exp_avg_sq):
         _need(t, torch.float32, 'adam tensor')
