@@ -18,7 +18,7 @@ for shape in [(1,352,1216),(4,352,1216)]:
     n,h,w=shape
     xs=[torch.randn((n,h,w,32),device=dev).to(torch.bfloat16) for _ in range(max(2, min(8, int(300e6/(n*h*w*64)))))]
     res=[]
-    for dbg in (0,1,2,4,8,16,1|2,1|4,2|8,1|2|4|8|16):
+    for dbg in (0,1|2|4,1|2|4|8,1|2|4|16,1|2|4|8|16,8,16):
         _lib.lib().ptta_debug_set(dbg)
         us=timeit(lambda x: ops.conv3x3_tc(x, wp, bias, relu_in=False), xs)
         res.append('dbg%d %.1f'%(dbg,us))

@@ -128,16 +128,17 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 
 }  // namespace tc
 
-__device__ int g_tc_dbg = 0;   // timing experiments only (ptta_debug_set): 1 one MMA per tile, 2 no epilogue stores, 4 no loads, 8 no TMEM read, 16 skip fence
+__device__ int g_tc_dbg = 0;   // timing experiments only (ptta_debug_set): 1 one MMA per row, 2 no epilogue stores, 4 no loads
 
 struct ConvTcCfg {
-    static const int RB = 16;                     // row slots in the ring
+    static const int RB = 16;                     // input-row slots in the shared-memory ring (power of two: cheap index math)
+    static const int NSLOT = 16;                  // output-row accumulator slots in TMEM (16 x 32 columns = all 512)
     static const int BOXW = 130;                  // pixels per staged row (128 + one halo pixel each side)
     static const int SLOT_BYTES = 9216;           // 130 x 64 B rounded up to the 1024 B swizzle-pattern alignment
     static const int W_BYTES = 9 * 32 * 64;       // 18432
-    static const int BAR_BYTES = 512;
+    static const int BAR_BYTES = 1024;
     static const int SMEM = 1024 /*align slack*/ + RB * SLOT_BYTES + W_BYTES + BAR_BYTES;
-    static const int THREADS = 416;               // warp 0 MMA | warps 1-4 epilogue | warps 5-8 loaders | warps 9-12 ReLU transform
+    static const int THREADS = 416;               // warp 0 MMA | warps 1-4 epilogue | warps 5-8 loaders | warps 9-12 transform
 };
 
 // the mbarrier receives one arrival from this thread once all of its earlier cp.async copies have landed
@@ -147,44 +148,59 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+        ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Scatter-form implicit GEMM.  Input row i of a segment (image row y0-1+i) contributes to output rows j = i-2, i-1, i with
+// the vertical taps ky = 2, 1, 0.  The three taps are stacked along N, so one group of 6 MMAs (3 horizontal taps x 2 K
+// steps, M128 x N96 x K16) consumes an input row exactly once and accumulates into three neighbouring 32-column TMEM
+// slots; slot(t) = t mod 16 for the running output-row counter t.  A slot is complete after input row j+2, is drained
+// and re-zeroed by the epilogue warps, and is reused 16 rows later.
 __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const bf16* __restrict__ in, const ConvTcParams p) {
     typedef ConvTcCfg C;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t rows_s = smem_base;                                   // RB row slots
-    const uint32_t w_s = smem_base + C::RB * C::SLOT_BYTES;              // weights (SW64 canonical)
+    const uint32_t w_s = smem_base + C::RB * C::SLOT_BYTES;              // weights, SW64 canonical, row = kx*96 + (2-ky)*32 + cout
     const uint32_t bar_s = w_s + C::W_BYTES;
-    const uint32_t row_landed = bar_s;                // [RB]  loaders -> MMA / transform (128 async arrivals, cp.async completion)
-    const uint32_t row_ready_t = bar_s + 8 * C::RB;   // [RB]  transform -> MMA   (128 arrivals; only used with relu_in)
-    const uint32_t row_free = bar_s + 16 * C::RB;     // [RB]  MMA -> loaders     (tcgen05.commit)
-    const uint32_t acc_full = bar_s + 24 * C::RB;     // [2]   MMA -> epilogue    (tcgen05.commit)
-    const uint32_t acc_empty = acc_full + 16;         // [2]   epilogue -> MMA    (128 arrivals)
-    const uint32_t tmem_slot = acc_empty + 16;        // u32
+    const uint32_t row_landed = bar_s;                       // [RB]    loaders -> transform     (128 async arrivals, cp.async completion)
+    const uint32_t row_ready = bar_s + 8 * C::RB;            // [RB]    transform -> MMA        (128 arrivals, after ReLU + proxy fence)
+    const uint32_t row_free = bar_s + 16 * C::RB;            // [RB]    MMA -> loaders          (tcgen05.commit)
+    const uint32_t slot_full = bar_s + 24 * C::RB;           // [NSLOT] MMA -> epilogue         (tcgen05.commit)
+    const uint32_t slot_empty = slot_full + 8 * C::NSLOT;    // [NSLOT] epilogue -> MMA         (128 arrivals, slot re-zeroed)
+    const uint32_t tmem_slot = slot_empty + 8 * C::NSLOT;    // u32
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dbg = g_tc_dbg;
 
     // ---- one-time setup ----------------------------------------------------------------------------------
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::RB; ++i) {
             tc::mbar_init(row_landed + 8 * i, 128);
-            tc::mbar_init(row_ready_t + 8 * i, 128);
+            tc::mbar_init(row_ready + 8 * i, 128);
             tc::mbar_init(row_free + 8 * i, 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(acc_full + 8 * i, 1);
-            tc::mbar_init(acc_empty + 8 * i, 128);
+        for (int i = 0; i < C::NSLOT; ++i) {
+            tc::mbar_init(slot_full + 8 * i, 1);
+            tc::mbar_init(slot_empty + 8 * i, 128);
         }
         tc::fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, 64);
-    {   // weights -> shared memory in the canonical K-major SWIZZLE_64B layout (row = tap*32 + cout, 64 B per row)
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+    {   // weights -> shared memory: K-major SWIZZLE_64B, vertical taps stacked along N per horizontal tap
         unsigned char* wdst = smem + (w_s - smem_base);
         for (int i = tid; i < 9 * 32 * 4; i += C::THREADS) {
-            int row = i >> 2, c = i & 3;
-            uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w + (size_t)row * 32 + c * 8));
+            const int row = i >> 2, c = i & 3;
+            const int kx = row / 96, rem = row - kx * 96;
+            const int ky = 2 - rem / 32, co = rem & 31;
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w + (size_t)((ky * 3 + kx) * 32 + co) * 32 + c * 8));
             *reinterpret_cast<uint4*>(wdst + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)) = v;
         }
         tc::fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async proxy
@@ -193,64 +209,62 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    if (warp >= 1 && warp < 5) {      // all accumulator slots start at zero: every MMA accumulates
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int s2 = 0; s2 < C::NSLOT; ++s2) tmem_st32_zero(lane_base + s2 * 32);
+        tmem_wait_st();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
 
     const int seg_stride = gridDim.x;
-    const int dbg = g_tc_dbg;
 
     if (warp == 0) {
-        // =========================== MMA issuer ===========================
-        // One thread issues everything, so its instruction count per MMA is the budget that matters: descriptors are
-        // kept as (lo, hi) halves, `hi` constant, `lo` = base + compile-time offset + slot * SLOT_BYTES/16.
+        // =========================== MMA issuer (one thread) ===========================
         if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(128, 32);
+            const uint32_t idesc32 = tc::make_idesc_bf16(128, 32), idesc64 = tc::make_idesc_bf16(128, 64), idesc96 = tc::make_idesc_bf16(128, 96);
             const uint64_t d0 = tc::make_desc_sw64(0, 512, 0);
             const uint32_t hi = (uint32_t)(d0 >> 32);
-            const uint32_t lo0 = (uint32_t)d0;                       // LBO field, start address 0
+            const uint32_t lo0 = (uint32_t)d0;
             const uint32_t a_lo0 = lo0 + (rows_s >> 4), b_lo0 = lo0 + (w_s >> 4);
-            const uint32_t row_ready = p.relu_in ? row_ready_t : row_landed;
-            uint32_t r_base = 0, t = 0;
+            uint32_t r = 0, t_base = 0;
             for (int seg = blockIdx.x; seg < p.total_segs; seg += seg_stride) {
                 const int rem = seg % (p.strips * p.segs_y);
                 const int sy = rem % p.segs_y;
                 const int y0 = sy * p.rows_per_seg;
                 const int nrows = min(y0 + p.rows_per_seg, p.H) - y0;
-                // rows r_base, r_base+1 are waited for here; every tile then waits only for its newest row
-                tc::mbar_wait(row_ready + 8 * (r_base % C::RB), (r_base / C::RB) & 1);
-                tc::mbar_wait(row_ready + 8 * ((r_base + 1) % C::RB), ((r_base + 1) / C::RB) & 1);
-                for (int j = 0; j < nrows; ++j, ++t) {
-                    const uint32_t as = t & 1;
-                    tc::mbar_wait(acc_empty + 8 * as, ((t >> 1) & 1) ^ 1);
-                    const uint32_t rn = r_base + j + 2;
-                    tc::mbar_wait(row_ready + 8 * (rn % C::RB), (rn / C::RB) & 1);
-                    // rows were written through the generic proxy (cp.async / ReLU stores) and observed complete through the
-                    // mbarrier: order them before this thread's async-proxy (tensor core) reads
-                    if (!(dbg & 16)) tc::fence_proxy_async();
+                for (int i = 0; i < nrows + 2; ++i, ++r) {
+                    const uint32_t rs = r % C::RB;
+                    if (i < nrows) {                                   // first touch of the slot of output row i in this round
+                        const uint32_t tn = t_base + i;
+                        tc::mbar_wait(slot_empty + 8 * (tn % C::NSLOT), ((tn / C::NSLOT) & 1) ^ 1);
+                    }
+                    tc::mbar_wait(row_ready + 8 * rs, (r / C::RB) & 1);
                     tc::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + as * 32;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const uint32_t slot = (r_base + j + ky) % C::RB;
-                        const uint32_t a_lo = a_lo0 + slot * (C::SLOT_BYTES >> 4);
+                    const int j_lo = max(i - 2, 0), j_hi = min(i, nrows - 1);
+                    int cnt = j_hi - j_lo + 1;                         // 1..3 output rows receive this input row
+                    int b_row = (2 - i + j_lo) * 32;                   // first stacked-weight row: ky = i - j_lo
+                    uint32_t s0 = (t_base + j_lo) % C::NSLOT;
+                    const uint32_t a_lo = a_lo0 + rs * (C::SLOT_BYTES >> 4);
+                    while (cnt > 0) {
+                        const int c1 = min(cnt, C::NSLOT - (int)s0);   // contiguous TMEM slots before the ring wraps
+                        const uint32_t idesc = c1 == 3 ? idesc96 : (c1 == 2 ? idesc64 : idesc32);
+                        const uint32_t d_tmem = tmem_base + s0 * 32;
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
                             for (int ks = 0; ks < 2; ++ks) {
-                                if ((dbg & 1) && (ky | kx | ks)) continue;
-                                const uint32_t a_off = kx * 4 + ks * 2;                  // one pixel = 64 B = 4 x 16 B; K step = 32 B
-                                const uint32_t b_off = (ky * 3 + kx) * 128 + ks * 2;
-                                if (ky == 0 && kx == 0 && ks == 0)
-                                    tc::umma_f16_split<false>(d_tmem, a_lo + a_off, hi, b_lo0 + b_off, hi, idesc);
-                                else
-                                    tc::umma_f16_split<true>(d_tmem, a_lo + a_off, hi, b_lo0 + b_off, hi, idesc);
+                                if ((dbg & 1) && (kx | ks)) continue;
+                                tc::umma_f16_split<true>(d_tmem, a_lo + kx * 4 + ks * 2, hi, b_lo0 + (kx * 96 + b_row) * 4 + ks * 2, hi, idesc);
                             }
                         }
+                        cnt -= c1; b_row += c1 * 32; s0 = 0;
                     }
-                    tc::umma_commit(acc_full + 8 * as);                                   // accumulator ready for the epilogue
-                    tc::umma_commit(row_free + 8 * ((r_base + j) % C::RB));               // oldest row no longer needed
+                    tc::umma_commit(row_free + 8 * rs);                                    // this input row is never read again
+                    if (i >= 2) tc::umma_commit(slot_full + 8 * ((t_base + i - 2) % C::NSLOT));   // output row i-2 is complete
                 }
-                tc::umma_commit(row_free + 8 * ((r_base + nrows) % C::RB));               // the two trailing halo rows of the segment
-                tc::umma_commit(row_free + 8 * ((r_base + nrows + 1) % C::RB));
-                r_base += nrows + 2;
+                t_base += nrows;
             }
         }
     } else if (warp < 5) {
@@ -267,13 +281,18 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
             const int x = sx * 128 + q * 32 + lane, y0 = sy * p.rows_per_seg;
             const int y1 = min(y0 + p.rows_per_seg, p.H);
             for (int y = y0; y < y1; ++y, ++t) {
-                const uint32_t as = t & 1;
-                tc::mbar_wait(acc_full + 8 * as, (t >> 1) & 1);
+                const uint32_t sl = t % C::NSLOT;
+                tc::mbar_wait(slot_full + 8 * sl, (t / C::NSLOT) & 1);
                 tc::tc_fence_after();
                 uint32_t v[32];
-                if (!(dbg & 8)) tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 32, v);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + sl * 32;
+                if (!(dbg & 8)) {
+                    tc::tmem_ld32(taddr, v);
+                    tmem_st32_zero(taddr);               // hand the slot back zeroed
+                    tmem_wait_st();
+                }
                 tc::tc_fence_before();
-                tc::mbar_arrive(acc_empty + 8 * as);     // values are in registers: the MMA warp may overwrite the stage
+                tc::mbar_arrive(slot_empty + 8 * sl);
                 if (x < p.W && !(dbg & 2)) {
                     const size_t off = (((size_t)n * p.H + y) * p.W + x) * 32;
                     float f[32];
@@ -325,7 +344,7 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
         // =========================== loaders: global -> shared (cp.async, SW64 swizzle) ===========================
         // Thread tt owns 16 B chunks tt, tt+128, ... of every row (pixel = chunk/4): coalesced 512 B per warp instruction.
         // Loaders never wait for data: completion is signalled to `row_landed` by cp.async.mbarrier.arrive.noinc, so up to
-        // RB-3 rows (108 KB per SM) stay in flight.
+        // RB-1 rows stay in flight.
         const int tt = tid - 160;                        // 0..127
         uint32_t r = 0;
         for (int seg = blockIdx.x; seg < p.total_segs; seg += seg_stride) {
@@ -355,19 +374,19 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
         }
         cp_async_wait_all();
     } else {
-        // =========================== prologue transform: ReLU in place on landed rows ===========================
-        if (p.relu_in) {
-            const int tt = tid - 288;                    // 0..127
-            const bf162 z = __floats2bfloat162_rn(0.f, 0.f);
-            uint32_t r = 0;
-            for (int seg = blockIdx.x; seg < p.total_segs; seg += seg_stride) {
-                const int rem = seg % (p.strips * p.segs_y);
-                const int sy = rem % p.segs_y;
-                const int y0 = sy * p.rows_per_seg;
-                const int nload = min(y0 + p.rows_per_seg, p.H) - y0 + 2;
-                for (int k2 = 0; k2 < nload; ++k2, ++r) {
-                    const uint32_t slot = r % C::RB;
-                    tc::mbar_wait(row_landed + 8 * slot, (r / C::RB) & 1);
+        // =========================== transform: optional ReLU in place, then publish the row to the tensor core ===========================
+        const int tt = tid - 288;                        // 0..127
+        const bf162 z = __floats2bfloat162_rn(0.f, 0.f);
+        uint32_t r = 0;
+        for (int seg = blockIdx.x; seg < p.total_segs; seg += seg_stride) {
+            const int rem = seg % (p.strips * p.segs_y);
+            const int sy = rem % p.segs_y;
+            const int y0 = sy * p.rows_per_seg;
+            const int nload = min(y0 + p.rows_per_seg, p.H) - y0 + 2;
+            for (int k2 = 0; k2 < nload; ++k2, ++r) {
+                const uint32_t slot = r % C::RB;
+                tc::mbar_wait(row_landed + 8 * slot, (r / C::RB) & 1);
+                if (p.relu_in) {
                     uint4* b4 = reinterpret_cast<uint4*>(smem + (rows_s - smem_base) + slot * C::SLOT_BYTES);
                     // swizzling permutes 16 B chunks inside a pixel's 64 B only and ReLU is elementwise: walk linearly
 #pragma unroll
@@ -381,9 +400,11 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
                             b4[i] = v;
                         }
                     }
-                    tc::fence_proxy_async();
-                    tc::mbar_arrive(row_ready_t + 8 * slot);
                 }
+                // the row was written through the generic proxy (cp.async, ReLU stores) and observed complete through the
+                // mbarrier: order it before the tensor core's async-proxy reads, then hand it to the MMA thread
+                if (!(dbg & 16)) tc::fence_proxy_async();
+                tc::mbar_arrive(row_ready + 8 * slot);
             }
         }
     }
@@ -393,7 +414,7 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
     __syncthreads();
     if (warp == 0) {
         tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, 64);
+        tc::tmem_dealloc(tmem_base, 512);
     }
 }
 

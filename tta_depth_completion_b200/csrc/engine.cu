@@ -118,7 +118,10 @@ struct ptta_msgchn {
     int N, H, W;
     bool two_layers, has_heads;
     std::string prepare_mode;
-    cudaStream_t st = nullptr;      // stream of the call in flight
+    cudaStream_t st = nullptr;      // stream of the call in flight (helpers launch on `st`)
+    cudaStream_t st2 = nullptr;     // side stream: the zero-image branch runs concurrently with the real branch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_projbn = nullptr;
+    bool two_streams = true, fork_pending = false;
     Arena arena;
     size_t ws_bytes = 0;
     bool bound = false, packed = false;
@@ -143,6 +146,7 @@ struct ptta_msgchn {
     Map1 fd, fv, dcl, d12, d14;      // filtered depth / validity, clamped depth, pyramid
     // heads
     long long R = 0;
+    bf16 *h_an2 = nullptr; double* partial2 = nullptr;
     bf16 *h_a0z = nullptr, *h_a0r = nullptr, *h_an = nullptr, *h_pz = nullptr, *h_q0 = nullptr, *emb = nullptr, *ref = nullptr;
     bf16 *g_ref = nullptr, *g_a3 = nullptr, *g_a0 = nullptr;
     BnState bnProjZ, bnProjR, bnPred;
@@ -326,6 +330,7 @@ struct ptta_msgchn {
             auto lin = [&](LinearLayer& L) { L.pack = allocv<bf16>((size_t)L.in * L.out); L.pack_t = allocv<bf16>((size_t)L.in * L.out); };
             lin(proj0); lin(proj3); lin(pred0); lin(pred3);
             size_t rm = (size_t)R * 512;
+            h_an2 = allocv<bf16>(rm);
             h_a0z = allocv<bf16>(rm); h_a0r = allocv<bf16>(rm); h_an = allocv<bf16>(rm); h_pz = allocv<bf16>(rm); h_q0 = allocv<bf16>(rm);
             emb = allocv<bf16>(rm); ref = allocv<bf16>(rm);
             reg("emb", emb, 1, R, 512, 1, 1); reg("ref", ref, 1, R, 512, 1, 1);
@@ -348,6 +353,7 @@ struct ptta_msgchn {
         long long max_rows = std::max<long long>(R, 1);
         partial_doubles = (size_t)cdiv(max_rows, STATS_ROWS_PER_BLOCK) * 2 * 512;
         partial = allocv<double>(partial_doubles);
+        partial2 = allocv<double>(partial_doubles);
         size_t wg = std::max(wgrad_partial_bytes(N, H / 4, W / 4, 32, 128), wgrad_partial_bytes(N, H / 4, W / 4, 128, 32));
         wgrad_ws = (float*)arena.take(wg);
         losses = (LossScalars*)arena.take(sizeof(LossScalars));
@@ -680,7 +686,10 @@ struct ptta_msgchn {
         return head_fwd(Wt.p3, A.h, add, out);
     }
     int run_cascade(Branch& B, bool is_real) {
-        if (is_real) PTTA_TRY(run_encoder(enc1W, B.e1, d14.p, nullptr, nullptr, nullptr, nullptr));
+        if (is_real) {
+            PTTA_TRY(run_encoder(enc1W, B.e1, d14.p, nullptr, nullptr, nullptr, nullptr));
+            if (fork_pending) { PTTA_CUDA(cudaEventRecord(ev_fork, st)); fork_pending = false; }   // zero branch may start: pyramid, meta, enc1 done
+        }
         PTTA_TRY(run_decoder(dec1W, B.d1, B.e1, B.c[2], B.c[3], B.c[4], nullptr, B.d1.out));
         PTTA_TRY(up2_1(B.d1.out, nullptr, nullptr, B.p12));                        // p12 = up2(out14)
         PTTA_TRY(run_encoder(enc2W, B.e2, d12.p, B.p12.p, &B.d1.x4, &B.d1.x3, &B.d1.x2));
@@ -691,11 +700,13 @@ struct ptta_msgchn {
         return run_decoder(dec3W, B.d3, B.e3, B.c[0], B.c[1], B.c[2], B.p11.p, B.output);   // output = out11 + p11
     }
     int mlp(const LinearLayer& L0, const BnLayer& bn, const BnState& s, const LinearLayer& L3, const bf16* x, int in_dim, bf16* a0, bf16* out,
-            bool training) {
+            bool training, bf16* scratch, cudaEvent_t after_bn = nullptr, cudaEvent_t before_bn = nullptr) {
         PTTA_TRY(gemm(x, L0.pack, a0, L0.b, R, L0.out, in_dim));
+        if (before_bn) PTTA_CUDA(cudaStreamWaitEvent(st, before_bn, 0));      // running statistics are updated in the reference's order
         PTTA_TRY(bn_forward_stats(bn, s, a0, R, training));
-        PTTA_TRY(bn_apply(a0, nullptr, h_an, R, L0.out, s, 1));
-        return gemm(h_an, L3.pack, out, L3.b, R, L3.out, L3.in);
+        if (after_bn) PTTA_CUDA(cudaEventRecord(after_bn, st));
+        PTTA_TRY(bn_apply(a0, nullptr, scratch, R, L0.out, s, 1));
+        return gemm(scratch, L3.pack, out, L3.b, R, L3.out, L3.in);
     }
 
     int forward(const float* image, const float* isc, const float* ish, const float* sparse, float cap, bool training) {
@@ -709,17 +720,37 @@ struct ptta_msgchn {
         Map32 rc[5] = {real.c[0], real.c[1], real.c2raw, real.c[3], real.c[4]};
         PTTA_TRY(run_rgb_encoder(image, isc, ish, rc));
         PTTA_TRY(run_meta(real, training));
+        if (!training) return run_cascade(real, true);
+        const bool fork = two_streams && st2 != nullptr;
+        if (!fork) {
+            PTTA_TRY(run_cascade(real, true));
+            PTTA_TRY(zero_side());
+            return mlp(proj0, projBn, bnProjR, proj3, real.e3.x2.p, 32, h_a0r, ref, true, h_an);
+        }
+        // real branch on `st`; zero-image branch + its head GEMMs on `st2` (fork after encoder 1, join before the loss)
+        fork_pending = true;
         PTTA_TRY(run_cascade(real, true));
-        if (!training) return 0;
-        // zero-image branch (no_grad in the reference, network_exp_msg_chn_adapt.py:508-532); BN running statistics
-        // are updated a second time here, exactly as the reference does
+        {
+            cudaStream_t main = st;
+            double* main_partial = partial;
+            PTTA_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
+            st = st2; partial = partial2;
+            int rc2 = zero_side();
+            if (!rc2 && cudaEventRecord(ev_join, st2) != cudaSuccess) { set_error("cudaEventRecord failed"); rc2 = 2; }
+            st = main; partial = main_partial;
+            if (rc2) return rc2;
+        }
+        PTTA_TRY(mlp(proj0, projBn, bnProjR, proj3, real.e3.x2.p, 32, h_a0r, ref, true, h_an, nullptr, ev_projbn));
+        PTTA_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+        return 0;
+    }
+    // zero-image branch (no_grad in the reference, network_exp_msg_chn_adapt.py:508-532; BN running statistics are updated a second
+    // time here, exactly as the reference does) and emb = pred(proj(z_zero)) (:553); rows = pixels of the /4 map (NHWC)
+    int zero_side() {
         PTTA_TRY(run_meta(zero, true));
         PTTA_TRY(run_cascade(zero, false));
-        // heads (:551-554): emb = pred(proj(z_zero)), ref = proj(z_real); rows = pixels of the /4 map (NHWC)
-        PTTA_TRY(mlp(proj0, projBn, bnProjZ, proj3, zero.e3.x2.p, 32, h_a0z, h_pz, true));
-        PTTA_TRY(mlp(pred0, predBn, bnPred, pred3, h_pz, 512, h_q0, emb, true));
-        PTTA_TRY(mlp(proj0, projBn, bnProjR, proj3, real.e3.x2.p, 32, h_a0r, ref, true));
-        return 0;
+        PTTA_TRY(mlp(proj0, projBn, bnProjZ, proj3, zero.e3.x2.p, 32, h_a0z, h_pz, true, h_an2, ev_projbn));
+        return mlp(pred0, predBn, bnPred, pred3, h_pz, 512, h_q0, emb, true, h_an2);
     }
 
     // ---- losses (src/external_model_adapt.py:371-441) ----------------------------------------------------
@@ -1039,6 +1070,7 @@ int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepa
 void ptta_msgchn_destroy(ptta_msgchn* e) {
     if (!e) return;
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->st2) { cudaStreamDestroy(e->st2); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaEventDestroy(e->ev_projbn); }
     delete e;
 }
 size_t ptta_msgchn_workspace_bytes(const ptta_msgchn* e) { return e ? e->ws_bytes : 0; }
@@ -1050,6 +1082,12 @@ int ptta_msgchn_bind_workspace(ptta_msgchn* e, void* ws, size_t bytes, ptta_stre
     e->arena.base = (char*)ws;
     e->plan();
     e->bound = true; e->packed = false;
+    if (!e->st2) {
+        PTTA_CUDA(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
+        PTTA_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        PTTA_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+        PTTA_CUDA(cudaEventCreateWithFlags(&e->ev_projbn, cudaEventDisableTiming));
+    }
     PTTA_CUDA(cudaMemsetAsync(ws, 0, e->ws_bytes, (cudaStream_t)stream));
     AdamHyper hy;
     {
