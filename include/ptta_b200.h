@@ -46,11 +46,16 @@ int ptta_conv3x3(const void* in_bf16, void* out_bf16, const void* wpack_bf16, co
                  int prologue, const float* pro_scale, const float* pro_shift, float slope,
                  const void* mask_bf16, int mask_mode, const float* mask_scale, const float* mask_shift,
                  const void* add_bf16, ptta_stream_t stream);
-/* the 32->32 stride-1 case of ptta_conv3x3 on the tcgen05 tensor cores (TMEM accumulators, cp.async-fed SW64 operands) */
-int ptta_conv3x3_tc(const void* in_bf16, void* out_bf16, const void* wpack_bf16, const float* bias, int n, int h, int w,
+/* the 32->32 stride-1 case of ptta_conv3x3 on the tcgen05 tensor cores (TMA-fed SWIZZLE_128B pixel-pair rows, TMEM
+ * accumulators).  wimage = ptta_pack_conv_weight_tc(wpack): the 18 KB shared-memory image of the [9][32][32] pack.
+ * W must be even; relu_in must be 0 (producers store ReLU(x) via relu_out); mask semantics: out = add + [mask>0]*(conv+bias) */
+int ptta_pack_conv_weight_tc(const void* wpack_bf16, void* wimage_bf16, ptta_stream_t stream);
+int ptta_conv3x3_tc(const void* in_bf16, void* out_bf16, const void* wimage_bf16, const float* bias, int n, int h, int w,
                     int relu_in, int relu_out, const void* mask_bf16, const void* add_bf16, ptta_stream_t stream);
 /* timing experiments only: bit mask of pipeline stages the tcgen05 conv skips (results are then wrong) */
 int ptta_debug_set(int mask);
+/* timing experiments only: per-row clock64() stamps of CTA 0 recorded by the tcgen05 conv when mask bit 64 is set */
+int ptta_debug_read_ts(long long* out_host, int n);
 /* weight gradient of a 3x3 stride-1 conv (autograd of the meta layer, network_exp_msg_chn_adapt.py:28-36) */
 size_t ptta_conv3x3_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout);
 int ptta_conv3x3_wgrad(const void* in_bf16, const void* gout_bf16, float* dw, void* workspace,

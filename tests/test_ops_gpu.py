@@ -256,7 +256,7 @@ def test_gemm_tcgen05(ops, m, n, k):
     assert float((got - got2).abs().max()) <= 2.0 ** -6 * float(want.abs().max())     # both accumulate in fp32
 
 
-@pytest.mark.parametrize('n,h,w', [(1, 16, 128), (1, 24, 300), (2, 19, 37), (1, 88, 304), (1, 352, 1216)])
+@pytest.mark.parametrize('n,h,w', [(1, 16, 128), (1, 24, 300), (2, 19, 38), (1, 88, 304), (3, 64, 514), (1, 352, 1216)])
 def test_conv_tcgen05_matches_mma(ops, n, h, w):
     """the tcgen05 conv is bit-identical to the mma.sync kernel (same bf16 products, fp32 accumulation of 288 terms)"""
     g = torch.Generator().manual_seed(12)
@@ -266,12 +266,25 @@ def test_conv_tcgen05_matches_mma(ops, n, h, w):
     x = torch.randn((n, h, w, 32), generator=g).to(DEV).to(torch.bfloat16)
     m = torch.randn((n, h, w, 32), generator=g).to(DEV).to(torch.bfloat16)
     a = torch.randn((n, h, w, 32), generator=g).to(DEV).to(torch.bfloat16)
+    # producers store ReLU(x) (relu_out), so the tcgen05 kernel has no ReLU-on-load: feed it the ReLU'd map
     want = ops.conv3x3(x, wp, bias, ops.MODE_S1, ops.PRO_RELU)
-    got = ops.conv3x3_tc(x, wp, bias, relu_in=True)
-    assert_close_bf16(got.float().cpu(), want.float().cpu(), 'conv_tc relu', ulps=1.0)
+    got = ops.conv3x3_tc(torch.relu(x), wp, bias)
+    assert torch.equal(got, want), 'conv_tc forward is not bit-identical to mma.sync'
+    got = ops.conv3x3_tc(torch.relu(x), wp, bias, relu_out=True)
+    assert torch.equal(got, torch.relu(want)), 'conv_tc relu_out'
     want = ops.conv3x3(x, wp, None, ops.MODE_S1, ops.PRO_NONE, mask=m, mask_mode=ops.MASK_RELU, add=a)
-    got = ops.conv3x3_tc(x, wp, None, relu_in=False, mask=m, add=a)
-    assert_close_bf16(got.float().cpu(), want.float().cpu(), 'conv_tc mask+add', ulps=1.0)
+    got = ops.conv3x3_tc(x, wp, None, mask=m, add=a)
+    assert torch.equal(got, want), 'conv_tc mask+add is not bit-identical to mma.sync'
+    acc = a.clone()                                    # in-place accumulate (out aliases add), as the backward pass uses it
+    from tta_depth_completion_b200 import _lib
+    wi = ops.pack_conv_weight_tc(wp)
+    _lib.check(_lib.lib().ptta_conv3x3_tc(_lib.ptr(x), _lib.ptr(acc), _lib.ptr(wi), None, n, h, w, 0, 0, _lib.ptr(m), _lib.ptr(acc),
+                                          torch.cuda.current_stream().cuda_stream), 'conv3x3_tc in place')
+    assert torch.equal(acc, want), 'conv_tc in-place accumulate'
+    with pytest.raises(RuntimeError):
+        ops.conv3x3_tc(x, wp, bias, relu_in=True)      # not supported: must fail loudly
+    with pytest.raises(RuntimeError):
+        ops.conv3x3_tc(x[:, :, :w - 1].contiguous(), wp, bias)      # odd width
 
 
 def test_adam_matches_torch(ops):

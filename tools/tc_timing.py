@@ -1,28 +1,55 @@
+#!/usr/bin/env python
+"""GPU experiment: tcgen05 conv vs mma.sync conv, timed from a CUDA graph of 40 back-to-back launches (no host launch cost)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tta_depth_completion_b200 import ops, _lib
-dev='cuda'
+dev = 'cuda'
 g = torch.Generator().manual_seed(0)
 wt = (torch.randn((32, 32, 3, 3), generator=g) * (2.0 / 288) ** 0.5).to(dev)
-wp = ops.pack_conv_weight(wt, 'conv_fwd'); bias = torch.zeros(32, device=dev)
-def timeit(fn, xs, iters=40):
-    for i in range(5): fn(xs[i % len(xs)])
+wp = ops.pack_conv_weight(wt, 'conv_fwd'); wi = ops.pack_conv_weight_tc(wp); bias = torch.zeros(32, device=dev)
+
+
+def timeit(fn, xs, iters=40, graph=True):
+    for i in range(3):
+        fn(xs[i % len(xs)])
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters): fn(xs[i % len(xs)])
-    e1.record(); torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        if graph:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                for i in range(iters):
+                    fn(xs[i % len(xs)])
+            run = gr.replay
+        else:
+            def run():
+                for i in range(iters):
+                    fn(xs[i % len(xs)])
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        run()
+        e1.record(s)
+        torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3
-for shape in [(1,352,1216),(4,352,1216)]:
-    n,h,w=shape
-    xs=[torch.randn((n,h,w,32),device=dev).to(torch.bfloat16) for _ in range(max(2, min(8, int(300e6/(n*h*w*64)))))]
-    res=[]
-    for dbg in (0,1|2|4,1|2|4|8,1|2|4|16,1|2|4|8|16,8,16):
+
+
+for shape in [(1, 352, 1216), (4, 352, 1216), (1, 176, 608), (1, 88, 304)]:
+    n, h, w = shape
+    cnt = max(2, min(64, int(300e6 / (n * h * w * 64))))
+    xs = [torch.randn((n, h, w, 32), device=dev).to(torch.bfloat16) for _ in range(cnt)]
+    mk = torch.randn((n, h, w, 32), device=dev).to(torch.bfloat16)
+    res = []
+    for dbg in (0, 1, 2, 4, 1 | 2 | 4):
         _lib.lib().ptta_debug_set(dbg)
-        us=timeit(lambda x: ops.conv3x3_tc(x, wp, bias, relu_in=False), xs)
-        res.append('dbg%d %.1f'%(dbg,us))
+        res.append('dbg%d %.1f' % (dbg, timeit(lambda x: ops.conv3x3_tc(x, wp, bias, wimage=wi), xs)))
     _lib.lib().ptta_debug_set(0)
-    us=timeit(lambda x: ops.conv3x3_tc(x, wp, bias, relu_in=True, variant=0), xs); res.append('relu %.1f'%us)
-    us=timeit(lambda x: ops.conv3x3(x, wp, bias, ops.MODE_S1, ops.PRO_RELU), xs); res.append('mma %.1f'%us)
-    print(shape, ' | '.join(res), flush=True)
+    res.append('eager %.1f' % timeit(lambda x: ops.conv3x3_tc(x, wp, bias, wimage=wi), xs, graph=False))
+    res.append('mask %.1f' % timeit(lambda x: ops.conv3x3_tc(x, wp, bias, mask=mk, wimage=wi), xs))
+    res.append('mask+add %.1f' % timeit(lambda x: ops.conv3x3_tc(x, wp, bias, mask=mk, add=mk, wimage=wi), xs))
+    res.append('mma %.1f' % timeit(lambda x: ops.conv3x3(x, wp, bias, ops.MODE_S1, ops.PRO_RELU), xs))
+    res.append('mma mask+add %.1f' % timeit(lambda x: ops.conv3x3(x, wp, bias, ops.MODE_S1, ops.PRO_NONE, mask=mk, mask_mode=ops.MASK_RELU, add=mk), xs))
+    gb = 2 * n * h * w * 64 / 1e3
+    print(shape, ' | '.join(res), '| tc %.0f GB/s' % (gb / float(res[0].split()[1])), flush=True)

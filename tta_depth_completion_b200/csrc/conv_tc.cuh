@@ -18,13 +18,14 @@
 // accumulators (2 x 32 TMEM columns) overlap the epilogue of row y with the MMAs of row y+1.
 #pragma once
 #include <cuda.h>
+#include <vector>
 #include "common.cuh"
 #include "conv_mma.cuh"
 
 namespace ptta {
 
 struct ConvTcParams {
-    const bf16* w;       // [9][32][32] (tap, cout, cin)
+    const bf16* w;       // 18 KB shared-memory image of the weights (pack_conv_weight_tc_kernel)
     const float* bias;   // [32] or null
     bf16* out;
     const bf16* mask;    // relu-derivative mask source (same shape as out) or null
@@ -128,25 +129,29 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 
 }  // namespace tc
 
-__device__ int g_tc_dbg = 0;   // timing experiments only (ptta_debug_set): 1 one MMA per row, 2 no epilogue stores, 4 no loads
+__device__ long long g_tc_ts[3 * 2048];   // timing experiments (dbg & 64): per-row clock64() stamps of CTA 0 (MMA | epilogue warp | producer)
+#define TC_TS(role, row, k) do { if ((dbg & 64) && blockIdx.x == 0 && (row) < 256) g_tc_ts[(role) * 2048 + (row) * 8 + (k)] = clock64(); } while (0)
+__device__ int g_tc_dbg = 0;   // timing experiments only (ptta_debug_set): 1 one MMA pair per row, 2 no epilogue stores, 4 no loads, 64 stamps
 
 struct ConvTcCfg {
-    static const int RB = 16;                     // input-row slots in the shared-memory ring (power of two: cheap index math)
-    static const int NSLOT = 16;                  // output-row accumulator slots in TMEM (16 x 32 columns = all 512)
-    static const int BOXW = 130;                  // pixels per staged row (128 + one halo pixel each side)
-    static const int SLOT_BYTES = 9216;           // 130 x 64 B rounded up to the 1024 B swizzle-pattern alignment
+    static const int RB = 8;                      // input-row slots in the shared-memory ring
+    static const int NSLOT = 8;                   // output-row accumulator slots per pixel parity (2 x 8 x 32 columns = all 512)
+    static const int BOXP = 130;                  // pixel PAIRS per staged row (128 + one halo pair each side)
+    static const int ROW_BYTES = BOXP * 128;      // 16640: what one TMA box delivers
+    static const int SLOT_BYTES = 17408;          // ROW_BYTES rounded up to the 1024 B swizzle-pattern alignment
     static const int W_BYTES = 9 * 32 * 64;       // 18432
+    static const int STAGE_BYTES = 4096;          // one epilogue warp's 32 pixel pairs x 128 B (output / `add` staging)
+    static const int MSTAGE_BYTES = 256;          // one epilogue warp's mask bits: one byte per 16 B chunk
+    static const int EPI_BYTES = 2 * STAGE_BYTES + MSTAGE_BYTES;
     static const int BAR_BYTES = 1024;
-    static const int SMEM = 1024 /*align slack*/ + RB * SLOT_BYTES + W_BYTES + BAR_BYTES;
-    static const int THREADS = 416;               // warp 0 MMA | warps 1-4 epilogue | warps 5-8 loaders | warps 9-12 transform
+    static const int SMEM = 1024 /*align slack*/ + RB * SLOT_BYTES + W_BYTES + 4 * EPI_BYTES + BAR_BYTES;
+    static const int THREADS = 192;               // warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 epilogue
 };
 
-// the mbarrier receives one arrival from this thread once all of its earlier cp.async copies have landed
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xFFFFFFFF;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+    return pred;
 }
 __device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
     const uint32_t z = 0;
@@ -155,93 +160,212 @@ __device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
         ::"r"(taddr), "r"(z) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+        "%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Scatter-form implicit GEMM.  Input row i of a segment (image row y0-1+i) contributes to output rows j = i-2, i-1, i with
-// the vertical taps ky = 2, 1, 0.  The three taps are stacked along N, so one group of 6 MMAs (3 horizontal taps x 2 K
-// steps, M128 x N96 x K16) consumes an input row exactly once and accumulates into three neighbouring 32-column TMEM
-// slots; slot(t) = t mod 16 for the running output-row counter t.  A slot is complete after input row j+2, is drained
-// and re-zeroed by the epilogue warps, and is reused 16 rows later.
-__global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const bf16* __restrict__ in, const ConvTcParams p) {
+// K-major SWIZZLE_128B operand descriptor: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+// one bit per bf16 of a 16 B chunk: value > 0
+__device__ __forceinline__ uint32_t positive_bits(const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t b = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        b |= ((short)(w[j] & 0xffffu) > 0 ? 1u : 0u) << (2 * j);
+        b |= ((int)w[j] >= 0x10000 ? 1u : 0u) << (2 * j + 1);
+    }
+    return b;
+}
+
+// bias / derivative mask / add / ReLU on one pixel's 32 accumulators -> four 16 B chunks of bf16
+// mbits: bit c set = keep channel c (all ones without a mask); addp: this pixel's four staged `add` chunks or null
+__device__ __forceinline__ void conv_tc_finish_pixel(const uint32_t (&v)[32], const float (&bias)[32], uint32_t mbits, const unsigned char* addrow,
+                                                     int chunk0, int swz, int relu_out, uint4 (&ov)[4]) {
+    float f[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) f[c] = (mbits >> c) & 1u ? __uint_as_float(v[c]) + bias[c] : 0.f;
+    if (addrow) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint4 av = *reinterpret_cast<const uint4*>(addrow + (((chunk0 + g) ^ swz) << 4));
+            const uint32_t* au = reinterpret_cast<const uint32_t*>(&av);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 a = unpack_bf162(au[j]);
+                f[g * 8 + j * 2] += a.x;
+                f[g * 8 + j * 2 + 1] += a.y;
+            }
+        }
+    }
+    if (relu_out) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.f);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        ov[g].x = pack_bf162(f[g * 8 + 0], f[g * 8 + 1]);
+        ov[g].y = pack_bf162(f[g * 8 + 2], f[g * 8 + 3]);
+        ov[g].z = pack_bf162(f[g * 8 + 4], f[g * 8 + 5]);
+        ov[g].w = pack_bf162(f[g * 8 + 6], f[g * 8 + 7]);
+    }
+}
+
+// [tap][cout][cin] bf16 (pack_conv_weight_kernel) -> the kernel's shared-memory weight image: row = kx*96 + (2-ky)*32 + cout,
+// 64 B per row, 16 B chunks XOR-swizzled exactly as SWIZZLE_64B lays them out at a 512 B aligned base.  One bulk copy stages it.
+__global__ void pack_conv_weight_tc_kernel(const bf16* __restrict__ pack, bf16* __restrict__ image) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * 32 * 4) return;
+    const int row = i >> 2, c = i & 3;
+    const int kx = row / 96, rem = row - kx * 96;
+    const int ky = 2 - rem / 32, co = rem & 31;
+    uint4 v = *reinterpret_cast<const uint4*>(pack + (size_t)((ky * 3 + kx) * 32 + co) * 32 + c * 8);
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(image) + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)) = v;
+}
+
+// Scatter-form implicit GEMM over PIXEL PAIRS.
+//
+// Shared-memory / TMA view of the NHWC bf16 input: [N][H][W/2][64] -- one 128 B row per pixel pair, SWIZZLE_128B, the layout
+// TMA moves at full speed (64 B rows do not).  A strip is 128 pairs = 256 output pixels wide; a staged input row holds 130
+// pairs (one halo pair each side, zero-filled by TMA outside the image = the convolution's padding).  The UMMA A operand is
+// "128 rows of 128 B"; a K = 16 slice at byte offset 0/32 of a row is the EVEN pixel of each pair, at 64/96 the ODD pixel,
+// and a descriptor may start at any pair row (the swizzle is a function of the shared-memory address).  Hence
+//     even output pixel 2j   = W[kx=0] . odd(j-1) + W[kx=1] . even(j) + W[kx=2] . odd(j)
+//     odd  output pixel 2j+1 = W[kx=0] . even(j)  + W[kx=1] . odd(j)  + W[kx=2] . even(j+1)
+// with no wasted FLOPs, and the even / odd outputs of one lane are 128 contiguous bytes of the output row.
+//
+// Vertical taps: input row i of a segment (image row y0-1+i) contributes to output rows j = i-2, i-1, i with ky = 2, 1, 0.
+// The three taps are stacked along N (weights pre-arranged as [kx][(2-ky)*32+cout][cin]), so 12 MMAs (2 parities x 3 kx x 2 K
+// steps, M128 x N96 x K16) consume an input row exactly once and accumulate into three neighbouring 32-column TMEM slots of
+// each parity bank; slot(t) = t mod 8 of the running output-row counter.  A slot is complete after input row j+2, is
+// drained and re-zeroed by the epilogue warps and reused 8 rows later.
+//
+// Roles: warp 0 TMA producer (one box per input row) | warp 1 MMA issuer (warp stays converged, elect.sync issues) |
+// warps 2-5 epilogue: TMEM -> registers -> bias / mask / add / ReLU -> bf16 -> warp-private transpose through shared
+// memory -> 512 B contiguous global stores.  Every mbarrier has one arrival per phase (slot_empty: one per epilogue warp).
+__global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTcParams p) {
     typedef ConvTcCfg C;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t rows_s = smem_base;                                   // RB row slots
     const uint32_t w_s = smem_base + C::RB * C::SLOT_BYTES;              // weights, SW64 canonical, row = kx*96 + (2-ky)*32 + cout
-    const uint32_t bar_s = w_s + C::W_BYTES;
-    const uint32_t row_landed = bar_s;                       // [RB]    loaders -> transform     (128 async arrivals, cp.async completion)
-    const uint32_t row_ready = bar_s + 8 * C::RB;            // [RB]    transform -> MMA        (128 arrivals, after ReLU + proxy fence)
-    const uint32_t row_free = bar_s + 16 * C::RB;            // [RB]    MMA -> loaders          (tcgen05.commit)
-    const uint32_t slot_full = bar_s + 24 * C::RB;           // [NSLOT] MMA -> epilogue         (tcgen05.commit)
-    const uint32_t slot_empty = slot_full + 8 * C::NSLOT;    // [NSLOT] epilogue -> MMA         (128 arrivals, slot re-zeroed)
-    const uint32_t tmem_slot = slot_empty + 8 * C::NSLOT;    // u32
+    const uint32_t stage_s = w_s + C::W_BYTES;                           // 4 epilogue warps x (out 4 KB | add 4 KB | mask bits 256 B)
+    const uint32_t bar_s = stage_s + 4 * C::EPI_BYTES;
+    const uint32_t row_full = bar_s;                         // [RB]    TMA     -> MMA       (expect_tx + complete_tx)
+    const uint32_t row_free = bar_s + 8 * C::RB;             // [RB]    MMA     -> producer  (tcgen05.commit)
+    const uint32_t slot_full = bar_s + 16 * C::RB;           // [NSLOT] MMA     -> epilogue  (tcgen05.commit)
+    const uint32_t slot_empty = slot_full + 8 * C::NSLOT;    // [NSLOT] epilogue -> MMA      (4 arrivals: one per epilogue warp)
+    const uint32_t w_full = slot_empty + 8 * C::NSLOT;       //         bulk copy of the weight image landed
+    const uint32_t tmem_ready = w_full + 8;                  //         accumulator slots zeroed (4 arrivals)
+    const uint32_t tmem_slot = tmem_ready + 8;               // u32
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dbg = g_tc_dbg;
+    if ((dbg & 64) && blockIdx.x == 0 && tid == 0) g_tc_ts[3 * 2048 - 8] = clock64();
 
-    // ---- one-time setup ----------------------------------------------------------------------------------
-    if (warp == 1 && lane == 0) {
+    // ---- one-time setup: one block-wide barrier, everything else overlaps with the first row loads ------------------
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_in);
         for (int i = 0; i < C::RB; ++i) {
-            tc::mbar_init(row_landed + 8 * i, 128);
-            tc::mbar_init(row_ready + 8 * i, 128);
+            tc::mbar_init(row_full + 8 * i, 1);
             tc::mbar_init(row_free + 8 * i, 1);
         }
         for (int i = 0; i < C::NSLOT; ++i) {
             tc::mbar_init(slot_full + 8 * i, 1);
-            tc::mbar_init(slot_empty + 8 * i, 128);
+            tc::mbar_init(slot_empty + 8 * i, 4);
         }
+        tc::mbar_init(w_full, 1);
+        tc::mbar_init(tmem_ready, 4);
         tc::fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
-    {   // weights -> shared memory: K-major SWIZZLE_64B, vertical taps stacked along N per horizontal tap
-        unsigned char* wdst = smem + (w_s - smem_base);
-        for (int i = tid; i < 9 * 32 * 4; i += C::THREADS) {
-            const int row = i >> 2, c = i & 3;
-            const int kx = row / 96, rem = row - kx * 96;
-            const int ky = 2 - rem / 32, co = rem & 31;
-            uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w + (size_t)((ky * 3 + kx) * 32 + co) * 32 + c * 8));
-            *reinterpret_cast<uint4*>(wdst + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)) = v;
-        }
-        tc::fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async proxy
-    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    if (warp >= 1 && warp < 5) {      // all accumulator slots start at zero: every MMA accumulates
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        for (int s2 = 0; s2 < C::NSLOT; ++s2) tmem_st32_zero(lane_base + s2 * 32);
-        tmem_wait_st();
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
+    if ((dbg & 64) && blockIdx.x == 0 && tid == 0) g_tc_ts[3 * 2048 - 7] = clock64();
 
     const int seg_stride = gridDim.x;
+    const int segs_per_image = p.strips * p.segs_y;
 
     if (warp == 0) {
-        // =========================== MMA issuer (one thread) ===========================
-        if (lane == 0) {
-            const uint32_t idesc32 = tc::make_idesc_bf16(128, 32), idesc64 = tc::make_idesc_bf16(128, 64), idesc96 = tc::make_idesc_bf16(128, 96);
-            const uint64_t d0 = tc::make_desc_sw64(0, 512, 0);
-            const uint32_t hi = (uint32_t)(d0 >> 32);
-            const uint32_t lo0 = (uint32_t)d0;
-            const uint32_t a_lo0 = lo0 + (rows_s >> 4), b_lo0 = lo0 + (w_s >> 4);
-            uint32_t r = 0, t_base = 0;
-            for (int seg = blockIdx.x; seg < p.total_segs; seg += seg_stride) {
-                const int rem = seg % (p.strips * p.segs_y);
-                const int sy = rem % p.segs_y;
-                const int y0 = sy * p.rows_per_seg;
-                const int nrows = min(y0 + p.rows_per_seg, p.H) - y0;
-                for (int i = 0; i < nrows + 2; ++i, ++r) {
-                    const uint32_t rs = r % C::RB;
-                    if (i < nrows) {                                   // first touch of the slot of output row i in this round
-                        const uint32_t tn = t_base + i;
-                        tc::mbar_wait(slot_empty + 8 * (tn % C::NSLOT), ((tn / C::NSLOT) & 1) ^ 1);
+        // =========================== TMA producer ===========================
+        if (elect_one()) {
+            tc::mbar_arrive_expect_tx(w_full, C::W_BYTES);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(w_s), "l"(p.w), "r"((uint32_t)C::W_BYTES), "r"(w_full) : "memory");
+        }
+        __syncwarp();
+        uint32_t r = 0;
+        for (int seg = blockIdx.x; seg < p.total_segs; seg += seg_stride) {
+            const int n = seg / segs_per_image;
+            const int rem = seg - n * segs_per_image;
+            const int sx = rem / p.segs_y, sy = rem - sx * p.segs_y;
+            const int y0 = sy * p.rows_per_seg;
+            const int y1 = min(y0 + p.rows_per_seg, p.H);
+            for (int yy = y0 - 1; yy <= y1; ++yy, ++r) {
+                const uint32_t slot = r % C::RB;
+                if (lane == 0) TC_TS(2, r, 0);
+                tc::mbar_wait(row_free + 8 * slot, ((r / C::RB) & 1) ^ 1);
+                if (lane == 0) TC_TS(2, r, 1);
+                if (elect_one()) {
+                    if (!(dbg & 4)) {
+                        tc::mbar_arrive_expect_tx(row_full + 8 * slot, C::ROW_BYTES);
+                        tc::tma_load_4d(rows_s + slot * C::SLOT_BYTES, &tmap_in, row_full + 8 * slot, 0, sx * 128 - 1, yy, n);
+                    } else {
+                        tc::mbar_arrive(row_full + 8 * slot);
                     }
-                    tc::mbar_wait(row_ready + 8 * rs, (r / C::RB) & 1);
-                    tc::tc_fence_after();
+                }
+                __syncwarp();
+                if (lane == 0) TC_TS(2, r, 2);
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer (converged warp, one elected lane issues) ===========================
+        const uint32_t idesc32 = tc::make_idesc_bf16(128, 32), idesc64 = tc::make_idesc_bf16(128, 64), idesc96 = tc::make_idesc_bf16(128, 96);
+        const uint64_t da0 = make_desc_sw128(0), db0 = tc::make_desc_sw64(0, 512, 0);
+        const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32);
+        const uint32_t a_lo0 = (uint32_t)da0 + (rows_s >> 4), b_lo0 = (uint32_t)db0 + (w_s >> 4);
+        uint32_t r = 0, t_base = 0;
+        tc::mbar_wait(w_full, 0);
+        tc::mbar_wait(tmem_ready, 0);
+        tc::tc_fence_after();
+        for (int seg = blockIdx.x; seg < p.total_segs; seg += seg_stride) {
+            const int rem = seg % segs_per_image;
+            const int sy = rem % p.segs_y;
+            const int y0 = sy * p.rows_per_seg;
+            const int nrows = min(y0 + p.rows_per_seg, p.H) - y0;
+            for (int i = 0; i < nrows + 2; ++i, ++r) {
+                const uint32_t rs = r % C::RB;
+                if (lane == 0) TC_TS(0, r, 0);
+                if (i < nrows) {                                   // first touch of the slot of output row i in this round
+                    const uint32_t tn = t_base + i;
+                    tc::mbar_wait(slot_empty + 8 * (tn % C::NSLOT), ((tn / C::NSLOT) & 1) ^ 1);
+                }
+                if (lane == 0) TC_TS(0, r, 1);
+                tc::mbar_wait(row_full + 8 * rs, (r / C::RB) & 1);
+                tc::tc_fence_after();
+                if (lane == 0) TC_TS(0, r, 2);
+                if (elect_one()) {
                     const int j_lo = max(i - 2, 0), j_hi = min(i, nrows - 1);
                     int cnt = j_hi - j_lo + 1;                         // 1..3 output rows receive this input row
                     int b_row = (2 - i + j_lo) * 32;                   // first stacked-weight row: ky = i - j_lo
@@ -250,13 +374,18 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
                     while (cnt > 0) {
                         const int c1 = min(cnt, C::NSLOT - (int)s0);   // contiguous TMEM slots before the ring wraps
                         const uint32_t idesc = c1 == 3 ? idesc96 : (c1 == 2 ? idesc64 : idesc32);
-                        const uint32_t d_tmem = tmem_base + s0 * 32;
+                        const uint32_t d_even = tmem_base + s0 * 32, d_odd = d_even + 32 * C::NSLOT;
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
+                            // 16 B units inside the slot: pair row = 8 units, odd pixel = +4, K step = +2
+                            const uint32_t ae = kx == 0 ? 4u : (kx == 1 ? 8u : 12u);      // odd(j-1) | even(j) | odd(j)
+                            const uint32_t ao = kx == 0 ? 8u : (kx == 1 ? 12u : 16u);     // even(j)  | odd(j)  | even(j+1)
 #pragma unroll
                             for (int ks = 0; ks < 2; ++ks) {
                                 if ((dbg & 1) && (kx | ks)) continue;
-                                tc::umma_f16_split<true>(d_tmem, a_lo + kx * 4 + ks * 2, hi, b_lo0 + (kx * 96 + b_row) * 4 + ks * 2, hi, idesc);
+                                const uint32_t b_lo = b_lo0 + (kx * 96 + b_row) * 4 + ks * 2;
+                                tc::umma_f16_split<true>(d_even, a_lo + ae + ks * 2, a_hi, b_lo, b_hi, idesc);
+                                tc::umma_f16_split<true>(d_odd, a_lo + ao + ks * 2, a_hi, b_lo, b_hi, idesc);
                             }
                         }
                         cnt -= c1; b_row += c1 * 32; s0 = 0;
@@ -264,147 +393,112 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
                     tc::umma_commit(row_free + 8 * rs);                                    // this input row is never read again
                     if (i >= 2) tc::umma_commit(slot_full + 8 * ((t_base + i - 2) % C::NSLOT));   // output row i-2 is complete
                 }
-                t_base += nrows;
+                __syncwarp();
+                if (lane == 0) TC_TS(0, r, 3);
             }
+            t_base += nrows;
         }
-    } else if (warp < 5) {
+    } else {
         // =========================== epilogue ===========================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        unsigned char* stage = smem + (stage_s - smem_base) + q * C::EPI_BYTES;       // output transpose
+        unsigned char* astage = stage + C::STAGE_BYTES;                               // `add` transpose
+        unsigned char* mstage = astage + C::STAGE_BYTES;                              // mask bits
+        {   // all accumulator slots start at zero: every MMA accumulates
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+            for (int s2 = 0; s2 < 2 * C::NSLOT; ++s2) tmem_st32_zero(lane_base + s2 * 32);
+            tmem_wait_st();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tmem_ready);
+        }
         float bias[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+        const int swz = lane & 7;
         uint32_t t = 0;
         for (int seg = blockIdx.x; seg < p.total_segs; seg += seg_stride) {
-            const int n = seg / (p.strips * p.segs_y);
-            const int rem = seg - n * p.strips * p.segs_y;
+            const int n = seg / segs_per_image;
+            const int rem = seg - n * segs_per_image;
             const int sx = rem / p.segs_y, sy = rem - sx * p.segs_y;
-            const int x = sx * 128 + q * 32 + lane, y0 = sy * p.rows_per_seg;
+            const int xw = sx * 256 + q * 64, y0 = sy * p.rows_per_seg;      // first pixel of this warp's 64
             const int y1 = min(y0 + p.rows_per_seg, p.H);
+            const int vp = min(32, (p.W - xw) / 2);                          // valid pixel pairs of this warp (may be <= 0)
             for (int y = y0; y < y1; ++y, ++t) {
                 const uint32_t sl = t % C::NSLOT;
+                const size_t off0 = (((size_t)n * p.H + y) * p.W + xw) * 32;     // first element of the warp's 64 pixels
+                // mask / add rows are fetched coalesced (512 B per warp instruction) BEFORE waiting for the accumulators
+                uint4 mk[8], ad[8];
+                if (p.mask) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int idx = k * 32 + lane;
+                        mk[k] = (idx >> 3) < vp ? __ldg(reinterpret_cast<const uint4*>(p.mask + off0 + (size_t)idx * 8)) : make_uint4(0, 0, 0, 0);
+                    }
+                }
+                if (p.add) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int idx = k * 32 + lane;
+                        ad[k] = (idx >> 3) < vp ? *reinterpret_cast<const uint4*>(p.add + off0 + (size_t)idx * 8) : make_uint4(0, 0, 0, 0);   // may alias `out`
+                    }
+                }
+                if (q == 2 && lane == 0) TC_TS(1, t, 0);
                 tc::mbar_wait(slot_full + 8 * sl, (t / C::NSLOT) & 1);
                 tc::tc_fence_after();
-                uint32_t v[32];
+                if (q == 2 && lane == 0) TC_TS(1, t, 1);
+                uint32_t ve[32], vo[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + sl * 32;
-                if (!(dbg & 8)) {
-                    tc::tmem_ld32(taddr, v);
-                    tmem_st32_zero(taddr);               // hand the slot back zeroed
-                    tmem_wait_st();
-                }
+                tmem_ld32_nowait(taddr, ve);
+                tmem_ld32_nowait(taddr + 32 * C::NSLOT, vo);
+                tmem_wait_ld();
+                tmem_st32_zero(taddr);               // hand the slots back zeroed
+                tmem_st32_zero(taddr + 32 * C::NSLOT);
+                tmem_wait_st();
                 tc::tc_fence_before();
-                tc::mbar_arrive(slot_empty + 8 * sl);
-                if (x < p.W && !(dbg & 2)) {
-                    const size_t off = (((size_t)n * p.H + y) * p.W + x) * 32;
-                    float f[32];
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(slot_empty + 8 * sl);
+                if (q == 2 && lane == 0) TC_TS(1, t, 2);
+                if (vp <= 0 || (dbg & 2)) continue;
+                // transpose mask bits / add chunks to "lane = pixel pair" through the warp's staging buffers
+                if (p.mask) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]) + bias[c];
+                    for (int k = 0; k < 8; ++k) mstage[k * 32 + lane] = (unsigned char)positive_bits(mk[k]);
+                }
+                if (p.add) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int idx = k * 32 + lane, pp = idx >> 3, c = idx & 7;
+                        *reinterpret_cast<uint4*>(astage + pp * 128 + ((c ^ (pp & 7)) << 4)) = ad[k];
+                    }
+                }
+                if (p.mask || p.add) __syncwarp();
+                if (lane < vp) {
+                    uint32_t me = 0xffffffffu, mo = 0xffffffffu;
                     if (p.mask) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint4 mv = __ldg(reinterpret_cast<const uint4*>(p.mask + off + g * 8));
-                            const uint32_t* mu = reinterpret_cast<const uint32_t*>(&mv);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 m = unpack_bf162(mu[j]);
-                                if (!(m.x > 0.f)) f[g * 8 + j * 2] = 0.f;
-                                if (!(m.y > 0.f)) f[g * 8 + j * 2 + 1] = 0.f;
-                            }
-                        }
+                        const uint2 mb = *reinterpret_cast<const uint2*>(mstage + lane * 8);
+                        me = mb.x; mo = mb.y;
                     }
-                    if (p.add) {
+                    const unsigned char* addrow = p.add ? astage + lane * 128 : nullptr;
+                    uint4 ov[4];
+                    conv_tc_finish_pixel(ve, bias, me, addrow, 0, swz, p.relu_out, ov);
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint4 av = *reinterpret_cast<const uint4*>(p.add + off + g * 8);
-                            const uint32_t* au = reinterpret_cast<const uint32_t*>(&av);
+                    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stage + lane * 128 + ((g ^ swz) << 4)) = ov[g];
+                    conv_tc_finish_pixel(vo, bias, mo, addrow, 4, swz, p.relu_out, ov);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 a = unpack_bf162(au[j]);
-                                f[g * 8 + j * 2] += a.x;
-                                f[g * 8 + j * 2 + 1] += a.y;
-                            }
-                        }
-                    }
-                    if (p.relu_out) {
+                    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stage + lane * 128 + (((g + 4) ^ swz) << 4)) = ov[g];
+                }
+                __syncwarp();
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.f);
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 ov;
-                        ov.x = pack_bf162(f[g * 8 + 0], f[g * 8 + 1]);
-                        ov.y = pack_bf162(f[g * 8 + 2], f[g * 8 + 3]);
-                        ov.z = pack_bf162(f[g * 8 + 4], f[g * 8 + 5]);
-                        ov.w = pack_bf162(f[g * 8 + 6], f[g * 8 + 7]);
-                        *reinterpret_cast<uint4*>(p.out + off + g * 8) = ov;
+                for (int k = 0; k < 8; ++k) {        // 512 contiguous bytes per warp instruction
+                    const int idx = k * 32 + lane, pp = idx >> 3, c = idx & 7;
+                    if (pp < vp) {
+                        uint4 val = *reinterpret_cast<const uint4*>(stage + pp * 128 + ((c ^ (pp & 7)) << 4));
+                        *reinterpret_cast<uint4*>(p.out + off0 + (size_t)idx * 8) = val;
                     }
                 }
-            }
-        }
-    } else if (warp < 9) {
-        // =========================== loaders: global -> shared (cp.async, SW64 swizzle) ===========================
-        // Thread tt owns 16 B chunks tt, tt+128, ... of every row (pixel = chunk/4): coalesced 512 B per warp instruction.
-        // Loaders never wait for data: completion is signalled to `row_landed` by cp.async.mbarrier.arrive.noinc, so up to
-        // RB-1 rows stay in flight.
-        const int tt = tid - 160;                        // 0..127
-        uint32_t r = 0;
-        for (int seg = blockIdx.x; seg < p.total_segs; seg += seg_stride) {
-            const int n = seg / (p.strips * p.segs_y);
-            const int rem = seg - n * p.strips * p.segs_y;
-            const int sx = rem / p.segs_y, sy = rem - sx * p.segs_y;
-            const int x0 = sx * 128, y0 = sy * p.rows_per_seg;
-            const int y1 = min(y0 + p.rows_per_seg, p.H);
-            for (int yy = y0 - 1; yy <= y1; ++yy, ++r) {
-                const uint32_t slot = r % C::RB;
-                tc::mbar_wait(row_free + 8 * slot, ((r / C::RB) & 1) ^ 1);
-                const uint32_t dst = rows_s + slot * C::SLOT_BYTES;
-                const bool row_ok = yy >= 0 && yy < p.H;
-                const bf16* row_src = in + ((size_t)n * p.H + (row_ok ? yy : 0)) * p.W * 32;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const int i = tt + k * 128;
-                    if (i < C::BOXW * 4 && !(dbg & 4)) {
-                        const int px = i >> 2, c = i & 3;
-                        const int x = x0 - 1 + px;
-                        const bool ok = row_ok && x >= 0 && x < p.W;
-                        cp_async16_zfill(dst + px * 64 + ((c ^ ((px >> 1) & 3)) << 4), row_src + (size_t)(ok ? x : 0) * 32 + c * 8, ok ? 16u : 0u);
-                    }
-                }
-                cp_async_mbar_arrive_noinc(row_landed + 8 * slot);
-            }
-        }
-        cp_async_wait_all();
-    } else {
-        // =========================== transform: optional ReLU in place, then publish the row to the tensor core ===========================
-        const int tt = tid - 288;                        // 0..127
-        const bf162 z = __floats2bfloat162_rn(0.f, 0.f);
-        uint32_t r = 0;
-        for (int seg = blockIdx.x; seg < p.total_segs; seg += seg_stride) {
-            const int rem = seg % (p.strips * p.segs_y);
-            const int sy = rem % p.segs_y;
-            const int y0 = sy * p.rows_per_seg;
-            const int nload = min(y0 + p.rows_per_seg, p.H) - y0 + 2;
-            for (int k2 = 0; k2 < nload; ++k2, ++r) {
-                const uint32_t slot = r % C::RB;
-                tc::mbar_wait(row_landed + 8 * slot, (r / C::RB) & 1);
-                if (p.relu_in) {
-                    uint4* b4 = reinterpret_cast<uint4*>(smem + (rows_s - smem_base) + slot * C::SLOT_BYTES);
-                    // swizzling permutes 16 B chunks inside a pixel's 64 B only and ReLU is elementwise: walk linearly
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        const int i = tt + k * 128;
-                        if (i < C::BOXW * 4) {
-                            uint4 v = b4[i];
-                            bf162* h = reinterpret_cast<bf162*>(&v);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) h[j] = __hmax2(h[j], z);
-                            b4[i] = v;
-                        }
-                    }
-                }
-                // the row was written through the generic proxy (cp.async, ReLU stores) and observed complete through the
-                // mbarrier: order it before the tensor core's async-proxy reads, then hand it to the MMA thread
-                if (!(dbg & 16)) tc::fence_proxy_async();
-                tc::mbar_arrive(row_ready + 8 * slot);
+                __syncwarp();                        // staging buffers are rewritten next row
+                if (q == 2 && lane == 0) TC_TS(1, t, 3);
             }
         }
     }
@@ -412,10 +506,11 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
     // ---- teardown -----------------------------------------------------------------------------------------
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 1) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
     }
+    if ((dbg & 64) && blockIdx.x == 0 && tid == 0) g_tc_ts[3 * 2048 - 6] = clock64();
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
@@ -449,28 +544,65 @@ inline int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int N, int H, int W
     return 0;
 }
 
+// NHWC bf16 [N,H,W,32] activation viewed as [N][H][W/2][64]: box = {64, 130 pairs, 1, 1}, SWIZZLE_128B, zero fill outside
+inline int make_tmap_pairs(CUtensorMap* map, const void* ptr, int N, int H, int W) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    PTTA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[4] = {64, (cuuint64_t)(W / 2), (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {128, (cuuint64_t)W * 64, (cuuint64_t)H * W * 64};
+    cuuint32_t box[4] = {64, (cuuint32_t)ConvTcCfg::BOXP, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PTTA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (N=%d H=%d W=%d)", (int)r, N, H, W);
+    return 0;
+}
+
+inline bool conv_tc_supported(int N, int H, int W) { return N >= 1 && H >= 1 && W >= 2 && (W % 2) == 0; }
+
+// tensor maps are cached per (pointer, shape): the engine's arena addresses are fixed, so a step encodes nothing
+inline int conv_tc_tmap(const bf16* in, int N, int H, int W, const CUtensorMap** out) {
+    struct Entry { const void* ptr; int n, h, w; CUtensorMap map; };
+    static thread_local std::vector<Entry> cache;
+    for (const Entry& e : cache)
+        if (e.ptr == in && e.n == N && e.h == H && e.w == W) { *out = &e.map; return 0; }
+    if (cache.size() >= 512) cache.clear();
+    Entry e; e.ptr = in; e.n = N; e.h = H; e.w = W;
+    PTTA_TRY(make_tmap_pairs(&e.map, in, N, H, W));
+    cache.push_back(e);
+    *out = &cache.back().map;
+    return 0;
+}
+
 inline int launch_conv_tc(const bf16* in, ConvTcParams p, cudaStream_t st) {
     typedef ConvTcCfg C;
-    static int max_ctas = 0;
-    if (!max_ctas) {
+    static int sms = 0;
+    if (!sms) {
         PTTA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        int dev = 0, sms = 0, occ = 0;
+        int dev = 0;
         PTTA_CUDA(cudaGetDevice(&dev));
         PTTA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        PTTA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv3x3_tc_kernel, C::THREADS, C::SMEM));
-        PTTA_CHECK(occ >= 1, "conv3x3_tc does not fit on an SM");
-        max_ctas = sms * occ;
     }
-    p.strips = cdiv(p.W, 128);
-    int want = 2 * 148;
-    int segs = cdiv(want, p.N * p.strips);
-    if (segs < 1) segs = 1;
-    if (segs > p.H) segs = p.H;
-    p.rows_per_seg = cdiv(p.H, segs);
+    PTTA_CHECK(conv_tc_supported(p.N, p.H, p.W), "conv3x3_tc: W=%d must be even", p.W);
+    PTTA_CHECK(!p.relu_in, "conv3x3_tc: ReLU-on-load is not supported (producers store ReLU(x): relu_out)");
+    p.strips = cdiv(p.W, 256);
+    // rows per segment: minimise waves x (rows + halo + fixed cost) over the segment counts that fill the machine
+    int best_rows = p.H; long long best_cost = -1;
+    for (int segs = 1; segs <= p.H; ++segs) {
+        const int rows = cdiv(p.H, segs);
+        const long long total = (long long)p.N * p.strips * cdiv(p.H, rows);
+        const long long waves = (total + sms - 1) / sms;
+        const long long cost = waves * (rows + 2 + 4);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_rows = rows; }
+    }
+    p.rows_per_seg = best_rows;
     p.segs_y = cdiv(p.H, p.rows_per_seg);
     p.total_segs = p.N * p.strips * p.segs_y;
-    int grid = p.total_segs < max_ctas ? p.total_segs : max_ctas;
-    conv3x3_tc_kernel<<<grid, C::THREADS, C::SMEM, st>>>(in, p);
+    int grid = p.total_segs < sms ? p.total_segs : sms;
+    const CUtensorMap* map = nullptr;
+    PTTA_TRY(conv_tc_tmap(in, p.N, p.H, p.W, &map));
+    conv3x3_tc_kernel<<<grid, C::THREADS, C::SMEM, st>>>(*map, p);
     return check_launch("conv3x3_tc");
 }
 

@@ -66,6 +66,7 @@ struct ConvLayer {
     bool transposed = false, has_bias = true;
     const float* w = nullptr; const float* b = nullptr;
     bf16* pack_fwd = nullptr; bf16* pack_dgrad = nullptr;
+    bf16* img_fwd = nullptr; bf16* img_dgrad = nullptr;     // tcgen05 weight images (32->32 stride-1 roles only)
     int mode_fwd = MODE_S1, mode_dgrad = MODE_S1;
 };
 struct StemLayer {   // init.0: {1,2,3} -> 32
@@ -122,6 +123,7 @@ struct ptta_msgchn {
     cudaStream_t st2 = nullptr;     // side stream: the zero-image branch runs concurrently with the real branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_projbn = nullptr;
     bool two_streams = true, fork_pending = false;
+    bool tc_enabled = true; long long tc_min_pixels = 60000;
     Arena arena;
     size_t ws_bytes = 0;
     bool bound = false, packed = false;
@@ -258,6 +260,10 @@ struct ptta_msgchn {
     void plan_conv(ConvLayer& L) {
         L.pack_fwd = allocv<bf16>((size_t)9 * L.cin * L.cout);
         L.pack_dgrad = allocv<bf16>((size_t)9 * L.cin * L.cout);
+        if (L.cin == 32 && L.cout == 32) {
+            L.img_fwd = L.mode_fwd == MODE_S1 ? allocv<bf16>(9 * 32 * 32) : nullptr;
+            L.img_dgrad = L.mode_dgrad == MODE_S1 ? allocv<bf16>(9 * 32 * 32) : nullptr;
+        }
     }
     void plan_enc_w(EncW& E) {
         E.init0.dgrad_ch1 = allocv<float>(288);
@@ -438,6 +444,14 @@ struct ptta_msgchn {
             pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(L.w, L.pack_dgrad, L.cin, L.cout, L.cout * 9, 9, 0);
             PTTA_TRY(check_launch("pack_dgrad_t"));
         }
+        if (L.img_fwd) {
+            pack_conv_weight_tc_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_fwd, L.img_fwd);
+            PTTA_TRY(check_launch("pack_fwd_tc"));
+        }
+        if (L.img_dgrad) {
+            pack_conv_weight_tc_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_dgrad, L.img_dgrad);
+            PTTA_TRY(check_launch("pack_dgrad_tc"));
+        }
         return 0;
     }
     int pack_enc(EncW& E) {
@@ -513,8 +527,18 @@ struct ptta_msgchn {
     }
 
     // ---- layer helpers ----------------------------------------------------------------------------------
-    int conv_fwd(const ConvLayer& L, const Map32& in, const Map32& out, int pro, const BnState* probn = nullptr) {
+    // the tcgen05 kernel takes the big 32->32 stride-1 maps; small maps (where any kernel is launch-bound) stay on mma.sync
+    bool use_tc(const Map32& m) const { return tc_enabled && conv_tc_supported(m.n, m.h, m.w) && (long long)m.n * m.h * m.w >= tc_min_pixels; }
+    int conv_tc(const bf16* image, const float* bias, const Map32& in, const Map32& out, int relu_out, const bf16* mask, const bf16* add) {
+        ConvTcParams p; memset(&p, 0, sizeof(p));
+        p.w = image; p.bias = bias; p.out = out.p; p.mask = mask; p.add = add; p.N = in.n; p.H = in.h; p.W = in.w; p.relu_out = relu_out;
+        return launch_conv_tc(in.p, p, st);
+    }
+    // relu_out: the output is only ever read through a ReLU (or as a ReLU mask), so ReLU(x) is what gets stored
+    int conv_fwd(const ConvLayer& L, const Map32& in, const Map32& out, int pro, const BnState* probn = nullptr, int relu_out = 0) {
+        if (L.img_fwd && pro == PRO_NONE && use_tc(in)) return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr);
         ConvParams p; memset(&p, 0, sizeof(p));
+        p.relu_out = relu_out;
         p.in = in.p; p.out = out.p; p.w = L.pack_fwd; p.bias = L.has_bias ? L.b : nullptr;
         p.N = in.n; p.Hin = in.h; p.Win = in.w; p.pro = pro; p.slope = 0.2f;
         if (probn) { p.pro_scale = probn->scale; p.pro_shift = probn->shift; }
@@ -523,6 +547,7 @@ struct ptta_msgchn {
     // gin = [add +] mask * dgrad(gout)
     int conv_dgrad(const ConvLayer& L, const Map32& gout, const Map32& gin, const bf16* mask, const bf16* add,
                    int mask_mode = MASK_RELU, const BnState* maskbn = nullptr) {
+        if (L.img_dgrad && (!mask || mask_mode == MASK_RELU) && use_tc(gout)) return conv_tc(L.img_dgrad, nullptr, gout, gin, 0, mask, add);
         ConvParams p; memset(&p, 0, sizeof(p));
         p.in = gout.p; p.out = gin.p; p.w = L.pack_dgrad; p.bias = nullptr;
         p.N = gout.n; p.Hin = gout.h; p.Win = gout.w; p.pro = PRO_NONE; p.slope = 0.2f;
@@ -530,9 +555,9 @@ struct ptta_msgchn {
         if (maskbn) { p.mask_scale = maskbn->scale; p.mask_shift = maskbn->shift; }
         return launch_conv3x3(p, L.cout, L.cin, L.mode_dgrad, st);
     }
-    int add32(const Map32& a, const Map32& b, const Map32& out) {
+    int add32(const Map32& a, const Map32& b, const Map32& out, int relu = 0) {
         long long n8 = (long long)a.numel() / 8;
-        ew_add_kernel<<<cdiv(n8, 256), 256, 0, st>>>(a.p, b.p, out.p, n8);
+        ew_add_kernel<<<cdiv(n8, 256), 256, 0, st>>>(a.p, b.p, out.p, n8, relu);
         return check_launch("ew_add");
     }
     int add_up2(const Map32& x, const Map32& half) {   // x += up2(half)
@@ -558,6 +583,7 @@ struct ptta_msgchn {
     int stem(const StemLayer& S, const float* p0, long long s0, float sc0, float sh0, const float* p1, long long s1, float sc1,
              float sh1, const float* p2, long long s2, float sc2, float sh2, const Map32& out) {
         StemParams p; memset(&p, 0, sizeof(p));
+        p.relu_out = 1;                 // init.0 outputs are consumed through ReLU only (and as ReLU masks in backward)
         p.plane[0] = p0; p.plane[1] = p1; p.plane[2] = p2;
         p.batch_stride[0] = s0; p.batch_stride[1] = s1; p.batch_stride[2] = s2;
         p.scale[0] = sc0; p.scale[1] = sc1; p.scale[2] = sc2; p.shift[0] = sh0; p.shift[1] = sh1; p.shift[2] = sh2;
@@ -578,7 +604,7 @@ struct ptta_msgchn {
     int head_dgrad(const HeadLayer& Hd, const Map1& gout, const Map32& hmask, const Map32& gh) {
         StemParams p; memset(&p, 0, sizeof(p));
         p.plane[0] = gout.p; p.batch_stride[0] = (long long)gout.h * gout.w; p.scale[0] = 1.f;
-        p.w = Hd.w_dgrad; p.bias = nullptr; p.mask = hmask.p; p.out = gh.p; p.N = gh.n; p.H = gh.h; p.W = gh.w;
+        p.w = Hd.w_dgrad; p.bias = nullptr; p.mask = hmask.p; p.out = gh.p; p.N = gh.n; p.H = gh.h; p.W = gh.w; p.relu_out = 0;
         long long tot = (long long)gh.n * gh.h * gh.w;
         stem_conv_kernel<1><<<cdiv(tot, 128), 128, 0, st>>>(p);
         return check_launch("head_dgrad");
@@ -638,11 +664,11 @@ struct ptta_msgchn {
             PTTA_TRY(stem(rgbW.init0, base, 3 * hw, s[0], b[0], base + hw, 3 * hw, s[1], b[1], base + 2 * hw, 3 * hw, s[2], b[2], rgbT[0]));
         else
             PTTA_TRY(stem(rgbW.init0, base, hw, 0.f, 0.f, base, hw, 0.f, 0.f, base, hw, 0.f, 0.f, rgbT[0]));
-        PTTA_TRY(conv_fwd(rgbW.init2, rgbT[0], c[0], PRO_RELU));
+        PTTA_TRY(conv_fwd(rgbW.init2, rgbT[0], c[0], PRO_NONE));
         const ConvLayer* ls[8] = {&rgbW.e1a, &rgbW.e1b, &rgbW.e2a, &rgbW.e2b, &rgbW.e3a, &rgbW.e3b, &rgbW.e4a, &rgbW.e4b};
         for (int k = 1; k <= 4; ++k) {
-            PTTA_TRY(conv_fwd(*ls[2 * (k - 1)], c[k - 1], rgbT[k], PRO_RELU));
-            PTTA_TRY(conv_fwd(*ls[2 * (k - 1) + 1], rgbT[k], c[k], PRO_RELU));
+            PTTA_TRY(conv_fwd(*ls[2 * (k - 1)], c[k - 1], rgbT[k], PRO_RELU, nullptr, 1));
+            PTTA_TRY(conv_fwd(*ls[2 * (k - 1) + 1], rgbT[k], c[k], PRO_NONE));
         }
         return 0;
     }
@@ -660,13 +686,14 @@ struct ptta_msgchn {
                     const Map32* pre_x2) {
         const long long hw = (long long)A.a0.h * A.a0.w;
         PTTA_TRY(stem(Wt.init0, p0, hw, 1.f, 0.f, p1 ? p1 : p0, hw, 1.f, 0.f, p0, hw, 0.f, 0.f, A.a0));
-        PTTA_TRY(conv_fwd(Wt.init2, A.a0, A.x0, PRO_RELU));
+        // a0, t1, t2 hold ReLU(.) (stored by their producers): the stride-1 convs need no prologue
+        PTTA_TRY(conv_fwd(Wt.init2, A.a0, A.x0, PRO_NONE));
         if (pre_x4) PTTA_TRY(add_up2(A.x0, *pre_x4));
-        PTTA_TRY(conv_fwd(Wt.e1a, A.x0, A.t1, PRO_RELU));
-        PTTA_TRY(conv_fwd(Wt.e1b, A.t1, A.x1, PRO_RELU));
+        PTTA_TRY(conv_fwd(Wt.e1a, A.x0, A.t1, PRO_RELU, nullptr, 1));
+        PTTA_TRY(conv_fwd(Wt.e1b, A.t1, A.x1, PRO_NONE));
         if (pre_x3) PTTA_TRY(add_up2(A.x1, *pre_x3));
-        PTTA_TRY(conv_fwd(Wt.e2a, A.x1, A.t2, PRO_RELU));
-        PTTA_TRY(conv_fwd(Wt.e2b, A.t2, A.x2, PRO_RELU));
+        PTTA_TRY(conv_fwd(Wt.e2a, A.x1, A.t2, PRO_RELU, nullptr, 1));
+        PTTA_TRY(conv_fwd(Wt.e2b, A.t2, A.x2, PRO_NONE));
         if (pre_x2) PTTA_TRY(add_up2(A.x2, *pre_x2));
         return 0;
     }
@@ -676,13 +703,14 @@ struct ptta_msgchn {
         PTTA_TRY(add32(E.x2, cx2, A.x2));
         PTTA_TRY(add32(E.x1, cx1, A.x1));
         PTTA_TRY(add32(E.x0, cx0, A.x0));
-        PTTA_TRY(conv_fwd(Wt.d2a, A.x2, A.u2, PRO_RELU));
-        PTTA_TRY(conv_fwd(Wt.d2b, A.u2, A.x3, PRO_RELU));
-        PTTA_TRY(add32(A.x1, A.x3, A.s1));
-        PTTA_TRY(conv_fwd(Wt.d1a, A.s1, A.u1, PRO_RELU));
-        PTTA_TRY(conv_fwd(Wt.d1b, A.u1, A.x4, PRO_RELU));
-        PTTA_TRY(add32(A.x4, A.x0, A.s0));
-        PTTA_TRY(conv_fwd(Wt.p1, A.s0, A.h, PRO_RELU));
+        // u2, s1, u1, s0, h hold ReLU(.): each is read through a ReLU only (forward) or as a ReLU mask (backward)
+        PTTA_TRY(conv_fwd(Wt.d2a, A.x2, A.u2, PRO_RELU, nullptr, 1));
+        PTTA_TRY(conv_fwd(Wt.d2b, A.u2, A.x3, PRO_NONE));
+        PTTA_TRY(add32(A.x1, A.x3, A.s1, 1));
+        PTTA_TRY(conv_fwd(Wt.d1a, A.s1, A.u1, PRO_NONE, nullptr, 1));
+        PTTA_TRY(conv_fwd(Wt.d1b, A.u1, A.x4, PRO_NONE));
+        PTTA_TRY(add32(A.x4, A.x0, A.s0, 1));
+        PTTA_TRY(conv_fwd(Wt.p1, A.s0, A.h, PRO_NONE, nullptr, 1));
         return head_fwd(Wt.p3, A.h, add, out);
     }
     int run_cascade(Branch& B, bool is_real) {
@@ -948,17 +976,29 @@ int ptta_conv3x3(const void* in, void* out, const void* wpack, const float* bias
     return launch_conv3x3(p, cin, cout, mode, (cudaStream_t)stream);
 }
 
-int ptta_conv3x3_tc(const void* in, void* out, const void* wpack, const float* bias, int n, int h, int w, int relu_in, int relu_out,
+int ptta_conv3x3_tc(const void* in, void* out, const void* wimage, const float* bias, int n, int h, int w, int relu_in, int relu_out,
                     const void* mask, const void* add, ptta_stream_t stream) {
-    PTTA_CHECK(in && out && wpack, "conv3x3_tc: null argument");
+    PTTA_CHECK(in && out && wimage, "conv3x3_tc: null argument");
     ConvTcParams p; memset(&p, 0, sizeof(p));
-    p.w = (const bf16*)wpack; p.bias = bias; p.out = (bf16*)out; p.mask = (const bf16*)mask; p.add = (const bf16*)add;
+    p.w = (const bf16*)wimage; p.bias = bias; p.out = (bf16*)out; p.mask = (const bf16*)mask; p.add = (const bf16*)add;
     p.N = n; p.H = h; p.W = w; p.relu_in = relu_in; p.relu_out = relu_out;
     return launch_conv_tc((const bf16*)in, p, (cudaStream_t)stream);
 }
 
+int ptta_pack_conv_weight_tc(const void* wpack, void* image, ptta_stream_t stream) {
+    PTTA_CHECK(wpack && image, "pack_conv_weight_tc: null argument");
+    pack_conv_weight_tc_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)wpack, (bf16*)image);
+    return check_launch("pack_conv_weight_tc");
+}
+
 int ptta_debug_set(int v) {
     PTTA_CUDA(cudaMemcpyToSymbol(g_tc_dbg, &v, sizeof(int)));
+    return 0;
+}
+
+int ptta_debug_read_ts(long long* out, int n) {
+    PTTA_CHECK(out && n > 0 && n <= 3 * 2048, "debug_read_ts: bad arguments");
+    PTTA_CUDA(cudaMemcpyFromSymbol(out, g_tc_ts, sizeof(long long) * n));
     return 0;
 }
 

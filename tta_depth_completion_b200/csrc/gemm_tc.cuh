@@ -24,17 +24,6 @@ struct GemmTcCfg {
     static const int THREADS = 192;               // warp 0 TMA | warp 1 MMA + TMEM alloc | warps 2-5 epilogue
 };
 
-// K-major SWIZZLE_128B operand descriptor: rows of 128 B, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-    return d;
-}
-
 __global__ void __launch_bounds__(GemmTcCfg::THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                        const __grid_constant__ CUtensorMap tmap_b, const GemmTcParams p) {
     typedef GemmTcCfg C;

@@ -115,6 +115,7 @@ struct StemParams {
     const bf16* mask;    // relu mask (NHWC 32) or null
     bf16* out;
     int N, H, W;
+    int relu_out;        // store ReLU(result): every consumer of an init.0 output applies ReLU first
 };
 
 template <int CIN>
@@ -167,6 +168,10 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams p) {
                 if (!(m.y > 0.f)) acc[q * 8 + j * 2 + 1] = 0.f;
             }
         }
+    }
+    if (p.relu_out) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = fmaxf(acc[c], 0.f);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -402,8 +407,8 @@ __global__ void up2_c32_adj_kernel(const bf16* __restrict__ gh, bf16* __restrict
     *reinterpret_cast<uint4*>(o) = ov;
 }
 
-// out = a + b (bf16, n multiple of 8)
-__global__ void ew_add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, long long n8) {
+// out = a + b, optionally ReLU'd (bf16, n multiple of 8)
+__global__ void ew_add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, long long n8, int relu) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n8) return;
     uint4 av = reinterpret_cast<const uint4*>(a)[i], bv = reinterpret_cast<const uint4*>(b)[i];
@@ -412,7 +417,9 @@ __global__ void ew_add_kernel(const bf16* __restrict__ a, const bf16* __restrict
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float2 fa = unpack_bf162(ua[j]), fb = unpack_bf162(ub[j]);
-        uo[j] = pack_bf162(fa.x + fb.x, fa.y + fb.y);
+        float s0 = fa.x + fb.x, s1 = fa.y + fb.y;
+        if (relu) { s0 = fmaxf(s0, 0.f); s1 = fmaxf(s1, 0.f); }
+        uo[j] = pack_bf162(s0, s1);
     }
     reinterpret_cast<uint4*>(out)[i] = ov;
 }

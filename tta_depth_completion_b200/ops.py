@@ -92,15 +92,27 @@ def conv3x3(x, wpack, bias=None, mode=MODE_S1, prologue=PRO_NONE, pro_scale=None
     return out
 
 
-def conv3x3_tc(x, wpack, bias=None, relu_in=True, relu_out=False, mask=None, add=None, variant=0):  # variant: unused
-    """32->32 stride-1 conv on tcgen05 (same operand conventions as conv3x3 with MODE_S1)."""
-    _need(x, torch.bfloat16, 'x')
+def pack_conv_weight_tc(wpack):
+    """[9][32][32] bf16 pack -> the tcgen05 kernel's 18 KB shared-memory weight image"""
     _need(wpack, torch.bfloat16, 'wpack')
+    if tuple(wpack.shape) != (9, 32, 32):
+        raise ValueError('pack_conv_weight_tc handles 32->32 channels only')
+    image = torch.empty((9 * 32 * 32,), dtype=torch.bfloat16, device=wpack.device)
+    check(_lib.lib().ptta_pack_conv_weight_tc(ptr(wpack), ptr(image), _stream()), 'pack_conv_weight_tc')
+    return image
+
+
+def conv3x3_tc(x, wpack, bias=None, relu_in=False, relu_out=False, mask=None, add=None, variant=0, wimage=None):  # variant: unused
+    """32->32 stride-1 conv on tcgen05 (same operand conventions as conv3x3 with MODE_S1, no ReLU-on-load).
+    Pass `wimage` (pack_conv_weight_tc) to skip the per-call weight-image kernel."""
+    _need(x, torch.bfloat16, 'x')
     n, h, w, cin = x.shape
-    if cin != 32 or tuple(wpack.shape) != (9, 32, 32):
+    if cin != 32:
         raise ValueError('conv3x3_tc handles 32->32 channels only')
+    if wimage is None:
+        wimage = pack_conv_weight_tc(wpack)
     out = torch.empty_like(x)
-    check(_lib.lib().ptta_conv3x3_tc(ptr(x), ptr(out), ptr(wpack), ptr(bias), n, h, w, 1 if relu_in else 0, 1 if relu_out else 0,
+    check(_lib.lib().ptta_conv3x3_tc(ptr(x), ptr(out), ptr(wimage), ptr(bias), n, h, w, 1 if relu_in else 0, 1 if relu_out else 0,
                                      ptr(mask), ptr(add), _stream()), 'conv3x3_tc')
     return out
 
