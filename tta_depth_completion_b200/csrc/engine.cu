@@ -597,7 +597,7 @@ struct ptta_msgchn {
     // prediction layer: out = conv32->1(relu(h)) + bias [+ add]
     int head_fwd(const HeadLayer& Hd, const Map32& h, const float* add, const Map1& out) {
         long long tot = (long long)out.numel();
-        head_conv_kernel<<<cdiv(tot, 128), 128, 0, st>>>(h.p, Hd.w_fwd, Hd.bias_host, add, out.p, out.n, out.h, out.w, 1, 0);
+        head_conv_kernel<<<dim3(cdiv(out.w, HEADC_TW), out.h, out.n), 128, 0, st>>>(h.p, Hd.w_fwd, Hd.bias_host, add, out.p, out.n, out.h, out.w, 1, 0);
         return check_launch("head_conv");
     }
     // g_h = dgrad_{1->32}(g_out) * [h > 0]
@@ -612,7 +612,7 @@ struct ptta_msgchn {
     // gradient wrt input plane 1 of a 2-plane stem: out = conv32->1(g_a0; flipped plane-1 weights) + add
     int stem_dgrad_ch1(const StemLayer& S, const Map32& ga0, const float* add, const Map1& out) {
         long long tot = (long long)out.numel();
-        head_conv_kernel<<<cdiv(tot, 128), 128, 0, st>>>(ga0.p, S.dgrad_ch1, 0.f, add, out.p, out.n, out.h, out.w, 0, 0);
+        head_conv_kernel<<<dim3(cdiv(out.w, HEADC_TW), out.h, out.n), 128, 0, st>>>(ga0.p, S.dgrad_ch1, 0.f, add, out.p, out.n, out.h, out.w, 0, 0);
         return check_launch("stem_dgrad");
     }
     int stats(const bf16* x, const bf16* dy, long long rows, int C, int mode, const BnState* s, int relu_mask, int& nblk) {
@@ -628,12 +628,11 @@ struct ptta_msgchn {
         if (training) PTTA_TRY(stats(x, nullptr, rows, L.c, 0, nullptr, 0, nblk));
         BnParams p; p.gamma = L.gamma; p.beta = L.beta; p.running_mean = L.rm; p.running_var = L.rv; p.num_batches_tracked = L.nbt;
         p.mean = s.mean; p.invstd = s.invstd; p.scale = s.scale; p.shift = s.shift; p.momentum = 0.1f; p.eps = 1e-5f;
-        bn_finalize_kernel<<<cdiv(L.c, 4), 128, 0, st>>>(partial, nblk, rows, L.c, p, training ? 1 : 0);
+        bn_finalize_kernel<<<cdiv(L.c, 32), FIN_THREADS, 0, st>>>(partial, nblk, rows, L.c, p, training ? 1 : 0);
         return check_launch("bn_finalize");
     }
     int bn_apply(const bf16* x, const bf16* res, bf16* y, long long rows, int C, const BnState& s, int act) {
-        long long tot = rows * (C / 8);
-        bn_apply_kernel<<<cdiv(tot, 256), 256, 0, st>>>(x, res, y, rows, C, s.scale, s.shift, act);
+        bn_apply_kernel<<<cdiv(rows, (256 / (C / 8)) * EW_ROWS), 256, 0, st>>>(x, res, y, rows, C, s.scale, s.shift, act);
         return check_launch("bn_apply");
     }
     // dx = BN-backward(dy [* relu mask]); optionally writes dgamma / dbeta
@@ -641,10 +640,9 @@ struct ptta_msgchn {
                     float* dgamma, float* dbeta) {
         int nblk = 0;
         PTTA_TRY(stats(x, dy, rows, L.c, 1, &s, relu_mask, nblk));
-        bn_bwd_finalize_kernel<<<cdiv(L.c, 4), 128, 0, st>>>(partial, nblk, rows, L.c, L.gamma, s.invstd, dgamma, dbeta, k0, k1, k2);
+        bn_bwd_finalize_kernel<<<cdiv(L.c, 32), FIN_THREADS, 0, st>>>(partial, nblk, rows, L.c, L.gamma, s.invstd, dgamma, dbeta, k0, k1, k2);
         PTTA_TRY(check_launch("bn_bwd_finalize"));
-        long long tot = rows * (L.c / 8);
-        bn_bwd_apply_kernel<<<cdiv(tot, 256), 256, 0, st>>>(dy, x, dx, rows, L.c, s.mean, s.invstd, k0, k1, k2, s.scale, s.shift, relu_mask);
+        bn_bwd_apply_kernel<<<cdiv(rows, (256 / (L.c / 8)) * EW_ROWS), 256, 0, st>>>(dy, x, dx, rows, L.c, s.mean, s.invstd, k0, k1, k2, s.scale, s.shift, relu_mask);
         return check_launch("bn_bwd_apply");
     }
     int gemm(const bf16* A, const bf16* B, bf16* C, const float* bias, long long M, int Nn, int K) {
@@ -875,7 +873,7 @@ struct ptta_msgchn {
             PTTA_TRY(launch_wgrad(wp, grad_of("conv1_rgb_meta.weight"), 32, 32, st));
             int nblk = 0;
             PTTA_TRY(stats(GC2.p, nullptr, rows, 32, 0, nullptr, 0, nblk));
-            colsum_finalize_kernel<<<8, 128, 0, st>>>(partial, nblk, 32, grad_of("conv1_rgb_meta.bias"));
+            colsum_finalize_kernel<<<1, FIN_THREADS, 0, st>>>(partial, nblk, 32, grad_of("conv1_rgb_meta.bias"));
             return check_launch("colsum_finalize");
         }
         const std::string p = "conv1_rgb_meta.conv1_meta";
@@ -884,7 +882,7 @@ struct ptta_msgchn {
         {
             int nblk = 0;
             PTTA_TRY(stats(G4a.p, nullptr, rows, 32, 0, nullptr, 0, nblk));
-            colsum_finalize_kernel<<<8, 128, 0, st>>>(partial, nblk, 32, grad_of(p + ".1.bias"));
+            colsum_finalize_kernel<<<1, FIN_THREADS, 0, st>>>(partial, nblk, 32, grad_of(p + ".1.bias"));
             PTTA_TRY(check_launch("colsum_finalize"));
         }
         {   // conv2 wgrad: input = leaky(bn1(mh))
@@ -1032,7 +1030,7 @@ int ptta_stem_conv(const float* const* planes, const long long* strides, const f
 int ptta_head_conv(const void* in, const float* w, float bias, const float* add, float* out, int n, int h, int ww, int relu_in,
                    int accumulate, ptta_stream_t stream) {
     long long tot = (long long)n * h * ww;
-    head_conv_kernel<<<cdiv(tot, 128), 128, 0, (cudaStream_t)stream>>>((const bf16*)in, w, bias, add, out, n, h, ww, relu_in, accumulate);
+    head_conv_kernel<<<dim3(cdiv(ww, HEADC_TW), h, n), 128, 0, (cudaStream_t)stream>>>((const bf16*)in, w, bias, add, out, n, h, ww, relu_in, accumulate);
     return check_launch("head_conv");
 }
 

@@ -122,65 +122,93 @@ template <int CIN>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams p) {
     __shared__ float s_w[CIN * 9 * 32];   // [ci][tap][co]
     __shared__ float s_b[32];
+    __shared__ __align__(16) unsigned char s_stage[4][2048];   // per warp: 32 pixels x 64 B (mask in, result out)
     for (int i = threadIdx.x; i < CIN * 9 * 32; i += blockDim.x) {
         int co = i & 31, r = i >> 5;       // r = ci*9 + tap
         s_w[i] = p.w[(size_t)co * CIN * 9 + r];
     }
     if (threadIdx.x < 32) s_b[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
     __syncthreads();
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)p.N * p.H * p.W;
-    if (idx >= total) return;
-    int x = idx % p.W;
-    int y = (idx / p.W) % p.H;
-    int n = idx / ((long long)p.W * p.H);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total = (long long)p.N * p.H * p.W;
+    const long long idx0 = (long long)blockIdx.x * blockDim.x + warp * 32;   // first pixel of this warp (pixels are contiguous in NHWC)
+    if (idx0 >= total) return;
+    const int nvalid = (int)min((long long)32, total - idx0);
+    const long long idx = idx0 + lane;
+    const bool valid = lane < nvalid;
+    unsigned char* stage = s_stage[warp];
+    const int swz = (lane >> 1) & 3;
+    // each warp instruction moves 512 contiguous bytes; lane l then owns pixel l's 64 B (16 B chunks XOR-swizzled: conflict-free)
+    if (p.mask) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.mask + (size_t)idx0 * 32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = k * 32 + lane, px = i >> 2, c = i & 3;
+            if (px < nvalid) *reinterpret_cast<uint4*>(stage + px * 64 + ((c ^ ((px >> 1) & 3)) << 4)) = __ldg(src + i);
+        }
+        __syncwarp();
+    }
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = s_b[c];
+    if (valid) {
+        const int x = idx % p.W;
+        const int y = (idx / p.W) % p.H;
+        const int n = idx / ((long long)p.W * p.H);
 #pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) {
-        const float* pl = p.plane[ci] + (size_t)n * p.batch_stride[ci];
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float* pl = p.plane[ci] + (size_t)n * p.batch_stride[ci];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            int gy = y + ky - 1;
-            if (gy < 0 || gy >= p.H) continue;
+            for (int ky = 0; ky < 3; ++ky) {
+                int gy = y + ky - 1;
+                if (gy < 0 || gy >= p.H) continue;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                int gx = x + kx - 1;
-                if (gx < 0 || gx >= p.W) continue;
-                float v = __ldg(pl + (size_t)gy * p.W + gx) * p.scale[ci] + p.shift[ci];
-                const float* wr = s_w + (ci * 9 + ky * 3 + kx) * 32;
+                for (int kx = 0; kx < 3; ++kx) {
+                    int gx = x + kx - 1;
+                    if (gx < 0 || gx >= p.W) continue;
+                    float v = __ldg(pl + (size_t)gy * p.W + gx) * p.scale[ci] + p.shift[ci];
+                    const float* wr = s_w + (ci * 9 + ky * 3 + kx) * 32;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+                    for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+                }
             }
         }
+        if (p.mask) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 mv = *reinterpret_cast<const uint4*>(stage + lane * 64 + ((q ^ swz) << 4));
+                const uint32_t* mu = reinterpret_cast<const uint32_t*>(&mv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 m = unpack_bf162(mu[j]);
+                    if (!(m.x > 0.f)) acc[q * 8 + j * 2] = 0.f;
+                    if (!(m.y > 0.f)) acc[q * 8 + j * 2 + 1] = 0.f;
+                }
+            }
+        }
+        if (p.relu_out) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = fmaxf(acc[c], 0.f);
+        }
     }
-    size_t o = (size_t)idx * 32;
-    if (p.mask) {
+    __syncwarp();                       // every lane is done with the staged mask
+    if (valid) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            uint4 mv = *reinterpret_cast<const uint4*>(p.mask + o + q * 8);
-            const uint32_t* mu = reinterpret_cast<const uint32_t*>(&mv);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 m = unpack_bf162(mu[j]);
-                if (!(m.x > 0.f)) acc[q * 8 + j * 2] = 0.f;
-                if (!(m.y > 0.f)) acc[q * 8 + j * 2 + 1] = 0.f;
-            }
+            uint4 ov;
+            ov.x = pack_bf162(acc[q * 8 + 0], acc[q * 8 + 1]);
+            ov.y = pack_bf162(acc[q * 8 + 2], acc[q * 8 + 3]);
+            ov.z = pack_bf162(acc[q * 8 + 4], acc[q * 8 + 5]);
+            ov.w = pack_bf162(acc[q * 8 + 6], acc[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(stage + lane * 64 + ((q ^ swz) << 4)) = ov;
         }
     }
-    if (p.relu_out) {
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)idx0 * 32);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = fmaxf(acc[c], 0.f);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint4 ov;
-        ov.x = pack_bf162(acc[q * 8 + 0], acc[q * 8 + 1]);
-        ov.y = pack_bf162(acc[q * 8 + 2], acc[q * 8 + 3]);
-        ov.z = pack_bf162(acc[q * 8 + 4], acc[q * 8 + 5]);
-        ov.w = pack_bf162(acc[q * 8 + 6], acc[q * 8 + 7]);
-        *reinterpret_cast<uint4*>(p.out + o + q * 8) = ov;
+    for (int k = 0; k < 4; ++k) {
+        const int i = k * 32 + lane, px = i >> 2, c = i & 3;
+        if (px < nvalid) dst[i] = *reinterpret_cast<const uint4*>(stage + px * 64 + ((c ^ ((px >> 1) & 3)) << 4));
     }
 }
 
@@ -189,44 +217,58 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams p) {
 // with ReLU-on-load, and -- with pre-flipped weights, no ReLU, accumulate -- the data-gradient of a
 // stem with respect to one of its input planes.  out = [acc_prev +] conv(in) + bias [+ add].
 // -------------------------------------------------------------------------------------------------
+// Block = 128 consecutive pixels of one output row: the three input rows (130 pixels each, zero padded) are staged in shared
+// memory with coalesced 16 B loads (ReLU applied on the way in), then every thread reads its 9 x 64 B taps conflict-free.
+// Launch: grid (cdiv(W, 128), H, N), 128 threads.
+#define HEADC_TW 128
 __global__ void __launch_bounds__(128) head_conv_kernel(const bf16* __restrict__ in, const float* __restrict__ w /*[9][32]*/,
                                                         float bias, const float* __restrict__ add, float* __restrict__ out,
                                                         int N, int H, int W, int relu_in, int accumulate) {
     __shared__ float s_w[9 * 32];
+    __shared__ __align__(16) unsigned char s_in[3 * (HEADC_TW + 2) * 64];
     for (int i = threadIdx.x; i < 288; i += blockDim.x) s_w[i] = w[i];
-    __syncthreads();
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)N * H * W;
-    if (idx >= total) return;
-    int x = idx % W;
-    int y = (idx / W) % H;
-    int n = idx / ((long long)W * H);
+    const int x0 = blockIdx.x * HEADC_TW, y = blockIdx.y, n = blockIdx.z;
     const bf16* inn = in + (size_t)n * H * W * 32;
+    const bf162 z = __floats2bfloat162_rn(0.f, 0.f);
+    for (int i = threadIdx.x; i < 3 * (HEADC_TW + 2) * 4; i += blockDim.x) {
+        const int c = i & 3, px = (i >> 2) % (HEADC_TW + 2), ry = (i >> 2) / (HEADC_TW + 2);
+        const int gy = y + ry - 1, gx = x0 + px - 1;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            v = __ldg(reinterpret_cast<const uint4*>(inn + ((size_t)gy * W + gx) * 32) + c);
+            if (relu_in) {
+                bf162* h = reinterpret_cast<bf162*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __hmax2(h[j], z);
+            }
+        }
+        const int row = ry * (HEADC_TW + 2) + px;
+        *reinterpret_cast<uint4*>(s_in + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)) = v;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= W) return;
     float acc = bias;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-        int gy = y + ky - 1;
-        if (gy < 0 || gy >= H) continue;
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-            int gx = x + kx - 1;
-            if (gx < 0 || gx >= W) continue;
-            const uint4* src = reinterpret_cast<const uint4*>(inn + ((size_t)gy * W + gx) * 32);
+            const int row = ky * (HEADC_TW + 2) + threadIdx.x + kx;
             const float* wr = s_w + (ky * 3 + kx) * 32;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                uint4 v = __ldg(src + q);
+                uint4 v = *reinterpret_cast<const uint4*>(s_in + row * 64 + ((q ^ ((row >> 1) & 3)) << 4));
                 const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float2 f = unpack_bf162(u[j]);
-                    if (relu_in) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
                     acc = fmaf(f.x, wr[q * 8 + j * 2], acc);
                     acc = fmaf(f.y, wr[q * 8 + j * 2 + 1], acc);
                 }
             }
         }
     }
+    const size_t idx = ((size_t)n * H + y) * W + x;
     if (add) acc += add[idx];
     if (accumulate) acc += out[idx];
     out[idx] = acc;
@@ -437,7 +479,7 @@ __global__ void ew_add_kernel(const bf16* __restrict__ a, const bf16* __restrict
 // `relu_mask`: the incoming dy is first multiplied by [x*scale+shift > 0] (the ReLU that follows BN
 // in the MLP heads), so no masked copy of dy is ever written.
 // -------------------------------------------------------------------------------------------------
-#define STATS_ROWS_PER_BLOCK 128
+#define STATS_ROWS_PER_BLOCK 64
 __global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, double* __restrict__ partial,
                                                         long long rows, int C, int mode, const float* __restrict__ mean,
                                                         const float* __restrict__ invstd, const float* __restrict__ scale,
@@ -460,6 +502,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__
             sc[j] = relu_mask ? scale[c * 8 + j] : 0.f; sh[j] = relu_mask ? shift[c * 8 + j] : 0.f;
         }
     }
+#pragma unroll 4
     for (long long r = row_begin + r0; r < row_end; r += step) {
         uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r * C + c * 8));
         const uint32_t* ux = reinterpret_cast<const uint32_t*>(&xv);
@@ -510,21 +553,33 @@ struct BnParams {
     float momentum, eps;
 };
 
-// sum of partial[k][slot][ch] over k, one warp per channel (fixed lane assignment + butterfly -> deterministic)
-__device__ __forceinline__ double warp_reduce_partials(const double* __restrict__ partial, int nblk, int C, int slot, int ch, int lane) {
-    double a = 0.0;
-    for (int k = lane; k < nblk; k += 32) a += partial[((size_t)k * 2 + slot) * C + ch];
-    return warp_sum_d(a);
+// sum of partial[k][slot][ch] over k for 32 channels per block: thread (cx = tid & 31, ks = tid >> 5) adds slice ks of the
+// partial list (256 B coalesced reads), the 8 slices are combined through shared memory in a fixed order (deterministic).
+// Returns the totals (a: slot 0, b: slot 1) in the threads with ks == 0; launch with FIN_THREADS threads, cdiv(C, 32) blocks.
+#define FIN_THREADS 256
+__device__ __forceinline__ bool block_reduce_partials(const double* __restrict__ partial, int nblk, int C, int nslots, int& ch, double& a, double& b) {
+    __shared__ double sh[2][8][32];
+    const int cx = threadIdx.x & 31, ks = threadIdx.x >> 5;
+    ch = blockIdx.x * 32 + cx;
+    a = 0.0; b = 0.0;
+    if (ch < C) {
+        for (int k = ks; k < nblk; k += 8) {
+            a += partial[((size_t)k * 2 + 0) * C + ch];
+            if (nslots > 1) b += partial[((size_t)k * 2 + 1) * C + ch];
+        }
+    }
+    sh[0][ks][cx] = a; sh[1][ks][cx] = b;
+    __syncthreads();
+    if (ks != 0 || ch >= C) return false;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { a += sh[0][k][cx]; b += sh[1][k][cx]; }
+    return true;
 }
 
-__global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C, BnParams p, int training) {
-    const int lane = threadIdx.x & 31;
-    const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (ch >= C) return;
+__global__ void __launch_bounds__(FIN_THREADS) bn_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C, BnParams p, int training) {
+    int ch; double a, b;
     if (training) {
-        double a = warp_reduce_partials(partial, nblk, C, 0, ch, lane);
-        double b = warp_reduce_partials(partial, nblk, C, 1, ch, lane);
-        if (lane != 0) return;
+        if (!block_reduce_partials(partial, nblk, C, 2, ch, a, b)) return;
         double m = a / (double)count;
         double var = b / (double)count - m * m;
         if (var < 0.0) var = 0.0;
@@ -541,7 +596,8 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restri
         }
         if (ch == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
     } else {
-        if (lane != 0) return;
+        ch = blockIdx.x * 32 + (threadIdx.x & 31);
+        if ((threadIdx.x >> 5) != 0 || ch >= C) return;
         float invstd = 1.f / sqrtf(p.running_var[ch] + p.eps);
         p.mean[ch] = p.running_mean[ch];
         p.invstd[ch] = invstd;
@@ -552,43 +608,49 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restri
 }
 
 // y = act(x*scale+shift) [+ res];  act: 0 none, 1 relu
-__global__ void bn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res, bf16* __restrict__ y, long long rows, int C,
+// thread = one 8-channel chunk x EW_ROWS rows (rows interleaved across the block's row groups: coalesced 16 B accesses);
+// the per-channel vectors are read once per thread.  Launch: blockDim 256, grid cdiv(rows, (256 / (C/8)) * EW_ROWS).
+#define EW_ROWS 8
+__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res, bf16* __restrict__ y, long long rows, int C,
                                 const float* __restrict__ scale, const float* __restrict__ shift, int act) {
-    const int CH = C / 8;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * CH) return;
-    int c = i % CH;
-    uint4 xv = reinterpret_cast<const uint4*>(x)[i];
-    const uint32_t* ux = reinterpret_cast<const uint32_t*>(&xv);
-    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-    if (res) rv = reinterpret_cast<const uint4*>(res)[i];
-    const uint32_t* ur = reinterpret_cast<const uint32_t*>(&rv);
-    uint4 ov; uint32_t* uo = reinterpret_cast<uint32_t*>(&ov);
+    const int CH = C / 8, step = 256 / CH;
+    const int c = threadIdx.x % CH, r0 = threadIdx.x / CH;
+    float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float2 f = unpack_bf162(ux[j]);
-        int ch = c * 8 + j * 2;
-        f.x = f.x * scale[ch] + shift[ch];
-        f.y = f.y * scale[ch + 1] + shift[ch + 1];
-        if (act == 1) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
-        if (res) { float2 r = unpack_bf162(ur[j]); f.x += r.x; f.y += r.y; }
-        uo[j] = pack_bf162(f.x, f.y);
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[c * 8 + j]; sh[j] = shift[c * 8 + j]; }
+    const long long rb = (long long)blockIdx.x * step * EW_ROWS + r0;
+#pragma unroll
+    for (int k = 0; k < EW_ROWS; ++k) {
+        const long long r = rb + (long long)k * step;
+        if (r >= rows) break;
+        const size_t i = (size_t)r * CH + c;
+        uint4 xv = reinterpret_cast<const uint4*>(x)[i];
+        const uint32_t* ux = reinterpret_cast<const uint32_t*>(&xv);
+        uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+        if (res) rv = reinterpret_cast<const uint4*>(res)[i];
+        const uint32_t* ur = reinterpret_cast<const uint32_t*>(&rv);
+        uint4 ov; uint32_t* uo = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_bf162(ux[j]);
+            f.x = f.x * sc[j * 2] + sh[j * 2];
+            f.y = f.y * sc[j * 2 + 1] + sh[j * 2 + 1];
+            if (act == 1) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+            if (res) { float2 rr = unpack_bf162(ur[j]); f.x += rr.x; f.y += rr.y; }
+            uo[j] = pack_bf162(f.x, f.y);
+        }
+        reinterpret_cast<uint4*>(y)[i] = ov;
     }
-    reinterpret_cast<uint4*>(y)[i] = ov;
 }
 
 // dgamma = sum dy*xhat, dbeta = sum dy;  dx = k0*dy - k1 - xhat*k2 with
 //   k0 = gamma*invstd, k1 = k0*mean(dy), k2 = k0*mean(dy*xhat)
-__global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C,
+__global__ void __launch_bounds__(FIN_THREADS) bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ k0, float* __restrict__ k1, float* __restrict__ k2) {
-    const int lane = threadIdx.x & 31;
-    const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (ch >= C) return;
-    double a = warp_reduce_partials(partial, nblk, C, 0, ch, lane);
-    double b = warp_reduce_partials(partial, nblk, C, 1, ch, lane);
-    if (lane != 0) return;
+    int ch; double a, b;
+    if (!block_reduce_partials(partial, nblk, C, 2, ch, a, b)) return;
     if (dbeta) dbeta[ch] = (float)a;
     if (dgamma) dgamma[ch] = (float)b;
     float g = gamma[ch] * invstd[ch];
@@ -597,40 +659,49 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const double* __re
     k2[ch] = (float)((double)g * b / (double)count);
 }
 
-__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, long long rows, int C,
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, long long rows, int C,
                                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ k0,
                                     const float* __restrict__ k1, const float* __restrict__ k2, const float* __restrict__ scale,
                                     const float* __restrict__ shift, int relu_mask) {
-    const int CH = C / 8;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * CH) return;
-    int c = i % CH;
-    uint4 xv = reinterpret_cast<const uint4*>(x)[i], gv = reinterpret_cast<const uint4*>(dy)[i];
-    const uint32_t *ux = reinterpret_cast<const uint32_t*>(&xv), *ug = reinterpret_cast<const uint32_t*>(&gv);
-    uint4 ov; uint32_t* uo = reinterpret_cast<uint32_t*>(&ov);
+    const int CH = C / 8, step = 256 / CH;
+    const int c = threadIdx.x % CH, r0 = threadIdx.x / CH;
+    float mu[8], is[8], a0[8], a1[8], a2[8], sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float2 f = unpack_bf162(ux[j]), g = unpack_bf162(ug[j]);
-        int ch = c * 8 + j * 2;
-        if (relu_mask) {
-            if (!(f.x * scale[ch] + shift[ch] > 0.f)) g.x = 0.f;
-            if (!(f.y * scale[ch + 1] + shift[ch + 1] > 0.f)) g.y = 0.f;
-        }
-        float xh0 = (f.x - mean[ch]) * invstd[ch], xh1 = (f.y - mean[ch + 1]) * invstd[ch + 1];
-        float o0 = k0[ch] * g.x - k1[ch] - xh0 * k2[ch];
-        float o1 = k0[ch + 1] * g.y - k1[ch + 1] - xh1 * k2[ch + 1];
-        uo[j] = pack_bf162(o0, o1);
+    for (int j = 0; j < 8; ++j) {
+        const int ch = c * 8 + j;
+        mu[j] = mean[ch]; is[j] = invstd[ch]; a0[j] = k0[ch]; a1[j] = k1[ch]; a2[j] = k2[ch];
+        sc[j] = relu_mask ? scale[ch] : 0.f; sh[j] = relu_mask ? shift[ch] : 0.f;
     }
-    reinterpret_cast<uint4*>(dx)[i] = ov;
+    const long long rb = (long long)blockIdx.x * step * EW_ROWS + r0;
+#pragma unroll
+    for (int k = 0; k < EW_ROWS; ++k) {
+        const long long r = rb + (long long)k * step;
+        if (r >= rows) break;
+        const size_t i = (size_t)r * CH + c;
+        uint4 xv = reinterpret_cast<const uint4*>(x)[i], gv = reinterpret_cast<const uint4*>(dy)[i];
+        const uint32_t *ux = reinterpret_cast<const uint32_t*>(&xv), *ug = reinterpret_cast<const uint32_t*>(&gv);
+        uint4 ov; uint32_t* uo = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_bf162(ux[j]), g = unpack_bf162(ug[j]);
+            if (relu_mask) {
+                if (!(f.x * sc[j * 2] + sh[j * 2] > 0.f)) g.x = 0.f;
+                if (!(f.y * sc[j * 2 + 1] + sh[j * 2 + 1] > 0.f)) g.y = 0.f;
+            }
+            float xh0 = (f.x - mu[j * 2]) * is[j * 2], xh1 = (f.y - mu[j * 2 + 1]) * is[j * 2 + 1];
+            float o0 = a0[j * 2] * g.x - a1[j * 2] - xh0 * a2[j * 2];
+            float o1 = a0[j * 2 + 1] * g.y - a1[j * 2 + 1] - xh1 * a2[j * 2 + 1];
+            uo[j] = pack_bf162(o0, o1);
+        }
+        reinterpret_cast<uint4*>(dx)[i] = ov;
+    }
 }
 
 // column sums of a [rows][C] bf16 matrix into fp32 (bias gradients): out[c] = sum_r x[r][c]; uses col_stats partials (mode 0, slot 0)
-__global__ void __launch_bounds__(128) colsum_finalize_kernel(const double* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (ch >= C) return;
-    double a = warp_reduce_partials(partial, nblk, C, 0, ch, lane);
-    if (lane == 0) out[ch] = (float)a;
+__global__ void __launch_bounds__(FIN_THREADS) colsum_finalize_kernel(const double* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
+    int ch; double a, b;
+    if (!block_reduce_partials(partial, nblk, C, 1, ch, a, b)) return;
+    out[ch] = (float)a;
 }
 
 // -------------------------------------------------------------------------------------------------
