@@ -81,6 +81,44 @@ int ptta_gemm_bf16_tc(const void* a, const void* b, void* c, const float* bias, 
 int ptta_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                    double lr, double beta1, double beta2, double eps, double weight_decay, int step, ptta_stream_t stream);
 
+/* ---- NLSPN non-local spatial propagation ----------------------------- */
+/* DCN.modulated_deform_conv_forward / _backward, the reference's one native FFI
+ * (external_src/NLSPN/src/model/deformconv/src/vision.cpp:6-13, modulated_deform_conv.h:10-87,
+ * cuda/modulated_deform_conv_cuda.cu:19-290): fp32 NCHW, offset [N, 2*kh*kw, Ho, Wo] ordered (dh, dw) per tap,
+ * mask [N, kh*kw, Ho, Wo], weight [C_out, C_in, kh, kw].  Implemented for what NLSPN calls: C_in = C_out = groups =
+ * deformable_groups = 1, square odd kernel <= 7, stride 1, dilation 1 (3x3 pad 1 propagation, 1x1 pad 0 confidence
+ * gather, nlspnmodel_adapt.py:300-304,332-336); anything else returns an error.  No columns buffer, no workspace.
+ * backward: grad_input / grad_weight / grad_bias may be null (then not computed); grad_input is zero-filled here. */
+int ptta_mdconv_forward(const float* input, const float* weight, const float* bias, const float* offset, const float* mask,
+                        float* output, int n, int c_in, int h, int w, int c_out, int kh, int kw, int stride, int pad, int dil,
+                        int groups, int deformable_groups, ptta_stream_t stream);
+int ptta_mdconv_backward(const float* input, const float* weight, const float* offset, const float* mask, const float* grad_output,
+                         float* grad_input, float* grad_offset, float* grad_mask, float* grad_weight, float* grad_bias,
+                         int n, int c_in, int h, int w, int c_out, int kh, int kw, int stride, int pad, int dil,
+                         int groups, int deformable_groups, ptta_stream_t stream);
+/* NLSPN._get_offset_affinity (nlspnmodel_adapt.py:255-330; affinity 'TGASS', k_f = 3): offset_aff [N,24,H,W] is the output
+ * of conv_offset_aff(guidance); confidence [N,1,H,W] or null (conf_prop off); legacy = the grid offset of :296-300.
+ * Outputs offset [N,18,H,W] and aff [N,9,H,W] in the layout ptta_nlspn_propagate_* and ptta_mdconv_* take.
+ * backward writes grad_offset_aff [N,24,H,W] and (zero-filled here, may be null) grad_confidence [N,1,H,W]. */
+int ptta_nlspn_offset_affinity_forward(const float* offset_aff, const float* confidence, float aff_scale_const, int legacy,
+                                       float* offset, float* aff, int n, int h, int w, ptta_stream_t stream);
+int ptta_nlspn_offset_affinity_backward(const float* offset_aff, const float* confidence, float aff_scale_const, int legacy,
+                                        const float* grad_offset, const float* grad_aff, float* grad_offset_aff, float* grad_confidence,
+                                        int n, int h, int w, ptta_stream_t stream);
+/* NLSPN.forward propagation loop (nlspnmodel_adapt.py:352-373): prop_time steps of
+ *   feat = feat_fix > 0 ? feat_fix : feat;  feat = sum_k aff_k * bilinear(feat, p + grid_k + offset_k)
+ * offset [N,18,H,W], aff [N,9,H,W] (after _get_offset_affinity), feat_* [N,1,H,W]; feat_fix may be null (preserve_input off).
+ * `saved` (ptta_nlspn_saved_bytes) receives the blended input of every step (needed by backward); `list_feat`
+ * (optional, [prop_time][N,H,W]) receives every step's output as the reference's list_feat does.
+ * backward: gradient of the final feature only (the TTA loss reads nothing else); scratch = ptta_nlspn_backward_scratch_bytes. */
+size_t ptta_nlspn_saved_bytes(int n, int h, int w, int prop_time);
+size_t ptta_nlspn_backward_scratch_bytes(int n, int h, int w);
+int ptta_nlspn_propagate_forward(const float* feat_init, const float* offset, const float* aff, const float* feat_fix, float* feat_out,
+                                 float* saved, float* list_feat, int n, int h, int w, int prop_time, ptta_stream_t stream);
+int ptta_nlspn_propagate_backward(const float* grad_out, const float* offset, const float* aff, const float* feat_fix, const float* saved,
+                                  float* grad_feat_init, float* grad_offset, float* grad_aff, float* scratch,
+                                  int n, int h, int w, int prop_time, ptta_stream_t stream);
+
 /* ---- MSG-CHN ProxyTTA engine ------------------------------------------------------------------- */
 /* prepare_mode: the reference's string, e.g. "meta_selfsup_seq_2layers_ema" (network_exp_msg_chn_adapt.py:1022-1087) */
 int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepare_mode);

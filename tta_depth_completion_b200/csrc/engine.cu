@@ -19,6 +19,7 @@
 #include "small_kernels.cuh"
 #include "conv_tc.cuh"
 #include "gemm_tc.cuh"
+#include "nlspn_prop.cuh"
 #include "../../include/ptta_b200.h"
 
 namespace ptta {
@@ -1085,6 +1086,114 @@ int ptta_adam_flat(float* p, const float* g, float* m, float* v, long long n, do
     int blocks = (int)std::min<long long>(cdiv(n, 256), 1184);
     adam_flat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, (float)eps, (float)wd, step);
     return check_launch("adam_flat");
+}
+
+// ---- NLSPN propagation path ------------------------------------------------------
+static int mdconv_check(int c_in, int c_out, int kh, int kw, int stride, int pad, int dil, int groups, int dgroups) {
+    PTTA_CHECK(c_in == 1 && c_out == 1 && groups == 1 && dgroups == 1,
+               "mdconv: only the single-channel configuration of NLSPN is implemented (got C_in=%d C_out=%d groups=%d deformable_groups=%d)",
+               c_in, c_out, groups, dgroups);
+    PTTA_CHECK(kh == kw && (kh & 1) && kh <= 7, "mdconv: kernel %dx%d must be square, odd and <= 7", kh, kw);
+    PTTA_CHECK(stride == 1 && dil == 1, "mdconv: stride %d / dilation %d not implemented (NLSPN uses 1 / 1)", stride, dil);
+    PTTA_CHECK(pad >= 0 && 2 * pad <= kh - 1, "mdconv: padding %d larger than (k-1)/2", pad);
+    return 0;
+}
+
+int ptta_mdconv_forward(const float* input, const float* weight, const float* bias, const float* offset, const float* mask, float* output,
+                        int n, int c_in, int h, int w, int c_out, int kh, int kw, int stride, int pad, int dil, int groups, int dgroups,
+                        ptta_stream_t stream) {
+    PTTA_CHECK(input && weight && offset && mask && output, "mdconv_forward: null argument");
+    PTTA_TRY(mdconv_check(c_in, c_out, kh, kw, stride, pad, dil, groups, dgroups));
+    const int ho = h + 2 * pad - (kh - 1), wo = w + 2 * pad - (kw - 1);
+    PTTA_CHECK(ho >= 1 && wo >= 1 && n >= 1, "mdconv_forward: empty output");
+    dim3 grid(cdiv(wo, PROP_TX), cdiv(ho, PROP_TY), n), block(PROP_TX, PROP_TY);
+    mdconv1_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(input, weight, bias, offset, mask, output, h, w, ho, wo, kh, pad);
+    return check_launch("mdconv1_forward");
+}
+
+int ptta_mdconv_backward(const float* input, const float* weight, const float* offset, const float* mask, const float* grad_output,
+                         float* grad_input, float* grad_offset, float* grad_mask, float* grad_weight, float* grad_bias,
+                         int n, int c_in, int h, int w, int c_out, int kh, int kw, int stride, int pad, int dil, int groups, int dgroups,
+                         ptta_stream_t stream) {
+    PTTA_CHECK(input && weight && offset && mask && grad_output, "mdconv_backward: null argument");
+    PTTA_TRY(mdconv_check(c_in, c_out, kh, kw, stride, pad, dil, groups, dgroups));
+    const int ho = h + 2 * pad - (kh - 1), wo = w + 2 * pad - (kw - 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (grad_input) PTTA_CUDA(cudaMemsetAsync(grad_input, 0, sizeof(float) * (size_t)n * h * w, st));
+    if (grad_weight) PTTA_CUDA(cudaMemsetAsync(grad_weight, 0, sizeof(float) * kh * kw, st));
+    if (grad_bias) PTTA_CUDA(cudaMemsetAsync(grad_bias, 0, sizeof(float), st));
+    dim3 grid(cdiv(wo, PROP_TX), cdiv(ho, PROP_TY), n), block(PROP_TX, PROP_TY);
+    mdconv1_backward_kernel<<<grid, block, 0, st>>>(input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask, grad_weight,
+                                                   grad_bias, h, w, ho, wo, kh, pad);
+    return check_launch("mdconv1_backward");
+}
+
+int ptta_nlspn_offset_affinity_forward(const float* offset_aff, const float* confidence, float aff_scale_const, int legacy, float* offset,
+                                       float* aff, int n, int h, int w, ptta_stream_t stream) {
+    PTTA_CHECK(offset_aff && offset && aff, "nlspn_offset_affinity_forward: null argument");
+    PTTA_CHECK(n >= 1 && h >= 1 && w >= 1, "nlspn_offset_affinity_forward: bad shape %dx%dx%d", n, h, w);
+    dim3 grid(cdiv(w, PROP_TX), cdiv(h, PROP_TY), n), block(PROP_TX, PROP_TY);
+    offset_affinity_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(offset_aff, confidence, 1.f / (aff_scale_const + 1e-8f), legacy, offset, aff,
+                                                                             h, w);
+    return check_launch("offset_affinity_forward");
+}
+int ptta_nlspn_offset_affinity_backward(const float* offset_aff, const float* confidence, float aff_scale_const, int legacy,
+                                        const float* grad_offset, const float* grad_aff, float* grad_offset_aff, float* grad_confidence,
+                                        int n, int h, int w, ptta_stream_t stream) {
+    PTTA_CHECK(offset_aff && grad_offset && grad_aff && grad_offset_aff, "nlspn_offset_affinity_backward: null argument");
+    PTTA_CHECK(!confidence == !grad_confidence || !grad_confidence, "nlspn_offset_affinity_backward: grad_confidence without confidence");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (grad_confidence) PTTA_CUDA(cudaMemsetAsync(grad_confidence, 0, sizeof(float) * (size_t)n * h * w, st));
+    dim3 grid(cdiv(w, PROP_TX), cdiv(h, PROP_TY), n), block(PROP_TX, PROP_TY);
+    offset_affinity_backward_kernel<<<grid, block, 0, st>>>(offset_aff, confidence, 1.f / (aff_scale_const + 1e-8f), legacy, grad_offset, grad_aff,
+                                                           grad_offset_aff, grad_confidence, h, w);
+    return check_launch("offset_affinity_backward");
+}
+
+size_t ptta_nlspn_saved_bytes(int n, int h, int w, int prop_time) { return sizeof(float) * (size_t)n * h * w * (size_t)(prop_time > 0 ? prop_time : 0); }
+size_t ptta_nlspn_backward_scratch_bytes(int n, int h, int w) { return sizeof(float) * 2 * (size_t)n * h * w; }
+
+int ptta_nlspn_propagate_forward(const float* feat_init, const float* offset, const float* aff, const float* feat_fix, float* feat_out,
+                                 float* saved, float* list_feat, int n, int h, int w, int prop_time, ptta_stream_t stream) {
+    PTTA_CHECK(feat_init && offset && aff && feat_out && saved, "nlspn_propagate_forward: null argument");
+    PTTA_CHECK(n >= 1 && h >= 1 && w >= 1 && prop_time >= 1, "nlspn_propagate_forward: bad shape %dx%dx%d, prop_time %d", n, h, w, prop_time);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)n * h * w;
+    prop_blend_kernel<<<cdiv(total, 256), 256, 0, st>>>(feat_init, feat_fix, saved, total);
+    PTTA_TRY(check_launch("prop_blend"));
+    dim3 grid(cdiv(w, PROP_TX), cdiv(h, PROP_TY), n), block(PROP_TX, PROP_TY);
+    for (int k = 0; k < prop_time; ++k) {
+        const bool last = k == prop_time - 1;
+        float* raw = last ? feat_out : (list_feat ? list_feat + (size_t)k * total : nullptr);
+        prop_step_kernel<<<grid, block, 0, st>>>(saved + (size_t)k * total, offset, aff, feat_fix, raw, last ? nullptr : saved + (size_t)(k + 1) * total,
+                                                h, w);
+        PTTA_TRY(check_launch("prop_step"));
+        if (last && list_feat) PTTA_CUDA(cudaMemcpyAsync(list_feat + (size_t)k * total, feat_out, sizeof(float) * total, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+int ptta_nlspn_propagate_backward(const float* grad_out, const float* offset, const float* aff, const float* feat_fix, const float* saved,
+                                  float* grad_feat_init, float* grad_offset, float* grad_aff, float* scratch, int n, int h, int w, int prop_time,
+                                  ptta_stream_t stream) {
+    PTTA_CHECK(grad_out && offset && aff && saved && grad_feat_init && grad_offset && grad_aff && scratch, "nlspn_propagate_backward: null argument");
+    PTTA_CHECK(n >= 1 && h >= 1 && w >= 1 && prop_time >= 1, "nlspn_propagate_backward: bad shape %dx%dx%d, prop_time %d", n, h, w, prop_time);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)n * h * w;
+    float* a = scratch;
+    float* b = scratch + total;
+    PTTA_CUDA(cudaMemcpyAsync(a, grad_out, sizeof(float) * total, cudaMemcpyDeviceToDevice, st));
+    PTTA_CUDA(cudaMemsetAsync(b, 0, sizeof(float) * total, st));
+    dim3 grid(cdiv(w, PROP_TX), cdiv(h, PROP_TY), n), block(PROP_TX, PROP_TY);
+    for (int k = prop_time - 1; k >= 0; --k) {
+        const bool first = k == prop_time - 1;
+        prop_step_backward_kernel<<<grid, block, 0, st>>>(saved + (size_t)k * total, offset, aff, feat_fix, a, b, grad_offset, grad_aff, h, w,
+                                                         first ? 0 : 1, first ? 0 : 1);
+        PTTA_TRY(check_launch("prop_step_backward"));
+        float* t = a; a = b; b = t;          // `a` now holds the gradient wrt this step's blended input; `b` has been cleared
+    }
+    prop_mask_grad_kernel<<<cdiv(total, 256), 256, 0, st>>>(a, feat_fix, grad_feat_init, total);
+    return check_launch("prop_mask_grad");
 }
 
 // ---- engine ---------------------------------------------------------------------------------------
