@@ -11,7 +11,7 @@ W_SD, W_SM, W_COS = 1.0, 1.0, 0.1
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.pt')))
+    return sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, 'msgchn_*.pt')))
 
 
 def load_golden(name):
