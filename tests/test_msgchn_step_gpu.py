@@ -100,7 +100,7 @@ def eng_adapt_names(model):
     return list(model.model._adapt_names)
 
 
-@pytest.mark.parametrize('name', ALIGNED)
+@pytest.mark.parametrize('name', golden_names())      # includes the H, W % 16 != 0 case (pad + flip-pad ensembling, a4)
 def test_step_matches_reference_fixture(name):
     fx = load_golden(name)
     case = fx['case']
@@ -250,5 +250,8 @@ def test_errors_are_loud():
     model._prepare_head('meta_selfsup_seq_2layers_ema')
     with pytest.raises(NotImplementedError):
         model.adapt_parameters('bn')
-    with pytest.raises(NotImplementedError):
-        model.forward(torch.zeros(1, 3, 40, 72, device=DEV), torch.zeros(1, 1, 40, 72, device=DEV), loss_type='adapt')
+    model.train()
+    out, emb, ref = model.forward(torch.zeros(1, 3, 40, 72, device=DEV), torch.zeros(1, 1, 40, 72, device=DEV), loss_type='adapt')
+    assert tuple(out.shape) == (1, 1, 40, 72) and emb.shape[0] == 2 * (48 // 4) * (80 // 4)     # padded to 48x80, flip pair -> 2 images of rows
+    with pytest.raises(ValueError):
+        model.forward(torch.zeros(1, 3, 40, 72, device=DEV), torch.zeros(1, 1, 40, 70, device=DEV), loss_type='adapt')      # shape mismatch

@@ -117,7 +117,11 @@ struct Branch {
 using namespace ptta;
 
 struct ptta_msgchn {
-    int N, H, W;
+    int N, H, W;                    // shape the network runs at (multiples of 16; 2 x the user batch when `padded`)
+    int Nu, Hu, Wu;                 // shape of the caller's tensors
+    bool padded = false;            // pad + flip-pad ensembling active (src/msg_chn_model_adapt.py:58-125)
+    float *pimg = nullptr, *psp = nullptr;   // padded image [N,3,H,W] / sparse depth [N,1,H,W]
+    Map1 out_u, g_out_u;            // un-padded mean prediction and its gradient
     bool two_layers, has_heads;
     std::string prepare_mode;
     cudaStream_t st = nullptr;      // stream of the call in flight (helpers launch on `st`)
@@ -325,11 +329,26 @@ struct ptta_msgchn {
         plan_conv(meta1);
         if (two_layers) plan_conv(meta2);
         zero_bias = allocv<float>(512);
-        fd = alloc1("filtered_depth", H, W); fv = alloc1("filtered_validity", H, W);
+        auto alloc_user = [&](const char* name) {
+            Map1 m; m.n = Nu; m.h = Hu; m.w = Wu;
+            m.p = (float*)arena.take(m.numel() * sizeof(float));
+            reg(name, m.p, 0, Nu, Hu, Wu, 1);
+            return m;
+        };
+        fd = alloc_user("filtered_depth"); fv = alloc_user("filtered_validity");
+        if (padded) {
+            pimg = allocv<float>((size_t)N * 3 * H * W);
+            psp = allocv<float>((size_t)N * H * W);
+            out_u = alloc_user("output_mean"); g_out_u = alloc_user("g_output_mean");
+        }
         dcl = alloc1("depth_clamped", H, W); d12 = alloc1("d12", H / 2, W / 2); d14 = alloc1("d14", H / 4, W / 4);
         for (int k = 0; k < 5; ++k) rgbT[k] = alloc32(("rgbT" + std::to_string(k)).c_str(), H >> k, W >> k);
         plan_branch(real, "real", true);
-        reg("output", real.output.p, 0, N, H, W, 1);
+        if (padded) {
+            reg("output", out_u.p, 0, Nu, Hu, Wu, 1); reg("output_padded", real.output.p, 0, N, H, W, 1);
+        } else {
+            reg("output", real.output.p, 0, N, H, W, 1);
+        }
         R = (long long)N * (H / 4) * (W / 4);
         if (has_heads) {
             for (int k = 0; k < 5; ++k) zc[k] = alloc32(("zc" + std::to_string(k)).c_str(), H >> k, W >> k);
@@ -354,7 +373,8 @@ struct ptta_msgchn {
         GC2 = alloc32("g_c2", H / 4, W / 4);
         D8 = alloc32("D8", H / 8, W / 8); E8 = alloc32("E8", H / 8, W / 8);
         if (two_layers) { M128a = alloc32("M128a", H / 4, W / 4, 128); M128b = alloc32("M128b", H / 4, W / 4, 128); }
-        g_out = alloc1("g_output", H, W); g_p11 = alloc1("g_p11", H, W);
+        g_out = alloc1(padded ? "g_output_padded" : "g_output", H, W); g_p11 = alloc1("g_p11", H, W);
+        if (padded) reg("g_output", g_out_u.p, 0, Nu, Hu, Wu, 1);
         g_q = alloc1("g_q", H / 2, W / 2); g_p12 = alloc1("g_p12", H / 2, W / 2); g_o14 = alloc1("g_out14", H / 4, W / 4);
         k0 = allocv<float>(512); k1 = allocv<float>(512); k2 = allocv<float>(512);
         long long max_rows = std::max<long long>(R, 1);
@@ -736,9 +756,29 @@ struct ptta_msgchn {
         return gemm(scratch, L3.pack, out, L3.b, R, L3.out, L3.in);
     }
 
+    // image / sparse are the caller's (Nu, Hu, Wu) tensors; with `padded` the network runs on the flip-padded pair
     int forward(const float* image, const float* isc, const float* ish, const float* sparse, float cap, bool training) {
         PTTA_CHECK(bound && packed, "engine not ready: bind a workspace and pack weights first");
         PTTA_CHECK(!training || has_heads, "training forward needs the proxy heads ('selfsup' prepare mode)");
+        if (!padded) return forward_impl(image, isc, ish, sparse, cap, training);
+        {
+            // the reference pads the NORMALISED image with zeros (msg_chn_model_adapt.py:79-101): fill with the raw value that
+            // normalises to zero, so that the affine folded into the stem reproduces it
+            float f[3];
+            for (int c = 0; c < 3; ++c) f[c] = isc[c] != 0.f ? -ish[c] / isc[c] : 0.f;
+            long long tot = (long long)N * 3 * H * W;
+            pad_pair_kernel<<<cdiv(tot, 256), 256, 0, st>>>(image, pimg, Nu, 3, Hu, Wu, H, W, 1.f, f[0], f[1], f[2]);
+            PTTA_TRY(check_launch("pad_pair(image)"));
+            tot = (long long)N * H * W;
+            pad_pair_kernel<<<cdiv(tot, 256), 256, 0, st>>>(sparse, psp, Nu, 1, Hu, Wu, H, W, 1.f, 0.f, 0.f, 0.f);
+            PTTA_TRY(check_launch("pad_pair(sparse)"));
+        }
+        PTTA_TRY(forward_impl(pimg, isc, ish, psp, cap, training));
+        long long tot = (long long)Nu * Hu * Wu;
+        unpad_mean_kernel<<<cdiv(tot, 256), 256, 0, st>>>(real.output.p, out_u.p, Nu, Hu, Wu, H, W);
+        return check_launch("unpad_mean");
+    }
+    int forward_impl(const float* image, const float* isc, const float* ish, const float* sparse, float cap, bool training) {
         {
             long long tot = (long long)N * (H / 4) * (W / 4);
             pyramid_kernel<<<cdiv(tot, 128), 128, 0, st>>>(sparse, dcl.p, d12.p, d14.p, N, H, W, cap, cap > 0.f ? 1 : 0);
@@ -782,15 +822,17 @@ struct ptta_msgchn {
 
     // ---- losses (src/external_model_adapt.py:371-441) ----------------------------------------------------
     int loss(const float* image_raw, const float* sparse, const float* validity, float cap, float w_sd, float w_sm, float w_cos) {
-        PTTA_CHECK(N <= 64, "loss: batch size %d > 64 not supported", N);
+        PTTA_CHECK(Nu <= 64, "loss: batch size %d > 64 not supported", Nu);
         l_img = image_raw; l_d = sparse; l_v = validity; l_cap = cap; l_wsd = w_sd; l_wsm = w_sm;
-        dim3 grid(loss_map_blocks, N);
-        loss_map_reduce_kernel<<<grid, LOSS_BLOCK, 0, st>>>(real.output.p, sparse, validity, image_raw, loss_map_partial, H, W, cap,
+        // the map losses are taken on the caller-shaped prediction (the un-padded mean when `padded`); the cosine loss on all R rows
+        const float* pred = padded ? out_u.p : real.output.p;
+        dim3 grid(loss_map_blocks, Nu);
+        loss_map_reduce_kernel<<<grid, LOSS_BLOCK, 0, st>>>(pred, sparse, validity, image_raw, loss_map_partial, Hu, Wu, cap,
                                                            cap > 0.f ? 1 : 0);
         PTTA_TRY(check_launch("loss_map_reduce"));
         loss_cos_rows_kernel<<<loss_cos_blocks, 256, 0, st>>>(emb, ref, rowstat, loss_cos_partial, R, 512);
         PTTA_TRY(check_launch("loss_cos_rows"));
-        loss_finalize_kernel<<<1, 256, 0, st>>>(loss_map_partial, loss_map_blocks, loss_cos_partial, loss_cos_blocks, N, H, W, R, w_sd, w_sm,
+        loss_finalize_kernel<<<1, 256, 0, st>>>(loss_map_partial, loss_map_blocks, loss_cos_partial, loss_cos_blocks, Nu, Hu, Wu, R, w_sd, w_sm,
                                               w_cos, 0.3f, losses);
         return check_launch("loss_finalize");
     }
@@ -810,9 +852,9 @@ struct ptta_msgchn {
         PTTA_CHECK(l_img != nullptr, "backward called before loss");
         const Branch& B = real;
         {
-            long long tot = (long long)N * H * W;
-            loss_map_grad_kernel<<<cdiv(tot, 256), 256, 0, st>>>(B.output.p, l_d, l_v, l_img, g_out.p, losses, N, H, W, l_cap,
-                                                               l_cap > 0.f ? 1 : 0, l_wsd, l_wsm, gscale);
+            long long tot = (long long)Nu * Hu * Wu;
+            loss_map_grad_kernel<<<cdiv(tot, 256), 256, 0, st>>>(padded ? out_u.p : B.output.p, l_d, l_v, l_img, padded ? g_out_u.p : g_out.p, losses,
+                                                               Nu, Hu, Wu, l_cap, l_cap > 0.f ? 1 : 0, l_wsd, l_wsm, gscale);
             PTTA_TRY(check_launch("loss_map_grad"));
             loss_cos_grad_kernel<<<loss_cos_blocks, 256, 0, st>>>(emb, ref, rowstat, losses, g_ref, R, 512, gscale);
             PTTA_TRY(check_launch("loss_cos_grad"));
@@ -823,6 +865,11 @@ struct ptta_msgchn {
     int network_backward() {
         for (const std::string& k : adapt_names) PTTA_CHECK(grad_of(k) != nullptr, "gradient buffer 'grad/%s' not bound", k.c_str());
         const Branch& B = real;
+        if (padded) {   // adjoint of the crop + mean: each copy receives half of the gradient at its crop, zero elsewhere
+            long long tot = (long long)N * H * W;
+            pad_pair_kernel<<<cdiv(tot, 256), 256, 0, st>>>(g_out_u.p, g_out.p, Nu, 1, Hu, Wu, H, W, 0.5f, 0.f, 0.f, 0.f);
+            PTTA_TRY(check_launch("pad_pair(g_output)"));
+        }
         // proxy head on the real rows: ref = L3(relu(bn(L0(z))))
         PTTA_TRY(gemm(g_ref, proj3.pack_t, g_a3, nullptr, R, 512, 512));
         PTTA_TRY(bn_backward(projBn, bnProjR, g_a3, h_a0r, g_a0, R, 1, nullptr, nullptr));
@@ -917,9 +964,9 @@ struct ptta_msgchn {
     }
 
     int outlier(const float* sparse) {
-        dim3 grid(cdiv(W, OR_TX), cdiv(H, OR_TY), N), block(OR_TX, OR_TY);
+        dim3 grid(cdiv(Wu, OR_TX), cdiv(Hu, OR_TY), Nu), block(OR_TX, OR_TY);
         size_t sm = (size_t)(OR_TX + 6) * (OR_TY + 6) * sizeof(float);
-        outlier_removal_kernel<<<grid, block, sm, st>>>(sparse, fd.p, fv.p, H, W, 7, 1.5f);
+        outlier_removal_kernel<<<grid, block, sm, st>>>(sparse, fd.p, fv.p, Hu, Wu, 7, 1.5f);
         return check_launch("outlier_removal");
     }
 
@@ -1199,15 +1246,17 @@ int ptta_nlspn_propagate_backward(const float* grad_out, const float* offset, co
 // ---- engine ---------------------------------------------------------------------------------------
 int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepare_mode) {
     PTTA_CHECK(out != nullptr, "create: null out pointer");
-    PTTA_CHECK(n >= 1 && h >= 16 && w >= 16, "create: bad shape %dx%dx%d", n, h, w);
-    PTTA_CHECK(h % 16 == 0 && w % 16 == 0, "create: H=%d, W=%d must be multiples of 16 (pad first, src/msg_chn_model_adapt.py:58-102)", h, w);
+    PTTA_CHECK(n >= 1 && h >= 1 && w >= 1, "create: bad shape %dx%dx%d", n, h, w);
     std::string mode = prepare_mode ? prepare_mode : "";
     PTTA_CHECK(mode.find("meta") != std::string::npos && mode.find("seq") != std::string::npos,
                "create: prepare_mode '%s' has no sequential meta layer (network_exp_msg_chn_adapt.py:1063-1077)", mode.c_str());
     bool two = mode.find("2layers") != std::string::npos, one = mode.find("1layer") != std::string::npos;
     PTTA_CHECK(two || one, "create: prepare_mode '%s' must contain '1layer' or '2layers'", mode.c_str());
     ptta_msgchn* e = new ptta_msgchn();
-    e->N = n; e->H = h; e->W = w; e->two_layers = two; e->prepare_mode = mode;
+    e->Nu = n; e->Hu = h; e->Wu = w;
+    e->padded = (h % 16 != 0) || (w % 16 != 0);          // pad to /16 + flip-pad pair (src/msg_chn_model_adapt.py:58-102)
+    e->N = e->padded ? 2 * n : n; e->H = (h + 15) / 16 * 16; e->W = (w + 15) / 16 * 16;
+    e->two_layers = two; e->prepare_mode = mode;
     e->has_heads = mode.find("selfsup") != std::string::npos;
     e->define_model();
     e->plan();

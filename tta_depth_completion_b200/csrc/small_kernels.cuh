@@ -99,6 +99,35 @@ __global__ void pyramid_kernel(const float* __restrict__ d, float* __restrict__ 
 }
 
 // -------------------------------------------------------------------------------------------------
+// a4: pad-to-/16 + flip-pad ensembling of MsgChnModel_Adapt.forward (src/msg_chn_model_adapt.py:54-197).  An N x C x Hu x Wu
+// input becomes a 2N x C x H x W batch: copy 0 padded at the top / right, copy 1 padded at the bottom / left; the two
+// predictions are cropped back and averaged.  pad_pair(scale = 0.5, fill = 0) is also the exact adjoint of unpad_mean.
+// -------------------------------------------------------------------------------------------------
+__global__ void pad_pair_kernel(const float* __restrict__ src, float* __restrict__ dst, int Nu, int C, int Hu, int Wu, int H, int W, float scale,
+                                float f0, float f1, float f2) {
+    const long long total = 2LL * Nu * C * H * W;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = idx % W, y = (idx / W) % H, c = (idx / ((long long)W * H)) % C, n2 = idx / ((long long)W * H * C);
+    const int copy = n2 / Nu, n = n2 - copy * Nu;
+    const int pt = H - Hu, pr = W - Wu;
+    const int sy = copy == 0 ? y - pt : y, sx = copy == 0 ? x : x - pr;
+    float v = c == 0 ? f0 : (c == 1 ? f1 : f2);
+    if (sy >= 0 && sy < Hu && sx >= 0 && sx < Wu) v = scale * __ldg(src + (((long long)n * C + c) * Hu + sy) * Wu + sx);
+    dst[idx] = v;
+}
+__global__ void unpad_mean_kernel(const float* __restrict__ src, float* __restrict__ dst, int Nu, int Hu, int Wu, int H, int W) {
+    const long long total = (long long)Nu * Hu * Wu;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = idx % Wu, y = (idx / Wu) % Hu, n = idx / ((long long)Wu * Hu);
+    const int pt = H - Hu, pr = W - Wu;
+    const float a = __ldg(src + ((long long)n * H + (y + pt)) * W + x);
+    const float b = __ldg(src + ((long long)(Nu + n) * H + y) * W + (x + pr));
+    dst[idx] = 0.5f * (a + b);      // torch.mean over the stacked pair (msg_chn_model_adapt.py:116-121)
+}
+
+// -------------------------------------------------------------------------------------------------
 // Stem: {1,2,3} fp32 planes -> 32 channels bf16 NHWC, 3x3 s1 p1 (init.0 of every encoder,
 // network_exp_msg_chn_adapt.py:172,220).  Each plane has its own pointer / batch stride and an
 // affine (x*scale + shift) so that image normalisation (src/transforms.py:669-712) and the

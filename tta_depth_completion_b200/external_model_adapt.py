@@ -239,10 +239,7 @@ class MsgChnModel_Adapt(object):
         key = (image.shape[0], image.shape[2], image.shape[3])
         eng = self._engines.get(key)
         if eng is None:
-            n, h, w = key
-            if h % 16 or w % 16:
-                raise NotImplementedError('H, W must be multiples of 16: the pad + flip ensembling of '
-                                          'src/msg_chn_model_adapt.py:58-125 is not implemented on the native path yet')
+            n, h, w = key          # H, W need not be multiples of 16: the engine pads and flip-ensembles (src/msg_chn_model_adapt.py:58-125)
             state = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in self._sd.items()}
             eng = MsgChnEngine(n, h, w, self.prepare_mode, state, self._grad_views, self._m_views, self._v_views)
             self._engines[key] = eng
