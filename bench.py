@@ -331,7 +331,7 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--workload', default='kitti', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=1)
-    ap.add_argument('--graph', action='store_true', help='replay the step from its CUDA graph (measured slower than eager launches: DESIGN.md)')
+    ap.add_argument('--no-graph', dest='graph', action='store_false', help='launch the step kernels eagerly instead of replaying the captured CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip the roofline / cpu_baseline legs (profiling runs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

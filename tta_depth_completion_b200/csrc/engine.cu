@@ -174,7 +174,7 @@ struct ptta_msgchn {
     const float *l_img = nullptr, *l_d = nullptr, *l_v = nullptr; float l_cap = 0, l_wsd = 0, l_wsm = 0;
     // graph
     cudaGraphExec_t graph_exec = nullptr;
-    const void* graph_key[4] = {nullptr, nullptr, nullptr, nullptr};
+    struct GraphKey { const void* image; const void* sparse; float isc[3], ish[3], cap, w_sd, w_sm, w_cos; } graph_key;   // everything a capture bakes in
 
     // ---------------------------------------------------------------------------------------------
     Map32 alloc32(const char* name, int h, int w, int c = 32) {
@@ -1386,8 +1386,11 @@ int ptta_msgchn_tta_step_graph(ptta_msgchn* e, const float* image_raw, const flo
     PTTA_CHECK(e && image_raw && sparse && isc && ish, "tta_step_graph: null argument");
     cudaStream_t st = (cudaStream_t)stream;
     PTTA_CHECK(st != nullptr, "tta_step_graph: needs a non-default stream (legacy stream 0 cannot be captured)");
-    const void* key[4] = {image_raw, sparse, isc, ish};
-    if (e->graph_exec && memcmp(key, e->graph_key, sizeof(key)) != 0) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    ptta_msgchn::GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.image = image_raw; key.sparse = sparse; key.cap = cap; key.w_sd = w_sd; key.w_sm = w_sm; key.w_cos = w_cos;
+    for (int c = 0; c < 3; ++c) { key.isc[c] = isc[c]; key.ish[c] = ish[c]; }
+    if (e->graph_exec && memcmp(&key, &e->graph_key, sizeof(key)) != 0) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     if (!e->graph_exec) {
         // one eager step first: sets every cudaFuncAttribute (not capturable) and validates the arguments
         e->st = st;
@@ -1403,7 +1406,7 @@ int ptta_msgchn_tta_step_graph(ptta_msgchn* e, const float* image_raw, const flo
         ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
         cudaGraphDestroy(graph);
         PTTA_CHECK(ce == cudaSuccess, "graph instantiate failed: %s", cudaGetErrorString(ce));
-        memcpy(e->graph_key, key, sizeof(key));
+        memcpy(&e->graph_key, &key, sizeof(key));
         return 0;   // the eager step above WAS this call's step
     }
     PTTA_CUDA(cudaGraphLaunch(e->graph_exec, st));
