@@ -52,6 +52,11 @@ int ptta_conv3x3(const void* in_bf16, void* out_bf16, const void* wpack_bf16, co
 int ptta_pack_conv_weight_tc(const void* wpack_bf16, void* wimage_bf16, ptta_stream_t stream);
 int ptta_conv3x3_tc(const void* in_bf16, void* out_bf16, const void* wimage_bf16, const float* bias, int n, int h, int w,
                     int relu_in, int relu_out, const void* mask_bf16, const void* add_bf16, ptta_stream_t stream);
+/* the 32->32 STRIDE-2 case (mode 1 of ptta_conv3x3: Conv2d(s2) forward, ConvTranspose2d(s2) data gradient) on tcgen05.
+ * h, w = input size (even); out is [n, h/2, w/2, 32]; out_relu (optional) additionally receives ReLU(out). */
+int ptta_pack_conv_weight_tc_s2(const void* wpack_bf16, void* wimage_bf16, ptta_stream_t stream);
+int ptta_conv3x3_tc_s2(const void* in_bf16, void* out_bf16, void* out_relu_bf16, const void* wimage_bf16, const float* bias,
+                       int n, int h, int w, int relu_out, const void* mask_bf16, const void* add_bf16, ptta_stream_t stream);
 /* timing experiments only: bit mask of pipeline stages the tcgen05 conv skips (results are then wrong) */
 int ptta_debug_set(int mask);
 /* timing experiments only: per-row clock64() stamps of CTA 0 recorded by the tcgen05 conv when mask bit 64 is set */

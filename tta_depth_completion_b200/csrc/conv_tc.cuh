@@ -28,6 +28,7 @@ struct ConvTcParams {
     const bf16* w;       // 18 KB shared-memory image of the weights (pack_conv_weight_tc_kernel)
     const float* bias;   // [32] or null
     bf16* out;
+    bf16* out2;          // optional second output: ReLU(out) (for consumers that have no ReLU-on-load), or null
     const bf16* mask;    // relu-derivative mask source (same shape as out) or null
     const bf16* add;     // out = add + mask * (conv + bias), or null
     int N, H, W;
@@ -495,6 +496,13 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
                     if (pp < vp) {
                         uint4 val = *reinterpret_cast<const uint4*>(stage + pp * 128 + ((c ^ (pp & 7)) << 4));
                         *reinterpret_cast<uint4*>(p.out + off0 + (size_t)idx * 8) = val;
+                        if (p.out2) {
+                            const bf162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+                            bf162* h2 = reinterpret_cast<bf162*>(&val);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) h2[j] = __hmax2(h2[j], z2);
+                            *reinterpret_cast<uint4*>(p.out2 + off0 + (size_t)idx * 8) = val;
+                        }
                     }
                 }
                 __syncwarp();                        // staging buffers are rewritten next row

@@ -18,6 +18,7 @@
 #include "gemm_mma.cuh"
 #include "small_kernels.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc_s2.cuh"
 #include "gemm_tc.cuh"
 #include "nlspn_prop.cuh"
 #include "../../include/ptta_b200.h"
@@ -618,7 +619,7 @@ struct ptta_msgchn {
     // prediction layer: out = conv32->1(relu(h)) + bias [+ add]
     int head_fwd(const HeadLayer& Hd, const Map32& h, const float* add, const Map1& out) {
         long long tot = (long long)out.numel();
-        head_conv_kernel<<<dim3(cdiv(out.w, HEADC_TW), out.h, out.n), 128, 0, st>>>(h.p, Hd.w_fwd, Hd.bias_host, add, out.p, out.n, out.h, out.w, 1, 0);
+        head_conv_kernel<<<dim3(cdiv(out.w, HEADC_TW), cdiv(out.h, HEADC_TH), out.n), dim3(HEADC_TW, HEADC_TH), 0, st>>>(h.p, Hd.w_fwd, Hd.bias_host, add, out.p, out.n, out.h, out.w, 1, 0);
         return check_launch("head_conv");
     }
     // g_h = dgrad_{1->32}(g_out) * [h > 0]
@@ -633,7 +634,7 @@ struct ptta_msgchn {
     // gradient wrt input plane 1 of a 2-plane stem: out = conv32->1(g_a0; flipped plane-1 weights) + add
     int stem_dgrad_ch1(const StemLayer& S, const Map32& ga0, const float* add, const Map1& out) {
         long long tot = (long long)out.numel();
-        head_conv_kernel<<<dim3(cdiv(out.w, HEADC_TW), out.h, out.n), 128, 0, st>>>(ga0.p, S.dgrad_ch1, 0.f, add, out.p, out.n, out.h, out.w, 0, 0);
+        head_conv_kernel<<<dim3(cdiv(out.w, HEADC_TW), cdiv(out.h, HEADC_TH), out.n), dim3(HEADC_TW, HEADC_TH), 0, st>>>(ga0.p, S.dgrad_ch1, 0.f, add, out.p, out.n, out.h, out.w, 0, 0);
         return check_launch("stem_dgrad");
     }
     int stats(const bf16* x, const bf16* dy, long long rows, int C, int mode, const BnState* s, int relu_mask, int& nblk) {
@@ -1037,6 +1038,20 @@ int ptta_pack_conv_weight_tc(const void* wpack, void* image, ptta_stream_t strea
     return check_launch("pack_conv_weight_tc");
 }
 
+int ptta_pack_conv_weight_tc_s2(const void* wpack, void* image, ptta_stream_t stream) {
+    PTTA_CHECK(wpack && image, "pack_conv_weight_tc_s2: null argument");
+    pack_conv_weight_tc_s2_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)wpack, (bf16*)image);
+    return check_launch("pack_conv_weight_tc_s2");
+}
+int ptta_conv3x3_tc_s2(const void* in, void* out, void* out_relu, const void* wimage, const float* bias, int n, int h, int w, int relu_out,
+                       const void* mask, const void* add, ptta_stream_t stream) {
+    PTTA_CHECK(in && out && wimage, "conv3x3_tc_s2: null argument");
+    ConvTcParams p; memset(&p, 0, sizeof(p));
+    p.w = (const bf16*)wimage; p.bias = bias; p.out = (bf16*)out; p.out2 = (bf16*)out_relu; p.mask = (const bf16*)mask; p.add = (const bf16*)add;
+    p.N = n; p.H = h; p.W = w; p.relu_out = relu_out;
+    return launch_conv_tc_s2((const bf16*)in, p, (cudaStream_t)stream);
+}
+
 int ptta_debug_set(int v) {
     PTTA_CUDA(cudaMemcpyToSymbol(g_tc_dbg, &v, sizeof(int)));
     return 0;
@@ -1078,7 +1093,7 @@ int ptta_stem_conv(const float* const* planes, const long long* strides, const f
 int ptta_head_conv(const void* in, const float* w, float bias, const float* add, float* out, int n, int h, int ww, int relu_in,
                    int accumulate, ptta_stream_t stream) {
     long long tot = (long long)n * h * ww;
-    head_conv_kernel<<<dim3(cdiv(ww, HEADC_TW), h, n), 128, 0, (cudaStream_t)stream>>>((const bf16*)in, w, bias, add, out, n, h, ww, relu_in, accumulate);
+    head_conv_kernel<<<dim3(cdiv(ww, HEADC_TW), cdiv(h, HEADC_TH), n), dim3(HEADC_TW, HEADC_TH), 0, (cudaStream_t)stream>>>((const bf16*)in, w, bias, add, out, n, h, ww, relu_in, accumulate);
     return check_launch("head_conv");
 }
 

@@ -246,22 +246,24 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams p) {
 // with ReLU-on-load, and -- with pre-flipped weights, no ReLU, accumulate -- the data-gradient of a
 // stem with respect to one of its input planes.  out = [acc_prev +] conv(in) + bias [+ add].
 // -------------------------------------------------------------------------------------------------
-// Block = 128 consecutive pixels of one output row: the three input rows (130 pixels each, zero padded) are staged in shared
-// memory with coalesced 16 B loads (ReLU applied on the way in), then every thread reads its 9 x 64 B taps conflict-free.
-// Launch: grid (cdiv(W, 128), H, N), 128 threads.
-#define HEADC_TW 128
-__global__ void __launch_bounds__(128) head_conv_kernel(const bf16* __restrict__ in, const float* __restrict__ w /*[9][32]*/,
+// Block = a 32 x 8 tile of output pixels: the (34 x 10) input halo (zero padded) is staged in shared memory with coalesced
+// 16 B loads (ReLU applied on the way in), then every thread reads its 9 x 64 B taps conflict-free.
+// Launch: grid (cdiv(W, 32), cdiv(H, 8), N), block (32, 8).
+#define HEADC_TW 32
+#define HEADC_TH 8
+__global__ void __launch_bounds__(HEADC_TW * HEADC_TH) head_conv_kernel(const bf16* __restrict__ in, const float* __restrict__ w /*[9][32]*/,
                                                         float bias, const float* __restrict__ add, float* __restrict__ out,
                                                         int N, int H, int W, int relu_in, int accumulate) {
     __shared__ float s_w[9 * 32];
-    __shared__ __align__(16) unsigned char s_in[3 * (HEADC_TW + 2) * 64];
-    for (int i = threadIdx.x; i < 288; i += blockDim.x) s_w[i] = w[i];
-    const int x0 = blockIdx.x * HEADC_TW, y = blockIdx.y, n = blockIdx.z;
+    __shared__ __align__(16) unsigned char s_in[(HEADC_TH + 2) * (HEADC_TW + 2) * 64];
+    const int tid = threadIdx.y * HEADC_TW + threadIdx.x;
+    for (int i = tid; i < 288; i += HEADC_TW * HEADC_TH) s_w[i] = w[i];
+    const int x0 = blockIdx.x * HEADC_TW, y0 = blockIdx.y * HEADC_TH, n = blockIdx.z;
     const bf16* inn = in + (size_t)n * H * W * 32;
     const bf162 z = __floats2bfloat162_rn(0.f, 0.f);
-    for (int i = threadIdx.x; i < 3 * (HEADC_TW + 2) * 4; i += blockDim.x) {
+    for (int i = tid; i < (HEADC_TH + 2) * (HEADC_TW + 2) * 4; i += HEADC_TW * HEADC_TH) {
         const int c = i & 3, px = (i >> 2) % (HEADC_TW + 2), ry = (i >> 2) / (HEADC_TW + 2);
-        const int gy = y + ry - 1, gx = x0 + px - 1;
+        const int gy = y0 + ry - 1, gx = x0 + px - 1;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
             v = __ldg(reinterpret_cast<const uint4*>(inn + ((size_t)gy * W + gx) * 32) + c);
@@ -275,14 +277,14 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const bf16* __restrict__
         *reinterpret_cast<uint4*>(s_in + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)) = v;
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x;
-    if (x >= W) return;
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
     float acc = bias;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-            const int row = ky * (HEADC_TW + 2) + threadIdx.x + kx;
+            const int row = (threadIdx.y + ky) * (HEADC_TW + 2) + threadIdx.x + kx;
             const float* wr = s_w + (ky * 3 + kx) * 32;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -583,25 +585,38 @@ struct BnParams {
 };
 
 // sum of partial[k][slot][ch] over k for 32 channels per block: thread (cx = tid & 31, ks = tid >> 5) adds slice ks of the
-// partial list (256 B coalesced reads), the 8 slices are combined through shared memory in a fixed order (deterministic).
-// Returns the totals (a: slot 0, b: slot 1) in the threads with ks == 0; launch with FIN_THREADS threads, cdiv(C, 32) blocks.
-#define FIN_THREADS 256
+// partial list (256 B coalesced reads, four independent loads in flight), the FIN_SLICES slices are combined through shared
+// memory in a fixed order (deterministic).  Returns the totals (a: slot 0, b: slot 1) in the threads with ks == 0; launch
+// with FIN_THREADS threads, cdiv(C, 32) blocks.
+#define FIN_SLICES 32
+#define FIN_THREADS (32 * FIN_SLICES)
 __device__ __forceinline__ bool block_reduce_partials(const double* __restrict__ partial, int nblk, int C, int nslots, int& ch, double& a, double& b) {
-    __shared__ double sh[2][8][32];
+    __shared__ double sh[2][FIN_SLICES][32];
     const int cx = threadIdx.x & 31, ks = threadIdx.x >> 5;
     ch = blockIdx.x * 32 + cx;
     a = 0.0; b = 0.0;
     if (ch < C) {
-        for (int k = ks; k < nblk; k += 8) {
-            a += partial[((size_t)k * 2 + 0) * C + ch];
-            if (nslots > 1) b += partial[((size_t)k * 2 + 1) * C + ch];
+        double a4[4] = {0.0, 0.0, 0.0, 0.0}, b4[4] = {0.0, 0.0, 0.0, 0.0};
+        int k = ks;
+        for (; k + 3 * FIN_SLICES < nblk; k += 4 * FIN_SLICES) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a4[u] += partial[((size_t)(k + u * FIN_SLICES) * 2 + 0) * C + ch];
+                if (nslots > 1) b4[u] += partial[((size_t)(k + u * FIN_SLICES) * 2 + 1) * C + ch];
+            }
         }
+        for (; k < nblk; k += FIN_SLICES) {
+            a4[0] += partial[((size_t)k * 2 + 0) * C + ch];
+            if (nslots > 1) b4[0] += partial[((size_t)k * 2 + 1) * C + ch];
+        }
+        a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+        b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
     }
     sh[0][ks][cx] = a; sh[1][ks][cx] = b;
     __syncthreads();
     if (ks != 0 || ch >= C) return false;
 #pragma unroll
-    for (int k = 1; k < 8; ++k) { a += sh[0][k][cx]; b += sh[1][k][cx]; }
+    for (int k = 1; k < FIN_SLICES; ++k) { a += sh[0][k][cx]; b += sh[1][k][cx]; }
     return true;
 }
 

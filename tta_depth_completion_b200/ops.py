@@ -117,6 +117,23 @@ def conv3x3_tc(x, wpack, bias=None, relu_in=False, relu_out=False, mask=None, ad
     return out
 
 
+def conv3x3_tc_s2(x, wpack, bias=None, relu_out=False, mask=None, add=None, want_relu_copy=False):
+    """32->32 stride-2 conv on tcgen05 (operand conventions of conv3x3 with MODE_S2, no ReLU-on-load); H, W even.
+    Returns out, or (out, relu(out)) with want_relu_copy."""
+    _need(x, torch.bfloat16, 'x')
+    _need(wpack, torch.bfloat16, 'wpack')
+    n, h, w, cin = x.shape
+    if cin != 32 or tuple(wpack.shape) != (9, 32, 32):
+        raise ValueError('conv3x3_tc_s2 handles 32->32 channels only')
+    image = torch.empty((9 * 32 * 32,), dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().ptta_pack_conv_weight_tc_s2(ptr(wpack), ptr(image), _stream()), 'pack_conv_weight_tc_s2')
+    out = torch.empty((n, h // 2, w // 2, 32), dtype=torch.bfloat16, device=x.device)
+    out2 = torch.empty_like(out) if want_relu_copy else None
+    check(_lib.lib().ptta_conv3x3_tc_s2(ptr(x), ptr(out), ptr(out2), ptr(image), ptr(bias), n, h, w, 1 if relu_out else 0, ptr(mask), ptr(add),
+                                        _stream()), 'conv3x3_tc_s2')
+    return (out, out2) if want_relu_copy else out
+
+
 def conv3x3_wgrad(x, gout, prologue=PRO_NONE, pro_scale=None, pro_shift=None, slope=0.2):
     _need(x, torch.bfloat16, 'x')
     _need(gout, torch.bfloat16, 'gout')
