@@ -39,6 +39,7 @@ struct ConvParams {
     const float* mask_shift;
     const bf16* add;     // [N,Hout,Wout,COUT] or null; out = add + mask*(acc + bias)
     int relu_out;        // store ReLU(out) (outputs that are only ever consumed through a ReLU)
+    bf16* out2;          // optional second output: ReLU(out)
     int tiles_x, tiles_y;
 };
 
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(256) conv3x3_mma_kernel(const ConvParams p) {
                     }
                     if (p.relu_out) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
                     *reinterpret_cast<uint32_t*>(p.out + pix_off + co) = pack_bf162(v0, v1);
+                    if (p.out2) *reinterpret_cast<uint32_t*>(p.out2 + pix_off + co) = pack_bf162(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
                 }
             }
         }

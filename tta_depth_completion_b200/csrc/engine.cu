@@ -100,10 +100,11 @@ struct LinearLayer {
 struct EncW { StemLayer init0; ConvLayer init2, e1a, e1b, e2a, e2b, e3a, e3b, e4a, e4b; int nenc = 2; };
 struct DecW { ConvLayer d2a, d2b, d1a, d1b, p1; HeadLayer p3; };
 
-struct EncAct { Map32 a0, x0, t1, x1, t2, x2; };
+struct EncAct { Map32 a0, x0, t1, x1, t2, x2; Map32 x0r, x1r; };   // x0r / x1r = ReLU(x0) / ReLU(x1): inputs of the stride-2 convs
 struct DecAct { Map32 x2, x1, x0, u2, x3, s1, u1, x4, s0, h; Map1 out; };
 struct Branch {
     Map32 c[5];            // rgb features (c[2] after the meta layer)
+    Map32 cr[4];           // ReLU of the rgb encoder's own x0..x3 (inputs of its stride-2 convs)
     Map32 c2raw;           // rgb x2 before the meta layer
     Map32 mh, mg;          // meta: conv1 output (128 ch), conv2 output (32 ch), both pre-BN
     BnState bn1, bn2;
@@ -129,7 +130,7 @@ struct ptta_msgchn {
     cudaStream_t st2 = nullptr;     // side stream: the zero-image branch runs concurrently with the real branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_projbn = nullptr;
     bool two_streams = true, fork_pending = false;
-    bool tc_enabled = true; long long tc_min_pixels = 60000;
+    bool tc_enabled = true; long long tc_min_pixels = 60000, tc_s2_min_pixels = 16000;
     Arena arena;
     size_t ws_bytes = 0;
     bool bound = false, packed = false;
@@ -151,6 +152,7 @@ struct ptta_msgchn {
     Branch real, zero;
     Map32 rgbT[5];                   // rgb encoder temporaries (a0 / t_k), per resolution
     Map32 zc[5];                     // cached rgb_encoder(0) features
+    Map32 zcr[4];                    // scratch ReLU copies while rgb_encoder(0) is (re)computed
     Map1 fd, fv, dcl, d12, d14;      // filtered depth / validity, clamped depth, pyramid
     // heads
     long long R = 0;
@@ -267,8 +269,8 @@ struct ptta_msgchn {
         L.pack_fwd = allocv<bf16>((size_t)9 * L.cin * L.cout);
         L.pack_dgrad = allocv<bf16>((size_t)9 * L.cin * L.cout);
         if (L.cin == 32 && L.cout == 32) {
-            L.img_fwd = L.mode_fwd == MODE_S1 ? allocv<bf16>(9 * 32 * 32) : nullptr;
-            L.img_dgrad = L.mode_dgrad == MODE_S1 ? allocv<bf16>(9 * 32 * 32) : nullptr;
+            L.img_fwd = L.mode_fwd != MODE_T2 ? allocv<bf16>(9 * 32 * 32) : nullptr;
+            L.img_dgrad = L.mode_dgrad != MODE_T2 ? allocv<bf16>(9 * 32 * 32) : nullptr;
         }
     }
     void plan_enc_w(EncW& E) {
@@ -285,6 +287,7 @@ struct ptta_msgchn {
         A.a0 = alloc32((tag + ".a0").c_str(), h, w); A.x0 = alloc32((tag + ".x0").c_str(), h, w);
         A.t1 = alloc32((tag + ".t1").c_str(), h / 2, w / 2); A.x1 = alloc32((tag + ".x1").c_str(), h / 2, w / 2);
         A.t2 = alloc32((tag + ".t2").c_str(), h / 4, w / 4); A.x2 = alloc32((tag + ".x2").c_str(), h / 4, w / 4);
+        A.x0r = alloc32(nullptr, h, w); A.x1r = alloc32(nullptr, h / 2, w / 2);
     }
     void plan_dec_act(DecAct& A, const std::string& tag, int h, int w) {   // h,w = resolution of x0 / out
         A.x2 = alloc32((tag + ".x2").c_str(), h / 4, w / 4); A.x1 = alloc32((tag + ".x1").c_str(), h / 2, w / 2);
@@ -298,6 +301,7 @@ struct ptta_msgchn {
     void plan_branch(Branch& B, const std::string& tag, bool is_real) {
         if (is_real) {
             for (int k = 0; k < 5; ++k) B.c[k] = alloc32((tag + ".c" + std::to_string(k)).c_str(), H >> k, W >> k);
+            for (int k = 0; k < 4; ++k) B.cr[k] = alloc32(nullptr, H >> k, W >> k);
             B.c2raw = alloc32((tag + ".c2raw").c_str(), H / 4, W / 4);
         } else {
             // zero-image branch: rgb features are the cached rgb_encoder(0) maps; only the meta output is its own
@@ -353,6 +357,7 @@ struct ptta_msgchn {
         R = (long long)N * (H / 4) * (W / 4);
         if (has_heads) {
             for (int k = 0; k < 5; ++k) zc[k] = alloc32(("zc" + std::to_string(k)).c_str(), H >> k, W >> k);
+            for (int k = 0; k < 4; ++k) zcr[k] = real.cr[k];      // rgb_encoder(0) runs at pack time only: borrow the real branch's copies
             plan_branch(zero, "zero", false);
             auto lin = [&](LinearLayer& L) { L.pack = allocv<bf16>((size_t)L.in * L.out); L.pack_t = allocv<bf16>((size_t)L.in * L.out); };
             lin(proj0); lin(proj3); lin(pred0); lin(pred3);
@@ -467,11 +472,13 @@ struct ptta_msgchn {
             PTTA_TRY(check_launch("pack_dgrad_t"));
         }
         if (L.img_fwd) {
-            pack_conv_weight_tc_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_fwd, L.img_fwd);
+            if (L.mode_fwd == MODE_S1) pack_conv_weight_tc_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_fwd, L.img_fwd);
+            else pack_conv_weight_tc_s2_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_fwd, L.img_fwd);
             PTTA_TRY(check_launch("pack_fwd_tc"));
         }
         if (L.img_dgrad) {
-            pack_conv_weight_tc_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_dgrad, L.img_dgrad);
+            if (L.mode_dgrad == MODE_S1) pack_conv_weight_tc_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_dgrad, L.img_dgrad);
+            else pack_conv_weight_tc_s2_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_dgrad, L.img_dgrad);
             PTTA_TRY(check_launch("pack_dgrad_tc"));
         }
         return 0;
@@ -540,7 +547,7 @@ struct ptta_msgchn {
         if (n_adam_chunks) PTTA_CUDA(cudaMemcpyAsync(adam_chunks, chunks.data(), sizeof(AdamChunk) * chunks.size(), cudaMemcpyHostToDevice, st));
         if (has_heads) {
             // rgb_encoder(0): constant while the encoder is frozen ('meta' adapt mode never touches it)
-            PTTA_TRY(run_rgb_encoder(nullptr, nullptr, nullptr, zc));
+            PTTA_TRY(run_rgb_encoder(nullptr, nullptr, nullptr, zc, zcr));
         }
         PTTA_CUDA(cudaStreamSynchronize(st));
         packed = true;
@@ -551,16 +558,25 @@ struct ptta_msgchn {
     // ---- layer helpers ----------------------------------------------------------------------------------
     // the tcgen05 kernel takes the big 32->32 stride-1 maps; small maps (where any kernel is launch-bound) stay on mma.sync
     bool use_tc(const Map32& m) const { return tc_enabled && conv_tc_supported(m.n, m.h, m.w) && (long long)m.n * m.h * m.w >= tc_min_pixels; }
-    int conv_tc(const bf16* image, const float* bias, const Map32& in, const Map32& out, int relu_out, const bf16* mask, const bf16* add) {
+    bool use_tc_s2(const Map32& m) const {
+        return tc_enabled && conv_tc_s2_supported(m.n, m.h, m.w) && (long long)m.n * m.h * m.w >= tc_s2_min_pixels;
+    }
+    int conv_tc(const bf16* image, const float* bias, const Map32& in, const Map32& out, int relu_out, const bf16* mask, const bf16* add,
+                bf16* out2 = nullptr, bool stride2 = false) {
         ConvTcParams p; memset(&p, 0, sizeof(p));
-        p.w = image; p.bias = bias; p.out = out.p; p.mask = mask; p.add = add; p.N = in.n; p.H = in.h; p.W = in.w; p.relu_out = relu_out;
-        return launch_conv_tc(in.p, p, st);
+        p.w = image; p.bias = bias; p.out = out.p; p.out2 = out2; p.mask = mask; p.add = add; p.N = in.n; p.H = in.h; p.W = in.w; p.relu_out = relu_out;
+        return stride2 ? launch_conv_tc_s2(in.p, p, st) : launch_conv_tc(in.p, p, st);
     }
     // relu_out: the output is only ever read through a ReLU (or as a ReLU mask), so ReLU(x) is what gets stored
-    int conv_fwd(const ConvLayer& L, const Map32& in, const Map32& out, int pro, const BnState* probn = nullptr, int relu_out = 0) {
-        if (L.img_fwd && pro == PRO_NONE && use_tc(in)) return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr);
+    // out2 (optional): a second copy holding ReLU(out), for outputs that are read both raw and through a tensor-core conv
+    int conv_fwd(const ConvLayer& L, const Map32& in, const Map32& out, int pro, const BnState* probn = nullptr, int relu_out = 0,
+                 bf16* out2 = nullptr) {
+        if (L.img_fwd && pro == PRO_NONE) {
+            if (L.mode_fwd == MODE_S1 && use_tc(in)) return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr, out2);
+            if (L.mode_fwd == MODE_S2 && use_tc_s2(in)) return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr, out2, true);
+        }
         ConvParams p; memset(&p, 0, sizeof(p));
-        p.relu_out = relu_out;
+        p.relu_out = relu_out; p.out2 = out2;
         p.in = in.p; p.out = out.p; p.w = L.pack_fwd; p.bias = L.has_bias ? L.b : nullptr;
         p.N = in.n; p.Hin = in.h; p.Win = in.w; p.pro = pro; p.slope = 0.2f;
         if (probn) { p.pro_scale = probn->scale; p.pro_shift = probn->shift; }
@@ -569,7 +585,10 @@ struct ptta_msgchn {
     // gin = [add +] mask * dgrad(gout)
     int conv_dgrad(const ConvLayer& L, const Map32& gout, const Map32& gin, const bf16* mask, const bf16* add,
                    int mask_mode = MASK_RELU, const BnState* maskbn = nullptr) {
-        if (L.img_dgrad && (!mask || mask_mode == MASK_RELU) && use_tc(gout)) return conv_tc(L.img_dgrad, nullptr, gout, gin, 0, mask, add);
+        if (L.img_dgrad && (!mask || mask_mode == MASK_RELU)) {
+            if (L.mode_dgrad == MODE_S1 && use_tc(gout)) return conv_tc(L.img_dgrad, nullptr, gout, gin, 0, mask, add);
+            if (L.mode_dgrad == MODE_S2 && use_tc_s2(gout)) return conv_tc(L.img_dgrad, nullptr, gout, gin, 0, mask, add, nullptr, true);
+        }
         ConvParams p; memset(&p, 0, sizeof(p));
         p.in = gout.p; p.out = gin.p; p.w = L.pack_dgrad; p.bias = nullptr;
         p.N = gout.n; p.Hin = gout.h; p.Win = gout.w; p.pro = PRO_NONE; p.slope = 0.2f;
@@ -582,9 +601,9 @@ struct ptta_msgchn {
         ew_add_kernel<<<cdiv(n8, 256), 256, 0, st>>>(a.p, b.p, out.p, n8, relu);
         return check_launch("ew_add");
     }
-    int add_up2(const Map32& x, const Map32& half) {   // x += up2(half)
+    int add_up2(const Map32& x, const Map32& half, bf16* relu_copy = nullptr) {   // x += up2(half) [; relu_copy = ReLU(x)]
         long long tot = (long long)x.n * x.h * x.w * 4;
-        add_up2_c32_kernel<<<cdiv(tot, 256), 256, 0, st>>>(x.p, half.p, x.p, x.n, half.h, half.w);
+        add_up2_c32_kernel<<<cdiv(tot, 256), 256, 0, st>>>(x.p, half.p, x.p, x.n, half.h, half.w, relu_copy);
         return check_launch("add_up2_c32");
     }
     int up2_adj32(const Map32& ghi, const Map32& glo, int accumulate) {
@@ -675,7 +694,7 @@ struct ptta_msgchn {
 
     // ---- network pieces -------------------------------------------------------------------------------
     // image == nullptr -> zero image (constant planes: scale 0, shift 0)
-    int run_rgb_encoder(const float* image, const float* isc, const float* ish, Map32* c) {
+    int run_rgb_encoder(const float* image, const float* isc, const float* ish, Map32* c, Map32* cr) {
         const long long hw = (long long)H * W;
         const float* base = image ? image : fd.p;   // any valid pointer; scale 0 makes the value irrelevant
         float s[3], b[3];
@@ -684,11 +703,11 @@ struct ptta_msgchn {
             PTTA_TRY(stem(rgbW.init0, base, 3 * hw, s[0], b[0], base + hw, 3 * hw, s[1], b[1], base + 2 * hw, 3 * hw, s[2], b[2], rgbT[0]));
         else
             PTTA_TRY(stem(rgbW.init0, base, hw, 0.f, 0.f, base, hw, 0.f, 0.f, base, hw, 0.f, 0.f, rgbT[0]));
-        PTTA_TRY(conv_fwd(rgbW.init2, rgbT[0], c[0], PRO_NONE));
+        PTTA_TRY(conv_fwd(rgbW.init2, rgbT[0], c[0], PRO_NONE, nullptr, 0, cr[0].p));
         const ConvLayer* ls[8] = {&rgbW.e1a, &rgbW.e1b, &rgbW.e2a, &rgbW.e2b, &rgbW.e3a, &rgbW.e3b, &rgbW.e4a, &rgbW.e4b};
         for (int k = 1; k <= 4; ++k) {
-            PTTA_TRY(conv_fwd(*ls[2 * (k - 1)], c[k - 1], rgbT[k], PRO_RELU, nullptr, 1));
-            PTTA_TRY(conv_fwd(*ls[2 * (k - 1) + 1], rgbT[k], c[k], PRO_NONE));
+            PTTA_TRY(conv_fwd(*ls[2 * (k - 1)], cr[k - 1], rgbT[k], PRO_NONE, nullptr, 1));      // stride 2 on ReLU(x_{k-1})
+            PTTA_TRY(conv_fwd(*ls[2 * (k - 1) + 1], rgbT[k], c[k], PRO_NONE, nullptr, 0, k < 4 ? cr[k].p : nullptr));
         }
         return 0;
     }
@@ -707,12 +726,14 @@ struct ptta_msgchn {
         const long long hw = (long long)A.a0.h * A.a0.w;
         PTTA_TRY(stem(Wt.init0, p0, hw, 1.f, 0.f, p1 ? p1 : p0, hw, 1.f, 0.f, p0, hw, 0.f, 0.f, A.a0));
         // a0, t1, t2 hold ReLU(.) (stored by their producers): the stride-1 convs need no prologue
-        PTTA_TRY(conv_fwd(Wt.init2, A.a0, A.x0, PRO_NONE));
-        if (pre_x4) PTTA_TRY(add_up2(A.x0, *pre_x4));
-        PTTA_TRY(conv_fwd(Wt.e1a, A.x0, A.t1, PRO_RELU, nullptr, 1));
-        PTTA_TRY(conv_fwd(Wt.e1b, A.t1, A.x1, PRO_NONE));
-        if (pre_x3) PTTA_TRY(add_up2(A.x1, *pre_x3));
-        PTTA_TRY(conv_fwd(Wt.e2a, A.x1, A.t2, PRO_RELU, nullptr, 1));
+        // x0 / x1 are needed raw (decoder sums, masks) AND through ReLU by the stride-2 convs: whoever writes them last also
+        // writes the ReLU copy
+        PTTA_TRY(conv_fwd(Wt.init2, A.a0, A.x0, PRO_NONE, nullptr, 0, pre_x4 ? nullptr : A.x0r.p));
+        if (pre_x4) PTTA_TRY(add_up2(A.x0, *pre_x4, A.x0r.p));
+        PTTA_TRY(conv_fwd(Wt.e1a, A.x0r, A.t1, PRO_NONE, nullptr, 1));
+        PTTA_TRY(conv_fwd(Wt.e1b, A.t1, A.x1, PRO_NONE, nullptr, 0, pre_x3 ? nullptr : A.x1r.p));
+        if (pre_x3) PTTA_TRY(add_up2(A.x1, *pre_x3, A.x1r.p));
+        PTTA_TRY(conv_fwd(Wt.e2a, A.x1r, A.t2, PRO_NONE, nullptr, 1));
         PTTA_TRY(conv_fwd(Wt.e2b, A.t2, A.x2, PRO_NONE));
         if (pre_x2) PTTA_TRY(add_up2(A.x2, *pre_x2));
         return 0;
@@ -786,7 +807,7 @@ struct ptta_msgchn {
             PTTA_TRY(check_launch("pyramid"));
         }
         Map32 rc[5] = {real.c[0], real.c[1], real.c2raw, real.c[3], real.c[4]};
-        PTTA_TRY(run_rgb_encoder(image, isc, ish, rc));
+        PTTA_TRY(run_rgb_encoder(image, isc, ish, rc, real.cr));
         PTTA_TRY(run_meta(real, training));
         if (!training) return run_cascade(real, true);
         const bool fork = two_streams && st2 != nullptr;
@@ -1109,7 +1130,7 @@ int ptta_up2_1ch_adjoint(const float* ghi, float* glo, int n, int h, int w, int 
 }
 int ptta_add_up2_c32(const void* x, const void* half, void* out, int n, int h, int w, ptta_stream_t stream) {
     long long tot = (long long)n * h * w * 4 * 4;
-    add_up2_c32_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)half, (bf16*)out, n, h, w);
+    add_up2_c32_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)half, (bf16*)out, n, h, w, nullptr);
     return check_launch("add_up2_c32");
 }
 int ptta_up2_c32_adjoint(const void* ghi, void* glo, int n, int h, int w, int accumulate, ptta_stream_t stream) {

@@ -390,7 +390,9 @@ __global__ void up2_1ch_adj_kernel(const float* __restrict__ gh, float* __restri
 }
 
 // 32-channel NHWC bf16: out[p] = x[p] + up2(half)[p]   (thread = pixel x 8 channels)
-__global__ void add_up2_c32_kernel(const bf16* __restrict__ x, const bf16* __restrict__ half, bf16* __restrict__ out, int N, int h, int w) {
+// out2 (optional) additionally receives ReLU(out): the stride-2 tensor-core conv that consumes it has no ReLU-on-load
+__global__ void add_up2_c32_kernel(const bf16* __restrict__ x, const bf16* __restrict__ half, bf16* __restrict__ out, int N, int h, int w,
+                                   bf16* __restrict__ out2) {
     int H = 2 * h, W = 2 * w;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)N * H * W * 4) return;
@@ -421,6 +423,13 @@ __global__ void add_up2_c32_kernel(const bf16* __restrict__ x, const bf16* __res
         uo[j] = pack_bf162(fx.x + r0, fx.y + r1);
     }
     *reinterpret_cast<uint4*>(out + (size_t)pix * 32 + q * 8) = ov;
+    if (out2) {
+        const bf162 z = __floats2bfloat162_rn(0.f, 0.f);
+        bf162* h2 = reinterpret_cast<bf162*>(&ov);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h2[j] = __hmax2(h2[j], z);
+        *reinterpret_cast<uint4*>(out2 + (size_t)pix * 32 + q * 8) = ov;
+    }
 }
 
 // adjoint for 32-channel maps: gl[s] [+]= sum_t w(t,s) gh[t]
