@@ -57,6 +57,9 @@ int ptta_conv3x3_tc(const void* in_bf16, void* out_bf16, const void* wimage_bf16
 int ptta_pack_conv_weight_tc_s2(const void* wpack_bf16, void* wimage_bf16, ptta_stream_t stream);
 int ptta_conv3x3_tc_s2(const void* in_bf16, void* out_bf16, void* out_relu_bf16, const void* wimage_bf16, const float* bias,
                        int n, int h, int w, int relu_out, const void* mask_bf16, const void* add_bf16, ptta_stream_t stream);
+/* timing experiments only: one eager step with a CUDA event after every kernel launch; prints the per-stream timeline */
+int ptta_msgchn_trace_step(ptta_msgchn* engine, const float* image_raw, const float* img_scale3, const float* img_shift3,
+                           const float* sparse_depth, float max_input_depth, float w_sd, float w_sm, float w_cos, ptta_stream_t stream);
 /* timing experiments only: bit mask of pipeline stages the tcgen05 conv skips (results are then wrong) */
 int ptta_debug_set(int mask);
 /* timing experiments only: per-row clock64() stamps of CTA 0 recorded by the tcgen05 conv when mask bit 64 is set */

@@ -39,7 +39,8 @@ struct ConvParams {
     const float* mask_shift;
     const bf16* add;     // [N,Hout,Wout,COUT] or null; out = add + mask*(acc + bias)
     int relu_out;        // store ReLU(out) (outputs that are only ever consumed through a ReLU)
-    bf16* out2;          // optional second output: ReLU(out)
+    bf16* out2;          // optional second output: ReLU(out [+ add2])
+    const bf16* add2;    // optional addend of out2 only
     int tiles_x, tiles_y;
 };
 
@@ -258,7 +259,14 @@ __global__ void __launch_bounds__(256) conv3x3_mma_kernel(const ConvParams p) {
                     }
                     if (p.relu_out) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
                     *reinterpret_cast<uint32_t*>(p.out + pix_off + co) = pack_bf162(v0, v1);
-                    if (p.out2) *reinterpret_cast<uint32_t*>(p.out2 + pix_off + co) = pack_bf162(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+                    if (p.out2) {
+                        if (p.add2) {   // ReLU(bf16(out) + add2), bit-identical to a separate add kernel reading the stored output
+                            const float2 o2 = unpack_bf162(pack_bf162(v0, v1));
+                            const float2 a2 = unpack_bf162(*reinterpret_cast<const uint32_t*>(p.add2 + pix_off + co));
+                            v0 = o2.x + a2.x; v1 = o2.y + a2.y;
+                        }
+                        *reinterpret_cast<uint32_t*>(p.out2 + pix_off + co) = pack_bf162(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+                    }
                 }
             }
         }

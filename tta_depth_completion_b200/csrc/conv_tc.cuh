@@ -28,7 +28,8 @@ struct ConvTcParams {
     const bf16* w;       // 18 KB shared-memory image of the weights (pack_conv_weight_tc_kernel)
     const float* bias;   // [32] or null
     bf16* out;
-    bf16* out2;          // optional second output: ReLU(out) (for consumers that have no ReLU-on-load), or null
+    bf16* out2;          // optional second output: ReLU(out [+ add2]) (for consumers that have no ReLU-on-load), or null
+    const bf16* add2;    // optional addend of out2 only (decoder sums s = ReLU(conv + skip)); mutually exclusive with `add`
     const bf16* mask;    // relu-derivative mask source (same shape as out) or null
     const bf16* add;     // out = add + mask * (conv + bias), or null
     int N, H, W;
@@ -437,11 +438,12 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
                         mk[k] = (idx >> 3) < vp ? __ldg(reinterpret_cast<const uint4*>(p.mask + off0 + (size_t)idx * 8)) : make_uint4(0, 0, 0, 0);
                     }
                 }
-                if (p.add) {
+                const bf16* addsrc = p.add ? p.add : p.add2;             // same registers: the two are never used together
+                if (addsrc) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int idx = k * 32 + lane;
-                        ad[k] = (idx >> 3) < vp ? *reinterpret_cast<const uint4*>(p.add + off0 + (size_t)idx * 8) : make_uint4(0, 0, 0, 0);   // may alias `out`
+                        ad[k] = (idx >> 3) < vp ? *reinterpret_cast<const uint4*>(addsrc + off0 + (size_t)idx * 8) : make_uint4(0, 0, 0, 0);   // may alias `out`
                     }
                 }
                 if (q == 2 && lane == 0) TC_TS(1, t, 0);
@@ -497,6 +499,15 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
                         uint4 val = *reinterpret_cast<const uint4*>(stage + pp * 128 + ((c ^ (pp & 7)) << 4));
                         *reinterpret_cast<uint4*>(p.out + off0 + (size_t)idx * 8) = val;
                         if (p.out2) {
+                            if (p.add2) {        // out2 = ReLU(bf16(out) + add2): the chunk prefetched for this lane is the one it stores
+                                uint32_t* vu = reinterpret_cast<uint32_t*>(&val);
+                                const uint32_t* au = reinterpret_cast<const uint32_t*>(&ad[k]);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 a = unpack_bf162(vu[j]), b = unpack_bf162(au[j]);
+                                    vu[j] = pack_bf162(a.x + b.x, a.y + b.y);
+                                }
+                            }
                             const bf162 z2 = __floats2bfloat162_rn(0.f, 0.f);
                             bf162* h2 = reinterpret_cast<bf162*>(&val);
 #pragma unroll

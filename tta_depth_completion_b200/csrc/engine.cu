@@ -8,6 +8,7 @@
 // rows, decoder3/encoder3/decoder2/encoder2, decoder1's prediction layers and the meta layer.
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -37,8 +38,18 @@ void set_error(const char* fmt, ...) {
     g_error = buf;
 }
 
+// timing experiments: when a trace is active every launch is followed by an event on the stream it went to
+struct LaunchTrace { std::vector<std::string> names; std::vector<int> streams; std::vector<cudaEvent_t> events; cudaStream_t* cur; cudaStream_t main; };
+static LaunchTrace* g_trace = nullptr;
+
 int check_launch(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_trace) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, *g_trace->cur);
+        g_trace->names.push_back(what); g_trace->streams.push_back(*g_trace->cur == g_trace->main ? 0 : 1); g_trace->events.push_back(ev);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("kernel launch %s failed: %s", what, cudaGetErrorString(e));
@@ -84,7 +95,7 @@ struct HeadLayer {   // prdct.3: 32 -> 1
     float bias_host = 0.f;
 };
 struct BnState {     // per call-site statistics
-    float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr;
+    float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *uvar = nullptr;
 };
 struct BnLayer {
     std::string name; int c = 0;
@@ -128,9 +139,10 @@ struct ptta_msgchn {
     std::string prepare_mode;
     cudaStream_t st = nullptr;      // stream of the call in flight (helpers launch on `st`)
     cudaStream_t st2 = nullptr;     // side stream: the zero-image branch runs concurrently with the real branch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_projbn = nullptr;
-    bool two_streams = true, fork_pending = false;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_projbn = nullptr, ev_enc1 = nullptr, ev_zmeta = nullptr;
+    bool two_streams = true;
     bool tc_enabled = true; long long tc_min_pixels = 60000, tc_s2_min_pixels = 16000;
+    bool fuse_dec_sums = true;      // experiment switches (environment: PTTA_NO_TC, PTTA_NO_FUSE_DEC_SUMS, PTTA_ONE_STREAM)
     Arena arena;
     size_t ws_bytes = 0;
     bool bound = false, packed = false;
@@ -200,6 +212,7 @@ struct ptta_msgchn {
     }
     BnState alloc_bn(int c) {
         BnState s; s.mean = allocv<float>(c); s.invstd = allocv<float>(c); s.scale = allocv<float>(c); s.shift = allocv<float>(c);
+        s.uvar = allocv<float>(c);
         return s;
     }
     void need(const std::string& k) { keys.push_back(k); }
@@ -562,21 +575,25 @@ struct ptta_msgchn {
         return tc_enabled && conv_tc_s2_supported(m.n, m.h, m.w) && (long long)m.n * m.h * m.w >= tc_s2_min_pixels;
     }
     int conv_tc(const bf16* image, const float* bias, const Map32& in, const Map32& out, int relu_out, const bf16* mask, const bf16* add,
-                bf16* out2 = nullptr, bool stride2 = false) {
+                bf16* out2 = nullptr, bool stride2 = false, const bf16* add2 = nullptr) {
         ConvTcParams p; memset(&p, 0, sizeof(p));
-        p.w = image; p.bias = bias; p.out = out.p; p.out2 = out2; p.mask = mask; p.add = add; p.N = in.n; p.H = in.h; p.W = in.w; p.relu_out = relu_out;
+        p.w = image; p.bias = bias; p.out = out.p; p.out2 = out2; p.add2 = add2; p.mask = mask; p.add = add; p.N = in.n; p.H = in.h; p.W = in.w;
+        p.relu_out = relu_out;
         return stride2 ? launch_conv_tc_s2(in.p, p, st) : launch_conv_tc(in.p, p, st);
     }
     // relu_out: the output is only ever read through a ReLU (or as a ReLU mask), so ReLU(x) is what gets stored
     // out2 (optional): a second copy holding ReLU(out), for outputs that are read both raw and through a tensor-core conv
+    // add2 (with out2): out2 = ReLU(out + add2) -- the decoder sums s = ReLU(conv(..) + skip) without a separate pass
     int conv_fwd(const ConvLayer& L, const Map32& in, const Map32& out, int pro, const BnState* probn = nullptr, int relu_out = 0,
-                 bf16* out2 = nullptr) {
+                 bf16* out2 = nullptr, const bf16* add2 = nullptr) {
         if (L.img_fwd && pro == PRO_NONE) {
-            if (L.mode_fwd == MODE_S1 && use_tc(in)) return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr, out2);
-            if (L.mode_fwd == MODE_S2 && use_tc_s2(in)) return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr, out2, true);
+            if (L.mode_fwd == MODE_S1 && use_tc(in))
+                return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr, out2, false, add2);
+            if (L.mode_fwd == MODE_S2 && use_tc_s2(in) && !add2)
+                return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr, out2, true);
         }
         ConvParams p; memset(&p, 0, sizeof(p));
-        p.relu_out = relu_out; p.out2 = out2;
+        p.relu_out = relu_out; p.out2 = out2; p.add2 = add2;
         p.in = in.p; p.out = out.p; p.w = L.pack_fwd; p.bias = L.has_bias ? L.b : nullptr;
         p.N = in.n; p.Hin = in.h; p.Win = in.w; p.pro = pro; p.slope = 0.2f;
         if (probn) { p.pro_scale = probn->scale; p.pro_shift = probn->shift; }
@@ -664,13 +681,20 @@ struct ptta_msgchn {
                                                                       s ? s->shift : nullptr, relu_mask);
         return check_launch("col_stats");
     }
-    int bn_forward_stats(const BnLayer& L, const BnState& s, const bf16* x, long long rows, bool training) {
+    // defer_running: compute the batch statistics now, leave the running-statistics update to bn_running_update (ordering)
+    int bn_forward_stats(const BnLayer& L, const BnState& s, const bf16* x, long long rows, bool training, bool defer_running = false) {
         int nblk = 0;
         if (training) PTTA_TRY(stats(x, nullptr, rows, L.c, 0, nullptr, 0, nblk));
         BnParams p; p.gamma = L.gamma; p.beta = L.beta; p.running_mean = L.rm; p.running_var = L.rv; p.num_batches_tracked = L.nbt;
+        if (defer_running) { p.running_mean = nullptr; p.running_var = nullptr; p.num_batches_tracked = nullptr; }
+        p.uvar = s.uvar;
         p.mean = s.mean; p.invstd = s.invstd; p.scale = s.scale; p.shift = s.shift; p.momentum = 0.1f; p.eps = 1e-5f;
         bn_finalize_kernel<<<cdiv(L.c, 32), FIN_THREADS, 0, st>>>(partial, nblk, rows, L.c, p, training ? 1 : 0);
         return check_launch("bn_finalize");
+    }
+    int bn_running_update(const BnLayer& L, const BnState& s) {
+        bn_running_update_kernel<<<cdiv(L.c, 128), 128, 0, st>>>(s.mean, s.uvar, L.rm, L.rv, L.nbt, L.c, 0.1f);
+        return check_launch("bn_running_update");
     }
     int bn_apply(const bf16* x, const bf16* res, bf16* y, long long rows, int C, const BnState& s, int act) {
         bn_apply_kernel<<<cdiv(rows, (256 / (C / 8)) * EW_ROWS), 256, 0, st>>>(x, res, y, rows, C, s.scale, s.shift, act);
@@ -712,13 +736,13 @@ struct ptta_msgchn {
         return 0;
     }
     // c2 = meta(c2raw)
-    int run_meta(Branch& B, bool training) {
+    int run_meta(Branch& B, bool training, bool defer_running = false) {
         if (!two_layers) return conv_fwd(meta1, B.c2raw, B.c[2], PRO_NONE);
         const long long rows = (long long)N * (H / 4) * (W / 4);
         PTTA_TRY(conv_fwd(meta1, B.c2raw, B.mh, PRO_NONE));
-        PTTA_TRY(bn_forward_stats(metaBn1, B.bn1, B.mh.p, rows, training));
+        PTTA_TRY(bn_forward_stats(metaBn1, B.bn1, B.mh.p, rows, training, defer_running));
         PTTA_TRY(conv_fwd(meta2, B.mh, B.mg, PRO_BN_LEAKY, &B.bn1));
-        PTTA_TRY(bn_forward_stats(metaBn2, B.bn2, B.mg.p, rows, training));
+        PTTA_TRY(bn_forward_stats(metaBn2, B.bn2, B.mg.p, rows, training, defer_running));
         return bn_apply(B.mg.p, B.c2raw.p, B.c[2].p, rows, 32, B.bn2, 0);
     }
     int run_encoder(const EncW& Wt, EncAct& A, const float* p0, const float* p1, const Map32* pre_x4, const Map32* pre_x3,
@@ -746,19 +770,22 @@ struct ptta_msgchn {
         PTTA_TRY(add32(E.x0, cx0, A.x0));
         // u2, s1, u1, s0, h hold ReLU(.): each is read through a ReLU only (forward) or as a ReLU mask (backward)
         PTTA_TRY(conv_fwd(Wt.d2a, A.x2, A.u2, PRO_RELU, nullptr, 1));
-        PTTA_TRY(conv_fwd(Wt.d2b, A.u2, A.x3, PRO_NONE));
-        PTTA_TRY(add32(A.x1, A.x3, A.s1, 1));
-        PTTA_TRY(conv_fwd(Wt.d1a, A.s1, A.u1, PRO_NONE, nullptr, 1));
-        PTTA_TRY(conv_fwd(Wt.d1b, A.u1, A.x4, PRO_NONE));
-        PTTA_TRY(add32(A.x4, A.x0, A.s0, 1));
+        if (fuse_dec_sums) {
+            PTTA_TRY(conv_fwd(Wt.d2b, A.u2, A.x3, PRO_NONE, nullptr, 0, A.s1.p, A.x1.p));      // x3, and s1 = ReLU(x1 + x3) from the same epilogue
+            PTTA_TRY(conv_fwd(Wt.d1a, A.s1, A.u1, PRO_NONE, nullptr, 1));
+            PTTA_TRY(conv_fwd(Wt.d1b, A.u1, A.x4, PRO_NONE, nullptr, 0, A.s0.p, A.x0.p));      // x4, and s0 = ReLU(x4 + x0)
+        } else {
+            PTTA_TRY(conv_fwd(Wt.d2b, A.u2, A.x3, PRO_NONE));
+            PTTA_TRY(add32(A.x1, A.x3, A.s1, 1));
+            PTTA_TRY(conv_fwd(Wt.d1a, A.s1, A.u1, PRO_NONE, nullptr, 1));
+            PTTA_TRY(conv_fwd(Wt.d1b, A.u1, A.x4, PRO_NONE));
+            PTTA_TRY(add32(A.x4, A.x0, A.s0, 1));
+        }
         PTTA_TRY(conv_fwd(Wt.p1, A.s0, A.h, PRO_NONE, nullptr, 1));
         return head_fwd(Wt.p3, A.h, add, out);
     }
-    int run_cascade(Branch& B, bool is_real) {
-        if (is_real) {
-            PTTA_TRY(run_encoder(enc1W, B.e1, d14.p, nullptr, nullptr, nullptr, nullptr));
-            if (fork_pending) { PTTA_CUDA(cudaEventRecord(ev_fork, st)); fork_pending = false; }   // zero branch may start: pyramid, meta, enc1 done
-        }
+    int run_cascade(Branch& B, bool is_real, bool enc1_done = false) {
+        if (is_real && !enc1_done) PTTA_TRY(run_encoder(enc1W, B.e1, d14.p, nullptr, nullptr, nullptr, nullptr));
         PTTA_TRY(run_decoder(dec1W, B.d1, B.e1, B.c[2], B.c[3], B.c[4], nullptr, B.d1.out));
         PTTA_TRY(up2_1(B.d1.out, nullptr, nullptr, B.p12));                        // p12 = up2(out14)
         PTTA_TRY(run_encoder(enc2W, B.e2, d12.p, B.p12.p, &B.d1.x4, &B.d1.x3, &B.d1.x2));
@@ -807,36 +834,51 @@ struct ptta_msgchn {
             PTTA_TRY(check_launch("pyramid"));
         }
         Map32 rc[5] = {real.c[0], real.c[1], real.c2raw, real.c[3], real.c[4]};
-        PTTA_TRY(run_rgb_encoder(image, isc, ish, rc, real.cr));
-        PTTA_TRY(run_meta(real, training));
-        if (!training) return run_cascade(real, true);
-        const bool fork = two_streams && st2 != nullptr;
+        const bool fork = training && two_streams && st2 != nullptr;
         if (!fork) {
+            PTTA_TRY(run_rgb_encoder(image, isc, ish, rc, real.cr));
+            PTTA_TRY(run_meta(real, training));
             PTTA_TRY(run_cascade(real, true));
-            PTTA_TRY(zero_side());
+            if (!training) return 0;
+            PTTA_TRY(zero_side(false));
             return mlp(proj0, projBn, bnProjR, proj3, real.e3.x2.p, 32, h_a0r, ref, true, h_an);
         }
-        // real branch on `st`; zero-image branch + its head GEMMs on `st2` (fork after encoder 1, join before the loss)
-        fork_pending = true;
-        PTTA_TRY(run_cascade(real, true));
+        // Two streams.  The zero-image branch depends on the sparse depth and the weights only -- not on the image -- so it
+        // starts right after the pyramid, together with encoder 1 (shared by both branches), while the main stream runs the RGB
+        // encoder.  What the reference's execution order fixes (real branch first, zero branch second) are the in-place
+        // BatchNorm running-statistics updates: the zero branch defers its meta-layer updates (they are applied on the main
+        // stream after the real ones) and the proxy-head BatchNorm keeps zero rows -> real rows through ev_projbn.
+        PTTA_CUDA(cudaEventRecord(ev_fork, st));
         {
             cudaStream_t main = st;
             double* main_partial = partial;
             PTTA_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
             st = st2; partial = partial2;
-            int rc2 = zero_side();
+            int rc2 = run_encoder(enc1W, real.e1, d14.p, nullptr, nullptr, nullptr, nullptr);
+            if (!rc2 && cudaEventRecord(ev_enc1, st2) != cudaSuccess) { set_error("cudaEventRecord failed"); rc2 = 2; }
+            if (!rc2) rc2 = zero_side(true);
             if (!rc2 && cudaEventRecord(ev_join, st2) != cudaSuccess) { set_error("cudaEventRecord failed"); rc2 = 2; }
             st = main; partial = main_partial;
             if (rc2) return rc2;
         }
+        PTTA_TRY(run_rgb_encoder(image, isc, ish, rc, real.cr));
+        PTTA_TRY(run_meta(real, true));
+        if (two_layers) {
+            PTTA_CUDA(cudaStreamWaitEvent(st, ev_zmeta, 0));
+            PTTA_TRY(bn_running_update(metaBn1, zero.bn1));
+            PTTA_TRY(bn_running_update(metaBn2, zero.bn2));
+        }
+        PTTA_CUDA(cudaStreamWaitEvent(st, ev_enc1, 0));
+        PTTA_TRY(run_cascade(real, true, true));
         PTTA_TRY(mlp(proj0, projBn, bnProjR, proj3, real.e3.x2.p, 32, h_a0r, ref, true, h_an, nullptr, ev_projbn));
         PTTA_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
         return 0;
     }
     // zero-image branch (no_grad in the reference, network_exp_msg_chn_adapt.py:508-532; BN running statistics are updated a second
     // time here, exactly as the reference does) and emb = pred(proj(z_zero)) (:553); rows = pixels of the /4 map (NHWC)
-    int zero_side() {
-        PTTA_TRY(run_meta(zero, true));
+    int zero_side(bool defer_meta_running) {
+        PTTA_TRY(run_meta(zero, true, defer_meta_running));
+        if (defer_meta_running && two_layers) PTTA_CUDA(cudaEventRecord(ev_zmeta, st));
         PTTA_TRY(run_cascade(zero, false));
         PTTA_TRY(mlp(proj0, projBn, bnProjZ, proj3, zero.e3.x2.p, 32, h_a0z, h_pz, true, h_an2, ev_projbn));
         return mlp(pred0, predBn, bnPred, pred3, h_pz, 512, h_q0, emb, true, h_an2);
@@ -1294,6 +1336,9 @@ int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepa
     e->N = e->padded ? 2 * n : n; e->H = (h + 15) / 16 * 16; e->W = (w + 15) / 16 * 16;
     e->two_layers = two; e->prepare_mode = mode;
     e->has_heads = mode.find("selfsup") != std::string::npos;
+    if (getenv("PTTA_NO_TC")) e->tc_enabled = false;
+    if (getenv("PTTA_NO_FUSE_DEC_SUMS")) e->fuse_dec_sums = false;
+    if (getenv("PTTA_ONE_STREAM")) e->two_streams = false;
     e->define_model();
     e->plan();
     *out = e;
@@ -1302,7 +1347,8 @@ int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepa
 void ptta_msgchn_destroy(ptta_msgchn* e) {
     if (!e) return;
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
-    if (e->st2) { cudaStreamDestroy(e->st2); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaEventDestroy(e->ev_projbn); }
+    if (e->st2) { cudaStreamDestroy(e->st2); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaEventDestroy(e->ev_projbn);
+                 cudaEventDestroy(e->ev_enc1); cudaEventDestroy(e->ev_zmeta); }
     delete e;
 }
 size_t ptta_msgchn_workspace_bytes(const ptta_msgchn* e) { return e ? e->ws_bytes : 0; }
@@ -1319,6 +1365,8 @@ int ptta_msgchn_bind_workspace(ptta_msgchn* e, void* ws, size_t bytes, ptta_stre
         PTTA_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
         PTTA_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         PTTA_CUDA(cudaEventCreateWithFlags(&e->ev_projbn, cudaEventDisableTiming));
+        PTTA_CUDA(cudaEventCreateWithFlags(&e->ev_enc1, cudaEventDisableTiming));
+        PTTA_CUDA(cudaEventCreateWithFlags(&e->ev_zmeta, cudaEventDisableTiming));
     }
     PTTA_CUDA(cudaMemsetAsync(ws, 0, e->ws_bytes, (cudaStream_t)stream));
     AdamHyper hy;
@@ -1464,5 +1512,32 @@ const char* ptta_msgchn_tensor_name(const ptta_msgchn* e, int i) {
     return (e && i >= 0 && i < (int)e->named_order.size()) ? e->named_order[i].c_str() : nullptr;
 }
 long long ptta_msgchn_launch_count(const ptta_msgchn*) { return g_launches.load(); }
+
+/* timing experiments only: one eager step with an event after every launch; prints "end_us stream kernel" lines to stdout */
+int ptta_msgchn_trace_step(ptta_msgchn* e, const float* image_raw, const float* isc, const float* ish, const float* sparse, float cap,
+                           float w_sd, float w_sm, float w_cos, ptta_stream_t stream) {
+    PTTA_CHECK(e && image_raw && sparse && isc && ish, "trace_step: null argument");
+    e->st = (cudaStream_t)stream;
+    LaunchTrace tr; tr.cur = &e->st; tr.main = e->st;
+    cudaEvent_t t0;
+    PTTA_CUDA(cudaEventCreate(&t0));
+    PTTA_CUDA(cudaStreamSynchronize(e->st));
+    PTTA_CUDA(cudaEventRecord(t0, e->st));
+    g_trace = &tr;
+    int rc = e->tta_step(image_raw, isc, ish, sparse, cap, w_sd, w_sm, w_cos);
+    g_trace = nullptr;
+    PTTA_CUDA(cudaDeviceSynchronize());
+    float prev[2] = {0.f, 0.f};
+    for (size_t i = 0; i < tr.events.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, tr.events[i]);
+        printf("%9.1f  s%d  +%7.1f  %s\n", ms * 1e3f, tr.streams[i], ms * 1e3f - prev[tr.streams[i]], tr.names[i].c_str());
+        prev[tr.streams[i]] = ms * 1e3f;
+        cudaEventDestroy(tr.events[i]);
+    }
+    fflush(stdout);
+    cudaEventDestroy(t0);
+    return rc;
+}
 
 }  // extern "C"

@@ -590,6 +590,7 @@ struct BnParams {
     const float* gamma; const float* beta;
     float* running_mean; float* running_var; long long* num_batches_tracked;
     float* mean; float* invstd; float* scale; float* shift;
+    float* uvar;          // optional: unbiased batch variance (what a deferred running-statistics update needs)
     float momentum, eps;
 };
 
@@ -642,8 +643,9 @@ __global__ void __launch_bounds__(FIN_THREADS) bn_finalize_kernel(const double* 
         float sc = p.gamma[ch] * invstd;
         p.scale[ch] = sc;
         p.shift[ch] = p.beta[ch] - (float)m * sc;
+        double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+        if (p.uvar) p.uvar[ch] = (float)unbiased;
         if (p.running_mean) {
-            double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
             p.running_mean[ch] = (1.f - p.momentum) * p.running_mean[ch] + p.momentum * (float)m;
             p.running_var[ch] = (1.f - p.momentum) * p.running_var[ch] + p.momentum * (float)unbiased;
         }
@@ -658,6 +660,18 @@ __global__ void __launch_bounds__(FIN_THREADS) bn_finalize_kernel(const double* 
         p.scale[ch] = sc;
         p.shift[ch] = p.beta[ch] - p.running_mean[ch] * sc;
     }
+}
+
+// deferred running-statistics update (momentum form of nn.BatchNorm) from statistics computed earlier on another stream:
+// keeps the reference's update ORDER (real image first, zero image second) while the zero-image branch runs ahead
+__global__ void bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ uvar, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var, long long* __restrict__ num_batches_tracked, int C, float momentum) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < C) {
+        running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean[ch];
+        running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * uvar[ch];
+    }
+    if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
 }
 
 // y = act(x*scale+shift) [+ res];  act: 0 none, 1 relu
