@@ -137,7 +137,9 @@ def workload_config(args):
     return {'workload': 'MSG-CHN ProxyTTA continual adaptation, synthetic %s-shape %dx3x%dx%d frames, prepare_mode %s, adapt_mode meta, '
                         'lr %g, w_sd/w_smooth/w_cos %g/%g/%g, Adam(0.9,0.999,1e-8)' % (dataset.upper(), args.batch, h, w, mode, lr, W_SD, W_SM,
                                                                                        W_COS),
-            'batch_per_gpu': args.batch, 'parallelism': 'independent sequence shard per GPU (no collective)',
+            'batch_per_gpu': args.batch,
+            'parallelism': 'independent sequence shard per GPU (no collective)' if getattr(args, 'mode', 'shards') == 'shards' else
+                           'shared model: NCCL mean all-reduce of the flat adapted-gradient buffer, identical fused Adam on every rank',
             'l2': 'ring of %d distinct frames; per-step working set (~1.5 GB of activations) exceeds the 126 MB L2' % RING}
 
 
@@ -242,22 +244,32 @@ def run_native(args):
     # ---- device-resident throughput (`value`) -------------------------------------------------------------------
     # every step: D2D copy of the next ring frame into the step's fixed input buffers, then the whole step replayed from
     # its CUDA graph (--no-graph: the same kernels launched eagerly)
-    use_graph = args.graph
+    use_graph = args.graph and args.mode == 'shards'
+    if args.mode == 'shared':
+        # BASELINE.json configs[4]: one shared model, every rank adapts on its own batch, the flat adapted-gradient buffer
+        # (74 080 floats) is mean-all-reduced over NCCL before the fused Adam step
+        from tta_depth_completion_b200 import sharding
+
+        def run_step(img, sp, graph=False):
+            sharding.shared_model_step(model, img, sp, lr, W_SD, W_SM, W_COS)
+    else:
+        def run_step(img, sp, graph=False):
+            model.tta_step(img, sp, lr, W_SD, W_SM, W_COS, graph=graph)
     img_d = torch.empty_like(dev_frames[0][0])
     sp_d = torch.empty_like(dev_frames[0][1])
     eng = None
     with torch.cuda.stream(stream):
         # launches per step are counted on one eager step (graph replays do not pass through the launch counter)
         img_d.copy_(dev_frames[0][0]); sp_d.copy_(dev_frames[0][1])
-        model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS)
+        run_step(img_d, sp_d)
         eng = model._last_engine
         l0 = eng.launch_count()
-        model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS)
+        run_step(img_d, sp_d)
         launches_per_step = eng.launch_count() - l0
         for i in range(args.warmup):
             img, sp = dev_frames[i % RING]
             img_d.copy_(img, non_blocking=True); sp_d.copy_(sp, non_blocking=True)
-            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS, graph=use_graph)
+            run_step(img_d, sp_d, graph=use_graph)
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -266,7 +278,7 @@ def run_native(args):
         for i in range(args.steps):
             img, sp = dev_frames[(args.warmup + i) % RING]
             img_d.copy_(img, non_blocking=True); sp_d.copy_(sp, non_blocking=True)
-            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS, graph=use_graph)
+            run_step(img_d, sp_d, graph=use_graph)
         e1.record(stream)
         barrier()
         ms_total = e0.elapsed_time(e1)
@@ -277,7 +289,7 @@ def run_native(args):
         for i in range(max(3, args.warmup)):
             img_d.copy_(pinned[i % RING][0], non_blocking=True)
             sp_d.copy_(pinned[i % RING][1], non_blocking=True)
-            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS, graph=use_graph)
+            run_step(img_d, sp_d, graph=use_graph)
             model.last_losses()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,7 +297,7 @@ def run_native(args):
         for i in range(args.steps):
             img_d.copy_(pinned[i % RING][0], non_blocking=True)
             sp_d.copy_(pinned[i % RING][1], non_blocking=True)
-            model.tta_step(img_d, sp_d, lr, W_SD, W_SM, W_COS, graph=use_graph)
+            run_step(img_d, sp_d, graph=use_graph)
             e2e_losses = model.last_losses()            # D2H + sync (the driver reads the loss every step, src/tta_main.py:801)
         f1.record(stream)
         barrier()
@@ -331,6 +343,7 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--workload', default='kitti', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=1)
+    ap.add_argument('--mode', default='shards', choices=['shards', 'shared'], help='shards: independent sequence shard per GPU, no collective (default); shared: one shared model, NCCL all-reduce of the adapted-parameter gradients (BASELINE.json configs[4])')
     ap.add_argument('--no-graph', dest='graph', action='store_false', help='launch the step kernels eagerly instead of replaying the captured CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip the roofline / cpu_baseline legs (profiling runs)')
     args = ap.parse_args()
