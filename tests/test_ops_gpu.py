@@ -287,6 +287,27 @@ def test_conv_tcgen05_matches_mma(ops, n, h, w):
         ops.conv3x3_tc(x[:, :, :w - 1].contiguous(), wp, bias)      # odd width
 
 
+@pytest.mark.parametrize('n,h,w', [(1, 16, 256), (1, 32, 48), (2, 18, 38), (1, 88, 304), (3, 64, 516), (1, 352, 1216)])
+def test_conv_tcgen05_stride2_matches_mma(ops, n, h, w):
+    """the stride-2 tcgen05 conv (Conv2d(s2) forward / ConvTranspose2d(s2) data gradient) is bit-identical to the mma.sync kernel"""
+    g = torch.Generator().manual_seed(13)
+    wt = (torch.randn((32, 32, 3, 3), generator=g) * (2.0 / 288) ** 0.5).to(DEV)
+    wp = ops.pack_conv_weight(wt, 'conv_fwd')
+    bias = (torch.randn(32, generator=g) * 0.1).to(DEV)
+    x = torch.randn((n, h, w, 32), generator=g).to(DEV).to(torch.bfloat16)
+    m = torch.randn((n, h // 2, w // 2, 32), generator=g).to(DEV).to(torch.bfloat16)
+    a = torch.randn((n, h // 2, w // 2, 32), generator=g).to(DEV).to(torch.bfloat16)
+    want = ops.conv3x3(x, wp, bias, ops.MODE_S2, ops.PRO_RELU)
+    got, got_relu = ops.conv3x3_tc_s2(torch.relu(x), wp, bias, want_relu_copy=True)
+    assert torch.equal(got, want), 'conv_tc_s2 forward is not bit-identical to mma.sync'
+    assert torch.equal(got_relu, torch.relu(want)), 'conv_tc_s2 ReLU copy'
+    assert torch.equal(ops.conv3x3_tc_s2(torch.relu(x), wp, bias, relu_out=True), torch.relu(want))
+    want = ops.conv3x3(x, wp, None, ops.MODE_S2, ops.PRO_NONE, mask=m, mask_mode=ops.MASK_RELU, add=a)
+    assert torch.equal(ops.conv3x3_tc_s2(x, wp, None, mask=m, add=a), want), 'conv_tc_s2 mask+add'
+    with pytest.raises(RuntimeError):
+        ops.conv3x3_tc_s2(x[:, :h - 1].contiguous(), wp, bias)       # odd height: must fail loudly
+
+
 def test_adam_matches_torch(ops):
     g = torch.Generator().manual_seed(10)
     p0 = torch.randn((5000,), generator=g)
