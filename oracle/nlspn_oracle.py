@@ -1,0 +1,287 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (plain PyTorch fp32) of ProxyTTA's per-frame adaptation step for the
+NLSPN back-end (SURVEY.md section 8 row a18 on top of a19-a21).  It is the checker for the CUDA path, never the thing
+shipped or measured: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
+import it.
+
+Parity pinning: the reference holds no golden vectors; this file is pinned against *outputs of the reference itself*
+(`oracle/gen_golden_nlspn_net.py` instantiates the reference's own `ExternalModel_Adapt('nlspn')`, loads the seeded
+checkpoint produced by `make_synthetic_checkpoint` below, runs the driver's forward / compute_loss / backward / Adam
+lines and commits losses, outputs, gradients and adapted tensors under tests/golden/nlspn_net_*.pt).
+tests/test_nlspn_net_oracle.py checks this file against those fixtures.  The reference's DCN CUDA extension has no CPU
+path; in the fixture run that one import is resolved to oracle.nlspn_prop_oracle.MDConvFn (pinned separately against
+torchvision's DCNv2 in fp64 and against the extension itself on the GPU box).
+
+Functional over a flat state dict whose keys and shapes are those of the reference's `NLSPNModel_Adapt.state_dict()`
+after `_prepare_head('meta_selfsup_seq_1layer_ema')` (oracle/nlspn_state_manifest.json, written by the generator).
+
+Reference files restated here (paths relative to the reference root):
+  M  = external_src/NLSPN/src/model/nlspnmodel_adapt.py
+  C  = external_src/NLSPN/src/model/common.py
+  W  = src/nlspn_model_adapt.py
+  E  = src/external_model_adapt.py
+  T  = src/tta_main.py
+  torchvision.models.resnet34 (BasicBlock, layers [3, 4, 6, 3]) -- third-party, pinned torchvision==0.10.1 by the
+  reference's README; restated from its published definition (conv3x3-BN-ReLU-conv3x3-BN (+1x1/s2 conv-BN shortcut)-add-ReLU).
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+from . import msgchn_oracle as O
+from . import nlspn_prop_oracle as P
+
+PREPARE_MODE = 'meta_selfsup_seq_1layer_ema'
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+RESNET34_LAYERS = (('conv2', 64, 64, 3, 1), ('conv3', 64, 128, 4, 2), ('conv4', 128, 256, 6, 2), ('conv5', 256, 512, 3, 2))
+BN_EPS = 1e-5
+
+
+class Precision(O.Precision):
+    pass
+
+
+FP32 = O.FP32
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic checkpoint: seeded, so the GPU box regenerates the identical state dict
+# ----------------------------------------------------------------------------------------------------------------
+def _conv(sd, g, name, cout, cin, k=3, bias=False, transposed=False, gain=1.0):
+    shape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+    std = gain * math.sqrt(2.0 / (cin * k * k))
+    sd[name + '.weight'] = torch.randn(shape, generator=g) * std
+    if bias:
+        sd[name + '.bias'] = 0.02 * torch.randn(cout, generator=g)
+
+
+def _bn(sd, g, name, c):
+    sd[name + '.weight'] = 1.0 + 0.1 * torch.randn(c, generator=g)
+    sd[name + '.bias'] = 0.05 * torch.randn(c, generator=g)
+    sd[name + '.running_mean'] = 0.05 * torch.randn(c, generator=g)
+    sd[name + '.running_var'] = 1.0 + 0.1 * torch.rand(c, generator=g)
+    sd[name + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+
+
+def make_synthetic_checkpoint(seed=0, prepare_mode=PREPARE_MODE):
+    """Key order follows the reference module's registration order (M:384-448 then `_prepare_head` M:1338-1374)."""
+    if 'meta' not in prepare_mode or '1layer' not in prepare_mode or 'ema' not in prepare_mode:
+        raise NotImplementedError(prepare_mode)
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    _conv(sd, g, 'conv1_rgb.0', 48, 3, bias=True)
+    _conv(sd, g, 'conv1_dep.0', 16, 1, bias=True, gain=0.05)      # depth in metres (up to 80) -> O(1) features
+    for name, cin, cout, blocks, stride in RESNET34_LAYERS:
+        for b in range(blocks):
+            p = '%s.%d' % (name, b)
+            _conv(sd, g, p + '.conv1', cout, cin if b == 0 else cout)
+            _bn(sd, g, p + '.bn1', cout)
+            _conv(sd, g, p + '.conv2', cout, cout, gain=0.5)
+            _bn(sd, g, p + '.bn2', cout)
+            if b == 0 and stride != 1:
+                _conv(sd, g, p + '.downsample.0', cout, cin, k=1)
+                _bn(sd, g, p + '.downsample.1', cout)
+    _conv(sd, g, 'conv6.0', 512, 512)
+    _bn(sd, g, 'conv6.1', 512)
+    for name, cin, cout in (('dec5', 512, 256), ('dec4', 768, 128), ('dec3', 384, 64), ('dec2', 192, 64)):
+        _conv(sd, g, name + '.0', cout, cin, transposed=True)
+        _bn(sd, g, name + '.1', cout)
+    _conv(sd, g, 'id_dec1.0', 64, 128)
+    _bn(sd, g, 'id_dec1.1', 64)
+    _conv(sd, g, 'id_dec0.0', 1, 128, bias=True)
+    sd['id_dec0.0.bias'] += 8.0                    # initial depth of a few metres, so the propagated depth is not clamped to 0
+    _conv(sd, g, 'gd_dec1.0', 64, 128)
+    _bn(sd, g, 'gd_dec1.1', 64)
+    _conv(sd, g, 'gd_dec0.0', 8, 128, bias=True)
+    _conv(sd, g, 'cf_dec1.0', 32, 128)
+    _bn(sd, g, 'cf_dec1.1', 32)
+    _conv(sd, g, 'cf_dec0.0', 1, 96, bias=True)
+    # prop_layer (M:219-247): conv_offset_aff is zero-initialised by the reference, which makes the propagation the identity
+    # -> seeded values (offsets ~1 px, affinities small), SURVEY.md 8c
+    scale = torch.cat((torch.full((16,), 0.05), torch.full((8,), 0.004))).view(24, 1, 1, 1)
+    sd['prop_layer.aff_scale_const'] = torch.full((1,), 0.5 * 8)
+    sd['prop_layer.w'] = torch.ones((1, 1, 3, 3))
+    sd['prop_layer.b'] = torch.zeros(1)
+    sd['prop_layer.w_conf'] = torch.ones((1, 1, 1, 1))
+    sd['prop_layer.conv_offset_aff.weight'] = torch.randn((24, 8, 3, 3), generator=g) * scale
+    sd['prop_layer.conv_offset_aff.bias'] = torch.randn((24,), generator=g) * 0.05
+    # heads (M:1338-1343): proj, proj_t = deepcopy(proj), pred
+    O._mlp_entries(sd, g, 'proj', 512, 1024, 1024)
+    for k in [k for k in sd if k.startswith('proj.')]:
+        sd['proj_t.' + k[5:]] = sd[k].clone()
+    O._mlp_entries(sd, g, 'pred', 1024, 1024, 1024)
+    # meta layer (M:1370-1374): Conv2d(48,48,3,1,1)
+    _conv(sd, g, 'conv1_rgb_meta', 48, 48, bias=True, gain=0.7)
+    return sd
+
+
+def synthetic_frame(seq_seed, t, n, h, w, dataset='kitti'):
+    return O.synthetic_frame(seq_seed, t, n, h, w, dataset)
+
+
+def normalize_image(image):
+    """bash/adapt/adapt_nlspn_vkitti.sh:25-28: ImageNet statistics on the [0,1] image (T:595-604)"""
+    mean = torch.tensor(IMAGENET_MEAN, dtype=image.dtype).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, dtype=image.dtype).view(1, 3, 1, 1)
+    return (image / 255.0 - mean) / std
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# network pieces
+# ----------------------------------------------------------------------------------------------------------------
+def _bn2d(sd, name, x):
+    """Every BatchNorm2d after adapt_parameters('meta_bn') (W:322-337): batch statistics in train AND eval, no running
+    statistics (track_running_stats False, buffers None)."""
+    return F.batch_norm(x, None, None, sd[name + '.weight'], sd[name + '.bias'], True, 0.1, BN_EPS)
+
+
+def _cbr(sd, name, x, pr, stride=1, bn=True, act='leaky'):
+    # C:45-60 conv_bn_relu: Conv2d(bias = not bn) [+ BN] [+ LeakyReLU(0.2)]
+    y = F.conv2d(pr.act(x), pr.wgt(sd[name + '.0.weight']), sd.get(name + '.0.bias'), stride=stride, padding=1)
+    if bn:
+        y = _bn2d(sd, name + '.1', y)
+    if act == 'leaky':
+        y = F.leaky_relu(y, 0.2)
+    return y
+
+
+def _ctbr(sd, name, x, pr):
+    # C:63-80 convt_bn_relu: ConvTranspose2d(k3, s2, p1, op1, no bias) + BN + LeakyReLU(0.2)
+    y = F.conv_transpose2d(pr.act(x), pr.wgt(sd[name + '.0.weight']), None, stride=2, padding=1, output_padding=1)
+    return F.leaky_relu(_bn2d(sd, name + '.1', y), 0.2)
+
+
+def _basic_block(sd, p, x, stride, pr):
+    # torchvision BasicBlock.forward
+    out = F.conv2d(pr.act(x), pr.wgt(sd[p + '.conv1.weight']), None, stride=stride, padding=1)
+    out = F.relu(_bn2d(sd, p + '.bn1', out))
+    out = F.conv2d(pr.act(out), pr.wgt(sd[p + '.conv2.weight']), None, stride=1, padding=1)
+    out = _bn2d(sd, p + '.bn2', out)
+    if (p + '.downsample.0.weight') in sd:
+        idt = F.conv2d(pr.act(x), pr.wgt(sd[p + '.downsample.0.weight']), None, stride=stride)
+        idt = _bn2d(sd, p + '.downsample.1', idt)
+    else:
+        idt = x
+    return F.relu(out + idt)
+
+
+def _res_layer(sd, name, x, blocks, stride, pr):
+    for b in range(blocks):
+        x = _basic_block(sd, '%s.%d' % (name, b), x, stride if b == 0 else 1, pr)
+    return x
+
+
+def _concat(fd, fe):
+    # M:473-490: crop the decoder feature if it is larger than the encoder one
+    hd, wd = fd.shape[-2:]
+    he, we = fe.shape[-2:]
+    if hd > he:
+        fd = fd[:, :, :he, :]
+    if wd > we:
+        fd = fd[:, :, :, :we]
+    return torch.cat((fd, fe), dim=1)
+
+
+def encoder(sd, image, sparse_depth, pr=FP32):
+    """M:866-880: fe1 .. fe6"""
+    x = _cbr(sd, 'conv1_rgb', image, pr, bn=False)
+    fe1_rgb = F.conv2d(pr.act(x), pr.wgt(sd['conv1_rgb_meta.weight']), sd['conv1_rgb_meta.bias'], padding=1)   # '1layer' meta conv
+    fe1_dep = _cbr(sd, 'conv1_dep', sparse_depth, pr, bn=False)                                               # conv1_dep_meta = Identity
+    fe = [torch.cat((fe1_rgb, fe1_dep), dim=1)]
+    for name, cin, cout, blocks, stride in RESNET34_LAYERS:
+        fe.append(_res_layer(sd, name, fe[-1], blocks, stride, pr))
+    fe.append(_cbr(sd, 'conv6', fe[-1], pr, stride=2))
+    return fe
+
+
+def _mlp(sd, name, x, training, pr):
+    return O._mlp(sd, name, x, training, pr)
+
+
+def network_forward(sd, image, sparse_depth, training, pr=FP32, legacy=True, prop_time=18, trace=None):
+    """NLSPNModel_Adapt._rgbd_meta_contrast with mode = [adapt, seq, reverse, ema] (M:850-944)."""
+    fe1, fe2, fe3, fe4, fe5, fe6 = encoder(sd, image, sparse_depth, pr)
+    fd5 = _ctbr(sd, 'dec5', fe6, pr)
+    fd4 = _ctbr(sd, 'dec4', _concat(fd5, fe5), pr)
+    fd3 = _ctbr(sd, 'dec3', _concat(fd4, fe4), pr)
+    fd2 = _ctbr(sd, 'dec2', _concat(fd3, fe3), pr)
+    f21 = _concat(fd2, fe2)
+    id_fd1 = _cbr(sd, 'id_dec1', f21, pr)
+    pred_init = _cbr(sd, 'id_dec0', _concat(id_fd1, fe1), pr, bn=False)           # conv + LeakyReLU (M:430-431)
+    gd_fd1 = _cbr(sd, 'gd_dec1', f21, pr)
+    guide = _cbr(sd, 'gd_dec0', _concat(gd_fd1, fe1), pr, bn=False, act=None)
+    cf_fd1 = _cbr(sd, 'cf_dec1', f21, pr)
+    confidence = torch.sigmoid(F.conv2d(pr.act(_concat(cf_fd1, fe1)), pr.wgt(sd['cf_dec0.0.weight']), sd['cf_dec0.0.bias'], padding=1))
+    # prop_layer (M:340-373)
+    offset_aff = F.conv2d(guide, sd['prop_layer.conv_offset_aff.weight'], sd['prop_layer.conv_offset_aff.bias'], padding=1)
+    offset, aff = P.offset_affinity(offset_aff, confidence, sd['prop_layer.aff_scale_const'], legacy=legacy)
+    y, _ = P.propagate(pred_init, offset, aff, sparse_depth, prop_time=prop_time, preserve_input=True)
+    output = torch.clamp(y, min=0)                                                 # M:901
+    if trace is not None:
+        trace.update(fe1=fe1, fe2=fe2, fe3=fe3, fe4=fe4, fe5=fe5, fe6=fe6, fd5=fd5, fd4=fd4, fd3=fd3, fd2=fd2, pred_init=pred_init,
+                     guide=guide, confidence=confidence, offset=offset, aff=aff, y=y)
+    if not training:
+        return output
+    with torch.no_grad():                                                          # M:905-914
+        fe6_z = encoder(sd, torch.zeros_like(image), sparse_depth, pr)[-1]
+    # M:935-936 ('ema', 'reverse', 'adapt'): rows are pixels of the /16 map in NHWC order
+    z_zero = fe6_z.permute(0, 2, 3, 1).reshape(-1, 512).detach()
+    z_real = fe6.permute(0, 2, 3, 1).reshape(-1, 512)
+    emb = _mlp(sd, 'pred', _mlp(sd, 'proj', z_zero, training, pr), training, pr)
+    ref = _mlp(sd, 'proj_t', z_real, training, pr)
+    if trace is not None:
+        trace.update(fe6_zero=fe6_z, emb=emb, ref=ref)
+    return output, emb, ref
+
+
+def model_forward(sd, image, sparse_depth, training, max_input_depth, pr=FP32, trace=None):
+    """ExternalModel_Adapt.forward (E:103-108: clamp) -> NLSPNModel_Adapt.forward (W:88-128; the eval-time CPU
+    `inpainting` of W:124-127 is not part of the adaptation step)."""
+    if max_input_depth is not None:
+        sparse_depth = torch.clamp(sparse_depth, 0, max_input_depth)
+    return network_forward(sd, image, sparse_depth, training, pr, trace=trace)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# adapted parameters (W:322-337) and one TTA step (T:583-633)
+# ----------------------------------------------------------------------------------------------------------------
+def adapt_parameter_names(sd, mode='meta_bn'):
+    """'meta_bn': every parameter whose name contains 'meta', then weight and bias of every BatchNorm2d in module order
+    (BatchNorm1d of the heads is not a BatchNorm2d: without convert_syncbn it is not adapted -- SURVEY.md 3.4)."""
+    if mode != 'meta_bn':
+        raise NotImplementedError(mode)
+    names = [k for k in sd if 'meta' in k and k.rsplit('.', 1)[-1] in ('weight', 'bias')]
+    for k in sd:
+        if k.endswith('.running_mean') and not k.startswith(('proj', 'pred')):
+            base = k[:-len('.running_mean')]
+            names += [base + '.weight', base + '.bias']
+    return names
+
+
+def tta_step(sd, state, image, sparse_depth, *, lr=3e-4, w_sd=1.0, w_sm=1.0, w_cos=0.1, max_input_depth=80.0,
+             pr=FP32, return_grads=False, trace=None):
+    """`image` is the raw [0,255] image; the network sees the ImageNet-normalised one, the smoothness loss the raw one.
+    Mutates `sd` (adapted tensors, BatchNorm1d running statistics of the heads) and `state`."""
+    names = list(state.m.keys())
+    v = O.validity_map(sparse_depth)
+    d_f, v_f = O.remove_outliers(sparse_depth, v)
+    work = dict(sd)
+    leaves = {}
+    for k in names:
+        leaves[k] = sd[k].detach().clone().requires_grad_(True)
+        work[k] = leaves[k]
+    out, emb, ref = model_forward(work, normalize_image(image), d_f, True, max_input_depth, pr, trace=trace)
+    loss, info = O.adapt_loss(image, out, d_f, v_f, emb, ref, w_sd, w_sm, w_cos, max_input_depth)
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(names, grads)}
+    O.adam_update(sd, grads, state, lr)
+    res = {'validity': v_f, 'sparse_depth': d_f, 'output_depth': out.detach(), 'loss': float(loss),
+           'loss_smooth': float(info['loss_smooth']), 'loss_sparse_depth': float(info['loss_sparse_depth']),
+           'loss_cos': float(info['loss_cos'])}
+    if return_grads:
+        res['grads'] = grads
+        res['emb'] = emb.detach()
+        res['ref'] = ref.detach()
+    return res
