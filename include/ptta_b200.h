@@ -127,6 +127,22 @@ int ptta_nlspn_propagate_backward(const float* grad_out, const float* offset, co
                                   float* grad_feat_init, float* grad_offset, float* grad_aff, float* scratch,
                                   int n, int h, int w, int prop_time, ptta_stream_t stream);
 
+/* ---- general-channel convolutions of the NLSPN network (tcgen05, csrc/conv_gen.cuh) ------------------------------
+ * external_src/NLSPN/src/model/nlspnmodel_adapt.py:384-448 (resnet34.layer1-4 = torchvision BasicBlock stacks, conv6,
+ * dec5..dec2 ConvTranspose2d with skip concat, id/gd/cf_dec1) and the data gradients autograd runs for them.
+ * kind: 0 Conv2d 3x3 s1 p1 | 1 Conv2d 3x3 s2 p1 | 2 ConvTranspose2d 3x3 s2 p1 op1 | 3 Conv2d 1x1 s2.
+ * role: 0 forward (x0 [n,h,w,cin0] (+ x1 [n,h,w,cin1], the second half of a channel concat) -> out), 1 data gradient
+ * (x0 = dL/d(layer output) -> out = dL/d(layer input) [n,h,w,cin0]; cin1 must be 0; has_short: kind 1 only, x1 = gradient
+ * of the block's 1x1/s2 shortcut output, its weight packed behind the 3x3 one).  h, w = LAYER INPUT size.  All maps NHWC
+ * bf16 with stored channel counts that are multiples of 64; weights are the reference's fp32 tensors (cin_w / cout_w real
+ * channels, zero-padded to the stored counts).  ident_from >= 0: output channels >= ident_from copy the same input channel
+ * (centre-tap identity; used to carry conv1_dep's 16 channels through the 48->48 meta conv, nlspnmodel_adapt.py:866-870). */
+long long ptta_convg_packed_elems(int kind, int role, int cin0, int cin1, int cout, int has_short);
+int ptta_convg_pack(int kind, int role, const float* weight, const float* weight_short, int cin_w, int cout_w,
+                    int cin0, int cin1, int cout, int has_short, int ident_from, void* packed_bf16, ptta_stream_t stream);
+int ptta_convg_run(int kind, int role, const void* x0_bf16, const void* x1_bf16, const void* packed_bf16, const float* bias,
+                   void* out_bf16, int n, int h, int w, int cin0, int cin1, int cout, int has_short, ptta_stream_t stream);
+
 /* ---- MSG-CHN ProxyTTA engine ------------------------------------------------------------------- */
 /* prepare_mode: the reference's string, e.g. "meta_selfsup_seq_2layers_ema" (network_exp_msg_chn_adapt.py:1022-1087) */
 int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepare_mode);

@@ -1,0 +1,145 @@
+"""General-channel tcgen05 convolution family (csrc/conv_gen.cuh) against PyTorch fp32 convolutions of the same bf16-rounded
+operands: every layer geometry of the NLSPN network (nlspnmodel_adapt.py:384-448) in the forward and data-gradient roles.
+Tolerance: the kernel accumulates in fp32 and stores bf16, so the only differences are summation order and the final
+rounding: |out - ref| <= 2^-8 |ref| + 2e-3 * rms(ref) element-wise, and <= 3e-3 norm-wise."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _seed(*a):
+    return sum((i + 1) * 7919 * (sum(map(ord, str(v))) % 1009) for i, v in enumerate(a)) & 0xffffff
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+def _rand_nhwc(g, n, h, w, c, dev):
+    x = torch.randn((n, h, w, c), generator=g, dtype=torch.float32).to(dev).to(torch.bfloat16)
+    return x
+
+
+def _nchw(x):
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def _check(out, ref_nchw, what):
+    ref = ref_nchw.permute(0, 2, 3, 1)
+    got = out.float()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    rms = float(ref.pow(2).mean().sqrt())
+    err = (got - ref).abs()
+    bound = ref.abs() * 2.0 ** -8 + 2e-3 * rms
+    bad = int((err > bound).sum())
+    nrel = float((got - ref).norm() / ref.norm())
+    assert bad == 0 and nrel < 3e-3, '%s: %d elements out of bound, norm-wise %.2e, max err %.3e (rms %.3e)' % (what, bad, nrel, float(err.max()), rms)
+
+
+def _layer(kind, wt, x, stride_pad=None):
+    if kind == 's1':
+        return F.conv2d(x, wt, None, 1, 1)
+    if kind == 's2':
+        return F.conv2d(x, wt, None, 2, 1)
+    if kind == 'p1s2':
+        return F.conv2d(x, wt, None, 2, 0)
+    return F.conv_transpose2d(x, wt, None, 2, 1, 1)
+
+
+FWD_CASES = [
+    # kind, (cin0, cin1), cout, n, h, w
+    ('s1', (64, 0), 64, 1, 24, 40),
+    ('s1', (64, 0), 64, 2, 17, 23),
+    ('s1', (128, 0), 128, 1, 16, 48),
+    ('s1', (64, 64), 64, 1, 20, 36),
+    ('s1', (512, 0), 512, 1, 6, 10),
+    ('s1', (256, 0), 256, 2, 8, 20),
+    ('s2', (64, 0), 128, 1, 32, 48),
+    ('s2', (256, 0), 512, 2, 12, 20),
+    ('p1s2', (64, 0), 128, 1, 32, 48),
+    ('p1s2', (128, 0), 256, 2, 10, 36),
+    ('t2', (512, 0), 256, 2, 3, 5),
+    ('t2', (256, 512), 128, 1, 6, 10),
+    ('t2', (64, 128), 64, 1, 24, 40),
+    ('s1', (64, 0), 64, 1, 1, 130),
+    ('s1', (64, 0), 64, 1, 40, 200),
+]
+
+
+@pytest.mark.parametrize('kind,cin,cout,n,h,w', FWD_CASES)
+def test_forward(kind, cin, cout, n, h, w):
+    from tta_depth_completion_b200.convg import ConvG, FWD
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = _dev()
+    g = torch.Generator().manual_seed(_seed(kind, cin, cout, n, h, w))
+    c = cin[0] + cin[1]
+    k = 1 if kind == 'p1s2' else 3
+    shape = (c, cout, 3, 3) if kind == 't2' else (cout, c, k, k)
+    wt = (torch.randn(shape, generator=g) * (2.0 / (c * k * k)) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev) * 0.1
+    x0 = _rand_nhwc(g, n, h, w, cin[0], dev)
+    x1 = _rand_nhwc(g, n, h, w, cin[1], dev) if cin[1] else None
+    op = ConvG(kind, FWD, wt, cin if cin[1] else cin[0], cout, bias=bias)
+    out = op(x0, x1)
+    xin = _nchw(x0) if x1 is None else torch.cat((_nchw(x0), _nchw(x1)), 1)
+    ref = _layer(kind, wt.to(torch.bfloat16).float(), xin) + bias.view(1, -1, 1, 1)
+    _check(out, ref, 'fwd %s %s->%d %dx%dx%d' % (kind, cin, cout, n, h, w))
+
+
+DGRAD_CASES = [
+    # kind, cin, cout, n, h, w (layer input size), with_short
+    ('s1', 64, 64, 1, 24, 40, False),
+    ('s1', 128, 64, 2, 17, 23, False),
+    ('s1', 512, 512, 1, 6, 10, False),
+    ('s2', 64, 128, 1, 32, 48, False),
+    ('s2', 64, 128, 2, 16, 40, True),
+    ('s2', 256, 512, 1, 12, 20, True),
+    ('s2', 512, 512, 1, 6, 10, False),
+    ('t2', 768, 128, 1, 6, 10, False),
+    ('t2', 192, 64, 1, 24, 40, False),
+    ('t2', 512, 256, 2, 3, 5, False),
+]
+
+
+@pytest.mark.parametrize('kind,cin,cout,n,h,w,short', DGRAD_CASES)
+def test_data_gradient(kind, cin, cout, n, h, w, short):
+    from tta_depth_completion_b200.convg import ConvG, DGRAD
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = _dev()
+    g = torch.Generator().manual_seed(_seed(kind, cin, cout, n, h, w, short))
+    shape = (cin, cout, 3, 3) if kind == 't2' else (cout, cin, 3, 3)
+    wt = (torch.randn(shape, generator=g) * (2.0 / (cin * 9)) ** 0.5).to(dev)
+    ws = (torch.randn((cout, cin, 1, 1), generator=g) * (2.0 / cin) ** 0.5).to(dev) if short else None
+    x = torch.zeros((n, cin, h, w), device=dev, requires_grad=True)
+    y = _layer(kind, wt.to(torch.bfloat16).float(), x)
+    gy = _rand_nhwc(g, n, y.shape[2], y.shape[3], cout, dev)
+    loss = (y * _nchw(gy)).sum()
+    gys = None
+    if short:
+        ys = _layer('p1s2', ws.to(torch.bfloat16).float(), x)
+        gys = _rand_nhwc(g, n, ys.shape[2], ys.shape[3], cout, dev)
+        loss = loss + (ys * _nchw(gys)).sum()
+    ref, = torch.autograd.grad(loss, x)
+    op = ConvG(kind, DGRAD, wt, cin, cout, weight_short=ws)
+    out = op(gy, gys, hw=(h, w))
+    _check(out, ref, 'dgrad %s %d->%d %dx%dx%d short=%s' % (kind, cin, cout, n, h, w, short))
+
+
+def test_meta_conv_carries_depth_channels():
+    """48->48 meta conv stored as 64->64: output channels 48..63 are bit-exact copies of input channels 48..63 (conv1_dep's
+    features), so the kernel writes fe1 = cat(fe1_rgb, fe1_dep) directly (nlspnmodel_adapt.py:866-870)."""
+    from tta_depth_completion_b200.convg import ConvG, FWD
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    wt = (torch.randn((48, 48, 3, 3), generator=g) * 0.05).to(dev)
+    bias = (torch.randn(48, generator=g) * 0.1).to(dev)
+    x = _rand_nhwc(g, 2, 19, 37, 64, dev)
+    op = ConvG('s1', FWD, wt, 64, 64, bias=bias, ident_from=48)
+    out = op(x)
+    assert torch.equal(out[..., 48:], x[..., 48:])
+    ref = F.conv2d(_nchw(x)[:, :48], wt.to(torch.bfloat16).float(), bias, 1, 1)
+    _check(out[..., :48], ref, 'meta conv 48->48')

@@ -1,4 +1,5 @@
-"""Builds libptta_b200.so in-tree with nvcc for sm_100a (no torch headers: the library is plain C ABI)."""
+"""Builds libptta_b200.so in-tree with nvcc for sm_100a (no torch headers: the library is plain C ABI).
+Every .cu under csrc/ is one translation unit, compiled to an object only when it or a header is newer, then linked."""
 import os
 import shutil
 import subprocess
@@ -7,22 +8,34 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libptta_b200.so')
-SOURCES = ['engine.cu']
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared']
+SOURCES = ['engine.cu', 'nlspn_net.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 
 
-def _newest_source_mtime():
+def _header_mtime():
     t = 0.0
     for root in (CSRC, os.path.join(os.path.dirname(PKG), 'include')):
         for f in os.listdir(root):
-            if f.endswith(('.cu', '.cuh', '.h')):
+            if f.endswith(('.cuh', '.h')):
                 t = max(t, os.path.getmtime(os.path.join(root, f)))
     return t
 
 
+def _obj(src):
+    return os.path.join(LIB_DIR, src[:-3] + '.o')
+
+
+def _stale(src, hdr_t):
+    o = _obj(src)
+    return not os.path.exists(o) or os.path.getmtime(o) < max(hdr_t, os.path.getmtime(os.path.join(CSRC, src)))
+
+
 def needs_build():
-    return not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < _newest_source_mtime()
+    hdr_t = _header_mtime()
+    if not os.path.exists(LIB_PATH):
+        return True
+    lib_t = os.path.getmtime(LIB_PATH)
+    return any(lib_t < max(hdr_t, os.path.getmtime(os.path.join(CSRC, s))) for s in SOURCES)
 
 
 def build_library(force=False, verbose=False):
@@ -33,12 +46,26 @@ def build_library(force=False, verbose=False):
     if not os.path.exists(nvcc):
         raise RuntimeError('nvcc not found: cannot build libptta_b200.so')
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    hdr_t = _header_mtime()
+    procs = []
+    for s in SOURCES:
+        if force or _stale(s, hdr_t):
+            cmd = [nvcc] + NVCC_FLAGS + ['-c', '-o', _obj(s), os.path.join(CSRC, s)]
+            if verbose:
+                print(' '.join(cmd))
+            procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError('nvcc failed:\n' + out)
+        if verbose and out.strip():
+            print(out)
+    cmd = [nvcc, '-shared', '-o', LIB_PATH] + [_obj(s) for s in SOURCES]
     if verbose:
         print(' '.join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+        raise RuntimeError('link failed:\n' + res.stdout + res.stderr)
     return LIB_PATH
 
 

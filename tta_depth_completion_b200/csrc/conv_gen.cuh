@@ -1,0 +1,454 @@
+// General-channel NHWC bf16 convolution family on the 5th-generation tensor cores, for the NLSPN network
+// (external_src/NLSPN/src/model/nlspnmodel_adapt.py:384-448: ResNet34 layers 64..512 channels, the transposed-conv decoder
+// with skip concatenation, the three full-resolution 128->64 heads) and every data gradient of those layers.
+//
+// One kernel, implicit GEMM:   out[pixel, n] = sum over K-items  A_src[pixel + (dy, dx), c0 .. c0+63] . Wpk[item][n][0..63]
+//   * M tile = 128 output positions = a th x tw patch (8x16, 4x32, 2x64 or 1x128) of ONE image, brought by ONE 5-D TMA box per
+//     K-item, {64 channels, tw, 1, th, 1}, SWIZZLE_128B, zero-filled outside the image (= the conv's padding).  The 5-D view
+//     {PX*C, W/PX, PY, H/PY, N} addresses plain maps (PX = PY = 1) and the pixel-parity view (PX = PY = 2) a stride-2 conv
+//     reads, so the stride costs nothing; the same view on the OUTPUT side places the four parity classes of a transposed
+//     conv (and of the data gradient of a stride-2 conv).
+//   * a K-item = (source tensor 0/1, channel offset, dx, dy, parity, 64-wide weight chunk): 3x3 / 1x1 taps, channel
+//     chunks, the two halves of a skip concatenation (two tensor maps -- no concat copy), and the 1x1/s2 shortcut of a
+//     ResNet down-sampling block folded into the data gradient of its 3x3/s2 conv are all just items.  The list sits in
+//     the kernel parameters (constant bank).
+//   * N tile = BN in {64, 128, 256} output channels; weights pre-packed [item][Cout][64] bf16 (pack_convg_kernel), one 3-D
+//     TMA box {64, BN, 1} per item.  tcgen05.mma M128 x BN x K16, 4 per item, fp32 accumulators in TMEM, 2 x 256 columns
+//     double buffered so the epilogue of tile t overlaps the MMAs of tile t+1.
+//   * epilogue (4 warps): tcgen05.ld -> + bias -> bf16 -> SWIZZLE_128B staging tile in shared memory -> one TMA store per 64
+//     channels (the store clips partial tiles, and addresses parity classes through the 5-D output view).
+// Roles: warp 0 TMA producer | warp 1 TMEM allocator + MMA issuer | warps 2-5 epilogue.  Persistent CTAs, one per SM.
+#pragma once
+#include <cuda.h>
+#include <vector>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace ptta {
+
+struct ConvGItem {
+    int c_inner;   // inner coordinate in the source view: px * C + channel offset
+    int dx;        // added to the tile's grid x
+    int dyps;      // dy (low 16 bits, signed) | py << 16 | src << 20
+    int wk;        // K-chunk index in the packed weights
+};
+
+struct ConvGParams {
+    ConvGItem items[128];
+    int cls_start[4], cls_count[4];
+    int cls_out_c[4];    // inner coordinate of the class in the output view (qx * Cout)
+    int cls_out_py[4];   // qy
+    int n_classes;
+    int N, tiles_y, tiles_x, n_tiles, BN;
+    int th, tw;
+    int total_tiles;
+    const float* bias;   // [Cout] or null
+};
+
+struct ConvGCfg {
+    static const int STAGES = 4;
+    static const int A_BYTES = 128 * 128;            // 128 positions x 64 channels bf16
+    static const int B_BYTES = 256 * 128;            // up to 256 output channels x 64
+    static const int STAGE_BYTES = A_BYTES + B_BYTES;
+    static const int OUT_BYTES = 128 * 128;          // one 64-channel output group
+    static const int SMEM = 1024 + STAGES * STAGE_BYTES + 2 * OUT_BYTES + 256;
+    static const int THREADS = 192;
+};
+
+namespace tc {
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+}  // namespace tc
+
+__global__ void __launch_bounds__(ConvGCfg::THREADS, 1)
+convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+             const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
+             const __grid_constant__ ConvGParams p) {
+    typedef ConvGCfg C;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t out_s = smem_base + C::STAGES * C::STAGE_BYTES;
+    const uint32_t bar_s = out_s + 2 * C::OUT_BYTES;
+    const uint32_t full = bar_s, empty = bar_s + 8 * C::STAGES, acc_full = bar_s + 16 * C::STAGES, acc_empty = acc_full + 16;
+    const uint32_t tmem_slot = acc_empty + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t stage_tx = C::A_BYTES + (uint32_t)p.BN * 128u;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_a0);
+        tc::prefetch_tmap(&tmap_a1);
+        tc::prefetch_tmap(&tmap_b);
+        tc::prefetch_tmap(&tmap_out);
+        for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(full + 8 * i, 1); tc::mbar_init(empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + 8 * i, 1); tc::mbar_init(acc_empty + 8 * i, 128); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int r = tile;
+                const int nt = r % p.n_tiles; r /= p.n_tiles;
+                const int tx = r % p.tiles_x; r /= p.tiles_x;
+                const int ty = r % p.tiles_y; r /= p.tiles_y;
+                const int n = r % p.N, cls = r / p.N;
+                const int gx0 = tx * p.tw, gy0 = ty * p.th;
+                const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
+                for (int i = 0; i < cnt; ++i, ++it) {
+                    const ConvGItem item = p.items[i0 + i];
+                    const uint32_t s = it % C::STAGES, par = (it / C::STAGES) & 1;
+                    tc::mbar_wait(empty + 8 * s, par ^ 1);
+                    tc::mbar_arrive_expect_tx(full + 8 * s, stage_tx);
+                    const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
+                    const int dy = (int)(short)(item.dyps & 0xffff), py = (item.dyps >> 16) & 3, src = (item.dyps >> 20) & 1;
+                    tc::tma_load_5d(a_dst, src ? &tmap_a1 : &tmap_a0, full + 8 * s, item.c_inner, gx0 + item.dx, py, gy0 + dy, n);
+                    tc::tma_load_3d(a_dst + C::A_BYTES, &tmap_b, full + 8 * s, 0, nt * p.BN, item.wk);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(128, p.BN);
+            const uint64_t d0 = make_desc_sw128(0);
+            const uint32_t hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
+            uint32_t it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+                const int cls = tile / (p.n_tiles * p.tiles_x * p.tiles_y * p.N);
+                const int cnt = p.cls_count[cls];
+                const uint32_t as = t & 1;
+                tc::mbar_wait(acc_empty + 8 * as, ((t >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                for (int i = 0; i < cnt; ++i, ++it) {
+                    const uint32_t s = it % C::STAGES;
+                    tc::mbar_wait(full + 8 * s, (it / C::STAGES) & 1);
+                    tc::tc_fence_after();
+                    const uint32_t a_lo = lo0 + ((smem_base + s * C::STAGE_BYTES) >> 4);
+                    const uint32_t b_lo = a_lo + (C::A_BYTES >> 4);
+                    if (i == 0) tc::umma_f16_split<false>(d_tmem, a_lo, hi, b_lo, hi, idesc);
+                    else tc::umma_f16_split<true>(d_tmem, a_lo, hi, b_lo, hi, idesc);
+#pragma unroll
+                    for (int k = 1; k < 4; ++k) tc::umma_f16_split<true>(d_tmem, a_lo + k * 2, hi, b_lo + k * 2, hi, idesc);
+                    tc::umma_commit(empty + 8 * s);
+                }
+                tc::umma_commit(acc_full + 8 * as);
+            }
+        }
+    } else {
+        const int q = warp & 3, et = (warp - 2) * 32 + lane;     // et: 0..127, thread 0 issues the stores
+        const int row = q * 32 + lane;                           // position inside the tile == TMEM lane
+        const int groups = p.BN >> 6;
+        uint32_t t = 0, sg = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+            int r = tile;
+            const int nt = r % p.n_tiles; r /= p.n_tiles;
+            const int tx = r % p.tiles_x; r /= p.tiles_x;
+            const int ty = r % p.tiles_y; r /= p.tiles_y;
+            const int n = r % p.N, cls = r / p.N;
+            const uint32_t as = t & 1;
+            tc::mbar_wait(acc_full + 8 * as, (t >> 1) & 1);
+            tc::tc_fence_after();
+            for (int g = 0; g < groups; ++g, ++sg) {
+                const uint32_t buf = out_s + (sg & 1) * C::OUT_BYTES;
+                if (et == 0) tc::bulk_wait_read<1>();            // the store that used this buffer two groups ago has read it
+                tc::epi_bar();
+                const int ch0 = nt * p.BN + g * 64;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + g * 64 + h * 32, v);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[c * 8 + j]) + (p.bias ? __ldg(p.bias + ch0 + h * 32 + c * 8 + j) : 0.f);
+                        uint4 ov;
+                        ov.x = pack_bf162(f[0], f[1]); ov.y = pack_bf162(f[2], f[3]);
+                        ov.z = pack_bf162(f[4], f[5]); ov.w = pack_bf162(f[6], f[7]);
+                        const int chunk = h * 4 + c;
+                        *reinterpret_cast<uint4*>(smem + (buf - smem_base) + row * 128 + ((chunk ^ (row & 7)) << 4)) = ov;
+                    }
+                }
+                tc::fence_proxy_async();
+                tc::epi_bar();
+                if (et == 0) {
+                    tc::tma_store_5d(&tmap_out, buf, p.cls_out_c[cls] + ch0, tx * p.tw, p.cls_out_py[cls], ty * p.th, n);
+                    tc::bulk_commit();
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(acc_empty + 8 * as);
+        }
+        if (et == 0) tc::bulk_wait_all();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---- weight packing: Wpk[wk][n][j] = W[n * sn + (k0 + j) * sk + tap] (0 outside the real extents) ---------------------------
+struct ConvGPackEntry { int wsel_tap; int k0; };      // wsel_tap = which weight tensor (bit 8) | tap index (low 8 bits)
+struct ConvGPackParams {
+    ConvGPackEntry e[128];
+    const float* w[2];
+    long long sn[2], sk[2];
+    int n_real[2], k_real[2];
+    int n_pad;            // rows per chunk in the packed buffer
+    int ident_from;       // >= 0: rows/cols [ident_from, n_pad) of the centre tap (tap 4) of tensor 0 form an identity
+};
+
+__global__ void __launch_bounds__(256) pack_convg_kernel(const __grid_constant__ ConvGPackParams p, bf16* __restrict__ out) {
+    const int wk = blockIdx.x;
+    const ConvGPackEntry e = p.e[wk];
+    const int sel = (e.wsel_tap >> 8) & 1, tap = e.wsel_tap & 255;
+    const float* w = p.w[sel];
+    for (int i = threadIdx.x; i < p.n_pad * 64; i += blockDim.x) {
+        const int n = i >> 6, j = i & 63, k = e.k0 + j;
+        float v = 0.f;
+        if (n < p.n_real[sel] && k < p.k_real[sel]) v = w[(long long)n * p.sn[sel] + (long long)k * p.sk[sel] + tap];
+        else if (p.ident_from >= 0 && sel == 0 && tap == 4 && n >= p.ident_from && n == k) v = 1.f;
+        out[((size_t)wk * p.n_pad + n) * 64 + j] = __float2bfloat16(v);
+    }
+}
+
+// ---- host side: plans ------------------------------------------------------------------------------------------------------
+enum { CONVG_S1 = 0, CONVG_S2 = 1, CONVG_T2 = 2, CONVG_P1S2 = 3 };
+
+struct ConvGPlan {
+    ConvGParams p;
+    ConvGPackEntry pack[128];
+    int n_items;          // == number of K-chunks in the packed weights
+    int in_parity;        // source view: 1 plain, 2 pixel-parity
+    int out_parity;       // output view
+    int k_src[2];         // stored channels of source 0 / 1 (0 = absent)
+    int n_out;            // stored output channels
+    int grid_h, grid_w;   // tile grid extents (output positions per class)
+    int in_h, in_w, out_h, out_w;
+};
+
+// kind/role/shapes -> item list.  h, w: spatial size of the LAYER's input (forward sense); cin0 + cin1 = layer input channels
+// (two sources only in the forward role), cout = layer output channels; all stored channel counts are multiples of 64.
+// has_short: role 1 of CONVG_S2 additionally folds the data gradient of a 1x1/s2 shortcut conv (second source = its dY).
+inline int convg_make_plan(ConvGPlan& pl, int kind, int role, int n, int h, int w, int cin0, int cin1, int cout, int has_short) {
+    PTTA_CHECK(kind >= 0 && kind <= 3 && (role == 0 || role == 1), "convg: bad kind %d / role %d", kind, role);
+    PTTA_CHECK(cin0 > 0 && cin0 % 64 == 0 && cin1 % 64 == 0 && cout > 0 && cout % 64 == 0, "convg: channels must be multiples of 64 (%d+%d -> %d)", cin0, cin1, cout);
+    PTTA_CHECK(role == 0 || cin1 == 0, "convg: two sources only in the forward role");
+    PTTA_CHECK(!has_short || (kind == CONVG_S2 && role == 1), "convg: shortcut folding only for the data gradient of a stride-2 conv");
+    PTTA_CHECK(kind == CONVG_S1 || kind == CONVG_T2 || (h % 2 == 0 && w % 2 == 0), "convg: stride-2 layers need even H, W (%d x %d)", h, w);
+    PTTA_CHECK(!(kind == CONVG_P1S2 && role == 1), "convg: the 1x1/s2 data gradient only exists folded into its block's 3x3/s2 one (has_short)");
+    memset(&pl, 0, sizeof(pl));
+    const int cin = cin0 + cin1;
+    // the GEMM's K sources and N extent
+    int ksrc[2] = {cin0, cin1}, nout = cout;
+    if (role == 1) { ksrc[0] = cout; ksrc[1] = has_short ? cout : 0; nout = cin; }
+    pl.k_src[0] = ksrc[0]; pl.k_src[1] = ksrc[1]; pl.n_out = nout;
+    // geometry family
+    //   gather-s1 : plain in, plain out, same grid                       (S1 fwd, S1 dgrad)
+    //   gather-s2 : parity in, plain out, grid = in/2                    (S2 fwd, P1S2 fwd, T2 dgrad)
+    //   scatter-s2: plain in, parity out (4 classes), grid = in          (T2 fwd, S2 dgrad [+ P1S2 dgrad])
+    int family;
+    if (kind == CONVG_S1) family = 0;
+    else if ((kind == CONVG_T2) == (role == 0)) family = 2;
+    else family = 1;
+    // spatial sizes of the GEMM's source / destination tensors
+    int lin_h = h, lin_w = w, lout_h, lout_w;              // layer input / output
+    if (kind == CONVG_S1) { lout_h = h; lout_w = w; }
+    else if (kind == CONVG_T2) { lout_h = 2 * h; lout_w = 2 * w; }
+    else { lout_h = h / 2; lout_w = w / 2; }
+    pl.in_h = role == 0 ? lin_h : lout_h; pl.in_w = role == 0 ? lin_w : lout_w;
+    pl.out_h = role == 0 ? lout_h : lin_h; pl.out_w = role == 0 ? lout_w : lin_w;
+    pl.in_parity = family == 1 ? 2 : 1;
+    pl.out_parity = family == 2 ? 2 : 1;
+    pl.grid_h = family == 1 ? pl.in_h / 2 : pl.in_h;
+    pl.grid_w = family == 1 ? pl.in_w / 2 : pl.in_w;
+    const int ntap = kind == CONVG_P1S2 ? 1 : 9;
+    int ni = 0;
+    auto add_item = [&](int src, int csrc_total, int c, int px, int dx, int py, int dy, int wsel, int tap, int k0) {
+        ConvGItem& it = pl.p.items[ni];
+        it.c_inner = px * csrc_total + c;
+        it.dx = dx;
+        it.dyps = (dy & 0xffff) | (py << 16) | (src << 20);
+        it.wk = ni;
+        pl.pack[ni].wsel_tap = (wsel << 8) | tap;
+        pl.pack[ni].k0 = k0;
+        ++ni;
+    };
+    // one tap of one source: all its 64-channel chunks
+    auto add_tap = [&](int src, int px, int dx, int py, int dy, int wsel, int tap, int kbase) -> int {
+        for (int c = 0; c < ksrc[src]; c += 64) {
+            if (ni >= 128) return 1;
+            add_item(src, ksrc[src], c, px, dx, py, dy, wsel, tap, kbase + c);
+        }
+        return 0;
+    };
+    int overflow = 0;
+    if (family == 0) {
+        pl.p.n_classes = 1;
+        pl.p.cls_start[0] = 0;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) {
+                const int dy = role == 0 ? ky - 1 : 1 - ky, dx = role == 0 ? kx - 1 : 1 - kx;
+                overflow |= add_tap(0, 0, dx, 0, dy, 0, ky * 3 + kx, 0);
+                if (ksrc[1]) overflow |= add_tap(1, 0, dx, 0, dy, 0, ky * 3 + kx, cin0);
+            }
+        pl.p.cls_count[0] = ni;
+    } else if (family == 1) {
+        pl.p.n_classes = 1;
+        pl.p.cls_start[0] = 0;
+        if (ntap == 1) {
+            overflow |= add_tap(0, 0, 0, 0, 0, 0, 0, 0);
+        } else {
+            // input row 2*oy + ky - 1:  ky 0 -> parity 1 of pair oy-1, ky 1 -> parity 0 of pair oy, ky 2 -> parity 1 of pair oy
+            const int par[3] = {1, 0, 1}, off[3] = {-1, 0, 0};
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx) {
+                    overflow |= add_tap(0, par[kx], off[kx], par[ky], off[ky], 0, ky * 3 + kx, 0);
+                    if (ksrc[1]) overflow |= add_tap(1, par[kx], off[kx], par[ky], off[ky], 0, ky * 3 + kx, cin0);
+                }
+        }
+        pl.p.cls_count[0] = ni;
+    } else {
+        // output position 2*g + q receives: q = 0: tap 1 from g;  q = 1: tap 0 from g+1 and tap 2 from g
+        pl.p.n_classes = 4;
+        for (int qy = 0; qy < 2; ++qy)
+            for (int qx = 0; qx < 2; ++qx) {
+                const int cls = qy * 2 + qx;
+                pl.p.cls_start[cls] = ni;
+                pl.p.cls_out_c[cls] = qx * nout;
+                pl.p.cls_out_py[cls] = qy;
+                const int nky = qy ? 2 : 1, nkx = qx ? 2 : 1;
+                const int kys[2] = {qy ? 0 : 1, 2}, dys[2] = {qy ? 1 : 0, 0};
+                const int kxs[2] = {qx ? 0 : 1, 2}, dxs[2] = {qx ? 1 : 0, 0};
+                for (int a = 0; a < nky; ++a)
+                    for (int b = 0; b < nkx; ++b) {
+                        overflow |= add_tap(0, 0, dxs[b], 0, dys[a], 0, kys[a] * 3 + kxs[b], 0);
+                        if (ksrc[1] && !has_short) overflow |= add_tap(1, 0, dxs[b], 0, dys[a], 0, kys[a] * 3 + kxs[b], cin0);
+                    }
+                if (has_short && cls == 0) overflow |= add_tap(1, 0, 0, 0, 0, 1, 0, 0);
+                pl.p.cls_count[cls] = ni - pl.p.cls_start[cls];
+            }
+    }
+    PTTA_CHECK(!overflow, "convg: more than 128 K-items (kind %d role %d, %d+%d -> %d)", kind, role, cin0, cin1, cout);
+    pl.n_items = ni;
+    // tiles
+    const int BN = nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : 64);
+    static const int shapes[4][2] = {{8, 16}, {4, 32}, {2, 64}, {1, 128}};
+    long long best = -1; int bi = 0;
+    for (int i = 0; i < 4; ++i) {
+        long long tiles = (long long)cdiv(pl.grid_h, shapes[i][0]) * cdiv(pl.grid_w, shapes[i][1]);
+        if (best < 0 || tiles < best) { best = tiles; bi = i; }
+    }
+    pl.p.th = shapes[bi][0]; pl.p.tw = shapes[bi][1];
+    pl.p.tiles_y = cdiv(pl.grid_h, pl.p.th); pl.p.tiles_x = cdiv(pl.grid_w, pl.p.tw);
+    pl.p.N = n; pl.p.BN = BN; pl.p.n_tiles = nout / BN;
+    pl.p.total_tiles = pl.p.n_classes * n * pl.p.tiles_y * pl.p.tiles_x * pl.p.n_tiles;
+    return 0;
+}
+
+// 5-D view {P*C, W/P, P, H/P, N} of an NHWC bf16 tensor, box {64, tw, 1, th, 1}, SWIZZLE_128B
+inline int make_tmap_view5(CUtensorMap* map, const void* ptr, int N, int H, int W, int Cc, int P, int th, int tw) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    PTTA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[5] = {(cuuint64_t)P * Cc, (cuuint64_t)(W / P), (cuuint64_t)P, (cuuint64_t)(H / P), (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)P * Cc * 2, (cuuint64_t)W * Cc * 2, (cuuint64_t)P * W * Cc * 2, (cuuint64_t)H * W * Cc * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)tw, 1, (cuuint32_t)th, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PTTA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(view5) failed with %d (N=%d H=%d W=%d C=%d P=%d box %dx%d)", (int)r, N, H, W, Cc, P, th, tw);
+    return 0;
+}
+
+// packed weights [chunks][n_pad][64] bf16, box {64, BN, 1}
+inline int make_tmap_wpk(CUtensorMap* map, const void* ptr, int chunks, int n_pad, int BN) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    PTTA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {64, (cuuint64_t)n_pad, (cuuint64_t)chunks};
+    cuuint64_t strides[2] = {128, (cuuint64_t)n_pad * 128};
+    cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PTTA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(wpk) failed with %d (chunks=%d n=%d BN=%d)", (int)r, chunks, n_pad, BN);
+    return 0;
+}
+
+inline long long convg_packed_elems(const ConvGPlan& pl) { return (long long)pl.n_items * pl.n_out * 64; }
+
+// w: the layer's weight (Conv2d [cout_w][cin_w][k][k] or ConvTranspose2d [cin_w][cout_w][3][3]); w_short: the 1x1 shortcut [cout_w][cin_w]
+inline int launch_convg_pack(const ConvGPlan& pl, int kind, int role, const float* w, const float* w_short, int cin_w, int cout_w,
+                             int ident_from, bf16* packed, cudaStream_t st) {
+    ConvGPackParams pp;
+    memset(&pp, 0, sizeof(pp));
+    memcpy(pp.e, pl.pack, sizeof(pp.e));
+    const int T = kind == CONVG_P1S2 ? 1 : 9;
+    pp.w[0] = w; pp.w[1] = w_short;
+    const bool conv_layout = kind != CONVG_T2;     // [cout][cin][T] vs [cin][cout][T]
+    if (role == 0) {          // n = cout, k = cin
+        pp.sn[0] = conv_layout ? (long long)cin_w * T : T;
+        pp.sk[0] = conv_layout ? T : (long long)cout_w * T;
+        pp.n_real[0] = cout_w; pp.k_real[0] = cin_w;
+    } else {                  // n = cin, k = cout
+        pp.sn[0] = conv_layout ? T : (long long)cout_w * T;
+        pp.sk[0] = conv_layout ? (long long)cin_w * T : T;
+        pp.n_real[0] = cin_w; pp.k_real[0] = cout_w;
+    }
+    // shortcut (role 1 only): Conv2d [cout][cin][1][1] -> n = cin, k = cout
+    pp.sn[1] = 1; pp.sk[1] = cin_w; pp.n_real[1] = cin_w; pp.k_real[1] = cout_w;
+    pp.n_pad = pl.n_out;
+    pp.ident_from = ident_from;
+    pack_convg_kernel<<<pl.n_items, 256, 0, st>>>(pp, packed);
+    return check_launch("pack_convg");
+}
+
+inline int launch_convg(const ConvGPlan& pl, const bf16* x0, const bf16* x1, const bf16* packed, const float* bias, bf16* out, cudaStream_t st) {
+    typedef ConvGCfg C;
+    static int sms = 0;
+    if (!sms) {
+        PTTA_CUDA(cudaFuncSetAttribute(convg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        int dev = 0;
+        PTTA_CUDA(cudaGetDevice(&dev));
+        PTTA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    PTTA_CHECK(x0 && packed && out && (x1 || !pl.k_src[1]), "convg: null operand");
+    CUtensorMap ta0, ta1, tb, to;
+    const ConvGParams& p = pl.p;
+    PTTA_TRY(make_tmap_view5(&ta0, x0, p.N, pl.in_h, pl.in_w, pl.k_src[0], pl.in_parity, p.th, p.tw));
+    if (pl.k_src[1]) PTTA_TRY(make_tmap_view5(&ta1, x1, p.N, pl.in_h, pl.in_w, pl.k_src[1], pl.in_parity, p.th, p.tw));
+    else ta1 = ta0;
+    PTTA_TRY(make_tmap_wpk(&tb, packed, pl.n_items, pl.n_out, p.BN));
+    PTTA_TRY(make_tmap_view5(&to, out, p.N, pl.out_h, pl.out_w, pl.n_out, pl.out_parity, p.th, p.tw));
+    ConvGParams pr = p;
+    pr.bias = bias;
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    convg_kernel<<<grid, C::THREADS, C::SMEM, st>>>(ta0, ta1, tb, to, pr);
+    return check_launch("convg");
+}
+
+}  // namespace ptta
