@@ -127,6 +127,19 @@ int ptta_nlspn_propagate_backward(const float* grad_out, const float* offset, co
                                   float* grad_feat_init, float* grad_offset, float* grad_aff, float* scratch,
                                   int n, int h, int w, int prop_time, ptta_stream_t stream);
 
+/* the three TTA losses as stand-alone calls (src/loss_utils.py:116-169,624-638; src/external_model_adapt.py:371-441, incl. the
+ * `loss_cos < 0.3 -> w_cos = 0` gate on the device).  emb / ref: bf16 [rows][dim].  The first five floats of `workspace` are
+ * (loss, loss_sparse_depth, loss_smooth, loss_cos, w_cos_eff) after forward.  backward: g_pred fp32 [n,h,w], g_ref bf16 [rows][dim]. */
+size_t ptta_tta_loss_workspace_bytes(int n, int h, int w, long long rows);
+int ptta_tta_loss_forward(const float* pred, const float* image_raw, const float* sparse_depth, const float* validity,
+                          float max_input_depth, const void* emb_bf16, const void* ref_bf16, long long rows, int dim,
+                          float w_sparse_depth, float w_smoothness, float w_cos, void* workspace, int n, int h, int w,
+                          ptta_stream_t stream);
+int ptta_tta_loss_backward(const float* pred, const float* image_raw, const float* sparse_depth, const float* validity,
+                           float max_input_depth, const void* emb_bf16, const void* ref_bf16, long long rows, int dim,
+                           float w_sparse_depth, float w_smoothness, void* workspace, float grad_scale, float* g_pred,
+                           void* g_ref_bf16, int n, int h, int w, ptta_stream_t stream);
+
 /* ---- general-channel convolutions of the NLSPN network (tcgen05, csrc/conv_gen.cuh) ------------------------------
  * external_src/NLSPN/src/model/nlspnmodel_adapt.py:384-448 (resnet34.layer1-4 = torchvision BasicBlock stacks, conv6,
  * dec5..dec2 ConvTranspose2d with skip concat, id/gd/cf_dec1) and the data gradients autograd runs for them.
@@ -142,6 +155,51 @@ int ptta_convg_pack(int kind, int role, const float* weight, const float* weight
                     int cin0, int cin1, int cout, int has_short, int ident_from, void* packed_bf16, ptta_stream_t stream);
 int ptta_convg_run(int kind, int role, const void* x0_bf16, const void* x1_bf16, const void* packed_bf16, const float* bias,
                    void* out_bf16, int n, int h, int w, int cin0, int cin1, int cout, int has_short, ptta_stream_t stream);
+
+/* thin heads id_dec0 / gd_dec0 / cf_dec0 (nlspnmodel_adapt.py:430-448, 883-895) as ONE 16-output-channel conv over the concat
+ * (x0 | x1): fp32 planar outputs through per-channel plane pointers (host arrays of n_real entries), activation per channel
+ * (0 none, 1 LeakyReLU(0.2), 2 sigmoid).  Weights packed by ptta_convg_pack(kind 0, role 0, ..., cout = 16). */
+int ptta_convg_run_thin(const void* x0_bf16, const void* x1_bf16, const void* packed_bf16, const float* bias, float* const* planes,
+                        const long long* image_strides, const int* acts, int n_real, int n, int h, int w, int cin0, int cin1,
+                        ptta_stream_t stream);
+
+/* ---- channel-generic kernels of the NLSPN network (csrc/nlspn_net.cuh); NHWC bf16 maps [rows][c], c % 64 == 0 ------------- */
+/* conv1_rgb + conv1_dep + LeakyReLU(0.2) (nlspnmodel_adapt.py:385-388, 866-867); image == NULL: the zero image of :907 */
+int ptta_nl_stem(const float* image_nchw, const float* depth, const float* w_rgb, const float* b_rgb, const float* w_dep,
+                 const float* b_dep, void* out_bf16_c64, int n, int h, int w, ptta_stream_t stream);
+/* number of partial blocks the reductions below use: `partial` must hold 2 * c * blocks floats */
+int ptta_nl_reduce_blocks(long long rows, int c);
+/* train-mode BatchNorm statistics (batch mean, biased variance) -> mean, rstd, scale = gamma*rstd, shift = beta - mean*scale;
+ * run_mean/run_var/num_batches_tracked (nullable): momentum update with the unbiased variance (BatchNorm1d of the heads) */
+int ptta_nl_bn_stats(const void* x_bf16, long long ldx, long long rows, int c, const float* gamma, const float* beta, float eps,
+                     float* partial, float* mean, float* rstd, float* scale, float* shift, float* run_mean, float* run_var,
+                     long long* num_batches_tracked, float momentum, ptta_stream_t stream);
+int ptta_nl_col_sums(const void* x_bf16, long long ldx, long long rows, int c, float* partial, float* sums, ptta_stream_t stream);
+/* y = act(x*scale + shift [+ res | + res*rscale + rshift]); act: 0 none, 1 ReLU, 2 LeakyReLU(0.2) */
+int ptta_nl_bn_act(const void* x_bf16, const float* scale, const float* shift, const void* res_bf16, long long ldr,
+                   const float* rscale, const float* rshift, void* y_bf16, long long rows, int c, int act, ptta_stream_t stream);
+/* g = (dy_a [+ dy_b]) * act'(y); dgamma = sum g*xhat, dbeta = sum g (nullable); dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat));
+ * gskip (nullable) receives g.  coef: 3*c floats of scratch. */
+int ptta_nl_bn_backward(const void* dy_a, long long ld_a, const void* dy_b, long long ld_b, const void* y_bf16, int act,
+                        const void* x_bf16, const float* mean, const float* rstd, const float* gamma, float* partial,
+                        float* dgamma, float* dbeta, float* coef, void* dx_bf16, void* gskip_bf16, long long rows, int c,
+                        ptta_stream_t stream);
+int ptta_nl_add3(const void* a, long long lda, const void* b, long long ldb, const void* c3, long long ldc, void* out, long long rows,
+                 int c, ptta_stream_t stream);
+/* output = clamp(y, min=0) (nlspnmodel_adapt.py:901) and its adjoint */
+int ptta_nl_clamp0(const float* y, float* out, long long n, ptta_stream_t stream);
+int ptta_nl_mask_pos(const float* g, const float* y, float* out, long long n, ptta_stream_t stream);
+/* gradients of (pred_init, guide[8], confidence) through LeakyReLU / identity / sigmoid -> NHWC bf16 [n,h,w,64] (ch >= 10 zero) */
+int ptta_nl_thin_grad_pack(const float* g_pred, const float* pred_init, const float* g_guide, const float* g_conf, const float* conf,
+                           void* out_bf16_c64, int n, int h, int w, ptta_stream_t stream);
+/* prop_layer.conv_offset_aff = Conv2d(8,24,3,1,1) in fp32 on planar maps (nlspnmodel_adapt.py:219-224,259); transposed != 0:
+ * the data gradient ([n,24,h,w] -> [n,8,h,w]) */
+int ptta_nl_conv8to24(const float* in, const float* weight, const float* bias, float* out, int n, int h, int w, int transposed,
+                      ptta_stream_t stream);
+/* weight gradient of the adapted Conv2d(48,48,3,1,1) meta layer (nlspnmodel_adapt.py:1370-1374) over 64-channel NHWC maps */
+size_t ptta_nl_wgrad48_workspace_bytes(void);
+int ptta_nl_wgrad48(const void* x_bf16_c64, const void* gout_bf16_c64, float* dw_48x48x3x3, void* workspace, int n, int h, int w,
+                    ptta_stream_t stream);
 
 /* ---- MSG-CHN ProxyTTA engine ------------------------------------------------------------------- */
 /* prepare_mode: the reference's string, e.g. "meta_selfsup_seq_2layers_ema" (network_exp_msg_chn_adapt.py:1022-1087) */

@@ -43,6 +43,11 @@ struct ConvGParams {
     int th, tw;
     int total_tiles;
     const float* bias;   // [Cout] or null
+    // thin epilogue (BN == 16): fp32 planar outputs, one plane pointer per channel (image 0), activation per channel
+    int thin, thin_n, H, W;
+    float* thin_ptr[16];
+    long long thin_ns[16];   // elements between consecutive images of that plane
+    int thin_act[16];        // 0 none, 1 LeakyReLU(0.2), 2 sigmoid
 };
 
 struct ConvGCfg {
@@ -160,7 +165,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     } else {
         const int q = warp & 3, et = (warp - 2) * 32 + lane;     // et: 0..127, thread 0 issues the stores
         const int row = q * 32 + lane;                           // position inside the tile == TMEM lane
-        const int groups = p.BN >> 6;
+        const int groups = p.BN >> 6;      // 0 in thin mode
         uint32_t t = 0, sg = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
             int r = tile;
@@ -171,6 +176,23 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
             const uint32_t as = t & 1;
             tc::mbar_wait(acc_full + 8 * as, (t >> 1) & 1);
             tc::tc_fence_after();
+            if (p.thin) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256, v);
+                const int gy = ty * p.th + row / p.tw, gx = tx * p.tw + row % p.tw;
+                if (gy < p.H && gx < p.W) {
+                    const long long pix = (long long)gy * p.W + gx;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        if (c < p.thin_n) {
+                            float f = __uint_as_float(v[c]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+                            const int a = p.thin_act[c];
+                            f = a == 1 ? (f > 0.f ? f : 0.2f * f) : (a == 2 ? 1.f / (1.f + __expf(-f)) : f);
+                            p.thin_ptr[c][(long long)n * p.thin_ns[c] + pix] = f;
+                        }
+                    }
+                }
+            }
             for (int g = 0; g < groups; ++g, ++sg) {
                 const uint32_t buf = out_s + (sg & 1) * C::OUT_BYTES;
                 if (et == 0) tc::bulk_wait_read<1>();            // the store that used this buffer two groups ago has read it
@@ -257,7 +279,8 @@ struct ConvGPlan {
 // has_short: role 1 of CONVG_S2 additionally folds the data gradient of a 1x1/s2 shortcut conv (second source = its dY).
 inline int convg_make_plan(ConvGPlan& pl, int kind, int role, int n, int h, int w, int cin0, int cin1, int cout, int has_short) {
     PTTA_CHECK(kind >= 0 && kind <= 3 && (role == 0 || role == 1), "convg: bad kind %d / role %d", kind, role);
-    PTTA_CHECK(cin0 > 0 && cin0 % 64 == 0 && cin1 % 64 == 0 && cout > 0 && cout % 64 == 0, "convg: channels must be multiples of 64 (%d+%d -> %d)", cin0, cin1, cout);
+    const bool thin = cout == 16 && kind == CONVG_S1 && role == 0;      // thin head: 16 output channels, fp32 planar epilogue
+    PTTA_CHECK(cin0 > 0 && cin0 % 64 == 0 && cin1 % 64 == 0 && cout > 0 && (cout % 64 == 0 || thin), "convg: channels must be multiples of 64 (%d+%d -> %d)", cin0, cin1, cout);
     PTTA_CHECK(role == 0 || cin1 == 0, "convg: two sources only in the forward role");
     PTTA_CHECK(!has_short || (kind == CONVG_S2 && role == 1), "convg: shortcut folding only for the data gradient of a stride-2 conv");
     PTTA_CHECK(kind == CONVG_S1 || kind == CONVG_T2 || (h % 2 == 0 && w % 2 == 0), "convg: stride-2 layers need even H, W (%d x %d)", h, w);
@@ -357,7 +380,9 @@ inline int convg_make_plan(ConvGPlan& pl, int kind, int role, int n, int h, int 
     PTTA_CHECK(!overflow, "convg: more than 128 K-items (kind %d role %d, %d+%d -> %d)", kind, role, cin0, cin1, cout);
     pl.n_items = ni;
     // tiles
-    const int BN = nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : 64);
+    int BN = 16;                       // largest multiple of 64 that is <= 256 and divides the output channels
+    if (!thin) for (BN = 256; nout % BN; BN -= 64) {}
+    pl.p.thin = thin ? 1 : 0;
     static const int shapes[4][2] = {{8, 16}, {4, 32}, {2, 64}, {1, 128}};
     long long best = -1; int bi = 0;
     for (int i = 0; i < 4; ++i) {
@@ -436,16 +461,18 @@ inline int launch_convg(const ConvGPlan& pl, const bf16* x0, const bf16* x1, con
         PTTA_CUDA(cudaGetDevice(&dev));
         PTTA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    PTTA_CHECK(x0 && packed && out && (x1 || !pl.k_src[1]), "convg: null operand");
+    PTTA_CHECK(x0 && packed && (out || pl.p.thin) && (x1 || !pl.k_src[1]), "convg: null operand");
     CUtensorMap ta0, ta1, tb, to;
     const ConvGParams& p = pl.p;
     PTTA_TRY(make_tmap_view5(&ta0, x0, p.N, pl.in_h, pl.in_w, pl.k_src[0], pl.in_parity, p.th, p.tw));
     if (pl.k_src[1]) PTTA_TRY(make_tmap_view5(&ta1, x1, p.N, pl.in_h, pl.in_w, pl.k_src[1], pl.in_parity, p.th, p.tw));
     else ta1 = ta0;
     PTTA_TRY(make_tmap_wpk(&tb, packed, pl.n_items, pl.n_out, p.BN));
-    PTTA_TRY(make_tmap_view5(&to, out, p.N, pl.out_h, pl.out_w, pl.n_out, pl.out_parity, p.th, p.tw));
+    if (p.thin) to = ta0;
+    else PTTA_TRY(make_tmap_view5(&to, out, p.N, pl.out_h, pl.out_w, pl.n_out, pl.out_parity, p.th, p.tw));
     ConvGParams pr = p;
     pr.bias = bias;
+    pr.H = pl.out_h; pr.W = pl.out_w;
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     convg_kernel<<<grid, C::THREADS, C::SMEM, st>>>(ta0, ta1, tb, to, pr);
     return check_launch("convg");

@@ -1204,6 +1204,56 @@ __global__ void adam_flat_kernel(float* p, const float* g, float* m, float* v, l
         p[i] = pp; m[i] = mm; v[i] = vv;
     }
 }
+// ---- stand-alone fused TTA loss (used by the NLSPN back-end, whose graph is driven from Python) -------------------------------------
+struct TtaLossLayout { size_t scalars, map_partial, cos_partial, rowstat, total; int map_blocks, cos_blocks; };
+static TtaLossLayout tta_loss_layout(int n, int h, int w, long long rows) {
+    TtaLossLayout L;
+    L.map_blocks = std::min(cdiv((long long)h * w, LOSS_BLOCK * 4), 256);
+    L.cos_blocks = (int)std::min<long long>(std::max<long long>(cdiv(rows, 8), 1), 1184);
+    size_t o = 0;
+    L.scalars = o; o += 512;
+    L.map_partial = o; o += (size_t)n * L.map_blocks * 4 * sizeof(double);
+    L.cos_partial = o; o += (size_t)L.cos_blocks * sizeof(double);
+    L.rowstat = o; o += (size_t)rows * 3 * sizeof(float);
+    L.total = (o + 255) / 256 * 256;
+    return L;
+}
+size_t ptta_tta_loss_workspace_bytes(int n, int h, int w, long long rows) { return tta_loss_layout(n, h, w, rows).total; }
+
+int ptta_tta_loss_forward(const float* pred, const float* image_raw, const float* sparse, const float* validity, float cap, const void* emb,
+                          const void* ref, long long rows, int dim, float w_sd, float w_sm, float w_cos, void* workspace, int n, int h, int w,
+                          ptta_stream_t stream) {
+    PTTA_CHECK(pred && image_raw && sparse && validity && emb && ref && workspace, "tta_loss_forward: null pointer");
+    PTTA_CHECK(n <= 64 && dim % 256 == 0, "tta_loss_forward: batch %d > 64 or row length %d not a multiple of 256", n, dim);
+    const TtaLossLayout L = tta_loss_layout(n, h, w, rows);
+    char* ws = (char*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(L.map_blocks, n);
+    loss_map_reduce_kernel<<<grid, LOSS_BLOCK, 0, st>>>(pred, sparse, validity, image_raw, (double*)(ws + L.map_partial), h, w, cap, cap > 0.f ? 1 : 0);
+    PTTA_TRY(check_launch("loss_map_reduce"));
+    loss_cos_rows_kernel<<<L.cos_blocks, 256, 0, st>>>((const bf16*)emb, (const bf16*)ref, (float*)(ws + L.rowstat), (double*)(ws + L.cos_partial), rows, dim);
+    PTTA_TRY(check_launch("loss_cos_rows"));
+    loss_finalize_kernel<<<1, 256, 0, st>>>((const double*)(ws + L.map_partial), L.map_blocks, (const double*)(ws + L.cos_partial), L.cos_blocks, n, h, w,
+                                          rows, w_sd, w_sm, w_cos, 0.3f, (LossScalars*)(ws + L.scalars));
+    return check_launch("loss_finalize");
+}
+
+int ptta_tta_loss_backward(const float* pred, const float* image_raw, const float* sparse, const float* validity, float cap, const void* emb,
+                           const void* ref, long long rows, int dim, float w_sd, float w_sm, void* workspace, float gscale, float* g_pred,
+                           void* g_ref, int n, int h, int w, ptta_stream_t stream) {
+    PTTA_CHECK(pred && image_raw && sparse && validity && emb && ref && workspace && g_pred && g_ref, "tta_loss_backward: null pointer");
+    const TtaLossLayout L = tta_loss_layout(n, h, w, rows);
+    char* ws = (char*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long tot = (long long)n * h * w;
+    loss_map_grad_kernel<<<cdiv(tot, 256), 256, 0, st>>>(pred, sparse, validity, image_raw, g_pred, (const LossScalars*)(ws + L.scalars), n, h, w, cap,
+                                                       cap > 0.f ? 1 : 0, w_sd, w_sm, gscale);
+    PTTA_TRY(check_launch("loss_map_grad"));
+    loss_cos_grad_kernel<<<L.cos_blocks, 256, 0, st>>>((const bf16*)emb, (const bf16*)ref, (const float*)(ws + L.rowstat),
+                                                      (const LossScalars*)(ws + L.scalars), (bf16*)g_ref, rows, dim, gscale);
+    return check_launch("loss_cos_grad");
+}
+
 int ptta_adam_flat(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps, double wd, int step,
                    ptta_stream_t stream) {
     PTTA_CHECK(step >= 1, "adam: step must be >= 1");

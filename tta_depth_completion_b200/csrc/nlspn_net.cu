@@ -4,6 +4,7 @@
 #include <string.h>
 #include "common.cuh"
 #include "conv_gen.cuh"
+#include "nlspn_net.cuh"
 #include "../../include/ptta_b200.h"
 
 using namespace ptta;
@@ -30,6 +31,143 @@ int ptta_convg_run(int kind, int role, const void* x0, const void* x1, const voi
     ConvGPlan pl;
     PTTA_TRY(convg_make_plan(pl, kind, role, n, h, w, cin0, cin1, cout, has_short));
     return launch_convg(pl, (const bf16*)x0, (const bf16*)x1, (const bf16*)packed, bias, (bf16*)out, (cudaStream_t)stream);
+}
+
+int ptta_convg_run_thin(const void* x0, const void* x1, const void* packed, const float* bias, float* const* planes, const long long* nstrides,
+                        const int* acts, int n_real, int n, int h, int w, int cin0, int cin1, ptta_stream_t stream) {
+    ConvGPlan pl;
+    PTTA_TRY(convg_make_plan(pl, CONVG_S1, 0, n, h, w, cin0, cin1, 16, 0));
+    PTTA_CHECK(n_real >= 1 && n_real <= 16 && planes && nstrides && acts, "convg_run_thin: bad arguments");
+    pl.p.thin_n = n_real;
+    for (int c = 0; c < n_real; ++c) { pl.p.thin_ptr[c] = planes[c]; pl.p.thin_ns[c] = nstrides[c]; pl.p.thin_act[c] = acts[c]; }
+    return launch_convg(pl, (const bf16*)x0, (const bf16*)x1, (const bf16*)packed, bias, nullptr, (cudaStream_t)stream);
+}
+
+int ptta_nl_stem(const float* image, const float* depth, const float* w_rgb, const float* b_rgb, const float* w_dep, const float* b_dep,
+                 void* out, int n, int h, int w, ptta_stream_t stream) {
+    PTTA_CHECK(depth && w_rgb && b_rgb && w_dep && b_dep && out, "nl_stem: null pointer");
+    const long long total = (long long)n * h * w;
+    nl_stem_kernel<<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(image, depth, w_rgb, b_rgb, w_dep, b_dep, (bf16*)out, n, h, w);
+    return check_launch("nl_stem");
+}
+
+int ptta_nl_reduce_blocks(long long rows, int c) {
+    long long by_rows = (rows + 31) / 32;
+    long long target = 592 / (c / 64 > 0 ? c / 64 : 1);
+    if (target < 1) target = 1;
+    long long b = by_rows < target ? by_rows : target;
+    return (int)(b < 1 ? 1 : b);
+}
+
+int ptta_nl_bn_stats(const void* x, long long ldx, long long rows, int c, const float* gamma, const float* beta, float eps, float* partial,
+                     float* mean, float* rstd, float* scale, float* shift, float* run_mean, float* run_var, long long* num_batches_tracked,
+                     float momentum, ptta_stream_t stream) {
+    PTTA_CHECK(x && gamma && beta && partial && mean && rstd && scale && shift && c % 64 == 0 && rows > 0, "nl_bn_stats: bad arguments");
+    const int nblk = ptta_nl_reduce_blocks(rows, c);
+    dim3 grid(nblk, c / 64);
+    chan_reduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, rows, c, partial);
+    PTTA_TRY(check_launch("nl_chan_stats"));
+    bn_finalize2_kernel<<<cdiv(c, 128), 128, 0, (cudaStream_t)stream>>>(partial, nblk, rows, c, gamma, beta, eps, mean, rstd, scale, shift, run_mean,
+                                                                       run_var, num_batches_tracked, momentum, nullptr);
+    return check_launch("nl_bn_finalize");
+}
+
+int ptta_nl_col_sums(const void* x, long long ldx, long long rows, int c, float* partial, float* sums, ptta_stream_t stream) {
+    PTTA_CHECK(x && partial && sums && c % 64 == 0 && rows > 0, "nl_col_sums: bad arguments");
+    const int nblk = ptta_nl_reduce_blocks(rows, c);
+    dim3 grid(nblk, c / 64);
+    chan_reduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, rows, c, partial);
+    PTTA_TRY(check_launch("nl_chan_stats"));
+    bn_finalize2_kernel<<<cdiv(c, 128), 128, 0, (cudaStream_t)stream>>>(partial, nblk, rows, c, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr,
+                                                                       nullptr, nullptr, nullptr, 0.f, sums);
+    return check_launch("nl_col_sums");
+}
+
+int ptta_nl_bn_act(const void* x, const float* scale, const float* shift, const void* res, long long ldr, const float* rscale,
+                   const float* rshift, void* y, long long rows, int c, int act, ptta_stream_t stream) {
+    PTTA_CHECK(x && scale && shift && y && c % 64 == 0 && rows > 0 && (!rscale || (res && rshift)), "nl_bn_act: bad arguments");
+    const long long total = rows * (c / 8);
+    bn_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, scale, shift, (const bf16*)res, ldr, rscale, rshift, (bf16*)y,
+                                                                     rows, c, act);
+    return check_launch("nl_bn_act");
+}
+
+int ptta_nl_bn_backward(const void* dy_a, long long ld_a, const void* dy_b, long long ld_b, const void* y, int act, const void* x,
+                        const float* mean, const float* rstd, const float* gamma, float* partial, float* dgamma, float* dbeta, float* coef,
+                        void* dx, void* gskip, long long rows, int c, ptta_stream_t stream) {
+    PTTA_CHECK(dy_a && x && mean && rstd && gamma && partial && coef && dx && c % 64 == 0 && rows > 0 && (!act || y), "nl_bn_backward: bad arguments");
+    const int nblk = ptta_nl_reduce_blocks(rows, c);
+    dim3 grid(nblk, c / 64);
+    cudaStream_t st = (cudaStream_t)stream;
+    chan_reduce_kernel<1><<<grid, 256, 0, st>>>((const bf16*)x, c, (const bf16*)dy_a, ld_a, (const bf16*)dy_b, ld_b, (const bf16*)y, act, mean, rstd,
+                                               rows, c, partial);
+    PTTA_TRY(check_launch("nl_bn_bwd_reduce"));
+    bn_bwd_finalize2_kernel<<<cdiv(c, 128), 128, 0, st>>>(partial, nblk, rows, c, gamma, rstd, dgamma, dbeta, coef, coef + c, coef + 2 * c);
+    PTTA_TRY(check_launch("nl_bn_bwd_finalize"));
+    const long long total = rows * (c / 8);
+    bn_bwd_apply2_kernel<<<cdiv(total, 256), 256, 0, st>>>((const bf16*)dy_a, ld_a, (const bf16*)dy_b, ld_b, (const bf16*)y, act, (const bf16*)x, mean,
+                                                          rstd, coef, coef + c, coef + 2 * c, (bf16*)dx, (bf16*)gskip, rows, c);
+    return check_launch("nl_bn_bwd_apply");
+}
+
+int ptta_nl_add3(const void* a, long long lda, const void* b, long long ldb, const void* c3, long long ldc, void* out, long long rows, int c,
+                 ptta_stream_t stream) {
+    PTTA_CHECK(a && b && out && c % 64 == 0 && rows > 0, "nl_add3: bad arguments");
+    const long long total = rows * (c / 8);
+    add3_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)b, ldb, (const bf16*)c3, ldc, (bf16*)out, rows, c);
+    return check_launch("nl_add3");
+}
+
+int ptta_nl_clamp0(const float* y, float* out, long long n, ptta_stream_t stream) {
+    clamp0_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(y, out, n);
+    return check_launch("nl_clamp0");
+}
+
+int ptta_nl_mask_pos(const float* g, const float* y, float* out, long long n, ptta_stream_t stream) {
+    mask_pos_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(g, y, out, n);
+    return check_launch("nl_mask_pos");
+}
+
+int ptta_nl_thin_grad_pack(const float* g_pred, const float* pred_init, const float* g_guide, const float* g_conf, const float* conf, void* out,
+                           int n, int h, int w, ptta_stream_t stream) {
+    PTTA_CHECK(g_pred && pred_init && g_guide && g_conf && conf && out, "nl_thin_grad_pack: null pointer");
+    const long long hw = (long long)h * w;
+    thin_grad_pack_kernel<<<cdiv(n * hw, 256), 256, 0, (cudaStream_t)stream>>>(g_pred, pred_init, g_guide, g_conf, conf, (bf16*)out, n, hw);
+    return check_launch("nl_thin_grad_pack");
+}
+
+int ptta_nl_conv8to24(const float* in, const float* weight, const float* bias, float* out, int n, int h, int w, int transposed, ptta_stream_t stream) {
+    PTTA_CHECK(in && weight && out, "nl_conv8to24: null pointer");
+    const long long total = (long long)n * h * w;
+    if (transposed) conv8to24_kernel<true><<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(in, weight, nullptr, out, n, h, w);
+    else conv8to24_kernel<false><<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(in, weight, bias, out, n, h, w);
+    return check_launch("nl_conv8to24");
+}
+
+static int wgrad48_grid() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    return sms;
+}
+
+size_t ptta_nl_wgrad48_workspace_bytes(void) { return (size_t)wgrad48_grid() * 9 * 48 * 48 * sizeof(float); }
+
+int ptta_nl_wgrad48(const void* x, const void* gout, float* dw, void* workspace, int n, int h, int w, ptta_stream_t stream) {
+    PTTA_CHECK(x && gout && dw && workspace, "nl_wgrad48: null pointer");
+    static bool attr = false;
+    if (!attr) {
+        PTTA_CUDA(cudaFuncSetAttribute(wgrad48_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Wgrad48Cfg::SMEM));
+        attr = true;
+    }
+    const int tiles = n * cdiv(h, 16) * cdiv(w, 16);
+    const int grid = tiles < wgrad48_grid() ? tiles : wgrad48_grid();
+    wgrad48_kernel<<<grid, Wgrad48Cfg::THREADS, Wgrad48Cfg::SMEM, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gout, (float*)workspace, n, h, w);
+    PTTA_TRY(check_launch("nl_wgrad48"));
+    wgrad48_reduce_kernel<<<cdiv(9 * 48 * 48, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dw, grid);
+    return check_launch("nl_wgrad48_reduce");
 }
 
 }  // extern "C"
