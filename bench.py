@@ -34,7 +34,10 @@ WORKLOADS = {
     # name: (H, W, dataset, prepare_mode, lr, max_input_depth)
     'kitti': (352, 1216, 'kitti', 'meta_selfsup_seq_2layers_ema', 1e-4, 80.0),
     'void': (480, 640, 'void', 'meta_selfsup_seq_1layer_ema', 3e-3, 8.0),
+    # BASELINE.json configs[3]: NLSPN back-end (ResNet34 encoder/decoder + 18-step non-local propagation), adapt_mode meta_bn
+    'nlspn': (352, 1216, 'kitti', 'meta_selfsup_seq_1layer_ema', 3e-4, 80.0),
 }
+NLSPN_GFLOP_STEP = 3445.9        # forward 2 227.0 + required dgrad 1 201.1 + wgrad 17.8 at 1x352x1216
 W_SD, W_SM, W_COS = 1.0, 1.0, 0.1
 RING = 8                      # distinct frames cycled through (device-resident for `value`, pinned host for `e2e`)
 CONV_GFLOP_R1 = 2 * 9 * 32 * 32 * 352 * 1216 / 1e9      # 32->32 3x3 s1 @352x1216: SURVEY.md section 8(d) / Appendix A
@@ -99,11 +102,46 @@ def make_checkpoint(workload):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def nlspn_cpu_sample(args, steps, warmup):
+    """NLSPN oracle port on the host cores.  A full 352x1216 step needs ~25 GB of fp32 activations and minutes on CPU, so the
+    bounded sample is a HALF-resolution frame (176x608, 1/4 of the pixels; every layer's work scales with the pixel count) and
+    the throughput is scaled by 1/4."""
+    from oracle import msgchn_oracle as O
+    from oracle import nlspn_oracle as NO
+    h, w, dataset, mode, lr, cap = WORKLOADS['nlspn']
+    hs, ws = h // 2, w // 2
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = NO.make_synthetic_checkpoint(0)
+    names = NO.adapt_parameter_names(sd, 'meta_bn')
+    state = O.AdamState(names, sd)
+    frames = [NO.synthetic_frame(1, t, args.batch, hs, ws, dataset)[:2] for t in range(2)]
+    for i in range(warmup):
+        NO.tta_step(sd, state, *frames[i % 2], lr=lr, w_sd=W_SD, w_sm=W_SM, w_cos=W_COS, max_input_depth=cap)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        NO.tta_step(sd, state, *frames[i % 2], lr=lr, w_sd=W_SD, w_sm=W_SM, w_cos=W_COS, max_input_depth=cap)
+    dt = time.perf_counter() - t0
+    value = 0.25 * args.batch * steps / dt
+    return value, dt, {'value': value, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                       'sample': '%d TTA step(s) of oracle/nlspn_oracle.py (torch %s CPU fp32) on %dx3x%dx%d frames = 1/4 of the pixels of the '
+                                 '352x1216 workload, %.1f s/step, throughput scaled by 1/4' % (steps, torch.__version__, args.batch, hs, ws, dt / steps)}
+
+
 def run_reference(args):
     """CPU arm: the oracle port of the reference step on all host cores."""
     from oracle import msgchn_oracle as O
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
+        return
+    if args.workload == 'nlspn':
+        steps = min(args.steps, 3)
+        value, dt, cb = nlspn_cpu_sample(args, steps, min(args.warmup, 1))
+        print(json.dumps({'impl': 'reference', 'metric': 'adapted_frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus,
+                          'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * 4.0 * dt / steps, 'higher_is_better': True,
+                          'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args),
+                          'cpu_baseline': cb, 'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}),
+              flush=True)
         return
     h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
@@ -134,6 +172,12 @@ def run_reference(args):
 
 def workload_config(args):
     h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
+    if args.workload == 'nlspn':
+        return {'workload': 'NLSPN ProxyTTA continual adaptation (ResNet34 encoder/decoder, 18-step non-local propagation), synthetic KITTI-shape '
+                            '%dx3x%dx%d frames, prepare_mode %s, adapt_mode meta_bn (88 tensors), lr %g, w_sd/w_smooth/w_cos %g/%g/%g, '
+                            'Adam(0.9,0.999,1e-8)' % (args.batch, h, w, mode, lr, W_SD, W_SM, W_COS),
+                'batch_per_gpu': args.batch, 'parallelism': 'independent sequence shard per GPU (no collective)',
+                'l2': 'ring of %d distinct frames; per-step working set (~7 GB of activations) exceeds the 126 MB L2' % RING}
     return {'workload': 'MSG-CHN ProxyTTA continual adaptation, synthetic %s-shape %dx3x%dx%d frames, prepare_mode %s, adapt_mode meta, '
                         'lr %g, w_sd/w_smooth/w_cos %g/%g/%g, Adam(0.9,0.999,1e-8)' % (dataset.upper(), args.batch, h, w, mode, lr, W_SD, W_SM,
                                                                                        W_COS),
@@ -211,7 +255,136 @@ def time_dominant_kernel(dev, peaks, iters=40):
             'peak_source': peaks['source'] + ', burst figures (kernel timed alone, 40 launches replayed from a CUDA graph)'}
 
 
+def time_convg_kernel(dev, peaks, iters=24):
+    """dominant kernel of the NLSPN step: the 64->64 3x3 stride-1 conv of resnet34.layer1 at full resolution (12 forward + 12
+    data-gradient launches per step) on the general-channel tcgen05 kernel, timed alone with CUDA events over a ring of 6 inputs
+    (6 x 55 MB > L2).  31.6 GFLOP per 110 MB = 288 FLOP/B is above the ridge, so it is reported against the bf16 tensor peak."""
+    from tta_depth_completion_b200.convg import ConvG, FWD
+    h, w = 352, 1216
+    g = torch.Generator().manual_seed(0)
+    wt = (torch.randn((64, 64, 3, 3), generator=g) * (2.0 / 576) ** 0.5).to(dev)
+    op = ConvG('s1', FWD, wt, 64, 64)
+    xs = [torch.randn((1, h, w, 64), device=dev).to(torch.bfloat16) for _ in range(6)]
+    outs = [torch.empty((1, h, w, 64), dtype=torch.bfloat16, device=dev) for _ in range(6)]
+    for i in range(3):
+        op(xs[i], out=outs[i])
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        op(xs[i % 6], out=outs[i % 6])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    gflop = 2 * 9 * 64 * 64 * h * w / 1e9
+    alg_bytes = 2 * h * w * 64 * 2 + 9 * 64 * 64 * 2
+    tflops = gflop / ms
+    return {'kernel': 'convg_kernel: 3x3 64->64 s1 @352x1216 (NHWC bf16, tcgen05 + TMEM, TMA loads and stores, fp32 accumulate)',
+            'bound': 'tensor', 'achieved': tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': tflops / peaks['bf16_tflops'],
+            'traffic': None, 'us_per_launch': 1e3 * ms, 'gflop_per_launch': gflop, 'algorithmic_bytes_per_launch': alg_bytes,
+            'hbm_gbs_achieved': alg_bytes / ms / 1e6, 'flop_per_byte': gflop * 1e9 / alg_bytes,
+            'peak_source': peaks['source'] + ', burst figure (kernel timed alone)'}
+
+
+def run_native_nlspn(args):
+    """BASELINE.json configs[3]: NLSPN ProxyTTA at 352x1216, one adapting model per GPU, no collective."""
+    from oracle import nlspn_oracle as NO              # synthetic checkpoint / frame generators only
+    from tta_depth_completion_b200.nlspn_engine import NlspnEngine
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the TTA step has no CPU fallback (use --impl reference for the CPU arm)')
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    h, w, dataset, mode, lr, cap = WORKLOADS['nlspn']
+    peaks = load_peaks()
+    eng = NlspnEngine(NO.make_synthetic_checkpoint(0), args.batch, h, w, dev)
+    mean, std = NO.IMAGENET_MEAN, NO.IMAGENET_STD
+    eng.set_image_normalization([1.0 / (255.0 * s) for s in std], [-m / s for m, s in zip(mean, std)])
+    frames = [NO.synthetic_frame(1 + rank, t, args.batch, h, w, dataset)[:2] for t in range(RING)]
+    dev_frames = [(i.to(dev), s.to(dev)) for i, s in frames]
+    pinned = [(i.pin_memory(), s.pin_memory()) for i, s in frames]
+    img_d, sp_d = torch.empty_like(dev_frames[0][0]), torch.empty_like(dev_frames[0][1])
+    stream = torch.cuda.Stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        eng.tta_step(img_d, img_d, sp_d, lr, W_SD, W_SM, W_COS, cap)
+
+    with torch.cuda.stream(stream):
+        img_d.copy_(dev_frames[0][0]); sp_d.copy_(dev_frames[0][1])
+        step()
+        l0 = eng.launches
+        step()
+        launches_per_step = eng.launches - l0
+        for i in range(args.warmup):
+            img_d.copy_(dev_frames[i % RING][0], non_blocking=True); sp_d.copy_(dev_frames[i % RING][1], non_blocking=True)
+            step()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            img_d.copy_(dev_frames[(args.warmup + i) % RING][0], non_blocking=True); sp_d.copy_(dev_frames[(args.warmup + i) % RING][1], non_blocking=True)
+            step()
+        e1.record(stream)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        sampler.stop_flag = True
+        losses = eng.read_losses()
+        for i in range(3):
+            img_d.copy_(pinned[i % RING][0], non_blocking=True); sp_d.copy_(pinned[i % RING][1], non_blocking=True)
+            step()
+            eng.read_losses()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for i in range(args.steps):
+            img_d.copy_(pinned[i % RING][0], non_blocking=True); sp_d.copy_(pinned[i % RING][1], non_blocking=True)
+            step()
+            eng.read_losses()                       # D2H + sync, every step (src/tta_main.py:801)
+        f1.record(stream)
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    frames_total = world * args.batch * args.steps
+    h2d = frames[0][0].numel() * 4 + frames[0][1].numel() * 4
+    line = {'metric': 'adapted_frames_per_sec', 'value': frames_total / (ms_total / 1e3), 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(args),
+            'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 20,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step, 'cuda_graph': False,
+            'clocks': sampler.summary(), 'last_losses': losses,
+            'step_tflops': NLSPN_GFLOP_STEP * args.batch / (ms_total / args.steps),
+            'step_tflops_note': 'algorithmic work per step (%.1f GFLOP x batch: SURVEY.md 8d) / ms_per_step' % NLSPN_GFLOP_STEP}
+    if world == 1 and not args.no_extras:
+        line['roofline'] = time_convg_kernel(dev, peaks)
+        line['cpu_baseline'] = nlspn_cpu_sample(args, 1, 1)[2]
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_native(args):
+    if args.workload == 'nlspn':
+        return run_native_nlspn(args)
     from tta_depth_completion_b200 import ExternalModel_Adapt
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

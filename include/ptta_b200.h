@@ -164,9 +164,11 @@ int ptta_convg_run_thin(const void* x0_bf16, const void* x1_bf16, const void* pa
                         ptta_stream_t stream);
 
 /* ---- channel-generic kernels of the NLSPN network (csrc/nlspn_net.cuh); NHWC bf16 maps [rows][c], c % 64 == 0 ------------- */
-/* conv1_rgb + conv1_dep + LeakyReLU(0.2) (nlspnmodel_adapt.py:385-388, 866-867); image == NULL: the zero image of :907 */
+/* conv1_rgb + conv1_dep + LeakyReLU(0.2) (nlspnmodel_adapt.py:385-388, 866-867); image == NULL: the zero image of :907;
+ * scale3 / shift3 (nullable): per-channel image normalisation x*scale+shift folded into the load (src/tta_main.py:595-604) */
 int ptta_nl_stem(const float* image_nchw, const float* depth, const float* w_rgb, const float* b_rgb, const float* w_dep,
-                 const float* b_dep, void* out_bf16_c64, int n, int h, int w, ptta_stream_t stream);
+                 const float* b_dep, const float* scale3, const float* shift3, void* out_bf16_c64, int n, int h, int w,
+                 ptta_stream_t stream);
 /* number of partial blocks the reductions below use: `partial` must hold 2 * c * blocks floats */
 int ptta_nl_reduce_blocks(long long rows, int c);
 /* train-mode BatchNorm statistics (batch mean, biased variance) -> mean, rstd, scale = gamma*rstd, shift = beta - mean*scale;
@@ -188,6 +190,8 @@ int ptta_nl_add3(const void* a, long long lda, const void* b, long long ldb, con
                  int c, ptta_stream_t stream);
 /* output = clamp(y, min=0) (nlspnmodel_adapt.py:901) and its adjoint */
 int ptta_nl_clamp0(const float* y, float* out, long long n, ptta_stream_t stream);
+/* src/external_model_adapt.py:103-108: clamp(sparse_depth, 0, max_input_depth) */
+int ptta_nl_clamp(const float* x, float* out, float lo, float hi, long long n, ptta_stream_t stream);
 int ptta_nl_mask_pos(const float* g, const float* y, float* out, long long n, ptta_stream_t stream);
 /* gradients of (pred_init, guide[8], confidence) through LeakyReLU / identity / sigmoid -> NHWC bf16 [n,h,w,64] (ch >= 10 zero) */
 int ptta_nl_thin_grad_pack(const float* g_pred, const float* pred_init, const float* g_guide, const float* g_conf, const float* conf,

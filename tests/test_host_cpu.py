@@ -58,8 +58,15 @@ def test_engine_host_logic_without_gpu(lib, mode, n_adapt):
 def test_engine_rejects_bad_arguments(lib):
     L = lib.lib()
     h = ctypes.c_void_p()
-    assert L.ptta_msgchn_create(ctypes.byref(h), 1, 350, 1216, b'meta_selfsup_seq_2layers_ema') != 0
-    assert 'multiples of 16' in lib.last_error()
+    # any H, W is accepted since the engine pads to /16 itself (a4); degenerate shapes are not
+    assert L.ptta_msgchn_create(ctypes.byref(h), 1, 0, 1216, b'meta_selfsup_seq_2layers_ema') != 0
+    assert 'bad shape' in lib.last_error()
+    # general-channel conv family: channel counts must be multiples of 64, the 1x1/s2 data gradient only exists folded
+    assert L.ptta_convg_packed_elems(0, 0, 48, 0, 64, 0) < 0
+    assert 'multiples of 64' in lib.last_error()
+    assert L.ptta_convg_packed_elems(3, 1, 64, 0, 128, 0) < 0
+    assert L.ptta_convg_packed_elems(0, 0, 64, 64, 64, 0) == 18 * 64 * 64          # 9 taps x 2 sources x [64][64]
+    assert L.ptta_convg_packed_elems(1, 1, 64, 0, 128, 1) == (9 * 2 + 2) * 64 * 64   # 3x3/s2 dgrad (K = 128) + folded 1x1 shortcut
     assert L.ptta_msgchn_create(ctypes.byref(h), 1, 352, 1216, b'selfsup_only') != 0
     assert 'meta' in lib.last_error()
     assert L.ptta_msgchn_create(ctypes.byref(h), 0, 352, 1216, b'meta_selfsup_seq_2layers_ema') != 0

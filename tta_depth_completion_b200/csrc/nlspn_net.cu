@@ -44,10 +44,10 @@ int ptta_convg_run_thin(const void* x0, const void* x1, const void* packed, cons
 }
 
 int ptta_nl_stem(const float* image, const float* depth, const float* w_rgb, const float* b_rgb, const float* w_dep, const float* b_dep,
-                 void* out, int n, int h, int w, ptta_stream_t stream) {
+                 const float* scale, const float* shift, void* out, int n, int h, int w, ptta_stream_t stream) {
     PTTA_CHECK(depth && w_rgb && b_rgb && w_dep && b_dep && out, "nl_stem: null pointer");
     const long long total = (long long)n * h * w;
-    nl_stem_kernel<<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(image, depth, w_rgb, b_rgb, w_dep, b_dep, (bf16*)out, n, h, w);
+    nl_stem_kernel<<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(image, depth, w_rgb, b_rgb, w_dep, b_dep, scale, shift, (bf16*)out, n, h, w);
     return check_launch("nl_stem");
 }
 
@@ -121,6 +121,11 @@ int ptta_nl_add3(const void* a, long long lda, const void* b, long long ldb, con
 int ptta_nl_clamp0(const float* y, float* out, long long n, ptta_stream_t stream) {
     clamp0_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(y, out, n);
     return check_launch("nl_clamp0");
+}
+
+int ptta_nl_clamp(const float* x, float* out, float lo, float hi, long long n, ptta_stream_t stream) {
+    clamp_range_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, out, lo, hi, n);
+    return check_launch("nl_clamp");
 }
 
 int ptta_nl_mask_pos(const float* g, const float* y, float* out, long long n, ptta_stream_t stream) {

@@ -40,6 +40,7 @@ __device__ __forceinline__ float act_der(float y, int act) { return act == 1 ? (
 __global__ void __launch_bounds__(128) nl_stem_kernel(const float* __restrict__ image, const float* __restrict__ depth,
                                                       const float* __restrict__ w_rgb, const float* __restrict__ b_rgb,
                                                       const float* __restrict__ w_dep, const float* __restrict__ b_dep,
+                                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                                       bf16* __restrict__ out, int N, int H, int W) {
     __shared__ float s_w[27 * 48 + 9 * 16];      // [ci*9+tap][48] then [tap][16]
     __shared__ float s_b[64];
@@ -47,6 +48,10 @@ __global__ void __launch_bounds__(128) nl_stem_kernel(const float* __restrict__ 
     for (int i = threadIdx.x; i < 9 * 16; i += blockDim.x) { const int co = i % 16, r = i / 16; s_w[27 * 48 + i] = w_dep[co * 9 + r]; }
     if (threadIdx.x < 64) s_b[threadIdx.x] = threadIdx.x < 48 ? b_rgb[threadIdx.x] : b_dep[threadIdx.x - 48];
     __syncthreads();
+    // image normalisation (x * scale + shift per channel) folded in; zero padding applies to the normalised image
+    float nsc[3], nsh[3];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) { nsc[ci] = scale ? scale[ci] : 1.f; nsh[ci] = shift ? shift[ci] : 0.f; }
     const long long HW = (long long)H * W, total = (long long)N * HW;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(128) nl_stem_kernel(const float* __restrict__ 
             if (image) {
 #pragma unroll
                 for (int ci = 0; ci < 3; ++ci) {
-                    const float v = __ldg(image + ((long long)n * 3 + ci) * HW + o);
+                    const float v = fmaf(__ldg(image + ((long long)n * 3 + ci) * HW + o), nsc[ci], nsh[ci]);
                     const float* wr = s_w + (ci * 9 + tap) * 48;
 #pragma unroll
                     for (int c = 0; c < 48; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
@@ -278,6 +283,10 @@ __global__ void __launch_bounds__(256) add3_kernel(const bf16* __restrict__ a, l
 __global__ void clamp0_kernel(const float* __restrict__ y, float* __restrict__ out, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = fmaxf(y[i], 0.f);
+}
+__global__ void clamp_range_kernel(const float* __restrict__ x, float* __restrict__ out, float lo, float hi, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fminf(fmaxf(x[i], lo), hi);
 }
 __global__ void mask_pos_kernel(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ out, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -62,6 +62,7 @@ class NlspnEngine:
         self.loss_ws = torch.zeros(_lib.lib().ptta_tta_loss_workspace_bytes(n, h, w, self.R), dtype=torch.uint8, device=self.dev)
         self.wgrad_ws = torch.empty(_lib.lib().ptta_nl_wgrad48_workspace_bytes() // 4, dtype=torch.float32, device=self.dev)
         self.step_count = 0
+        self.img_scale = self.img_shift = None
 
     # ---- parameters -------------------------------------------------------------------------------------------------------------
     def _build_flat(self, sd):
@@ -232,12 +233,18 @@ class NlspnEngine:
         return dx, gskip
 
     # ---- forward ----------------------------------------------------------------------------------------------------------------
+    def set_image_normalization(self, scale, shift):
+        """network input = image * scale + shift per channel, applied inside the stem kernel (None: the caller passes the
+        normalised image, as the reference's forward() expects)"""
+        self.img_scale = None if scale is None else torch.tensor(scale, dtype=torch.float32, device=self.dev)
+        self.img_shift = None if shift is None else torch.tensor(shift, dtype=torch.float32, device=self.dev)
+
     def encoder(self, pre, image, depth):
         """fe1 .. fe6 (nlspnmodel_adapt.py:866-880); `pre` prefixes the buffer names ('r.' real branch, 'z.' zero-image branch)"""
         sd, N, H, W = self.sd, self.N, self.H, self.W
         x1 = self.buf(pre + 'stem', (N, H, W, 64))
         check(_lib.lib().ptta_nl_stem(ptr(image), ptr(depth), ptr(sd['conv1_rgb.0.weight']), ptr(sd['conv1_rgb.0.bias']), ptr(sd['conv1_dep.0.weight']),
-                                      ptr(sd['conv1_dep.0.bias']), ptr(x1), N, H, W, _stream()), 'nl_stem')
+                                      ptr(sd['conv1_dep.0.bias']), ptr(self.img_scale), ptr(self.img_shift), ptr(x1), N, H, W, _stream()), 'nl_stem')
         self.launches += 1
         x = self.conv('meta', x1, out_name=pre + 'fe1')
         fe = [x]
@@ -459,10 +466,8 @@ class NlspnEngine:
         v_f = self.buf('filtered_validity', (N, 1, H, W), torch.float32)
         check(_lib.lib().ptta_outlier_removal(ptr(sparse_depth), ptr(d_f), ptr(v_f), N, H, W, 7, 1.5, _stream()), 'outlier_removal')
         d_c = self.buf('clamped_depth', (N, 1, H, W), torch.float32)
-        if cap is not None:
-            torch.clamp(d_f, 0, cap, out=d_c)                      # src/external_model_adapt.py:103-108
-        else:
-            d_c.copy_(d_f)
+        hi = float(cap) if cap is not None else 3.0e38                # src/external_model_adapt.py:103-108
+        check(_lib.lib().ptta_nl_clamp(ptr(d_f), ptr(d_c), 0.0, hi, d_f.numel(), _stream()), 'nl_clamp')
         self._depth = d_c
         self.forward(image_norm, d_c, training=True)
         self.loss(image_raw, d_f, v_f, cap, w_sd, w_sm, w_cos)
