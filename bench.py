@@ -316,15 +316,16 @@ def run_native_nlspn(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step():
-        eng.tta_step(img_d, img_d, sp_d, lr, W_SD, W_SM, W_COS, cap)
+    def step(graph=None):
+        eng.tta_step(img_d, img_d, sp_d, lr, W_SD, W_SM, W_COS, cap, graph=args.graph if graph is None else graph)
 
     with torch.cuda.stream(stream):
         img_d.copy_(dev_frames[0][0]); sp_d.copy_(dev_frames[0][1])
-        step()
+        step(False)
         l0 = eng.launches
-        step()
+        step(False)
         launches_per_step = eng.launches - l0
+        step(); step()                                   # graph mode: first call eager, second captures
         for i in range(args.warmup):
             img_d.copy_(dev_frames[i % RING][0], non_blocking=True); sp_d.copy_(dev_frames[i % RING][1], non_blocking=True)
             step()
@@ -370,7 +371,7 @@ def run_native_nlspn(args):
             'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(args),
             'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 20,
                     'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step, 'cuda_graph': False,
+            'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step, 'cuda_graph': bool(args.graph),
             'clocks': sampler.summary(), 'last_losses': losses,
             'step_tflops': NLSPN_GFLOP_STEP * args.batch / (ms_total / args.steps),
             'step_tflops_note': 'algorithmic work per step (%.1f GFLOP x batch: SURVEY.md 8d) / ms_per_step' % NLSPN_GFLOP_STEP}

@@ -88,6 +88,10 @@ int ptta_gemm_bf16_tc(const void* a, const void* b, void* c, const float* bias, 
 /* torch.optim.Adam over one flat fp32 buffer (src/tta_main.py:341-346,633); step is 1-based */
 int ptta_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                    double lr, double beta1, double beta2, double eps, double weight_decay, int step, ptta_stream_t stream);
+/* same update with the step counter (int, incremented by the call) and the hyper-parameters {lr, beta1, beta2, eps, weight_decay}
+ * (doubles) in DEVICE memory, so the call can be captured into a CUDA graph and replayed */
+int ptta_adam_flat_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, const double* hyper_dev,
+                       int* step_dev, ptta_stream_t stream);
 
 /* ---- NLSPN non-local spatial propagation ----------------------------- */
 /* DCN.modulated_deform_conv_forward / _backward, the reference's one native FFI

@@ -42,6 +42,7 @@ struct ConvGParams {
     int N, tiles_y, tiles_x, n_tiles, BN;
     int th, tw;
     int total_tiles;
+    int stages, stage_bytes;   // operand ring: stage = A tile (16 KB) + B tile (BN x 128 B, rounded up to 1 KB)
     const float* bias;   // [Cout] or null
     // thin epilogue (BN == 16): fp32 planar outputs, one plane pointer per channel (image 0), activation per channel
     int thin, thin_n, H, W;
@@ -51,12 +52,11 @@ struct ConvGParams {
 };
 
 struct ConvGCfg {
-    static const int STAGES = 4;
+    static const int MAX_STAGES = 8;
     static const int A_BYTES = 128 * 128;            // 128 positions x 64 channels bf16
-    static const int B_BYTES = 256 * 128;            // up to 256 output channels x 64
-    static const int STAGE_BYTES = A_BYTES + B_BYTES;
+    static const int RING_BYTES = 4 * (A_BYTES + 256 * 128);   // 192 KB of operand stages: 4 at BN = 256 ... 8 at BN <= 64
     static const int OUT_BYTES = 128 * 128;          // one 64-channel output group
-    static const int SMEM = 1024 + STAGES * STAGE_BYTES + 2 * OUT_BYTES + 256;
+    static const int SMEM = 1024 + RING_BYTES + 2 * OUT_BYTES + 256;
     static const int THREADS = 192;
 };
 
@@ -88,9 +88,10 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t out_s = smem_base + C::STAGES * C::STAGE_BYTES;
+    const uint32_t out_s = smem_base + C::RING_BYTES;
     const uint32_t bar_s = out_s + 2 * C::OUT_BYTES;
-    const uint32_t full = bar_s, empty = bar_s + 8 * C::STAGES, acc_full = bar_s + 16 * C::STAGES, acc_empty = acc_full + 16;
+    const uint32_t full = bar_s, empty = bar_s + 8 * C::MAX_STAGES, acc_full = bar_s + 16 * C::MAX_STAGES, acc_empty = acc_full + 16;
+    const uint32_t STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
     const uint32_t tmem_slot = acc_empty + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -101,7 +102,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
         tc::prefetch_tmap(&tmap_a1);
         tc::prefetch_tmap(&tmap_b);
         tc::prefetch_tmap(&tmap_out);
-        for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(full + 8 * i, 1); tc::mbar_init(empty + 8 * i, 1); }
+        for (int i = 0; i < C::MAX_STAGES; ++i) { tc::mbar_init(full + 8 * i, 1); tc::mbar_init(empty + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + 8 * i, 1); tc::mbar_init(acc_empty + 8 * i, 128); }
         tc::fence_barrier_init();
     }
@@ -112,54 +113,59 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                int r = tile;
-                const int nt = r % p.n_tiles; r /= p.n_tiles;
-                const int tx = r % p.tiles_x; r /= p.tiles_x;
-                const int ty = r % p.tiles_y; r /= p.tiles_y;
-                const int n = r % p.N, cls = r / p.N;
-                const int gx0 = tx * p.tw, gy0 = ty * p.th;
-                const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
-                for (int i = 0; i < cnt; ++i, ++it) {
-                    const ConvGItem item = p.items[i0 + i];
-                    const uint32_t s = it % C::STAGES, par = (it / C::STAGES) & 1;
-                    tc::mbar_wait(empty + 8 * s, par ^ 1);
+        // TMA producer: the warp stays converged, one elected lane issues (a divergent `if (lane == 0)` makes the compiler wrap
+        // every UTMALDG / UTCHMMA in an ELECT + BRA.U.ANY loop)
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int r = tile;
+            const int nt = r % p.n_tiles; r /= p.n_tiles;
+            const int tx = r % p.tiles_x; r /= p.tiles_x;
+            const int ty = r % p.tiles_y; r /= p.tiles_y;
+            const int n = r % p.N, cls = r / p.N;
+            const int gx0 = tx * p.tw, gy0 = ty * p.th;
+            const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
+            for (int i = 0; i < cnt; ++i, ++it) {
+                const ConvGItem item = p.items[i0 + i];
+                const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
+                tc::mbar_wait(empty + 8 * s, par ^ 1);
+                if (elect_one()) {
                     tc::mbar_arrive_expect_tx(full + 8 * s, stage_tx);
-                    const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
+                    const uint32_t a_dst = smem_base + s * STAGE_BYTES;
                     const int dy = (int)(short)(item.dyps & 0xffff), py = (item.dyps >> 16) & 3, src = (item.dyps >> 20) & 1;
                     tc::tma_load_5d(a_dst, src ? &tmap_a1 : &tmap_a0, full + 8 * s, item.c_inner, gx0 + item.dx, py, gy0 + dy, n);
                     tc::tma_load_3d(a_dst + C::A_BYTES, &tmap_b, full + 8 * s, 0, nt * p.BN, item.wk);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(128, p.BN);
-            const uint64_t d0 = make_desc_sw128(0);
-            const uint32_t hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
-            uint32_t it = 0, t = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-                const int cls = tile / (p.n_tiles * p.tiles_x * p.tiles_y * p.N);
-                const int cnt = p.cls_count[cls];
-                const uint32_t as = t & 1;
-                tc::mbar_wait(acc_empty + 8 * as, ((t >> 1) & 1) ^ 1);
+        // MMA issuer (converged warp, one elected lane issues and commits)
+        const uint32_t idesc = tc::make_idesc_bf16(128, p.BN);
+        const uint64_t d0 = make_desc_sw128(0);
+        const uint32_t hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
+        uint32_t it = 0, t = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+            const int cls = tile / (p.n_tiles * p.tiles_x * p.tiles_y * p.N);
+            const int cnt = p.cls_count[cls];
+            const uint32_t as = t & 1;
+            tc::mbar_wait(acc_empty + 8 * as, ((t >> 1) & 1) ^ 1);
+            tc::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * 256;
+            for (int i = 0; i < cnt; ++i, ++it) {
+                const uint32_t s = it % STAGES;
+                tc::mbar_wait(full + 8 * s, (it / STAGES) & 1);
                 tc::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * 256;
-                for (int i = 0; i < cnt; ++i, ++it) {
-                    const uint32_t s = it % C::STAGES;
-                    tc::mbar_wait(full + 8 * s, (it / C::STAGES) & 1);
-                    tc::tc_fence_after();
-                    const uint32_t a_lo = lo0 + ((smem_base + s * C::STAGE_BYTES) >> 4);
+                if (elect_one()) {
+                    const uint32_t a_lo = lo0 + ((smem_base + s * STAGE_BYTES) >> 4);
                     const uint32_t b_lo = a_lo + (C::A_BYTES >> 4);
                     if (i == 0) tc::umma_f16_split<false>(d_tmem, a_lo, hi, b_lo, hi, idesc);
                     else tc::umma_f16_split<true>(d_tmem, a_lo, hi, b_lo, hi, idesc);
 #pragma unroll
                     for (int k = 1; k < 4; ++k) tc::umma_f16_split<true>(d_tmem, a_lo + k * 2, hi, b_lo + k * 2, hi, idesc);
                     tc::umma_commit(empty + 8 * s);
+                    if (i == cnt - 1) tc::umma_commit(acc_full + 8 * as);
                 }
-                tc::umma_commit(acc_full + 8 * as);
+                __syncwarp();
             }
         }
     } else {
@@ -383,6 +389,9 @@ inline int convg_make_plan(ConvGPlan& pl, int kind, int role, int n, int h, int 
     int BN = 16;                       // largest multiple of 64 that is <= 256 and divides the output channels
     if (!thin) for (BN = 256; nout % BN; BN -= 64) {}
     pl.p.thin = thin ? 1 : 0;
+    pl.p.stage_bytes = ConvGCfg::A_BYTES + ((BN * 128 + 1023) / 1024) * 1024;
+    pl.p.stages = ConvGCfg::RING_BYTES / pl.p.stage_bytes;
+    if (pl.p.stages > ConvGCfg::MAX_STAGES) pl.p.stages = ConvGCfg::MAX_STAGES;
     static const int shapes[4][2] = {{8, 16}, {4, 32}, {2, 64}, {1, 128}};
     long long best = -1; int bi = 0;
     for (int i = 0; i < 4; ++i) {

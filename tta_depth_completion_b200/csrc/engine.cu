@@ -1204,6 +1204,22 @@ __global__ void adam_flat_kernel(float* p, const float* g, float* m, float* v, l
         p[i] = pp; m[i] = mm; v[i] = vv;
     }
 }
+// CUDA-graph friendly variant: step counter and hyper-parameters (lr, beta1, beta2, eps, weight_decay as doubles) live on the device
+__global__ void adam_tick_kernel(int* step) { *step += 1; }
+__global__ void adam_flat_dev_kernel(float* p, const float* g, float* m, float* v, long long n, const double* __restrict__ hy, const int* __restrict__ step) {
+    const double b1 = hy[1], b2 = hy[2];
+    const int t = *step;
+    const double bc1 = 1.0 - pow(b1, (double)t);
+    const double bc2 = 1.0 - pow(b2, (double)t);
+    const float step_size = (float)(hy[0] / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float fb2 = (float)b2, omb1 = (float)(1.0 - b1), omb2 = (float)(1.0 - b2), eps = (float)hy[3], wd = (float)hy[4];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float pp = p[i], mm = m[i], vv = v[i];
+        adam_update(pp, g[i], mm, vv, fb2, omb1, omb2, eps, wd, step_size, bc2_sqrt);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
 // ---- stand-alone fused TTA loss (used by the NLSPN back-end, whose graph is driven from Python) -------------------------------------
 struct TtaLossLayout { size_t scalars, map_partial, cos_partial, rowstat, total; int map_blocks, cos_blocks; };
 static TtaLossLayout tta_loss_layout(int n, int h, int w, long long rows) {
@@ -1261,6 +1277,16 @@ int ptta_adam_flat(float* p, const float* g, float* m, float* v, long long n, do
     int blocks = (int)std::min<long long>(cdiv(n, 256), 1184);
     adam_flat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, (float)eps, (float)wd, step);
     return check_launch("adam_flat");
+}
+
+int ptta_adam_flat_dev(float* p, const float* g, float* m, float* v, long long n, const double* hyper_dev, int* step_dev, ptta_stream_t stream) {
+    PTTA_CHECK(p && g && m && v && hyper_dev && step_dev, "adam_flat_dev: null pointer");
+    if (n <= 0) return 0;
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    PTTA_TRY(check_launch("adam_tick"));
+    int blocks = (int)std::min<long long>(cdiv(n, 256), 1184);
+    adam_flat_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper_dev, step_dev);
+    return check_launch("adam_flat_dev");
 }
 
 // ---- NLSPN propagation path ------------------------------------------------------

@@ -153,15 +153,23 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const bf16* __restrict
     }
 }
 
-__global__ void __launch_bounds__(128) bn_finalize2_kernel(const float* __restrict__ partial, int nblk, long long count, int C,
+// one warp per channel: lanes stride over the partial blocks, double accumulation, fixed-order shuffle tree (deterministic)
+__device__ __forceinline__ void partial_sums(const float* __restrict__ partial, int nblk, int C, int c, int lane, double& s, double& q) {
+    s = 0.0; q = 0.0;
+    for (int b = lane; b < nblk; b += 32) { s += (double)partial[((size_t)b * 2) * C + c]; q += (double)partial[((size_t)b * 2 + 1) * C + c]; }
+    s = warp_sum_d(s); q = warp_sum_d(q);
+}
+
+__global__ void __launch_bounds__(256) bn_finalize2_kernel(const float* __restrict__ partial, int nblk, long long count, int C,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                            float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
                                                            float* __restrict__ shift, float* __restrict__ run_mean, float* __restrict__ run_var,
                                                            long long* __restrict__ nbt, float momentum, float* __restrict__ sums_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblk; ++b) { s += (double)partial[((size_t)b * 2) * C + c]; q += (double)partial[((size_t)b * 2 + 1) * C + c]; }
+    double s, q;
+    partial_sums(partial, nblk, C, c, lane, s, q);
+    if (lane != 0) return;
     if (sums_out) { sums_out[c] = (float)s; return; }          // plain column sums (bias gradients)
     const double m = s / (double)count;
     double var = q / (double)count - m * m;
@@ -178,14 +186,15 @@ __global__ void __launch_bounds__(128) bn_finalize2_kernel(const float* __restri
     }
 }
 
-__global__ void __launch_bounds__(128) bn_bwd_finalize2_kernel(const float* __restrict__ partial, int nblk, long long count, int C,
+__global__ void __launch_bounds__(256) bn_bwd_finalize2_kernel(const float* __restrict__ partial, int nblk, long long count, int C,
                                                                const float* __restrict__ gamma, const float* __restrict__ rstd,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ k0,
                                                                float* __restrict__ k1, float* __restrict__ k2) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
-    double sg = 0.0, sgx = 0.0;
-    for (int b = 0; b < nblk; ++b) { sg += (double)partial[((size_t)b * 2) * C + c]; sgx += (double)partial[((size_t)b * 2 + 1) * C + c]; }
+    double sg, sgx;
+    partial_sums(partial, nblk, C, c, lane, sg, sgx);
+    if (lane != 0) return;
     if (dgamma) dgamma[c] = (float)sgx;
     if (dbeta) dbeta[c] = (float)sg;
     const float a = gamma[c] * rstd[c];

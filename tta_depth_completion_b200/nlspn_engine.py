@@ -63,6 +63,11 @@ class NlspnEngine:
         self.wgrad_ws = torch.empty(_lib.lib().ptta_nl_wgrad48_workspace_bytes() // 4, dtype=torch.float32, device=self.dev)
         self.step_count = 0
         self.img_scale = self.img_shift = None
+        self.aff_scale = float(sd['prop_layer.aff_scale_const'])
+        self.adam_hyper = torch.tensor([0.0, 0.9, 0.999, 1e-8, 0.0], dtype=torch.float64, device=self.dev)
+        self._adam_host = None
+        self.adam_step_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._graph, self._graph_key, self._seen_key = None, None, None
 
     # ---- parameters -------------------------------------------------------------------------------------------------------------
     def _build_flat(self, sd):
@@ -300,7 +305,6 @@ class NlspnEngine:
                                            ptr(oa), N, H, W, 0, _stream()), 'nl_conv8to24')
         offset = self.buf('offset', (N, 18, H, W), torch.float32)
         aff = self.buf('aff', (N, 9, H, W), torch.float32)
-        self.aff_scale = float(sd['prop_layer.aff_scale_const'])
         check(_lib.lib().ptta_nlspn_offset_affinity_forward(ptr(oa), ptr(conf), self.aff_scale, int(self.legacy), ptr(offset), ptr(aff), N, H, W,
                                                             _stream()), 'offset_affinity_forward')
         y = self.buf('y', (N, 1, H, W), torch.float32)
@@ -451,16 +455,49 @@ class NlspnEngine:
         self.launches += 6
 
     # ---- optimiser + whole step ---------------------------------------------------------------------------------------------------
-    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
-        self.step_count += 1
-        check(_lib.lib().ptta_adam_flat(ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), ptr(self.flat_v), self.flat_p.numel(), lr, betas[0],
-                                        betas[1], eps, weight_decay, self.step_count, _stream()), 'adam_flat')
-        self.repack_adapted()
-        self.launches += 2
+    def set_adam(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        """hyper-parameters live on the device (the captured step reads them there); a change costs one small H2D copy"""
+        host = (float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay))
+        if host != self._adam_host:
+            self.adam_hyper.copy_(torch.tensor(host, dtype=torch.float64))
+            self._adam_host = host
 
-    def tta_step(self, image_norm, image_raw, sparse_depth, lr, w_sd=1.0, w_sm=1.0, w_cos=0.1, cap=80.0):
+    def adam_step(self):
+        self.step_count += 1
+        check(_lib.lib().ptta_adam_flat_dev(ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), ptr(self.flat_v), self.flat_p.numel(),
+                                            ptr(self.adam_hyper), ptr(self.adam_step_dev), _stream()), 'adam_flat_dev')
+        self.repack_adapted()
+        self.launches += 3
+
+    def tta_step(self, image_norm, image_raw, sparse_depth, lr, w_sd=1.0, w_sm=1.0, w_cos=0.1, cap=80.0, graph=False):
         """src/tta_main.py:583-633 for the NLSPN back-end: outlier removal, forward, losses, backward, Adam.
-        image_norm: the normalised image the network sees, image_raw: the [0,255] image the smoothness loss sees."""
+        image_norm: the image the network sees (normalised by the caller, or raw when set_image_normalization folds the
+        normalisation into the stem), image_raw: the [0,255] image the smoothness loss sees.
+        graph=True: the step is captured into a CUDA graph the second time it is called with the same input buffers and
+        loss weights, and replayed from then on (the inputs are read from those buffers at every replay)."""
+        self.set_adam(lr)
+        if not graph:
+            return self._step_body(image_norm, image_raw, sparse_depth, w_sd, w_sm, w_cos, cap)
+        key = (image_norm.data_ptr(), image_raw.data_ptr(), sparse_depth.data_ptr(), float(w_sd), float(w_sm), float(w_cos), cap)
+        if self._graph is not None and self._graph_key == key:
+            self._graph.replay()
+            self.step_count += 1
+            return
+        if self._seen_key != key:
+            self._seen_key = key                               # first call: eager (allocates every buffer, sets kernel attributes)
+            return self._step_body(image_norm, image_raw, sparse_depth, w_sd, w_sm, w_cos, cap)
+        g = torch.cuda.CUDAGraph()
+        l0 = self.launches
+        torch.cuda.synchronize(self.dev)
+        with torch.cuda.graph(g):
+            self._step_body(image_norm, image_raw, sparse_depth, w_sd, w_sm, w_cos, cap)
+        self.step_count -= 1                                   # capture does not execute
+        self.launches_per_step = self.launches - l0
+        self._graph, self._graph_key = g, key
+        g.replay()
+        self.step_count += 1
+
+    def _step_body(self, image_norm, image_raw, sparse_depth, w_sd, w_sm, w_cos, cap):
         N, H, W = self.N, self.H, self.W
         d_f = self.buf('filtered_depth', (N, 1, H, W), torch.float32)
         v_f = self.buf('filtered_validity', (N, 1, H, W), torch.float32)
@@ -472,5 +509,5 @@ class NlspnEngine:
         self.forward(image_norm, d_c, training=True)
         self.loss(image_raw, d_f, v_f, cap, w_sd, w_sm, w_cos)
         self.backward()
-        self.adam_step(lr)
+        self.adam_step()
         self.launches += 2
