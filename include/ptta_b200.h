@@ -160,6 +160,8 @@ int ptta_convg_pack(int kind, int role, const float* weight, const float* weight
 int ptta_convg_run(int kind, int role, const void* x0_bf16, const void* x1_bf16, const void* packed_bf16, const float* bias,
                    void* out_bf16, int n, int h, int w, int cin0, int cin1, int cout, int has_short, ptta_stream_t stream);
 
+/* timing experiments only: 1 one MMA per K-item, 2 no epilogue work, 4 no epilogue fence / store (results are then wrong) */
+int ptta_convg_debug_set(int mask);
 /* thin heads id_dec0 / gd_dec0 / cf_dec0 (nlspnmodel_adapt.py:430-448, 883-895) as ONE 16-output-channel conv over the concat
  * (x0 | x1): fp32 planar outputs through per-channel plane pointers (host arrays of n_real entries), activation per channel
  * (0 none, 1 LeakyReLU(0.2), 2 sigmoid).  Weights packed by ptta_convg_pack(kind 0, role 0, ..., cout = 16). */

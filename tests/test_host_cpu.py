@@ -91,7 +91,10 @@ def test_facade_refuses_cpu_and_unknown_models():
     with pytest.raises(ValueError):
         ExternalModel_Adapt('resnet', 0.0, 100.0, device=torch.device('cpu'))
     with pytest.raises(NotImplementedError):
-        ExternalModel_Adapt('nlspn', 0.0, 100.0, device=torch.device('cpu'))
+        ExternalModel_Adapt('costdcnet', 0.0, 100.0, device=torch.device('cpu'))
+    nl = ExternalModel_Adapt('nlspn', 0.0, 100.0, device=torch.device('cpu'))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        nl._prepare_head('meta_selfsup_seq_1layer_ema')
     m = ExternalModel_Adapt('msg_chn', 0.0, 100.0, device=torch.device('cpu'))
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         m._prepare_head('meta_selfsup_seq_2layers_ema')
@@ -143,3 +146,25 @@ def test_shared_model_gradient_allreduce_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and 'ok %d' % r in o, o
+
+
+def test_nlspn_facade_state_matches_reference_keys():
+    """key set, order and shapes of the NLSPN facade's fresh state == the reference's NLSPNModel_Adapt.state_dict() (manifest written
+    from the live reference by oracle/gen_golden_nlspn_net.py)"""
+    import json
+    import os
+    from tta_depth_completion_b200.nlspn_model_adapt import build_nlspn_state
+    from tta_depth_completion_b200.nlspn_engine import adapt_parameter_names
+    from oracle import nlspn_oracle as NO
+    sd = build_nlspn_state('meta_selfsup_seq_1layer_ema')
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, '..', 'oracle', 'nlspn_state_manifest.json')) as f:
+        manifest = json.load(f)
+    assert set(sd) == set(manifest)
+    for k, shape in manifest.items():
+        assert list(sd[k].shape) == shape, k
+    ref = NO.make_synthetic_checkpoint(0)
+    assert list(sd.keys()) == list(ref.keys())
+    assert adapt_parameter_names(sd) == NO.adapt_parameter_names(ref, 'meta_bn')
+    with pytest.raises(NotImplementedError):
+        build_nlspn_state('meta_selfsup_seq_2layers_ema')

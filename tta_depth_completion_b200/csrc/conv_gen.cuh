@@ -29,8 +29,10 @@ namespace ptta {
 struct ConvGItem {
     int c_inner;   // inner coordinate in the source view: px * C + channel offset
     int dx;        // added to the tile's grid x
-    int dyps;      // dy (low 16 bits, signed) | py << 16 | src << 20
+    int dyps;      // dy (low 16 bits, signed) | py << 16 | src << 20 | new_a << 24 | last_of_a << 25
     int wk;        // K-chunk index in the packed weights
+    int a_off16;   // start of this item's A operand inside the current A tile, in 16-byte units (halo mode: (ky*10 + kx)*8)
+    int pad;
 };
 
 struct ConvGParams {
@@ -42,7 +44,13 @@ struct ConvGParams {
     int N, tiles_y, tiles_x, n_tiles, BN;
     int th, tw;
     int total_tiles;
-    int stages, stage_bytes;   // operand ring: stage = A tile (16 KB) + B tile (BN x 128 B, rounded up to 1 KB)
+    // operand rings: A tiles (16 KB boxes, or 18x10-pixel halo tiles shared by the 9 taps of a 3x3/s1 conv) and B tiles
+    // (BN x 128 B); b_resident: every B tile of the layer is loaded once and stays in shared memory
+    int n_a, a_slot_bytes, a_tx_bytes, n_b, b_slot_bytes, b_resident, halo;
+    int halo_rev;        // data-gradient role: tap (ky, kx) reads the halo at (2-ky, 2-kx)
+    // tile index -> (n-tile, tile x, tile y, image, class) without integer division: q = umulhi(x, mul) >> shr (d > 1)
+    unsigned div_mul[4], div_shr[4];
+    int per_class;
     const float* bias;   // [Cout] or null
     // thin epilogue (BN == 16): fp32 planar outputs, one plane pointer per channel (image 0), activation per channel
     int thin, thin_n, H, W;
@@ -56,7 +64,10 @@ struct ConvGCfg {
     static const int A_BYTES = 128 * 128;            // 128 positions x 64 channels bf16
     static const int RING_BYTES = 4 * (A_BYTES + 256 * 128);   // 192 KB of operand stages: 4 at BN = 256 ... 8 at BN <= 64
     static const int OUT_BYTES = 128 * 128;          // one 64-channel output group
-    static const int SMEM = 1024 + RING_BYTES + 2 * OUT_BYTES + 256;
+    static const int HALO_W = 10, HALO_H = 18;        // halo of a 16-row x 8-column output tile
+    static const int HALO_BYTES = HALO_W * HALO_H * 128;          // 23040
+    static const int HALO_SLOT = 23 * 1024;
+    static const int SMEM = 1024 + RING_BYTES + 2 * OUT_BYTES + 512;
     static const int THREADS = 192;
 };
 
@@ -80,6 +91,24 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 }  // namespace tc
 
+__device__ __forceinline__ void fast_divmod(int x, int d, unsigned mul, unsigned shr, int& q, int& r) {
+    q = d == 1 ? x : (int)(__umulhi((unsigned)x, mul) >> shr);
+    r = x - q * d;
+}
+// tile -> coordinates; the class index (transposed-conv parity classes) is the slowest and rare: one real division only there
+#define CONVG_DECODE_TILE(tile, nt, tx, ty, n, cls)                                   \
+    int nt, tx, ty, n, cls;                                                           \
+    {                                                                                 \
+        int r_ = (tile);                                                              \
+        cls = p.n_classes == 1 ? 0 : r_ / p.per_class;                                \
+        r_ -= cls * p.per_class;                                                      \
+        fast_divmod(r_, p.n_tiles, p.div_mul[0], p.div_shr[0], r_, nt);               \
+        fast_divmod(r_, p.tiles_x, p.div_mul[1], p.div_shr[1], r_, tx);               \
+        fast_divmod(r_, p.tiles_y, p.div_mul[2], p.div_shr[2], n, ty);                \
+    }
+
+__device__ int g_convg_dbg = 0;   // timing experiments only (ptta_convg_debug_set): 1 one MMA per item, 2 no epilogue work, 4 no fence/store
+
 __global__ void __launch_bounds__(ConvGCfg::THREADS, 1)
 convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
              const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_out,
@@ -90,20 +119,27 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     unsigned char* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t out_s = smem_base + C::RING_BYTES;
     const uint32_t bar_s = out_s + 2 * C::OUT_BYTES;
-    const uint32_t full = bar_s, empty = bar_s + 8 * C::MAX_STAGES, acc_full = bar_s + 16 * C::MAX_STAGES, acc_empty = acc_full + 16;
-    const uint32_t STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
-    const uint32_t tmem_slot = acc_empty + 16;
+    const uint32_t a_full = bar_s, a_empty = bar_s + 64, b_full = bar_s + 128, b_empty = bar_s + 192, acc_full = bar_s + 256,
+                   acc_empty = bar_s + 272, w_full = bar_s + 288;
+    const uint32_t tmem_slot = bar_s + 296;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t stage_tx = C::A_BYTES + (uint32_t)p.BN * 128u;
+    const int dbg = g_convg_dbg;
+    const uint32_t NA = p.n_a, NB = p.n_b, A_SLOT = p.a_slot_bytes, B_SLOT = p.b_slot_bytes;
+    const uint32_t b_base = smem_base + NA * A_SLOT;            // B ring, or the resident weights
+    const uint32_t b_tx = (uint32_t)p.BN * 128u;
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmap_a0);
         tc::prefetch_tmap(&tmap_a1);
         tc::prefetch_tmap(&tmap_b);
         tc::prefetch_tmap(&tmap_out);
-        for (int i = 0; i < C::MAX_STAGES; ++i) { tc::mbar_init(full + 8 * i, 1); tc::mbar_init(empty + 8 * i, 1); }
+        for (int i = 0; i < C::MAX_STAGES; ++i) {
+            tc::mbar_init(a_full + 8 * i, 1); tc::mbar_init(a_empty + 8 * i, 1);
+            tc::mbar_init(b_full + 8 * i, 1); tc::mbar_init(b_empty + 8 * i, 1);
+        }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + 8 * i, 1); tc::mbar_init(acc_empty + 8 * i, 128); }
+        tc::mbar_init(w_full, 1);
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
@@ -115,57 +151,157 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     if (warp == 0) {
         // TMA producer: the warp stays converged, one elected lane issues (a divergent `if (lane == 0)` makes the compiler wrap
         // every UTMALDG / UTCHMMA in an ELECT + BRA.U.ANY loop)
-        uint32_t it = 0;
+        if (p.b_resident) {
+            if (elect_one()) {
+                int total = 0;
+                for (int c = 0; c < p.n_classes; ++c) total += p.cls_count[c];
+                tc::mbar_arrive_expect_tx(w_full, (uint32_t)total * b_tx);
+                for (int i = 0; i < total; ++i) tc::tma_load_3d(b_base + i * B_SLOT, &tmap_b, w_full, 0, 0, p.items[i].wk);
+            }
+            __syncwarp();
+        }
+        // ring positions are kept as (slot, phase) pairs: no division in the per-item path (one warp runs this serial code)
+        uint32_t sa = 0, pa = 1, sb = 0, pb = 1;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            int r = tile;
-            const int nt = r % p.n_tiles; r /= p.n_tiles;
-            const int tx = r % p.tiles_x; r /= p.tiles_x;
-            const int ty = r % p.tiles_y; r /= p.tiles_y;
-            const int n = r % p.N, cls = r / p.N;
+            CONVG_DECODE_TILE(tile, nt, tx, ty, n, cls)
             const int gx0 = tx * p.tw, gy0 = ty * p.th;
             const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
-            for (int i = 0; i < cnt; ++i, ++it) {
-                const ConvGItem item = p.items[i0 + i];
-                const uint32_t s = it % STAGES, par = (it / STAGES) & 1;
-                tc::mbar_wait(empty + 8 * s, par ^ 1);
-                if (elect_one()) {
-                    tc::mbar_arrive_expect_tx(full + 8 * s, stage_tx);
-                    const uint32_t a_dst = smem_base + s * STAGE_BYTES;
-                    const int dy = (int)(short)(item.dyps & 0xffff), py = (item.dyps >> 16) & 3, src = (item.dyps >> 20) & 1;
-                    tc::tma_load_5d(a_dst, src ? &tmap_a1 : &tmap_a0, full + 8 * s, item.c_inner, gx0 + item.dx, py, gy0 + dy, n);
-                    tc::tma_load_3d(a_dst + C::A_BYTES, &tmap_b, full + 8 * s, 0, nt * p.BN, item.wk);
+            if (p.halo) {
+                for (int i = 0; i < cnt; i += 9) {                  // one halo tile per 64-channel chunk, then its nine weight tiles
+                    const int c_inner = p.items[i0 + i].c_inner, src = (p.items[i0 + i].dyps >> 20) & 1;
+                    tc::mbar_wait(a_empty + 8 * sa, pa);
+                    if (elect_one()) {
+                        if (dbg & 8) {
+                            tc::mbar_arrive(a_full + 8 * sa);
+                        } else {
+                            tc::mbar_arrive_expect_tx(a_full + 8 * sa, (uint32_t)p.a_tx_bytes);
+                            tc::tma_load_5d(smem_base + sa * A_SLOT, src ? &tmap_a1 : &tmap_a0, a_full + 8 * sa, c_inner, gx0 - 1, 0, gy0 - 1, n);
+                        }
+                    }
+                    __syncwarp();
+                    if (++sa == NA) { sa = 0; pa ^= 1; }
+                    if (!p.b_resident) {
+                        for (int tap = 0; tap < 9; ++tap) {
+                            tc::mbar_wait(b_empty + 8 * sb, pb);
+                            if (elect_one()) {
+                                if (dbg & 16) {
+                                    tc::mbar_arrive(b_full + 8 * sb);
+                                } else {
+                                    tc::mbar_arrive_expect_tx(b_full + 8 * sb, b_tx);
+                                    tc::tma_load_3d(b_base + sb * B_SLOT, &tmap_b, b_full + 8 * sb, 0, nt * p.BN, i0 + i + tap);
+                                }
+                            }
+                            __syncwarp();
+                            if (++sb == NB) { sb = 0; pb ^= 1; }
+                        }
+                    }
                 }
-                __syncwarp();
+            } else {
+                for (int i = 0; i < cnt; ++i) {                     // one stage = A box + B tile, one barrier
+                    const ConvGItem item = p.items[i0 + i];
+                    tc::mbar_wait(a_empty + 8 * sa, pa);
+                    if (elect_one()) {
+                        tc::mbar_arrive_expect_tx(a_full + 8 * sa, (uint32_t)p.a_tx_bytes + b_tx);
+                        const int dy = (int)(short)(item.dyps & 0xffff), py = (item.dyps >> 16) & 3, src = (item.dyps >> 20) & 1;
+                        tc::tma_load_5d(smem_base + sa * A_SLOT, src ? &tmap_a1 : &tmap_a0, a_full + 8 * sa, item.c_inner, gx0 + item.dx, py,
+                                        gy0 + dy, n);
+                        tc::tma_load_3d(b_base + sa * B_SLOT, &tmap_b, a_full + 8 * sa, 0, nt * p.BN, i0 + i);
+                    }
+                    __syncwarp();
+                    if (++sa == NA) { sa = 0; pa ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
         // MMA issuer (converged warp, one elected lane issues and commits)
         const uint32_t idesc = tc::make_idesc_bf16(128, p.BN);
-        const uint64_t d0 = make_desc_sw128(0);
-        const uint32_t hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
-        uint32_t it = 0, t = 0;
+        // A: 8-row groups are 1024 B apart in a plain tile, HALO_W pixels (1280 B) apart in a halo tile (tile rows of 8 pixels);
+        // SWIZZLE_128B is a function of the shared-memory address, so any 128 B-aligned start inside the halo is a valid operand
+        const uint64_t da0 = make_desc_sw128_sbo(0, p.halo ? C::HALO_W * 128 : 1024), db0 = make_desc_sw128_sbo(0, 1024);
+        const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32), lo0 = (uint32_t)da0;
+        uint32_t sa = 0, pa = 0, sb = 0, pb = 0, t = 0;
+        if (p.b_resident) { tc::mbar_wait(w_full, 0); tc::tc_fence_after(); }
+        const int rev = p.halo_rev;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-            const int cls = tile / (p.n_tiles * p.tiles_x * p.tiles_y * p.N);
-            const int cnt = p.cls_count[cls];
+            const int cls = p.n_classes == 1 ? 0 : tile / p.per_class;
+            const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
             const uint32_t as = t & 1;
             tc::mbar_wait(acc_empty + 8 * as, ((t >> 1) & 1) ^ 1);
             tc::tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * 256;
-            for (int i = 0; i < cnt; ++i, ++it) {
-                const uint32_t s = it % STAGES;
-                tc::mbar_wait(full + 8 * s, (it / STAGES) & 1);
-                tc::tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t a_lo = lo0 + ((smem_base + s * STAGE_BYTES) >> 4);
-                    const uint32_t b_lo = a_lo + (C::A_BYTES >> 4);
-                    if (i == 0) tc::umma_f16_split<false>(d_tmem, a_lo, hi, b_lo, hi, idesc);
-                    else tc::umma_f16_split<true>(d_tmem, a_lo, hi, b_lo, hi, idesc);
+            if (p.halo) {
+                for (int i = 0; i < cnt; i += 9) {
+                    tc::mbar_wait(a_full + 8 * sa, pa);
+                    tc::tc_fence_after();
+                    const uint32_t a_tile = lo0 + ((smem_base + sa * A_SLOT) >> 4);
+                    if (p.b_resident) {
+                        // the whole chunk (9 taps x 4 K-steps) is issued by one elected lane as straight-line code
+                        if (elect_one()) {
+                            const uint32_t b_tile = lo0 + ((b_base + (uint32_t)(i0 + i) * B_SLOT) >> 4);
 #pragma unroll
-                    for (int k = 1; k < 4; ++k) tc::umma_f16_split<true>(d_tmem, a_lo + k * 2, hi, b_lo + k * 2, hi, idesc);
-                    tc::umma_commit(empty + 8 * s);
-                    if (i == cnt - 1) tc::umma_commit(acc_full + 8 * as);
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int hy = tap / 3, hx = tap - hy * 3;
+                                const uint32_t off_f = (uint32_t)(hy * C::HALO_W + hx) * 8, off_r = (uint32_t)((2 - hy) * C::HALO_W + (2 - hx)) * 8;
+                                const uint32_t a_lo = a_tile + (rev ? off_r : off_f);
+                                const uint32_t b_lo = b_tile + (uint32_t)tap * (B_SLOT >> 4);
+                                if (tap == 0 && i == 0) tc::umma_f16_split<false>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
+                                else tc::umma_f16_split<true>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
+                                if (!(dbg & 1)) {
+#pragma unroll
+                                    for (int k = 1; k < 4; ++k) tc::umma_f16_split<true>(d_tmem, a_lo + k * 2, a_hi, b_lo + k * 2, b_hi, idesc);
+                                }
+                            }
+                            tc::umma_commit(a_empty + 8 * sa);
+                            if (i + 9 >= cnt) tc::umma_commit(acc_full + 8 * as);
+                        }
+                        __syncwarp();
+                    } else {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            tc::mbar_wait(b_full + 8 * sb, pb);
+                            tc::tc_fence_after();
+                            if (elect_one()) {
+                                const int hy = tap / 3, hx = tap - hy * 3;
+                                const uint32_t off_f = (uint32_t)(hy * C::HALO_W + hx) * 8, off_r = (uint32_t)((2 - hy) * C::HALO_W + (2 - hx)) * 8;
+                                const uint32_t a_lo = a_tile + (rev ? off_r : off_f);
+                                const uint32_t b_lo = lo0 + ((b_base + sb * B_SLOT) >> 4);
+                                if (tap == 0 && i == 0) tc::umma_f16_split<false>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
+                                else tc::umma_f16_split<true>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
+                                if (!(dbg & 1)) {
+#pragma unroll
+                                    for (int k = 1; k < 4; ++k) tc::umma_f16_split<true>(d_tmem, a_lo + k * 2, a_hi, b_lo + k * 2, b_hi, idesc);
+                                }
+                                tc::umma_commit(b_empty + 8 * sb);
+                                if (tap == 8) {
+                                    tc::umma_commit(a_empty + 8 * sa);
+                                    if (i + 9 >= cnt) tc::umma_commit(acc_full + 8 * as);
+                                }
+                            }
+                            __syncwarp();
+                            if (++sb == NB) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                    if (++sa == NA) { sa = 0; pa ^= 1; }
                 }
-                __syncwarp();
+            } else {
+                for (int i = 0; i < cnt; ++i) {
+                    tc::mbar_wait(a_full + 8 * sa, pa);
+                    tc::tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_lo = lo0 + ((smem_base + sa * A_SLOT) >> 4);
+                        const uint32_t b_lo = lo0 + ((b_base + sa * B_SLOT) >> 4);
+                        if (i == 0) tc::umma_f16_split<false>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
+                        else tc::umma_f16_split<true>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
+                        if (!(dbg & 1)) {
+#pragma unroll
+                            for (int k = 1; k < 4; ++k) tc::umma_f16_split<true>(d_tmem, a_lo + k * 2, a_hi, b_lo + k * 2, b_hi, idesc);
+                        }
+                        tc::umma_commit(a_empty + 8 * sa);
+                        if (i == cnt - 1) tc::umma_commit(acc_full + 8 * as);
+                    }
+                    __syncwarp();
+                    if (++sa == NA) { sa = 0; pa ^= 1; }
+                }
             }
         }
     } else {
@@ -174,11 +310,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
         const int groups = p.BN >> 6;      // 0 in thin mode
         uint32_t t = 0, sg = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-            int r = tile;
-            const int nt = r % p.n_tiles; r /= p.n_tiles;
-            const int tx = r % p.tiles_x; r /= p.tiles_x;
-            const int ty = r % p.tiles_y; r /= p.tiles_y;
-            const int n = r % p.N, cls = r / p.N;
+            CONVG_DECODE_TILE(tile, nt, tx, ty, n, cls)
             const uint32_t as = t & 1;
             tc::mbar_wait(acc_full + 8 * as, (t >> 1) & 1);
             tc::tc_fence_after();
@@ -199,7 +331,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
                     }
                 }
             }
-            for (int g = 0; g < groups; ++g, ++sg) {
+            for (int g = 0; g < ((dbg & 2) ? 0 : groups); ++g, ++sg) {
                 const uint32_t buf = out_s + (sg & 1) * C::OUT_BYTES;
                 if (et == 0) tc::bulk_wait_read<1>();            // the store that used this buffer two groups ago has read it
                 tc::epi_bar();
@@ -220,9 +352,9 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
                         *reinterpret_cast<uint4*>(smem + (buf - smem_base) + row * 128 + ((chunk ^ (row & 7)) << 4)) = ov;
                     }
                 }
-                tc::fence_proxy_async();
+                if (!(dbg & 4)) tc::fence_proxy_async();
                 tc::epi_bar();
-                if (et == 0) {
+                if (et == 0 && !(dbg & 4)) {
                     tc::tma_store_5d(&tmap_out, buf, p.cls_out_c[cls] + ch0, tx * p.tw, p.cls_out_py[cls], ty * p.th, n);
                     tc::bulk_commit();
                 }
@@ -318,34 +450,43 @@ inline int convg_make_plan(ConvGPlan& pl, int kind, int role, int n, int h, int 
     pl.grid_w = family == 1 ? pl.in_w / 2 : pl.in_w;
     const int ntap = kind == CONVG_P1S2 ? 1 : 9;
     int ni = 0;
-    auto add_item = [&](int src, int csrc_total, int c, int px, int dx, int py, int dy, int wsel, int tap, int k0) {
+    int overflow = 0;
+    auto add_item = [&](int src, int csrc_total, int c, int px, int dx, int py, int dy, int wsel, int tap, int k0, int new_a, int last_a,
+                        int a_off16) {
         ConvGItem& it = pl.p.items[ni];
         it.c_inner = px * csrc_total + c;
         it.dx = dx;
-        it.dyps = (dy & 0xffff) | (py << 16) | (src << 20);
+        it.dyps = (dy & 0xffff) | (py << 16) | (src << 20) | (new_a << 24) | (last_a << 25);
         it.wk = ni;
+        it.a_off16 = a_off16;
         pl.pack[ni].wsel_tap = (wsel << 8) | tap;
         pl.pack[ni].k0 = k0;
         ++ni;
     };
-    // one tap of one source: all its 64-channel chunks
+    // one tap of one source: all its 64-channel chunks, each with its own A box
     auto add_tap = [&](int src, int px, int dx, int py, int dy, int wsel, int tap, int kbase) -> int {
         for (int c = 0; c < ksrc[src]; c += 64) {
             if (ni >= 128) return 1;
-            add_item(src, ksrc[src], c, px, dx, py, dy, wsel, tap, kbase + c);
+            add_item(src, ksrc[src], c, px, dx, py, dy, wsel, tap, kbase + c, 1, 1, 0);
         }
         return 0;
     };
-    int overflow = 0;
     if (family == 0) {
+        // halo mode: ONE 18x10-pixel A tile per 64-channel chunk serves the nine taps (descriptor start offsets into the halo)
         pl.p.n_classes = 1;
         pl.p.cls_start[0] = 0;
-        for (int ky = 0; ky < 3; ++ky)
-            for (int kx = 0; kx < 3; ++kx) {
-                const int dy = role == 0 ? ky - 1 : 1 - ky, dx = role == 0 ? kx - 1 : 1 - kx;
-                overflow |= add_tap(0, 0, dx, 0, dy, 0, ky * 3 + kx, 0);
-                if (ksrc[1]) overflow |= add_tap(1, 0, dx, 0, dy, 0, ky * 3 + kx, cin0);
-            }
+        pl.p.halo = 1;
+        pl.p.halo_rev = role;
+        for (int src = 0; src < 2; ++src)
+            for (int c = 0; c < ksrc[src]; c += 64)
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int kx = 0; kx < 3; ++kx) {
+                        if (ni >= 128) { overflow = 1; break; }
+                        const int hy = role == 0 ? ky : 2 - ky, hx = role == 0 ? kx : 2 - kx;     // position of the tap inside the halo
+                        const int tap = ky * 3 + kx;
+                        add_item(src, ksrc[src], c, 0, -1, 0, -1, 0, tap, (src ? cin0 : 0) + c, tap == 0, tap == 8,
+                                 (hy * ConvGCfg::HALO_W + hx) * 8);
+                    }
         pl.p.cls_count[0] = ni;
     } else if (family == 1) {
         pl.p.n_classes = 1;
@@ -389,9 +530,6 @@ inline int convg_make_plan(ConvGPlan& pl, int kind, int role, int n, int h, int 
     int BN = 16;                       // largest multiple of 64 that is <= 256 and divides the output channels
     if (!thin) for (BN = 256; nout % BN; BN -= 64) {}
     pl.p.thin = thin ? 1 : 0;
-    pl.p.stage_bytes = ConvGCfg::A_BYTES + ((BN * 128 + 1023) / 1024) * 1024;
-    pl.p.stages = ConvGCfg::RING_BYTES / pl.p.stage_bytes;
-    if (pl.p.stages > ConvGCfg::MAX_STAGES) pl.p.stages = ConvGCfg::MAX_STAGES;
     static const int shapes[4][2] = {{8, 16}, {4, 32}, {2, 64}, {1, 128}};
     long long best = -1; int bi = 0;
     for (int i = 0; i < 4; ++i) {
@@ -399,9 +537,40 @@ inline int convg_make_plan(ConvGPlan& pl, int kind, int role, int n, int h, int 
         if (best < 0 || tiles < best) { best = tiles; bi = i; }
     }
     pl.p.th = shapes[bi][0]; pl.p.tw = shapes[bi][1];
+    if (pl.p.halo) { pl.p.th = 16; pl.p.tw = 8; }
     pl.p.tiles_y = cdiv(pl.grid_h, pl.p.th); pl.p.tiles_x = cdiv(pl.grid_w, pl.p.tw);
     pl.p.N = n; pl.p.BN = BN; pl.p.n_tiles = nout / BN;
     pl.p.total_tiles = pl.p.n_classes * n * pl.p.tiles_y * pl.p.tiles_x * pl.p.n_tiles;
+    pl.p.per_class = n * pl.p.tiles_y * pl.p.tiles_x * pl.p.n_tiles;
+    {
+        const int divs[4] = {pl.p.n_tiles, pl.p.tiles_x, pl.p.tiles_y, n};
+        for (int i = 0; i < 4; ++i) {
+            const unsigned d = (unsigned)divs[i];
+            unsigned lg = 0;
+            while ((1u << lg) < d) ++lg;                 // ceil(log2 d)
+            const unsigned pw = 31 + lg;
+            pl.p.div_mul[i] = d <= 1 ? 0u : (unsigned)(((1ull << pw) + d - 1) / d);
+            pl.p.div_shr[i] = d <= 1 ? 0u : pw - 32;
+        }
+    }
+    // operand rings
+    const int b_tile = ((BN * 128 + 1023) / 1024) * 1024;
+    pl.p.b_slot_bytes = b_tile;
+    if (pl.p.halo) {
+        pl.p.a_slot_bytes = ConvGCfg::HALO_SLOT; pl.p.a_tx_bytes = ConvGCfg::HALO_BYTES;
+        if (pl.p.n_tiles == 1 && ni * b_tile <= 96 * 1024) {
+            pl.p.b_resident = 1; pl.p.n_b = 0;
+            pl.p.n_a = (ConvGCfg::RING_BYTES - ni * b_tile) / ConvGCfg::HALO_SLOT;
+        } else {
+            pl.p.n_a = BN >= 256 ? 2 : 3;
+            pl.p.n_b = (ConvGCfg::RING_BYTES - pl.p.n_a * ConvGCfg::HALO_SLOT) / b_tile;
+        }
+    } else {
+        pl.p.a_slot_bytes = pl.p.a_tx_bytes = ConvGCfg::A_BYTES;
+        pl.p.n_a = pl.p.n_b = ConvGCfg::RING_BYTES / (ConvGCfg::A_BYTES + b_tile);
+    }
+    if (pl.p.n_a > ConvGCfg::MAX_STAGES) pl.p.n_a = ConvGCfg::MAX_STAGES;
+    if (pl.p.n_b > ConvGCfg::MAX_STAGES) pl.p.n_b = ConvGCfg::MAX_STAGES;
     return 0;
 }
 
@@ -473,8 +642,9 @@ inline int launch_convg(const ConvGPlan& pl, const bf16* x0, const bf16* x1, con
     PTTA_CHECK(x0 && packed && (out || pl.p.thin) && (x1 || !pl.k_src[1]), "convg: null operand");
     CUtensorMap ta0, ta1, tb, to;
     const ConvGParams& p = pl.p;
-    PTTA_TRY(make_tmap_view5(&ta0, x0, p.N, pl.in_h, pl.in_w, pl.k_src[0], pl.in_parity, p.th, p.tw));
-    if (pl.k_src[1]) PTTA_TRY(make_tmap_view5(&ta1, x1, p.N, pl.in_h, pl.in_w, pl.k_src[1], pl.in_parity, p.th, p.tw));
+    const int ath = p.halo ? ConvGCfg::HALO_H : p.th, atw = p.halo ? ConvGCfg::HALO_W : p.tw;
+    PTTA_TRY(make_tmap_view5(&ta0, x0, p.N, pl.in_h, pl.in_w, pl.k_src[0], pl.in_parity, ath, atw));
+    if (pl.k_src[1]) PTTA_TRY(make_tmap_view5(&ta1, x1, p.N, pl.in_h, pl.in_w, pl.k_src[1], pl.in_parity, ath, atw));
     else ta1 = ta0;
     PTTA_TRY(make_tmap_wpk(&tb, packed, pl.n_items, pl.n_out, p.BN));
     if (p.thin) to = ta0;

@@ -33,6 +33,11 @@ int ptta_convg_run(int kind, int role, const void* x0, const void* x1, const voi
     return launch_convg(pl, (const bf16*)x0, (const bf16*)x1, (const bf16*)packed, bias, (bf16*)out, (cudaStream_t)stream);
 }
 
+int ptta_convg_debug_set(int mask) {
+    PTTA_CUDA(cudaMemcpyToSymbol(g_convg_dbg, &mask, sizeof(int)));
+    return 0;
+}
+
 int ptta_convg_run_thin(const void* x0, const void* x1, const void* packed, const float* bias, float* const* planes, const long long* nstrides,
                         const int* acts, int n_real, int n, int h, int w, int cin0, int cin1, ptta_stream_t stream) {
     ConvGPlan pl;

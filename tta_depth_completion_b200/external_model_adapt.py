@@ -322,7 +322,7 @@ class MsgChnModel_Adapt(object):
 
 
 class ExternalModel_Adapt(object):
-    """src/external_model_adapt.py:29-660, restricted to the TTA hot path (MSG-CHN; 'adapt' losses)."""
+    """src/external_model_adapt.py:29-660, restricted to the TTA hot path (MSG-CHN and NLSPN back-ends; 'adapt' losses)."""
 
     def __init__(self, model_name, min_predict_depth, max_predict_depth, max_input_depth=None, offset=False, from_scratch=False,
                  dataset_name=None, device=torch.device('cuda')):
@@ -333,8 +333,12 @@ class ExternalModel_Adapt(object):
         self.max_input_depth = max_input_depth
         if model_name == 'msg_chn':
             self.model = MsgChnModel_Adapt(device=self.device, max_predict_depth=max_predict_depth)
-        elif model_name == 'nlspn' or 'costdcnet' in model_name:
-            raise NotImplementedError('%s has no native back-end yet (DESIGN.md, scope table)' % model_name)
+        elif model_name == 'nlspn':
+            from .nlspn_model_adapt import NLSPNModel_Adapt
+            self.model = NLSPNModel_Adapt(device=self.device, max_depth=max_predict_depth, offset=offset, dataset_name=dataset_name,
+                                          from_scratch=from_scratch)
+        elif 'costdcnet' in model_name:
+            raise NotImplementedError('%s has no native back-end (needs MinkowskiEngine; DESIGN.md, out of scope)' % model_name)
         else:
             raise ValueError('Unsupported depth completion model: {}'.format(model_name))
 
@@ -359,7 +363,11 @@ class ExternalModel_Adapt(object):
                    w_loss_smoothness=1.0, w_loss_cos=1.0):
         """src/external_model_adapt.py:371-441 (the clamp of :191-193 is applied inside the loss kernel)."""
         eng = self.model._engine_for(input_rgb)
-        loss, parts = _LossFn.apply(eng, output_depth, embedding, reference, input_rgb.contiguous(), sparse_depth.contiguous(),
+        if self.model_name == 'nlspn':
+            from .nlspn_model_adapt import _NlspnLossFn as loss_fn
+        else:
+            loss_fn = _LossFn
+        loss, parts = loss_fn.apply(eng, output_depth, embedding, reference, input_rgb.contiguous(), sparse_depth.contiguous(),
                                     validity_map.contiguous(), self.max_input_depth, float(w_loss_sparse_depth),
                                     float(w_loss_smoothness), float(w_loss_cos))
         info = {'loss': loss.detach(), 'loss_sparse_depth': parts[0], 'loss_smooth': parts[1], 'loss_cos': parts[2]}
@@ -375,6 +383,12 @@ class ExternalModel_Adapt(object):
         """One whole adaptation step (src/tta_main.py:583-633) in a single library call; returns nothing -- read
         `last_losses()` when the values are needed (that read synchronises)."""
         eng = self.model._engine_for(image_raw)
+        if self.model_name == 'nlspn':
+            eng.set_image_normalization(getattr(self.model, 'img_scale', None), getattr(self.model, 'img_shift', None))
+            eng.tta_step(image_raw, image_raw, sparse_depth, learning_rate, w_loss_sparse_depth, w_loss_smoothness, w_loss_cos,
+                         self.max_input_depth, graph=graph)
+            self._last_engine = eng
+            return
         hyper = (learning_rate, betas, eps, weight_decay)
         if getattr(eng, '_hyper', None) != hyper:
             eng.set_adam(learning_rate, betas, eps, weight_decay, step_count=-1)
@@ -388,6 +402,8 @@ class ExternalModel_Adapt(object):
 
     def last_output(self):
         e = self._last_engine
+        if self.model_name == 'nlspn':
+            return e.B['output']
         return e.tensor('output').view(e.n, 1, e.h, e.w)
 
     # -- plumbing identical to the reference ---------------------------------------------------------------------

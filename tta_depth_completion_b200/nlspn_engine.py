@@ -40,7 +40,7 @@ def adapt_parameter_names(sd):
 
 
 class NlspnEngine:
-    def __init__(self, state_dict, n, h, w, device, prop_time=18, legacy=True):
+    def __init__(self, state_dict, n, h, w, device, prop_time=18, legacy=True, share_from=None):
         if h % 16 or w % 16:
             raise NotImplementedError('NLSPN engine: H and W must be multiples of 16 (got %dx%d)' % (h, w))
         _lib.lib()
@@ -49,11 +49,21 @@ class NlspnEngine:
         self.prop_time, self.legacy = prop_time, legacy
         self.launches = 0
         self.B = {}            # named activation / gradient buffers
-        sd = {k: v.detach().to(self.dev).contiguous() for k, v in state_dict.items()}
-        self.sd = sd
-        self._build_flat(sd)
-        self._build_convs()
-        self._build_heads()
+        if share_from is not None:
+            # another input shape of the same model: parameters, packed operands and optimiser state are shared
+            o = share_from
+            self.sd, self.adapt_names, self.layout, self.params, self.grads = o.sd, o.adapt_names, o.layout, o.params, o.grads
+            self.flat_p, self.flat_g, self.flat_m, self.flat_v = o.flat_p, o.flat_g, o.flat_m, o.flat_v
+            self.fused_bn_w, self.fused_bn_b = o.fused_bn_w, o.fused_bn_b
+            self.C, self.w_dec1, self.w_dec0, self.b_dec0, self.head_w = o.C, o.w_dec1, o.w_dec0, o.b_dec0, o.head_w
+            self.bn_state = {}
+            sd = self.sd
+        else:
+            sd = {k: v.detach().to(self.dev).contiguous() for k, v in state_dict.items()}
+            self.sd = sd
+            self._build_flat(sd)
+            self._build_convs()
+            self._build_heads()
         blocks = _lib.lib().ptta_nl_reduce_blocks(1 << 30, 64)
         self.partial = torch.empty(2 * 1024 * blocks, dtype=torch.float32, device=self.dev)
         self.coef = torch.empty(3 * 1024, dtype=torch.float32, device=self.dev)
@@ -66,7 +76,7 @@ class NlspnEngine:
         self.aff_scale = float(sd['prop_layer.aff_scale_const'])
         self.adam_hyper = torch.tensor([0.0, 0.9, 0.999, 1e-8, 0.0], dtype=torch.float64, device=self.dev)
         self._adam_host = None
-        self.adam_step_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.adam_step_dev = share_from.adam_step_dev if share_from is not None else torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._graph, self._graph_key, self._seen_key = None, None, None
 
     # ---- parameters -------------------------------------------------------------------------------------------------------------
@@ -241,6 +251,10 @@ class NlspnEngine:
     def set_image_normalization(self, scale, shift):
         """network input = image * scale + shift per channel, applied inside the stem kernel (None: the caller passes the
         normalised image, as the reference's forward() expects)"""
+        key = (None if scale is None else tuple(scale), None if shift is None else tuple(shift))
+        if getattr(self, '_norm_key', ()) == key:
+            return
+        self._norm_key = key
         self.img_scale = None if scale is None else torch.tensor(scale, dtype=torch.float32, device=self.dev)
         self.img_shift = None if shift is None else torch.tensor(shift, dtype=torch.float32, device=self.dev)
 
@@ -335,6 +349,7 @@ class NlspnEngine:
     def forward(self, image, sparse_depth, training=True):
         """image: normalised fp32 NCHW; sparse_depth fp32 [N,1,H,W] (already clamped).  Returns (output, emb, ref) in training,
         output otherwise; all device tensors owned by the engine."""
+        self._depth = sparse_depth
         fe = self.encoder('r.', image, sparse_depth)
         self.fe = fe
         out = self.decoder(fe, sparse_depth)
@@ -362,13 +377,25 @@ class NlspnEngine:
 
     # ---- backward -----------------------------------------------------------------------------------------------------------------
     def backward(self, gscale=1.0):
-        L, sd, N, H, W, B = _lib.lib(), self.sd, self.N, self.H, self.W, self.B
+        self.loss_backward(gscale)
+        self.network_backward()
+
+    def loss_backward(self, gscale=1.0):
+        """d loss / d output -> B['g.out'] (fp32 [N,1,H,W]) and d loss / d ref -> B['g.ref'] (bf16 [R,1024])"""
+        L, N, H, W, B = _lib.lib(), self.N, self.H, self.W, self.B
         image_raw, sparse, validity, cap, w_sd, w_sm = self._loss_args
-        fe1, fe2, fe3, fe4, fe5, fe6 = self.fe
         g_out = self.buf('g.out', (N, 1, H, W), torch.float32)
         g_ref = self.buf('g.ref', (self.R, 1024))
         check(L.ptta_tta_loss_backward(ptr(B['output']), ptr(image_raw), ptr(sparse), ptr(validity), cap, ptr(self.emb), ptr(self.ref), self.R, 1024,
                                        w_sd, w_sm, ptr(self.loss_ws), gscale, ptr(g_out), ptr(g_ref), N, H, W, _stream()), 'tta_loss_backward')
+        self.launches += 2
+
+    def network_backward(self):
+        """from (B['g.out'], B['g.ref']) to the gradients of the 88 adapted tensors (flat_g)"""
+        L, sd, N, H, W, B = _lib.lib(), self.sd, self.N, self.H, self.W, self.B
+        fe1, fe2, fe3, fe4, fe5, fe6 = self.fe
+        g_out = self.buf('g.out', (N, 1, H, W), torch.float32)
+        g_ref = self.buf('g.ref', (self.R, 1024))
         g_y = self.buf('g.y', (N, 1, H, W), torch.float32)
         check(L.ptta_nl_mask_pos(ptr(g_out), ptr(B['y']), ptr(g_y), g_y.numel(), _stream()), 'nl_mask_pos')
         g_init = self.buf('g.pred_init', (N, 1, H, W), torch.float32)
@@ -386,7 +413,7 @@ class NlspnEngine:
         T = self.buf('g.thin', (N, H, W, 64))
         check(L.ptta_nl_thin_grad_pack(ptr(g_init), ptr(B['pred_init']), ptr(g_guide), ptr(g_conf), ptr(B['confidence']), ptr(T), N, H, W, _stream()),
               'nl_thin_grad_pack')
-        self.launches += 7 + self.prop_time
+        self.launches += 5 + self.prop_time
         # thin heads -> d(F | fe1)
         dcat1 = self.conv('dec0.d', T, out_name='g.cat1', hw=(H, W))                                   # [N,H,W,256]
         gw, _ = self._fused_dec1_params()
