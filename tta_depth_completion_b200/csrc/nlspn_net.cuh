@@ -153,11 +153,21 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const bf16* __restrict
     }
 }
 
-// one warp per channel: lanes stride over the partial blocks, double accumulation, fixed-order shuffle tree (deterministic)
-__device__ __forceinline__ void partial_sums(const float* __restrict__ partial, int nblk, int C, int c, int lane, double& s, double& q) {
+// 256 threads = 8 block-slices x 32 channels: every warp load is one coalesced 128 B row of the partial table; the slices are
+// combined through shared memory in a fixed order (deterministic).  Returns the totals to the threads of slice 0.
+__device__ __forceinline__ bool partial_sums(const float* __restrict__ partial, int nblk, int C, int& c, double& s, double& q) {
+    __shared__ double sh[2][8][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    c = blockIdx.x * 32 + lane;
     s = 0.0; q = 0.0;
-    for (int b = lane; b < nblk; b += 32) { s += (double)partial[((size_t)b * 2) * C + c]; q += (double)partial[((size_t)b * 2 + 1) * C + c]; }
-    s = warp_sum_d(s); q = warp_sum_d(q);
+    if (c < C)
+        for (int b = slice; b < nblk; b += 8) { s += (double)partial[((size_t)b * 2) * C + c]; q += (double)partial[((size_t)b * 2 + 1) * C + c]; }
+    sh[0][slice][lane] = s; sh[1][slice][lane] = q;
+    __syncthreads();
+    if (slice != 0 || c >= C) return false;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { s += sh[0][k][lane]; q += sh[1][k][lane]; }
+    return true;
 }
 
 __global__ void __launch_bounds__(256) bn_finalize2_kernel(const float* __restrict__ partial, int nblk, long long count, int C,
@@ -165,11 +175,9 @@ __global__ void __launch_bounds__(256) bn_finalize2_kernel(const float* __restri
                                                            float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
                                                            float* __restrict__ shift, float* __restrict__ run_mean, float* __restrict__ run_var,
                                                            long long* __restrict__ nbt, float momentum, float* __restrict__ sums_out) {
-    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (c >= C) return;
+    int c;
     double s, q;
-    partial_sums(partial, nblk, C, c, lane, s, q);
-    if (lane != 0) return;
+    if (!partial_sums(partial, nblk, C, c, s, q)) return;
     if (sums_out) { sums_out[c] = (float)s; return; }          // plain column sums (bias gradients)
     const double m = s / (double)count;
     double var = q / (double)count - m * m;
@@ -190,11 +198,9 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize2_kernel(const float* __re
                                                                const float* __restrict__ gamma, const float* __restrict__ rstd,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ k0,
                                                                float* __restrict__ k1, float* __restrict__ k2) {
-    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (c >= C) return;
+    int c;
     double sg, sgx;
-    partial_sums(partial, nblk, C, c, lane, sg, sgx);
-    if (lane != 0) return;
+    if (!partial_sums(partial, nblk, C, c, sg, sgx)) return;
     if (dgamma) dgamma[c] = (float)sgx;
     if (dbeta) dbeta[c] = (float)sg;
     const float a = gamma[c] * rstd[c];
