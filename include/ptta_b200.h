@@ -211,6 +211,12 @@ size_t ptta_nl_wgrad48_workspace_bytes(void);
 int ptta_nl_wgrad48(const void* x_bf16_c64, const void* gout_bf16_c64, float* dw_48x48x3x3, void* workspace, int n, int h, int w,
                     ptta_stream_t stream);
 
+/* evaluation metrics on the device (src/eval_utils.py:117-175 as used by src/tta_main.py:760-798): mask = gt > 0 and
+ * min_depth <= gt <= max_depth; result5 (device) = {MAE [mm], RMSE [mm], iMAE [1/km], iRMSE [1/km], evaluated pixels} */
+size_t ptta_eval_metrics_workspace_bytes(void);
+int ptta_eval_metrics(const float* output_depth, const float* ground_truth, long long n, float min_depth, float max_depth,
+                      void* workspace, float* result5, ptta_stream_t stream);
+
 /* ---- MSG-CHN ProxyTTA engine ------------------------------------------------------------------- */
 /* prepare_mode: the reference's string, e.g. "meta_selfsup_seq_2layers_ema" (network_exp_msg_chn_adapt.py:1022-1087) */
 int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepare_mode);

@@ -180,4 +180,16 @@ int ptta_nl_wgrad48(const void* x, const void* gout, float* dw, void* workspace,
     return check_launch("nl_wgrad48_reduce");
 }
 
+size_t ptta_eval_metrics_workspace_bytes(void) { return 296 * 5 * sizeof(double); }
+
+int ptta_eval_metrics(const float* output_depth, const float* ground_truth, long long n, float min_depth, float max_depth, void* workspace,
+                      float* result5, ptta_stream_t stream) {
+    PTTA_CHECK(output_depth && ground_truth && workspace && result5 && n > 0, "eval_metrics: bad arguments");
+    int blocks = (int)(cdiv(n, 256) < 296 ? cdiv(n, 256) : 296);
+    eval_metrics_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(output_depth, ground_truth, n, min_depth, max_depth, (double*)workspace);
+    PTTA_TRY(check_launch("eval_metrics"));
+    eval_metrics_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const double*)workspace, blocks, result5);
+    return check_launch("eval_metrics_finalize");
+}
+
 }  // extern "C"

@@ -467,4 +467,40 @@ __global__ void __launch_bounds__(256) wgrad48_reduce_kernel(const float* __rest
     dw[(co * 48 + ci) * 9 + tap] = s;
 }
 
+// ---- evaluation metrics on the device (src/eval_utils.py:117-175 as used by src/tta_main.py:760-798) ------------------------------
+// mask = gt > 0 and min <= gt <= max; MAE / RMSE on 1000*depth (mm), iMAE / iRMSE on 1 / (0.001*depth + 1e-9) (1/km)
+// partial[blk][5] (double): sum |d|, sum d^2, sum |id|, sum id^2, count
+__global__ void __launch_bounds__(256) eval_metrics_kernel(const float* __restrict__ out, const float* __restrict__ gt, long long n, float min_d,
+                                                           float max_d, double* __restrict__ partial) {
+    __shared__ double sh[32];
+    double a = 0.0, b = 0.0, c = 0.0, d = 0.0, cnt = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float g = gt[i], o = out[i];
+        if (g > 0.f && !(g < min_d) && !(g > max_d)) {
+            const float e = 1000.f * g - 1000.f * o;
+            const float ie = 1.f / (0.001f * g + 1e-9f) - 1.f / (0.001f * o + 1e-9f);
+            a += (double)fabsf(e); b += (double)(e * e); c += (double)fabsf(ie); d += (double)(ie * ie); cnt += 1.0;
+        }
+    }
+    const double r0 = block_sum_d(a, sh), r1 = block_sum_d(b, sh), r2 = block_sum_d(c, sh), r3 = block_sum_d(d, sh), r4 = block_sum_d(cnt, sh);
+    if (threadIdx.x == 0) {
+        double* o5 = partial + (size_t)blockIdx.x * 5;
+        o5[0] = r0; o5[1] = r1; o5[2] = r2; o5[3] = r3; o5[4] = r4;
+    }
+}
+// result[5] (float): mae, rmse, imae, irmse, number of evaluated pixels
+__global__ void __launch_bounds__(256) eval_metrics_finalize_kernel(const double* __restrict__ partial, int nblk, float* __restrict__ result) {
+    __shared__ double sh[32];
+    double v[5] = {0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x)
+        for (int k = 0; k < 5; ++k) v[k] += partial[(size_t)b * 5 + k];
+    double t[5];
+    for (int k = 0; k < 5; ++k) t[k] = block_sum_d(v[k], sh);
+    if (threadIdx.x == 0) {
+        const double c = t[4];
+        result[0] = (float)(t[0] / c); result[1] = (float)sqrt(t[1] / c); result[2] = (float)(t[2] / c); result[3] = (float)sqrt(t[3] / c);
+        result[4] = (float)c;
+    }
+}
+
 }  // namespace ptta

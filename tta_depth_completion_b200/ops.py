@@ -234,3 +234,20 @@ def adam_flat(param, grad, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), ep
         _need(t, torch.float32, 'adam tensor')
     check(_lib.lib().ptta_adam_flat(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, betas[0], betas[1], eps,
                                     weight_decay, step, _stream()), 'adam_flat')
+
+
+def eval_metrics(output_depth, ground_truth, min_depth, max_depth):
+    """MAE / RMSE (mm) and iMAE / iRMSE (1/km) over the pixels with min_depth <= gt <= max_depth, gt > 0, computed on the device
+    (src/eval_utils.py:117-175 as called from src/tta_main.py:760-798; the reference moves both maps to the CPU first).
+    Returns a dict of floats (one 20-byte D2H read)."""
+    _need(output_depth, torch.float32, 'output_depth')
+    _need(ground_truth, torch.float32, 'ground_truth')
+    if output_depth.numel() != ground_truth.numel():
+        raise ValueError('output_depth and ground_truth differ in size')
+    L = _lib.lib()
+    ws = torch.empty(L.ptta_eval_metrics_workspace_bytes(), dtype=torch.uint8, device=output_depth.device)
+    res = torch.empty(5, dtype=torch.float32, device=output_depth.device)
+    check(L.ptta_eval_metrics(ptr(output_depth), ptr(ground_truth), output_depth.numel(), float(min_depth), float(max_depth), ptr(ws), ptr(res),
+                              _stream()), 'eval_metrics')
+    v = res.cpu()
+    return {'mae': float(v[0]), 'rmse': float(v[1]), 'imae': float(v[2]), 'irmse': float(v[3]), 'count': int(v[4])}
