@@ -66,6 +66,9 @@ class NlspnEngine:
             self._build_heads()
         blocks = _lib.lib().ptta_nl_reduce_blocks(1 << 30, 64)
         self.partial = torch.empty(2 * 1024 * blocks, dtype=torch.float32, device=self.dev)
+        self.partial_z = torch.empty_like(self.partial)      # reduction scratch of the zero-image branch (runs on its own stream)
+        self.side_stream = torch.cuda.Stream(self.dev)
+        self.two_streams = True
         self.coef = torch.empty(3 * 1024, dtype=torch.float32, device=self.dev)
         self.scratch_c = torch.empty(1024, dtype=torch.float32, device=self.dev)
         self.R = n * (h // 16) * (w // 16)
@@ -211,7 +214,8 @@ class NlspnEngine:
             st = {k: torch.empty(c, dtype=torch.float32, device=self.dev) for k in ('mean', 'rstd', 'scale', 'shift')}
             self.bn_state[bn] = st
         rm, rv, nbt = running if running is not None else (None, None, None)
-        check(_lib.lib().ptta_nl_bn_stats(ptr(x), c, rows, c, ptr(gamma), ptr(beta), BN_EPS, ptr(self.partial), ptr(st['mean']), ptr(st['rstd']),
+        partial = self.partial_z if bn.startswith('z.') else self.partial
+        check(_lib.lib().ptta_nl_bn_stats(ptr(x), c, rows, c, ptr(gamma), ptr(beta), BN_EPS, ptr(partial), ptr(st['mean']), ptr(st['rstd']),
                                           ptr(st['scale']), ptr(st['shift']), ptr(rm), ptr(rv), ptr(nbt), 0.1, _stream()), 'nl_bn_stats')
         self.launches += 2
         return st
@@ -350,16 +354,26 @@ class NlspnEngine:
         """image: normalised fp32 NCHW; sparse_depth fp32 [N,1,H,W] (already clamped).  Returns (output, emb, ref) in training,
         output otherwise; all device tensors owned by the engine."""
         self._depth = sparse_depth
+        if not training:
+            fe = self.encoder('r.', image, sparse_depth)
+            self.fe = fe
+            return self.decoder(fe, sparse_depth)
+        # the zero-image branch (nlspnmodel_adapt.py:905-914) and its heads depend only on the sparse depth and frozen / already
+        # packed weights: they run on a second stream, concurrently with the real branch (fork / join through events, also inside a
+        # CUDA-graph capture); their small layers fill the SMs the real branch's small layers leave idle
+        main = torch.cuda.current_stream()
+        side = self.side_stream if self.two_streams else main
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            fe_z = self.encoder('z.', None, sparse_depth)
+            emb = self.mlp('z.', 'pred', self.mlp('z.', 'proj', fe_z[-1].view(self.R, 512)))
         fe = self.encoder('r.', image, sparse_depth)
         self.fe = fe
         out = self.decoder(fe, sparse_depth)
-        if not training:
-            return out
-        fe_z = self.encoder('z.', None, sparse_depth)                       # zero-image branch (nlspnmodel_adapt.py:905-914)
-        z_zero = fe_z[-1].view(self.R, 512)
-        z_real = fe[-1].view(self.R, 512)
-        emb = self.mlp('z.', 'pred', self.mlp('z.', 'proj', z_zero))
-        ref = self.mlp('r.', 'proj_t', z_real)
+        ref = self.mlp('r.', 'proj_t', fe[-1].view(self.R, 512))
+        if side is not main:
+            main.wait_stream(side)
         self.emb, self.ref = emb, ref
         return out, emb, ref
 
