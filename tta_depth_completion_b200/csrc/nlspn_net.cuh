@@ -21,6 +21,11 @@ __device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf162(u[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
 }
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf162(u[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
 __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
     uint4 v;
     v.x = pack_bf162(f[0], f[1]); v.y = pack_bf162(f[2], f[3]); v.z = pack_bf162(f[4], f[5]); v.w = pack_bf162(f[6], f[7]);
@@ -109,29 +114,49 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const bf16* __restrict
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
     if (MODE == 1) { load8f(mean + c0, mu); load8f(rstd + c0, rs); }
-    for (long long p = (long long)blockIdx.x * 32 + pl; p < P; p += (long long)gridDim.x * 32) {
-        float xv[8];
-        load8(x + p * ldx + c0, xv);
-        if (MODE == 0) {
+    // U pixels per iteration: all their loads are issued before the first use (the kernel is a latency-bound stream otherwise)
+    constexpr int U = MODE == 0 ? 4 : 2;
+    const long long stride = (long long)gridDim.x * 32;
+    for (long long p0 = (long long)blockIdx.x * 32 + pl; p0 < P; p0 += stride * U) {
+        uint4 rx[U], ra[U], rb[U], ry[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { s[j] += xv[j]; q[j] = fmaf(xv[j], xv[j], q[j]); }
-        } else {
-            float g[8];
-            load8(dyA + p * ldA + c0, g);
-            if (dyB) {
-                float b[8];
-                load8(dyB + p * ldB + c0, b);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] += b[j];
+        for (int u = 0; u < U; ++u) {
+            const long long p = p0 + u * stride;
+            const bool ok = p < P;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            rx[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + p * ldx + c0)) : z;
+            if (MODE == 1) {
+                ra[u] = ok ? __ldg(reinterpret_cast<const uint4*>(dyA + p * ldA + c0)) : z;
+                rb[u] = (ok && dyB) ? __ldg(reinterpret_cast<const uint4*>(dyB + p * ldB + c0)) : z;
+                ry[u] = (ok && act) ? __ldg(reinterpret_cast<const uint4*>(y + p * (long long)C + c0)) : z;
             }
-            if (act) {
-                float yv[8];
-                load8(y + p * (long long)C + c0, yv);
+        }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] *= act_der(yv[j], act);
+        for (int u = 0; u < U; ++u) {
+            if (p0 + u * stride >= P) break;
+            float xv[8];
+            unpack8(rx[u], xv);
+            if (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s[j] += xv[j]; q[j] = fmaf(xv[j], xv[j], q[j]); }
+            } else {
+                float g[8];
+                unpack8(ra[u], g);
+                if (dyB) {
+                    float b[8];
+                    unpack8(rb[u], b);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) g[j] += b[j];
+                }
+                if (act) {
+                    float yv[8];
+                    unpack8(ry[u], yv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) g[j] *= act_der(yv[j], act);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s[j] += g[j]; q[j] = fmaf(g[j], (xv[j] - mu[j]) * rs[j], q[j]); }
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { s[j] += g[j]; q[j] = fmaf(g[j], (xv[j] - mu[j]) * rs[j], q[j]); }
         }
     }
 #pragma unroll
