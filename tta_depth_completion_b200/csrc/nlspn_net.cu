@@ -91,7 +91,7 @@ int ptta_nl_col_sums(const void* x, long long ldx, long long rows, int c, float*
 int ptta_nl_bn_act(const void* x, const float* scale, const float* shift, const void* res, long long ldr, const float* rscale,
                    const float* rshift, void* y, long long rows, int c, int act, ptta_stream_t stream) {
     PTTA_CHECK(x && scale && shift && y && c % 64 == 0 && rows > 0 && (!rscale || (res && rshift)), "nl_bn_act: bad arguments");
-    const long long total = rows * (c / 8);
+    const long long total = (rows * (c / 8) + 1) / 2;
     bn_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, scale, shift, (const bf16*)res, ldr, rscale, rshift, (bf16*)y,
                                                                      rows, c, act);
     return check_launch("nl_bn_act");
@@ -109,7 +109,7 @@ int ptta_nl_bn_backward(const void* dy_a, long long ld_a, const void* dy_b, long
     PTTA_TRY(check_launch("nl_bn_bwd_reduce"));
     bn_bwd_finalize2_kernel<<<cdiv(c, 32), 256, 0, st>>>(partial, nblk, rows, c, gamma, rstd, dgamma, dbeta, coef, coef + c, coef + 2 * c);
     PTTA_TRY(check_launch("nl_bn_bwd_finalize"));
-    const long long total = rows * (c / 8);
+    const long long total = (rows * (c / 8) + 1) / 2;
     bn_bwd_apply2_kernel<<<cdiv(total, 256), 256, 0, st>>>((const bf16*)dy_a, ld_a, (const bf16*)dy_b, ld_b, (const bf16*)y, act, (const bf16*)x, mean,
                                                           rstd, coef, coef + c, coef + 2 * c, (bf16*)dx, (bf16*)gskip, rows, c);
     return check_launch("nl_bn_bwd_apply");

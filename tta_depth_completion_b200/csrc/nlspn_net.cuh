@@ -236,30 +236,46 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize2_kernel(const float* __re
 __global__ void __launch_bounds__(256) bn_act_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                                                      const bf16* __restrict__ res, long long ldr, const float* __restrict__ rscale,
                                                      const float* __restrict__ rshift, bf16* __restrict__ y, long long P, int C, int act) {
+    // two 16-byte elements per thread, `half` apart, loads first (more bytes in flight per thread)
     const int c8n = C >> 3;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P * c8n) return;
-    const long long p = idx / c8n;
-    const int c0 = (int)(idx - p * c8n) * 8;
-    float v[8], sc[8], sh[8];
-    load8(x + p * C + c0, v);
-    load8f(scale + c0, sc); load8f(shift + c0, sh);
+    const long long total = P * c8n, half = (total + 1) >> 1;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= half) return;
+    long long idx[2] = {i0, i0 + half};
+    uint4 rx[2], rr[2];
+    long long pp[2]; int cc[2]; bool ok[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-    if (res) {
-        float r[8];
-        load8(res + p * ldr + c0, r);
-        if (rscale) {
-            load8f(rscale + c0, sc); load8f(rshift + c0, sh);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = fmaf(r[j], sc[j], sh[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += r[j];
+    for (int u = 0; u < 2; ++u) {
+        ok[u] = idx[u] < total;
+        pp[u] = ok[u] ? idx[u] / c8n : 0;
+        cc[u] = ok[u] ? (int)(idx[u] - pp[u] * c8n) * 8 : 0;
+        rx[u] = __ldg(reinterpret_cast<const uint4*>(x + pp[u] * C + cc[u]));
+        if (res) rr[u] = __ldg(reinterpret_cast<const uint4*>(res + pp[u] * ldr + cc[u]));
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j], act);
-    store8(y + p * C + c0, v);
+    for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+        const int c0 = cc[u];
+        float v[8], sc[8], sh[8];
+        unpack8(rx[u], v);
+        load8f(scale + c0, sc); load8f(shift + c0, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+        if (res) {
+            float r[8];
+            unpack8(rr[u], r);
+            if (rscale) {
+                load8f(rscale + c0, sc); load8f(rshift + c0, sh);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = fmaf(r[j], sc[j], sh[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += r[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j], act);
+        store8(y + pp[u] * C + c0, v);
+    }
 }
 
 // dx = k0*g - k1 - xhat*k2 (bf16); optionally gskip = g (the gradient that flows on through the residual connection)
@@ -269,32 +285,50 @@ __global__ void __launch_bounds__(256) bn_bwd_apply2_kernel(const bf16* __restri
                                                             const float* __restrict__ k0, const float* __restrict__ k1, const float* __restrict__ k2,
                                                             bf16* __restrict__ dx, bf16* __restrict__ gskip, long long P, int C) {
     const int c8n = C >> 3;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P * c8n) return;
-    const long long p = idx / c8n;
-    const int c0 = (int)(idx - p * c8n) * 8;
-    float g[8];
-    load8(dyA + p * ldA + c0, g);
-    if (dyB) {
-        float b[8];
-        load8(dyB + p * ldB + c0, b);
+    const long long total = P * c8n, half = (total + 1) >> 1;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= half) return;
+    long long idx[2] = {i0, i0 + half};
+    uint4 ra[2], rb[2], ry[2], rx[2];
+    long long pp[2]; int cc[2]; bool ok[2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += b[j];
+    for (int u = 0; u < 2; ++u) {
+        ok[u] = idx[u] < total;
+        pp[u] = ok[u] ? idx[u] / c8n : 0;
+        cc[u] = ok[u] ? (int)(idx[u] - pp[u] * c8n) * 8 : 0;
+        ra[u] = __ldg(reinterpret_cast<const uint4*>(dyA + pp[u] * ldA + cc[u]));
+        if (dyB) rb[u] = __ldg(reinterpret_cast<const uint4*>(dyB + pp[u] * ldB + cc[u]));
+        if (act) ry[u] = __ldg(reinterpret_cast<const uint4*>(y + pp[u] * C + cc[u]));
+        if (dx) rx[u] = __ldg(reinterpret_cast<const uint4*>(x + pp[u] * C + cc[u]));
     }
-    if (act) {
-        float yv[8];
-        load8(y + p * C + c0, yv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= act_der(yv[j], act);
-    }
-    if (gskip) store8(gskip + p * C + c0, g);
-    if (dx) {
-        float xv[8], mu[8], rs[8], a0[8], a1[8], a2[8], o[8];
-        load8(x + p * C + c0, xv);
-        load8f(mean + c0, mu); load8f(rstd + c0, rs); load8f(k0 + c0, a0); load8f(k1 + c0, a1); load8f(k2 + c0, a2);
+    for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+        const long long p = pp[u];
+        const int c0 = cc[u];
+        float g[8];
+        unpack8(ra[u], g);
+        if (dyB) {
+            float b[8];
+            unpack8(rb[u], b);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = a0[j] * g[j] - a1[j] - (xv[j] - mu[j]) * rs[j] * a2[j];
-        store8(dx + p * C + c0, o);
+            for (int j = 0; j < 8; ++j) g[j] += b[j];
+        }
+        if (act) {
+            float yv[8];
+            unpack8(ry[u], yv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] *= act_der(yv[j], act);
+        }
+        if (gskip) store8(gskip + p * C + c0, g);
+        if (dx) {
+            float xv[8], mu[8], rs[8], a0[8], a1[8], a2[8], o[8];
+            unpack8(rx[u], xv);
+            load8f(mean + c0, mu); load8f(rstd + c0, rs); load8f(k0 + c0, a0); load8f(k1 + c0, a1); load8f(k2 + c0, a2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = a0[j] * g[j] - a1[j] - (xv[j] - mu[j]) * rs[j] * a2[j];
+            store8(dx + p * C + c0, o);
+        }
     }
 }
 
