@@ -72,7 +72,7 @@ int ptta_nl_bn_stats(const void* x, long long ldx, long long rows, int c, const 
     dim3 grid(nblk, c / 64);
     chan_reduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, rows, c, partial);
     PTTA_TRY(check_launch("nl_chan_stats"));
-    bn_finalize2_kernel<<<cdiv(c, 32), 256, 0, (cudaStream_t)stream>>>(partial, nblk, rows, c, gamma, beta, eps, mean, rstd, scale, shift, run_mean,
+    bn_finalize2_kernel<<<cdiv(c, 32), 1024, 0, (cudaStream_t)stream>>>(partial, nblk, rows, c, gamma, beta, eps, mean, rstd, scale, shift, run_mean,
                                                                        run_var, num_batches_tracked, momentum, nullptr);
     return check_launch("nl_bn_finalize");
 }
@@ -83,7 +83,7 @@ int ptta_nl_col_sums(const void* x, long long ldx, long long rows, int c, float*
     dim3 grid(nblk, c / 64);
     chan_reduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, rows, c, partial);
     PTTA_TRY(check_launch("nl_chan_stats"));
-    bn_finalize2_kernel<<<cdiv(c, 32), 256, 0, (cudaStream_t)stream>>>(partial, nblk, rows, c, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr,
+    bn_finalize2_kernel<<<cdiv(c, 32), 1024, 0, (cudaStream_t)stream>>>(partial, nblk, rows, c, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr,
                                                                        nullptr, nullptr, nullptr, 0.f, sums);
     return check_launch("nl_col_sums");
 }
@@ -107,7 +107,7 @@ int ptta_nl_bn_backward(const void* dy_a, long long ld_a, const void* dy_b, long
     chan_reduce_kernel<1><<<grid, 256, 0, st>>>((const bf16*)x, c, (const bf16*)dy_a, ld_a, (const bf16*)dy_b, ld_b, (const bf16*)y, act, mean, rstd,
                                                rows, c, partial);
     PTTA_TRY(check_launch("nl_bn_bwd_reduce"));
-    bn_bwd_finalize2_kernel<<<cdiv(c, 32), 256, 0, st>>>(partial, nblk, rows, c, gamma, rstd, dgamma, dbeta, coef, coef + c, coef + 2 * c);
+    bn_bwd_finalize2_kernel<<<cdiv(c, 32), 1024, 0, st>>>(partial, nblk, rows, c, gamma, rstd, dgamma, dbeta, coef, coef + c, coef + 2 * c);
     PTTA_TRY(check_launch("nl_bn_bwd_finalize"));
     const long long total = (rows * (c / 8) + 1) / 2;
     bn_bwd_apply2_kernel<<<cdiv(total, 256), 256, 0, st>>>((const bf16*)dy_a, ld_a, (const bf16*)dy_b, ld_b, (const bf16*)y, act, (const bf16*)x, mean,

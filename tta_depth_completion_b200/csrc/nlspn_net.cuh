@@ -178,24 +178,37 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const bf16* __restrict
     }
 }
 
-// 256 threads = 8 block-slices x 32 channels: every warp load is one coalesced 128 B row of the partial table; the slices are
-// combined through shared memory in a fixed order (deterministic).  Returns the totals to the threads of slice 0.
+// 1024 threads = 32 block-slices x 32 channels: every warp load is one coalesced 128 B row of the partial table, four rows in
+// flight per thread (the loop is a chain of L2 round trips otherwise); the slices are combined through shared memory in a fixed
+// order (deterministic).  Returns the totals to the threads of slice 0.
 __device__ __forceinline__ bool partial_sums(const float* __restrict__ partial, int nblk, int C, int& c, double& s, double& q) {
-    __shared__ double sh[2][8][32];
+    __shared__ double sh[2][32][32];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     c = blockIdx.x * 32 + lane;
     s = 0.0; q = 0.0;
-    if (c < C)
-        for (int b = slice; b < nblk; b += 8) { s += (double)partial[((size_t)b * 2) * C + c]; q += (double)partial[((size_t)b * 2 + 1) * C + c]; }
+    if (c < C) {
+        int b = slice;
+        for (; b + 96 < nblk; b += 128) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[2 * u] = partial[((size_t)(b + 32 * u) * 2) * C + c];
+                v[2 * u + 1] = partial[((size_t)(b + 32 * u) * 2 + 1) * C + c];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { s += (double)v[2 * u]; q += (double)v[2 * u + 1]; }
+        }
+        for (; b < nblk; b += 32) { s += (double)partial[((size_t)b * 2) * C + c]; q += (double)partial[((size_t)b * 2 + 1) * C + c]; }
+    }
     sh[0][slice][lane] = s; sh[1][slice][lane] = q;
     __syncthreads();
     if (slice != 0 || c >= C) return false;
 #pragma unroll
-    for (int k = 1; k < 8; ++k) { s += sh[0][k][lane]; q += sh[1][k][lane]; }
+    for (int k = 1; k < 32; ++k) { s += sh[0][k][lane]; q += sh[1][k][lane]; }
     return true;
 }
 
-__global__ void __launch_bounds__(256) bn_finalize2_kernel(const float* __restrict__ partial, int nblk, long long count, int C,
+__global__ void __launch_bounds__(1024) bn_finalize2_kernel(const float* __restrict__ partial, int nblk, long long count, int C,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                            float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
                                                            float* __restrict__ shift, float* __restrict__ run_mean, float* __restrict__ run_var,
@@ -219,7 +232,7 @@ __global__ void __launch_bounds__(256) bn_finalize2_kernel(const float* __restri
     }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_finalize2_kernel(const float* __restrict__ partial, int nblk, long long count, int C,
+__global__ void __launch_bounds__(1024) bn_bwd_finalize2_kernel(const float* __restrict__ partial, int nblk, long long count, int C,
                                                                const float* __restrict__ gamma, const float* __restrict__ rstd,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ k0,
                                                                float* __restrict__ k1, float* __restrict__ k2) {
