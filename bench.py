@@ -86,6 +86,36 @@ class ClockSampler(threading.Thread):
                 'samples': len(self.samples)}
 
 
+class HostPrefetcher:
+    """Double-buffered input staging for the end-to-end leg: the H2D copy of frame t+1 (pinned host -> device staging buffer, on
+    its own copy stream) is issued right after step t is launched, so it overlaps the step; the step's fixed input buffers are then
+    filled by a device-to-device copy on the compute stream.  Every frame still crosses PCIe inside the timed region -- this is
+    what a prefetching data loader does for the reference's `inputs.to(device)` (src/tta_main.py:521-523)."""
+
+    def __init__(self, pinned, img_d, sp_d, compute_stream, dev):
+        self.pinned, self.img_d, self.sp_d, self.compute = pinned, img_d, sp_d, compute_stream
+        self.copy = torch.cuda.Stream(dev)
+        self.stage = [(torch.empty_like(img_d), torch.empty_like(sp_d)) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.issued = 0
+
+    def prefetch(self, i):
+        k = i % 2
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(self.consumed[k])           # the D2D copy that read this staging slot two frames ago is done
+            self.stage[k][0].copy_(self.pinned[i % len(self.pinned)][0], non_blocking=True)
+            self.stage[k][1].copy_(self.pinned[i % len(self.pinned)][1], non_blocking=True)
+            self.ready[k].record(self.copy)
+
+    def take(self, i):
+        k = i % 2
+        self.compute.wait_event(self.ready[k])
+        self.img_d.copy_(self.stage[k][0], non_blocking=True)
+        self.sp_d.copy_(self.stage[k][1], non_blocking=True)
+        self.consumed[k].record(self.compute)
+
+
 def make_frames(workload, batch, count, seq_seed):
     from oracle import msgchn_oracle as O          # synthetic-input generator only (SURVEY.md section 8d)
     h, w, dataset = WORKLOADS[workload][:3]
@@ -349,15 +379,20 @@ def run_native_nlspn(args):
         ms_total = e0.elapsed_time(e1)
         sampler.stop_flag = True
         losses = eng.read_losses()
+        pre = HostPrefetcher(pinned, img_d, sp_d, stream, dev)
+        pre.consumed[0].record(stream); pre.consumed[1].record(stream)
+        pre.prefetch(0)
         for i in range(3):
-            img_d.copy_(pinned[i % RING][0], non_blocking=True); sp_d.copy_(pinned[i % RING][1], non_blocking=True)
+            pre.take(i)
+            pre.prefetch(i + 1)
             step()
             eng.read_losses()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
-        for i in range(args.steps):
-            img_d.copy_(pinned[i % RING][0], non_blocking=True); sp_d.copy_(pinned[i % RING][1], non_blocking=True)
+        for i in range(3, 3 + args.steps):
+            pre.take(i)
+            pre.prefetch(i + 1)
             step()
             eng.read_losses()                       # D2H + sync, every step (src/tta_main.py:801)
         f1.record(stream)
@@ -377,7 +412,8 @@ def run_native_nlspn(args):
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(args),
             'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 20,
-                    'ms_per_step': ms_e2e / args.steps},
+                    'ms_per_step': ms_e2e / args.steps,
+                    'input_staging': 'pinned host frames, double-buffered: the H2D copy of frame t+1 runs on a copy stream while step t computes; loss read back (D2H + sync) every step'},
             'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step, 'cuda_graph': bool(args.graph),
             'clocks': sampler.summary(), 'last_losses': losses,
             'step_tflops': NLSPN_GFLOP_STEP * args.batch / (ms_total / args.steps),
@@ -467,17 +503,21 @@ def run_native(args):
         losses = model.last_losses()
 
         # ---- end to end: host pinned inputs -> H2D -> step -> D2H loss read, every step -------------------------------
-        for i in range(max(3, args.warmup)):
-            img_d.copy_(pinned[i % RING][0], non_blocking=True)
-            sp_d.copy_(pinned[i % RING][1], non_blocking=True)
+        pre = HostPrefetcher(pinned, img_d, sp_d, stream, dev)
+        pre.consumed[0].record(stream); pre.consumed[1].record(stream)
+        nwarm = max(3, args.warmup)
+        pre.prefetch(0)
+        for i in range(nwarm):
+            pre.take(i)
+            pre.prefetch(i + 1)
             run_step(img_d, sp_d, graph=use_graph)
             model.last_losses()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
-        for i in range(args.steps):
-            img_d.copy_(pinned[i % RING][0], non_blocking=True)
-            sp_d.copy_(pinned[i % RING][1], non_blocking=True)
+        for i in range(nwarm, nwarm + args.steps):
+            pre.take(i)                                 # frame i: staged by the copy stream while step i-1 was running
+            pre.prefetch(i + 1)
             run_step(img_d, sp_d, graph=use_graph)
             e2e_losses = model.last_losses()            # D2H + sync (the driver reads the loss every step, src/tta_main.py:801)
         f1.record(stream)
@@ -499,7 +539,8 @@ def run_native(args):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(args),
         'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 20,
-                'ms_per_step': ms_e2e / args.steps},
+                'ms_per_step': ms_e2e / args.steps,
+                'input_staging': 'pinned host frames, double-buffered: the H2D copy of frame t+1 runs on a copy stream while step t computes; loss read back (D2H + sync) every step'},
         'gpu_launches': (launches_per_step or 0) * args.steps,
         'launches_per_step': launches_per_step, 'cuda_graph': use_graph,
         'clocks': sampler.summary(),
