@@ -160,58 +160,53 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
             }
             __syncwarp();
         }
-        // ring positions are kept as (slot, phase) pairs: no division in the per-item path (one warp runs this serial code)
-        uint32_t sa = 0, pa = 1, sb = 0, pb = 1;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            CONVG_DECODE_TILE(tile, nt, tx, ty, n, cls)
-            const int gx0 = tx * p.tw, gy0 = ty * p.th;
-            const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
-            if (p.halo) {
-                for (int i = 0; i < cnt; i += 9) {                  // one halo tile per 64-channel chunk, then its nine weight tiles
-                    const int c_inner = p.items[i0 + i].c_inner, src = (p.items[i0 + i].dyps >> 20) & 1;
-                    tc::mbar_wait(a_empty + 8 * sa, pa);
-                    if (elect_one()) {
+        // ring positions are kept as (slot, phase) pairs: no division in the per-item path.  ONE elected lane runs the whole producer
+        // loop (waits included): no per-item warp synchronisation; the other lanes wait at the final barrier
+        if (elect_one()) {
+            uint32_t sa = 0, pa = 1, sb = 0, pb = 1;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                CONVG_DECODE_TILE(tile, nt, tx, ty, n, cls)
+                const int gx0 = tx * p.tw, gy0 = ty * p.th;
+                const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
+                if (p.halo) {
+                    for (int i = 0; i < cnt; i += 9) {              // one halo tile per 64-channel chunk, then its nine weight tiles
+                        const int c_inner = p.items[i0 + i].c_inner, src = (p.items[i0 + i].dyps >> 20) & 1;
+                        tc::mbar_wait(a_empty + 8 * sa, pa);
                         if (dbg & 8) {
                             tc::mbar_arrive(a_full + 8 * sa);
                         } else {
                             tc::mbar_arrive_expect_tx(a_full + 8 * sa, (uint32_t)p.a_tx_bytes);
                             tc::tma_load_5d(smem_base + sa * A_SLOT, src ? &tmap_a1 : &tmap_a0, a_full + 8 * sa, c_inner, gx0 - 1, 0, gy0 - 1, n);
                         }
-                    }
-                    __syncwarp();
-                    if (++sa == NA) { sa = 0; pa ^= 1; }
-                    if (!p.b_resident) {
-                        for (int tap = 0; tap < 9; ++tap) {
-                            tc::mbar_wait(b_empty + 8 * sb, pb);
-                            if (elect_one()) {
+                        if (++sa == NA) { sa = 0; pa ^= 1; }
+                        if (!p.b_resident) {
+                            for (int tap = 0; tap < 9; ++tap) {
+                                tc::mbar_wait(b_empty + 8 * sb, pb);
                                 if (dbg & 16) {
                                     tc::mbar_arrive(b_full + 8 * sb);
                                 } else {
                                     tc::mbar_arrive_expect_tx(b_full + 8 * sb, b_tx);
                                     tc::tma_load_3d(b_base + sb * B_SLOT, &tmap_b, b_full + 8 * sb, 0, nt * p.BN, i0 + i + tap);
                                 }
+                                if (++sb == NB) { sb = 0; pb ^= 1; }
                             }
-                            __syncwarp();
-                            if (++sb == NB) { sb = 0; pb ^= 1; }
                         }
                     }
-                }
-            } else {
-                for (int i = 0; i < cnt; ++i) {                     // one stage = A box + B tile, one barrier
-                    const ConvGItem item = p.items[i0 + i];
-                    tc::mbar_wait(a_empty + 8 * sa, pa);
-                    if (elect_one()) {
+                } else {
+                    for (int i = 0; i < cnt; ++i) {                 // one stage = A box + B tile, one barrier
+                        const ConvGItem item = p.items[i0 + i];
+                        tc::mbar_wait(a_empty + 8 * sa, pa);
                         tc::mbar_arrive_expect_tx(a_full + 8 * sa, (uint32_t)p.a_tx_bytes + b_tx);
                         const int dy = (int)(short)(item.dyps & 0xffff), py = (item.dyps >> 16) & 3, src = (item.dyps >> 20) & 1;
                         tc::tma_load_5d(smem_base + sa * A_SLOT, src ? &tmap_a1 : &tmap_a0, a_full + 8 * sa, item.c_inner, gx0 + item.dx, py,
                                         gy0 + dy, n);
                         tc::tma_load_3d(b_base + sa * B_SLOT, &tmap_b, a_full + 8 * sa, 0, nt * p.BN, i0 + i);
+                        if (++sa == NA) { sa = 0; pa ^= 1; }
                     }
-                    __syncwarp();
-                    if (++sa == NA) { sa = 0; pa ^= 1; }
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // MMA issuer (converged warp, one elected lane issues and commits)
         const uint32_t idesc = tc::make_idesc_bf16(128, p.BN);
@@ -219,75 +214,54 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
         // SWIZZLE_128B is a function of the shared-memory address, so any 128 B-aligned start inside the halo is a valid operand
         const uint64_t da0 = make_desc_sw128_sbo(0, p.halo ? C::HALO_W * 128 : 1024), db0 = make_desc_sw128_sbo(0, 1024);
         const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32), lo0 = (uint32_t)da0;
-        uint32_t sa = 0, pa = 0, sb = 0, pb = 0, t = 0;
-        if (p.b_resident) { tc::mbar_wait(w_full, 0); tc::tc_fence_after(); }
         const int rev = p.halo_rev;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-            const int cls = p.n_classes == 1 ? 0 : tile / p.per_class;
-            const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
-            const uint32_t as = t & 1;
-            tc::mbar_wait(acc_empty + 8 * as, ((t >> 1) & 1) ^ 1);
-            tc::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * 256;
-            if (p.halo) {
-                for (int i = 0; i < cnt; i += 9) {
-                    tc::mbar_wait(a_full + 8 * sa, pa);
-                    tc::tc_fence_after();
-                    const uint32_t a_tile = lo0 + ((smem_base + sa * A_SLOT) >> 4);
-                    if (p.b_resident) {
-                        // the whole chunk (9 taps x 4 K-steps) is issued by one elected lane as straight-line code
-                        if (elect_one()) {
-                            const uint32_t b_tile = lo0 + ((b_base + (uint32_t)(i0 + i) * B_SLOT) >> 4);
-#pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const int hy = tap / 3, hx = tap - hy * 3;
-                                const uint32_t off_f = (uint32_t)(hy * C::HALO_W + hx) * 8, off_r = (uint32_t)((2 - hy) * C::HALO_W + (2 - hx)) * 8;
-                                const uint32_t a_lo = a_tile + (rev ? off_r : off_f);
-                                const uint32_t b_lo = b_tile + (uint32_t)tap * (B_SLOT >> 4);
-                                if (tap == 0 && i == 0) tc::umma_f16_split<false>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
-                                else tc::umma_f16_split<true>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
-                                if (!(dbg & 1)) {
-#pragma unroll
-                                    for (int k = 1; k < 4; ++k) tc::umma_f16_split<true>(d_tmem, a_lo + k * 2, a_hi, b_lo + k * 2, b_hi, idesc);
-                                }
-                            }
-                            tc::umma_commit(a_empty + 8 * sa);
-                            if (i + 9 >= cnt) tc::umma_commit(acc_full + 8 * as);
-                        }
-                        __syncwarp();
-                    } else {
+        // ONE elected lane runs the whole issue loop, waits included (no per-item elect / __syncwarp)
+        if (elect_one()) {
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0, t = 0;
+            if (p.b_resident) { tc::mbar_wait(w_full, 0); tc::tc_fence_after(); }
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+                const int cls = p.n_classes == 1 ? 0 : tile / p.per_class;
+                const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
+                const uint32_t as = t & 1;
+                tc::mbar_wait(acc_empty + 8 * as, ((t >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                if (p.halo) {
+                    for (int i = 0; i < cnt; i += 9) {
+                        tc::mbar_wait(a_full + 8 * sa, pa);
+                        tc::tc_fence_after();
+                        const uint32_t a_tile = lo0 + ((smem_base + sa * A_SLOT) >> 4);
+                        const uint32_t b_res = lo0 + ((b_base + (uint32_t)(i0 + i) * B_SLOT) >> 4);
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
-                            tc::mbar_wait(b_full + 8 * sb, pb);
-                            tc::tc_fence_after();
-                            if (elect_one()) {
-                                const int hy = tap / 3, hx = tap - hy * 3;
-                                const uint32_t off_f = (uint32_t)(hy * C::HALO_W + hx) * 8, off_r = (uint32_t)((2 - hy) * C::HALO_W + (2 - hx)) * 8;
-                                const uint32_t a_lo = a_tile + (rev ? off_r : off_f);
-                                const uint32_t b_lo = lo0 + ((b_base + sb * B_SLOT) >> 4);
-                                if (tap == 0 && i == 0) tc::umma_f16_split<false>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
-                                else tc::umma_f16_split<true>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
-                                if (!(dbg & 1)) {
-#pragma unroll
-                                    for (int k = 1; k < 4; ++k) tc::umma_f16_split<true>(d_tmem, a_lo + k * 2, a_hi, b_lo + k * 2, b_hi, idesc);
-                                }
-                                tc::umma_commit(b_empty + 8 * sb);
-                                if (tap == 8) {
-                                    tc::umma_commit(a_empty + 8 * sa);
-                                    if (i + 9 >= cnt) tc::umma_commit(acc_full + 8 * as);
-                                }
+                            uint32_t b_lo = b_res + (uint32_t)tap * (B_SLOT >> 4);
+                            if (!p.b_resident) {
+                                tc::mbar_wait(b_full + 8 * sb, pb);
+                                tc::tc_fence_after();
+                                b_lo = lo0 + ((b_base + sb * B_SLOT) >> 4);
                             }
-                            __syncwarp();
-                            if (++sb == NB) { sb = 0; pb ^= 1; }
+                            const int hy = tap / 3, hx = tap - hy * 3;
+                            const uint32_t off_f = (uint32_t)(hy * C::HALO_W + hx) * 8, off_r = (uint32_t)((2 - hy) * C::HALO_W + (2 - hx)) * 8;
+                            const uint32_t a_lo = a_tile + (rev ? off_r : off_f);
+                            if (tap == 0 && i == 0) tc::umma_f16_split<false>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
+                            else tc::umma_f16_split<true>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
+                            if (!(dbg & 1)) {
+#pragma unroll
+                                for (int k = 1; k < 4; ++k) tc::umma_f16_split<true>(d_tmem, a_lo + k * 2, a_hi, b_lo + k * 2, b_hi, idesc);
+                            }
+                            if (!p.b_resident) {
+                                tc::umma_commit(b_empty + 8 * sb);
+                                if (++sb == NB) { sb = 0; pb ^= 1; }
+                            }
                         }
+                        tc::umma_commit(a_empty + 8 * sa);
+                        if (i + 9 >= cnt) tc::umma_commit(acc_full + 8 * as);
+                        if (++sa == NA) { sa = 0; pa ^= 1; }
                     }
-                    if (++sa == NA) { sa = 0; pa ^= 1; }
-                }
-            } else {
-                for (int i = 0; i < cnt; ++i) {
-                    tc::mbar_wait(a_full + 8 * sa, pa);
-                    tc::tc_fence_after();
-                    if (elect_one()) {
+                } else {
+                    for (int i = 0; i < cnt; ++i) {
+                        tc::mbar_wait(a_full + 8 * sa, pa);
+                        tc::tc_fence_after();
                         const uint32_t a_lo = lo0 + ((smem_base + sa * A_SLOT) >> 4);
                         const uint32_t b_lo = lo0 + ((b_base + sa * B_SLOT) >> 4);
                         if (i == 0) tc::umma_f16_split<false>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc);
@@ -298,12 +272,12 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
                         }
                         tc::umma_commit(a_empty + 8 * sa);
                         if (i == cnt - 1) tc::umma_commit(acc_full + 8 * as);
+                        if (++sa == NA) { sa = 0; pa ^= 1; }
                     }
-                    __syncwarp();
-                    if (++sa == NA) { sa = 0; pa ^= 1; }
                 }
             }
         }
+        __syncwarp();
     } else {
         const int q = warp & 3, et = (warp - 2) * 32 + lane;     // et: 0..127, thread 0 issues the stores
         const int row = q * 32 + lane;                           // position inside the tile == TMEM lane
