@@ -217,6 +217,12 @@ size_t ptta_eval_metrics_workspace_bytes(void);
 int ptta_eval_metrics(const float* output_depth, const float* ground_truth, long long n, float min_depth, float max_depth,
                       void* workspace, float* result5, ptta_stream_t stream);
 
+/* input stage: src/data_utils.py:134-200 (load_image, load_depth_with_validity_map: depth = png / 256,
+ * <= 0 -> 0, validity = depth > 0) + the crop of src/datasets.py:83-170, on decoded 8-bit RGB [n,h0,w0,3] and 16-bit depth [n,h0,w0]
+ * payloads -> fp32 image NCHW in [0,255], depth and validity [n,1,h,w]; bit-exact with the numpy code */
+int ptta_input_stage(const void* image_u8_hwc, const void* depth_u16, float* image_nchw, float* depth, float* validity, int n,
+                     int h0, int w0, int y0, int x0, int h, int w, float depth_multiplier, ptta_stream_t stream);
+
 /* ---- MSG-CHN ProxyTTA engine ------------------------------------------------------------------- */
 /* prepare_mode: the reference's string, e.g. "meta_selfsup_seq_2layers_ema" (network_exp_msg_chn_adapt.py:1022-1087) */
 int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepare_mode);

@@ -324,3 +324,30 @@ def test_adam_matches_torch(ops):
     assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-6, atol=1e-7)
     assert torch.allclose(m.cpu(), opt.state[ref]['exp_avg'], rtol=1e-6, atol=1e-12)
     assert torch.allclose(v.cpu(), opt.state[ref]['exp_avg_sq'], rtol=1e-6, atol=1e-20)
+
+
+@pytest.mark.gpu
+def test_input_stage_matches_numpy_loader():
+    """ptta_input_stage == src/data_utils.py:134-200 (np.asarray(image, float32) transposed to CHW; depth = png / 256, <= 0 -> 0,
+    validity = depth > 0) followed by the bottom / centre crop of src/datasets.py:83-170, bit-exact"""
+    import numpy as np
+    from tta_depth_completion_b200 import ops
+    rng = np.random.RandomState(3)
+    n, h0, w0, h, w = 2, 375, 1242, 352, 1216
+    img = rng.randint(0, 256, size=(n, h0, w0, 3)).astype(np.uint8)
+    png = (rng.randint(0, 65536, size=(n, h0, w0)) * (rng.rand(n, h0, w0) < 0.05)).astype(np.uint16)
+    # reference arithmetic
+    image_ref = np.transpose(np.asarray(img, np.float32), (0, 3, 1, 2))
+    z = png.astype(np.float32) / 256.0
+    z[z <= 0] = 0.0
+    v = z.astype(np.float32).copy()
+    v[z > 0] = 1.0
+    x0, y0 = (w0 - w) // 2, h0 - h
+    image_ref, z, v = image_ref[:, :, y0:y0 + h, x0:x0 + w], z[:, None, y0:y0 + h, x0:x0 + w], v[:, None, y0:y0 + h, x0:x0 + w]
+    dev = torch.device('cuda:0')
+    image, depth, validity = ops.input_stage(torch.from_numpy(img).to(dev), torch.from_numpy(png.view(np.int16)).to(dev), (h, w), ('bottom',))
+    assert torch.equal(image.cpu(), torch.from_numpy(np.ascontiguousarray(image_ref)))
+    assert torch.equal(depth.cpu(), torch.from_numpy(np.ascontiguousarray(z)))
+    assert torch.equal(validity.cpu(), torch.from_numpy(np.ascontiguousarray(v)))
+    with pytest.raises(RuntimeError):
+        ops.input_stage(torch.from_numpy(img).to(dev), torch.from_numpy(png.view(np.int16)).to(dev), (400, 1216))

@@ -192,4 +192,15 @@ int ptta_eval_metrics(const float* output_depth, const float* ground_truth, long
     return check_launch("eval_metrics_finalize");
 }
 
+int ptta_input_stage(const void* image_u8_hwc, const void* depth_u16, float* image_nchw, float* depth, float* validity, int n, int h0, int w0,
+                     int y0, int x0, int h, int w, float depth_multiplier, ptta_stream_t stream) {
+    PTTA_CHECK(image_u8_hwc && depth_u16 && image_nchw && depth && validity, "input_stage: null pointer");
+    PTTA_CHECK(n >= 1 && y0 >= 0 && x0 >= 0 && h >= 1 && w >= 1 && y0 + h <= h0 && x0 + w <= w0 && depth_multiplier > 0.f,
+               "input_stage: crop %dx%d at (%d,%d) does not fit %dx%d", h, w, y0, x0, h0, w0);
+    const long long total = (long long)n * h * w;
+    input_stage_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const unsigned char*)image_u8_hwc, (const unsigned short*)depth_u16, image_nchw,
+                                                                          depth, validity, n, h0, w0, y0, x0, h, w, depth_multiplier);
+    return check_launch("input_stage");
+}
+
 }  // extern "C"

@@ -575,4 +575,25 @@ __global__ void __launch_bounds__(256) eval_metrics_finalize_kernel(const double
     }
 }
 
+// ---- input stage (src/data_utils.py:134-200 load_image / load_depth_with_validity_map + the crop of src/datasets.py:83-170) -------
+// decoded 8-bit RGB (HWC) and 16-bit depth PNG payloads -> fp32 NCHW image in [0, 255], depth = png / multiplier (<= 0 -> 0) and the
+// binary validity map, cropped to (h, w) at (y0, x0): the frames cross PCIe in their native compact types (3.2x fewer bytes)
+__global__ void __launch_bounds__(256) input_stage_kernel(const unsigned char* __restrict__ img, const unsigned short* __restrict__ dep,
+                                                          float* __restrict__ image, float* __restrict__ depth, float* __restrict__ validity,
+                                                          int N, int H0, int W0, int y0, int x0, int h, int w, float multiplier) {
+    const long long hw = (long long)h * w;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * hw) return;
+    const int n = (int)(idx / hw);
+    const long long o = idx - n * hw;
+    const int y = (int)(o / w), x = (int)(o - (long long)y * w);
+    const long long src = ((long long)n * H0 + (y0 + y)) * W0 + (x0 + x);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) image[((long long)n * 3 + c) * hw + o] = (float)img[src * 3 + c];
+    float z = (float)dep[src] / multiplier;
+    if (z <= 0.f) z = 0.f;
+    depth[idx] = z;
+    validity[idx] = z > 0.f ? 1.f : z;
+}
+
 }  // namespace ptta

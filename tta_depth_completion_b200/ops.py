@@ -251,3 +251,23 @@ def eval_metrics(output_depth, ground_truth, min_depth, max_depth):
                               _stream()), 'eval_metrics')
     v = res.cpu()
     return {'mae': float(v[0]), 'rmse': float(v[1]), 'imae': float(v[2]), 'irmse': float(v[3]), 'count': int(v[4])}
+
+
+def input_stage(image_u8_hwc, depth_u16, crop_shape=None, crop_type=('bottom',), depth_multiplier=256.0):
+    """Decoded 8-bit RGB [N,H0,W0,3] (uint8) and 16-bit depth [N,H0,W0] (int16/uint16 bit pattern) -> (image fp32 NCHW in [0,255],
+    sparse depth, validity map), cropped like the reference's default crop (src/datasets.py:83-170: horizontally centred, vertically
+    centred or at the bottom).  src/data_utils.py:134-200 on the device; the frames cross PCIe in their compact types."""
+    if image_u8_hwc.dtype != torch.uint8 or not image_u8_hwc.is_cuda or not image_u8_hwc.is_contiguous():
+        raise TypeError('image must be a contiguous CUDA uint8 tensor [N,H0,W0,3]')
+    if depth_u16.dtype not in (torch.int16, torch.uint16) or not depth_u16.is_cuda or not depth_u16.is_contiguous():
+        raise TypeError('depth must be a contiguous CUDA 16-bit integer tensor [N,H0,W0]')
+    n, h0, w0, _ = image_u8_hwc.shape
+    h, w = (h0, w0) if crop_shape is None else crop_shape
+    x0 = (w0 - w) // 2
+    y0 = (h0 - h) if 'bottom' in crop_type else (h0 - h) // 2
+    image = torch.empty((n, 3, h, w), dtype=torch.float32, device=image_u8_hwc.device)
+    depth = torch.empty((n, 1, h, w), dtype=torch.float32, device=image_u8_hwc.device)
+    validity = torch.empty_like(depth)
+    check(_lib.lib().ptta_input_stage(ptr(image_u8_hwc), ptr(depth_u16), ptr(image), ptr(depth), ptr(validity), n, h0, w0, y0, x0, h, w,
+                                      float(depth_multiplier), _stream()), 'input_stage')
+    return image, depth, validity
