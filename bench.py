@@ -316,9 +316,15 @@ def time_convg_kernel(dev, peaks, iters=24):
     gflop = 2 * 9 * 64 * 64 * h * w / 1e9
     alg_bytes = 2 * h * w * 64 * 2 + 9 * 64 * 64 * 2
     tflops = gflop / ms
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'convg_kernel_traffic.json')) as f:
+            traffic = json.load(f).get('dram_bytes_per_launch')
+    except Exception:
+        pass
     return {'kernel': 'convg_kernel: 3x3 64->64 s1 @352x1216 (NHWC bf16, tcgen05 + TMEM, TMA loads and stores, fp32 accumulate)',
             'bound': 'tensor', 'achieved': tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': tflops / peaks['bf16_tflops'],
-            'traffic': None, 'us_per_launch': 1e3 * ms, 'gflop_per_launch': gflop, 'algorithmic_bytes_per_launch': alg_bytes,
+            'traffic': traffic, 'us_per_launch': 1e3 * ms, 'gflop_per_launch': gflop, 'algorithmic_bytes_per_launch': alg_bytes,
             'hbm_gbs_achieved': alg_bytes / ms / 1e6, 'flop_per_byte': gflop * 1e9 / alg_bytes,
             'peak_source': peaks['source'] + ', burst figure (kernel timed alone, %d launches replayed from a CUDA graph)' % iters}
 
