@@ -160,6 +160,11 @@ int ptta_convg_pack(int kind, int role, const float* weight, const float* weight
 int ptta_convg_run(int kind, int role, const void* x0_bf16, const void* x1_bf16, const void* packed_bf16, const float* bias,
                    void* out_bf16, int n, int h, int w, int cin0, int cin1, int cout, int has_short, ptta_stream_t stream);
 
+/* host-only introspection of the K-item plan of a layer (CPU tests replay the implicit GEMM from it): header[16] = {n_items,
+ * n_classes, th, tw, tiles_y, tiles_x, n_tiles, BN, halo, b_resident, n_a, n_b, in_parity, out_parity, n_out, halo_rev}, 4 x
+ * {start, count, out_c, out_py} per class, then {c_inner, dx, dy, py, src, wsel, tap, k0} per item; returns the ints written */
+int ptta_convg_plan_describe(int kind, int role, int n, int h, int w, int cin0, int cin1, int cout, int has_short, int* out,
+                             int capacity);
 /* timing experiments only: 1 one MMA per K-item, 2 no epilogue work, 4 no epilogue fence / store (results are then wrong) */
 int ptta_convg_debug_set(int mask);
 /* thin heads id_dec0 / gd_dec0 / cf_dec0 (nlspnmodel_adapt.py:430-448, 883-895) as ONE 16-output-channel conv over the concat

@@ -203,4 +203,32 @@ int ptta_input_stage(const void* image_u8_hwc, const void* depth_u16, float* ima
     return check_launch("input_stage");
 }
 
+// host-only: the plan convg_make_plan builds for a layer, flattened into ints (CPU tests replay the implicit GEMM from it).
+// header[16] = {n_items, n_classes, th, tw, tiles_y, tiles_x, n_tiles, BN, halo, b_resident, n_a, n_b, in_parity, out_parity, n_out, halo_rev},
+// then per class {start, count, out_c, out_py}, then per item {c_inner, dx, dy, py, src, wsel, tap, k0}.  Returns the ints written, < 0 on error.
+int ptta_convg_plan_describe(int kind, int role, int n, int h, int w, int cin0, int cin1, int cout, int has_short, int* out, int capacity) {
+    ConvGPlan pl;
+    if (convg_make_plan(pl, kind, role, n, h, w, cin0, cin1, cout, has_short)) return -1;
+    const int need = 16 + 4 * 4 + 8 * pl.n_items;
+    if (!out || capacity < need) { set_error("convg_plan_describe: need %d ints", need); return -need; }
+    const ConvGParams& p = pl.p;
+    const int hdr[16] = {pl.n_items, p.n_classes, p.th, p.tw, p.tiles_y, p.tiles_x, p.n_tiles, p.BN, p.halo, p.b_resident, p.n_a, p.n_b,
+                         pl.in_parity, pl.out_parity, pl.n_out, p.halo_rev};
+    int k = 0;
+    for (int i = 0; i < 16; ++i) out[k++] = hdr[i];
+    for (int c = 0; c < 4; ++c) { out[k++] = p.cls_start[c]; out[k++] = p.cls_count[c]; out[k++] = p.cls_out_c[c]; out[k++] = p.cls_out_py[c]; }
+    for (int i = 0; i < pl.n_items; ++i) {
+        const ConvGItem& it = p.items[i];
+        int dx = it.dx, dy = (int)(short)(it.dyps & 0xffff);
+        if (p.halo) {          // halo mode: the tap position is the descriptor offset into the 18x10 halo whose origin is (-1, -1)
+            const int hpix = it.a_off16 / 8;
+            dy = hpix / ConvGCfg::HALO_W - 1;
+            dx = hpix % ConvGCfg::HALO_W - 1;
+        }
+        out[k++] = it.c_inner; out[k++] = dx; out[k++] = dy; out[k++] = (it.dyps >> 16) & 3; out[k++] = (it.dyps >> 20) & 1;
+        out[k++] = (pl.pack[i].wsel_tap >> 8) & 1; out[k++] = pl.pack[i].wsel_tap & 255; out[k++] = pl.pack[i].k0;
+    }
+    return k;
+}
+
 }  // extern "C"
