@@ -358,12 +358,14 @@ struct ConvGPackParams {
 };
 
 __global__ void __launch_bounds__(256) pack_convg_kernel(const __grid_constant__ ConvGPackParams p, bf16* __restrict__ out) {
+    // grid (chunk, 16-row group): the adapted meta conv is re-packed after every Adam step, so this sits on the step's critical path
     const int wk = blockIdx.x;
     const ConvGPackEntry e = p.e[wk];
     const int sel = (e.wsel_tap >> 8) & 1, tap = e.wsel_tap & 255;
     const float* w = p.w[sel];
-    for (int i = threadIdx.x; i < p.n_pad * 64; i += blockDim.x) {
-        const int n = i >> 6, j = i & 63, k = e.k0 + j;
+    const int row0 = blockIdx.y * 16, rows = min(16, p.n_pad - row0);
+    for (int i = threadIdx.x; i < rows * 64; i += blockDim.x) {
+        const int n = row0 + (i >> 6), j = i & 63, k = e.k0 + j;
         float v = 0.f;
         if (n < p.n_real[sel] && k < p.k_real[sel]) v = w[(long long)n * p.sn[sel] + (long long)k * p.sk[sel] + tap];
         else if (p.ident_from >= 0 && sel == 0 && tap == 4 && n >= p.ident_from && n == k) v = 1.f;
@@ -600,7 +602,7 @@ inline int launch_convg_pack(const ConvGPlan& pl, int kind, int role, const floa
     pp.sn[1] = 1; pp.sk[1] = cin_w; pp.n_real[1] = cin_w; pp.k_real[1] = cout_w;
     pp.n_pad = pl.n_out;
     pp.ident_from = ident_from;
-    pack_convg_kernel<<<pl.n_items, 256, 0, st>>>(pp, packed);
+    pack_convg_kernel<<<dim3(pl.n_items, cdiv(pl.n_out, 16)), 256, 0, st>>>(pp, packed);
     return check_launch("pack_convg");
 }
 

@@ -456,23 +456,45 @@ __global__ void __launch_bounds__(128) conv8to24_kernel(const float* __restrict_
 struct Wgrad48Cfg {
     static const int HALO_BYTES = 18 * 18 * 128;     // 41472
     static const int G_BYTES = 256 * 128;            // 32768
-    static const int SMEM = HALO_BYTES + G_BYTES;
+    static const int STAGE = HALO_BYTES + G_BYTES;   // one tile's operands
+    static const int SMEM = 2 * STAGE;               // double buffered: tile t+1 is fetched with cp.async while tile t is multiplied
     static const int THREADS = 288;
 };
 __device__ __forceinline__ int swz128(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
+// cp.async (zero-fill outside the image) of one tile's halo (18x18 pixels of the conv input) and gradient tile (16x16 pixels)
+__device__ __forceinline__ void wgrad48_fetch(unsigned char* stage, const bf16* __restrict__ xin, const bf16* __restrict__ gout, int tile, int tiles_x,
+                                              int tiles_y, int H, int W, int tid) {
+    const int n = tile / (tiles_y * tiles_x), r = tile - n * tiles_y * tiles_x;
+    const int y0 = (r / tiles_x) * 16, x0 = (r % tiles_x) * 16;
+    const uint32_t hs = smem_u32(stage), gs = hs + Wgrad48Cfg::HALO_BYTES;
+    const bf16* in_n = xin + (size_t)n * H * W * 64;
+    for (int i = tid; i < 18 * 18 * 8; i += Wgrad48Cfg::THREADS) {
+        const int pix = i >> 3, c = i & 7;
+        const int hy = pix / 18, hx = pix - hy * 18;
+        const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        cp_async16(hs + swz128(pix, c), ok ? in_n + ((size_t)gy * W + gx) * 64 + c * 8 : in_n, ok);
+    }
+    const bf16* g_n = gout + (size_t)n * H * W * 64;
+    for (int i = tid; i < 256 * 8; i += Wgrad48Cfg::THREADS) {
+        const int pix = i >> 3, c = i & 7;
+        const int gy = y0 + (pix >> 4), gx = x0 + (pix & 15);
+        const bool ok = gy < H && gx < W;
+        cp_async16(gs + swz128(pix, c), ok ? g_n + ((size_t)gy * W + gx) * 64 + c * 8 : g_n, ok);
+    }
+    cp_async_commit();
+}
+
 __global__ void __launch_bounds__(Wgrad48Cfg::THREADS, 1) wgrad48_kernel(const bf16* __restrict__ xin, const bf16* __restrict__ gout,
                                                                         float* __restrict__ partial, int N, int H, int W) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* s_halo = smem;
-    unsigned char* s_g = smem + Wgrad48Cfg::HALO_BYTES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_x = (W + 15) / 16, tiles_y = (H + 15) / 16;
     const int total = N * tiles_y * tiles_x;
     const int ky = warp / 3, kx = warp - ky * 3;
     const int a_k = (lane & 7) + (lane >> 4) * 8, a_mc = (lane >> 3) & 1;
     const int b_k = (lane & 7) + ((lane >> 3) & 1) * 8, b_nc = lane >> 4;
-    const uint32_t hb = smem_u32(s_halo), gb = smem_u32(s_g);
     float acc[3][6][4];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -480,28 +502,18 @@ __global__ void __launch_bounds__(Wgrad48Cfg::THREADS, 1) wgrad48_kernel(const b
         for (int b = 0; b < 6; ++b)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int n = tile / (tiles_y * tiles_x), r = tile - n * tiles_y * tiles_x;
-        const int y0 = (r / tiles_x) * 16, x0 = (r % tiles_x) * 16;
-        __syncthreads();                              // previous tile fully consumed
-        const bf16* in_n = xin + (size_t)n * H * W * 64;
-        for (int i = tid; i < 18 * 18 * 8; i += Wgrad48Cfg::THREADS) {
-            const int pix = i >> 3, c = i & 7;
-            const int hy = pix / 18, hx = pix - hy * 18;
-            const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const uint4*>(in_n + ((size_t)gy * W + gx) * 64 + c * 8));
-            *reinterpret_cast<uint4*>(s_halo + swz128(pix, c)) = v;
-        }
-        const bf16* g_n = gout + (size_t)n * H * W * 64;
-        for (int i = tid; i < 256 * 8; i += Wgrad48Cfg::THREADS) {
-            const int pix = i >> 3, c = i & 7;
-            const int gy = y0 + (pix >> 4), gx = x0 + (pix & 15);
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (gy < H && gx < W) v = __ldg(reinterpret_cast<const uint4*>(g_n + ((size_t)gy * W + gx) * 64 + c * 8));
-            *reinterpret_cast<uint4*>(s_g + swz128(pix, c)) = v;
+    int buf = 0;
+    if ((int)blockIdx.x < total) wgrad48_fetch(smem, xin, gout, blockIdx.x, tiles_x, tiles_y, H, W, tid);
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, buf ^= 1) {
+        const int next = tile + gridDim.x;
+        if (next < total) {
+            wgrad48_fetch(smem + (buf ^ 1) * Wgrad48Cfg::STAGE, xin, gout, next, tiles_x, tiles_y, H, W, tid);
+            cp_async_wait<1>();                       // this tile's group has landed, the next one may still be in flight
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
+        const uint32_t hb = smem_u32(smem + buf * Wgrad48Cfg::STAGE), gb = hb + Wgrad48Cfg::HALO_BYTES;
 #pragma unroll 2
         for (int ks = 0; ks < 16; ++ks) {             // one tile row of 16 pixels per k16 step
             uint32_t a[3][4], b[12];
@@ -515,6 +527,7 @@ __global__ void __launch_bounds__(Wgrad48Cfg::THREADS, 1) wgrad48_kernel(const b
 #pragma unroll
                 for (int nt = 0; nt < 6; ++nt) mma_bf16_16816(acc[mt][nt], a[mt], b[nt * 2], b[nt * 2 + 1]);
         }
+        __syncthreads();                              // everyone is done with this buffer before the fetch after next overwrites it
     }
     const int c_row = lane >> 2, c_col = (lane & 3) * 2;
     float* part = partial + ((size_t)blockIdx.x * 9 + warp) * 48 * 48;
