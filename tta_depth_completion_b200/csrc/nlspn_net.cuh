@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) nl_stem_kernel(const float* __restrict__ 
                                                       const float* __restrict__ w_rgb, const float* __restrict__ b_rgb,
                                                       const float* __restrict__ w_dep, const float* __restrict__ b_dep,
                                                       const float* __restrict__ scale, const float* __restrict__ shift,
-                                                      bf16* __restrict__ out, int N, int H, int W) {
+                                                      bf16* __restrict__ out, int N, int H, int W, int n_src) {
     __shared__ float s_w[27 * 48 + 9 * 16];      // [ci*9+tap][48] then [tap][16]
     __shared__ float s_b[64];
     for (int i = threadIdx.x; i < 27 * 48; i += blockDim.x) { const int co = i % 48, r = i / 48; s_w[i] = w_rgb[co * 27 + r]; }
@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(128) nl_stem_kernel(const float* __restrict__ 
     const long long HW = (long long)H * W, total = (long long)N * HW;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int x = idx % W, y = (idx / W) % H, n = idx / HW;
+    const int x = idx % W, y = (idx / W) % H, n_out = idx / HW;
+    // pair mode (n_src < N): output images n_src .. N-1 are the zero-image copies of images 0 .. n_src-1 (same sparse depth)
+    const int n = n_out % n_src;
+    const bool has_image = image != nullptr && n_out < n_src;
     float acc[64];
 #pragma unroll
     for (int c = 0; c < 64; ++c) acc[c] = s_b[c];
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(128) nl_stem_kernel(const float* __restrict__ 
             if (gx < 0 || gx >= W) continue;
             const long long o = (long long)gy * W + gx;
             const int tap = ky * 3 + kx;
-            if (image) {
+            if (has_image) {
 #pragma unroll
                 for (int ci = 0; ci < 3; ++ci) {
                     const float v = fmaf(__ldg(image + ((long long)n * 3 + ci) * HW + o), nsc[ci], nsh[ci]);
@@ -107,6 +110,9 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ dyB, long long ldB, const bf16* __restrict__ y, int act,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd, long long P, int C,
                                                           float* __restrict__ partial) {
+    // blockIdx.z = statistics group (independent row ranges of P rows each, e.g. the real / zero-image halves of a merged batch)
+    x += (long long)blockIdx.z * P * ldx;
+    partial += (size_t)blockIdx.z * gridDim.x * 2 * C;
     __shared__ float sh[2][8][64];
     const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.y * 64 + cg * 8;
@@ -215,6 +221,9 @@ __global__ void __launch_bounds__(1024) bn_finalize2_kernel(const float* __restr
                                                            long long* __restrict__ nbt, float momentum, float* __restrict__ sums_out) {
     int c;
     double s, q;
+    partial += (size_t)blockIdx.y * nblk * 2 * C;                     // statistics group
+    const int go = blockIdx.y * C;
+    mean += go; rstd += go; scale += go; shift += go;
     if (!partial_sums(partial, nblk, C, c, s, q)) return;
     if (sums_out) { sums_out[c] = (float)s; return; }          // plain column sums (bias gradients)
     const double m = s / (double)count;
@@ -248,7 +257,9 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize2_kernel(const float* __r
 // ---- elementwise -----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_act_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                                                      const bf16* __restrict__ res, long long ldr, const float* __restrict__ rscale,
-                                                     const float* __restrict__ rshift, bf16* __restrict__ y, long long P, int C, int act) {
+                                                     const float* __restrict__ rshift, bf16* __restrict__ y, long long P, int C, int act,
+                                                     long long rows_per_group) {
+    // rows_per_group > 0: row p uses the scale / shift vectors of group p / rows_per_group (merged real | zero-image batch)
     // two 16-byte elements per thread, `half` apart, loads first (more bytes in flight per thread)
     const int c8n = C >> 3;
     const long long total = P * c8n, half = (total + 1) >> 1;
@@ -269,16 +280,17 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const bf16* __restrict__ x,
     for (int u = 0; u < 2; ++u) {
         if (!ok[u]) continue;
         const int c0 = cc[u];
+        const int gofs = rows_per_group > 0 ? (int)(pp[u] / rows_per_group) * C : 0;
         float v[8], sc[8], sh[8];
         unpack8(rx[u], v);
-        load8f(scale + c0, sc); load8f(shift + c0, sh);
+        load8f(scale + gofs + c0, sc); load8f(shift + gofs + c0, sh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
         if (res) {
             float r[8];
             unpack8(rr[u], r);
             if (rscale) {
-                load8f(rscale + c0, sc); load8f(rshift + c0, sh);
+                load8f(rscale + gofs + c0, sc); load8f(rshift + gofs + c0, sh);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) r[j] = fmaf(r[j], sc[j], sh[j]);
             }
