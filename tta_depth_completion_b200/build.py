@@ -7,7 +7,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
-LIB_PATH = os.path.join(LIB_DIR, 'libptta_b200.so')
+LIB_PATH = os.environ.get('PTTA_B200_LIB') or os.path.join(LIB_DIR, 'libptta_b200.so')     # override: A/B experiments with another build
 SOURCES = ['engine.cu', 'nlspn_net.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 

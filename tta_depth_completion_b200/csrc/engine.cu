@@ -765,20 +765,9 @@ struct ptta_msgchn {
     // cx0/cx1/cx2: rgb features at the resolutions of x0/x1/x2; out = prediction [+ add]
     int run_decoder(const DecW& Wt, DecAct& A, const EncAct& E, const Map32& cx0, const Map32& cx1, const Map32& cx2,
                     const float* add, const Map1& out) {
-        {   // x2 = dx2 + cx2, x1 = dx1 + cx1, x0 = dx0 + cx0 in one launch
-            EwAdd3 q;
-            const Map32* aa[3] = {&E.x2, &E.x1, &E.x0};
-            const Map32* bb[3] = {&cx2, &cx1, &cx0};
-            const Map32* oo[3] = {&A.x2, &A.x1, &A.x0};
-            int blocks = 0;
-            for (int k = 0; k < 3; ++k) {
-                q.a[k] = aa[k]->p; q.b[k] = bb[k]->p; q.out[k] = oo[k]->p; q.n8[k] = (long long)aa[k]->numel() / 8;
-                blocks += cdiv(q.n8[k], 256);
-                q.blk_end[k] = blocks;
-            }
-            ew_add3_kernel<<<blocks, 256, 0, st>>>(q);
-            PTTA_TRY(check_launch("ew_add3"));
-        }
+        PTTA_TRY(add32(E.x2, cx2, A.x2));
+        PTTA_TRY(add32(E.x1, cx1, A.x1));
+        PTTA_TRY(add32(E.x0, cx0, A.x0));
         // u2, s1, u1, s0, h hold ReLU(.): each is read through a ReLU only (forward) or as a ReLU mask (backward)
         PTTA_TRY(conv_fwd(Wt.d2a, A.x2, A.u2, PRO_RELU, nullptr, 1));
         if (fuse_dec_sums) {

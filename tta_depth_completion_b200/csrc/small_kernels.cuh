@@ -489,25 +489,6 @@ __global__ void up2_c32_adj_kernel(const bf16* __restrict__ gh, bf16* __restrict
     *reinterpret_cast<uint4*>(o) = ov;
 }
 
-// three independent out = a + b segments in one launch (the decoder's x2 = dx2 + cx2, x1 = dx1 + cx1, x0 = dx0 + cx0,
-// network_exp_msg_chn_adapt.py:283-285): block ranges [0,b0) [b0,b1) [b1,b2)
-struct EwAdd3 { const bf16* a[3]; const bf16* b[3]; bf16* out[3]; long long n8[3]; int blk_end[3]; };
-__global__ void ew_add3_kernel(const EwAdd3 p) {
-    const int seg = blockIdx.x < p.blk_end[0] ? 0 : (blockIdx.x < p.blk_end[1] ? 1 : 2);
-    const int blk0 = seg == 0 ? 0 : p.blk_end[seg - 1];
-    const long long i = (long long)(blockIdx.x - blk0) * blockDim.x + threadIdx.x;
-    if (i >= p.n8[seg]) return;
-    const uint4 av = reinterpret_cast<const uint4*>(p.a[seg])[i], bv = reinterpret_cast<const uint4*>(p.b[seg])[i];
-    const uint32_t *ua = reinterpret_cast<const uint32_t*>(&av), *ub = reinterpret_cast<const uint32_t*>(&bv);
-    uint4 ov; uint32_t* uo = reinterpret_cast<uint32_t*>(&ov);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float2 fa = unpack_bf162(ua[j]), fb = unpack_bf162(ub[j]);
-        uo[j] = pack_bf162(fa.x + fb.x, fa.y + fb.y);
-    }
-    reinterpret_cast<uint4*>(p.out[seg])[i] = ov;
-}
-
 // out = a + b, optionally ReLU'd (bf16, n multiple of 8)
 __global__ void ew_add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, long long n8, int relu) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
