@@ -36,6 +36,8 @@ WORKLOADS = {
     'void': (480, 640, 'void', 'meta_selfsup_seq_1layer_ema', 3e-3, 8.0),
     # BASELINE.json configs[3]: NLSPN back-end (ResNet34 encoder/decoder + 18-step non-local propagation), adapt_mode meta_bn
     'nlspn': (352, 1216, 'kitti', 'meta_selfsup_seq_1layer_ema', 3e-4, 80.0),
+    # the NLSPN back-end on synthetic VOID-shape indoor frames (480x640, ~0.5 % density, depth cap 8 m)
+    'nlspn_void': (480, 640, 'void', 'meta_selfsup_seq_1layer_ema', 3e-4, 8.0),
 }
 NLSPN_GFLOP_STEP = 3445.9        # forward 2 227.0 + required dgrad 1 201.1 + wgrad 17.8 at 1x352x1216
 W_SD, W_SM, W_COS = 1.0, 1.0, 0.1
@@ -138,7 +140,7 @@ def nlspn_cpu_sample(args, steps, warmup):
     the throughput is scaled by 1/4."""
     from oracle import msgchn_oracle as O
     from oracle import nlspn_oracle as NO
-    h, w, dataset, mode, lr, cap = WORKLOADS['nlspn']
+    h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
     hs, ws = h // 2, w // 2
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -155,7 +157,7 @@ def nlspn_cpu_sample(args, steps, warmup):
     value = 0.25 * args.batch * steps / dt
     return value, dt, {'value': value, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                        'sample': '%d TTA step(s) of oracle/nlspn_oracle.py (torch %s CPU fp32) on %dx3x%dx%d frames = 1/4 of the pixels of the '
-                                 '352x1216 workload, %.1f s/step, throughput scaled by 1/4' % (steps, torch.__version__, args.batch, hs, ws, dt / steps)}
+                                 'workload, %.1f s/step, throughput scaled by 1/4' % (steps, torch.__version__, args.batch, hs, ws, dt / steps)}
 
 
 def run_reference(args):
@@ -164,7 +166,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    if args.workload == 'nlspn':
+    if args.workload.startswith('nlspn'):
         steps = min(args.steps, 3)
         value, dt, cb = nlspn_cpu_sample(args, steps, min(args.warmup, 1))
         print(json.dumps({'impl': 'reference', 'metric': 'adapted_frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus,
@@ -202,8 +204,8 @@ def run_reference(args):
 
 def workload_config(args):
     h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
-    if args.workload == 'nlspn':
-        return {'workload': 'NLSPN ProxyTTA continual adaptation (ResNet34 encoder/decoder, 18-step non-local propagation), synthetic KITTI-shape '
+    if args.workload.startswith('nlspn'):
+        return {'workload': 'NLSPN ProxyTTA continual adaptation (ResNet34 encoder/decoder, 18-step non-local propagation), synthetic ' + dataset.upper() + '-shape '
                             '%dx3x%dx%d frames, prepare_mode %s, adapt_mode meta_bn (88 tensors), lr %g, w_sd/w_smooth/w_cos %g/%g/%g, '
                             'Adam(0.9,0.999,1e-8)' % (args.batch, h, w, mode, lr, W_SD, W_SM, W_COS),
                 'batch_per_gpu': args.batch, 'parallelism': 'independent sequence shard per GPU (no collective)',
@@ -343,7 +345,7 @@ def run_native_nlspn(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
-    h, w, dataset, mode, lr, cap = WORKLOADS['nlspn']
+    h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
     peaks = load_peaks()
     eng = NlspnEngine(NO.make_synthetic_checkpoint(0), args.batch, h, w, dev)
     mean, std = NO.IMAGENET_MEAN, NO.IMAGENET_STD
@@ -422,8 +424,8 @@ def run_native_nlspn(args):
                     'input_staging': 'pinned host frames, double-buffered: the H2D copy of frame t+1 runs on a copy stream while step t computes; loss read back (D2H + sync) every step'},
             'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step, 'cuda_graph': bool(args.graph),
             'clocks': sampler.summary(), 'last_losses': losses,
-            'step_tflops': NLSPN_GFLOP_STEP * args.batch / (ms_total / args.steps),
-            'step_tflops_note': 'algorithmic work per step (%.1f GFLOP x batch: SURVEY.md 8d) / ms_per_step' % NLSPN_GFLOP_STEP}
+            'step_tflops': NLSPN_GFLOP_STEP * (h * w / (352.0 * 1216.0)) * args.batch / (ms_total / args.steps),
+            'step_tflops_note': 'algorithmic work per step (%.1f GFLOP at 352x1216, scaled by the pixel count, x batch: SURVEY.md 8d) / ms_per_step' % NLSPN_GFLOP_STEP}
     if world == 1 and not args.no_extras:
         line['roofline'] = time_convg_kernel(dev, peaks)
         line['cpu_baseline'] = nlspn_cpu_sample(args, 1, 1)[2]
@@ -433,7 +435,7 @@ def run_native_nlspn(args):
 
 
 def run_native(args):
-    if args.workload == 'nlspn':
+    if args.workload.startswith('nlspn'):
         return run_native_nlspn(args)
     from tta_depth_completion_b200 import ExternalModel_Adapt
     world = int(os.environ.get('WORLD_SIZE', '1'))
