@@ -118,6 +118,37 @@ class HostPrefetcher:
         self.consumed[k].record(self.compute)
 
 
+class LossReader:
+    """Reads every step's loss block back to pinned host memory WITHOUT stalling the stream: the D2H copy of step t is enqueued right
+    after step t, its event is waited for only after step t+1 has been launched (the reference's progress bar reads the loss
+    synchronously every step, src/tta_main.py:801; nothing downstream needs it before the next frame)."""
+
+    def __init__(self, stream):
+        self.stream = stream
+        self.host = [torch.empty(5, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.ev = [torch.cuda.Event() for _ in range(2)]
+        self.pending = None
+        self.last = None
+
+    def enqueue(self, dev_losses, i):
+        k = i % 2
+        self.host[k].copy_(dev_losses, non_blocking=True)
+        self.ev[k].record(self.stream)
+        prev, self.pending = self.pending, k
+        if prev is not None:
+            self.collect(prev)
+
+    def collect(self, k):
+        self.ev[k].synchronize()
+        self.last = self.host[k].tolist()
+
+    def drain(self):
+        if self.pending is not None:
+            self.collect(self.pending)
+            self.pending = None
+        return self.last
+
+
 def make_frames(workload, batch, count, seq_seed):
     from oracle import msgchn_oracle as O          # synthetic-input generator only (SURVEY.md section 8d)
     h, w, dataset = WORKLOADS[workload][:3]
@@ -398,11 +429,13 @@ def run_native_nlspn(args):
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
+        reader = LossReader(stream)
         for i in range(3, 3 + args.steps):
             pre.take(i)
             pre.prefetch(i + 1)
             step()
-            eng.read_losses()                       # D2H + sync, every step (src/tta_main.py:801)
+            reader.enqueue(eng.loss_ws[:20].view(torch.float32), i)   # D2H of this step's losses, read one step later
+        reader.drain()
         f1.record(stream)
         barrier()
         ms_e2e = f0.elapsed_time(f1)
@@ -421,7 +454,7 @@ def run_native_nlspn(args):
             'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(args),
             'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 20,
                     'ms_per_step': ms_e2e / args.steps,
-                    'input_staging': 'pinned host frames, double-buffered: the H2D copy of frame t+1 runs on a copy stream while step t computes; loss read back (D2H + sync) every step'},
+                    'input_staging': 'pinned host frames, double-buffered: the H2D copy of frame t+1 runs on a copy stream while step t computes; every step\'s loss block is copied D2H to pinned memory and read by the host after the next step has been launched (no per-step stream stall)'},
             'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step, 'cuda_graph': bool(args.graph),
             'clocks': sampler.summary(), 'last_losses': losses,
             'step_tflops': NLSPN_GFLOP_STEP * (h * w / (352.0 * 1216.0)) * args.batch / (ms_total / args.steps),
@@ -523,11 +556,13 @@ def run_native(args):
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
+        reader = LossReader(stream)
         for i in range(nwarm, nwarm + args.steps):
             pre.take(i)                                 # frame i: staged by the copy stream while step i-1 was running
             pre.prefetch(i + 1)
             run_step(img_d, sp_d, graph=use_graph)
-            e2e_losses = model.last_losses()            # D2H + sync (the driver reads the loss every step, src/tta_main.py:801)
+            reader.enqueue(model.last_losses_device(), i)   # D2H of this step's losses; looked at after the next step is launched
+        e2e_losses = reader.drain()
         f1.record(stream)
         barrier()
         ms_e2e = f0.elapsed_time(f1)
@@ -548,7 +583,7 @@ def run_native(args):
         'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(args),
         'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 20,
                 'ms_per_step': ms_e2e / args.steps,
-                'input_staging': 'pinned host frames, double-buffered: the H2D copy of frame t+1 runs on a copy stream while step t computes; loss read back (D2H + sync) every step'},
+                'input_staging': 'pinned host frames, double-buffered: the H2D copy of frame t+1 runs on a copy stream while step t computes; every step\'s loss block is copied D2H to pinned memory and read by the host after the next step has been launched (no per-step stream stall)'},
         'gpu_launches': (launches_per_step or 0) * args.steps,
         'launches_per_step': launches_per_step, 'cuda_graph': use_graph,
         'clocks': sampler.summary(),

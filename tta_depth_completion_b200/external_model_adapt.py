@@ -400,6 +400,14 @@ class ExternalModel_Adapt(object):
     def last_losses(self):
         return self._last_engine.read_losses()
 
+    def last_losses_device(self):
+        """device tensor (fp32 [5]: loss, loss_sparse_depth, loss_smooth, loss_cos, effective w_cos) of the last step: lets a driver
+        copy it to pinned memory asynchronously and look at it one step later instead of stalling the stream every step"""
+        e = self._last_engine
+        if self.model_name == 'nlspn':
+            return e.loss_ws[:20].view(torch.float32)
+        return e.tensor('losses').view(-1)[:5]
+
     def last_output(self):
         e = self._last_engine
         if self.model_name == 'nlspn':
