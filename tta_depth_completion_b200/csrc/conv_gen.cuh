@@ -17,7 +17,8 @@
 //     double buffered so the epilogue of tile t overlaps the MMAs of tile t+1.
 //   * epilogue (4 warps): tcgen05.ld -> + bias -> bf16 -> SWIZZLE_128B staging tile in shared memory -> one TMA store per 64
 //     channels (the store clips partial tiles, and addresses parity classes through the 5-D output view).
-// Roles: warp 0 TMA producer | warp 1 TMEM allocator + MMA issuer | warps 2-5 epilogue.  Persistent CTAs, one per SM.
+// Roles: warp 0 TMA producer | warp 1 TMEM allocator + MMA issuer, warp 2 second issuer (resident-weight layers: the two threads
+// take alternate tiles, so one keeps the tensor pipe fed while the other waits / commits) | warps 3-6 epilogue.  Persistent CTAs.
 #pragma once
 #include <cuda.h>
 #include <vector>
@@ -68,7 +69,7 @@ struct ConvGCfg {
     static const int HALO_BYTES = HALO_W * HALO_H * 128;          // 23040
     static const int HALO_SLOT = 23 * 1024;
     static const int SMEM = 1024 + RING_BYTES + 2 * OUT_BYTES + 512;
-    static const int THREADS = 192;
+    static const int THREADS = 224;                 // warp 0 TMA producer | warps 1-2 MMA issue | warps 3-6 epilogue
 };
 
 namespace tc {
@@ -107,6 +108,8 @@ __device__ __forceinline__ void fast_divmod(int x, int d, unsigned mul, unsigned
         fast_divmod(r_, p.tiles_y, p.div_mul[2], p.div_shr[2], n, ty);                \
     }
 
+__device__ long long g_convg_ts[64 * 16];   // timing experiments (dbg & 64): clock64() stamps of CTA 0, [tile][event]
+#define CONVG_TS(tl, k) do { if ((dbg & 64) && blockIdx.x == 0 && (tl) < 64) g_convg_ts[(tl) * 16 + (k)] = clock64(); } while (0)
 __device__ int g_convg_dbg = 0;   // timing experiments only (ptta_convg_debug_set): 1 one MMA per item, 2 no epilogue work, 4 no fence/store
 
 __global__ void __launch_bounds__(ConvGCfg::THREADS, 1)
@@ -120,8 +123,11 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     const uint32_t out_s = smem_base + C::RING_BYTES;
     const uint32_t bar_s = out_s + 2 * C::OUT_BYTES;
     const uint32_t a_full = bar_s, a_empty = bar_s + 64, b_full = bar_s + 128, b_empty = bar_s + 192, acc_full = bar_s + 256,
-                   acc_empty = bar_s + 272, w_full = bar_s + 288;
-    const uint32_t tmem_slot = bar_s + 296;
+                   acc_empty = bar_s + 320, w_full = bar_s + 384;
+    const uint32_t tmem_slot = bar_s + 392;
+    // accumulator ring in TMEM: 512 columns / (64 | 128 | 256 columns per tile) = 8 | 4 | 2 buffers (tile t uses buffer t mod NACC):
+    // with two issuing threads the epilogue's latency per tile has to be covered by more than one spare accumulator
+    const uint32_t ACC_LOG = p.BN <= 64 ? 3u : (p.BN <= 128 ? 2u : 1u), NACC = 1u << ACC_LOG, ACC_STRIDE = 512u >> ACC_LOG;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dbg = g_convg_dbg;
@@ -138,7 +144,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
             tc::mbar_init(a_full + 8 * i, 1); tc::mbar_init(a_empty + 8 * i, 1);
             tc::mbar_init(b_full + 8 * i, 1); tc::mbar_init(b_empty + 8 * i, 1);
         }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + 8 * i, 1); tc::mbar_init(acc_empty + 8 * i, 128); }
+        for (int i = 0; i < 8; ++i) { tc::mbar_init(acc_full + 8 * i, 1); tc::mbar_init(acc_empty + 8 * i, 128); }
         tc::mbar_init(w_full, 1);
         tc::fence_barrier_init();
     }
@@ -164,7 +170,9 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
         // loop (waits included): no per-item warp synchronisation; the other lanes wait at the final barrier
         if (elect_one()) {
             uint32_t sa = 0, pa = 1, sb = 0, pb = 1;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int tlp = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tlp) {
+                CONVG_TS(tlp, 8);
                 CONVG_DECODE_TILE(tile, nt, tx, ty, n, cls)
                 const int gx0 = tx * p.tw, gy0 = ty * p.th;
                 const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
@@ -178,6 +186,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
                             tc::mbar_arrive_expect_tx(a_full + 8 * sa, (uint32_t)p.a_tx_bytes);
                             tc::tma_load_5d(smem_base + sa * A_SLOT, src ? &tmap_a1 : &tmap_a0, a_full + 8 * sa, c_inner, gx0 - 1, 0, gy0 - 1, n);
                         }
+                        CONVG_TS(tlp, 9);
                         if (++sa == NA) { sa = 0; pa ^= 1; }
                         if (!p.b_resident) {
                             for (int tap = 0; tap < 9; ++tap) {
@@ -207,8 +216,11 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // MMA issuer (converged warp, one elected lane issues and commits)
+    } else if (warp == 1 || warp == 2) {
+        // MMA issuers (one elected lane each).  Layers with resident weights use BOTH: thread `me` takes the tiles t = me, me + 2, ...
+        // (accumulator buffer t & 1 = me), so the ~750 cycles a thread spends per tile outside the MMA issue (barrier waits, fences,
+        // commits, loop overhead: measured with tools/convg_trace.py) overlap with the other thread's 36 MMAs.
+        const int nissue = (p.halo && p.b_resident) ? 2 : 1, me = warp - 1;
         const uint32_t idesc = tc::make_idesc_bf16(128, p.BN);
         // A: 8-row groups are 1024 B apart in a plain tile, HALO_W pixels (1280 B) apart in a halo tile (tile rows of 8 pixels);
         // SWIZZLE_128B is a function of the shared-memory address, so any 128 B-aligned start inside the halo is a valid operand
@@ -216,20 +228,25 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
         const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32), lo0 = (uint32_t)da0;
         const int rev = p.halo_rev;
         // ONE elected lane runs the whole issue loop, waits included (no per-item elect / __syncwarp)
-        if (elect_one()) {
-            uint32_t sa = 0, pa = 0, sb = 0, pb = 0, t = 0;
+        if (me < nissue && elect_one()) {
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0, t = me;
             if (p.b_resident) { tc::mbar_wait(w_full, 0); tc::tc_fence_after(); }
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+            const int skip = (nissue - 1) * (p.cls_count[0] / 9);      // A-ring slots the other issuer consumes between two of my tiles
+            for (int k = 0; k < me * (p.cls_count[0] / 9); ++k) { if (++sa == NA) { sa = 0; pa ^= 1; } }
+            for (int tile = blockIdx.x + me * gridDim.x; tile < p.total_tiles; tile += nissue * gridDim.x, t += nissue) {
                 const int cls = p.n_classes == 1 ? 0 : tile / p.per_class;
                 const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
-                const uint32_t as = t & 1;
-                tc::mbar_wait(acc_empty + 8 * as, ((t >> 1) & 1) ^ 1);
+                const uint32_t as = t & (NACC - 1);
+                CONVG_TS(t, 0);
+                tc::mbar_wait(acc_empty + 8 * as, ((t >> ACC_LOG) & 1) ^ 1);
                 tc::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * 256;
+                CONVG_TS(t, 1);
+                const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
                 if (p.halo) {
                     for (int i = 0; i < cnt; i += 9) {
                         tc::mbar_wait(a_full + 8 * sa, pa);
                         tc::tc_fence_after();
+                        CONVG_TS(t, 2);
                         const uint32_t a_tile = lo0 + ((smem_base + sa * A_SLOT) >> 4);
                         const uint32_t b_res = lo0 + ((b_base + (uint32_t)(i0 + i) * B_SLOT) >> 4);
 #pragma unroll
@@ -256,8 +273,10 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
                         }
                         tc::umma_commit(a_empty + 8 * sa);
                         if (i + 9 >= cnt) tc::umma_commit(acc_full + 8 * as);
+                        CONVG_TS(t, 3);
                         if (++sa == NA) { sa = 0; pa ^= 1; }
                     }
+                    for (int k = 0; k < skip; ++k) { if (++sa == NA) { sa = 0; pa ^= 1; } }
                 } else {
                     for (int i = 0; i < cnt; ++i) {
                         tc::mbar_wait(a_full + 8 * sa, pa);
@@ -279,18 +298,20 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
         }
         __syncwarp();
     } else {
-        const int q = warp & 3, et = (warp - 2) * 32 + lane;     // et: 0..127, thread 0 issues the stores
+        const int q = warp & 3, et = (warp - 3) * 32 + lane;     // et: 0..127, thread 0 issues the stores
         const int row = q * 32 + lane;                           // position inside the tile == TMEM lane
         const int groups = p.BN >> 6;      // 0 in thin mode
         uint32_t t = 0, sg = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
             CONVG_DECODE_TILE(tile, nt, tx, ty, n, cls)
-            const uint32_t as = t & 1;
-            tc::mbar_wait(acc_full + 8 * as, (t >> 1) & 1);
+            const uint32_t as = t & (NACC - 1);
+            if (et == 0) CONVG_TS(t, 4);
+            tc::mbar_wait(acc_full + 8 * as, (t >> ACC_LOG) & 1);
             tc::tc_fence_after();
+            if (et == 0) CONVG_TS(t, 5);
             if (p.thin) {
                 uint32_t v[32];
-                tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256, v);
+                tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE, v);
                 const int gy = ty * p.th + row / p.tw, gx = tx * p.tw + row % p.tw;
                 if (gy < p.H && gx < p.W) {
                     const long long pix = (long long)gy * p.W + gx;
@@ -313,7 +334,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t v[32];
-                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + g * 64 + h * 32, v);
+                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE + g * 64 + h * 32, v);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float f[8];
@@ -328,6 +349,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
                 }
                 if (!(dbg & 4)) tc::fence_proxy_async();
                 tc::epi_bar();
+                if (et == 0 && g == 0) CONVG_TS(t, 6);
                 if (et == 0 && !(dbg & 4)) {
                     tc::tma_store_5d(&tmap_out, buf, p.cls_out_c[cls] + ch0, tx * p.tw, p.cls_out_py[cls], ty * p.th, n);
                     tc::bulk_commit();
@@ -335,6 +357,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
             }
             tc::tc_fence_before();
             tc::mbar_arrive(acc_empty + 8 * as);
+            if (et == 0) CONVG_TS(t, 7);
         }
         if (et == 0) tc::bulk_wait_all();
     }

@@ -38,6 +38,13 @@ int ptta_convg_debug_set(int mask) {
     return 0;
 }
 
+int ptta_convg_debug_read_ts(long long* out_host, int n) {
+    PTTA_CHECK(out_host && n > 0 && n <= 64 * 16, "convg_debug_read_ts: bad arguments");
+    PTTA_CUDA(cudaDeviceSynchronize());
+    PTTA_CUDA(cudaMemcpyFromSymbol(out_host, g_convg_ts, (size_t)n * sizeof(long long)));
+    return 0;
+}
+
 int ptta_convg_run_thin(const void* x0, const void* x1, const void* packed, const float* bias, float* const* planes, const long long* nstrides,
                         const int* acts, int n_real, int n, int h, int w, int cin0, int cin1, ptta_stream_t stream) {
     ConvGPlan pl;
