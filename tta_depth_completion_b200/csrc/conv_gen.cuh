@@ -49,6 +49,7 @@ struct ConvGParams {
     // (BN x 128 B); b_resident: every B tile of the layer is loaded once and stays in shared memory
     int n_a, a_slot_bytes, a_tx_bytes, n_b, b_slot_bytes, b_resident, halo;
     int halo_rev;        // data-gradient role: tap (ky, kx) reads the halo at (2-ky, 2-kx)
+    int b_group;         // streamed weights in halo mode: taps per B stage (3 = one kernel row per barrier round, 1 otherwise)
     // tile index -> (n-tile, tile x, tile y, image, class) without integer division: q = umulhi(x, mul) >> shr (d > 1)
     unsigned div_mul[4], div_shr[4];
     int per_class;
@@ -189,13 +190,15 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
                         CONVG_TS(tlp, 9);
                         if (++sa == NA) { sa = 0; pa ^= 1; }
                         if (!p.b_resident) {
-                            for (int tap = 0; tap < 9; ++tap) {
+                            const int bg = p.b_group;                    // taps per stage: B_SLOT holds bg weight tiles
+                            for (int tap = 0; tap < 9; tap += bg) {
                                 tc::mbar_wait(b_empty + 8 * sb, pb);
                                 if (dbg & 16) {
                                     tc::mbar_arrive(b_full + 8 * sb);
                                 } else {
-                                    tc::mbar_arrive_expect_tx(b_full + 8 * sb, b_tx);
-                                    tc::tma_load_3d(b_base + sb * B_SLOT, &tmap_b, b_full + 8 * sb, 0, nt * p.BN, i0 + i + tap);
+                                    tc::mbar_arrive_expect_tx(b_full + 8 * sb, b_tx * bg);
+                                    for (int u = 0; u < bg; ++u)
+                                        tc::tma_load_3d(b_base + sb * B_SLOT + u * (B_SLOT / bg), &tmap_b, b_full + 8 * sb, 0, nt * p.BN, i0 + i + tap + u);
                                 }
                                 if (++sb == NB) { sb = 0; pb ^= 1; }
                             }
@@ -253,9 +256,12 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
                         for (int tap = 0; tap < 9; ++tap) {
                             uint32_t b_lo = b_res + (uint32_t)tap * (B_SLOT >> 4);
                             if (!p.b_resident) {
-                                tc::mbar_wait(b_full + 8 * sb, pb);
-                                tc::tc_fence_after();
-                                b_lo = lo0 + ((b_base + sb * B_SLOT) >> 4);
+                                const int bg = p.b_group, u = bg == 3 ? tap % 3 : 0;
+                                if (u == 0) {
+                                    tc::mbar_wait(b_full + 8 * sb, pb);
+                                    tc::tc_fence_after();
+                                }
+                                b_lo = lo0 + ((b_base + sb * B_SLOT + u * (B_SLOT / bg)) >> 4);
                             }
                             const int hy = tap / 3, hx = tap - hy * 3;
                             const uint32_t off_f = (uint32_t)(hy * C::HALO_W + hx) * 8, off_r = (uint32_t)((2 - hy) * C::HALO_W + (2 - hx)) * 8;
@@ -266,7 +272,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
 #pragma unroll
                                 for (int k = 1; k < 4; ++k) tc::umma_f16_split<true>(d_tmem, a_lo + k * 2, a_hi, b_lo + k * 2, b_hi, idesc);
                             }
-                            if (!p.b_resident) {
+                            if (!p.b_resident && (p.b_group == 1 || tap % 3 == 2)) {
                                 tc::umma_commit(b_empty + 8 * sb);
                                 if (++sb == NB) { sb = 0; pb ^= 1; }
                             }
@@ -555,11 +561,18 @@ inline int convg_make_plan(ConvGPlan& pl, int kind, int role, int n, int h, int 
     // operand rings
     const int b_tile = ((BN * 128 + 1023) / 1024) * 1024;
     pl.p.b_slot_bytes = b_tile;
+    pl.p.b_group = 1;
     if (pl.p.halo) {
         pl.p.a_slot_bytes = ConvGCfg::HALO_SLOT; pl.p.a_tx_bytes = ConvGCfg::HALO_BYTES;
         if (pl.p.n_tiles == 1 && ni * b_tile <= 96 * 1024) {
             pl.p.b_resident = 1; pl.p.n_b = 0;
             pl.p.n_a = (ConvGCfg::RING_BYTES - ni * b_tile) / ConvGCfg::HALO_SLOT;
+        } else if (2 * (3 * b_tile) + 2 * ConvGCfg::HALO_SLOT <= ConvGCfg::RING_BYTES) {
+            // one kernel row (3 taps) of weights per stage: one barrier round per 12 MMAs instead of per 4
+            pl.p.b_group = 3;
+            pl.p.b_slot_bytes = 3 * b_tile;
+            pl.p.n_a = 2;
+            pl.p.n_b = (ConvGCfg::RING_BYTES - pl.p.n_a * ConvGCfg::HALO_SLOT) / (3 * b_tile);
         } else {
             pl.p.n_a = BN >= 256 ? 2 : 3;
             pl.p.n_b = (ConvGCfg::RING_BYTES - pl.p.n_a * ConvGCfg::HALO_SLOT) / b_tile;
