@@ -165,7 +165,8 @@ int ptta_convg_run(int kind, int role, const void* x0_bf16, const void* x1_bf16,
  * {start, count, out_c, out_py} per class, then {c_inner, dx, dy, py, src, wsel, tap, k0} per item; returns the ints written */
 int ptta_convg_plan_describe(int kind, int role, int n, int h, int w, int cin0, int cin1, int cout, int has_short, int* out,
                              int capacity);
-/* timing experiments only: 1 one MMA per K-item, 2 no epilogue work, 4 no epilogue fence / store (results are then wrong) */
+/* timing experiments only: 1 one MMA per K-item, 2 no epilogue work, 4 no epilogue fence / store, 8 / 16 no A / B loads (results are
+ * then wrong); 32 (results stay right): streamed weight tiles multicast over clusters of two CTAs; 64: cycle stamps (read_ts) */
 int ptta_convg_debug_set(int mask);
 /* mask & 64: CTA 0 records clock64() stamps per tile ([tile][16 events]: issue thread 0-3, epilogue 4-7, producer 8-9); synchronises */
 int ptta_convg_debug_read_ts(long long* out_host, int n);

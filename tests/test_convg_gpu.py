@@ -143,3 +143,26 @@ def test_meta_conv_carries_depth_channels():
     assert torch.equal(out[..., 48:], x[..., 48:])
     ref = F.conv2d(_nchw(x)[:, :48], wt.to(torch.bfloat16).float(), bias, 1, 1)
     _check(out[..., :48], ref, 'meta conv 48->48')
+
+
+def test_weight_multicast_switch_is_bit_identical():
+    """experiment switch 32 (ptta_convg_debug_set): the streamed weight tiles are loaded half by each CTA of a 2-CTA cluster and
+    multicast to both; results must be bit-identical to the default launch (odd tile counts run a clipped ghost tile)"""
+    from tta_depth_completion_b200 import _lib
+    from tta_depth_completion_b200.convg import ConvG, FWD, DGRAD
+    dev = _dev()
+    g = torch.Generator().manual_seed(77)
+    L = _lib.lib()
+    try:
+        for c, n, h, w, role in ((128, 1, 40, 72, FWD), (256, 2, 17, 23, FWD), (128, 1, 48, 40, DGRAD)):
+            wt = (torch.randn((c, c, 3, 3), generator=g) * (2.0 / (c * 9)) ** 0.5).to(dev)
+            x = _rand_nhwc(g, n, h, w, c, dev)
+            op = ConvG('s1', role, wt, c, c)
+            L.ptta_convg_debug_set(0)
+            ref = op(x, hw=(h, w))
+            L.ptta_convg_debug_set(32)
+            got = op(x, hw=(h, w))
+            torch.cuda.synchronize()
+            assert torch.equal(ref, got), (c, n, h, w, role)
+    finally:
+        L.ptta_convg_debug_set(0)

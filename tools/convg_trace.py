@@ -26,6 +26,15 @@ _lib.check(L.ptta_convg_debug_read_ts(buf, 64 * 16), 'read_ts')
 L.ptta_convg_debug_set(0)
 ts = [[buf[t * 16 + k] for k in range(16)] for t in range(64)]
 t0 = ts[0][0]
+if ts[8][0] == 0:          # few tiles per CTA (streamed-weight layers): print everything, no steady-state summary
+    print('tile | issue: top accfree Aready(last chunk) issued(last chunk) | chunk 0: wait/got B taps 0, 3, 6 | epi: wait full staged released | prod: top tma')
+    for t in range(64):
+        r = ts[t]
+        if r[0] == 0 and t > 0:
+            break
+        print('%3d | %7d %7d %7d %7d | %7d %7d  %7d %7d  %7d %7d | %7d %7d %7d %7d | %7d %7d' % (
+            (t,) + tuple(v - t0 for v in r[:4]) + tuple(v - t0 for v in r[10:16]) + tuple(v - t0 for v in r[4:8]) + tuple(v - t0 for v in r[8:10])))
+    sys.exit(0)
 print('tile | issue: top accfree Aready issued | epi: wait full staged released | prod: top tma   (cycles since the first stamp)')
 for t in range(2, 24):
     r = ts[t]

@@ -49,6 +49,8 @@ struct ConvGParams {
     // (BN x 128 B); b_resident: every B tile of the layer is loaded once and stays in shared memory
     int n_a, a_slot_bytes, a_tx_bytes, n_b, b_slot_bytes, b_resident, halo;
     int halo_rev;        // data-gradient role: tap (ky, kx) reads the halo at (2-ky, 2-kx)
+    int mcast;           // 1: launched as clusters of 2 CTAs (adjacent tiles, same weights): each CTA loads half of every weight tile and
+                         // multicasts it to both, halving the L2 -> SM weight traffic that bounds the streamed-weight layers
     int b_group;         // streamed weights in halo mode: taps per B stage (3 = one kernel row per barrier round, 1 otherwise)
     // tile index -> (n-tile, tile x, tile y, image, class) without integer division: q = umulhi(x, mul) >> shr (d > 1)
     unsigned div_mul[4], div_shr[4];
@@ -85,6 +87,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+// weight tile multicast: the box lands at the same CTA-relative offset (and signals the same barrier offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+// tcgen05.commit that arrives on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -143,7 +162,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
         tc::prefetch_tmap(&tmap_out);
         for (int i = 0; i < C::MAX_STAGES; ++i) {
             tc::mbar_init(a_full + 8 * i, 1); tc::mbar_init(a_empty + 8 * i, 1);
-            tc::mbar_init(b_full + 8 * i, 1); tc::mbar_init(b_empty + 8 * i, 1);
+            tc::mbar_init(b_full + 8 * i, 1); tc::mbar_init(b_empty + 8 * i, p.mcast ? 2 : 1);
         }
         for (int i = 0; i < 8; ++i) { tc::mbar_init(acc_full + 8 * i, 1); tc::mbar_init(acc_empty + 8 * i, 128); }
         tc::mbar_init(w_full, 1);
@@ -152,8 +171,12 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
     tc::tc_fence_before();
     __syncthreads();
+    if (p.mcast) tc::cluster_sync();        // the peer's barriers are initialised before anything is multicast to them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t crank = p.mcast ? tc::cluster_ctarank() : 0u;
+    // multicast mode: tile indices run to an even count; a ghost tile (image index == N) loads zeros and stores nothing (TMA clips)
+    const int tiles_end = p.mcast ? ((p.total_tiles + 1) & ~1) : p.total_tiles;
 
     if (warp == 0) {
         // TMA producer: the warp stays converged, one elected lane issues (a divergent `if (lane == 0)` makes the compiler wrap
@@ -172,7 +195,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
         if (elect_one()) {
             uint32_t sa = 0, pa = 1, sb = 0, pb = 1;
             int tlp = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tlp) {
+            for (int tile = blockIdx.x; tile < tiles_end; tile += gridDim.x, ++tlp) {
                 CONVG_TS(tlp, 8);
                 CONVG_DECODE_TILE(tile, nt, tx, ty, n, cls)
                 const int gx0 = tx * p.tw, gy0 = ty * p.th;
@@ -197,8 +220,14 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
                                     tc::mbar_arrive(b_full + 8 * sb);
                                 } else {
                                     tc::mbar_arrive_expect_tx(b_full + 8 * sb, b_tx * bg);
-                                    for (int u = 0; u < bg; ++u)
-                                        tc::tma_load_3d(b_base + sb * B_SLOT + u * (B_SLOT / bg), &tmap_b, b_full + 8 * sb, 0, nt * p.BN, i0 + i + tap + u);
+                                    for (int u = 0; u < bg; ++u) {
+                                        const uint32_t dst = b_base + sb * B_SLOT + u * (B_SLOT / bg);
+                                        if (p.mcast)     // my half of the rows, to both CTAs of the pair
+                                            tc::tma_load_3d_mc(dst + crank * (b_tx >> 1), &tmap_b, b_full + 8 * sb, 0, nt * p.BN + crank * (p.BN >> 1),
+                                                               i0 + i + tap + u, (uint16_t)3);
+                                        else
+                                            tc::tma_load_3d(dst, &tmap_b, b_full + 8 * sb, 0, nt * p.BN, i0 + i + tap + u);
+                                    }
                                 }
                                 if (++sb == NB) { sb = 0; pb ^= 1; }
                             }
@@ -236,7 +265,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
             if (p.b_resident) { tc::mbar_wait(w_full, 0); tc::tc_fence_after(); }
             const int skip = (nissue - 1) * (p.cls_count[0] / 9);      // A-ring slots the other issuer consumes between two of my tiles
             for (int k = 0; k < me * (p.cls_count[0] / 9); ++k) { if (++sa == NA) { sa = 0; pa ^= 1; } }
-            for (int tile = blockIdx.x + me * gridDim.x; tile < p.total_tiles; tile += nissue * gridDim.x, t += nissue) {
+            for (int tile = blockIdx.x + me * gridDim.x; tile < tiles_end; tile += nissue * gridDim.x, t += nissue) {
                 const int cls = p.n_classes == 1 ? 0 : tile / p.per_class;
                 const int i0 = p.cls_start[cls], cnt = p.cls_count[cls];
                 const uint32_t as = t & (NACC - 1);
@@ -258,8 +287,10 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
                             if (!p.b_resident) {
                                 const int bg = p.b_group, u = bg == 3 ? tap % 3 : 0;
                                 if (u == 0) {
+                                    if (i == 0 && tap % 3 == 0) CONVG_TS(t, 10 + 2 * (tap / 3));        // chunk 0: before the wait of taps 0 / 3 / 6
                                     tc::mbar_wait(b_full + 8 * sb, pb);
                                     tc::tc_fence_after();
+                                    if (i == 0 && tap % 3 == 0) CONVG_TS(t, 11 + 2 * (tap / 3));        // ... and after it
                                 }
                                 b_lo = lo0 + ((b_base + sb * B_SLOT + u * (B_SLOT / bg)) >> 4);
                             }
@@ -273,7 +304,8 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
                                 for (int k = 1; k < 4; ++k) tc::umma_f16_split<true>(d_tmem, a_lo + k * 2, a_hi, b_lo + k * 2, b_hi, idesc);
                             }
                             if (!p.b_resident && (p.b_group == 1 || tap % 3 == 2)) {
-                                tc::umma_commit(b_empty + 8 * sb);
+                                if (p.mcast) tc::umma_commit_mc(b_empty + 8 * sb, (uint16_t)3);     // both CTAs' producers wait for both consumers
+                                else tc::umma_commit(b_empty + 8 * sb);
                                 if (++sb == NB) { sb = 0; pb ^= 1; }
                             }
                         }
@@ -308,7 +340,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
         const int row = q * 32 + lane;                           // position inside the tile == TMEM lane
         const int groups = p.BN >> 6;      // 0 in thin mode
         uint32_t t = 0, sg = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+        for (int tile = blockIdx.x; tile < tiles_end; tile += gridDim.x, ++t) {
             CONVG_DECODE_TILE(tile, nt, tx, ty, n, cls)
             const uint32_t as = t & (NACC - 1);
             if (et == 0) CONVG_TS(t, 4);
@@ -369,6 +401,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     }
     tc::tc_fence_before();
     __syncthreads();
+    if (p.mcast) tc::cluster_sync();        // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
@@ -401,6 +434,9 @@ __global__ void __launch_bounds__(256) pack_convg_kernel(const __grid_constant__
         out[((size_t)wk * p.n_pad + n) * 64 + j] = __float2bfloat16(v);
     }
 }
+
+inline int& convg_multicast_flag() { static int f = 0; return f; }
+inline bool convg_multicast_enabled() { return convg_multicast_flag() != 0; }
 
 // ---- host side: plans ------------------------------------------------------------------------------------------------------
 enum { CONVG_S1 = 0, CONVG_S2 = 1, CONVG_T2 = 2, CONVG_P1S2 = 3 };
@@ -581,6 +617,10 @@ inline int convg_make_plan(ConvGPlan& pl, int kind, int role, int n, int h, int 
         pl.p.a_slot_bytes = pl.p.a_tx_bytes = ConvGCfg::A_BYTES;
         pl.p.n_a = pl.p.n_b = ConvGCfg::RING_BYTES / (ConvGCfg::A_BYTES + b_tile);
     }
+    // weight-tile multicast over clusters of two CTAs: implemented and parity-tested, but it does not shorten the streamed-weight layers
+    // (128->128: 29.3 us with and without: the per-tile trace shows them MMA-bound at ~75 cycles per N = 128 MMA with 8 us of
+    // prologue / tail per launch, not L2-bound), so it stays an experiment switch: convg_multicast_enabled() <- ptta_convg_debug_set(32)
+    pl.p.mcast = (convg_multicast_enabled() && pl.p.halo && !pl.p.b_resident && pl.p.n_tiles == 1 && BN % 16 == 0 && pl.p.total_tiles >= 2) ? 1 : 0;
     if (pl.p.n_a > ConvGCfg::MAX_STAGES) pl.p.n_a = ConvGCfg::MAX_STAGES;
     if (pl.p.n_b > ConvGCfg::MAX_STAGES) pl.p.n_b = ConvGCfg::MAX_STAGES;
     return 0;
@@ -658,13 +698,26 @@ inline int launch_convg(const ConvGPlan& pl, const bf16* x0, const bf16* x1, con
     PTTA_TRY(make_tmap_view5(&ta0, x0, p.N, pl.in_h, pl.in_w, pl.k_src[0], pl.in_parity, ath, atw));
     if (pl.k_src[1]) PTTA_TRY(make_tmap_view5(&ta1, x1, p.N, pl.in_h, pl.in_w, pl.k_src[1], pl.in_parity, ath, atw));
     else ta1 = ta0;
-    PTTA_TRY(make_tmap_wpk(&tb, packed, pl.n_items, pl.n_out, p.BN));
+    PTTA_TRY(make_tmap_wpk(&tb, packed, pl.n_items, pl.n_out, p.mcast ? p.BN / 2 : p.BN));
     if (p.thin) to = ta0;
     else PTTA_TRY(make_tmap_view5(&to, out, p.N, pl.out_h, pl.out_w, pl.n_out, pl.out_parity, p.th, p.tw));
     ConvGParams pr = p;
     pr.bias = bias;
     pr.H = pl.out_h; pr.W = pl.out_w;
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    if (p.mcast) {
+        int g2 = grid & ~1;                      // clusters of two CTAs
+        if (g2 < 2) g2 = 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(g2); cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        PTTA_CUDA(cudaLaunchKernelEx(&cfg, convg_kernel, ta0, ta1, tb, to, pr));
+        return check_launch("convg(mc)");
+    }
     convg_kernel<<<grid, C::THREADS, C::SMEM, st>>>(ta0, ta1, tb, to, pr);
     return check_launch("convg");
 }

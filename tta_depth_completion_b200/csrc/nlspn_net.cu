@@ -34,6 +34,7 @@ int ptta_convg_run(int kind, int role, const void* x0, const void* x1, const voi
 }
 
 int ptta_convg_debug_set(int mask) {
+    convg_multicast_flag() = (mask & 32) ? 1 : 0;          // host-side switch: weight-tile multicast over 2-CTA clusters
     PTTA_CUDA(cudaMemcpyToSymbol(g_convg_dbg, &mask, sizeof(int)));
     return 0;
 }
