@@ -26,6 +26,7 @@ _lib.check(L.ptta_convg_debug_read_ts(buf, 64 * 16), 'read_ts')
 L.ptta_convg_debug_set(0)
 ts = [[buf[t * 16 + k] for k in range(16)] for t in range(64)]
 t0 = ts[0][0]
+print('kernel entry %d, set-up done %d, first tile top 0, all roles finished %d (cycles relative to the first tile)' % (ts[63][0] - t0, ts[63][1] - t0, ts[63][2] - t0))
 if ts[8][0] == 0:          # few tiles per CTA (streamed-weight layers): print everything, no steady-state summary
     print('tile | issue: top accfree Aready(last chunk) issued(last chunk) | chunk 0: wait/got B taps 0, 3, 6 | epi: wait full staged released | prod: top tma')
     for t in range(64):

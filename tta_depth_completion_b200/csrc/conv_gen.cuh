@@ -151,6 +151,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dbg = g_convg_dbg;
+    if (tid == 0) CONVG_TS(63, 0);                   // kernel entry
     const uint32_t NA = p.n_a, NB = p.n_b, A_SLOT = p.a_slot_bytes, B_SLOT = p.b_slot_bytes;
     const uint32_t b_base = smem_base + NA * A_SLOT;            // B ring, or the resident weights
     const uint32_t b_tx = (uint32_t)p.BN * 128u;
@@ -174,6 +175,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     if (p.mcast) tc::cluster_sync();        // the peer's barriers are initialised before anything is multicast to them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    if (tid == 0) CONVG_TS(63, 1);                   // set-up done (barriers, TMEM allocation)
     const uint32_t crank = p.mcast ? tc::cluster_ctarank() : 0u;
     // multicast mode: tile indices run to an even count; a ghost tile (image index == N) loads zeros and stores nothing (TMA clips)
     const int tiles_end = p.mcast ? ((p.total_tiles + 1) & ~1) : p.total_tiles;
@@ -401,6 +403,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     }
     tc::tc_fence_before();
     __syncthreads();
+    if (tid == 0) CONVG_TS(63, 2);                   // all roles finished (stores drained)
     if (p.mcast) tc::cluster_sync();        // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc::tc_fence_after();
