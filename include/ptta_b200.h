@@ -170,6 +170,8 @@ int ptta_convg_plan_describe(int kind, int role, int n, int h, int w, int cin0, 
 int ptta_convg_debug_set(int mask);
 /* mask & 64: CTA 0 records clock64() stamps per tile ([tile][16 events]: issue thread 0-3, epilogue 4-7, producer 8-9); synchronises */
 int ptta_convg_debug_read_ts(long long* out_host, int n);
+/* mask & 64: %globaltimer (ns) at entry / exit of every CTA ([cta][2]) */
+int ptta_convg_debug_read_cta(unsigned long long* out_host, int n);
 /* thin heads id_dec0 / gd_dec0 / cf_dec0 (nlspnmodel_adapt.py:430-448, 883-895) as ONE 16-output-channel conv over the concat
  * (x0 | x1): fp32 planar outputs through per-channel plane pointers (host arrays of n_real entries), activation per channel
  * (0 none, 1 LeakyReLU(0.2), 2 sigmoid).  Weights packed by ptta_convg_pack(kind 0, role 0, ..., cout = 16). */

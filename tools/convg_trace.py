@@ -24,6 +24,16 @@ op(x, out=out)
 buf = (ctypes.c_longlong * (64 * 16))()
 _lib.check(L.ptta_convg_debug_read_ts(buf, 64 * 16), 'read_ts')
 L.ptta_convg_debug_set(0)
+cta = (ctypes.c_ulonglong * 296)()
+_lib.check(L.ptta_convg_debug_read_cta(cta, 296), 'read_cta')
+spans = [(cta[2 * i], cta[2 * i + 1]) for i in range(148) if cta[2 * i + 1] > 0]
+if spans:
+    first = min(a for a, b in spans)
+    durs = sorted((b - a) / 1e3 for a, b in spans)
+    print('CTAs: %d; start spread %.2f us; busy min %.2f median %.2f max %.2f us; last exit at %.2f us after the first entry' % (
+        len(spans), (max(a for a, b in spans) - first) / 1e3, durs[0], durs[len(durs) // 2], durs[-1], (max(b for a, b in spans) - first) / 1e3))
+    late = sorted(((b - first) / 1e3, i) for i, (a, b) in enumerate(spans))[-5:]
+    print('latest exits (us, cta):', [(round(t, 2), i) for t, i in late])
 ts = [[buf[t * 16 + k] for k in range(16)] for t in range(64)]
 t0 = ts[0][0]
 print('kernel entry %d, set-up done %d, first tile top 0, all roles finished %d (cycles relative to the first tile)' % (ts[63][0] - t0, ts[63][1] - t0, ts[63][2] - t0))

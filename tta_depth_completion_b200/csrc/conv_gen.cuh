@@ -130,6 +130,12 @@ __device__ __forceinline__ void fast_divmod(int x, int d, unsigned mul, unsigned
 
 __device__ long long g_convg_ts[64 * 16];   // timing experiments (dbg & 64): clock64() stamps of CTA 0, [tile][event]
 #define CONVG_TS(tl, k) do { if ((dbg & 64) && blockIdx.x == 0 && (tl) < 64) g_convg_ts[(tl) * 16 + (k)] = clock64(); } while (0)
+__device__ unsigned long long g_convg_cta[256 * 2];   // dbg & 64: %globaltimer (ns) at entry / exit of every CTA
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ int g_convg_dbg = 0;   // timing experiments only (ptta_convg_debug_set): 1 one MMA per item, 2 no epilogue work, 4 no fence/store
 
 __global__ void __launch_bounds__(ConvGCfg::THREADS, 1)
@@ -152,6 +158,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dbg = g_convg_dbg;
     if (tid == 0) CONVG_TS(63, 0);                   // kernel entry
+    if ((dbg & 64) && tid == 0 && blockIdx.x < 256) g_convg_cta[blockIdx.x * 2] = globaltimer_ns();
     const uint32_t NA = p.n_a, NB = p.n_b, A_SLOT = p.a_slot_bytes, B_SLOT = p.b_slot_bytes;
     const uint32_t b_base = smem_base + NA * A_SLOT;            // B ring, or the resident weights
     const uint32_t b_tx = (uint32_t)p.BN * 128u;
@@ -404,6 +411,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     tc::tc_fence_before();
     __syncthreads();
     if (tid == 0) CONVG_TS(63, 2);                   // all roles finished (stores drained)
+    if ((dbg & 64) && tid == 0 && blockIdx.x < 256) g_convg_cta[blockIdx.x * 2 + 1] = globaltimer_ns();
     if (p.mcast) tc::cluster_sync();        // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc::tc_fence_after();

@@ -39,6 +39,13 @@ int ptta_convg_debug_set(int mask) {
     return 0;
 }
 
+int ptta_convg_debug_read_cta(unsigned long long* out_host, int n) {
+    PTTA_CHECK(out_host && n > 0 && n <= 512, "convg_debug_read_cta: bad arguments");
+    PTTA_CUDA(cudaDeviceSynchronize());
+    PTTA_CUDA(cudaMemcpyFromSymbol(out_host, g_convg_cta, (size_t)n * sizeof(unsigned long long)));
+    return 0;
+}
+
 int ptta_convg_debug_read_ts(long long* out_host, int n) {
     PTTA_CHECK(out_host && n > 0 && n <= 64 * 16, "convg_debug_read_ts: bad arguments");
     PTTA_CUDA(cudaDeviceSynchronize());
