@@ -150,18 +150,18 @@ class LossReader:
 
 
 def make_frames(workload, batch, count, seq_seed):
-    from oracle import msgchn_oracle as O          # synthetic-input generator only
+    from tta_depth_completion_b200 import synthetic          # seeded input generators; no oracle on the product arm
     h, w, dataset = WORKLOADS[workload][:3]
     frames = []
     for t in range(count):
-        image, sparse, _ = O.synthetic_frame(seq_seed, t, batch, h, w, dataset)
+        image, sparse, _ = synthetic.synthetic_frame(seq_seed, t, batch, h, w, dataset)
         frames.append((image.contiguous(), sparse.contiguous()))
     return frames
 
 
 def make_checkpoint(workload):
-    from oracle import msgchn_oracle as O
-    return O.make_synthetic_checkpoint(0, WORKLOADS[workload][3])
+    from tta_depth_completion_b200 import synthetic
+    return synthetic.make_synthetic_checkpoint(0, WORKLOADS[workload][3])
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -364,7 +364,7 @@ def time_convg_kernel(dev, peaks, iters=24):
 
 def run_native_nlspn(args):
     """BASELINE.json configs[3]: NLSPN ProxyTTA at 352x1216, one adapting model per GPU, no collective."""
-    from oracle import nlspn_oracle as NO              # synthetic checkpoint / frame generators only
+    from tta_depth_completion_b200 import synthetic as NO
     from tta_depth_completion_b200.nlspn_engine import NlspnEngine
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -378,7 +378,7 @@ def run_native_nlspn(args):
         dist.init_process_group('nccl', device_id=dev)
     h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
     peaks = load_peaks()
-    eng = NlspnEngine(NO.make_synthetic_checkpoint(0), args.batch, h, w, dev)
+    eng = NlspnEngine(NO.make_nlspn_checkpoint(0), args.batch, h, w, dev)
     mean, std = NO.IMAGENET_MEAN, NO.IMAGENET_STD
     eng.set_image_normalization([1.0 / (255.0 * s) for s in std], [-m / s for m, s in zip(mean, std)])
     frames = [NO.synthetic_frame(1 + rank, t, args.batch, h, w, dataset)[:2] for t in range(RING)]

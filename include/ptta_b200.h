@@ -250,6 +250,10 @@ int ptta_input_stage(const void* image_u8_hwc, const void* depth_u16, float* ima
 /* prepare_mode: the reference's string, e.g. "meta_selfsup_seq_2layers_ema" (network_exp_msg_chn_adapt.py:1022-1087) */
 int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepare_mode);
 void ptta_msgchn_destroy(ptta_msgchn* e);
+/* dispatch options (results stay right for every value; used by the parity tests to run ALL kernel families at every size):
+ * "tc_min_pixels" / "tc_s2_min_pixels": smallest map (N*H*W) the stride-1 / stride-2 tcgen05 convs take (0 = always),
+ * "tc_enabled" 0/1, "two_streams" 0/1, "fuse_dec_sums" 0/1.  Unknown names fail. */
+int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value);
 size_t ptta_msgchn_workspace_bytes(const ptta_msgchn* e);
 int ptta_msgchn_bind_workspace(ptta_msgchn* e, void* workspace, size_t bytes, ptta_stream_t stream);
 /* bind one state-dict entry (fp32, or int64 for num_batches_tracked) by its reference key; also

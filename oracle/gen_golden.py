@@ -40,6 +40,17 @@ CASES = [
     # H, W not multiples of 16 -> exercises the pad + flip-pad ensembling of src/msg_chn_model_adapt.py:58-125
     dict(name='msgchn_2layers_kitti_1x40x72_pad', prepare_mode='meta_selfsup_seq_2layers_ema', dataset='kitti',
          n=1, h=40, w=72, steps=1, lr=1e-4, max_input_depth=80.0, ckpt_seed=0, seq_seed=7, density=None),
+    # FITTED checkpoints (oracle/make_fitted_checkpoint.py: the reference's own supervised / head stages in miniature): the network
+    # predicts depth (MAE ~0.5 m instead of ~40 m), loss_cos is O(0.1-1) instead of 2.0
+    dict(name='msgchn_fit_kitti_1x64x128', prepare_mode='meta_selfsup_seq_2layers_ema', dataset='kitti', ckpt='kitti_2layers_a',
+         n=1, h=64, w=128, steps=3, lr=1e-4, max_input_depth=80.0, ckpt_seed=None, seq_seed=21, density=None),
+    # ... and with the heads fully fitted: loss_cos < 0.3, so the gate of src/external_model_adapt.py:424 sets w_cos = 0
+    dict(name='msgchn_fit_kitti_gate_2x48x80', prepare_mode='meta_selfsup_seq_2layers_ema', dataset='kitti', ckpt='kitti_2layers_b',
+         n=2, h=48, w=80, steps=3, lr=1e-4, max_input_depth=80.0, ckpt_seed=None, seq_seed=22, density=None),
+    dict(name='msgchn_fit_void_1x48x64', prepare_mode='meta_selfsup_seq_1layer_ema', dataset='void', ckpt='void_1layer_a',
+         n=1, h=48, w=64, steps=3, lr=3e-3, max_input_depth=8.0, ckpt_seed=None, seq_seed=23, density=0.03),
+    dict(name='msgchn_fit_kitti_1x40x72_pad', prepare_mode='meta_selfsup_seq_2layers_ema', dataset='kitti', ckpt='kitti_2layers_a',
+         n=1, h=40, w=72, steps=2, lr=1e-4, max_input_depth=80.0, ckpt_seed=None, seq_seed=24, density=None),
 ]
 W_SD, W_SM, W_COS = 1.0, 1.0, 0.1
 
@@ -56,7 +67,7 @@ def case_frame(case, t):
 
 def run_reference_case(case):
     ref = ref_shims.load_reference()
-    sd0 = O.make_synthetic_checkpoint(case['ckpt_seed'], case['prepare_mode'])
+    sd0 = O.get_checkpoint(case.get('ckpt', case['ckpt_seed']), case['prepare_mode'])
     model = ref_shims.build_reference_msgchn(case['prepare_mode'], case['max_input_depth'])
     net = model.model.model
     missing = net.load_state_dict(sd0, strict=True)        # same keys/shapes as the reference checkpoint
@@ -89,6 +100,7 @@ def run_reference_case(case):
             'grad_norm': grad_norms,
             'param_norm': {k: float(dict(net.named_parameters())[k].detach().norm()) for k in names},
             'n_valid': int(fvm.sum()), 'n_valid_in': int(validity_map_depth.sum()),
+            'w_cos_eff': 0.0 if float(info['loss_cos']) < 0.3 else W_COS,
         })
     model.eval()
     with torch.no_grad():
@@ -113,7 +125,10 @@ def run_reference_case(case):
 def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = sys.argv[1:]
     for case in CASES:
+        if only and not any(o in case['name'] for o in only):
+            continue
         fx = run_reference_case(case)
         path = os.path.join(GOLDEN_DIR, case['name'] + '.pt')
         torch.save(fx, path)

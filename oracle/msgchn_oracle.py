@@ -55,134 +55,10 @@ FP32 = Precision(None)
 
 
 # ----------------------------------------------------------------------------------------------
-# synthetic checkpoint / frames
+# synthetic checkpoint / frames: input generators shared with bench.py, re-exported
 # ----------------------------------------------------------------------------------------------
-def _conv_entry(sd, g, name, cout, cin, bias=True, transposed=False):
-    # N:188-194  xavier_normal_ weights, bias 0.01 (encoders / decoders)
-    shape = (cin, cout, 3, 3) if transposed else (cout, cin, 3, 3)
-    fan_in, fan_out = cin * 9, cout * 9
-    if transposed:
-        fan_in, fan_out = cout * 9, cin * 9
-    std = math.sqrt(2.0 / (fan_in + fan_out))
-    sd[name + '.weight'] = torch.randn(shape, generator=g) * std
-    if bias:
-        sd[name + '.bias'] = torch.full((cout,), 0.01)
-
-
-def _bn_entry(sd, g, name, c):
-    # affine / running stats perturbed away from the (1, 0, 0, 1) init so that tests see them
-    sd[name + '.weight'] = 1.0 + 0.1 * torch.randn(c, generator=g)
-    sd[name + '.bias'] = 0.05 * torch.randn(c, generator=g)
-    sd[name + '.running_mean'] = 0.05 * torch.randn(c, generator=g)
-    sd[name + '.running_var'] = 1.0 + 0.1 * torch.rand(c, generator=g)
-    sd[name + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
-
-
-def _linear_entry(sd, g, name, cout, cin):
-    bound = 1.0 / math.sqrt(cin)       # nn.Linear default: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
-    sd[name + '.weight'] = (torch.rand((cout, cin), generator=g) * 2 - 1) * bound
-    sd[name + '.bias'] = (torch.rand((cout,), generator=g) * 2 - 1) * bound
-
-
-def _mlp_entries(sd, g, name, dim, out, hidden):
-    # N:1089-1098  Linear -> BatchNorm1d -> ReLU -> Linear
-    _linear_entry(sd, g, name + '.0', hidden, dim)
-    _bn_entry(sd, g, name + '.1', hidden)
-    _linear_entry(sd, g, name + '.3', out, hidden)
-
-
-def make_synthetic_checkpoint(seed=0, prepare_mode='meta_selfsup_seq_2layers_ema'):
-    """Seeded stand-in for the Google-Drive checkpoints (none is in the reference tree).  Key set
-    and shapes follow N:166-335 (network) and N:1022-1087 (`_prepare_head`)."""
-    g = torch.Generator().manual_seed(seed)
-    sd = OrderedDict()
-
-    def encoder(prefix, cin, n_enc):
-        _conv_entry(sd, g, prefix + '.init.0', 32, cin)
-        _conv_entry(sd, g, prefix + '.init.2', 32, 32)
-        for k in range(1, n_enc + 1):
-            _conv_entry(sd, g, '%s.enc%d.1' % (prefix, k), 32, 32)
-            _conv_entry(sd, g, '%s.enc%d.3' % (prefix, k), 32, 32)
-
-    def decoder(prefix):
-        for blk in ('dec2', 'dec1'):
-            _conv_entry(sd, g, '%s.%s.1' % (prefix, blk), 32, 32, transposed=True)
-            _conv_entry(sd, g, '%s.%s.3' % (prefix, blk), 32, 32)
-        _conv_entry(sd, g, prefix + '.prdct.1', 32, 32)
-        _conv_entry(sd, g, prefix + '.prdct.3', 1, 32)
-
-    encoder('rgb_encoder', 3, 4)
-    encoder('depth_encoder1', 1, 2)
-    decoder('depth_decoder1')
-    encoder('depth_encoder2', 2, 2)
-    decoder('depth_decoder2')
-    encoder('depth_encoder3', 2, 2)
-    decoder('depth_decoder3')
-    if 'selfsup' in prepare_mode:
-        _mlp_entries(sd, g, 'proj', 32, 512, 512)
-        if 'ema' in prepare_mode:
-            for k in [k for k in sd if k.startswith('proj.')]:
-                sd['proj_t.' + k[5:]] = sd[k].clone()
-        _mlp_entries(sd, g, 'pred', 512, 512, 512)
-    if 'meta' in prepare_mode and 'seq' in prepare_mode:
-        if '1layer' in prepare_mode:
-            # N:1066-1068  Conv2d(32,32,3,1,1), kaiming_normal fan_out
-            sd['conv1_rgb_meta.weight'] = torch.randn((32, 32, 3, 3), generator=g) * math.sqrt(2.0 / (32 * 9))
-            sd['conv1_rgb_meta.bias'] = (torch.rand((32,), generator=g) * 2 - 1) / math.sqrt(32 * 9)
-        elif '2layers' in prepare_mode:
-            # N:28-36, 1073  Res_Conv(32,128,3,1,1)
-            p = 'conv1_rgb_meta.conv1_meta'
-            bound = 1.0 / math.sqrt(32 * 9)
-            sd[p + '.0.0.weight'] = (torch.rand((128, 32, 3, 3), generator=g) * 2 - 1) * bound
-            _bn_entry(sd, g, p + '.0.1', 128)
-            bound = 1.0 / math.sqrt(128 * 9)
-            sd[p + '.1.weight'] = (torch.rand((32, 128, 3, 3), generator=g) * 2 - 1) * bound
-            sd[p + '.1.bias'] = (torch.rand((32,), generator=g) * 2 - 1) * bound
-            _bn_entry(sd, g, p + '.2', 32)
-        else:
-            raise NotImplementedError(prepare_mode)
-    return sd
-
-
-def checkpoint_digest(sd):
-    """Order-independent fingerprint of a state dict (guards the 'same seed -> same checkpoint on
-    the GPU box' assumption the fixtures rely on)."""
-    tot = 0.0
-    for k in sorted(sd):
-        v = sd[k].double()
-        tot += float(v.sum()) + 0.5 * float(v.abs().sum()) + 1e-3 * v.numel()
-    return tot
-
-
-DATASETS = {
-    # name: (sampling density, depth cap, dense depth surface)  -- SURVEY.md §8d
-    'kitti': (0.05, 80.0),
-    'void': (0.005, 8.0),
-}
-
-
-def synthetic_frame(seq_seed, t, n, h, w, dataset='kitti', outlier_fraction=0.01):
-    """Frame t of synthetic sequence `seq_seed`: image in [0,255]; sparse depth = smooth
-    surface x Bernoulli(p), with ~1 % of the samples pushed +5 m so the outlier filter has work."""
-    p, cap = DATASETS[dataset]
-    g = torch.Generator().manual_seed(1000 * seq_seed + t)
-    yy = torch.arange(h, dtype=torch.float32).view(1, 1, h, 1)
-    xx = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w)
-    # smooth texture + +-4 grey levels of noise: i.i.d. uniform [0,255] pixels would make the
-    # edge-aware weights exp(-|dI|) underflow to 0 and the smoothness loss vanish
-    ph = torch.tensor([0.0, 1.3, 2.1]).view(1, 3, 1, 1)
-    image = 127.0 + 100.0 * torch.sin(xx / 31.0 + ph + 0.05 * t) * torch.cos(yy / 17.0 + 0.5 * ph)
-    image = image + 8.0 * (torch.rand((n, 3, h, w), generator=g) - 0.5)
-    image = image.clamp(0.0, 255.0).contiguous()
-    if dataset == 'kitti':
-        dense = 5.0 + 70.0 * (1.0 - yy / h) + 2.0 * torch.sin((xx + 3.0 * t) / 97.0)
-    else:
-        dense = 0.5 + 4.0 * (yy / h) + 0.3 * torch.sin((xx + 3.0 * t) / 53.0)
-    dense = dense.expand(n, 1, h, w).contiguous()
-    mask = (torch.rand((n, 1, h, w), generator=g) < p).float()
-    out = (torch.rand((n, 1, h, w), generator=g) < outlier_fraction).float()
-    sparse = (dense + 5.0 * out * (cap / 80.0)) * mask
-    return image, sparse, dense
+from tta_depth_completion_b200.synthetic import (make_synthetic_checkpoint, checkpoint_digest, synthetic_frame, DATASETS,  # noqa: E402,F401
+                                                 load_fitted_checkpoint, get_checkpoint, fitted_checkpoint_available)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -47,85 +47,10 @@ FP32 = O.FP32
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# synthetic checkpoint: seeded, so the GPU box regenerates the identical state dict
+# synthetic checkpoint / frames: input generators shared with bench.py, re-exported
 # ----------------------------------------------------------------------------------------------------------------
-def _conv(sd, g, name, cout, cin, k=3, bias=False, transposed=False, gain=1.0):
-    shape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
-    std = gain * math.sqrt(2.0 / (cin * k * k))
-    sd[name + '.weight'] = torch.randn(shape, generator=g) * std
-    if bias:
-        sd[name + '.bias'] = 0.02 * torch.randn(cout, generator=g)
-
-
-def _bn(sd, g, name, c):
-    sd[name + '.weight'] = 1.0 + 0.1 * torch.randn(c, generator=g)
-    sd[name + '.bias'] = 0.05 * torch.randn(c, generator=g)
-    sd[name + '.running_mean'] = 0.05 * torch.randn(c, generator=g)
-    sd[name + '.running_var'] = 1.0 + 0.1 * torch.rand(c, generator=g)
-    sd[name + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
-
-
-def make_synthetic_checkpoint(seed=0, prepare_mode=PREPARE_MODE):
-    """Key order follows the reference module's registration order (M:384-448 then `_prepare_head` M:1338-1374)."""
-    if 'meta' not in prepare_mode or '1layer' not in prepare_mode or 'ema' not in prepare_mode:
-        raise NotImplementedError(prepare_mode)
-    g = torch.Generator().manual_seed(seed)
-    sd = OrderedDict()
-    _conv(sd, g, 'conv1_rgb.0', 48, 3, bias=True)
-    _conv(sd, g, 'conv1_dep.0', 16, 1, bias=True, gain=0.05)      # depth in metres (up to 80) -> O(1) features
-    for name, cin, cout, blocks, stride in RESNET34_LAYERS:
-        for b in range(blocks):
-            p = '%s.%d' % (name, b)
-            _conv(sd, g, p + '.conv1', cout, cin if b == 0 else cout)
-            _bn(sd, g, p + '.bn1', cout)
-            _conv(sd, g, p + '.conv2', cout, cout, gain=0.5)
-            _bn(sd, g, p + '.bn2', cout)
-            if b == 0 and stride != 1:
-                _conv(sd, g, p + '.downsample.0', cout, cin, k=1)
-                _bn(sd, g, p + '.downsample.1', cout)
-    _conv(sd, g, 'conv6.0', 512, 512)
-    _bn(sd, g, 'conv6.1', 512)
-    for name, cin, cout in (('dec5', 512, 256), ('dec4', 768, 128), ('dec3', 384, 64), ('dec2', 192, 64)):
-        _conv(sd, g, name + '.0', cout, cin, transposed=True)
-        _bn(sd, g, name + '.1', cout)
-    _conv(sd, g, 'id_dec1.0', 64, 128)
-    _bn(sd, g, 'id_dec1.1', 64)
-    _conv(sd, g, 'id_dec0.0', 1, 128, bias=True)
-    sd['id_dec0.0.bias'] += 8.0                    # initial depth of a few metres, so the propagated depth is not clamped to 0
-    _conv(sd, g, 'gd_dec1.0', 64, 128)
-    _bn(sd, g, 'gd_dec1.1', 64)
-    _conv(sd, g, 'gd_dec0.0', 8, 128, bias=True)
-    _conv(sd, g, 'cf_dec1.0', 32, 128)
-    _bn(sd, g, 'cf_dec1.1', 32)
-    _conv(sd, g, 'cf_dec0.0', 1, 96, bias=True)
-    # prop_layer (M:219-247): conv_offset_aff is zero-initialised by the reference, which makes the propagation the identity
-    # -> seeded values (offsets ~1 px, affinities small), SURVEY.md 8c
-    scale = torch.cat((torch.full((16,), 0.05), torch.full((8,), 0.004))).view(24, 1, 1, 1)
-    sd['prop_layer.aff_scale_const'] = torch.full((1,), 0.5 * 8)
-    sd['prop_layer.w'] = torch.ones((1, 1, 3, 3))
-    sd['prop_layer.b'] = torch.zeros(1)
-    sd['prop_layer.w_conf'] = torch.ones((1, 1, 1, 1))
-    sd['prop_layer.conv_offset_aff.weight'] = torch.randn((24, 8, 3, 3), generator=g) * scale
-    sd['prop_layer.conv_offset_aff.bias'] = torch.randn((24,), generator=g) * 0.05
-    # heads (M:1338-1343): proj, proj_t = deepcopy(proj), pred
-    O._mlp_entries(sd, g, 'proj', 512, 1024, 1024)
-    for k in [k for k in sd if k.startswith('proj.')]:
-        sd['proj_t.' + k[5:]] = sd[k].clone()
-    O._mlp_entries(sd, g, 'pred', 1024, 1024, 1024)
-    # meta layer (M:1370-1374): Conv2d(48,48,3,1,1)
-    _conv(sd, g, 'conv1_rgb_meta', 48, 48, bias=True, gain=0.7)
-    return sd
-
-
-def synthetic_frame(seq_seed, t, n, h, w, dataset='kitti'):
-    return O.synthetic_frame(seq_seed, t, n, h, w, dataset)
-
-
-def normalize_image(image):
-    """bash/adapt/adapt_nlspn_vkitti.sh:25-28: ImageNet statistics on the [0,1] image (T:595-604)"""
-    mean = torch.tensor(IMAGENET_MEAN, dtype=image.dtype).view(1, 3, 1, 1)
-    std = torch.tensor(IMAGENET_STD, dtype=image.dtype).view(1, 3, 1, 1)
-    return (image / 255.0 - mean) / std
+from tta_depth_completion_b200.synthetic import (make_nlspn_checkpoint as make_synthetic_checkpoint, synthetic_frame,  # noqa: E402,F401
+                                                 normalize_image_imagenet as normalize_image)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -27,6 +27,12 @@ def case_frame(case, t):
     return image, sparse, dense
 
 
+def case_checkpoint(case):
+    """the checkpoint a fixture was generated from: a fitted one (case['ckpt'] names tests/golden/ckpt_*.pt) or the seeded
+    randomly initialised stand-in"""
+    return O.get_checkpoint(case.get('ckpt', case['ckpt_seed']), case['prepare_mode'])
+
+
 def rel(a, b):
     return abs(a - b) / max(abs(b), 1e-12)
 

@@ -65,6 +65,18 @@ FWD_CASES = [
     ('t2', (64, 128), 64, 1, 24, 40),
     ('s1', (64, 0), 64, 1, 1, 130),
     ('s1', (64, 0), 64, 1, 40, 200),
+    # multi-wave launches (tiles >> 148 CTAs): the persistent `tile += gridDim.x` loops, ring slot / phase wrap, the TMEM
+    # accumulator ring and the second issuing thread -- the code paths every full-size NLSPN number comes from
+    ('s1', (64, 0), 64, 1, 352, 1216),      # resnet34.layer1: 3 344 tiles, resident weights, two issuing threads
+    ('s1', (128, 0), 128, 1, 176, 608),     # layer2: streamed weights
+    ('s1', (256, 0), 256, 1, 88, 304),      # layer3
+    ('s1', (512, 0), 512, 1, 44, 152),      # layer4
+    ('s1', (64, 64), 192, 1, 352, 1216),    # id/gd/cf_dec1 as one 128->192 conv over a concat
+    ('s2', (64, 0), 128, 1, 352, 1216),     # layer2.0 stride 2
+    ('p1s2', (64, 0), 128, 1, 352, 1216),   # layer2.0 downsample
+    ('t2', (64, 128), 64, 1, 176, 608),     # dec2: ConvTranspose 192->64 over a skip concat
+    ('t2', (128, 256), 64, 1, 88, 304),     # dec3
+    ('s1', (64, 0), 64, 2, 180, 612),       # batch 2, ragged tiles on both edges
 ]
 
 
@@ -101,6 +113,13 @@ DGRAD_CASES = [
     ('t2', 768, 128, 1, 6, 10, False),
     ('t2', 192, 64, 1, 24, 40, False),
     ('t2', 512, 256, 2, 3, 5, False),
+    # multi-wave (layer sizes of the 352x1216 step)
+    ('s1', 64, 64, 1, 352, 1216, False),
+    ('s1', 128, 128, 1, 176, 608, False),
+    ('s2', 64, 128, 1, 352, 1216, True),    # stride-2 data gradient with the folded 1x1/s2 shortcut, 4 parity classes
+    ('s2', 128, 256, 1, 176, 608, True),
+    ('t2', 192, 64, 1, 176, 608, False),
+    ('s1', 64, 64, 2, 180, 612, False),
 ]
 
 
@@ -127,6 +146,40 @@ def test_data_gradient(kind, cin, cout, n, h, w, short):
     op = ConvG(kind, DGRAD, wt, cin, cout, weight_short=ws)
     out = op(gy, gys, hw=(h, w))
     _check(out, ref, 'dgrad %s %d->%d %dx%dx%d short=%s' % (kind, cin, cout, n, h, w, short))
+
+
+def test_thin_head_conv_full_size():
+    """id_dec0 | gd_dec0 | cf_dec0 as ONE 16-output-channel conv over (F | fe1) with fp32 planar outputs and a per-channel
+    activation (nlspnmodel_adapt.py:430-448, 883-895), at 352x1216 (multi-wave) against fp32 convolutions."""
+    import ctypes
+    from tta_depth_completion_b200 import _lib
+    from tta_depth_completion_b200._lib import check, ptr, c_void_p
+    from tta_depth_completion_b200.convg import ConvG, FWD
+    torch.backends.cudnn.allow_tf32 = False
+    dev = _dev()
+    for (n, h, w) in ((1, 352, 1216), (2, 40, 72)):
+        g = torch.Generator().manual_seed(31 + h)
+        wt = torch.zeros((16, 256, 3, 3))
+        wt[:10] = torch.randn((10, 256, 3, 3), generator=g) * (2.0 / (256 * 9)) ** 0.5
+        wt = wt.to(dev)
+        bias = torch.zeros(16, device=dev)
+        bias[:10] = (torch.randn(10, generator=g) * 0.1).to(dev)
+        x0, x1 = _rand_nhwc(g, n, h, w, 192, dev), _rand_nhwc(g, n, h, w, 64, dev)
+        op = ConvG('s1', FWD, wt, (192, 64), 16, bias=bias)
+        out = torch.empty((10, n, h, w), dtype=torch.float32, device=dev)
+        planes = (ctypes.c_void_p * 10)(*[out[c].data_ptr() for c in range(10)])
+        strides = (ctypes.c_longlong * 10)(*([h * w] * 10))
+        acts_l = [1, 0, 0, 0, 0, 0, 0, 0, 0, 2]              # LeakyReLU (init depth) | identity x 8 (guidance) | sigmoid (confidence)
+        acts = (ctypes.c_int * 10)(*acts_l)
+        check(_lib.lib().ptta_convg_run_thin(ptr(x0), ptr(x1), ptr(op.packed), ptr(op.bias), planes, strides, acts, 10, n, h, w, 192, 64,
+                                             c_void_p(torch.cuda.current_stream().cuda_stream)), 'convg_run_thin')
+        ref = F.conv2d(torch.cat((_nchw(x0), _nchw(x1)), 1), wt[:10].to(torch.bfloat16).float(), bias[:10], 1, 1)
+        ref[:, 0] = F.leaky_relu(ref[:, 0], 0.2)
+        ref[:, 9] = torch.sigmoid(ref[:, 9])
+        got = out.permute(1, 0, 2, 3)
+        e = float((got - ref).norm() / ref.norm())
+        assert e < 2e-3, (n, h, w, e)
+        assert float((got - ref).abs().max()) < 2e-2 * float(ref.abs().max()), (n, h, w)
 
 
 def test_meta_conv_carries_depth_channels():

@@ -1,0 +1,128 @@
+"""Parity of the dispatch that is BENCHMARKED: the MSG-CHN TTA step at the full BASELINE.json sizes (1x352x1216 `2layers`,
+1x480x640 `1layer`), where the engine routes the 32->32 convolutions and their data gradients to the tcgen05 kernels
+(csrc/conv_tc.cuh, conv_tc_s2.cuh, conv_tc_t2.cuh), against the CPU oracle run on the same seeded inputs -- and the small
+reference fixtures run BOTH ways (every tcgen05 kernel forced on / all of them off) so that each kernel family is compared
+with outputs of the real reference.
+
+Tolerances (north star): filtered validity / filtered sparse depth bit-exact; the four per-step losses <= 1e-3 relative;
+adapted tensors after Adam: see test_msgchn_step_gpu.weight_tolerance."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import msgchn_oracle as O
+from golden_util import golden_names, load_golden, case_frame, case_checkpoint, rel, nrel, W_SD, W_SM, W_COS
+from oracle_trace import trace_step, to_nchw
+from test_msgchn_step_gpu import make_model, report, ZERO_GRAD, eng_adapt_names, weight_tolerance, TOL_LOSS, FWD_NAMES, GRAD_NAMES
+
+DEV = 'cuda'
+
+FULL = [
+    # name, checkpoint, prepare_mode, dataset, n, h, w, lr, cap
+    ('kitti_2layers_fitted', 'kitti_2layers_a', 'meta_selfsup_seq_2layers_ema', 'kitti', 1, 352, 1216, 1e-4, 80.0),
+    ('kitti_2layers_gate', 'kitti_2layers_b', 'meta_selfsup_seq_2layers_ema', 'kitti', 1, 352, 1216, 1e-4, 80.0),
+    ('kitti_2layers_random', 0, 'meta_selfsup_seq_2layers_ema', 'kitti', 1, 352, 1216, 1e-4, 80.0),
+    ('void_1layer_fitted', 'void_1layer_a', 'meta_selfsup_seq_1layer_ema', 'void', 1, 480, 640, 3e-3, 8.0),
+    ('void_1layer_random', 1, 'meta_selfsup_seq_1layer_ema', 'void', 1, 480, 640, 3e-3, 8.0),
+    ('kitti_2layers_batch2', 'kitti_2layers_a', 'meta_selfsup_seq_2layers_ema', 'kitti', 2, 176, 608, 1e-4, 80.0),
+]
+IDS = [c[0] for c in FULL]
+
+
+@pytest.mark.parametrize('case', FULL, ids=IDS)
+def test_fullsize_steps_match_oracle(case):
+    """3 continual TTA steps at the benchmarked size, native (tcgen05 dispatch) vs oracle."""
+    name, ckpt, mode, dataset, n, h, w, lr, cap = case
+    sd = O.get_checkpoint(ckpt, mode)
+    model = make_model(mode, sd, cap)
+    sd_o = {k: v.clone() for k, v in sd.items()}
+    names = O.adapt_parameter_names(sd_o)
+    state = O.AdamState(names, sd_o)
+    for t in range(3):
+        image, sparse, dense = O.synthetic_frame(11, t, n, h, w, dataset)
+        model.tta_step(image.to(DEV), sparse.to(DEV), lr, W_SD, W_SM, W_COS)
+        got = model.last_losses()
+        res = O.tta_step(sd_o, state, image, sparse, lr=lr, max_input_depth=cap)
+        eng = model._last_engine
+        assert torch.equal(eng.tensor('filtered_validity').view(n, 1, h, w).cpu(), res['validity']), t
+        assert torch.equal(eng.tensor('filtered_depth').view(n, 1, h, w).cpu(), res['sparse_depth']), t
+        for k in ('loss', 'loss_sparse_depth', 'loss_smooth', 'loss_cos'):
+            report('%s step %d %-18s native %.6f oracle %.6f rel %.2e' % (name, t, k, got[k], res[k], rel(got[k], res[k])))
+            assert rel(got[k], res[k]) < TOL_LOSS, (t, k, got[k], res[k])
+        gate = 0.0 if res['loss_cos'] < 0.3 else W_COS
+        assert got['w_cos_eff'] == pytest.approx(gate), (t, got, res['loss_cos'])
+        e_out = nrel(model.last_output().cpu(), res['output_depth'])
+        report('%s step %d output depth nrel %.3e' % (name, t, e_out))
+        assert e_out < 1e-2, (t, e_out)
+    sd_n = model.state_dict()
+    for k in names:
+        if k in ZERO_GRAD:
+            continue
+        e, upd = nrel(sd_n[k].cpu(), sd_o[k]), nrel(sd[k], sd_o[k])
+        report('%s 3 steps lr=%g %-40s weight nrel %.3e  (update/|w| %.3e, error/update %.3f)' % (name, lr, k, e, upd, e / max(upd, 1e-30)))
+        assert e < weight_tolerance(upd), (k, e, upd)
+
+
+@pytest.mark.parametrize('case', FULL[:1] + FULL[3:4], ids=IDS[:1] + IDS[3:4])
+def test_fullsize_blocks_against_oracle_trace(case):
+    """One training forward + backward at the benchmarked size, block by block: every conv_tc / conv_tc_s2 / conv_tc_t2 role
+    (forward, data gradient + mask + add, out2 / add2, stride 2 both ways) is hit inside the engine."""
+    name, ckpt, mode, dataset, n, h, w, lr, cap = case
+    sd = O.get_checkpoint(ckpt, mode)
+    model = make_model(mode, sd, cap)
+    image, sparse, _ = O.synthetic_frame(12, 0, n, h, w, dataset)
+    T, G, L, grads = trace_step({k: v.clone() for k, v in sd.items()}, image, sparse, cap, W_SD, W_SM, W_COS)
+    eng = model.model._engine_for(image.to(DEV))
+    eng.set_adam(0.0)
+    model.tta_step(image.to(DEV), sparse.to(DEV), 0.0, W_SD, W_SM, W_COS)
+    torch.cuda.synchronize()
+    rep, worst = [], 0.0
+    for nm in FWD_NAMES:
+        got, want = to_nchw(eng.tensor(nm)), T[nm]
+        e = nrel(got.reshape(want.shape), want)
+        rep.append('%-14s %.3e' % (nm, e))
+        worst = max(worst, e)
+    report('%s forward blocks, worst %.3e' % (name, worst))
+    assert worst < 2e-2, 'forward block mismatch:\n' + '\n'.join(rep)
+    got_l = model.last_losses()
+    for k in ('loss', 'loss_sparse_depth', 'loss_smooth', 'loss_cos'):
+        assert rel(got_l[k], L[k]) < TOL_LOSS, (k, got_l[k], L[k])
+    greport = []
+    for nm in GRAD_NAMES:
+        got, want = to_nchw(eng.tensor(nm)), G[nm]
+        greport.append((nm, nrel(got.reshape(want.shape), want)))
+    for k in eng_adapt_names(model):
+        if k not in ZERO_GRAD:
+            greport.append((k, nrel(model.model._grad_views[k].cpu(), grads[k])))
+    for nm, e in greport:
+        report('%s gradient %-44s nrel %.3e' % (name, nm, e))
+    worst_g = max(e for _, e in greport)
+    assert worst_g < 0.1, greport
+
+
+@pytest.mark.parametrize('force', ['tc_all', 'tc_off'])
+@pytest.mark.parametrize('name', golden_names())
+def test_fixtures_with_forced_dispatch(name, force):
+    """The reference's own fixtures with every tcgen05 conv forced on at these small sizes (tc_min_pixels = 0) and with all of
+    them off (mma.sync kernels): both dispatches must reproduce the reference."""
+    fx = load_golden(name)
+    case = fx['case']
+    sd = case_checkpoint(case)
+    opts = {'tc_min_pixels': 0, 'tc_s2_min_pixels': 0} if force == 'tc_all' else {'tc_enabled': 0}
+    model = make_model(case, sd, case['max_input_depth'], options=opts)
+    for t in range(case['steps']):
+        image, sparse, _ = case_frame(case, t)
+        model.tta_step(image.to(DEV), sparse.to(DEV), case['lr'], W_SD, W_SM, W_COS)
+        got, g = model.last_losses(), fx['steps'][t]
+        for k in ('loss', 'loss_smooth', 'loss_sparse_depth', 'loss_cos'):
+            assert rel(got[k], g[k]) < TOL_LOSS, (force, t, k, got[k], g[k])
+    out = model.last_output().cpu()
+    assert nrel(out, fx['output_depth']) < 1e-2, nrel(out, fx['output_depth'])
+    sd_after = model.state_dict()
+    for k in fx['adapt_names']:
+        if k in ZERO_GRAD:
+            continue
+        e, upd = nrel(sd_after[k].cpu(), fx['params_after'][k]), nrel(sd[k], fx['params_after'][k])
+        report('%s [%s] %-40s weight nrel %.3e (update/|w| %.3e)' % (name, force, k, e, upd))
+        assert e < weight_tolerance(upd), (force, k, e, upd)

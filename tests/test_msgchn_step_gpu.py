@@ -17,7 +17,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import msgchn_oracle as O
-from golden_util import golden_names, load_golden, case_frame, rel, nrel, W_SD, W_SM, W_COS
+from golden_util import golden_names, load_golden, case_frame, case_checkpoint, rel, nrel, W_SD, W_SM, W_COS
 from oracle_trace import trace_step, to_nchw
 
 DEV = 'cuda'
@@ -28,6 +28,19 @@ ZERO_GRAD = ('conv1_rgb_meta.conv1_meta.1.bias',)      # bias in front of a trai
 ALIGNED = [n for n in golden_names() if not n.endswith('_pad')]
 
 
+FWD_NAMES = ['depth_clamped', 'd12', 'd14', 'real.c0', 'real.c1', 'real.c2raw', 'real.c3', 'real.c4', 'real.c2',
+             'real.e1.x0', 'real.e1.x1', 'real.e1.x2', 'real.d1.x2', 'real.d1.x3', 'real.d1.x4', 'real.d1.out', 'real.p12',
+             'real.e2.x0', 'real.e2.x1', 'real.e2.x2', 'real.d2.x2', 'real.d2.x3', 'real.d2.x4', 'real.d2.out', 'real.p11',
+             'real.e3.x0', 'real.e3.x1', 'real.e3.x2', 'real.d3.x2', 'real.d3.x3', 'real.d3.x4', 'real.output',
+             'zc1', 'zc2', 'zc3', 'zc4', 'zero.c2', 'zero.d1.out', 'zero.e2.x2', 'zero.d2.out', 'zero.e3.x2', 'emb', 'ref']
+GRAD_NAMES = ('g_output', 'g_ref', 'g_p11', 'g_p12', 'g_out14', 'g_c2')
+
+
+def weight_tolerance(upd):
+    """bound on ||w - w_ref|| / ||w_ref|| for an adapted tensor whose accumulated update is `upd` = ||w_ref - w_0|| / ||w_ref||"""
+    return max(TOL_W, TOL_UPD * upd)
+
+
 def report(line):
     import os
     os.makedirs('gpurun_out', exist_ok=True)
@@ -36,10 +49,11 @@ def report(line):
     print(line)
 
 
-def make_model(case_or_mode, sd, cap):
+def make_model(case_or_mode, sd, cap, options=None):
     from tta_depth_completion_b200 import ExternalModel_Adapt
     mode = case_or_mode if isinstance(case_or_mode, str) else case_or_mode['prepare_mode']
     model = ExternalModel_Adapt('msg_chn', 0.0, 100.0, max_input_depth=cap, device=torch.device(DEV))
+    model.model.engine_options = dict(options or {})
     model._prepare_head(mode)
     model.load_state_dict(sd)
     model.set_image_normalization((1 / 255.0,) * 3, (0.0,) * 3)
@@ -52,7 +66,7 @@ def test_blocks_against_oracle_trace(name):
     """One training forward + backward, compared block by block (diagnostic granularity)."""
     fx = load_golden(name)
     case = fx['case']
-    sd = O.make_synthetic_checkpoint(case['ckpt_seed'], case['prepare_mode'])
+    sd = case_checkpoint(case)
     model = make_model(case, sd, case['max_input_depth'])
     image, sparse, _ = case_frame(case, 0)
     T, G, L, grads = trace_step({k: v.clone() for k, v in sd.items()}, image, sparse, case['max_input_depth'], W_SD, W_SM, W_COS)
@@ -61,12 +75,7 @@ def test_blocks_against_oracle_trace(name):
     model.tta_step(image.to(DEV), sparse.to(DEV), 0.0, W_SD, W_SM, W_COS)
     torch.cuda.synchronize()
     rep, worst = [], 0.0
-    fwd_names = ['depth_clamped', 'd12', 'd14', 'real.c0', 'real.c1', 'real.c2raw', 'real.c3', 'real.c4', 'real.c2',
-                 'real.e1.x0', 'real.e1.x1', 'real.e1.x2', 'real.d1.x2', 'real.d1.x3', 'real.d1.x4', 'real.d1.out', 'real.p12',
-                 'real.e2.x0', 'real.e2.x1', 'real.e2.x2', 'real.d2.x2', 'real.d2.x3', 'real.d2.x4', 'real.d2.out', 'real.p11',
-                 'real.e3.x0', 'real.e3.x1', 'real.e3.x2', 'real.d3.x2', 'real.d3.x3', 'real.d3.x4', 'real.output',
-                 'zc1', 'zc2', 'zc3', 'zc4', 'zero.c2', 'zero.d1.out', 'zero.e2.x2', 'zero.d2.out', 'zero.e3.x2', 'emb', 'ref']
-    for nm in fwd_names:
+    for nm in FWD_NAMES:
         got = to_nchw(eng.tensor(nm))
         want = T[nm]
         if want.dim() == 2:
@@ -80,7 +89,7 @@ def test_blocks_against_oracle_trace(name):
     for k in ('loss', 'loss_sparse_depth', 'loss_smooth', 'loss_cos'):
         assert rel(got_l[k], L[k]) < TOL_LOSS, (k, got_l[k], L[k])
     greport, gworst = [], 0.0
-    for nm in ('g_output', 'g_ref', 'g_p11', 'g_p12', 'g_out14', 'g_c2'):
+    for nm in GRAD_NAMES:
         got = to_nchw(eng.tensor(nm))
         want = G[nm]
         e = nrel(got.reshape(want.shape), want)
@@ -104,7 +113,7 @@ def eng_adapt_names(model):
 def test_step_matches_reference_fixture(name):
     fx = load_golden(name)
     case = fx['case']
-    sd = O.make_synthetic_checkpoint(case['ckpt_seed'], case['prepare_mode'])
+    sd = case_checkpoint(case)
     assert O.checkpoint_digest(sd) == pytest.approx(fx['digest'], rel=1e-12)
     model = make_model(case, sd, case['max_input_depth'])
     names = eng_adapt_names(model)
@@ -133,7 +142,7 @@ def test_step_matches_reference_fixture(name):
         upd = nrel(sd[k], fx['params_after'][k])             # ||w_ref - w_0|| / ||w_ref||
         report('%s steps=%d lr=%g %-40s weight nrel %.3e  (update/|w| %.3e, error/update %.3f)' % (
             name, case['steps'], case['lr'], k, e, upd, e / max(upd, 1e-30)))
-        assert e < max(TOL_W, TOL_UPD * upd), (k, e, upd)
+        assert e < weight_tolerance(upd), (k, e, upd)
     for k, v in fx['buffers_after'].items():
         if k not in sd_after:
             continue
@@ -148,6 +157,67 @@ def test_step_matches_reference_fixture(name):
     out = model.forward(image=(image / 255.0).to(DEV), sparse_depth=d_f, loss_type='adapt_meta_selfsup_seq_ema_reverse')
     assert out.shape == fx['eval_output_depth'].shape
     assert nrel(out.cpu(), fx['eval_output_depth']) < 2e-2, nrel(out.cpu(), fx['eval_output_depth'])
+
+
+@pytest.mark.parametrize('name', [n for n in ALIGNED if '_fit_' in n] + ['msgchn_2layers_kitti_1x64x128'])
+def test_native_matches_bf16_emulation(name):
+    """The one comparison that can be tight: the oracle with its bf16 emulation switched on rounds the stored activations,
+    the conv / linear weights and the gradient maps at the same points as the native path, so what is left is summation
+    order and the few places where the native path rounds once instead of twice.  Bounds: losses <= 1e-3, every
+    adapted-tensor gradient <= 1e-2 norm-wise, adapted weights after the fixture's steps <= 1e-3 norm-wise."""
+    fx = load_golden(name)
+    case = fx['case']
+    sd = case_checkpoint(case)
+    model = make_model(case, sd, case['max_input_depth'])
+    sd_e = {k: v.clone() for k, v in sd.items()}
+    names = O.adapt_parameter_names(sd_e)
+    state = O.AdamState(names, sd_e)
+    pr = O.Precision('bf16')
+    for t in range(case['steps']):
+        image, sparse, _ = case_frame(case, t)
+        model.tta_step(image.to(DEV), sparse.to(DEV), case['lr'], W_SD, W_SM, W_COS)
+        got = model.last_losses()
+        res = O.tta_step(sd_e, state, image, sparse, lr=case['lr'], max_input_depth=case['max_input_depth'], pr=pr, return_grads=True)
+        for k in ('loss', 'loss_sparse_depth', 'loss_smooth', 'loss_cos'):
+            report('%s emu step %d %-18s native %.6f emulation %.6f rel %.2e' % (name, t, k, got[k], res[k], rel(got[k], res[k])))
+            assert rel(got[k], res[k]) < TOL_LOSS, (t, k, got[k], res[k])
+        gate = res['loss_cos'] < 0.3
+        for k in names:
+            if k in ZERO_GRAD:
+                continue
+            if gate and float(res['grads'][k].norm()) == 0.0:
+                assert float(model.model._grad_views[k].norm()) == 0.0, k
+                continue
+            e = nrel(model.model._grad_views[k].cpu(), res['grads'][k])
+            report('%s emu step %d grad %-44s nrel %.3e' % (name, t, k, e))
+            assert e < 1e-2, (t, k, e)
+    sd_n = model.state_dict()
+    for k in names:
+        if k in ZERO_GRAD:
+            continue
+        e, upd = nrel(sd_n[k].cpu(), sd_e[k]), nrel(sd[k], sd_e[k])
+        report('%s emu %-44s weight nrel %.3e (update/|w| %.3e, error/update %.3f)' % (name, k, e, upd, e / max(upd, 1e-30)))
+        assert e < TOL_W, (k, e, upd)
+
+
+def test_second_shape_continues_adam_bias_correction():
+    """One wrapper, two input shapes (e.g. the smaller last batch of a sequence): the engines share the Adam moments, so they must
+    share the step counter as well -- the third step, taken on a new shape, uses bias correction t = 3, as torch.optim.Adam does."""
+    mode, cap, lr = 'meta_selfsup_seq_2layers_ema', 80.0, 1e-4
+    sd = O.make_synthetic_checkpoint(0, mode)
+    model = make_model(mode, sd, cap)
+    sd_o = {k: v.clone() for k, v in sd.items()}
+    names = O.adapt_parameter_names(sd_o)
+    state = O.AdamState(names, sd_o)
+    for t, (h, w) in enumerate([(64, 128), (64, 128), (48, 80), (64, 128)]):
+        image, sparse, _ = O.synthetic_frame(13, t, 1, h, w, 'kitti')
+        k = names[0]
+        before_o, before_n = sd_o[k].clone(), model.state_dict()[k].cpu().clone()
+        model.tta_step(image.to(DEV), sparse.to(DEV), lr, W_SD, W_SM, W_COS)
+        O.tta_step(sd_o, state, image, sparse, lr=lr, max_input_depth=cap)
+        step_n = float((model.state_dict()[k].cpu() - before_n).norm())        # size of this step's update
+        step_o = float((sd_o[k] - before_o).norm())
+        assert abs(step_n / step_o - 1.0) < 0.1, (t, step_n, step_o)     # a restarted counter (t = 1) would give 2.7x at t = 3
 
 
 def test_dropin_api_equals_fused_step():

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import msgchn_oracle as O
-from golden_util import golden_names, load_golden, case_frame, rel, nrel, W_SD, W_SM, W_COS
+from golden_util import golden_names, load_golden, case_frame, case_checkpoint, rel, nrel, W_SD, W_SM, W_COS
 
 # fp32 CPU vs fp32 CPU of the same torch build: only summation-order noise is expected
 TOL_LOSS = 2e-5
@@ -19,8 +19,8 @@ def test_oracle_matches_reference_fixture(name):
     fx = load_golden(name)
     case = fx['case']
     torch.manual_seed(0)
-    sd = O.make_synthetic_checkpoint(case['ckpt_seed'], case['prepare_mode'])
-    assert O.checkpoint_digest(sd) == pytest.approx(fx['digest'], rel=1e-12), 'seeded checkpoint differs'
+    sd = case_checkpoint(case)
+    assert O.checkpoint_digest(sd) == pytest.approx(fx['digest'], rel=1e-12), 'checkpoint differs from the one the fixture was made with'
     names = O.adapt_parameter_names(sd, 'meta')
     assert names == fx['adapt_names']
     state = O.AdamState(names, sd)
@@ -32,6 +32,8 @@ def test_oracle_matches_reference_fixture(name):
         for k in ('loss', 'loss_smooth', 'loss_sparse_depth', 'loss_cos'):
             assert rel(res[k], g[k]) < TOL_LOSS, (t, k, res[k], g[k])
         assert int(res['validity'].sum()) == g['n_valid']
+        if 'w_cos_eff' in g:       # the `loss_cos < 0.3` gate of src/external_model_adapt.py:424
+            assert (res['loss_cos'] < 0.3) == (g['w_cos_eff'] == 0.0), (t, res['loss_cos'], g['w_cos_eff'])
         for k in names:
             if k in ZERO_GRAD:
                 # analytically zero gradient: what the reference holds is fp32 rounding noise

@@ -166,6 +166,7 @@ struct ptta_msgchn {
     Map32 zc[5];                     // cached rgb_encoder(0) features
     Map32 zcr[4];                    // scratch ReLU copies while rgb_encoder(0) is (re)computed
     Map1 fd, fv, dcl, d12, d14;      // filtered depth / validity, clamped depth, pyramid
+    float *stage_img = nullptr, *stage_sp = nullptr;   // engine-owned copies of the caller's frame: what a captured step reads
     // heads
     long long R = 0;
     bf16 *h_an2 = nullptr; double* partial2 = nullptr;
@@ -189,7 +190,7 @@ struct ptta_msgchn {
     const float *l_img = nullptr, *l_d = nullptr, *l_v = nullptr; float l_cap = 0, l_wsd = 0, l_wsm = 0;
     // graph
     cudaGraphExec_t graph_exec = nullptr;
-    struct GraphKey { const void* image; const void* sparse; float isc[3], ish[3], cap, w_sd, w_sm, w_cos; } graph_key;   // everything a capture bakes in
+    struct GraphKey { float isc[3], ish[3], cap, w_sd, w_sm, w_cos; } graph_key;   // everything a capture bakes in (inputs are staged)
 
     // ---------------------------------------------------------------------------------------------
     Map32 alloc32(const char* name, int h, int w, int c = 32) {
@@ -354,6 +355,8 @@ struct ptta_msgchn {
             return m;
         };
         fd = alloc_user("filtered_depth"); fv = alloc_user("filtered_validity");
+        stage_img = allocv<float>((size_t)Nu * 3 * Hu * Wu); reg("stage_image", stage_img, 0, Nu, 3, Hu, Wu);
+        stage_sp = allocv<float>((size_t)Nu * Hu * Wu); reg("stage_sparse", stage_sp, 0, Nu, 1, Hu, Wu);
         if (padded) {
             pimg = allocv<float>((size_t)N * 3 * H * W);
             psp = allocv<float>((size_t)N * H * W);
@@ -554,6 +557,12 @@ struct ptta_msgchn {
                 AdamChunk c; c.p = p + o; c.g = g + o; c.m = m + o; c.v = v + o; c.n = (int)std::min<long long>(ADAM_CHUNK, n - o);
                 chunks.push_back(c);
             }
+        }
+        if (ext.count("adam/hyper")) {
+            // one step counter / hyper-parameter block per WRAPPER, shared by its engines of all shapes (a second shape must not
+            // restart the bias correction at step 0 on warm moments)
+            PTTA_CHECK(ext["adam/hyper"].second >= (long long)sizeof(AdamHyper), "'adam/hyper' needs %zu bytes", sizeof(AdamHyper));
+            adam_hyper = (AdamHyper*)ext["adam/hyper"].first;
         }
         PTTA_CHECK(chunks.size() <= 256, "too many Adam chunks (%zu)", chunks.size());
         n_adam_chunks = (int)chunks.size();
@@ -1415,9 +1424,22 @@ int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepa
     if (getenv("PTTA_NO_TC")) e->tc_enabled = false;
     if (getenv("PTTA_NO_FUSE_DEC_SUMS")) e->fuse_dec_sums = false;
     if (getenv("PTTA_ONE_STREAM")) e->two_streams = false;
+    if (const char* v = getenv("PTTA_TC_MIN_PIXELS")) e->tc_min_pixels = e->tc_s2_min_pixels = atoll(v);
     e->define_model();
     e->plan();
     *out = e;
+    return 0;
+}
+int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value) {
+    PTTA_CHECK(e && name, "set_option: null argument");
+    const std::string k = name;
+    if (k == "tc_min_pixels") e->tc_min_pixels = value;                 // smallest map (pixels) the stride-1 tcgen05 conv takes
+    else if (k == "tc_s2_min_pixels") e->tc_s2_min_pixels = value;      // same for the stride-2 tcgen05 conv
+    else if (k == "tc_enabled") e->tc_enabled = value != 0;
+    else if (k == "two_streams") e->two_streams = value != 0;
+    else if (k == "fuse_dec_sums") e->fuse_dec_sums = value != 0;
+    else PTTA_CHECK(false, "set_option: unknown option '%s'", name);
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }   // a captured step bakes the dispatch in
     return 0;
 }
 void ptta_msgchn_destroy(ptta_msgchn* e) {
@@ -1548,8 +1570,15 @@ int ptta_msgchn_tta_step_graph(ptta_msgchn* e, const float* image_raw, const flo
     PTTA_CHECK(st != nullptr, "tta_step_graph: needs a non-default stream (legacy stream 0 cannot be captured)");
     ptta_msgchn::GraphKey key;
     memset(&key, 0, sizeof(key));
-    key.image = image_raw; key.sparse = sparse; key.cap = cap; key.w_sd = w_sd; key.w_sm = w_sm; key.w_cos = w_cos;
+    key.cap = cap; key.w_sd = w_sd; key.w_sm = w_sm; key.w_cos = w_cos;
     for (int c = 0; c < 3; ++c) { key.isc[c] = isc[c]; key.ish[c] = ish[c]; }
+    // The captured step reads engine-owned staging buffers, so a caller may pass a fresh tensor every frame (the usual
+    // `.to(device)` of a data loader) without re-capturing; a caller that writes its frames straight into "stage_image" /
+    // "stage_sparse" (ptta_msgchn_get_tensor) and passes those pointers skips the copies.
+    const size_t px = (size_t)e->Nu * e->Hu * e->Wu;
+    if (image_raw != e->stage_img) PTTA_CUDA(cudaMemcpyAsync(e->stage_img, image_raw, 3 * px * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (sparse != e->stage_sp) PTTA_CUDA(cudaMemcpyAsync(e->stage_sp, sparse, px * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    image_raw = e->stage_img; sparse = e->stage_sp;
     if (e->graph_exec && memcmp(&key, &e->graph_key, sizeof(key)) != 0) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     if (!e->graph_exec) {
         // one eager step first: sets every cudaFuncAttribute (not capturable) and validates the arguments

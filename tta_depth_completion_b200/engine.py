@@ -24,12 +24,14 @@ class MsgChnEngine:
     engine reads them in place and updates the BatchNorm buffers in place.  The adapted tensors
     (`adapt_names`) get gradient / Adam-moment buffers that the engine writes."""
 
-    def __init__(self, n, h, w, prepare_mode, state, grads=None, adam_m=None, adam_v=None):
+    def __init__(self, n, h, w, prepare_mode, state, grads=None, adam_m=None, adam_v=None, options=None, adam_hyper=None):
         self.L = _lib.lib()
         self.n, self.h, self.w, self.prepare_mode = n, h, w, prepare_mode
         handle = c_void_p()
         check(self.L.ptta_msgchn_create(ctypes.byref(handle), n, h, w, prepare_mode.encode()), 'msgchn_create')
         self.handle = handle
+        for k, v in (options or {}).items():
+            self.set_option(k, v)
         self.device = next(iter(state.values())).device
         nbytes = self.L.ptta_msgchn_workspace_bytes(self.handle)
         self.workspace = torch.empty(nbytes + 512, dtype=torch.uint8, device=self.device)
@@ -39,6 +41,7 @@ class MsgChnEngine:
               'bind_workspace')
         self.state = state
         self.grads, self.adam_m, self.adam_v = grads, adam_m, adam_v
+        self.adam_hyper = adam_hyper
         self.required_keys = [self.L.ptta_msgchn_key(self.handle, i).decode()
                               for i in range(self.L.ptta_msgchn_num_keys(self.handle))]
         missing = [k for k in self.required_keys if k not in state]
@@ -59,7 +62,13 @@ class MsgChnEngine:
             if d:
                 for k, t in d.items():
                     check(self.L.ptta_msgchn_set_tensor(self.handle, (prefix + k).encode(), ptr(t), t.numel()), 'set_tensor')
+        if self.adam_hyper is not None:
+            check(self.L.ptta_msgchn_set_tensor(self.handle, b'adam/hyper', ptr(self.adam_hyper), self.adam_hyper.numel()), 'set_tensor')
         check(self.L.ptta_msgchn_pack_weights(self.handle, _stream()), 'pack_weights')
+
+    def set_option(self, name, value):
+        """Kernel-dispatch options of include/ptta_b200.h (`ptta_msgchn_set_option`)."""
+        check(self.L.ptta_msgchn_set_option(self.handle, name.encode(), int(value)), 'set_option')
 
     def close(self):
         if getattr(self, 'handle', None):

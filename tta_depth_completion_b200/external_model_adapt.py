@@ -196,6 +196,7 @@ class MsgChnModel_Adapt(object):
         self.img_scale = (1.0, 1.0, 1.0)
         self.img_shift = (0.0, 0.0, 0.0)
         self._adam_step = 0
+        self.engine_options = {}       # ptta_msgchn_set_option(name, value) applied to every engine this wrapper creates
 
     # -- construction ---------------------------------------------------------------------------------
     def _prepare_head(self, mode=''):
@@ -214,6 +215,9 @@ class MsgChnModel_Adapt(object):
         self._adapt_names = [k for k in self._sd if 'meta' in k and k.endswith(_PARAM_SUFFIX)]   # msg_chn_model_adapt.py:392-396
         total = sum(self._sd[k].numel() for k in self._adapt_names)
         self._flat = {name: torch.zeros(total, dtype=torch.float32, device=self.device) for name in ('param', 'grad', 'm', 'v')}
+        # Adam step counter + hyper-parameters: ONE device block per wrapper, bound into every engine (all shapes share the
+        # moments, so they must share the bias-correction step as well)
+        self._adam_hyper = torch.zeros(64, dtype=torch.uint8, device=self.device)
         self._grad_views, self._m_views, self._v_views = {}, {}, {}
         self._param_objs = OrderedDict()
         off = 0
@@ -241,7 +245,8 @@ class MsgChnModel_Adapt(object):
         if eng is None:
             n, h, w = key          # H, W need not be multiples of 16: the engine pads and flip-ensembles (src/msg_chn_model_adapt.py:58-125)
             state = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in self._sd.items()}
-            eng = MsgChnEngine(n, h, w, self.prepare_mode, state, self._grad_views, self._m_views, self._v_views)
+            eng = MsgChnEngine(n, h, w, self.prepare_mode, state, self._grad_views, self._m_views, self._v_views,
+                               options=self.engine_options, adam_hyper=self._adam_hyper)
             self._engines[key] = eng
         return eng
 
