@@ -49,6 +49,12 @@ CASES = [
          n=2, h=48, w=80, steps=3, lr=1e-4, max_input_depth=80.0, ckpt_seed=None, seq_seed=22, density=None),
     dict(name='msgchn_fit_void_1x48x64', prepare_mode='meta_selfsup_seq_1layer_ema', dataset='void', ckpt='void_1layer_a',
          n=1, h=48, w=64, steps=3, lr=3e-3, max_input_depth=8.0, ckpt_seed=None, seq_seed=23, density=0.03),
+    # test-domain shift (what TTA is for): the sensor reads 3 % deeper than the surface the network was fitted on, so the L1 residual
+    # (0.15 ... 2.3 m) is far above the bf16 noise of the prediction and sign(pred - d) is stable between implementations
+    dict(name='msgchn_fit_kitti_shift_1x64x128', prepare_mode='meta_selfsup_seq_2layers_ema', dataset='kitti', ckpt='kitti_2layers_a',
+         n=1, h=64, w=128, steps=3, lr=1e-4, max_input_depth=80.0, ckpt_seed=None, seq_seed=25, density=None, depth_scale=1.03),
+    dict(name='msgchn_fit_void_shift_1x48x64', prepare_mode='meta_selfsup_seq_1layer_ema', dataset='void', ckpt='void_1layer_a',
+         n=1, h=48, w=64, steps=3, lr=3e-3, max_input_depth=8.0, ckpt_seed=None, seq_seed=26, density=0.03, depth_scale=1.05),
     dict(name='msgchn_fit_kitti_1x40x72_pad', prepare_mode='meta_selfsup_seq_2layers_ema', dataset='kitti', ckpt='kitti_2layers_a',
          n=1, h=40, w=72, steps=2, lr=1e-4, max_input_depth=80.0, ckpt_seed=None, seq_seed=24, density=None),
 ]
@@ -56,7 +62,8 @@ W_SD, W_SM, W_COS = 1.0, 1.0, 0.1
 
 
 def case_frame(case, t):
-    image, sparse, dense = O.synthetic_frame(case['seq_seed'], t, case['n'], case['h'], case['w'], case['dataset'])
+    image, sparse, dense = O.synthetic_frame(case['seq_seed'], t, case['n'], case['h'], case['w'], case['dataset'],
+                                             depth_scale=case.get('depth_scale', 1.0))
     if case.get('density'):
         # tiny frames at 0.5 % density would have ~15 points; re-sample denser for the small fixtures
         g = torch.Generator().manual_seed(77 + t)

@@ -34,20 +34,23 @@ import torch.nn.functional as F
 # precision emulation hook (used only for tolerance studies: rounds a tensor to bf16 and back)
 # ----------------------------------------------------------------------------------------------
 class Precision:
-    """`act(x)` is applied to every 32/128-channel activation and head matrix, `wgt(w)` to every
-    conv / linear weight.  Identity in the fp32 oracle."""
+    """`act(x)` is applied to every 32/128-channel activation and head matrix, `wgt(w)` to every conv / linear weight that the
+    native path feeds to the tensor cores (the {1,2,3}->32 stems and the 32->1 prediction convs run in fp32 there, from the
+    fp32 weights).  Identity in the fp32 oracle.  Because the rounding is applied with `.to(dtype)`, autograd rounds the gradient
+    arriving at each of these tensors as well -- the stored gradient maps of the native backward."""
 
     def __init__(self, emulate=None):
         self.emulate = emulate
+        self.dtype = {'bf16': torch.bfloat16, 'fp16': torch.float16}.get(emulate)
 
     def act(self, x):
-        if self.emulate == 'bf16':
-            return x.to(torch.bfloat16).to(torch.float32)
+        if self.dtype is not None:
+            return x.to(self.dtype).to(torch.float32)
         return x
 
     def wgt(self, w):
-        if self.emulate == 'bf16':
-            return w.to(torch.bfloat16).to(torch.float32)
+        if self.dtype is not None and not (w.dim() == 4 and min(w.shape[0], w.shape[1]) < 32):
+            return w.to(self.dtype).to(torch.float32)
         return w
 
 

@@ -40,7 +40,8 @@ BN_EPS = 1e-5
 
 
 class Precision(O.Precision):
-    pass
+    def wgt(self, w):          # every NLSPN conv / linear weight is a bf16 tensor-core operand on the native path
+        return w.to(self.dtype).to(torch.float32) if self.dtype is not None else w
 
 
 FP32 = O.FP32

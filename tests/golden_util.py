@@ -19,7 +19,8 @@ def load_golden(name):
 
 
 def case_frame(case, t):
-    image, sparse, dense = O.synthetic_frame(case['seq_seed'], t, case['n'], case['h'], case['w'], case['dataset'])
+    image, sparse, dense = O.synthetic_frame(case['seq_seed'], t, case['n'], case['h'], case['w'], case['dataset'],
+                                             depth_scale=case.get('depth_scale', 1.0))
     if case.get('density'):
         g = torch.Generator().manual_seed(77 + t)
         mask = (torch.rand(dense.shape, generator=g) < case['density']).float()

@@ -118,9 +118,11 @@ DATASETS = {
 }
 
 
-def synthetic_frame(seq_seed, t, n, h, w, dataset='kitti', outlier_fraction=0.01):
+def synthetic_frame(seq_seed, t, n, h, w, dataset='kitti', outlier_fraction=0.01, depth_scale=1.0):
     """Frame t of synthetic sequence `seq_seed`: image in [0,255]; sparse depth = smooth
-    surface x Bernoulli(p), with ~1 % of the samples pushed +5 m so the outlier filter has work."""
+    surface x Bernoulli(p), with ~1 % of the samples pushed +5 m so the outlier filter has work.
+    depth_scale != 1 models a test-domain shift (the sensor reads depth_scale x the surface the source-domain network was
+    fitted on): the sparse samples are scaled, the returned dense ground truth is scaled with them."""
     p, cap = DATASETS[dataset]
     g = torch.Generator().manual_seed(1000 * seq_seed + t)
     yy = torch.arange(h, dtype=torch.float32).view(1, 1, h, 1)
@@ -135,7 +137,7 @@ def synthetic_frame(seq_seed, t, n, h, w, dataset='kitti', outlier_fraction=0.01
         dense = 5.0 + 70.0 * (1.0 - yy / h) + 2.0 * torch.sin((xx + 3.0 * t) / 97.0)
     else:
         dense = 0.5 + 4.0 * (yy / h) + 0.3 * torch.sin((xx + 3.0 * t) / 53.0)
-    dense = dense.expand(n, 1, h, w).contiguous()
+    dense = (dense * depth_scale if depth_scale != 1.0 else dense).expand(n, 1, h, w).contiguous()
     mask = (torch.rand((n, 1, h, w), generator=g) < p).float()
     out = (torch.rand((n, 1, h, w), generator=g) < outlier_fraction).float()
     sparse = (dense + 5.0 * out * (cap / 80.0)) * mask
