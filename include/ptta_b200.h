@@ -52,6 +52,10 @@ int ptta_conv3x3(const void* in_bf16, void* out_bf16, const void* wpack_bf16, co
 int ptta_pack_conv_weight_tc(const void* wpack_bf16, void* wimage_bf16, ptta_stream_t stream);
 int ptta_conv3x3_tc(const void* in_bf16, void* out_bf16, const void* wimage_bf16, const float* bias, int n, int h, int w,
                     int relu_in, int relu_out, const void* mask_bf16, const void* add_bf16, ptta_stream_t stream);
+/* same with the two fused extras the engine uses: out2 (optional) = ReLU(bf16(out) [+ add2]) -- the ReLU'd copy a following tensor-core
+ * conv reads, or the decoder sum s = ReLU(conv + skip) (network_exp_msg_chn_adapt.py:301-309).  add and add2 are mutually exclusive. */
+int ptta_conv3x3_tc_ex(const void* in_bf16, void* out_bf16, void* out2_bf16, const void* wimage_bf16, const float* bias, int n, int h, int w,
+                       int relu_out, const void* mask_bf16, const void* add_bf16, const void* add2_bf16, ptta_stream_t stream);
 /* the 32->32 STRIDE-2 case (mode 1 of ptta_conv3x3: Conv2d(s2) forward, ConvTranspose2d(s2) data gradient) on tcgen05.
  * h, w = input size (even); out is [n, h/2, w/2, 32]; out_relu (optional) additionally receives ReLU(out). */
 int ptta_pack_conv_weight_tc_s2(const void* wpack_bf16, void* wimage_bf16, ptta_stream_t stream);
@@ -60,10 +64,6 @@ int ptta_conv3x3_tc_s2(const void* in_bf16, void* out_bf16, void* out_relu_bf16,
 /* timing experiments only: one eager step with a CUDA event after every kernel launch; prints the per-stream timeline */
 int ptta_msgchn_trace_step(ptta_msgchn* engine, const float* image_raw, const float* img_scale3, const float* img_shift3,
                            const float* sparse_depth, float max_input_depth, float w_sd, float w_sm, float w_cos, ptta_stream_t stream);
-/* timing experiments only: bit mask of pipeline stages the tcgen05 conv skips (results are then wrong) */
-int ptta_debug_set(int mask);
-/* timing experiments only: per-row clock64() stamps of CTA 0 recorded by the tcgen05 conv when mask bit 64 is set */
-int ptta_debug_read_ts(long long* out_host, int n);
 /* weight gradient of a 3x3 stride-1 conv (autograd of the meta layer, network_exp_msg_chn_adapt.py:28-36) */
 size_t ptta_conv3x3_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout);
 int ptta_conv3x3_wgrad(const void* in_bf16, const void* gout_bf16, float* dw, void* workspace,

@@ -281,6 +281,19 @@ def test_conv_tcgen05_matches_mma(ops, n, h, w):
     _lib.check(_lib.lib().ptta_conv3x3_tc(_lib.ptr(x), _lib.ptr(acc), _lib.ptr(wi), None, n, h, w, 0, 0, _lib.ptr(m), _lib.ptr(acc),
                                           torch.cuda.current_stream().cuda_stream), 'conv3x3_tc in place')
     assert torch.equal(acc, want), 'conv_tc in-place accumulate'
+    # second output: ReLU copy, and the decoder sum ReLU(bf16(out) + skip)
+    base = ops.conv3x3_tc(torch.relu(x), wp, bias)
+    o, o2 = ops.conv3x3_tc_ex(torch.relu(x), wp, bias)
+    assert torch.equal(o, base) and torch.equal(o2, torch.relu(base)), 'conv_tc out2 = ReLU(out)'
+    o, o2 = ops.conv3x3_tc_ex(torch.relu(x), wp, bias, add2=a)
+    assert torch.equal(o, base) and torch.equal(o2, torch.relu((base.float() + a.float()).to(torch.bfloat16))), 'conv_tc out2 = ReLU(out + add2)'
+    # independent of the mma.sync kernel: fp32 convolution of the same bf16 operands (fp32 accumulation of 288 products; the only
+    # differences are summation order and the final rounding to bf16)
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(torch.relu(x).float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias, 1, 1).permute(0, 2, 3, 1)
+    err = (base.float() - ref).abs()
+    assert int((err > ref.abs() * 2.0 ** -8 + 2e-3 * float(ref.pow(2).mean().sqrt())).sum()) == 0, 'conv_tc vs fp32 conv'
     with pytest.raises(RuntimeError):
         ops.conv3x3_tc(x, wp, bias, relu_in=True)      # not supported: must fail loudly
     with pytest.raises(RuntimeError):
@@ -304,6 +317,11 @@ def test_conv_tcgen05_stride2_matches_mma(ops, n, h, w):
     assert torch.equal(ops.conv3x3_tc_s2(torch.relu(x), wp, bias, relu_out=True), torch.relu(want))
     want = ops.conv3x3(x, wp, None, ops.MODE_S2, ops.PRO_NONE, mask=m, mask_mode=ops.MASK_RELU, add=a)
     assert torch.equal(ops.conv3x3_tc_s2(x, wp, None, mask=m, add=a), want), 'conv_tc_s2 mask+add'
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(torch.relu(x).float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias, 2, 1).permute(0, 2, 3, 1)
+    err = (got.float() - ref).abs()
+    assert int((err > ref.abs() * 2.0 ** -8 + 2e-3 * float(ref.pow(2).mean().sqrt())).sum()) == 0, 'conv_tc_s2 vs fp32 conv'
     with pytest.raises(RuntimeError):
         ops.conv3x3_tc_s2(x[:, :h - 1].contiguous(), wp, bias)       # odd height: must fail loudly
 

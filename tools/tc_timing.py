@@ -42,11 +42,9 @@ for shape in [(1, 352, 1216), (4, 352, 1216), (1, 176, 608), (1, 88, 304)]:
     xs = [torch.randn((n, h, w, 32), device=dev).to(torch.bfloat16) for _ in range(cnt)]
     mk = torch.randn((n, h, w, 32), device=dev).to(torch.bfloat16)
     res = []
-    for dbg in (0, 1, 2, 4, 1 | 2 | 4):
-        _lib.lib().ptta_debug_set(dbg)
-        res.append('dbg%d %.1f' % (dbg, timeit(lambda x: ops.conv3x3_tc(x, wp, bias, wimage=wi), xs)))
-    _lib.lib().ptta_debug_set(0)
-    res.append('eager %.1f' % timeit(lambda x: ops.conv3x3_tc(x, wp, bias, wimage=wi), xs, graph=False))
+    res.append('tc %.1f' % timeit(lambda x: ops.conv3x3_tc(x, wp, bias, wimage=wi), xs))
+    res.append('warm %.1f' % timeit(lambda x: ops.conv3x3_tc(x, wp, bias, wimage=wi), xs[:1]))
+    res.append('out2+add2 %.1f' % timeit(lambda x: ops.conv3x3_tc_ex(x, wp, bias, add2=mk, wimage=wi), xs))
     res.append('mask %.1f' % timeit(lambda x: ops.conv3x3_tc(x, wp, bias, mask=mk, wimage=wi), xs))
     res.append('mask+add %.1f' % timeit(lambda x: ops.conv3x3_tc(x, wp, bias, mask=mk, add=mk, wimage=wi), xs))
     res.append('mma %.1f' % timeit(lambda x: ops.conv3x3(x, wp, bias, ops.MODE_S1, ops.PRO_RELU), xs))

@@ -69,5 +69,20 @@ def build_library(force=False, verbose=False):
     return LIB_PATH
 
 
+def build_stamps_library(verbose=False):
+    """Profiling build (-DPTTA_STAMPS): every kernel records its in-situ start time (tools/graph_stamps.py).  Not the product."""
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    out = os.path.join(LIB_DIR, 'libptta_b200_stamps.so')
+    cmd = [nvcc] + NVCC_FLAGS + ['-DPTTA_STAMPS', '-shared', '-o', out] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == '__main__':
-    print(build_library(force=True, verbose=True))
+    import sys
+    if 'stamps' in sys.argv:
+        print(build_stamps_library(verbose=True))
+    else:
+        print(build_library(force=True, verbose=True))

@@ -41,7 +41,48 @@ int check_launch(const char* what);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- launches: programmatic dependent launch (PDL) ------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute and starts with PDL_SYNC():
+// `griddepcontrol.wait` (all prerequisite grids complete, their memory visible) followed by `griddepcontrol.launch_dependents`
+// (the NEXT kernel of the stream may be scheduled now: its blocks become resident as SM resources free up, run their
+// set-up -- barrier init, TMEM allocation, descriptor prefetch -- and park in their own wait).  In a captured step this turns the
+// kernel -> kernel edges into programmatic edges: launch latency and block scheduling of kernel k+1 overlap the tail of kernel
+// k instead of following it.  The trigger comes AFTER the wait, so at most one successor is ever resident ahead of time and a
+// kernel that reads data produced two launches back is still ordered behind it.  PTTA_PDL=0 in the environment disables it.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface in check_launch()
+}
+
 // ---- device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifdef PTTA_STAMPS
+// profiling build only (lib/libptta_b200_stamps.so, tools/graph_stamps.py): block 0 of every kernel records %globaltimer right
+// after its dependency wait, so a REPLAYED graph yields the in-situ start time of each kernel (start-to-start = duration + gap)
+__device__ unsigned long long g_stamps[8192];
+__device__ unsigned int g_stamp_count;
+__device__ __forceinline__ void pdl_stamp() {
+    if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x | threadIdx.y | threadIdx.z) == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned int i = atomicAdd(&g_stamp_count, 1u);
+        if (i < 8192u) g_stamps[i] = t;
+    }
+}
+#define PDL_SYNC() do { ::ptta::pdl_wait(); ::ptta::pdl_trigger(); ::ptta::pdl_stamp(); } while (0)
+#else
+#define PDL_SYNC() do { ::ptta::pdl_wait(); ::ptta::pdl_trigger(); } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }

@@ -182,6 +182,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     if (p.mcast) tc::cluster_sync();        // the peer's barriers are initialised before anything is multicast to them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    PDL_SYNC();      // the set-up above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel; nothing before this line touches global data
     if (tid == 0) CONVG_TS(63, 1);                   // set-up done (barriers, TMEM allocation)
     const uint32_t crank = p.mcast ? tc::cluster_ctarank() : 0u;
     // multicast mode: tile indices run to an even count; a ghost tile (image index == N) loads zeros and stores nothing (TMA clips)
@@ -431,6 +432,7 @@ struct ConvGPackParams {
 };
 
 __global__ void __launch_bounds__(256) pack_convg_kernel(const __grid_constant__ ConvGPackParams p, bf16* __restrict__ out) {
+    PDL_SYNC();
     // grid (chunk, 16-row group): the adapted meta conv is re-packed after every Adam step, so this sits on the step's critical path
     const int wk = blockIdx.x;
     const ConvGPackEntry e = p.e[wk];
@@ -689,7 +691,7 @@ inline int launch_convg_pack(const ConvGPlan& pl, int kind, int role, const floa
     pp.sn[1] = 1; pp.sk[1] = cin_w; pp.n_real[1] = cin_w; pp.k_real[1] = cout_w;
     pp.n_pad = pl.n_out;
     pp.ident_from = ident_from;
-    pack_convg_kernel<<<dim3(pl.n_items, cdiv(pl.n_out, 16)), 256, 0, st>>>(pp, packed);
+    launch_k(pack_convg_kernel, dim3(pl.n_items, cdiv(pl.n_out, 16)), 256, 0, st, pp, packed);
     return check_launch("pack_convg");
 }
 
@@ -729,7 +731,7 @@ inline int launch_convg(const ConvGPlan& pl, const bf16* x0, const bf16* x1, con
         PTTA_CUDA(cudaLaunchKernelEx(&cfg, convg_kernel, ta0, ta1, tb, to, pr));
         return check_launch("convg(mc)");
     }
-    convg_kernel<<<grid, C::THREADS, C::SMEM, st>>>(ta0, ta1, tb, to, pr);
+    launch_k(convg_kernel, grid, C::THREADS, C::SMEM, st, ta0, ta1, tb, to, pr);
     return check_launch("convg");
 }
 

@@ -65,6 +65,7 @@ struct ConvSmem {
 
 template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(256) conv3x3_mma_kernel(const ConvParams p) {
+    PDL_SYNC();
     typedef ConvTile<MODE> T;
     typedef ConvSmem<CIN, COUT, MODE> S;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -290,7 +291,7 @@ int launch_conv3x3_t(ConvParams p, cudaStream_t st) {
         p.tiles_y = cdiv(p.Hout, T::TH);
     }
     dim3 grid(p.tiles_x * p.tiles_y, p.N);
-    conv3x3_mma_kernel<CIN, COUT, MODE><<<grid, 256, S::TOTAL, st>>>(p);
+    launch_k(conv3x3_mma_kernel<CIN, COUT, MODE>, grid, 256, S::TOTAL, st, p);
     return check_launch("conv3x3_mma");
 }
 
@@ -336,6 +337,7 @@ struct WgradSmem {
 
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const WgradParams p) {
+    PDL_SYNC();
     typedef WgradSmem<CIN, COUT> S;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_halo = smem;
@@ -456,6 +458,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const WgradParams p)
 // dW[co][ci][ky][kx] (PyTorch Conv2d layout) = sum over partial blocks.  Block = 32 outputs x 8 slices of the partial
 // list; slices are combined through shared memory in a fixed order (deterministic, coalesced 128 B reads).
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nblocks, int cout, int cin) {
+    PDL_SYNC();
     __shared__ float sh[8][32];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int total = 9 * cout * cin;
@@ -485,10 +488,10 @@ int launch_wgrad_t(WgradParams p, float* dw, cudaStream_t st) {
     p.tiles_x = cdiv(p.W, 16);
     p.tiles_y = cdiv(p.H, 16);
     dim3 grid(p.tiles_x * p.tiles_y, p.N);
-    conv3x3_wgrad_kernel<CIN, COUT><<<grid, 256, S::TOTAL, st>>>(p);
+    launch_k(conv3x3_wgrad_kernel<CIN, COUT>, grid, 256, S::TOTAL, st, p);
     PTTA_TRY(check_launch("conv3x3_wgrad"));
     int total = 9 * COUT * CIN;
-    wgrad_reduce_kernel<<<cdiv(total, 32), 256, 0, st>>>(p.partial, dw, p.tiles_x * p.tiles_y * p.N, COUT, CIN);
+    launch_k(wgrad_reduce_kernel, cdiv(total, 32), 256, 0, st, p.partial, dw, p.tiles_x * p.tiles_y * p.N, COUT, CIN);
     return check_launch("wgrad_reduce");
 }
 

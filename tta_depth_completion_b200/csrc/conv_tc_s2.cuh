@@ -32,6 +32,7 @@ struct ConvTcS2Cfg {
 // [tap][cout][cin] bf16 -> shared-memory weight image of the stride-2 kernel: row = kx*96 + blk*32 + cout with
 // blk 0 = ky 2, blk 1 = ky 0 (the pair an odd input row feeds), blk 2 = ky 1; 64 B rows, SWIZZLE_64B chunk order
 __global__ void pack_conv_weight_tc_s2_kernel(const bf16* __restrict__ pack, bf16* __restrict__ image) {
+    PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 9 * 32 * 4) return;
     const int row = i >> 2, c = i & 3;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(ConvTcS2Cfg::THREADS, 1) conv3x3_tc_s2_kernel(
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    PDL_SYNC();      // the set-up above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel; nothing before this line touches global data
 
     const int seg_stride = gridDim.x;
     const int segs_per_image = p.strips * p.segs_y;
@@ -306,7 +308,7 @@ inline int launch_conv_tc_s2(const bf16* in, ConvTcParams p, cudaStream_t st) {
     int grid = p.total_segs < sms ? p.total_segs : sms;
     const CUtensorMap* map = nullptr;
     PTTA_TRY(conv_tc_tmap(in, p.N, p.H, p.W, &map));
-    conv3x3_tc_s2_kernel<<<grid, C::THREADS, C::SMEM, st>>>(*map, p);
+    launch_k(conv3x3_tc_s2_kernel, grid, C::THREADS, C::SMEM, st, *map, p);
     return check_launch("conv3x3_tc_s2");
 }
 

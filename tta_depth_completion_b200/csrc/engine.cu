@@ -29,6 +29,12 @@ namespace ptta {
 static thread_local std::string g_error;
 static std::atomic<long long> g_launches(0);
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PTTA_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
 void set_error(const char* fmt, ...) {
     char buf[1024];
     va_list ap;
@@ -141,7 +147,7 @@ struct ptta_msgchn {
     cudaStream_t st2 = nullptr;     // side stream: the zero-image branch runs concurrently with the real branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_projbn = nullptr, ev_enc1 = nullptr, ev_zmeta = nullptr;
     bool two_streams = true;
-    bool tc_enabled = true; long long tc_min_pixels = 60000, tc_s2_min_pixels = 16000;
+    bool tc_enabled = true; long long tc_min_pixels = 20000, tc_s2_min_pixels = 16000;
     bool fuse_dec_sums = true;      // experiment switches (environment: PTTA_NO_TC, PTTA_NO_FUSE_DEC_SUMS, PTTA_ONE_STREAM)
     Arena arena;
     size_t ws_bytes = 0;
@@ -474,34 +480,34 @@ struct ptta_msgchn {
         const int blocks = cdiv(tot, 256);
         if (!L.transposed) {
             // Conv2d weight [cout][cin][3][3]
-            pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(L.w, L.pack_fwd, L.cout, L.cin, L.cin * 9, 9, 0);
+            launch_k(pack_conv_weight_kernel, blocks, 256, 0, st, L.w, L.pack_fwd, L.cout, L.cin, L.cin * 9, 9, 0);
             PTTA_TRY(check_launch("pack_fwd"));
             // data gradient: output channel = cin, input channel = cout; stride-1 layers flip the taps,
             // stride-2 layers run as a transposed conv with the taps as they are
-            pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(L.w, L.pack_dgrad, L.cin, L.cout, 9, L.cin * 9, L.mode_fwd == MODE_S1 ? 1 : 0);
+            launch_k(pack_conv_weight_kernel, blocks, 256, 0, st, L.w, L.pack_dgrad, L.cin, L.cout, 9, L.cin * 9, L.mode_fwd == MODE_S1 ? 1 : 0);
             PTTA_TRY(check_launch("pack_dgrad"));
         } else {
             // ConvTranspose2d weight [cin][cout][3][3]
-            pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(L.w, L.pack_fwd, L.cout, L.cin, 9, L.cout * 9, 0);
+            launch_k(pack_conv_weight_kernel, blocks, 256, 0, st, L.w, L.pack_fwd, L.cout, L.cin, 9, L.cout * 9, 0);
             PTTA_TRY(check_launch("pack_fwd_t"));
-            pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(L.w, L.pack_dgrad, L.cin, L.cout, L.cout * 9, 9, 0);
+            launch_k(pack_conv_weight_kernel, blocks, 256, 0, st, L.w, L.pack_dgrad, L.cin, L.cout, L.cout * 9, 9, 0);
             PTTA_TRY(check_launch("pack_dgrad_t"));
         }
         if (L.img_fwd) {
-            if (L.mode_fwd == MODE_S1) pack_conv_weight_tc_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_fwd, L.img_fwd);
-            else pack_conv_weight_tc_s2_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_fwd, L.img_fwd);
+            if (L.mode_fwd == MODE_S1) launch_k(pack_conv_weight_tc_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_fwd, L.img_fwd);
+            else launch_k(pack_conv_weight_tc_s2_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_fwd, L.img_fwd);
             PTTA_TRY(check_launch("pack_fwd_tc"));
         }
         if (L.img_dgrad) {
-            if (L.mode_dgrad == MODE_S1) pack_conv_weight_tc_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_dgrad, L.img_dgrad);
-            else pack_conv_weight_tc_s2_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, st>>>(L.pack_dgrad, L.img_dgrad);
+            if (L.mode_dgrad == MODE_S1) launch_k(pack_conv_weight_tc_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_dgrad, L.img_dgrad);
+            else launch_k(pack_conv_weight_tc_s2_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_dgrad, L.img_dgrad);
             PTTA_TRY(check_launch("pack_dgrad_tc"));
         }
         return 0;
     }
     int pack_enc(EncW& E) {
         if (E.init0.cin == 2) {
-            pack_head_weight_kernel<<<2, 256, 0, st>>>(E.init0.w + 9, E.init0.dgrad_ch1, 18, 1);
+            launch_k(pack_head_weight_kernel, 2, 256, 0, st, E.init0.w + 9, E.init0.dgrad_ch1, 18, 1);
             PTTA_TRY(check_launch("pack_stem_dgrad"));
         }
         PTTA_TRY(pack_conv(E.init2));
@@ -512,18 +518,18 @@ struct ptta_msgchn {
     int pack_dec(DecW& D) {
         PTTA_TRY(pack_conv(D.d2a)); PTTA_TRY(pack_conv(D.d2b)); PTTA_TRY(pack_conv(D.d1a)); PTTA_TRY(pack_conv(D.d1b));
         PTTA_TRY(pack_conv(D.p1));
-        pack_head_weight_kernel<<<2, 256, 0, st>>>(D.p3.w, D.p3.w_fwd, 9, 0);
+        launch_k(pack_head_weight_kernel, 2, 256, 0, st, D.p3.w, D.p3.w_fwd, 9, 0);
         PTTA_TRY(check_launch("pack_head"));
-        pack_flip9_kernel<<<2, 256, 0, st>>>(D.p3.w, D.p3.w_dgrad, 32);
+        launch_k(pack_flip9_kernel, 2, 256, 0, st, D.p3.w, D.p3.w_dgrad, 32);
         PTTA_TRY(check_launch("pack_head_dgrad"));
         PTTA_CUDA(cudaMemcpyAsync(&D.p3.bias_host, D.p3.b, sizeof(float), cudaMemcpyDeviceToHost, st));
         return 0;
     }
     int pack_linear(LinearLayer& L) {
         int tot = L.in * L.out;
-        pack_matrix_kernel<<<cdiv(tot, 256), 256, 0, st>>>(L.w, L.pack, L.out, L.in, L.in, 1);
+        launch_k(pack_matrix_kernel, cdiv(tot, 256), 256, 0, st, L.w, L.pack, L.out, L.in, L.in, 1);
         PTTA_TRY(check_launch("pack_linear"));
-        pack_matrix_kernel<<<cdiv(tot, 256), 256, 0, st>>>(L.w, L.pack_t, L.in, L.out, 1, L.in);
+        launch_k(pack_matrix_kernel, cdiv(tot, 256), 256, 0, st, L.w, L.pack_t, L.in, L.out, 1, L.in);
         PTTA_TRY(check_launch("pack_linear_t"));
         return 0;
     }
@@ -624,27 +630,27 @@ struct ptta_msgchn {
     }
     int add32(const Map32& a, const Map32& b, const Map32& out, int relu = 0) {
         long long n8 = (long long)a.numel() / 8;
-        ew_add_kernel<<<cdiv(n8, 256), 256, 0, st>>>(a.p, b.p, out.p, n8, relu);
+        launch_k(ew_add_kernel, cdiv(n8, 256), 256, 0, st, a.p, b.p, out.p, n8, relu);
         return check_launch("ew_add");
     }
     int add_up2(const Map32& x, const Map32& half, bf16* relu_copy = nullptr) {   // x += up2(half) [; relu_copy = ReLU(x)]
         long long tot = (long long)x.n * x.h * x.w * 4;
-        add_up2_c32_kernel<<<cdiv(tot, 256), 256, 0, st>>>(x.p, half.p, x.p, x.n, half.h, half.w, relu_copy);
+        launch_k(add_up2_c32_kernel, cdiv(tot, 256), 256, 0, st, x.p, half.p, x.p, x.n, half.h, half.w, relu_copy);
         return check_launch("add_up2_c32");
     }
     int up2_adj32(const Map32& ghi, const Map32& glo, int accumulate) {
         long long tot = (long long)glo.n * glo.h * glo.w * 4;
-        up2_c32_adj_kernel<<<cdiv(tot, 256), 256, 0, st>>>(ghi.p, glo.p, glo.n, glo.h, glo.w, accumulate);
+        launch_k(up2_c32_adj_kernel, cdiv(tot, 256), 256, 0, st, ghi.p, glo.p, glo.n, glo.h, glo.w, accumulate);
         return check_launch("up2_c32_adj");
     }
     int up2_1(const Map1& a, const float* b, const float* c, const Map1& out) {
         long long tot = (long long)out.numel();
-        up2_1ch_kernel<<<cdiv(tot, 256), 256, 0, st>>>(a.p, b, c, out.p, a.n, a.h, a.w);
+        launch_k(up2_1ch_kernel, cdiv(tot, 256), 256, 0, st, a.p, b, c, out.p, a.n, a.h, a.w);
         return check_launch("up2_1ch");
     }
     int up2_adj1(const Map1& ghi, const Map1& glo) {
         long long tot = (long long)glo.numel();
-        up2_1ch_adj_kernel<<<cdiv(tot, 256), 256, 0, st>>>(ghi.p, glo.p, glo.n, glo.h, glo.w, 0);
+        launch_k(up2_1ch_adj_kernel, cdiv(tot, 256), 256, 0, st, ghi.p, glo.p, glo.n, glo.h, glo.w, 0);
         return check_launch("up2_1ch_adj");
     }
     int stem(const StemLayer& S, const float* p0, long long s0, float sc0, float sh0, const float* p1, long long s1, float sc1,
@@ -656,15 +662,15 @@ struct ptta_msgchn {
         p.scale[0] = sc0; p.scale[1] = sc1; p.scale[2] = sc2; p.shift[0] = sh0; p.shift[1] = sh1; p.shift[2] = sh2;
         p.w = S.w; p.bias = S.b; p.mask = nullptr; p.out = out.p; p.N = out.n; p.H = out.h; p.W = out.w;
         long long tot = (long long)out.n * out.h * out.w;
-        if (S.cin == 1) stem_conv_kernel<1><<<cdiv(tot, 128), 128, 0, st>>>(p);
-        else if (S.cin == 2) stem_conv_kernel<2><<<cdiv(tot, 128), 128, 0, st>>>(p);
-        else stem_conv_kernel<3><<<cdiv(tot, 128), 128, 0, st>>>(p);
+        if (S.cin == 1) launch_k(stem_conv_kernel<1>, cdiv(tot, 128), 128, 0, st, p);
+        else if (S.cin == 2) launch_k(stem_conv_kernel<2>, cdiv(tot, 128), 128, 0, st, p);
+        else launch_k(stem_conv_kernel<3>, cdiv(tot, 128), 128, 0, st, p);
         return check_launch("stem_conv");
     }
     // prediction layer: out = conv32->1(relu(h)) + bias [+ add]
     int head_fwd(const HeadLayer& Hd, const Map32& h, const float* add, const Map1& out) {
         long long tot = (long long)out.numel();
-        head_conv_kernel<<<dim3(cdiv(out.w, HEADC_TW), cdiv(out.h, HEADC_TH), out.n), dim3(HEADC_TW, HEADC_TH), 0, st>>>(h.p, Hd.w_fwd, Hd.bias_host, add, out.p, out.n, out.h, out.w, 1, 0);
+        launch_k(head_conv_kernel, dim3(cdiv(out.w, HEADC_TW), cdiv(out.h, HEADC_TH), out.n), dim3(HEADC_TW, HEADC_TH), 0, st, h.p, Hd.w_fwd, Hd.bias_host, add, out.p, out.n, out.h, out.w, 1, 0);
         return check_launch("head_conv");
     }
     // g_h = dgrad_{1->32}(g_out) * [h > 0]
@@ -673,19 +679,19 @@ struct ptta_msgchn {
         p.plane[0] = gout.p; p.batch_stride[0] = (long long)gout.h * gout.w; p.scale[0] = 1.f;
         p.w = Hd.w_dgrad; p.bias = nullptr; p.mask = hmask.p; p.out = gh.p; p.N = gh.n; p.H = gh.h; p.W = gh.w; p.relu_out = 0;
         long long tot = (long long)gh.n * gh.h * gh.w;
-        stem_conv_kernel<1><<<cdiv(tot, 128), 128, 0, st>>>(p);
+        launch_k(stem_conv_kernel<1>, cdiv(tot, 128), 128, 0, st, p);
         return check_launch("head_dgrad");
     }
     // gradient wrt input plane 1 of a 2-plane stem: out = conv32->1(g_a0; flipped plane-1 weights) + add
     int stem_dgrad_ch1(const StemLayer& S, const Map32& ga0, const float* add, const Map1& out) {
         long long tot = (long long)out.numel();
-        head_conv_kernel<<<dim3(cdiv(out.w, HEADC_TW), cdiv(out.h, HEADC_TH), out.n), dim3(HEADC_TW, HEADC_TH), 0, st>>>(ga0.p, S.dgrad_ch1, 0.f, add, out.p, out.n, out.h, out.w, 0, 0);
+        launch_k(head_conv_kernel, dim3(cdiv(out.w, HEADC_TW), cdiv(out.h, HEADC_TH), out.n), dim3(HEADC_TW, HEADC_TH), 0, st, ga0.p, S.dgrad_ch1, 0.f, add, out.p, out.n, out.h, out.w, 0, 0);
         return check_launch("stem_dgrad");
     }
     int stats(const bf16* x, const bf16* dy, long long rows, int C, int mode, const BnState* s, int relu_mask, int& nblk) {
         nblk = cdiv(rows, STATS_ROWS_PER_BLOCK);
         PTTA_CHECK((size_t)nblk * 2 * C <= partial_doubles, "stats partial buffer too small");
-        col_stats_kernel<<<nblk, 256, 2 * 2048 * sizeof(double), st>>>(x, dy, partial, rows, C, mode, s ? s->mean : nullptr,
+        launch_k(col_stats_kernel, nblk, 256, 2 * 2048 * sizeof(double), st, x, dy, partial, rows, C, mode, s ? s->mean : nullptr,
                                                                       s ? s->invstd : nullptr, s ? s->scale : nullptr,
                                                                       s ? s->shift : nullptr, relu_mask);
         return check_launch("col_stats");
@@ -698,15 +704,15 @@ struct ptta_msgchn {
         if (defer_running) { p.running_mean = nullptr; p.running_var = nullptr; p.num_batches_tracked = nullptr; }
         p.uvar = s.uvar;
         p.mean = s.mean; p.invstd = s.invstd; p.scale = s.scale; p.shift = s.shift; p.momentum = 0.1f; p.eps = 1e-5f;
-        bn_finalize_kernel<<<cdiv(L.c, 32), FIN_THREADS, 0, st>>>(partial, nblk, rows, L.c, p, training ? 1 : 0);
+        launch_k(bn_finalize_kernel, cdiv(L.c, 32), FIN_THREADS, 0, st, partial, nblk, rows, L.c, p, training ? 1 : 0);
         return check_launch("bn_finalize");
     }
     int bn_running_update(const BnLayer& L, const BnState& s) {
-        bn_running_update_kernel<<<cdiv(L.c, 128), 128, 0, st>>>(s.mean, s.uvar, L.rm, L.rv, L.nbt, L.c, 0.1f);
+        launch_k(bn_running_update_kernel, cdiv(L.c, 128), 128, 0, st, s.mean, s.uvar, L.rm, L.rv, L.nbt, L.c, 0.1f);
         return check_launch("bn_running_update");
     }
     int bn_apply(const bf16* x, const bf16* res, bf16* y, long long rows, int C, const BnState& s, int act) {
-        bn_apply_kernel<<<cdiv(rows, (256 / (C / 8)) * EW_ROWS), 256, 0, st>>>(x, res, y, rows, C, s.scale, s.shift, act);
+        launch_k(bn_apply_kernel, cdiv(rows, (256 / (C / 8)) * EW_ROWS), 256, 0, st, x, res, y, rows, C, s.scale, s.shift, act);
         return check_launch("bn_apply");
     }
     // dx = BN-backward(dy [* relu mask]); optionally writes dgamma / dbeta
@@ -714,9 +720,9 @@ struct ptta_msgchn {
                     float* dgamma, float* dbeta) {
         int nblk = 0;
         PTTA_TRY(stats(x, dy, rows, L.c, 1, &s, relu_mask, nblk));
-        bn_bwd_finalize_kernel<<<cdiv(L.c, 32), FIN_THREADS, 0, st>>>(partial, nblk, rows, L.c, L.gamma, s.invstd, dgamma, dbeta, k0, k1, k2);
+        launch_k(bn_bwd_finalize_kernel, cdiv(L.c, 32), FIN_THREADS, 0, st, partial, nblk, rows, L.c, L.gamma, s.invstd, dgamma, dbeta, k0, k1, k2);
         PTTA_TRY(check_launch("bn_bwd_finalize"));
-        bn_bwd_apply_kernel<<<cdiv(rows, (256 / (L.c / 8)) * EW_ROWS), 256, 0, st>>>(dy, x, dx, rows, L.c, s.mean, s.invstd, k0, k1, k2, s.scale, s.shift, relu_mask);
+        launch_k(bn_bwd_apply_kernel, cdiv(rows, (256 / (L.c / 8)) * EW_ROWS), 256, 0, st, dy, x, dx, rows, L.c, s.mean, s.invstd, k0, k1, k2, s.scale, s.shift, relu_mask);
         return check_launch("bn_bwd_apply");
     }
     int gemm(const bf16* A, const bf16* B, bf16* C, const float* bias, long long M, int Nn, int K) {
@@ -825,21 +831,21 @@ struct ptta_msgchn {
             float f[3];
             for (int c = 0; c < 3; ++c) f[c] = isc[c] != 0.f ? -ish[c] / isc[c] : 0.f;
             long long tot = (long long)N * 3 * H * W;
-            pad_pair_kernel<<<cdiv(tot, 256), 256, 0, st>>>(image, pimg, Nu, 3, Hu, Wu, H, W, 1.f, f[0], f[1], f[2]);
+            launch_k(pad_pair_kernel, cdiv(tot, 256), 256, 0, st, image, pimg, Nu, 3, Hu, Wu, H, W, 1.f, f[0], f[1], f[2]);
             PTTA_TRY(check_launch("pad_pair(image)"));
             tot = (long long)N * H * W;
-            pad_pair_kernel<<<cdiv(tot, 256), 256, 0, st>>>(sparse, psp, Nu, 1, Hu, Wu, H, W, 1.f, 0.f, 0.f, 0.f);
+            launch_k(pad_pair_kernel, cdiv(tot, 256), 256, 0, st, sparse, psp, Nu, 1, Hu, Wu, H, W, 1.f, 0.f, 0.f, 0.f);
             PTTA_TRY(check_launch("pad_pair(sparse)"));
         }
         PTTA_TRY(forward_impl(pimg, isc, ish, psp, cap, training));
         long long tot = (long long)Nu * Hu * Wu;
-        unpad_mean_kernel<<<cdiv(tot, 256), 256, 0, st>>>(real.output.p, out_u.p, Nu, Hu, Wu, H, W);
+        launch_k(unpad_mean_kernel, cdiv(tot, 256), 256, 0, st, real.output.p, out_u.p, Nu, Hu, Wu, H, W);
         return check_launch("unpad_mean");
     }
     int forward_impl(const float* image, const float* isc, const float* ish, const float* sparse, float cap, bool training) {
         {
             long long tot = (long long)N * (H / 4) * (W / 4);
-            pyramid_kernel<<<cdiv(tot, 128), 128, 0, st>>>(sparse, dcl.p, d12.p, d14.p, N, H, W, cap, cap > 0.f ? 1 : 0);
+            launch_k(pyramid_kernel, cdiv(tot, 128), 128, 0, st, sparse, dcl.p, d12.p, d14.p, N, H, W, cap, cap > 0.f ? 1 : 0);
             PTTA_TRY(check_launch("pyramid"));
         }
         Map32 rc[5] = {real.c[0], real.c[1], real.c2raw, real.c[3], real.c[4]};
@@ -900,12 +906,12 @@ struct ptta_msgchn {
         // the map losses are taken on the caller-shaped prediction (the un-padded mean when `padded`); the cosine loss on all R rows
         const float* pred = padded ? out_u.p : real.output.p;
         dim3 grid(loss_map_blocks, Nu);
-        loss_map_reduce_kernel<<<grid, LOSS_BLOCK, 0, st>>>(pred, sparse, validity, image_raw, loss_map_partial, Hu, Wu, cap,
+        launch_k(loss_map_reduce_kernel, grid, LOSS_BLOCK, 0, st, pred, sparse, validity, image_raw, loss_map_partial, Hu, Wu, cap,
                                                            cap > 0.f ? 1 : 0);
         PTTA_TRY(check_launch("loss_map_reduce"));
-        loss_cos_rows_kernel<<<loss_cos_blocks, 256, 0, st>>>(emb, ref, rowstat, loss_cos_partial, R, 512);
+        launch_k(loss_cos_rows_kernel, loss_cos_blocks, 256, 0, st, emb, ref, rowstat, loss_cos_partial, R, 512);
         PTTA_TRY(check_launch("loss_cos_rows"));
-        loss_finalize_kernel<<<1, 256, 0, st>>>(loss_map_partial, loss_map_blocks, loss_cos_partial, loss_cos_blocks, Nu, Hu, Wu, R, w_sd, w_sm,
+        launch_k(loss_finalize_kernel, 1, 256, 0, st, loss_map_partial, loss_map_blocks, loss_cos_partial, loss_cos_blocks, Nu, Hu, Wu, R, w_sd, w_sm,
                                               w_cos, 0.3f, losses);
         return check_launch("loss_finalize");
     }
@@ -926,10 +932,10 @@ struct ptta_msgchn {
         const Branch& B = real;
         {
             long long tot = (long long)Nu * Hu * Wu;
-            loss_map_grad_kernel<<<cdiv(tot, 256), 256, 0, st>>>(padded ? out_u.p : B.output.p, l_d, l_v, l_img, padded ? g_out_u.p : g_out.p, losses,
+            launch_k(loss_map_grad_kernel, cdiv(tot, 256), 256, 0, st, padded ? out_u.p : B.output.p, l_d, l_v, l_img, padded ? g_out_u.p : g_out.p, losses,
                                                                Nu, Hu, Wu, l_cap, l_cap > 0.f ? 1 : 0, l_wsd, l_wsm, gscale);
             PTTA_TRY(check_launch("loss_map_grad"));
-            loss_cos_grad_kernel<<<loss_cos_blocks, 256, 0, st>>>(emb, ref, rowstat, losses, g_ref, R, 512, gscale);
+            launch_k(loss_cos_grad_kernel, loss_cos_blocks, 256, 0, st, emb, ref, rowstat, losses, g_ref, R, 512, gscale);
             PTTA_TRY(check_launch("loss_cos_grad"));
         }
         return 0;
@@ -940,7 +946,7 @@ struct ptta_msgchn {
         const Branch& B = real;
         if (padded) {   // adjoint of the crop + mean: each copy receives half of the gradient at its crop, zero elsewhere
             long long tot = (long long)N * H * W;
-            pad_pair_kernel<<<cdiv(tot, 256), 256, 0, st>>>(g_out_u.p, g_out.p, Nu, 1, Hu, Wu, H, W, 0.5f, 0.f, 0.f, 0.f);
+            launch_k(pad_pair_kernel, cdiv(tot, 256), 256, 0, st, g_out_u.p, g_out.p, Nu, 1, Hu, Wu, H, W, 0.5f, 0.f, 0.f, 0.f);
             PTTA_TRY(check_launch("pad_pair(g_output)"));
         }
         // proxy head on the real rows: ref = L3(relu(bn(L0(z))))
@@ -994,7 +1000,7 @@ struct ptta_msgchn {
             PTTA_TRY(launch_wgrad(wp, grad_of("conv1_rgb_meta.weight"), 32, 32, st));
             int nblk = 0;
             PTTA_TRY(stats(GC2.p, nullptr, rows, 32, 0, nullptr, 0, nblk));
-            colsum_finalize_kernel<<<1, FIN_THREADS, 0, st>>>(partial, nblk, 32, grad_of("conv1_rgb_meta.bias"));
+            launch_k(colsum_finalize_kernel, 1, FIN_THREADS, 0, st, partial, nblk, 32, grad_of("conv1_rgb_meta.bias"));
             return check_launch("colsum_finalize");
         }
         const std::string p = "conv1_rgb_meta.conv1_meta";
@@ -1003,7 +1009,7 @@ struct ptta_msgchn {
         {
             int nblk = 0;
             PTTA_TRY(stats(G4a.p, nullptr, rows, 32, 0, nullptr, 0, nblk));
-            colsum_finalize_kernel<<<1, FIN_THREADS, 0, st>>>(partial, nblk, 32, grad_of(p + ".1.bias"));
+            launch_k(colsum_finalize_kernel, 1, FIN_THREADS, 0, st, partial, nblk, 32, grad_of(p + ".1.bias"));
             PTTA_TRY(check_launch("colsum_finalize"));
         }
         {   // conv2 wgrad: input = leaky(bn1(mh))
@@ -1029,9 +1035,9 @@ struct ptta_msgchn {
 
     int adam_step() {
         PTTA_CHECK(n_adam_chunks > 0, "Adam state not bound (grad/, adam_m/, adam_v/ entries for every adapted tensor)");
-        adam_kernel<<<n_adam_chunks, 256, 0, st>>>(adam_chunks, adam_hyper);
+        launch_k(adam_kernel, n_adam_chunks, 256, 0, st, adam_chunks, adam_hyper);
         PTTA_TRY(check_launch("adam"));
-        adam_advance_kernel<<<1, 1, 0, st>>>(adam_hyper);
+        launch_k(adam_advance_kernel, 1, 1, 0, st, adam_hyper);
         PTTA_TRY(check_launch("adam_advance"));
         return pack_adapted();
     }
@@ -1039,7 +1045,7 @@ struct ptta_msgchn {
     int outlier(const float* sparse) {
         dim3 grid(cdiv(Wu, OR_TX), cdiv(Hu, OR_TY), Nu), block(OR_TX, OR_TY);
         size_t sm = (size_t)(OR_TX + 6) * (OR_TY + 6) * sizeof(float);
-        outlier_removal_kernel<<<grid, block, sm, st>>>(sparse, fd.p, fv.p, Hu, Wu, 7, 1.5f);
+        launch_k(outlier_removal_kernel, grid, block, sm, st, sparse, fd.p, fv.p, Hu, Wu, 7, 1.5f);
         return check_launch("outlier_removal");
     }
 
@@ -1066,19 +1072,19 @@ int ptta_outlier_removal(const float* d, float* d_out, float* v_out, int n, int 
     int pad = ksize / 2;
     dim3 grid(cdiv(w, OR_TX), cdiv(h, OR_TY), n), block(OR_TX, OR_TY);
     size_t sm = (size_t)(OR_TX + 2 * pad) * (OR_TY + 2 * pad) * sizeof(float);
-    outlier_removal_kernel<<<grid, block, sm, (cudaStream_t)stream>>>(d, d_out, v_out, h, w, ksize, thr);
+    launch_k(outlier_removal_kernel, grid, block, sm, (cudaStream_t)stream, d, d_out, v_out, h, w, ksize, thr);
     return check_launch("outlier_removal");
 }
 
 int ptta_pyramid(const float* d, float* dc, float* d2, float* d4, int n, int h, int w, float cap, int do_clamp, ptta_stream_t stream) {
     PTTA_CHECK(h % 4 == 0 && w % 4 == 0, "pyramid: %dx%d must be multiples of 4", h, w);
     long long tot = (long long)n * (h / 4) * (w / 4);
-    pyramid_kernel<<<cdiv(tot, 128), 128, 0, (cudaStream_t)stream>>>(d, dc, d2, d4, n, h, w, cap, do_clamp);
+    launch_k(pyramid_kernel, cdiv(tot, 128), 128, 0, (cudaStream_t)stream, d, dc, d2, d4, n, h, w, cap, do_clamp);
     return check_launch("pyramid");
 }
 
 int ptta_pack_conv_weight(const float* src, void* dst, int o, int i, int s_o, int s_i, int flip, ptta_stream_t stream) {
-    pack_conv_weight_kernel<<<cdiv(9 * o * i, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, o, i, s_o, s_i, flip);
+    launch_k(pack_conv_weight_kernel, cdiv(9 * o * i, 256), 256, 0, (cudaStream_t)stream, src, (bf16*)dst, o, i, s_o, s_i, flip);
     return check_launch("pack_conv_weight");
 }
 
@@ -1104,15 +1110,26 @@ int ptta_conv3x3_tc(const void* in, void* out, const void* wimage, const float* 
     return launch_conv_tc((const bf16*)in, p, (cudaStream_t)stream);
 }
 
+int ptta_conv3x3_tc_ex(const void* in, void* out, void* out2, const void* wimage, const float* bias, int n, int h, int w, int relu_out,
+                       const void* mask, const void* add, const void* add2, ptta_stream_t stream) {
+    PTTA_CHECK(in && out && wimage, "conv3x3_tc_ex: null argument");
+    PTTA_CHECK(!(add && add2), "conv3x3_tc_ex: add and add2 are mutually exclusive");
+    PTTA_CHECK(!add2 || out2, "conv3x3_tc_ex: add2 needs out2");
+    ConvTcParams p; memset(&p, 0, sizeof(p));
+    p.w = (const bf16*)wimage; p.bias = bias; p.out = (bf16*)out; p.out2 = (bf16*)out2; p.mask = (const bf16*)mask; p.add = (const bf16*)add;
+    p.add2 = (const bf16*)add2; p.N = n; p.H = h; p.W = w; p.relu_out = relu_out;
+    return launch_conv_tc((const bf16*)in, p, (cudaStream_t)stream);
+}
+
 int ptta_pack_conv_weight_tc(const void* wpack, void* image, ptta_stream_t stream) {
     PTTA_CHECK(wpack && image, "pack_conv_weight_tc: null argument");
-    pack_conv_weight_tc_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)wpack, (bf16*)image);
+    launch_k(pack_conv_weight_tc_kernel, cdiv(9 * 32 * 4, 256), 256, 0, (cudaStream_t)stream, (const bf16*)wpack, (bf16*)image);
     return check_launch("pack_conv_weight_tc");
 }
 
 int ptta_pack_conv_weight_tc_s2(const void* wpack, void* image, ptta_stream_t stream) {
     PTTA_CHECK(wpack && image, "pack_conv_weight_tc_s2: null argument");
-    pack_conv_weight_tc_s2_kernel<<<cdiv(9 * 32 * 4, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)wpack, (bf16*)image);
+    launch_k(pack_conv_weight_tc_s2_kernel, cdiv(9 * 32 * 4, 256), 256, 0, (cudaStream_t)stream, (const bf16*)wpack, (bf16*)image);
     return check_launch("pack_conv_weight_tc_s2");
 }
 int ptta_conv3x3_tc_s2(const void* in, void* out, void* out_relu, const void* wimage, const float* bias, int n, int h, int w, int relu_out,
@@ -1124,16 +1141,21 @@ int ptta_conv3x3_tc_s2(const void* in, void* out, void* out_relu, const void* wi
     return launch_conv_tc_s2((const bf16*)in, p, (cudaStream_t)stream);
 }
 
-int ptta_debug_set(int v) {
-    PTTA_CUDA(cudaMemcpyToSymbol(g_tc_dbg, &v, sizeof(int)));
+#ifdef PTTA_STAMPS
+extern "C" int ptta_stamps_reset(void) {
+    unsigned int z = 0;
+    PTTA_CUDA(cudaMemcpyToSymbol(g_stamp_count, &z, sizeof(z)));
     return 0;
 }
-
-int ptta_debug_read_ts(long long* out, int n) {
-    PTTA_CHECK(out && n > 0 && n <= 3 * 2048, "debug_read_ts: bad arguments");
-    PTTA_CUDA(cudaMemcpyFromSymbol(out, g_tc_ts, sizeof(long long) * n));
-    return 0;
+extern "C" int ptta_stamps_read(unsigned long long* out, int capacity) {
+    unsigned int n = 0;
+    PTTA_CUDA(cudaMemcpyFromSymbol(&n, g_stamp_count, sizeof(n)));
+    if ((int)n > capacity) n = capacity;
+    if (n > 8192u) n = 8192u;
+    PTTA_CUDA(cudaMemcpyFromSymbol(out, g_stamps, sizeof(unsigned long long) * n));
+    return (int)n + 1000000;      // count + 1e6 (so that 0 stays "ok" for the usual status convention)
 }
+#endif
 
 size_t ptta_conv3x3_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout) { return wgrad_partial_bytes(n, h, w, cin, cout); }
 
@@ -1156,37 +1178,37 @@ int ptta_stem_conv(const float* const* planes, const long long* strides, const f
     p.w = weight; p.bias = bias; p.mask = (const bf16*)mask; p.out = (bf16*)out; p.N = n; p.H = h; p.W = w;
     long long tot = (long long)n * h * w;
     cudaStream_t st = (cudaStream_t)stream;
-    if (cin == 1) stem_conv_kernel<1><<<cdiv(tot, 128), 128, 0, st>>>(p);
-    else if (cin == 2) stem_conv_kernel<2><<<cdiv(tot, 128), 128, 0, st>>>(p);
-    else stem_conv_kernel<3><<<cdiv(tot, 128), 128, 0, st>>>(p);
+    if (cin == 1) launch_k(stem_conv_kernel<1>, cdiv(tot, 128), 128, 0, st, p);
+    else if (cin == 2) launch_k(stem_conv_kernel<2>, cdiv(tot, 128), 128, 0, st, p);
+    else launch_k(stem_conv_kernel<3>, cdiv(tot, 128), 128, 0, st, p);
     return check_launch("stem_conv");
 }
 
 int ptta_head_conv(const void* in, const float* w, float bias, const float* add, float* out, int n, int h, int ww, int relu_in,
                    int accumulate, ptta_stream_t stream) {
     long long tot = (long long)n * h * ww;
-    head_conv_kernel<<<dim3(cdiv(ww, HEADC_TW), cdiv(h, HEADC_TH), n), dim3(HEADC_TW, HEADC_TH), 0, (cudaStream_t)stream>>>((const bf16*)in, w, bias, add, out, n, h, ww, relu_in, accumulate);
+    launch_k(head_conv_kernel, dim3(cdiv(ww, HEADC_TW), cdiv(h, HEADC_TH), n), dim3(HEADC_TW, HEADC_TH), 0, (cudaStream_t)stream, (const bf16*)in, w, bias, add, out, n, h, ww, relu_in, accumulate);
     return check_launch("head_conv");
 }
 
 int ptta_up2_1ch(const float* a, const float* b, const float* c, float* out, int n, int h, int w, ptta_stream_t stream) {
     long long tot = (long long)n * h * w * 4;
-    up2_1ch_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(a, b, c, out, n, h, w);
+    launch_k(up2_1ch_kernel, cdiv(tot, 256), 256, 0, (cudaStream_t)stream, a, b, c, out, n, h, w);
     return check_launch("up2_1ch");
 }
 int ptta_up2_1ch_adjoint(const float* ghi, float* glo, int n, int h, int w, int accumulate, ptta_stream_t stream) {
     long long tot = (long long)n * h * w;
-    up2_1ch_adj_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(ghi, glo, n, h, w, accumulate);
+    launch_k(up2_1ch_adj_kernel, cdiv(tot, 256), 256, 0, (cudaStream_t)stream, ghi, glo, n, h, w, accumulate);
     return check_launch("up2_1ch_adj");
 }
 int ptta_add_up2_c32(const void* x, const void* half, void* out, int n, int h, int w, ptta_stream_t stream) {
     long long tot = (long long)n * h * w * 4 * 4;
-    add_up2_c32_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)half, (bf16*)out, n, h, w, nullptr);
+    launch_k(add_up2_c32_kernel, cdiv(tot, 256), 256, 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)half, (bf16*)out, n, h, w, nullptr);
     return check_launch("add_up2_c32");
 }
 int ptta_up2_c32_adjoint(const void* ghi, void* glo, int n, int h, int w, int accumulate, ptta_stream_t stream) {
     long long tot = (long long)n * h * w * 4;
-    up2_c32_adj_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)ghi, (bf16*)glo, n, h, w, accumulate);
+    launch_k(up2_c32_adj_kernel, cdiv(tot, 256), 256, 0, (cudaStream_t)stream, (const bf16*)ghi, (bf16*)glo, n, h, w, accumulate);
     return check_launch("up2_c32_adj");
 }
 
@@ -1202,6 +1224,7 @@ int ptta_gemm_bf16_tc(const void* a, const void* b, void* c, const float* bias, 
 
 __global__ void adam_flat_kernel(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, float eps,
                                  float wd, int step) {
+    PDL_SYNC();
     const double bc1 = 1.0 - pow(b1, (double)step);
     const double bc2 = 1.0 - pow(b2, (double)step);
     const float step_size = (float)(lr / bc1);
@@ -1214,8 +1237,10 @@ __global__ void adam_flat_kernel(float* p, const float* g, float* m, float* v, l
     }
 }
 // CUDA-graph friendly variant: step counter and hyper-parameters (lr, beta1, beta2, eps, weight_decay as doubles) live on the device
-__global__ void adam_tick_kernel(int* step) { *step += 1; }
+__global__ void adam_tick_kernel(int* step) {
+    PDL_SYNC(); *step += 1; }
 __global__ void adam_flat_dev_kernel(float* p, const float* g, float* m, float* v, long long n, const double* __restrict__ hy, const int* __restrict__ step) {
+    PDL_SYNC();
     const double b1 = hy[1], b2 = hy[2];
     const int t = *step;
     const double bc1 = 1.0 - pow(b1, (double)t);
@@ -1254,11 +1279,11 @@ int ptta_tta_loss_forward(const float* pred, const float* image_raw, const float
     char* ws = (char*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(L.map_blocks, n);
-    loss_map_reduce_kernel<<<grid, LOSS_BLOCK, 0, st>>>(pred, sparse, validity, image_raw, (double*)(ws + L.map_partial), h, w, cap, cap > 0.f ? 1 : 0);
+    launch_k(loss_map_reduce_kernel, grid, LOSS_BLOCK, 0, st, pred, sparse, validity, image_raw, (double*)(ws + L.map_partial), h, w, cap, cap > 0.f ? 1 : 0);
     PTTA_TRY(check_launch("loss_map_reduce"));
-    loss_cos_rows_kernel<<<L.cos_blocks, 256, 0, st>>>((const bf16*)emb, (const bf16*)ref, (float*)(ws + L.rowstat), (double*)(ws + L.cos_partial), rows, dim);
+    launch_k(loss_cos_rows_kernel, L.cos_blocks, 256, 0, st, (const bf16*)emb, (const bf16*)ref, (float*)(ws + L.rowstat), (double*)(ws + L.cos_partial), rows, dim);
     PTTA_TRY(check_launch("loss_cos_rows"));
-    loss_finalize_kernel<<<1, 256, 0, st>>>((const double*)(ws + L.map_partial), L.map_blocks, (const double*)(ws + L.cos_partial), L.cos_blocks, n, h, w,
+    launch_k(loss_finalize_kernel, 1, 256, 0, st, (const double*)(ws + L.map_partial), L.map_blocks, (const double*)(ws + L.cos_partial), L.cos_blocks, n, h, w,
                                           rows, w_sd, w_sm, w_cos, 0.3f, (LossScalars*)(ws + L.scalars));
     return check_launch("loss_finalize");
 }
@@ -1271,10 +1296,10 @@ int ptta_tta_loss_backward(const float* pred, const float* image_raw, const floa
     char* ws = (char*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
     const long long tot = (long long)n * h * w;
-    loss_map_grad_kernel<<<cdiv(tot, 256), 256, 0, st>>>(pred, sparse, validity, image_raw, g_pred, (const LossScalars*)(ws + L.scalars), n, h, w, cap,
+    launch_k(loss_map_grad_kernel, cdiv(tot, 256), 256, 0, st, pred, sparse, validity, image_raw, g_pred, (const LossScalars*)(ws + L.scalars), n, h, w, cap,
                                                        cap > 0.f ? 1 : 0, w_sd, w_sm, gscale);
     PTTA_TRY(check_launch("loss_map_grad"));
-    loss_cos_grad_kernel<<<L.cos_blocks, 256, 0, st>>>((const bf16*)emb, (const bf16*)ref, (const float*)(ws + L.rowstat),
+    launch_k(loss_cos_grad_kernel, L.cos_blocks, 256, 0, st, (const bf16*)emb, (const bf16*)ref, (const float*)(ws + L.rowstat),
                                                       (const LossScalars*)(ws + L.scalars), (bf16*)g_ref, rows, dim, gscale);
     return check_launch("loss_cos_grad");
 }
@@ -1284,17 +1309,17 @@ int ptta_adam_flat(float* p, const float* g, float* m, float* v, long long n, do
     PTTA_CHECK(step >= 1, "adam: step must be >= 1");
     if (n <= 0) return 0;
     int blocks = (int)std::min<long long>(cdiv(n, 256), 1184);
-    adam_flat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, (float)eps, (float)wd, step);
+    launch_k(adam_flat_kernel, blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr, b1, b2, (float)eps, (float)wd, step);
     return check_launch("adam_flat");
 }
 
 int ptta_adam_flat_dev(float* p, const float* g, float* m, float* v, long long n, const double* hyper_dev, int* step_dev, ptta_stream_t stream) {
     PTTA_CHECK(p && g && m && v && hyper_dev && step_dev, "adam_flat_dev: null pointer");
     if (n <= 0) return 0;
-    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    launch_k(adam_tick_kernel, 1, 1, 0, (cudaStream_t)stream, step_dev);
     PTTA_TRY(check_launch("adam_tick"));
     int blocks = (int)std::min<long long>(cdiv(n, 256), 1184);
-    adam_flat_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper_dev, step_dev);
+    launch_k(adam_flat_dev_kernel, blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, n, hyper_dev, step_dev);
     return check_launch("adam_flat_dev");
 }
 
@@ -1317,7 +1342,7 @@ int ptta_mdconv_forward(const float* input, const float* weight, const float* bi
     const int ho = h + 2 * pad - (kh - 1), wo = w + 2 * pad - (kw - 1);
     PTTA_CHECK(ho >= 1 && wo >= 1 && n >= 1, "mdconv_forward: empty output");
     dim3 grid(cdiv(wo, PROP_TX), cdiv(ho, PROP_TY), n), block(PROP_TX, PROP_TY);
-    mdconv1_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(input, weight, bias, offset, mask, output, h, w, ho, wo, kh, pad);
+    launch_k(mdconv1_forward_kernel, grid, block, 0, (cudaStream_t)stream, input, weight, bias, offset, mask, output, h, w, ho, wo, kh, pad);
     return check_launch("mdconv1_forward");
 }
 
@@ -1333,7 +1358,7 @@ int ptta_mdconv_backward(const float* input, const float* weight, const float* o
     if (grad_weight) PTTA_CUDA(cudaMemsetAsync(grad_weight, 0, sizeof(float) * kh * kw, st));
     if (grad_bias) PTTA_CUDA(cudaMemsetAsync(grad_bias, 0, sizeof(float), st));
     dim3 grid(cdiv(wo, PROP_TX), cdiv(ho, PROP_TY), n), block(PROP_TX, PROP_TY);
-    mdconv1_backward_kernel<<<grid, block, 0, st>>>(input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask, grad_weight,
+    launch_k(mdconv1_backward_kernel, grid, block, 0, st, input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask, grad_weight,
                                                    grad_bias, h, w, ho, wo, kh, pad);
     return check_launch("mdconv1_backward");
 }
@@ -1343,7 +1368,7 @@ int ptta_nlspn_offset_affinity_forward(const float* offset_aff, const float* con
     PTTA_CHECK(offset_aff && offset && aff, "nlspn_offset_affinity_forward: null argument");
     PTTA_CHECK(n >= 1 && h >= 1 && w >= 1, "nlspn_offset_affinity_forward: bad shape %dx%dx%d", n, h, w);
     dim3 grid(cdiv(w, PROP_TX), cdiv(h, PROP_TY), n), block(PROP_TX, PROP_TY);
-    offset_affinity_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(offset_aff, confidence, 1.f / (aff_scale_const + 1e-8f), legacy, offset, aff,
+    launch_k(offset_affinity_forward_kernel, grid, block, 0, (cudaStream_t)stream, offset_aff, confidence, 1.f / (aff_scale_const + 1e-8f), legacy, offset, aff,
                                                                              h, w);
     return check_launch("offset_affinity_forward");
 }
@@ -1355,7 +1380,7 @@ int ptta_nlspn_offset_affinity_backward(const float* offset_aff, const float* co
     cudaStream_t st = (cudaStream_t)stream;
     if (grad_confidence) PTTA_CUDA(cudaMemsetAsync(grad_confidence, 0, sizeof(float) * (size_t)n * h * w, st));
     dim3 grid(cdiv(w, PROP_TX), cdiv(h, PROP_TY), n), block(PROP_TX, PROP_TY);
-    offset_affinity_backward_kernel<<<grid, block, 0, st>>>(offset_aff, confidence, 1.f / (aff_scale_const + 1e-8f), legacy, grad_offset, grad_aff,
+    launch_k(offset_affinity_backward_kernel, grid, block, 0, st, offset_aff, confidence, 1.f / (aff_scale_const + 1e-8f), legacy, grad_offset, grad_aff,
                                                            grad_offset_aff, grad_confidence, h, w);
     return check_launch("offset_affinity_backward");
 }
@@ -1369,13 +1394,13 @@ int ptta_nlspn_propagate_forward(const float* feat_init, const float* offset, co
     PTTA_CHECK(n >= 1 && h >= 1 && w >= 1 && prop_time >= 1, "nlspn_propagate_forward: bad shape %dx%dx%d, prop_time %d", n, h, w, prop_time);
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)n * h * w;
-    prop_blend_kernel<<<cdiv(total, 256), 256, 0, st>>>(feat_init, feat_fix, saved, total);
+    launch_k(prop_blend_kernel, cdiv(total, 256), 256, 0, st, feat_init, feat_fix, saved, total);
     PTTA_TRY(check_launch("prop_blend"));
     dim3 grid(cdiv(w, PROP_TX), cdiv(h, PROP_TY), n), block(PROP_TX, PROP_TY);
     for (int k = 0; k < prop_time; ++k) {
         const bool last = k == prop_time - 1;
         float* raw = last ? feat_out : (list_feat ? list_feat + (size_t)k * total : nullptr);
-        prop_step_kernel<<<grid, block, 0, st>>>(saved + (size_t)k * total, offset, aff, feat_fix, raw, last ? nullptr : saved + (size_t)(k + 1) * total,
+        launch_k(prop_step_kernel, grid, block, 0, st, saved + (size_t)k * total, offset, aff, feat_fix, raw, last ? nullptr : saved + (size_t)(k + 1) * total,
                                                 h, w);
         PTTA_TRY(check_launch("prop_step"));
         if (last && list_feat) PTTA_CUDA(cudaMemcpyAsync(list_feat + (size_t)k * total, feat_out, sizeof(float) * total, cudaMemcpyDeviceToDevice, st));
@@ -1397,12 +1422,12 @@ int ptta_nlspn_propagate_backward(const float* grad_out, const float* offset, co
     dim3 grid(cdiv(w, PROP_TX), cdiv(h, PROP_TY), n), block(PROP_TX, PROP_TY);
     for (int k = prop_time - 1; k >= 0; --k) {
         const bool first = k == prop_time - 1;
-        prop_step_backward_kernel<<<grid, block, 0, st>>>(saved + (size_t)k * total, offset, aff, feat_fix, a, b, grad_offset, grad_aff, h, w,
+        launch_k(prop_step_backward_kernel, grid, block, 0, st, saved + (size_t)k * total, offset, aff, feat_fix, a, b, grad_offset, grad_aff, h, w,
                                                          first ? 0 : 1, first ? 0 : 1);
         PTTA_TRY(check_launch("prop_step_backward"));
         float* t = a; a = b; b = t;          // `a` now holds the gradient wrt this step's blended input; `b` has been cleared
     }
-    prop_mask_grad_kernel<<<cdiv(total, 256), 256, 0, st>>>(a, feat_fix, grad_feat_init, total);
+    launch_k(prop_mask_grad_kernel, cdiv(total, 256), 256, 0, st, a, feat_fix, grad_feat_init, total);
     return check_launch("prop_mask_grad");
 }
 

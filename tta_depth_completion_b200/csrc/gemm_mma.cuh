@@ -16,6 +16,7 @@ struct GemmParams {
 
 template <int WARPS_M, int WARPS_N, int MT>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32) gemm_mma_kernel(const GemmParams p) {
+    PDL_SYNC();
     const int BM = WARPS_M * MT * 16, BN = WARPS_N * 32, BK = 32, STAGES = 3;
     const int NT = WARPS_M * WARPS_N * 32;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -111,7 +112,7 @@ int launch_gemm_t(const GemmParams& p, cudaStream_t st) {
         attr_set = true;
     }
     dim3 grid(cdiv(p.M, BM), p.N / BN);
-    gemm_mma_kernel<WARPS_M, WARPS_N, MT><<<grid, WARPS_M * WARPS_N * 32, smem, st>>>(p);
+    launch_k(gemm_mma_kernel<WARPS_M, WARPS_N, MT>, grid, WARPS_M * WARPS_N * 32, smem, st, p);
     return check_launch("gemm_mma");
 }
 

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(GemmTcCfg::THREADS, 1) gemm_tc_kernel(const __
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    PDL_SYNC();      // the set-up above (barriers, TMEM, descriptor prefetch) overlaps the previous kernel; nothing before this line touches global data
 
     if (warp == 0) {
         if (lane == 0) {
@@ -164,7 +165,7 @@ inline int launch_gemm_tc(const bf16* A, const bf16* B, bf16* Cout, const float*
     p.m_tiles = cdiv(M, C::BM); p.n_tiles = N / C::BN;
     int tiles = p.m_tiles * p.n_tiles;
     int grid = tiles < sms ? tiles : sms;
-    gemm_tc_kernel<<<grid, C::THREADS, C::SMEM, st>>>(ta, tb, p);
+    launch_k(gemm_tc_kernel, grid, C::THREADS, C::SMEM, st, ta, tb, p);
     return check_launch("gemm_tc");
 }
 

@@ -67,7 +67,7 @@ int ptta_nl_stem(const float* image, const float* depth, const float* w_rgb, con
                  const float* scale, const float* shift, void* out, int n, int h, int w, ptta_stream_t stream) {
     PTTA_CHECK(depth && w_rgb && b_rgb && w_dep && b_dep && out, "nl_stem: null pointer");
     const long long total = (long long)n * h * w;
-    nl_stem_kernel<<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(image, depth, w_rgb, b_rgb, w_dep, b_dep, scale, shift, (bf16*)out, n, h, w, n);
+    launch_k(nl_stem_kernel, cdiv(total, 128), 128, 0, (cudaStream_t)stream, image, depth, w_rgb, b_rgb, w_dep, b_dep, scale, shift, (bf16*)out, n, h, w, n);
     return check_launch("nl_stem");
 }
 
@@ -75,7 +75,7 @@ int ptta_nl_stem_pair(const float* image, const float* depth, const float* w_rgb
                       const float* scale, const float* shift, void* out, int n, int h, int w, ptta_stream_t stream) {
     PTTA_CHECK(image && depth && w_rgb && b_rgb && w_dep && b_dep && out, "nl_stem_pair: null pointer");
     const long long total = 2LL * n * h * w;
-    nl_stem_kernel<<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(image, depth, w_rgb, b_rgb, w_dep, b_dep, scale, shift, (bf16*)out, 2 * n, h, w, n);
+    launch_k(nl_stem_kernel, cdiv(total, 128), 128, 0, (cudaStream_t)stream, image, depth, w_rgb, b_rgb, w_dep, b_dep, scale, shift, (bf16*)out, 2 * n, h, w, n);
     return check_launch("nl_stem_pair");
 }
 
@@ -93,9 +93,9 @@ int ptta_nl_bn_stats(const void* x, long long ldx, long long rows, int c, const 
     PTTA_CHECK(x && gamma && beta && partial && mean && rstd && scale && shift && c % 64 == 0 && rows > 0, "nl_bn_stats: bad arguments");
     const int nblk = ptta_nl_reduce_blocks(rows, c);
     dim3 grid(nblk, c / 64);
-    chan_reduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, rows, c, partial);
+    launch_k(chan_reduce_kernel<0>, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, rows, c, partial);
     PTTA_TRY(check_launch("nl_chan_stats"));
-    bn_finalize2_kernel<<<cdiv(c, 32), 1024, 0, (cudaStream_t)stream>>>(partial, nblk, rows, c, gamma, beta, eps, mean, rstd, scale, shift, run_mean,
+    launch_k(bn_finalize2_kernel, cdiv(c, 32), 1024, 0, (cudaStream_t)stream, partial, nblk, rows, c, gamma, beta, eps, mean, rstd, scale, shift, run_mean,
                                                                        run_var, num_batches_tracked, momentum, nullptr);
     return check_launch("nl_bn_finalize");
 }
@@ -106,10 +106,10 @@ int ptta_nl_bn_stats_grouped(const void* x, long long ldx, long long rows_per_gr
                "nl_bn_stats_grouped: bad arguments");
     const int nblk = ptta_nl_reduce_blocks(rows_per_group, c);
     dim3 grid(nblk, c / 64, groups);
-    chan_reduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, rows_per_group,
+    launch_k(chan_reduce_kernel<0>, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, rows_per_group,
                                                                  c, partial);
     PTTA_TRY(check_launch("nl_chan_stats_grouped"));
-    bn_finalize2_kernel<<<dim3(cdiv(c, 32), groups), 1024, 0, (cudaStream_t)stream>>>(partial, nblk, rows_per_group, c, gamma, beta, eps, mean, rstd, scale,
+    launch_k(bn_finalize2_kernel, dim3(cdiv(c, 32), groups), 1024, 0, (cudaStream_t)stream, partial, nblk, rows_per_group, c, gamma, beta, eps, mean, rstd, scale,
                                                                                     shift, nullptr, nullptr, nullptr, 0.f, nullptr);
     return check_launch("nl_bn_finalize_grouped");
 }
@@ -118,9 +118,9 @@ int ptta_nl_col_sums(const void* x, long long ldx, long long rows, int c, float*
     PTTA_CHECK(x && partial && sums && c % 64 == 0 && rows > 0, "nl_col_sums: bad arguments");
     const int nblk = ptta_nl_reduce_blocks(rows, c);
     dim3 grid(nblk, c / 64);
-    chan_reduce_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, rows, c, partial);
+    launch_k(chan_reduce_kernel<0>, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, ldx, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, rows, c, partial);
     PTTA_TRY(check_launch("nl_chan_stats"));
-    bn_finalize2_kernel<<<cdiv(c, 32), 1024, 0, (cudaStream_t)stream>>>(partial, nblk, rows, c, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr,
+    launch_k(bn_finalize2_kernel, cdiv(c, 32), 1024, 0, (cudaStream_t)stream, partial, nblk, rows, c, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, nullptr,
                                                                        nullptr, nullptr, nullptr, 0.f, sums);
     return check_launch("nl_col_sums");
 }
@@ -143,7 +143,7 @@ static int bn_act_launch(const void* x, const float* scale, const float* shift, 
                          const float* rshift, void* y, long long rows, int c, int act, long long rows_per_group, ptta_stream_t stream) {
     PTTA_CHECK(x && scale && shift && y && c % 64 == 0 && rows > 0 && (!rscale || (res && rshift)), "nl_bn_act: bad arguments");
     const long long total = (rows * (c / 8) + 1) / 2;
-    bn_act_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, scale, shift, (const bf16*)res, ldr, rscale, rshift, (bf16*)y,
+    launch_k(bn_act_kernel, cdiv(total, 256), 256, 0, (cudaStream_t)stream, (const bf16*)x, scale, shift, (const bf16*)res, ldr, rscale, rshift, (bf16*)y,
                                                                      rows, c, act, rows_per_group);
     return check_launch("nl_bn_act");
 }
@@ -155,13 +155,13 @@ int ptta_nl_bn_backward(const void* dy_a, long long ld_a, const void* dy_b, long
     const int nblk = ptta_nl_reduce_blocks(rows, c);
     dim3 grid(nblk, c / 64);
     cudaStream_t st = (cudaStream_t)stream;
-    chan_reduce_kernel<1><<<grid, 256, 0, st>>>((const bf16*)x, c, (const bf16*)dy_a, ld_a, (const bf16*)dy_b, ld_b, (const bf16*)y, act, mean, rstd,
+    launch_k(chan_reduce_kernel<1>, grid, 256, 0, st, (const bf16*)x, c, (const bf16*)dy_a, ld_a, (const bf16*)dy_b, ld_b, (const bf16*)y, act, mean, rstd,
                                                rows, c, partial);
     PTTA_TRY(check_launch("nl_bn_bwd_reduce"));
-    bn_bwd_finalize2_kernel<<<cdiv(c, 32), 1024, 0, st>>>(partial, nblk, rows, c, gamma, rstd, dgamma, dbeta, coef, coef + c, coef + 2 * c);
+    launch_k(bn_bwd_finalize2_kernel, cdiv(c, 32), 1024, 0, st, partial, nblk, rows, c, gamma, rstd, dgamma, dbeta, coef, coef + c, coef + 2 * c);
     PTTA_TRY(check_launch("nl_bn_bwd_finalize"));
     const long long total = (rows * (c / 8) + 1) / 2;
-    bn_bwd_apply2_kernel<<<cdiv(total, 256), 256, 0, st>>>((const bf16*)dy_a, ld_a, (const bf16*)dy_b, ld_b, (const bf16*)y, act, (const bf16*)x, mean,
+    launch_k(bn_bwd_apply2_kernel, cdiv(total, 256), 256, 0, st, (const bf16*)dy_a, ld_a, (const bf16*)dy_b, ld_b, (const bf16*)y, act, (const bf16*)x, mean,
                                                           rstd, coef, coef + c, coef + 2 * c, (bf16*)dx, (bf16*)gskip, rows, c);
     return check_launch("nl_bn_bwd_apply");
 }
@@ -170,22 +170,22 @@ int ptta_nl_add3(const void* a, long long lda, const void* b, long long ldb, con
                  ptta_stream_t stream) {
     PTTA_CHECK(a && b && out && c % 64 == 0 && rows > 0, "nl_add3: bad arguments");
     const long long total = rows * (c / 8);
-    add3_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)b, ldb, (const bf16*)c3, ldc, (bf16*)out, rows, c);
+    launch_k(add3_kernel, cdiv(total, 256), 256, 0, (cudaStream_t)stream, (const bf16*)a, lda, (const bf16*)b, ldb, (const bf16*)c3, ldc, (bf16*)out, rows, c);
     return check_launch("nl_add3");
 }
 
 int ptta_nl_clamp0(const float* y, float* out, long long n, ptta_stream_t stream) {
-    clamp0_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(y, out, n);
+    launch_k(clamp0_kernel, cdiv(n, 256), 256, 0, (cudaStream_t)stream, y, out, n);
     return check_launch("nl_clamp0");
 }
 
 int ptta_nl_clamp(const float* x, float* out, float lo, float hi, long long n, ptta_stream_t stream) {
-    clamp_range_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, out, lo, hi, n);
+    launch_k(clamp_range_kernel, cdiv(n, 256), 256, 0, (cudaStream_t)stream, x, out, lo, hi, n);
     return check_launch("nl_clamp");
 }
 
 int ptta_nl_mask_pos(const float* g, const float* y, float* out, long long n, ptta_stream_t stream) {
-    mask_pos_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(g, y, out, n);
+    launch_k(mask_pos_kernel, cdiv(n, 256), 256, 0, (cudaStream_t)stream, g, y, out, n);
     return check_launch("nl_mask_pos");
 }
 
@@ -193,15 +193,15 @@ int ptta_nl_thin_grad_pack(const float* g_pred, const float* pred_init, const fl
                            int n, int h, int w, ptta_stream_t stream) {
     PTTA_CHECK(g_pred && pred_init && g_guide && g_conf && conf && out, "nl_thin_grad_pack: null pointer");
     const long long hw = (long long)h * w;
-    thin_grad_pack_kernel<<<cdiv(n * hw, 256), 256, 0, (cudaStream_t)stream>>>(g_pred, pred_init, g_guide, g_conf, conf, (bf16*)out, n, hw);
+    launch_k(thin_grad_pack_kernel, cdiv(n * hw, 256), 256, 0, (cudaStream_t)stream, g_pred, pred_init, g_guide, g_conf, conf, (bf16*)out, n, hw);
     return check_launch("nl_thin_grad_pack");
 }
 
 int ptta_nl_conv8to24(const float* in, const float* weight, const float* bias, float* out, int n, int h, int w, int transposed, ptta_stream_t stream) {
     PTTA_CHECK(in && weight && out, "nl_conv8to24: null pointer");
     const long long total = (long long)n * h * w;
-    if (transposed) conv8to24_kernel<true><<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(in, weight, nullptr, out, n, h, w);
-    else conv8to24_kernel<false><<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(in, weight, bias, out, n, h, w);
+    if (transposed) launch_k(conv8to24_kernel<true>, cdiv(total, 128), 128, 0, (cudaStream_t)stream, in, weight, nullptr, out, n, h, w);
+    else launch_k(conv8to24_kernel<false>, cdiv(total, 128), 128, 0, (cudaStream_t)stream, in, weight, bias, out, n, h, w);
     return check_launch("nl_conv8to24");
 }
 
@@ -225,9 +225,9 @@ int ptta_nl_wgrad48(const void* x, const void* gout, float* dw, void* workspace,
     }
     const int tiles = n * cdiv(h, 16) * cdiv(w, 16);
     const int grid = tiles < wgrad48_grid() ? tiles : wgrad48_grid();
-    wgrad48_kernel<<<grid, Wgrad48Cfg::THREADS, Wgrad48Cfg::SMEM, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gout, (float*)workspace, n, h, w);
+    launch_k(wgrad48_kernel, grid, Wgrad48Cfg::THREADS, Wgrad48Cfg::SMEM, (cudaStream_t)stream, (const bf16*)x, (const bf16*)gout, (float*)workspace, n, h, w);
     PTTA_TRY(check_launch("nl_wgrad48"));
-    wgrad48_reduce_kernel<<<cdiv(9 * 48 * 48, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dw, grid);
+    launch_k(wgrad48_reduce_kernel, cdiv(9 * 48 * 48, 256), 256, 0, (cudaStream_t)stream, (const float*)workspace, dw, grid);
     return check_launch("nl_wgrad48_reduce");
 }
 
@@ -237,9 +237,9 @@ int ptta_eval_metrics(const float* output_depth, const float* ground_truth, long
                       float* result5, ptta_stream_t stream) {
     PTTA_CHECK(output_depth && ground_truth && workspace && result5 && n > 0, "eval_metrics: bad arguments");
     int blocks = (int)(cdiv(n, 256) < 296 ? cdiv(n, 256) : 296);
-    eval_metrics_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(output_depth, ground_truth, n, min_depth, max_depth, (double*)workspace);
+    launch_k(eval_metrics_kernel, blocks, 256, 0, (cudaStream_t)stream, output_depth, ground_truth, n, min_depth, max_depth, (double*)workspace);
     PTTA_TRY(check_launch("eval_metrics"));
-    eval_metrics_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const double*)workspace, blocks, result5);
+    launch_k(eval_metrics_finalize_kernel, 1, 256, 0, (cudaStream_t)stream, (const double*)workspace, blocks, result5);
     return check_launch("eval_metrics_finalize");
 }
 
@@ -249,7 +249,7 @@ int ptta_input_stage(const void* image_u8_hwc, const void* depth_u16, float* ima
     PTTA_CHECK(n >= 1 && y0 >= 0 && x0 >= 0 && h >= 1 && w >= 1 && y0 + h <= h0 && x0 + w <= w0 && depth_multiplier > 0.f,
                "input_stage: crop %dx%d at (%d,%d) does not fit %dx%d", h, w, y0, x0, h0, w0);
     const long long total = (long long)n * h * w;
-    input_stage_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const unsigned char*)image_u8_hwc, (const unsigned short*)depth_u16, image_nchw,
+    launch_k(input_stage_kernel, cdiv(total, 256), 256, 0, (cudaStream_t)stream, (const unsigned char*)image_u8_hwc, (const unsigned short*)depth_u16, image_nchw,
                                                                           depth, validity, n, h0, w0, y0, x0, h, w, depth_multiplier);
     return check_launch("input_stage");
 }

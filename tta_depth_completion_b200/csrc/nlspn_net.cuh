@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(128) nl_stem_kernel(const float* __restrict__ 
                                                       const float* __restrict__ w_dep, const float* __restrict__ b_dep,
                                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                                       bf16* __restrict__ out, int N, int H, int W, int n_src) {
+    PDL_SYNC();
     __shared__ float s_w[27 * 48 + 9 * 16];      // [ci*9+tap][48] then [tap][16]
     __shared__ float s_b[64];
     for (int i = threadIdx.x; i < 27 * 48; i += blockDim.x) { const int co = i % 48, r = i / 48; s_w[i] = w_rgb[co * 27 + r]; }
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ dyB, long long ldB, const bf16* __restrict__ y, int act,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd, long long P, int C,
                                                           float* __restrict__ partial) {
+    PDL_SYNC();
     // blockIdx.z = statistics group (independent row ranges of P rows each, e.g. the real / zero-image halves of a merged batch)
     x += (long long)blockIdx.z * P * ldx;
     partial += (size_t)blockIdx.z * gridDim.x * 2 * C;
@@ -219,6 +221,7 @@ __global__ void __launch_bounds__(1024) bn_finalize2_kernel(const float* __restr
                                                            float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
                                                            float* __restrict__ shift, float* __restrict__ run_mean, float* __restrict__ run_var,
                                                            long long* __restrict__ nbt, float momentum, float* __restrict__ sums_out) {
+    PDL_SYNC();
     int c;
     double s, q;
     partial += (size_t)blockIdx.y * nblk * 2 * C;                     // statistics group
@@ -245,6 +248,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize2_kernel(const float* __r
                                                                const float* __restrict__ gamma, const float* __restrict__ rstd,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ k0,
                                                                float* __restrict__ k1, float* __restrict__ k2) {
+    PDL_SYNC();
     int c;
     double sg, sgx;
     if (!partial_sums(partial, nblk, C, c, sg, sgx)) return;
@@ -259,6 +263,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const bf16* __restrict__ x,
                                                      const bf16* __restrict__ res, long long ldr, const float* __restrict__ rscale,
                                                      const float* __restrict__ rshift, bf16* __restrict__ y, long long P, int C, int act,
                                                      long long rows_per_group) {
+    PDL_SYNC();
     // rows_per_group > 0: row p uses the scale / shift vectors of group p / rows_per_group (merged real | zero-image batch)
     // two 16-byte elements per thread, `half` apart, loads first (more bytes in flight per thread)
     const int c8n = C >> 3;
@@ -309,6 +314,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply2_kernel(const bf16* __restri
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ k0, const float* __restrict__ k1, const float* __restrict__ k2,
                                                             bf16* __restrict__ dx, bf16* __restrict__ gskip, long long P, int C) {
+    PDL_SYNC();
     const int c8n = C >> 3;
     const long long total = P * c8n, half = (total + 1) >> 1;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -360,6 +366,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply2_kernel(const bf16* __restri
 // out = a + b (+ c), each with its own pixel stride
 __global__ void __launch_bounds__(256) add3_kernel(const bf16* __restrict__ a, long long lda, const bf16* __restrict__ b, long long ldb,
                                                    const bf16* __restrict__ c, long long ldc, bf16* __restrict__ out, long long P, int C) {
+    PDL_SYNC();
     const int c8n = C >> 3;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P * c8n) return;
@@ -380,14 +387,17 @@ __global__ void __launch_bounds__(256) add3_kernel(const bf16* __restrict__ a, l
 
 // out = max(y, 0) (nlspnmodel_adapt.py:901);  backward: g_y = g_out * [y > 0]
 __global__ void clamp0_kernel(const float* __restrict__ y, float* __restrict__ out, long long n) {
+    PDL_SYNC();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = fmaxf(y[i], 0.f);
 }
 __global__ void clamp_range_kernel(const float* __restrict__ x, float* __restrict__ out, float lo, float hi, long long n) {
+    PDL_SYNC();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = fminf(fmaxf(x[i], lo), hi);
 }
 __global__ void mask_pos_kernel(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ out, long long n) {
+    PDL_SYNC();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = y[i] > 0.f ? g[i] : 0.f;
 }
@@ -397,6 +407,7 @@ __global__ void mask_pos_kernel(const float* __restrict__ g, const float* __rest
 __global__ void __launch_bounds__(256) thin_grad_pack_kernel(const float* __restrict__ g_pred, const float* __restrict__ pred_init,
                                                              const float* __restrict__ g_guide, const float* __restrict__ g_conf,
                                                              const float* __restrict__ conf, bf16* __restrict__ out, int N, long long HW) {
+    PDL_SYNC();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * HW) return;
     const long long n = idx / HW, o = idx - n * HW;
@@ -423,6 +434,7 @@ __global__ void __launch_bounds__(256) thin_grad_pack_kernel(const float* __rest
 template <bool TRANSPOSED>
 __global__ void __launch_bounds__(128) conv8to24_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                                                         float* __restrict__ out, int N, int H, int W) {
+    PDL_SYNC();
     constexpr int CI = TRANSPOSED ? 24 : 8, CO = TRANSPOSED ? 8 : 24;
     __shared__ float s_w[9 * CI * CO];          // [tap][ci][co]
     for (int i = threadIdx.x; i < 9 * CI * CO; i += blockDim.x) {
@@ -500,6 +512,7 @@ __device__ __forceinline__ void wgrad48_fetch(unsigned char* stage, const bf16* 
 
 __global__ void __launch_bounds__(Wgrad48Cfg::THREADS, 1) wgrad48_kernel(const bf16* __restrict__ xin, const bf16* __restrict__ gout,
                                                                         float* __restrict__ partial, int N, int H, int W) {
+    PDL_SYNC();
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_x = (W + 15) / 16, tiles_y = (H + 15) / 16;
@@ -556,6 +569,7 @@ __global__ void __launch_bounds__(Wgrad48Cfg::THREADS, 1) wgrad48_kernel(const b
 
 // dw[co][ci][tap] (Conv2d layout [48][48][3][3]) = sum over CTAs of partial[cta][tap][co][ci]
 __global__ void __launch_bounds__(256) wgrad48_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nblocks) {
+    PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 9 * 48 * 48) return;
     float s = 0.f;
@@ -569,6 +583,7 @@ __global__ void __launch_bounds__(256) wgrad48_reduce_kernel(const float* __rest
 // partial[blk][5] (double): sum |d|, sum d^2, sum |id|, sum id^2, count
 __global__ void __launch_bounds__(256) eval_metrics_kernel(const float* __restrict__ out, const float* __restrict__ gt, long long n, float min_d,
                                                            float max_d, double* __restrict__ partial) {
+    PDL_SYNC();
     __shared__ double sh[32];
     double a = 0.0, b = 0.0, c = 0.0, d = 0.0, cnt = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -587,6 +602,7 @@ __global__ void __launch_bounds__(256) eval_metrics_kernel(const float* __restri
 }
 // result[5] (float): mae, rmse, imae, irmse, number of evaluated pixels
 __global__ void __launch_bounds__(256) eval_metrics_finalize_kernel(const double* __restrict__ partial, int nblk, float* __restrict__ result) {
+    PDL_SYNC();
     __shared__ double sh[32];
     double v[5] = {0, 0, 0, 0, 0};
     for (int b = threadIdx.x; b < nblk; b += blockDim.x)
@@ -606,6 +622,7 @@ __global__ void __launch_bounds__(256) eval_metrics_finalize_kernel(const double
 __global__ void __launch_bounds__(256) input_stage_kernel(const unsigned char* __restrict__ img, const unsigned short* __restrict__ dep,
                                                           float* __restrict__ image, float* __restrict__ depth, float* __restrict__ validity,
                                                           int N, int H0, int W0, int y0, int x0, int h, int w, float multiplier) {
+    PDL_SYNC();
     const long long hw = (long long)h * w;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * hw) return;

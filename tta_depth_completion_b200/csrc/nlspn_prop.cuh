@@ -63,6 +63,7 @@ __device__ __forceinline__ float tap_value(const BilinearTap& t, float v1, float
 __global__ void __launch_bounds__(PROP_TX * PROP_TY) mdconv1_forward_kernel(
     const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias, const float* __restrict__ offset,
     const float* __restrict__ mask, float* __restrict__ out, int H, int W, int Ho, int Wo, int KS, int pad) {
+    PDL_SYNC();
     const int x = blockIdx.x * PROP_TX + threadIdx.x, y = blockIdx.y * PROP_TY + threadIdx.y, n = blockIdx.z;
     if (x >= Wo || y >= Ho) return;
     const int K = KS * KS;
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(PROP_TX * PROP_TY) mdconv1_backward_kernel(
     const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ offset, const float* __restrict__ mask,
     const float* __restrict__ gout, float* __restrict__ gin, float* __restrict__ goffset, float* __restrict__ gmask,
     float* __restrict__ gweight, float* __restrict__ gbias, int H, int W, int Ho, int Wo, int KS, int pad) {
+    PDL_SYNC();
     __shared__ float s_red[50][PROP_TY];
     const int x = blockIdx.x * PROP_TX + threadIdx.x, y = blockIdx.y * PROP_TY + threadIdx.y, n = blockIdx.z;
     const bool active = x < Wo && y < Ho;
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(PROP_TX * PROP_TY) mdconv1_backward_kernel(
 // ---------------------------------------------------------------------------------------------------------------------
 // out = fix > 0 ? fix : in   (nlspnmodel_adapt.py:356-358, 364-366: mask_fix = (feat_fix > 0), feat = (1-m)*feat + m*fix)
 __global__ void prop_blend_kernel(const float* __restrict__ in, const float* __restrict__ fix, float* __restrict__ out, long long total) {
+    PDL_SYNC();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float f = fix ? __ldg(fix + i) : 0.f;
@@ -168,6 +171,7 @@ __global__ void prop_blend_kernel(const float* __restrict__ in, const float* __r
 __global__ void __launch_bounds__(PROP_TX * PROP_TY) prop_step_kernel(const float* __restrict__ fb, const float* __restrict__ offset,
                                                                       const float* __restrict__ aff, const float* __restrict__ fix,
                                                                       float* __restrict__ out_raw, float* __restrict__ out_blend, int H, int W) {
+    PDL_SYNC();
     const int x = blockIdx.x * PROP_TX + threadIdx.x, y = blockIdx.y * PROP_TY + threadIdx.y, n = blockIdx.z;
     if (x >= W || y >= H) return;
     const long long plane = (long long)H * W, pix = (long long)y * W + x;
@@ -208,6 +212,7 @@ __global__ void __launch_bounds__(PROP_TX * PROP_TY) prop_step_backward_kernel(c
                                                                                float* __restrict__ g_in, float* __restrict__ g_scatter,
                                                                                float* __restrict__ goffset, float* __restrict__ gaff, int H, int W,
                                                                                int mask_g, int accumulate) {
+    PDL_SYNC();
     const int x = blockIdx.x * PROP_TX + threadIdx.x, y = blockIdx.y * PROP_TY + threadIdx.y, n = blockIdx.z;
     if (x >= W || y >= H) return;
     const long long plane = (long long)H * W, pix = (long long)y * W + x, idx = (long long)n * plane + pix;
@@ -255,6 +260,7 @@ __global__ void __launch_bounds__(PROP_TX * PROP_TY) prop_step_backward_kernel(c
 
 // grad wrt feat_init = [fix <= 0] * g   (backward of the first blend)
 __global__ void prop_mask_grad_kernel(const float* __restrict__ g, const float* __restrict__ fix, float* __restrict__ out, long long total) {
+    PDL_SYNC();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     out[i] = (fix && __ldg(fix + i) > 0.f) ? 0.f : g[i];
@@ -278,6 +284,7 @@ __global__ void __launch_bounds__(PROP_TX * PROP_TY) offset_affinity_forward_ker
                                                                                     const float* __restrict__ confidence, float inv_scale,
                                                                                     int legacy, float* __restrict__ offset, float* __restrict__ aff,
                                                                                     int H, int W) {
+    PDL_SYNC();
     const int x = blockIdx.x * PROP_TX + threadIdx.x, y = blockIdx.y * PROP_TY + threadIdx.y, n = blockIdx.z;
     if (x >= W || y >= H) return;
     const long long plane = (long long)H * W, pix = (long long)y * W + x;
@@ -325,6 +332,7 @@ __global__ void __launch_bounds__(PROP_TX * PROP_TY) offset_affinity_backward_ke
                                                                                      int legacy, const float* __restrict__ g_offset,
                                                                                      const float* __restrict__ g_aff, float* __restrict__ g_offset_aff,
                                                                                      float* __restrict__ g_confidence, int H, int W) {
+    PDL_SYNC();
     const int x = blockIdx.x * PROP_TX + threadIdx.x, y = blockIdx.y * PROP_TY + threadIdx.y, n = blockIdx.z;
     if (x >= W || y >= H) return;
     const long long plane = (long long)H * W, pix = (long long)y * W + x;

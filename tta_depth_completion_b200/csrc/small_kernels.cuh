@@ -16,6 +16,7 @@ namespace ptta {
 #define OR_TY 8
 __global__ void __launch_bounds__(OR_TX * OR_TY) outlier_removal_kernel(const float* __restrict__ d, float* __restrict__ d_out,
                                                                         float* __restrict__ v_out, int H, int W, int ksize, float thr) {
+    PDL_SYNC();
     extern __shared__ float s_or[];
     const int pad = ksize / 2;
     const int SW = OR_TX + 2 * pad, SH = OR_TY + 2 * pad;
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(OR_TX * OR_TY) outlier_removal_kernel(const fl
 // -------------------------------------------------------------------------------------------------
 __global__ void pyramid_kernel(const float* __restrict__ d, float* __restrict__ dc, float* __restrict__ d2, float* __restrict__ d4,
                                int N, int H, int W, float cap, int do_clamp) {
+    PDL_SYNC();
     int H4 = H / 4, W4 = W / 4;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)N * H4 * W4) return;
@@ -105,6 +107,7 @@ __global__ void pyramid_kernel(const float* __restrict__ d, float* __restrict__ 
 // -------------------------------------------------------------------------------------------------
 __global__ void pad_pair_kernel(const float* __restrict__ src, float* __restrict__ dst, int Nu, int C, int Hu, int Wu, int H, int W, float scale,
                                 float f0, float f1, float f2) {
+    PDL_SYNC();
     const long long total = 2LL * Nu * C * H * W;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -117,6 +120,7 @@ __global__ void pad_pair_kernel(const float* __restrict__ src, float* __restrict
     dst[idx] = v;
 }
 __global__ void unpad_mean_kernel(const float* __restrict__ src, float* __restrict__ dst, int Nu, int Hu, int Wu, int H, int W) {
+    PDL_SYNC();
     const long long total = (long long)Nu * Hu * Wu;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -149,6 +153,7 @@ struct StemParams {
 
 template <int CIN>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams p) {
+    PDL_SYNC();
     __shared__ float s_w[CIN * 9 * 32];   // [ci][tap][co]
     __shared__ float s_b[32];
     __shared__ __align__(16) unsigned char s_stage[4][2048];   // per warp: 32 pixels x 64 B (mask in, result out)
@@ -254,6 +259,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams p) {
 __global__ void __launch_bounds__(HEADC_TW * HEADC_TH) head_conv_kernel(const bf16* __restrict__ in, const float* __restrict__ w /*[9][32]*/,
                                                         float bias, const float* __restrict__ add, float* __restrict__ out,
                                                         int N, int H, int W, int relu_in, int accumulate) {
+    PDL_SYNC();
     __shared__ float s_w[9 * 32];
     __shared__ __align__(16) unsigned char s_in[(HEADC_TH + 2) * (HEADC_TW + 2) * 64];
     const int tid = threadIdx.y * HEADC_TW + threadIdx.x;
@@ -325,6 +331,7 @@ __host__ __device__ __forceinline__ float up2_scale(int in_size) {
 // out[y][x] = up2(a [+ b])[y][x] [+ c[y][x]]     (a, b: [N,h,w]; out, c: [N,2h,2w])
 __global__ void up2_1ch_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                                float* __restrict__ out, int N, int h, int w) {
+    PDL_SYNC();
     int H = 2 * h, W = 2 * w;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)N * H * W) return;
@@ -358,6 +365,7 @@ __device__ __forceinline__ float up2_adj_weight(int t, int s, int in_size, float
 
 // adjoint: gl[s] [+]= sum_t w(t,s) * gh[t]        (gh: [N,2h,2w] -> gl: [N,h,w])
 __global__ void up2_1ch_adj_kernel(const float* __restrict__ gh, float* __restrict__ gl, int N, int h, int w, int accumulate) {
+    PDL_SYNC();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)N * h * w) return;
     int x = idx % w;
@@ -393,6 +401,7 @@ __global__ void up2_1ch_adj_kernel(const float* __restrict__ gh, float* __restri
 // out2 (optional) additionally receives ReLU(out): the stride-2 tensor-core conv that consumes it has no ReLU-on-load
 __global__ void add_up2_c32_kernel(const bf16* __restrict__ x, const bf16* __restrict__ half, bf16* __restrict__ out, int N, int h, int w,
                                    bf16* __restrict__ out2) {
+    PDL_SYNC();
     int H = 2 * h, W = 2 * w;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)N * H * W * 4) return;
@@ -434,6 +443,7 @@ __global__ void add_up2_c32_kernel(const bf16* __restrict__ x, const bf16* __res
 
 // adjoint for 32-channel maps: gl[s] [+]= sum_t w(t,s) gh[t]
 __global__ void up2_c32_adj_kernel(const bf16* __restrict__ gh, bf16* __restrict__ gl, int N, int h, int w, int accumulate) {
+    PDL_SYNC();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)N * h * w * 4) return;
     int q = idx & 3;
@@ -491,6 +501,7 @@ __global__ void up2_c32_adj_kernel(const bf16* __restrict__ gh, bf16* __restrict
 
 // out = a + b, optionally ReLU'd (bf16, n multiple of 8)
 __global__ void ew_add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, long long n8, int relu) {
+    PDL_SYNC();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n8) return;
     uint4 av = reinterpret_cast<const uint4*>(a)[i], bv = reinterpret_cast<const uint4*>(b)[i];
@@ -524,6 +535,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__
                                                         long long rows, int C, int mode, const float* __restrict__ mean,
                                                         const float* __restrict__ invstd, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, int relu_mask) {
+    PDL_SYNC();
     extern __shared__ double s_red[];   // [256][2]... reduced per chunk below
     const int CH = C / 8;
     const int step = 256 / CH;
@@ -631,6 +643,7 @@ __device__ __forceinline__ bool block_reduce_partials(const double* __restrict__
 }
 
 __global__ void __launch_bounds__(FIN_THREADS) bn_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C, BnParams p, int training) {
+    PDL_SYNC();
     int ch; double a, b;
     if (training) {
         if (!block_reduce_partials(partial, nblk, C, 2, ch, a, b)) return;
@@ -666,6 +679,7 @@ __global__ void __launch_bounds__(FIN_THREADS) bn_finalize_kernel(const double* 
 // keeps the reference's update ORDER (real image first, zero image second) while the zero-image branch runs ahead
 __global__ void bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ uvar, float* __restrict__ running_mean,
                                          float* __restrict__ running_var, long long* __restrict__ num_batches_tracked, int C, float momentum) {
+    PDL_SYNC();
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch < C) {
         running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean[ch];
@@ -680,6 +694,7 @@ __global__ void bn_running_update_kernel(const float* __restrict__ mean, const f
 #define EW_ROWS 8
 __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res, bf16* __restrict__ y, long long rows, int C,
                                 const float* __restrict__ scale, const float* __restrict__ shift, int act) {
+    PDL_SYNC();
     const int CH = C / 8, step = 256 / CH;
     const int c = threadIdx.x % CH, r0 = threadIdx.x / CH;
     float sc[8], sh[8];
@@ -716,6 +731,7 @@ __global__ void __launch_bounds__(FIN_THREADS) bn_bwd_finalize_kernel(const doub
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ k0, float* __restrict__ k1, float* __restrict__ k2) {
+    PDL_SYNC();
     int ch; double a, b;
     if (!block_reduce_partials(partial, nblk, C, 2, ch, a, b)) return;
     if (dbeta) dbeta[ch] = (float)a;
@@ -730,6 +746,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
                                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ k0,
                                     const float* __restrict__ k1, const float* __restrict__ k2, const float* __restrict__ scale,
                                     const float* __restrict__ shift, int relu_mask) {
+    PDL_SYNC();
     const int CH = C / 8, step = 256 / CH;
     const int c = threadIdx.x % CH, r0 = threadIdx.x / CH;
     float mu[8], is[8], a0[8], a1[8], a2[8], sc[8], sh[8];
@@ -766,6 +783,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
 
 // column sums of a [rows][C] bf16 matrix into fp32 (bias gradients): out[c] = sum_r x[r][c]; uses col_stats partials (mode 0, slot 0)
 __global__ void __launch_bounds__(FIN_THREADS) colsum_finalize_kernel(const double* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
+    PDL_SYNC();
     int ch; double a, b;
     if (!block_reduce_partials(partial, nblk, C, 1, ch, a, b)) return;
     out[ch] = (float)a;
@@ -783,6 +801,7 @@ __global__ void __launch_bounds__(FIN_THREADS) colsum_finalize_kernel(const doub
 __global__ void __launch_bounds__(LOSS_BLOCK) loss_map_reduce_kernel(const float* __restrict__ pred, const float* __restrict__ d,
                                                                      const float* __restrict__ v, const float* __restrict__ img,
                                                                      double* __restrict__ partial, int H, int W, float cap, int do_clamp) {
+    PDL_SYNC();
     __shared__ double sh[32];
     const int n = blockIdx.y;
     const long long HW = (long long)H * W;
@@ -816,6 +835,7 @@ __global__ void __launch_bounds__(LOSS_BLOCK) loss_map_reduce_kernel(const float
 // rowstat[r] = {dot, |e|^2, |r|^2}; partial[blk] = sum over its rows of (2 - 2 cos)
 __global__ void __launch_bounds__(256) loss_cos_rows_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ ref, float* __restrict__ rowstat,
                                                             double* __restrict__ partial, long long R, int D) {
+    PDL_SYNC();
     __shared__ double sh[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double local = 0.0;
@@ -852,6 +872,7 @@ struct LossScalars {   // device-resident result block
 __global__ void __launch_bounds__(256) loss_finalize_kernel(const double* __restrict__ map_partial, int map_blocks, const double* __restrict__ cos_partial,
                                      int cos_blocks, int N, int H, int W, long long R, float w_sd, float w_sm, float w_cos,
                                      float cos_gate, LossScalars* out) {
+    PDL_SYNC();
     __shared__ double sh[32];
     __shared__ double s_sd;
     double sx = 0.0, sy = 0.0;
@@ -889,6 +910,7 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const double* __rest
 __global__ void loss_map_grad_kernel(const float* __restrict__ pred, const float* __restrict__ d, const float* __restrict__ v,
                                      const float* __restrict__ img, float* __restrict__ gpred, const LossScalars* __restrict__ ls,
                                      int N, int H, int W, float cap, int do_clamp, float w_sd, float w_sm, float gscale) {
+    PDL_SYNC();
     const long long HW = (long long)H * W;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * HW) return;
@@ -929,6 +951,7 @@ __global__ void loss_map_grad_kernel(const float* __restrict__ pred, const float
 // d loss / d ref = w_eff * (-2/R) * (ehat - cos*rhat) / max(|r|, eps)
 __global__ void __launch_bounds__(256) loss_cos_grad_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ ref, const float* __restrict__ rowstat,
                                                             const LossScalars* __restrict__ ls, bf16* __restrict__ gref, long long R, int D, float gscale) {
+    PDL_SYNC();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float coef = ls->w_cos_eff * (-2.f / (float)R) * gscale;
     for (long long r = (long long)blockIdx.x * 8 + warp; r < R; r += (long long)gridDim.x * 8) {
@@ -972,6 +995,7 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__ chunks, const AdamHyper* __restrict__ hy) {
+    PDL_SYNC();
     const AdamChunk ck = chunks[blockIdx.x];
     const int t = hy->step + 1;
     const double bc1 = 1.0 - pow(hy->beta1_d, (double)t);
@@ -985,13 +1009,15 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
         ck.p[i] = p; ck.m[i] = m; ck.v[i] = v;
     }
 }
-__global__ void adam_advance_kernel(AdamHyper* hy) { hy->step += 1; }
+__global__ void adam_advance_kernel(AdamHyper* hy) {
+    PDL_SYNC(); hy->step += 1; }
 
 // -------------------------------------------------------------------------------------------------
 // weight packing: fp32 parameter -> bf16 [tap][O][I] operand of conv3x3_mma
 //   dst[(tap*O + o)*I + i] = src[o*s_o + i*s_i + tap']   tap' = flip ? 8 - tap : tap
 // -------------------------------------------------------------------------------------------------
 __global__ void pack_conv_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I, int s_o, int s_i, int flip) {
+    PDL_SYNC();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 9 * O * I) return;
     int i = idx % I;
@@ -1002,6 +1028,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ src, bf16* __r
 }
 // generic 2-D cast with optional transpose: dst[r][c] = src[r*s_r + c*s_c]
 __global__ void pack_matrix_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int rows, int cols, int s_r, int s_c) {
+    PDL_SYNC();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * cols) return;
     int c = idx % cols, r = idx / cols;
@@ -1009,6 +1036,7 @@ __global__ void pack_matrix_kernel(const float* __restrict__ src, bf16* __restri
 }
 // head conv weights: dst[tap][c] = src[c*s_c + tap'] (fp32)
 __global__ void pack_head_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int s_c, int flip) {
+    PDL_SYNC();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 288) return;
     int c = idx & 31, tap = idx >> 5;
@@ -1016,6 +1044,7 @@ __global__ void pack_head_weight_kernel(const float* __restrict__ src, float* __
 }
 // stem-shaped fp32 weights for the 1->32 data gradient of prdct.3: dst[c][tap] = src[c*9 + (8 - tap)]
 __global__ void pack_flip9_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+    PDL_SYNC();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * 9) return;
     int tap = idx % 9, c = idx / 9;
@@ -1024,14 +1053,17 @@ __global__ void pack_flip9_kernel(const float* __restrict__ src, float* __restri
 
 // misc
 __global__ void fill_kernel(float* p, float v, long long n) {
+    PDL_SYNC();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
 __global__ void bf16_to_f32_kernel(const bf16* __restrict__ s, float* __restrict__ d, long long n) {
+    PDL_SYNC();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = __bfloat162float(s[i]);
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long n) {
+    PDL_SYNC();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = __float2bfloat16_rn(s[i]);
 }

@@ -117,6 +117,18 @@ def conv3x3_tc(x, wpack, bias=None, relu_in=False, relu_out=False, mask=None, ad
     return out
 
 
+def conv3x3_tc_ex(x, wpack, bias=None, relu_out=False, mask=None, add=None, add2=None, wimage=None):
+    """conv3x3_tc with the second output: returns (out, out2) with out2 = ReLU(bf16(out) [+ add2])"""
+    _need(x, torch.bfloat16, 'x')
+    n, h, w, cin = x.shape
+    if wimage is None:
+        wimage = pack_conv_weight_tc(wpack)
+    out, out2 = torch.empty_like(x), torch.empty_like(x)
+    check(_lib.lib().ptta_conv3x3_tc_ex(ptr(x), ptr(out), ptr(out2), ptr(wimage), ptr(bias), n, h, w, 1 if relu_out else 0, ptr(mask), ptr(add),
+                                        ptr(add2), _stream()), 'conv3x3_tc_ex')
+    return out, out2
+
+
 def conv3x3_tc_s2(x, wpack, bias=None, relu_out=False, mask=None, add=None, want_relu_copy=False):
     """32->32 stride-2 conv on tcgen05 (operand conventions of conv3x3 with MODE_S2, no ReLU-on-load); H, W even.
     Returns out, or (out, relu(out)) with want_relu_copy."""
