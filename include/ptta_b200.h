@@ -61,6 +61,11 @@ int ptta_conv3x3_tc_ex(const void* in_bf16, void* out_bf16, void* out2_bf16, con
 int ptta_pack_conv_weight_tc_s2(const void* wpack_bf16, void* wimage_bf16, ptta_stream_t stream);
 int ptta_conv3x3_tc_s2(const void* in_bf16, void* out_bf16, void* out_relu_bf16, const void* wimage_bf16, const float* bias,
                        int n, int h, int w, int relu_out, const void* mask_bf16, const void* add_bf16, ptta_stream_t stream);
+/* the 32->32 TRANSPOSED stride-2 case (mode 2 of ptta_conv3x3: ConvTranspose2d(32,32,3,2,1,1) forward, Conv2d(s2) data gradient;
+ * network_exp_msg_chn_adapt.py:276-283) on tcgen05.  h, w = INPUT size (w even); out / mask / add are [n, 2h, 2w, 32]. */
+int ptta_pack_conv_weight_tc_t2(const void* wpack_bf16, void* wimage_bf16, ptta_stream_t stream);
+int ptta_conv3x3_tc_t2(const void* in_bf16, void* out_bf16, const void* wimage_bf16, const float* bias, int n, int h, int w,
+                       int relu_out, const void* mask_bf16, const void* add_bf16, ptta_stream_t stream);
 /* timing experiments only: one eager step with a CUDA event after every kernel launch; prints the per-stream timeline */
 int ptta_msgchn_trace_step(ptta_msgchn* engine, const float* image_raw, const float* img_scale3, const float* img_shift3,
                            const float* sparse_depth, float max_input_depth, float w_sd, float w_sm, float w_cos, ptta_stream_t stream);
@@ -73,9 +78,17 @@ int ptta_conv3x3_wgrad(const void* in_bf16, const void* gout_bf16, float* dw, vo
 int ptta_stem_conv(const float* const* planes, const long long* batch_strides, const float* scale, const float* shift,
                    int cin, const float* weight, const float* bias, const void* mask_bf16, void* out_bf16,
                    int n, int h, int w, ptta_stream_t stream);
+/* same operator with the weights ([32][cin][3][3]) and bias given as HOST arrays: they travel by value in the kernel parameters, so the
+ * inner loop is FMAs with constant-bank operands only (what the engine uses for its frozen stems).  w must be even. */
+int ptta_stem_conv_const(const float* const* planes, const long long* batch_strides, const float* scale, const float* shift,
+                         int cin, const float* weight_host, const float* bias_host, const void* mask_bf16, void* out_bf16,
+                         int relu_out, int n, int h, int w, ptta_stream_t stream);
 /* 32 -> 1 conv (prdct.3, :289); weight is [9][32] fp32 */
 int ptta_head_conv(const void* in_bf16, const float* weight_9x32, float bias, const float* add, float* out,
                    int n, int h, int w, int relu_in, int accumulate, ptta_stream_t stream);
+/* same with the [9][32] weight given as a HOST array (by-value kernel parameters, constant-bank FMA operands) */
+int ptta_head_conv_const(const void* in_bf16, const float* weight_host_9x32, float bias, const float* add, float* out,
+                         int n, int h, int w, int relu_in, int accumulate, ptta_stream_t stream);
 /* F.interpolate(scale_factor=2, bilinear, align_corners=True) (:201-209,493,500) and adjoints */
 int ptta_up2_1ch(const float* a, const float* b, const float* c, float* out, int n, int h, int w, ptta_stream_t stream);
 int ptta_up2_1ch_adjoint(const float* g_hi, float* g_lo, int n, int h, int w, int accumulate, ptta_stream_t stream);
@@ -251,7 +264,8 @@ int ptta_input_stage(const void* image_u8_hwc, const void* depth_u16, float* ima
 int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepare_mode);
 void ptta_msgchn_destroy(ptta_msgchn* e);
 /* dispatch options (results stay right for every value; used by the parity tests to run ALL kernel families at every size):
- * "tc_min_pixels" / "tc_s2_min_pixels": smallest map (N*H*W) the stride-1 / stride-2 tcgen05 convs take (0 = always),
+ * "tc_min_pixels" / "tc_s2_min_pixels" / "tc_t2_min_pixels": smallest map (N*H*W of the INPUT) the stride-1 / stride-2 /
+ * transposed tcgen05 convs take (0 = always),
  * "tc_enabled" 0/1, "two_streams" 0/1, "fuse_dec_sums" 0/1.  Unknown names fail. */
 int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value);
 size_t ptta_msgchn_workspace_bytes(const ptta_msgchn* e);

@@ -197,6 +197,8 @@ def test_stem_and_head_conv(ops):
         planes = [x[:, c].contiguous().to(DEV) for c in range(cin)]
         got = ops.stem_conv(planes, wt.to(DEV), b.to(DEV))
         assert_close_bf16(nchw(got), want, 'stem cin=%d' % cin, ulps=2.0)
+        if w % 2 == 0:        # the engine's form: weights by value (constant bank); same FMA order -> bit-identical
+            assert torch.equal(ops.stem_conv_const(planes, wt, b), got), 'stem_conv_const cin=%d' % cin
     x = bf(torch.randn((n, 32, h, w), generator=g))
     wt = torch.randn((1, 32, 3, 3), generator=g) * 0.1
     add = torch.randn((n, h, w), generator=g)
@@ -204,6 +206,11 @@ def test_stem_and_head_conv(ops):
     w9 = wt[0].reshape(32, 9).t().contiguous()               # [tap][c]
     got = ops.head_conv(nhwc(x), w9.to(DEV), 0.25, add.to(DEV), relu_in=True)
     assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=1e-4)
+    got = ops.head_conv_const(nhwc(x), w9, 0.25, add.to(DEV), relu_in=True)
+    assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=1e-4), 'head_conv_const'
+    acc = add.to(DEV).clone()
+    ops.head_conv_const(nhwc(x), w9, 0.25, None, relu_in=True, out=acc, accumulate=True)
+    assert torch.allclose(acc.cpu(), want, rtol=1e-4, atol=1e-4), 'head_conv_const accumulate'
 
 
 @pytest.mark.parametrize('n,h,w', [(1, 8, 12), (2, 11, 19), (1, 88, 304)])
@@ -324,6 +331,43 @@ def test_conv_tcgen05_stride2_matches_mma(ops, n, h, w):
     assert int((err > ref.abs() * 2.0 ** -8 + 2e-3 * float(ref.pow(2).mean().sqrt())).sum()) == 0, 'conv_tc_s2 vs fp32 conv'
     with pytest.raises(RuntimeError):
         ops.conv3x3_tc_s2(x[:, :h - 1].contiguous(), wp, bias)       # odd height: must fail loudly
+
+
+@pytest.mark.parametrize('n,h,w', [(1, 8, 128), (1, 16, 24), (2, 9, 38), (1, 3, 6), (1, 44, 152), (3, 33, 258), (1, 88, 304), (1, 176, 608)])
+def test_conv_tcgen05_transposed_matches_mma_and_torch(ops, n, h, w):
+    """the transposed stride-2 tcgen05 conv (ConvTranspose2d(s2) forward / Conv2d(s2) data gradient): equal to the mma.sync kernel up to
+    the summation order of the 4-tap output class (a fraction < 1e-3 of the elements may differ by one bf16 ulp; measured 2e-4), and
+    within bf16 rounding of an fp32 conv_transpose2d of the same bf16 operands"""
+    def same(a, b, what):
+        d = (a.float() - b.float()).abs()
+        assert float((d > 0).float().mean()) < 1e-3 and bool((d <= b.float().abs() * 2.0 ** -7 + 1e-6).all()), what
+    g = torch.Generator().manual_seed(14)
+    wt = (torch.randn((32, 32, 3, 3), generator=g) * (2.0 / 288) ** 0.5).to(DEV)          # ConvTranspose2d weight [Cin, Cout, 3, 3]
+    wp = ops.pack_conv_weight(wt, 'convT_fwd')
+    bias = (torch.randn(32, generator=g) * 0.1).to(DEV)
+    x = torch.randn((n, h, w, 32), generator=g).to(DEV).to(torch.bfloat16)
+    m = torch.randn((n, 2 * h, 2 * w, 32), generator=g).to(DEV).to(torch.bfloat16)
+    a = torch.randn((n, 2 * h, 2 * w, 32), generator=g).to(DEV).to(torch.bfloat16)
+    want = ops.conv3x3(x, wp, bias, ops.MODE_T2, ops.PRO_RELU)
+    got = ops.conv3x3_tc_t2(torch.relu(x), wp, bias)
+    same(got, want, 'conv_tc_t2 forward vs mma.sync')
+    assert torch.equal(ops.conv3x3_tc_t2(torch.relu(x), wp, bias, relu_out=True), torch.relu(got)), 'conv_tc_t2 relu_out'
+    want2 = ops.conv3x3(x, wp, None, ops.MODE_T2, ops.PRO_NONE, mask=m, mask_mode=ops.MASK_RELU, add=a)
+    same(ops.conv3x3_tc_t2(x, wp, None, mask=m, add=a), want2, 'conv_tc_t2 mask+add vs mma.sync')
+    acc = a.clone()                                    # in-place accumulate (out aliases add), as the backward pass uses it
+    from tta_depth_completion_b200 import _lib
+    wi = torch.empty((9 * 32 * 32,), dtype=torch.bfloat16, device=DEV)
+    _lib.check(_lib.lib().ptta_pack_conv_weight_tc_t2(_lib.ptr(wp), _lib.ptr(wi), torch.cuda.current_stream().cuda_stream), 'pack')
+    _lib.check(_lib.lib().ptta_conv3x3_tc_t2(_lib.ptr(x), _lib.ptr(acc), _lib.ptr(wi), None, n, h, w, 0, _lib.ptr(m), _lib.ptr(acc),
+                                             torch.cuda.current_stream().cuda_stream), 'conv3x3_tc_t2 in place')
+    same(acc, want2, 'conv_tc_t2 in-place accumulate')
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv_transpose2d(torch.relu(x).float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias, stride=2, padding=1,
+                             output_padding=1).permute(0, 2, 3, 1)
+    err = (got.float() - ref).abs()
+    assert int((err > ref.abs() * 2.0 ** -8 + 2e-3 * float(ref.pow(2).mean().sqrt())).sum()) == 0, 'conv_tc_t2 vs fp32 conv_transpose2d'
+    with pytest.raises(RuntimeError):
+        ops.conv3x3_tc_t2(x[:, :, :w - 1].contiguous(), wp, bias)       # odd width: must fail loudly
 
 
 def test_adam_matches_torch(ops):

@@ -51,3 +51,16 @@ for shape in [(1, 352, 1216), (4, 352, 1216), (1, 176, 608), (1, 88, 304)]:
     res.append('mma mask+add %.1f' % timeit(lambda x: ops.conv3x3(x, wp, bias, ops.MODE_S1, ops.PRO_NONE, mask=mk, mask_mode=ops.MASK_RELU, add=mk), xs))
     gb = 2 * n * h * w * 64 / 1e3
     print(shape, ' | '.join(res), '| tc %.0f GB/s' % (gb / float(res[0].split()[1])), flush=True)
+
+# transposed stride-2: tcgen05 vs mma.sync (input sizes; output is 2x)
+wtT = (torch.randn((32, 32, 3, 3), generator=g) * (2.0 / 288) ** 0.5).to(dev)
+wpT = ops.pack_conv_weight(wtT, 'convT_fwd')
+for shape in [(1, 176, 608), (1, 88, 304), (1, 44, 152)]:
+    n, h, w = shape
+    xs = [torch.randn((n, h, w, 32), device=dev).to(torch.bfloat16) for _ in range(8)]
+    mk = torch.randn((n, 2 * h, 2 * w, 32), device=dev).to(torch.bfloat16)
+    res = ['t2 tc %.1f' % timeit(lambda x: ops.conv3x3_tc_t2(x, wpT, bias), xs),
+           't2 tc mask+add %.1f' % timeit(lambda x: ops.conv3x3_tc_t2(x, wpT, None, mask=mk, add=mk), xs),
+           't2 mma %.1f' % timeit(lambda x: ops.conv3x3(x, wpT, bias, ops.MODE_T2, ops.PRO_RELU), xs),
+           't2 mma mask+add %.1f' % timeit(lambda x: ops.conv3x3(x, wpT, None, ops.MODE_T2, ops.PRO_NONE, mask=mk, mask_mode=ops.MASK_RELU, add=mk), xs)]
+    print(shape, ' | '.join(res), flush=True)

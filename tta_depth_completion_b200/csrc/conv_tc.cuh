@@ -166,6 +166,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// L2 prefetch of a contiguous global range (bytes: multiple of 16): issued by the producer several rows ahead of the epilogue warps that
+// read the data with plain loads (mask / add rows), so those loads find the lines in L2 instead of paying the DRAM latency per row
+__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -238,6 +243,13 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
                 if (elect_one()) {
                     tc::mbar_arrive_expect_tx(row_full + 8 * slot, C::ROW_BYTES);
                     tc::tma_load_4d(rows_s + slot * C::SLOT_BYTES, &tmap_in, row_full + 8 * slot, 0, sx * 128 - 1, yy, n);
+                    if (yy >= y0 && yy < y1 && (p.mask || p.add || p.add2)) {       // the epilogue reads these rows ~3 input rows from now
+                        const size_t roff = (((size_t)n * p.H + yy) * p.W + sx * 256) * 32;
+                        const uint32_t rbytes = (uint32_t)min(256, p.W - sx * 256) * 64u;
+                        if (p.mask) tc::l2_prefetch(p.mask + roff, rbytes);
+                        if (p.add) tc::l2_prefetch(p.add + roff, rbytes);
+                        if (p.add2) tc::l2_prefetch(p.add2 + roff, rbytes);
+                    }
                 }
                 __syncwarp();
             }

@@ -20,6 +20,7 @@
 #include "small_kernels.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc_s2.cuh"
+#include "conv_tc_t2.cuh"
 #include "gemm_tc.cuh"
 #include "nlspn_prop.cuh"
 #include "../../include/ptta_b200.h"
@@ -92,6 +93,10 @@ struct StemLayer {   // init.0: {1,2,3} -> 32
     std::string name; int cin = 1;
     const float* w = nullptr; const float* b = nullptr;
     float* dgrad_ch1 = nullptr;   // [9][32] flipped weights of input plane 1 (cascade encoders)
+    std::vector<float> raw_host;  // host copy of w taken at pack time ...
+    float wk[3 * 9 * 32];         // ... re-ordered [ci][tap][co]: passed by value to stem_convc_kernel (constant-bank operands)
+    float bk[32];
+    float dk[9 * 32];             // host copy of dgrad_ch1 ([9][32]) for head_convc_kernel
 };
 struct HeadLayer {   // prdct.3: 32 -> 1
     std::string name;
@@ -99,6 +104,9 @@ struct HeadLayer {   // prdct.3: 32 -> 1
     float* w_fwd = nullptr;       // [9][32]
     float* w_dgrad = nullptr;     // [32][1][3][3] flipped, stem-shaped
     float bias_host = 0.f;
+    std::vector<float> raw_host;  // host copy of w_dgrad ([32][1][3][3], flipped) ...
+    float wdk[9 * 32];            // ... re-ordered [tap][co] for stem_convc_kernel<1>
+    float wfk[9 * 32];            // host copy of w_fwd ([9][32]) for head_convc_kernel
 };
 struct BnState {     // per call-site statistics
     float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *uvar = nullptr;
@@ -118,7 +126,7 @@ struct EncW { StemLayer init0; ConvLayer init2, e1a, e1b, e2a, e2b, e3a, e3b, e4
 struct DecW { ConvLayer d2a, d2b, d1a, d1b, p1; HeadLayer p3; };
 
 struct EncAct { Map32 a0, x0, t1, x1, t2, x2; Map32 x0r, x1r; };   // x0r / x1r = ReLU(x0) / ReLU(x1): inputs of the stride-2 convs
-struct DecAct { Map32 x2, x1, x0, u2, x3, s1, u1, x4, s0, h; Map1 out; };
+struct DecAct { Map32 x2, x1, x0, u2, x3, s1, u1, x4, s0, h; Map32 x2r; Map1 out; };   // x2r = ReLU(x2): input of the transposed conv dec2.1
 struct Branch {
     Map32 c[5];            // rgb features (c[2] after the meta layer)
     Map32 cr[4];           // ReLU of the rgb encoder's own x0..x3 (inputs of its stride-2 convs)
@@ -145,9 +153,13 @@ struct ptta_msgchn {
     std::string prepare_mode;
     cudaStream_t st = nullptr;      // stream of the call in flight (helpers launch on `st`)
     cudaStream_t st2 = nullptr;     // side stream: the zero-image branch runs concurrently with the real branch
+    cudaStream_t st3 = nullptr;     // second side stream: proxy head of the real rows (forward + backward) and the meta layer's second
+                                    // weight gradient run beside decoder 3 / the data-gradient chain
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_projbn = nullptr, ev_enc1 = nullptr, ev_zmeta = nullptr;
+    cudaEvent_t ev_e3 = nullptr, ev_mlp = nullptr, ev_lossg = nullptr, ev_headb = nullptr, ev_gmg = nullptr, ev_wg2 = nullptr;
     bool two_streams = true;
-    bool tc_enabled = true; long long tc_min_pixels = 20000, tc_s2_min_pixels = 16000;
+    bool mlp_on_st3 = false;        // set by forward_impl for the duration of the real cascade
+    bool tc_enabled = true; long long tc_min_pixels = 20000, tc_s2_min_pixels = 16000, tc_t2_min_pixels = 6000;
     bool fuse_dec_sums = true;      // experiment switches (environment: PTTA_NO_TC, PTTA_NO_FUSE_DEC_SUMS, PTTA_ONE_STREAM)
     Arena arena;
     size_t ws_bytes = 0;
@@ -181,11 +193,12 @@ struct ptta_msgchn {
     BnState bnProjZ, bnProjR, bnPred;
     float* rowstat = nullptr;
     // backward scratch
-    Map32 T1a, T1b, T2a, T2b, D2, G4a, G4b, D4, GC2, D8, E8, M128a, M128b;
+    Map32 T1a, T1b, T2a, T2b, D2, G4a, G4b, D4, GC2, GZ, D8, E8, M128a, M128b;
     Map1 g_out, g_p11, g_q, g_p12, g_o14;
     float *k0 = nullptr, *k1 = nullptr, *k2 = nullptr;
     double* partial = nullptr; size_t partial_doubles = 0;
-    float* wgrad_ws = nullptr;
+    float* wgrad_ws = nullptr; float* wgrad_ws2 = nullptr;
+    double* partial3 = nullptr;
     LossScalars* losses = nullptr;
     double *loss_map_partial = nullptr, *loss_cos_partial = nullptr;
     int loss_map_blocks = 0, loss_cos_blocks = 0;
@@ -289,8 +302,8 @@ struct ptta_msgchn {
         L.pack_fwd = allocv<bf16>((size_t)9 * L.cin * L.cout);
         L.pack_dgrad = allocv<bf16>((size_t)9 * L.cin * L.cout);
         if (L.cin == 32 && L.cout == 32) {
-            L.img_fwd = L.mode_fwd != MODE_T2 ? allocv<bf16>(9 * 32 * 32) : nullptr;
-            L.img_dgrad = L.mode_dgrad != MODE_T2 ? allocv<bf16>(9 * 32 * 32) : nullptr;
+            L.img_fwd = allocv<bf16>(9 * 32 * 32);
+            L.img_dgrad = allocv<bf16>(9 * 32 * 32);
         }
     }
     void plan_enc_w(EncW& E) {
@@ -312,6 +325,7 @@ struct ptta_msgchn {
     void plan_dec_act(DecAct& A, const std::string& tag, int h, int w) {   // h,w = resolution of x0 / out
         A.x2 = alloc32((tag + ".x2").c_str(), h / 4, w / 4); A.x1 = alloc32((tag + ".x1").c_str(), h / 2, w / 2);
         A.x0 = alloc32((tag + ".x0").c_str(), h, w);
+        A.x2r = alloc32(nullptr, h / 4, w / 4);
         A.u2 = alloc32((tag + ".u2").c_str(), h / 2, w / 2); A.x3 = alloc32((tag + ".x3").c_str(), h / 2, w / 2);
         A.s1 = alloc32((tag + ".s1").c_str(), h / 2, w / 2);
         A.u1 = alloc32((tag + ".u1").c_str(), h, w); A.x4 = alloc32((tag + ".x4").c_str(), h, w);
@@ -398,7 +412,7 @@ struct ptta_msgchn {
         T1a = alloc32("T1a", H, W); T1b = alloc32("T1b", H, W);
         T2a = alloc32("T2a", H / 2, W / 2); T2b = alloc32("T2b", H / 2, W / 2); D2 = alloc32("D2", H / 2, W / 2);
         G4a = alloc32("G4a", H / 4, W / 4); G4b = alloc32("G4b", H / 4, W / 4); D4 = alloc32("D4", H / 4, W / 4);
-        GC2 = alloc32("g_c2", H / 4, W / 4);
+        GC2 = alloc32("g_c2", H / 4, W / 4); GZ = alloc32("g_z", H / 4, W / 4);
         D8 = alloc32("D8", H / 8, W / 8); E8 = alloc32("E8", H / 8, W / 8);
         if (two_layers) { M128a = alloc32("M128a", H / 4, W / 4, 128); M128b = alloc32("M128b", H / 4, W / 4, 128); }
         g_out = alloc1(padded ? "g_output_padded" : "g_output", H, W); g_p11 = alloc1("g_p11", H, W);
@@ -411,6 +425,8 @@ struct ptta_msgchn {
         partial2 = allocv<double>(partial_doubles);
         size_t wg = std::max(wgrad_partial_bytes(N, H / 4, W / 4, 32, 128), wgrad_partial_bytes(N, H / 4, W / 4, 128, 32));
         wgrad_ws = (float*)arena.take(wg);
+        wgrad_ws2 = (float*)arena.take(wg);
+        partial3 = allocv<double>(partial_doubles);
         losses = (LossScalars*)arena.take(sizeof(LossScalars));
         reg("losses", losses, 0, 5, 1, 1, 1);
         loss_map_blocks = std::min(cdiv((long long)H * W, LOSS_BLOCK * 4), 256);
@@ -495,12 +511,14 @@ struct ptta_msgchn {
         }
         if (L.img_fwd) {
             if (L.mode_fwd == MODE_S1) launch_k(pack_conv_weight_tc_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_fwd, L.img_fwd);
-            else launch_k(pack_conv_weight_tc_s2_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_fwd, L.img_fwd);
+            else if (L.mode_fwd == MODE_S2) launch_k(pack_conv_weight_tc_s2_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_fwd, L.img_fwd);
+            else launch_k(pack_conv_weight_tc_t2_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_fwd, L.img_fwd);
             PTTA_TRY(check_launch("pack_fwd_tc"));
         }
         if (L.img_dgrad) {
             if (L.mode_dgrad == MODE_S1) launch_k(pack_conv_weight_tc_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_dgrad, L.img_dgrad);
-            else launch_k(pack_conv_weight_tc_s2_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_dgrad, L.img_dgrad);
+            else if (L.mode_dgrad == MODE_S2) launch_k(pack_conv_weight_tc_s2_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_dgrad, L.img_dgrad);
+            else launch_k(pack_conv_weight_tc_t2_kernel, cdiv(9 * 32 * 4, 256), 256, 0, st, L.pack_dgrad, L.img_dgrad);
             PTTA_TRY(check_launch("pack_dgrad_tc"));
         }
         return 0;
@@ -513,7 +531,22 @@ struct ptta_msgchn {
         PTTA_TRY(pack_conv(E.init2));
         ConvLayer* ls[8] = {&E.e1a, &E.e1b, &E.e2a, &E.e2b, &E.e3a, &E.e3b, &E.e4a, &E.e4b};
         for (int k = 0; k < 2 * E.nenc; ++k) PTTA_TRY(pack_conv(*ls[k]));
+        if (E.init0.cin == 2) PTTA_CUDA(cudaMemcpyAsync(E.init0.dk, E.init0.dgrad_ch1, sizeof(E.init0.dk), cudaMemcpyDeviceToHost, st));
+        E.init0.raw_host.resize(32 * E.init0.cin * 9 + 32);
+        PTTA_CUDA(cudaMemcpyAsync(E.init0.raw_host.data(), E.init0.w, sizeof(float) * 32 * E.init0.cin * 9, cudaMemcpyDeviceToHost, st));
+        PTTA_CUDA(cudaMemcpyAsync(E.init0.raw_host.data() + 32 * E.init0.cin * 9, E.init0.b, sizeof(float) * 32, cudaMemcpyDeviceToHost, st));
         return 0;
+    }
+    // after the stream has been synchronised: [co][ci][tap] -> [ci][tap][co]
+    void finish_host_weights(EncW& E) {
+        StemLayer& S = E.init0;
+        for (int co = 0; co < 32; ++co)
+            for (int r = 0; r < S.cin * 9; ++r) S.wk[r * 32 + co] = S.raw_host[(size_t)co * S.cin * 9 + r];
+        for (int c = 0; c < 32; ++c) S.bk[c] = S.raw_host[32 * S.cin * 9 + c];
+    }
+    void finish_host_weights(DecW& D) {
+        for (int co = 0; co < 32; ++co)
+            for (int t = 0; t < 9; ++t) D.p3.wdk[t * 32 + co] = D.p3.raw_host[co * 9 + t];
     }
     int pack_dec(DecW& D) {
         PTTA_TRY(pack_conv(D.d2a)); PTTA_TRY(pack_conv(D.d2b)); PTTA_TRY(pack_conv(D.d1a)); PTTA_TRY(pack_conv(D.d1b));
@@ -523,6 +556,9 @@ struct ptta_msgchn {
         launch_k(pack_flip9_kernel, 2, 256, 0, st, D.p3.w, D.p3.w_dgrad, 32);
         PTTA_TRY(check_launch("pack_head_dgrad"));
         PTTA_CUDA(cudaMemcpyAsync(&D.p3.bias_host, D.p3.b, sizeof(float), cudaMemcpyDeviceToHost, st));
+        PTTA_CUDA(cudaMemcpyAsync(D.p3.wfk, D.p3.w_fwd, sizeof(D.p3.wfk), cudaMemcpyDeviceToHost, st));
+        D.p3.raw_host.resize(288);
+        PTTA_CUDA(cudaMemcpyAsync(D.p3.raw_host.data(), D.p3.w_dgrad, sizeof(float) * 288, cudaMemcpyDeviceToHost, st));
         return 0;
     }
     int pack_linear(LinearLayer& L) {
@@ -547,7 +583,9 @@ struct ptta_msgchn {
         if (has_heads) {
             PTTA_TRY(pack_linear(proj0)); PTTA_TRY(pack_linear(proj3)); PTTA_TRY(pack_linear(pred0)); PTTA_TRY(pack_linear(pred3));
         }
-        PTTA_CUDA(cudaStreamSynchronize(st));   // bias_host copies
+        PTTA_CUDA(cudaStreamSynchronize(st));   // bias_host / host weight copies
+        finish_host_weights(rgbW); finish_host_weights(enc1W); finish_host_weights(enc2W); finish_host_weights(enc3W);
+        finish_host_weights(dec1W); finish_host_weights(dec2W); finish_host_weights(dec3W);
         // Adam chunk table over the adapted tensors
         std::vector<AdamChunk> chunks;
         for (const std::string& k : adapt_names) {
@@ -589,6 +627,14 @@ struct ptta_msgchn {
     bool use_tc_s2(const Map32& m) const {
         return tc_enabled && conv_tc_s2_supported(m.n, m.h, m.w) && (long long)m.n * m.h * m.w >= tc_s2_min_pixels;
     }
+    bool use_tc_t2(const Map32& m) const {       // m: the INPUT map of the transposed conv
+        return tc_enabled && conv_tc_t2_supported(m.n, m.h, m.w) && (long long)m.n * m.h * m.w >= tc_t2_min_pixels;
+    }
+    int conv_tc_t2(const bf16* image, const float* bias, const Map32& in, const Map32& out, int relu_out, const bf16* mask, const bf16* add) {
+        ConvTcParams p; memset(&p, 0, sizeof(p));
+        p.w = image; p.bias = bias; p.out = out.p; p.mask = mask; p.add = add; p.N = in.n; p.H = in.h; p.W = in.w; p.relu_out = relu_out;
+        return launch_conv_tc_t2(in.p, p, st);
+    }
     int conv_tc(const bf16* image, const float* bias, const Map32& in, const Map32& out, int relu_out, const bf16* mask, const bf16* add,
                 bf16* out2 = nullptr, bool stride2 = false, const bf16* add2 = nullptr) {
         ConvTcParams p; memset(&p, 0, sizeof(p));
@@ -606,6 +652,8 @@ struct ptta_msgchn {
                 return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr, out2, false, add2);
             if (L.mode_fwd == MODE_S2 && use_tc_s2(in) && !add2)
                 return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr, out2, true);
+            if (L.mode_fwd == MODE_T2 && use_tc_t2(in) && !add2 && !out2)
+                return conv_tc_t2(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr);
         }
         ConvParams p; memset(&p, 0, sizeof(p));
         p.relu_out = relu_out; p.out2 = out2; p.add2 = add2;
@@ -620,6 +668,7 @@ struct ptta_msgchn {
         if (L.img_dgrad && (!mask || mask_mode == MASK_RELU)) {
             if (L.mode_dgrad == MODE_S1 && use_tc(gout)) return conv_tc(L.img_dgrad, nullptr, gout, gin, 0, mask, add);
             if (L.mode_dgrad == MODE_S2 && use_tc_s2(gout)) return conv_tc(L.img_dgrad, nullptr, gout, gin, 0, mask, add, nullptr, true);
+            if (L.mode_dgrad == MODE_T2 && use_tc_t2(gout)) return conv_tc_t2(L.img_dgrad, nullptr, gout, gin, 0, mask, add);
         }
         ConvParams p; memset(&p, 0, sizeof(p));
         p.in = gout.p; p.out = gin.p; p.w = L.pack_dgrad; p.bias = nullptr;
@@ -655,37 +704,57 @@ struct ptta_msgchn {
     }
     int stem(const StemLayer& S, const float* p0, long long s0, float sc0, float sh0, const float* p1, long long s1, float sc1,
              float sh1, const float* p2, long long s2, float sc2, float sh2, const Map32& out) {
+        if ((out.w & 1) == 0) {         // weights by value (constant bank): the FMA-only kernel
+            StemCParams c; memset(&c, 0, sizeof(c));
+            c.relu_out = 1;
+            c.plane[0] = p0; c.plane[1] = p1; c.plane[2] = p2;
+            c.batch_stride[0] = s0; c.batch_stride[1] = s1; c.batch_stride[2] = s2;
+            c.scale[0] = sc0; c.scale[1] = sc1; c.scale[2] = sc2; c.shift[0] = sh0; c.shift[1] = sh1; c.shift[2] = sh2;
+            c.out = out.p; c.N = out.n; c.H = out.h; c.W = out.w;
+            memcpy(c.w, S.wk, sizeof(float) * S.cin * 9 * 32); memcpy(c.bias, S.bk, sizeof(c.bias));
+            launch_stem_const(c, S.cin, st);
+            return check_launch("stem_conv");
+        }
         StemParams p; memset(&p, 0, sizeof(p));
         p.relu_out = 1;                 // init.0 outputs are consumed through ReLU only (and as ReLU masks in backward)
         p.plane[0] = p0; p.plane[1] = p1; p.plane[2] = p2;
         p.batch_stride[0] = s0; p.batch_stride[1] = s1; p.batch_stride[2] = s2;
         p.scale[0] = sc0; p.scale[1] = sc1; p.scale[2] = sc2; p.shift[0] = sh0; p.shift[1] = sh1; p.shift[2] = sh2;
         p.w = S.w; p.bias = S.b; p.mask = nullptr; p.out = out.p; p.N = out.n; p.H = out.h; p.W = out.w;
-        long long tot = (long long)out.n * out.h * out.w;
-        if (S.cin == 1) launch_k(stem_conv_kernel<1>, cdiv(tot, 128), 128, 0, st, p);
-        else if (S.cin == 2) launch_k(stem_conv_kernel<2>, cdiv(tot, 128), 128, 0, st, p);
-        else launch_k(stem_conv_kernel<3>, cdiv(tot, 128), 128, 0, st, p);
+        launch_stem(p, S.cin, st);
         return check_launch("stem_conv");
     }
     // prediction layer: out = conv32->1(relu(h)) + bias [+ add]
+    int head_convv(const bf16* in, const float* wk, float bias, const float* add, const Map1& out, int relu_in) {
+        HeadCParams c; memset(&c, 0, sizeof(c));
+        c.in = in; c.add = add; c.out = out.p; c.N = out.n; c.H = out.h; c.W = out.w; c.relu_in = relu_in; c.bias = bias;
+        memcpy(c.w, wk, sizeof(c.w));
+        launch_k(head_convc_kernel, dim3(cdiv(out.w, HEADC_TW), cdiv(out.h, HEADC_TH), out.n), dim3(HEADC_TW, HEADC_TH), 0, st, c);
+        return 0;
+    }
     int head_fwd(const HeadLayer& Hd, const Map32& h, const float* add, const Map1& out) {
-        long long tot = (long long)out.numel();
-        launch_k(head_conv_kernel, dim3(cdiv(out.w, HEADC_TW), cdiv(out.h, HEADC_TH), out.n), dim3(HEADC_TW, HEADC_TH), 0, st, h.p, Hd.w_fwd, Hd.bias_host, add, out.p, out.n, out.h, out.w, 1, 0);
+        PTTA_TRY(head_convv(h.p, Hd.wfk, Hd.bias_host, add, out, 1));
         return check_launch("head_conv");
     }
     // g_h = dgrad_{1->32}(g_out) * [h > 0]
     int head_dgrad(const HeadLayer& Hd, const Map1& gout, const Map32& hmask, const Map32& gh) {
+        if ((gh.w & 1) == 0) {
+            StemCParams c; memset(&c, 0, sizeof(c));
+            c.plane[0] = gout.p; c.batch_stride[0] = (long long)gout.h * gout.w; c.scale[0] = 1.f;
+            c.mask = hmask.p; c.out = gh.p; c.N = gh.n; c.H = gh.h; c.W = gh.w;
+            memcpy(c.w, Hd.wdk, sizeof(Hd.wdk));
+            launch_stem_const(c, 1, st);
+            return check_launch("head_dgrad");
+        }
         StemParams p; memset(&p, 0, sizeof(p));
         p.plane[0] = gout.p; p.batch_stride[0] = (long long)gout.h * gout.w; p.scale[0] = 1.f;
         p.w = Hd.w_dgrad; p.bias = nullptr; p.mask = hmask.p; p.out = gh.p; p.N = gh.n; p.H = gh.h; p.W = gh.w; p.relu_out = 0;
-        long long tot = (long long)gh.n * gh.h * gh.w;
-        launch_k(stem_conv_kernel<1>, cdiv(tot, 128), 128, 0, st, p);
+        launch_stem(p, 1, st);
         return check_launch("head_dgrad");
     }
     // gradient wrt input plane 1 of a 2-plane stem: out = conv32->1(g_a0; flipped plane-1 weights) + add
     int stem_dgrad_ch1(const StemLayer& S, const Map32& ga0, const float* add, const Map1& out) {
-        long long tot = (long long)out.numel();
-        launch_k(head_conv_kernel, dim3(cdiv(out.w, HEADC_TW), cdiv(out.h, HEADC_TH), out.n), dim3(HEADC_TW, HEADC_TH), 0, st, ga0.p, S.dgrad_ch1, 0.f, add, out.p, out.n, out.h, out.w, 0, 0);
+        PTTA_TRY(head_convv(ga0.p, S.dk, 0.f, add, out, 0));
         return check_launch("stem_dgrad");
     }
     int stats(const bf16* x, const bf16* dy, long long rows, int C, int mode, const BnState* s, int relu_mask, int& nblk) {
@@ -780,11 +849,17 @@ struct ptta_msgchn {
     // cx0/cx1/cx2: rgb features at the resolutions of x0/x1/x2; out = prediction [+ add]
     int run_decoder(const DecW& Wt, DecAct& A, const EncAct& E, const Map32& cx0, const Map32& cx1, const Map32& cx2,
                     const float* add, const Map1& out) {
-        PTTA_TRY(add32(E.x2, cx2, A.x2));
-        PTTA_TRY(add32(E.x1, cx1, A.x1));
-        PTTA_TRY(add32(E.x0, cx0, A.x0));
-        // u2, s1, u1, s0, h hold ReLU(.): each is read through a ReLU only (forward) or as a ReLU mask (backward)
-        PTTA_TRY(conv_fwd(Wt.d2a, A.x2, A.u2, PRO_RELU, nullptr, 1));
+        {   // x2 = dx2 + cx2 (and ReLU(x2)), x1 = dx1 + cx1, x0 = dx0 + cx0 in one launch
+            DecSumsParams dp;
+            dp.a[0] = E.x2.p; dp.b[0] = cx2.p; dp.out[0] = A.x2.p; dp.n8[0] = (long long)A.x2.numel() / 8;
+            dp.a[1] = E.x1.p; dp.b[1] = cx1.p; dp.out[1] = A.x1.p; dp.n8[1] = (long long)A.x1.numel() / 8;
+            dp.a[2] = E.x0.p; dp.b[2] = cx0.p; dp.out[2] = A.x0.p; dp.n8[2] = (long long)A.x0.numel() / 8;
+            dp.out0_relu = A.x2r.p;
+            launch_k(dec_sums_kernel, cdiv(dp.n8[0] + dp.n8[1] + dp.n8[2], 256), 256, 0, st, dp);
+            PTTA_TRY(check_launch("dec_sums"));
+        }
+        // x2r, u2, s1, u1, s0, h hold ReLU(.): each is read through a ReLU only (forward) or as a ReLU mask (backward)
+        PTTA_TRY(conv_fwd(Wt.d2a, A.x2r, A.u2, PRO_NONE, nullptr, 1));
         if (fuse_dec_sums) {
             PTTA_TRY(conv_fwd(Wt.d2b, A.u2, A.x3, PRO_NONE, nullptr, 0, A.s1.p, A.x1.p));      // x3, and s1 = ReLU(x1 + x3) from the same epilogue
             PTTA_TRY(conv_fwd(Wt.d1a, A.s1, A.u1, PRO_NONE, nullptr, 1));
@@ -808,6 +883,17 @@ struct ptta_msgchn {
         PTTA_TRY(up2_1(B.d2.out, B.p12.p, nullptr, B.p11));                        // p11 = up2(out12 + p12)
         PTTA_TRY(run_encoder(enc3W, B.e3, dcl.p, B.p11.p, &B.d2.x4, &B.d2.x3, &B.d2.x2));
         if (!is_real) return 0;                                                    // zero branch stops after encoder 3
+        if (mlp_on_st3) {
+            // ref = proj(z_real) needs e3.x2 only: it runs on the second side stream while decoder 3 runs here
+            PTTA_CUDA(cudaEventRecord(ev_e3, st));
+            PTTA_CUDA(cudaStreamWaitEvent(st3, ev_e3, 0));
+            cudaStream_t main = st; double* main_partial = partial;
+            st = st3; partial = partial3;
+            int rc3 = mlp(proj0, projBn, bnProjR, proj3, real.e3.x2.p, 32, h_a0r, ref, true, h_an, nullptr, ev_projbn);
+            if (!rc3 && cudaEventRecord(ev_mlp, st3) != cudaSuccess) { set_error("cudaEventRecord failed"); rc3 = 2; }
+            st = main; partial = main_partial;
+            if (rc3) return rc3;
+        }
         return run_decoder(dec3W, B.d3, B.e3, B.c[0], B.c[1], B.c[2], B.p11.p, B.output);   // output = out11 + p11
     }
     int mlp(const LinearLayer& L0, const BnLayer& bn, const BnState& s, const LinearLayer& L3, const bf16* x, int in_dim, bf16* a0, bf16* out,
@@ -884,8 +970,11 @@ struct ptta_msgchn {
             PTTA_TRY(bn_running_update(metaBn2, zero.bn2));
         }
         PTTA_CUDA(cudaStreamWaitEvent(st, ev_enc1, 0));
-        PTTA_TRY(run_cascade(real, true, true));
-        PTTA_TRY(mlp(proj0, projBn, bnProjR, proj3, real.e3.x2.p, 32, h_a0r, ref, true, h_an, nullptr, ev_projbn));
+        mlp_on_st3 = true;
+        int rcc = run_cascade(real, true, true);
+        mlp_on_st3 = false;
+        PTTA_TRY(rcc);
+        PTTA_CUDA(cudaStreamWaitEvent(st, ev_mlp, 0));
         PTTA_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
         return 0;
     }
@@ -949,10 +1038,23 @@ struct ptta_msgchn {
             launch_k(pad_pair_kernel, cdiv(tot, 256), 256, 0, st, g_out_u.p, g_out.p, Nu, 1, Hu, Wu, H, W, 0.5f, 0.f, 0.f, 0.f);
             PTTA_TRY(check_launch("pad_pair(g_output)"));
         }
-        // proxy head on the real rows: ref = L3(relu(bn(L0(z))))
-        PTTA_TRY(gemm(g_ref, proj3.pack_t, g_a3, nullptr, R, 512, 512));
-        PTTA_TRY(bn_backward(projBn, bnProjR, g_a3, h_a0r, g_a0, R, 1, nullptr, nullptr));
-        PTTA_TRY(gemm(g_a0, proj0.pack_t, G4a.p, nullptr, R, 32, 512));     // g_z -> G4a  (grad wrt e3.x2 from the heads)
+        // proxy head on the real rows: ref = L3(relu(bn(L0(z)))).  Its data gradient g_z joins the decoder-3 chain only at "G4b = GC2 + g_z":
+        // with the side streams available it runs on st3 beside the full-resolution data gradients of decoder 3.
+        const bool side = two_streams && st3 != nullptr;
+        {
+            cudaStream_t main = st; double* main_partial = partial;
+            if (side) {
+                PTTA_CUDA(cudaEventRecord(ev_lossg, st));
+                PTTA_CUDA(cudaStreamWaitEvent(st3, ev_lossg, 0));
+                st = st3; partial = partial3;
+            }
+            int rc3 = gemm(g_ref, proj3.pack_t, g_a3, nullptr, R, 512, 512);
+            if (!rc3) rc3 = bn_backward(projBn, bnProjR, g_a3, h_a0r, g_a0, R, 1, nullptr, nullptr);
+            if (!rc3) rc3 = gemm(g_a0, proj0.pack_t, GZ.p, nullptr, R, 32, 512);     // g_z (grad wrt e3.x2 from the heads)
+            if (side && !rc3 && cudaEventRecord(ev_headb, st3) != cudaSuccess) { set_error("cudaEventRecord failed"); rc3 = 2; }
+            st = main; partial = main_partial;
+            if (rc3) return rc3;
+        }
 
         // ---- decoder 3 ----
         PTTA_TRY(dec_pred_backward(dec3W, B.d3, g_out, T1a, T1b, nullptr));                 // T1b = g_s0 (= g_x4 = g_e3x0)
@@ -960,7 +1062,8 @@ struct ptta_msgchn {
         PTTA_TRY(conv_dgrad(dec3W.d1a, T1a, T2a, B.d3.s1.p, nullptr));                      // T2a = g_s1 (= g_e3x1 = g_x3)
         PTTA_TRY(conv_dgrad(dec3W.d2b, T2a, T2b, B.d3.u2.p, nullptr));                      // T2b = g_u2
         PTTA_TRY(conv_dgrad(dec3W.d2a, T2b, GC2, B.d3.x2.p, nullptr));                      // GC2 = grad of d3.x2 (meta contribution #1)
-        PTTA_TRY(add32(GC2, G4a, G4b));                                                     // G4b = g_e3x2 = GC2 + g_z
+        if (side) PTTA_CUDA(cudaStreamWaitEvent(st, ev_headb, 0));
+        PTTA_TRY(add32(GC2, GZ, G4b));                                                      // G4b = g_e3x2 = GC2 + g_z
         // ---- encoder 3 ----
         PTTA_TRY(up2_adj32(G4b, D8, 0));                                                    // D8 = grad of d2.x2 (skip)
         PTTA_TRY(conv_dgrad(enc3W.e2b, G4b, G4a, B.e3.t2.p, nullptr));                      // G4a = g_t2
@@ -1006,17 +1109,28 @@ struct ptta_msgchn {
         const std::string p = "conv1_rgb_meta.conv1_meta";
         // BN2: c2 = bn2(mg) + c2raw
         PTTA_TRY(bn_backward(metaBn2, B.bn2, GC2.p, B.mg.p, G4a.p, rows, 0, grad_of(p + ".2.weight"), grad_of(p + ".2.bias")));   // G4a = g_mg
-        {
+        {   // conv2's bias and weight gradients need g_mg only: on st3, beside the data gradient of conv2 and everything upstream of it
+            cudaStream_t main = st; double* main_partial = partial; float* main_ws = wgrad_ws;
+            if (side) {
+                PTTA_CUDA(cudaEventRecord(ev_gmg, st));
+                PTTA_CUDA(cudaStreamWaitEvent(st3, ev_gmg, 0));
+                st = st3; partial = partial3; wgrad_ws = wgrad_ws2;
+            }
             int nblk = 0;
-            PTTA_TRY(stats(G4a.p, nullptr, rows, 32, 0, nullptr, 0, nblk));
-            launch_k(colsum_finalize_kernel, 1, FIN_THREADS, 0, st, partial, nblk, 32, grad_of(p + ".1.bias"));
-            PTTA_TRY(check_launch("colsum_finalize"));
-        }
-        {   // conv2 wgrad: input = leaky(bn1(mh))
-            WgradParams wp; memset(&wp, 0, sizeof(wp));
-            wp.in = B.mh.p; wp.gout = G4a.p; wp.partial = wgrad_ws; wp.N = N; wp.H = H / 4; wp.W = W / 4;
-            wp.pro = PRO_BN_LEAKY; wp.pro_scale = B.bn1.scale; wp.pro_shift = B.bn1.shift; wp.slope = 0.2f;
-            PTTA_TRY(launch_wgrad(wp, grad_of(p + ".1.weight"), 128, 32, st));
+            int rc3 = stats(G4a.p, nullptr, rows, 32, 0, nullptr, 0, nblk);
+            if (!rc3) {
+                launch_k(colsum_finalize_kernel, 1, FIN_THREADS, 0, st, partial, nblk, 32, grad_of(p + ".1.bias"));
+                rc3 = check_launch("colsum_finalize");
+            }
+            if (!rc3) {   // conv2 wgrad: input = leaky(bn1(mh))
+                WgradParams wp; memset(&wp, 0, sizeof(wp));
+                wp.in = B.mh.p; wp.gout = G4a.p; wp.partial = wgrad_ws; wp.N = N; wp.H = H / 4; wp.W = W / 4;
+                wp.pro = PRO_BN_LEAKY; wp.pro_scale = B.bn1.scale; wp.pro_shift = B.bn1.shift; wp.slope = 0.2f;
+                rc3 = launch_wgrad(wp, grad_of(p + ".1.weight"), 128, 32, st);
+            }
+            if (side && !rc3 && cudaEventRecord(ev_wg2, st3) != cudaSuccess) { set_error("cudaEventRecord failed"); rc3 = 2; }
+            st = main; partial = main_partial; wgrad_ws = main_ws;
+            if (rc3) return rc3;
         }
         PTTA_TRY(conv_dgrad(meta2, G4a, M128a, B.mh.p, nullptr, MASK_BN_LEAKY, &B.bn1));    // M128a = grad wrt bn1 output
         PTTA_TRY(bn_backward(metaBn1, B.bn1, M128a.p, B.mh.p, M128b.p, rows, 0, grad_of(p + ".0.1.weight"), grad_of(p + ".0.1.bias")));
@@ -1025,6 +1139,7 @@ struct ptta_msgchn {
             wp.in = B.c2raw.p; wp.gout = M128b.p; wp.partial = wgrad_ws; wp.N = N; wp.H = H / 4; wp.W = W / 4; wp.pro = PRO_NONE;
             PTTA_TRY(launch_wgrad(wp, grad_of(p + ".0.0.weight"), 32, 128, st));
         }
+        if (side) PTTA_CUDA(cudaStreamWaitEvent(st, ev_wg2, 0));
         return 0;
     }
 
@@ -1127,6 +1242,20 @@ int ptta_pack_conv_weight_tc(const void* wpack, void* image, ptta_stream_t strea
     return check_launch("pack_conv_weight_tc");
 }
 
+int ptta_pack_conv_weight_tc_t2(const void* wpack, void* image, ptta_stream_t stream) {
+    PTTA_CHECK(wpack && image, "pack_conv_weight_tc_t2: null argument");
+    launch_k(pack_conv_weight_tc_t2_kernel, cdiv(9 * 32 * 4, 256), 256, 0, (cudaStream_t)stream, (const bf16*)wpack, (bf16*)image);
+    return check_launch("pack_conv_weight_tc_t2");
+}
+int ptta_conv3x3_tc_t2(const void* in, void* out, const void* wimage, const float* bias, int n, int h, int w, int relu_out, const void* mask,
+                       const void* add, ptta_stream_t stream) {
+    PTTA_CHECK(in && out && wimage, "conv3x3_tc_t2: null argument");
+    ConvTcParams p; memset(&p, 0, sizeof(p));
+    p.w = (const bf16*)wimage; p.bias = bias; p.out = (bf16*)out; p.mask = (const bf16*)mask; p.add = (const bf16*)add;
+    p.N = n; p.H = h; p.W = w; p.relu_out = relu_out;
+    return launch_conv_tc_t2((const bf16*)in, p, (cudaStream_t)stream);
+}
+
 int ptta_pack_conv_weight_tc_s2(const void* wpack, void* image, ptta_stream_t stream) {
     PTTA_CHECK(wpack && image, "pack_conv_weight_tc_s2: null argument");
     launch_k(pack_conv_weight_tc_s2_kernel, cdiv(9 * 32 * 4, 256), 256, 0, (cudaStream_t)stream, (const bf16*)wpack, (bf16*)image);
@@ -1176,12 +1305,26 @@ int ptta_stem_conv(const float* const* planes, const long long* strides, const f
         p.plane[k] = planes[s]; p.batch_stride[k] = strides[s]; p.scale[k] = scale[s]; p.shift[k] = shift[s];
     }
     p.w = weight; p.bias = bias; p.mask = (const bf16*)mask; p.out = (bf16*)out; p.N = n; p.H = h; p.W = w;
-    long long tot = (long long)n * h * w;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (cin == 1) launch_k(stem_conv_kernel<1>, cdiv(tot, 128), 128, 0, st, p);
-    else if (cin == 2) launch_k(stem_conv_kernel<2>, cdiv(tot, 128), 128, 0, st, p);
-    else launch_k(stem_conv_kernel<3>, cdiv(tot, 128), 128, 0, st, p);
+    launch_stem(p, cin, (cudaStream_t)stream);
     return check_launch("stem_conv");
+}
+
+int ptta_stem_conv_const(const float* const* planes, const long long* strides, const float* scale, const float* shift, int cin,
+                         const float* weight_host, const float* bias_host, const void* mask, void* out, int relu_out, int n, int h, int w,
+                         ptta_stream_t stream) {
+    PTTA_CHECK(cin >= 1 && cin <= 3 && (w & 1) == 0, "stem_conv_const: cin=%d (1..3), W=%d (even)", cin, w);
+    PTTA_CHECK(weight_host && out, "stem_conv_const: null argument");
+    StemCParams c; memset(&c, 0, sizeof(c));
+    for (int k = 0; k < 3; ++k) {
+        int s = k < cin ? k : 0;
+        c.plane[k] = planes[s]; c.batch_stride[k] = strides[s]; c.scale[k] = scale[s]; c.shift[k] = shift[s];
+    }
+    for (int co = 0; co < 32; ++co)
+        for (int r = 0; r < cin * 9; ++r) c.w[r * 32 + co] = weight_host[(size_t)co * cin * 9 + r];
+    if (bias_host) memcpy(c.bias, bias_host, sizeof(c.bias));
+    c.mask = (const bf16*)mask; c.out = (bf16*)out; c.N = n; c.H = h; c.W = w; c.relu_out = relu_out;
+    launch_stem_const(c, cin, (cudaStream_t)stream);
+    return check_launch("stem_conv_const");
 }
 
 int ptta_head_conv(const void* in, const float* w, float bias, const float* add, float* out, int n, int h, int ww, int relu_in,
@@ -1189,6 +1332,16 @@ int ptta_head_conv(const void* in, const float* w, float bias, const float* add,
     long long tot = (long long)n * h * ww;
     launch_k(head_conv_kernel, dim3(cdiv(ww, HEADC_TW), cdiv(h, HEADC_TH), n), dim3(HEADC_TW, HEADC_TH), 0, (cudaStream_t)stream, (const bf16*)in, w, bias, add, out, n, h, ww, relu_in, accumulate);
     return check_launch("head_conv");
+}
+
+int ptta_head_conv_const(const void* in, const float* weight_host_9x32, float bias, const float* add, float* out, int n, int h, int ww,
+                         int relu_in, int accumulate, ptta_stream_t stream) {
+    PTTA_CHECK(in && weight_host_9x32 && out, "head_conv_const: null argument");
+    HeadCParams c; memset(&c, 0, sizeof(c));
+    c.in = (const bf16*)in; c.add = add; c.out = out; c.N = n; c.H = h; c.W = ww; c.relu_in = relu_in; c.accumulate = accumulate; c.bias = bias;
+    memcpy(c.w, weight_host_9x32, sizeof(c.w));
+    launch_k(head_convc_kernel, dim3(cdiv(ww, HEADC_TW), cdiv(h, HEADC_TH), n), dim3(HEADC_TW, HEADC_TH), 0, (cudaStream_t)stream, c);
+    return check_launch("head_conv_const");
 }
 
 int ptta_up2_1ch(const float* a, const float* b, const float* c, float* out, int n, int h, int w, ptta_stream_t stream) {
@@ -1449,7 +1602,7 @@ int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepa
     if (getenv("PTTA_NO_TC")) e->tc_enabled = false;
     if (getenv("PTTA_NO_FUSE_DEC_SUMS")) e->fuse_dec_sums = false;
     if (getenv("PTTA_ONE_STREAM")) e->two_streams = false;
-    if (const char* v = getenv("PTTA_TC_MIN_PIXELS")) e->tc_min_pixels = e->tc_s2_min_pixels = atoll(v);
+    if (const char* v = getenv("PTTA_TC_MIN_PIXELS")) e->tc_min_pixels = e->tc_s2_min_pixels = e->tc_t2_min_pixels = atoll(v);
     e->define_model();
     e->plan();
     *out = e;
@@ -1460,6 +1613,7 @@ int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value) {
     const std::string k = name;
     if (k == "tc_min_pixels") e->tc_min_pixels = value;                 // smallest map (pixels) the stride-1 tcgen05 conv takes
     else if (k == "tc_s2_min_pixels") e->tc_s2_min_pixels = value;      // same for the stride-2 tcgen05 conv
+    else if (k == "tc_t2_min_pixels") e->tc_t2_min_pixels = value;      // same for the transposed stride-2 tcgen05 conv (INPUT pixels)
     else if (k == "tc_enabled") e->tc_enabled = value != 0;
     else if (k == "two_streams") e->two_streams = value != 0;
     else if (k == "fuse_dec_sums") e->fuse_dec_sums = value != 0;
@@ -1472,6 +1626,8 @@ void ptta_msgchn_destroy(ptta_msgchn* e) {
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     if (e->st2) { cudaStreamDestroy(e->st2); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaEventDestroy(e->ev_projbn);
                  cudaEventDestroy(e->ev_enc1); cudaEventDestroy(e->ev_zmeta); }
+    if (e->st3) { cudaStreamDestroy(e->st3); cudaEventDestroy(e->ev_e3); cudaEventDestroy(e->ev_mlp); cudaEventDestroy(e->ev_lossg);
+                 cudaEventDestroy(e->ev_headb); cudaEventDestroy(e->ev_gmg); cudaEventDestroy(e->ev_wg2); }
     delete e;
 }
 size_t ptta_msgchn_workspace_bytes(const ptta_msgchn* e) { return e ? e->ws_bytes : 0; }
@@ -1490,6 +1646,9 @@ int ptta_msgchn_bind_workspace(ptta_msgchn* e, void* ws, size_t bytes, ptta_stre
         PTTA_CUDA(cudaEventCreateWithFlags(&e->ev_projbn, cudaEventDisableTiming));
         PTTA_CUDA(cudaEventCreateWithFlags(&e->ev_enc1, cudaEventDisableTiming));
         PTTA_CUDA(cudaEventCreateWithFlags(&e->ev_zmeta, cudaEventDisableTiming));
+        PTTA_CUDA(cudaStreamCreateWithFlags(&e->st3, cudaStreamNonBlocking));
+        cudaEvent_t* evs[6] = {&e->ev_e3, &e->ev_mlp, &e->ev_lossg, &e->ev_headb, &e->ev_gmg, &e->ev_wg2};
+        for (cudaEvent_t* ev : evs) PTTA_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     }
     PTTA_CUDA(cudaMemsetAsync(ws, 0, e->ws_bytes, (cudaStream_t)stream));
     AdamHyper hy;

@@ -246,6 +246,263 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams p) {
     }
 }
 
+// Same operator, PX (2 or 4) consecutive pixels of a row per thread (W % PX == 0): every weight read from shared memory (one 16 B
+// broadcast load = 4 output channels) feeds 4*PX FMAs instead of 4, the 3 x (PX+2) input window is loaded once per plane, and the
+// thread's PX x 64 B of bf16 output leave through a warp-private swizzled staging tile as 512 B coalesced stores.  The kernel is bound by
+// the fp32 FMA pipe (864 FMA per pixel for the 3-plane image stem: 10 us at 352x1216 at 100 % issue rate); tensor cores are not an
+// option here because the depth planes need fp32 inputs (metres with millimetre resolution: bf16 / tf32 would quantise a 40 m sample
+// by 12 cm / 2 cm).  PX = 2 with 4 blocks per SM: 16 warps hide the shared-memory latency of the weight loads (ncu on the PX = 4, 2
+// blocks per SM form: 36 % issue-slot utilisation, 2 warps per scheduler, 5.4 cycles per issued instruction).
+template <int CIN, int PX>
+__global__ void __launch_bounds__(128, PX == 2 ? 4 : 2) stem_convp_kernel(const StemParams p) {
+    PDL_SYNC();
+    constexpr int TB = PX * 64;                         // bytes of output per thread
+    constexpr int NCH = PX * 4;                         // 16 B chunks per thread
+    __shared__ __align__(16) float s_w[CIN * 9 * 32];   // [ci][tap][co]
+    __shared__ float s_b[32];
+    __shared__ __align__(16) unsigned char s_stage[4][32 * TB];   // per warp: 32 threads x TB
+    for (int i = threadIdx.x; i < CIN * 9 * 32; i += blockDim.x) {
+        int co = i & 31, r = i >> 5;       // r = ci*9 + tap
+        s_w[i] = p.w[(size_t)co * CIN * 9 + r];
+    }
+    if (threadIdx.x < 32) s_b[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wq = p.W / PX;
+    const long long total = (long long)p.N * p.H * wq;                          // groups; group q covers NHWC pixels PX*q .. PX*q+PX-1
+    const long long q0 = (long long)blockIdx.x * blockDim.x + warp * 32;
+    if (q0 >= total) return;
+    const int nvalid = (int)min((long long)32, total - q0);
+    const long long q = q0 + lane;
+    const bool valid = lane < nvalid;
+    unsigned char* stage = s_stage[warp];
+    float acc[PX][32];
+#pragma unroll
+    for (int px = 0; px < PX; ++px)
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[px][c] = s_b[c];
+    if (valid) {
+        const int x = (int)(q % wq) * PX;
+        const int y = (int)((q / wq) % p.H);
+        const long long n = q / ((long long)wq * p.H);
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float* pl = p.plane[ci] + n * p.batch_stride[ci];
+            const float sc = p.scale[ci], sh = p.shift[ci];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int gy = y + ky - 1;
+                if (gy < 0 || gy >= p.H) continue;                               // zero padding of the (normalised) input
+                const float* row = pl + (size_t)gy * p.W + x;
+                float v[PX + 2];
+                v[0] = x > 0 ? fmaf(__ldg(row - 1), sc, sh) : 0.f;
+                if (PX == 4) {
+                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(row));
+                    v[1] = fmaf(c4.x, sc, sh); v[2] = fmaf(c4.y, sc, sh); v[PX - 1] = fmaf(c4.z, sc, sh); v[PX] = fmaf(c4.w, sc, sh);
+                } else {
+                    const float2 c2 = __ldg(reinterpret_cast<const float2*>(row));
+                    v[1] = fmaf(c2.x, sc, sh); v[2] = fmaf(c2.y, sc, sh);
+                }
+                v[PX + 1] = x + PX < p.W ? fmaf(__ldg(row + PX), sc, sh) : 0.f;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4* wr = reinterpret_cast<const float4*>(s_w + (ci * 9 + ky * 3 + kx) * 32);
+#pragma unroll
+                    for (int c4i = 0; c4i < 8; ++c4i) {
+                        const float4 w4 = wr[c4i];
+#pragma unroll
+                        for (int px = 0; px < PX; ++px) {
+                            const float a = v[px + kx];
+                            acc[px][c4i * 4 + 0] = fmaf(a, w4.x, acc[px][c4i * 4 + 0]);
+                            acc[px][c4i * 4 + 1] = fmaf(a, w4.y, acc[px][c4i * 4 + 1]);
+                            acc[px][c4i * 4 + 2] = fmaf(a, w4.z, acc[px][c4i * 4 + 2]);
+                            acc[px][c4i * 4 + 3] = fmaf(a, w4.w, acc[px][c4i * 4 + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        const uint4* mrow = p.mask ? reinterpret_cast<const uint4*>(p.mask + (size_t)q * (PX * 32)) : nullptr;    // PX pixels x 32 channels
+#pragma unroll
+        for (int px = 0; px < PX; ++px) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float* a = &acc[px][g * 8];
+                if (mrow) {
+                    const uint4 mv = __ldg(mrow + px * 4 + g);
+                    const uint32_t* mu = reinterpret_cast<const uint32_t*>(&mv);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 m = unpack_bf162(mu[j]);
+                        if (!(m.x > 0.f)) a[j * 2] = 0.f;
+                        if (!(m.y > 0.f)) a[j * 2 + 1] = 0.f;
+                    }
+                }
+                if (p.relu_out) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+                }
+                uint4 ov;
+                ov.x = pack_bf162(a[0], a[1]); ov.y = pack_bf162(a[2], a[3]);
+                ov.z = pack_bf162(a[4], a[5]); ov.w = pack_bf162(a[6], a[7]);
+                const int k = px * 4 + g;
+                *reinterpret_cast<uint4*>(stage + lane * TB + ((k ^ (lane & (NCH - 1))) << 4)) = ov;
+            }
+        }
+    }
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)q0 * (PX * 32));
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int i = j * 32 + lane, r = i / NCH, c = i % NCH;
+        if (r < nvalid) dst[i] = *reinterpret_cast<const uint4*>(stage + r * TB + ((c ^ (r & (NCH - 1))) << 4));
+    }
+}
+
+// The engine's form: weights and bias travel BY VALUE in the kernel parameters (constant bank), so every FMA takes its weight as a
+// constant operand and the inner loop is FMAs only -- no shared-memory weight loads (a 16 B broadcast load costs the shared pipe
+// four wavefronts: with one per 8 / 16 FMAs that pipe, not the FMA pipe, set the speed of the kernels above), no staging barrier.
+// The layers it serves are frozen ('meta' adapt mode), so the host copy taken at pack time stays valid; a re-pack re-captures the graph.
+struct StemCParams {
+    const float* plane[3];
+    long long batch_stride[3];
+    float scale[3], shift[3];
+    const bf16* mask;    // relu mask (NHWC 32) or null
+    bf16* out;
+    int N, H, W;
+    int relu_out;
+    float bias[32];
+    float w[3 * 9 * 32]; // [ci][tap][co]
+};
+
+template <int CIN, int PX>
+__global__ void __launch_bounds__(128, 4) stem_convc_kernel(const __grid_constant__ StemCParams p) {
+    PDL_SYNC();
+    constexpr int TB = PX * 64, NCH = PX * 4;
+    __shared__ __align__(16) unsigned char s_stage[4][32 * TB];   // per warp: 32 threads x TB
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wq = p.W / PX;
+    const long long total = (long long)p.N * p.H * wq;
+    const long long q0 = (long long)blockIdx.x * blockDim.x + warp * 32;
+    if (q0 >= total) return;
+    const int nvalid = (int)min((long long)32, total - q0);
+    const long long q = q0 + lane;
+    const bool valid = lane < nvalid;
+    unsigned char* stage = s_stage[warp];
+    float acc[PX][32];
+#pragma unroll
+    for (int px = 0; px < PX; ++px)
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[px][c] = p.bias[c];
+    if (valid) {
+        const int x = (int)(q % wq) * PX;
+        const int y = (int)((q / wq) % p.H);
+        const long long n = q / ((long long)wq * p.H);
+        // the whole 3 x (PX+2) x CIN input window first (all loads in flight together: one exposed memory latency per thread, hidden by
+        // the FMA phases of the other warps), then FMAs only
+        float vin[CIN][3][PX + 2];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float* pl = p.plane[ci] + n * p.batch_stride[ci];
+            const float sc = p.scale[ci], sh = p.shift[ci];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int gy = y + ky - 1;
+                const bool rin = gy >= 0 && gy < p.H;                             // outside: zero padding of the (normalised) input
+                const float* row = pl + (size_t)(rin ? gy : y) * p.W + x;
+                float* v = vin[ci][ky];
+                v[0] = (rin && x > 0) ? fmaf(__ldg(row - 1), sc, sh) : 0.f;
+                if (PX == 4) {
+                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(row));
+                    v[1] = fmaf(c4.x, sc, sh); v[2] = fmaf(c4.y, sc, sh); v[PX - 1] = fmaf(c4.z, sc, sh); v[PX] = fmaf(c4.w, sc, sh);
+                } else {
+                    const float2 c2 = __ldg(reinterpret_cast<const float2*>(row));
+                    v[1] = fmaf(c2.x, sc, sh); v[2] = fmaf(c2.y, sc, sh);
+                }
+                v[PX + 1] = (rin && x + PX < p.W) ? fmaf(__ldg(row + PX), sc, sh) : 0.f;
+                if (!rin) {
+#pragma unroll
+                    for (int k = 1; k <= PX; ++k) v[k] = 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float wv = p.w[(ci * 9 + ky * 3 + kx) * 32 + c];      // constant-bank operand
+#pragma unroll
+                        for (int px = 0; px < PX; ++px) acc[px][c] = fmaf(vin[ci][ky][px + kx], wv, acc[px][c]);
+                    }
+                }
+            }
+        }
+        const uint4* mrow = p.mask ? reinterpret_cast<const uint4*>(p.mask + (size_t)q * (PX * 32)) : nullptr;
+#pragma unroll
+        for (int px = 0; px < PX; ++px) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float* a = &acc[px][g * 8];
+                if (mrow) {
+                    const uint4 mv = __ldg(mrow + px * 4 + g);
+                    const uint32_t* mu = reinterpret_cast<const uint32_t*>(&mv);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 m = unpack_bf162(mu[j]);
+                        if (!(m.x > 0.f)) a[j * 2] = 0.f;
+                        if (!(m.y > 0.f)) a[j * 2 + 1] = 0.f;
+                    }
+                }
+                if (p.relu_out) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+                }
+                uint4 ov;
+                ov.x = pack_bf162(a[0], a[1]); ov.y = pack_bf162(a[2], a[3]);
+                ov.z = pack_bf162(a[4], a[5]); ov.w = pack_bf162(a[6], a[7]);
+                const int k = px * 4 + g;
+                *reinterpret_cast<uint4*>(stage + lane * TB + ((k ^ (lane & (NCH - 1))) << 4)) = ov;
+            }
+        }
+    }
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)q0 * (PX * 32));
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int i = j * 32 + lane, r = i / NCH, c = i % NCH;
+        if (r < nvalid) dst[i] = *reinterpret_cast<const uint4*>(stage + r * TB + ((c ^ (r & (NCH - 1))) << 4));
+    }
+}
+
+// W must be even; `cin` selects the instantiation
+inline void launch_stem_const(const StemCParams& p, int cin, cudaStream_t st) {
+    const long long tot = (long long)p.N * p.H * p.W;
+    const int blocks = cdiv(tot / 2, 128);
+    if (cin == 1) launch_k(stem_convc_kernel<1, 2>, blocks, 128, 0, st, p);
+    else if (cin == 2) launch_k(stem_convc_kernel<2, 2>, blocks, 128, 0, st, p);
+    else launch_k(stem_convc_kernel<3, 2>, blocks, 128, 0, st, p);
+}
+
+// launches the 2-pixel kernel when the row length allows it, the 1-pixel kernel otherwise
+inline void launch_stem(const StemParams& p, int cin, cudaStream_t st) {
+    const long long tot = (long long)p.N * p.H * p.W;
+    if ((p.W & 1) == 0) {
+        const int blocks = cdiv(tot / 2, 128);
+        if (cin == 1) launch_k(stem_convp_kernel<1, 2>, blocks, 128, 0, st, p);
+        else if (cin == 2) launch_k(stem_convp_kernel<2, 2>, blocks, 128, 0, st, p);
+        else launch_k(stem_convp_kernel<3, 2>, blocks, 128, 0, st, p);
+    } else {
+        const int blocks = cdiv(tot, 128);
+        if (cin == 1) launch_k(stem_conv_kernel<1>, blocks, 128, 0, st, p);
+        else if (cin == 2) launch_k(stem_conv_kernel<2>, blocks, 128, 0, st, p);
+        else launch_k(stem_conv_kernel<3>, blocks, 128, 0, st, p);
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // 32 -> 1 channel 3x3 s1 p1 conv: the prediction layer prdct.3 (network_exp_msg_chn_adapt.py:289)
 // with ReLU-on-load, and -- with pre-flipped weights, no ReLU, accumulate -- the data-gradient of a
@@ -309,6 +566,71 @@ __global__ void __launch_bounds__(HEADC_TW * HEADC_TH) head_conv_kernel(const bf
     if (add) acc += add[idx];
     if (accumulate) acc += out[idx];
     out[idx] = acc;
+}
+
+// The engine's form of the 32 -> 1 conv: the same tile scheme with the weights BY VALUE in the kernel parameters (constant-bank FMA
+// operands instead of 72 shared-memory weight loads per output pixel).  A vertical-strip variant (4 outputs per thread, each staged pixel
+// unpacked once for the three rows it feeds) was measured at 36 us against 24 us for this form at 352x1216: register pressure made the
+// compiler redo the unpacking per tap.  Launch: grid (cdiv(W, 32), cdiv(H, 8), N), block (32, 8).
+struct HeadCParams {
+    const bf16* in; const float* add; float* out;
+    int N, H, W, relu_in, accumulate;
+    float bias;
+    float w[9 * 32];     // [tap][ci]
+};
+__global__ void __launch_bounds__(HEADC_TW * HEADC_TH) head_convc_kernel(const __grid_constant__ HeadCParams p) {
+    PDL_SYNC();
+    __shared__ __align__(16) unsigned char s_in[(HEADC_TH + 2) * (HEADC_TW + 2) * 64];
+    const int x0 = blockIdx.x * HEADC_TW, y0 = blockIdx.y * HEADC_TH, n = blockIdx.z;
+    const bf16* inn = p.in + (size_t)n * p.H * p.W * 32;
+    const bf162 z = __floats2bfloat162_rn(0.f, 0.f);
+    // halo: warp w stages rows w, w+8; lane j walks the row's 34 x 4 sixteen-byte chunks (no integer division on the way)
+    for (int ry = threadIdx.y; ry < HEADC_TH + 2; ry += HEADC_TH) {
+        const int gy = y0 + ry - 1;
+        const bool rin = gy >= 0 && gy < p.H;
+        const bf16* grow = inn + (size_t)(rin ? gy : 0) * p.W * 32;
+        for (int j = threadIdx.x; j < (HEADC_TW + 2) * 4; j += 32) {
+            const int c = j & 3, px = j >> 2;
+            const int gx = x0 + px - 1;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (rin && gx >= 0 && gx < p.W) {
+                v = __ldg(reinterpret_cast<const uint4*>(grow + (size_t)gx * 32) + c);
+                if (p.relu_in) {
+                    bf162* h = reinterpret_cast<bf162*>(&v);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) h[k] = __hmax2(h[k], z);
+                }
+            }
+            const int row = ry * (HEADC_TW + 2) + px;
+            *reinterpret_cast<uint4*>(s_in + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)) = v;
+        }
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= p.W || y >= p.H) return;
+    float acc = p.bias;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int row = (threadIdx.y + ky) * (HEADC_TW + 2) + threadIdx.x + kx;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 v = *reinterpret_cast<const uint4*>(s_in + row * 64 + ((q ^ ((row >> 1) & 3)) << 4));
+                const uint32_t* u = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf162(u[j]);
+                    acc = fmaf(f.x, p.w[(ky * 3 + kx) * 32 + q * 8 + j * 2], acc);
+                    acc = fmaf(f.y, p.w[(ky * 3 + kx) * 32 + q * 8 + j * 2 + 1], acc);
+                }
+            }
+        }
+    }
+    const size_t idx = ((size_t)n * p.H + y) * p.W + x;
+    if (p.add) acc += p.add[idx];
+    if (p.accumulate) acc += p.out[idx];
+    p.out[idx] = acc;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -515,6 +837,28 @@ __global__ void ew_add_kernel(const bf16* __restrict__ a, const bf16* __restrict
         uo[j] = pack_bf162(s0, s1);
     }
     reinterpret_cast<uint4*>(out)[i] = ov;
+}
+
+// The three skip sums of a decoder (network_exp_msg_chn_adapt.py:301-303: x2 = dx2 + cx2, x1 = dx1 + cx1, x0 = dx0 + cx0) in one
+// launch; the /4-resolution sum x2 is also written through a ReLU (the transposed conv that reads it has no ReLU-on-load).
+struct DecSumsParams { const bf16* a[3]; const bf16* b[3]; bf16* out[3]; bf16* out0_relu; long long n8[3]; };
+__global__ void dec_sums_kernel(const DecSumsParams p) {
+    PDL_SYNC();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int k = 0;
+    if (i >= p.n8[0]) { i -= p.n8[0]; k = 1; if (i >= p.n8[1]) { i -= p.n8[1]; k = 2; if (i >= p.n8[2]) return; } }
+    const uint4 av = reinterpret_cast<const uint4*>(p.a[k])[i], bv = reinterpret_cast<const uint4*>(p.b[k])[i];
+    const uint32_t *ua = reinterpret_cast<const uint32_t*>(&av), *ub = reinterpret_cast<const uint32_t*>(&bv);
+    uint4 ov, rv; uint32_t *uo = reinterpret_cast<uint32_t*>(&ov), *ur = reinterpret_cast<uint32_t*>(&rv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 fa = unpack_bf162(ua[j]), fb = unpack_bf162(ub[j]);
+        const float s0 = fa.x + fb.x, s1 = fa.y + fb.y;
+        uo[j] = pack_bf162(s0, s1);
+        ur[j] = pack_bf162(fmaxf(s0, 0.f), fmaxf(s1, 0.f));
+    }
+    reinterpret_cast<uint4*>(p.out[k])[i] = ov;
+    if (k == 0 && p.out0_relu) reinterpret_cast<uint4*>(p.out0_relu)[i] = rv;
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -146,6 +146,22 @@ def conv3x3_tc_s2(x, wpack, bias=None, relu_out=False, mask=None, add=None, want
     return (out, out2) if want_relu_copy else out
 
 
+def conv3x3_tc_t2(x, wpack, bias=None, relu_out=False, mask=None, add=None):
+    """32->32 transposed stride-2 conv on tcgen05 (operand conventions of conv3x3 with MODE_T2, no ReLU-on-load); W even.
+    x: [n, h, w, 32] -> [n, 2h, 2w, 32]"""
+    _need(x, torch.bfloat16, 'x')
+    _need(wpack, torch.bfloat16, 'wpack')
+    n, h, w, cin = x.shape
+    if cin != 32 or tuple(wpack.shape) != (9, 32, 32):
+        raise ValueError('conv3x3_tc_t2 handles 32->32 channels only')
+    image = torch.empty((9 * 32 * 32,), dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().ptta_pack_conv_weight_tc_t2(ptr(wpack), ptr(image), _stream()), 'pack_conv_weight_tc_t2')
+    out = torch.empty((n, 2 * h, 2 * w, 32), dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().ptta_conv3x3_tc_t2(ptr(x), ptr(out), ptr(image), ptr(bias), n, h, w, 1 if relu_out else 0, ptr(mask), ptr(add), _stream()),
+          'conv3x3_tc_t2')
+    return out
+
+
 def conv3x3_wgrad(x, gout, prologue=PRO_NONE, pro_scale=None, pro_shift=None, slope=0.2):
     _need(x, torch.bfloat16, 'x')
     _need(gout, torch.bfloat16, 'gout')
@@ -172,6 +188,34 @@ def stem_conv(planes, weight, bias=None, scale=None, shift=None, mask=None):
     sh = (ctypes.c_float * 3)(*(list(shift) if shift is not None else [0.0] * cin) + [0.0] * (3 - cin))
     out = torch.empty((n, h, w, 32), dtype=torch.bfloat16, device=weight.device)
     check(_lib.lib().ptta_stem_conv(pl, st, sc, sh, cin, ptr(weight), ptr(bias), ptr(mask), ptr(out), n, h, w, _stream()), 'stem_conv')
+    return out
+
+
+def stem_conv_const(planes, weight, bias=None, scale=None, shift=None, mask=None, relu_out=False):
+    """stem_conv with HOST weights [32, cin, 3, 3] / bias [32] (CPU tensors): by-value kernel parameters, constant-bank operands"""
+    cin = len(planes)
+    n, h, w = planes[0].shape
+    wh = weight.detach().cpu().contiguous().float()
+    bh = None if bias is None else bias.detach().cpu().contiguous().float()
+    pl = (ctypes.c_void_p * 3)(*[planes[min(k, cin - 1)].data_ptr() for k in range(3)])
+    st = (ctypes.c_longlong * 3)(*[h * w] * 3)
+    sc = (ctypes.c_float * 3)(*(list(scale) if scale is not None else [1.0] * cin) + [1.0] * (3 - cin))
+    sh = (ctypes.c_float * 3)(*(list(shift) if shift is not None else [0.0] * cin) + [0.0] * (3 - cin))
+    out = torch.empty((n, h, w, 32), dtype=torch.bfloat16, device=planes[0].device)
+    check(_lib.lib().ptta_stem_conv_const(pl, st, sc, sh, cin, ctypes.c_void_p(wh.data_ptr()), ctypes.c_void_p(bh.data_ptr()) if bh is not None else None,
+                                          ptr(mask), ptr(out), 1 if relu_out else 0, n, h, w, _stream()), 'stem_conv_const')
+    return out
+
+
+def head_conv_const(x, weight_9x32, bias=0.0, add=None, relu_in=True, out=None, accumulate=False):
+    """head_conv with a HOST [9, 32] weight (CPU tensor)"""
+    _need(x, torch.bfloat16, 'x')
+    n, h, w, _ = x.shape
+    wh = weight_9x32.detach().cpu().contiguous().float()
+    if out is None:
+        out = torch.empty((n, h, w), dtype=torch.float32, device=x.device)
+    check(_lib.lib().ptta_head_conv_const(ptr(x), ctypes.c_void_p(wh.data_ptr()), float(bias), ptr(add), ptr(out), n, h, w, 1 if relu_in else 0,
+                                          1 if accumulate else 0, _stream()), 'head_conv_const')
     return out
 
 
