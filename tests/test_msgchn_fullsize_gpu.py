@@ -31,9 +31,23 @@ FULL = [
 IDS = [c[0] for c in FULL]
 
 
+def _sync_oracle_to_native(model, sd_o, state, names, t):
+    """teacher forcing: the oracle takes the native path's weights, BatchNorm buffers and Adam moments, so that every step is an
+    independent comparison from IDENTICAL state (a continual comparison multiplies the L1-sign-flip error of step t by the
+    sensitivity of step t+1 -- at the indoor lr = 3e-3 the fitted network's loss doubles per step -- and stops measuring the kernels)"""
+    sd_n = model.state_dict()
+    for k in sd_o:
+        sd_o[k].copy_(sd_n[k].detach().cpu().to(sd_o[k].dtype).view(sd_o[k].shape))
+    for k in names:
+        state.m[k] = model.model._m_views[k].detach().cpu().clone().view(sd_o[k].shape)
+        state.v[k] = model.model._v_views[k].detach().cpu().clone().view(sd_o[k].shape)
+    state.step = t
+
+
 @pytest.mark.parametrize('case', FULL, ids=IDS)
 def test_fullsize_steps_match_oracle(case):
-    """3 continual TTA steps at the benchmarked size, native (tcgen05 dispatch) vs oracle."""
+    """3 TTA steps at the benchmarked size, native (tcgen05 dispatch) vs oracle; each step starts from the native path's own state
+    (weights, BatchNorm buffers, Adam moments copied into the oracle), so the bounds are per step and carry no step-to-step allowance."""
     name, ckpt, mode, dataset, n, h, w, lr, cap = case
     tol_key = {'ckpt': ckpt if isinstance(ckpt, str) else None}          # fitted checkpoints: test_msgchn_step_gpu.loss_tolerance
     sd = O.get_checkpoint(ckpt, mode)
@@ -41,8 +55,10 @@ def test_fullsize_steps_match_oracle(case):
     sd_o = {k: v.clone() for k, v in sd.items()}
     names = O.adapt_parameter_names(sd_o)
     state = O.AdamState(names, sd_o)
-    prev = None
     for t in range(3):
+        if t:
+            _sync_oracle_to_native(model, sd_o, state, names, t)
+        before = {k: sd_o[k].clone() for k in names}
         image, sparse, dense = O.synthetic_frame(11, t, n, h, w, dataset)
         model.tta_step(image.to(DEV), sparse.to(DEV), lr, W_SD, W_SM, W_COS)
         got = model.last_losses()
@@ -52,20 +68,19 @@ def test_fullsize_steps_match_oracle(case):
         assert torch.equal(eng.tensor('filtered_depth').view(n, 1, h, w).cpu(), res['sparse_depth']), t
         for k in ('loss', 'loss_sparse_depth', 'loss_smooth', 'loss_cos'):
             report('%s step %d %-18s native %.6f oracle %.6f rel %.2e' % (name, t, k, got[k], res[k], rel(got[k], res[k])))
-            assert rel(got[k], res[k]) < step_loss_tolerance(tol_key, t, res[k], prev[k] if prev else None), (t, k, got[k], res[k])
-        prev = res
+            assert rel(got[k], res[k]) < loss_tolerance(tol_key), (t, k, got[k], res[k])
         gate = 0.0 if res['loss_cos'] < 0.3 else W_COS
         assert got['w_cos_eff'] == pytest.approx(gate), (t, got, res['loss_cos'])
         e_out = nrel(model.last_output().cpu(), res['output_depth'])
         report('%s step %d output depth nrel %.3e' % (name, t, e_out))
         assert e_out < 2e-2, (t, e_out)
-    sd_n = model.state_dict()
-    for k in names:
-        if k in ZERO_GRAD:
-            continue
-        e, upd = nrel(sd_n[k].cpu(), sd_o[k]), nrel(sd[k], sd_o[k])
-        report('%s 3 steps lr=%g %-40s weight nrel %.3e  (update/|w| %.3e, error/update %.3f)' % (name, lr, k, e, upd, e / max(upd, 1e-30)))
-        assert e < weight_tolerance(upd), (k, e, upd)
+        sd_n = model.state_dict()
+        for k in names:
+            if k in ZERO_GRAD:
+                continue
+            e, upd = nrel(sd_n[k].cpu(), sd_o[k]), nrel(before[k], sd_o[k])
+            report('%s step %d lr=%g %-40s weight nrel %.3e  (update/|w| %.3e, error/update %.3f)' % (name, t, lr, k, e, upd, e / max(upd, 1e-30)))
+            assert e < weight_tolerance(upd), (t, k, e, upd)
 
 
 @pytest.mark.parametrize('case', FULL[:1] + FULL[3:4], ids=IDS[:1] + IDS[3:4])

@@ -297,17 +297,60 @@ class MsgChnModel_Adapt(object):
         for e in self._engines.values():
             e.rebind()
 
+    # -- checkpoints: same files as the reference (src/msg_chn_model_adapt.py:482-545) ---------------------------------------
+    _ADAM_STEP_WORD = 7        # AdamHyper.step: the int after seven floats (csrc/small_kernels.cuh)
+
+    def adam_step_count(self):
+        """number of optimiser steps the fused Adam has taken (device-resident counter shared by the engines of all shapes)"""
+        return int(self._adam_hyper.view(torch.int32)[self._ADAM_STEP_WORD].item())
+
+    def load_adam_state(self, opt_sd):
+        """torch.optim.Adam state dict (as written by the reference's save_model) -> the fused Adam's flat moment buffers and step
+        counter, so that `tta_step` continues the checkpointed run exactly as `optimizer.step()` would"""
+        ids = [i for g in opt_sd['param_groups'] for i in g['params']]
+        if len(ids) != len(self._adapt_names):
+            raise RuntimeError('optimizer state covers %d tensors, the adapted set has %d' % (len(ids), len(self._adapt_names)))
+        step = 0
+        for i, k in zip(ids, self._adapt_names):
+            st = opt_sd['state'].get(i)
+            if st is None:                      # tensor never stepped
+                self._m_views[k].zero_(); self._v_views[k].zero_()
+                continue
+            if tuple(st['exp_avg'].shape) != tuple(self._m_views[k].shape):
+                raise RuntimeError('optimizer state %d has shape %s, adapted tensor %s has %s' % (
+                    i, tuple(st['exp_avg'].shape), k, tuple(self._m_views[k].shape)))
+            self._m_views[k].copy_(st['exp_avg'].to(self.device, torch.float32))
+            self._v_views[k].copy_(st['exp_avg_sq'].to(self.device, torch.float32))
+            step = max(step, int(st['step']))
+        self._adam_hyper.view(torch.int32)[self._ADAM_STEP_WORD] = step
+
+    def adam_state_dict(self, lr=0.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        """the fused Adam's state in torch.optim.Adam's own state_dict format (built by a real torch.optim.Adam, so every key the
+        installed torch expects is there)"""
+        params = list(self._param_objs.values())
+        opt = torch.optim.Adam(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        step = self.adam_step_count()
+        if step > 0:
+            for k, p in self._param_objs.items():
+                opt.state[p] = {'step': torch.tensor(float(step)), 'exp_avg': self._m_views[k].clone(), 'exp_avg_sq': self._v_views[k].clone()}
+        return opt.state_dict()
+
     def restore_model(self, restore_path, optimizer=None):
         ckpt = torch.load(restore_path, map_location=self.device, weights_only=False)
         self.load_state_dict(ckpt['net'])
-        if optimizer is not None and 'optimizer' in ckpt:
-            optimizer.load_state_dict(ckpt['optimizer'])
+        if 'optimizer' in ckpt:
+            if optimizer is not None:
+                optimizer.load_state_dict(ckpt['optimizer'])
+            if self._param_objs:
+                self.load_adam_state(ckpt['optimizer'])      # the fused path (tta_step) continues from the same moments
         return optimizer, ckpt.get('train_step', 0)
 
     def save_model(self, checkpoint_path, step, optimizer, meanvar=None):
-        ckpt = {'net': OrderedDict((k, v.clone()) for k, v in self.state_dict().items()), 'train_step': step}
-        if optimizer is not None:
-            ckpt['optimizer'] = optimizer.state_dict()
+        """optimizer = the driver's torch.optim.Adam, or None when the fused `tta_step` path was used (its state is then written in
+        torch.optim.Adam's format, so the reference -- or this class -- restores it into a torch optimiser)"""
+        ckpt = {'net': OrderedDict((k, v.clone()) for k, v in self.state_dict().items()),
+                'optimizer': optimizer.state_dict() if optimizer is not None else self.adam_state_dict(),
+                'train_step': step}
         torch.save(ckpt, checkpoint_path)
 
     def convert_syncbn(self, apex=False):
