@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 from oracle import msgchn_oracle as O
 from golden_util import golden_names, load_golden, case_frame, case_checkpoint, rel, nrel, W_SD, W_SM, W_COS
 from oracle_trace import trace_step, to_nchw
-from test_msgchn_step_gpu import (make_model, report, ZERO_GRAD, eng_adapt_names, weight_tolerance, loss_tolerance, step_loss_tolerance,
+from test_msgchn_step_gpu import (make_model, report, ZERO_GRAD, eng_adapt_names, weight_tolerance, loss_tolerance, step_loss_tolerance, TOL_W,
                                   FWD_NAMES, GRAD_NAMES)
 
 DEV = 'cuda'
@@ -62,7 +62,7 @@ def test_fullsize_steps_match_oracle(case):
         image, sparse, dense = O.synthetic_frame(11, t, n, h, w, dataset)
         model.tta_step(image.to(DEV), sparse.to(DEV), lr, W_SD, W_SM, W_COS)
         got = model.last_losses()
-        res = O.tta_step(sd_o, state, image, sparse, lr=lr, max_input_depth=cap)
+        res = O.tta_step(sd_o, state, image, sparse, lr=lr, max_input_depth=cap, return_grads=True)
         eng = model._last_engine
         assert torch.equal(eng.tensor('filtered_validity').view(n, 1, h, w).cpu(), res['validity']), t
         assert torch.equal(eng.tensor('filtered_depth').view(n, 1, h, w).cpu(), res['sparse_depth']), t
@@ -80,7 +80,20 @@ def test_fullsize_steps_match_oracle(case):
                 continue
             e, upd = nrel(sd_n[k].cpu(), sd_o[k]), nrel(before[k], sd_o[k])
             report('%s step %d lr=%g %-40s weight nrel %.3e  (update/|w| %.3e, error/update %.3f)' % (name, t, lr, k, e, upd, e / max(upd, 1e-30)))
-            assert e < weight_tolerance(upd), (t, k, e, upd)
+            if t == 0:
+                # Adam's FIRST step is -lr * sign(g) (m / sqrt(v) = g / |g|): the two implementations can only differ where the sign of a
+                # gradient component differs, i.e. on components inside the gradient noise of the bf16 operands / L1 sign flips.  Asserted:
+                # few components flip, and every flipped one is a SMALL component of the oracle's gradient (a wrong backward flips large ones)
+                g_o = res['grads'][k].flatten()
+                d_n, d_o = (sd_n[k].cpu() - before[k]).flatten(), (sd_o[k] - before[k]).flatten()
+                flipped = (torch.sign(d_n) != torch.sign(d_o)) & (d_o != 0)
+                frac = float(flipped.float().mean())
+                rms = float(g_o.pow(2).mean().sqrt())
+                worst = float(g_o[flipped].abs().max()) if bool(flipped.any()) else 0.0
+                report('%s step 0 %-40s first Adam step: %.2f %% of the signs differ, largest flipped |g| = %.3f rms(g)' % (name, k, 100 * frac, worst / max(rms, 1e-30)))
+                assert frac < 0.12 and worst < 1.0 * rms, (k, frac, worst, rms)
+            else:
+                assert e < max(TOL_W, 0.25 * upd), (t, k, e, upd)
 
 
 @pytest.mark.parametrize('case', FULL[:1] + FULL[3:4], ids=IDS[:1] + IDS[3:4])
