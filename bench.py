@@ -559,6 +559,7 @@ def run_native(args):
     peaks = load_peaks()
 
     model = ExternalModel_Adapt('msg_chn', 0.0, 100.0, max_input_depth=cap, device=dev)
+    model.model.engine_options = dict((k, int(v)) for k, v in (o.split('=') for o in args.engine_opt))      # dispatch experiments
     model._prepare_head(mode)
     model.load_state_dict(make_checkpoint(args.workload))
     model.set_image_normalization((1 / 255.0,) * 3, (0.0,) * 3)
@@ -677,6 +678,8 @@ def run_native(args):
         'clocks': sampler.summary(),
         'last_losses': losses,
     }
+    if args.engine_opt:
+        line['engine_options'] = args.engine_opt
     gflop_step = {'kitti': 210.5, 'void': 152.8}[args.workload] * args.batch
     line['step_tflops'] = gflop_step / (ms_total / args.steps)
     line['step_tflops_note'] = 'work performed per step (%.1f GFLOP: fwd + required dgrad/wgrad, rgb_encoder(0) cached, SURVEY.md 8d) / ms_per_step' % gflop_step
@@ -706,6 +709,7 @@ def main():
     ap.add_argument('--mode', default='shards', choices=['shards', 'shared'], help='shards: independent sequence shard per GPU, no collective (default); shared: one shared model, NCCL all-reduce of the adapted-parameter gradients (BASELINE.json configs[4])')
     ap.add_argument('--no-graph', dest='graph', action='store_false', help='launch the step kernels eagerly instead of replaying the captured CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip the roofline / cpu_baseline legs (profiling runs)')
+    ap.add_argument('--engine-opt', action='append', default=[], metavar='NAME=VALUE', help='ptta_msgchn_set_option on the engine (dispatch experiments, e.g. tc_min_pixels=1000); not for headline runs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.steps is None:

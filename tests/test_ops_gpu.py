@@ -213,6 +213,26 @@ def test_stem_and_head_conv(ops):
     assert torch.allclose(acc.cpu(), want, rtol=1e-4, atol=1e-4), 'head_conv_const accumulate'
 
 
+@pytest.mark.parametrize('n,h,w', [(1, 8, 12), (2, 24, 40), (1, 37, 258), (2, 9, 600), (1, 88, 304), (1, 352, 1216)])
+def test_head_conv_tc(ops, n, h, w):
+    """32 -> 1 conv on tcgen05 (conv3x3_tc_head_kernel: the conv_tc producer / MMA schedule with N = 3 x 16 and weights carried as a
+    bf16 head + bf16 remainder) vs the fp32 torch conv of the same bf16 input and vs the CUDA-core kernel it replaces; multi-strip,
+    ragged-width and multi-CTA row ranges included."""
+    g = torch.Generator().manual_seed(17 + h)
+    x = bf(torch.relu(torch.randn((n, 32, h, w), generator=g)))
+    wt = torch.randn((1, 32, 3, 3), generator=g) * 0.1
+    add = torch.randn((n, h, w), generator=g)
+    want = F.conv2d(x, wt, torch.tensor([0.25]), padding=1)[:, 0] + add
+    w9 = wt[0].reshape(32, 9).t().contiguous()               # [tap][c]
+    got = ops.head_conv_tc(nhwc(x), w9.to(DEV), 0.25, add.to(DEV))
+    old = ops.head_conv(nhwc(x), w9.to(DEV), 0.25, add.to(DEV), relu_in=False)
+    err = float((got.cpu() - want).abs().max())
+    assert err < 2e-4, err                                   # 288 products of O(0.1): weights exact to 2^-17, fp32 accumulation
+    assert float((got - old).abs().max()) < 2e-4
+    got = ops.head_conv_tc(nhwc(x), w9.to(DEV), 0.0, None)   # no addend, no bias
+    assert float((got.cpu() - (want - add - 0.25)).abs().max()) < 2e-4
+
+
 @pytest.mark.parametrize('n,h,w', [(1, 8, 12), (2, 11, 19), (1, 88, 304)])
 def test_up2_and_adjoints(ops, n, h, w):
     g = torch.Generator().manual_seed(8)

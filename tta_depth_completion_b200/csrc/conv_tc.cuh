@@ -24,6 +24,8 @@ struct ConvTcParams {
     int relu_out;        // store ReLU(result) (producer-side activation for consumers that only read ReLU(x))
     int strips, segs_y, rows_per_seg, total_segs;      // stride-2 kernel: fixed row segments per strip
     int rows_per_cta, total_rows;                      // stride-1 kernel: contiguous range of the (image, strip, row) sequence per CTA
+    // 32 -> 1 channel form (conv3x3_tc_head_kernel): fp32 output plane, optional fp32 addend plane, scalar bias
+    float* out_f32; const float* add_f32; float bias0;
 };
 
 
@@ -177,10 +179,13 @@ __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.b
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 }  // namespace tc
 
-__global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in,
-                                                                           const __grid_constant__ CUtensorMap tmap_out,
-                                                                           const __grid_constant__ CUtensorMap tmap_out2, const ConvTcParams p) {
+// NC = accumulator columns per output row and pixel parity: 32 = the 32 -> 32 convolution; 16 = the 32 -> 1 prediction-layer form
+// (conv3x3_tc_head_kernel below: same producer and MMA schedule with N = 3 x 16, another epilogue)
+template <int NC>
+__device__ __forceinline__ void conv3x3_tc_body(const CUtensorMap& tmap_in, const CUtensorMap& tmap_out, const CUtensorMap& tmap_out2,
+                                                const ConvTcParams& p) {
     typedef ConvTcCfg C;
+    constexpr uint32_t W_BYTES_NC = 9 * NC * 64;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -228,9 +233,9 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
     if (warp == 0) {
         // =========================== TMA producer ===========================
         if (elect_one()) {
-            tc::mbar_arrive_expect_tx(w_full, C::W_BYTES);
+            tc::mbar_arrive_expect_tx(w_full, W_BYTES_NC);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(w_s), "l"(p.w), "r"((uint32_t)C::W_BYTES), "r"(w_full) : "memory");
+                         ::"r"(w_s), "l"(p.w), "r"(W_BYTES_NC), "r"(w_full) : "memory");
         }
         __syncwarp();
         uint32_t r = 0;
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
                 if (elect_one()) {
                     tc::mbar_arrive_expect_tx(row_full + 8 * slot, C::ROW_BYTES);
                     tc::tma_load_4d(rows_s + slot * C::SLOT_BYTES, &tmap_in, row_full + 8 * slot, 0, sx * 128 - 1, yy, n);
-                    if (yy >= y0 && yy < y1 && (p.mask || p.add || p.add2)) {       // the epilogue reads these rows ~3 input rows from now
+                    if (NC == 32 && yy >= y0 && yy < y1 && (p.mask || p.add || p.add2)) {       // the epilogue reads these rows ~3 input rows from now
                         const size_t roff = (((size_t)n * p.H + yy) * p.W + sx * 256) * 32;
                         const uint32_t rbytes = (uint32_t)min(256, p.W - sx * 256) * 64u;
                         if (p.mask) tc::l2_prefetch(p.mask + roff, rbytes);
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
         }
     } else if (warp == 1) {
         // =========================== MMA issuer (converged warp, one elected lane issues) ===========================
-        const uint32_t idesc32 = tc::make_idesc_bf16(128, 32), idesc64 = tc::make_idesc_bf16(128, 64), idesc96 = tc::make_idesc_bf16(128, 96);
+        const uint32_t idesc32 = tc::make_idesc_bf16(128, NC), idesc64 = tc::make_idesc_bf16(128, 2 * NC), idesc96 = tc::make_idesc_bf16(128, 3 * NC);
         const uint64_t da0 = make_desc_sw128(0), db0 = tc::make_desc_sw64(0, 512, 0);
         const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32);
         const uint32_t a_lo0 = (uint32_t)da0 + (rows_s >> 4), b_lo0 = (uint32_t)db0 + (w_s >> 4);
@@ -289,24 +294,24 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
                         for (int ks = 0; ks < 2; ++ks) {
                             const bool first = (kx | ks) == 0;
                             int j_lo = max(i - 2, 0), j_hi = min(i, nrows - 1);
-                            const uint32_t b_tap = b_lo0 + kx * 96 * 4 + ks * 2;
+                            const uint32_t b_tap = b_lo0 + kx * (3 * NC) * 4 + ks * 2;
                             if (first && i < nrows) {
                                 const uint32_t s = (t_base + i) % C::NSLOT;
-                                const uint32_t d_even = tmem_base + s * 32, d_odd = d_even + 32 * C::NSLOT;
-                                tc::umma_f16_split<false>(d_even, a_lo + ae, a_hi, b_tap + 64 * 4, b_hi, idesc32);
-                                tc::umma_f16_split<false>(d_odd, a_lo + ao, a_hi, b_tap + 64 * 4, b_hi, idesc32);
+                                const uint32_t d_even = tmem_base + s * NC, d_odd = d_even + NC * C::NSLOT;
+                                tc::umma_f16_split<false>(d_even, a_lo + ae, a_hi, b_tap + (2 * NC) * 4, b_hi, idesc32);
+                                tc::umma_f16_split<false>(d_odd, a_lo + ao, a_hi, b_tap + (2 * NC) * 4, b_hi, idesc32);
                                 j_hi = i - 1;
                             }
                             int cnt = j_hi - j_lo + 1;                          // 0..3 output rows accumulate this input row
-                            int b_row = (2 - i + j_lo) * 32;                    // first stacked-weight row: ky = i - j_lo
+                            int b_row = (2 - i + j_lo) * NC;                    // first stacked-weight row: ky = i - j_lo
                             uint32_t s0 = (t_base + j_lo) % C::NSLOT;
                             while (cnt > 0) {
                                 const int c1 = min(cnt, C::NSLOT - (int)s0);    // contiguous TMEM slots before the ring wraps
                                 const uint32_t idesc = c1 == 3 ? idesc96 : (c1 == 2 ? idesc64 : idesc32);
-                                const uint32_t d_even = tmem_base + s0 * 32, d_odd = d_even + 32 * C::NSLOT;
+                                const uint32_t d_even = tmem_base + s0 * NC, d_odd = d_even + NC * C::NSLOT;
                                 tc::umma_f16_split<true>(d_even, a_lo + ae + ks * 2, a_hi, b_tap + b_row * 4, b_hi, idesc);
                                 tc::umma_f16_split<true>(d_odd, a_lo + ao + ks * 2, a_hi, b_tap + b_row * 4, b_hi, idesc);
-                                cnt -= c1; b_row += c1 * 32; s0 = 0;
+                                cnt -= c1; b_row += c1 * NC; s0 = 0;
                             }
                         }
                     }
@@ -316,6 +321,35 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
                 __syncwarp();
             }
             t_base += nrows;
+        }
+    } else if (NC == 16) {
+        // =========================== epilogue, 32 -> 1 form ===========================
+        // accumulator column 0 holds the dot product with the bf16 head of the fp32 weights, column 1 with their bf16 remainder
+        // (pack_conv_weight_tc_head_kernel): their sum carries the weights to 16 mantissa bits, as the fp32 FMA kernel it replaces
+        const int q = warp & 3;
+        const int par = (warp - 2) >> 2;
+        uint32_t t = 0;
+        for (int lin = lin0; lin < lin1;) {
+            const int col = lin / p.H, y0 = lin - col * p.H, y1 = min(p.H, y0 + (lin1 - lin));
+            const int n = col / p.strips, sx = col - n * p.strips;
+            lin += y1 - y0;
+            const int xw = sx * 256 + q * 64;
+            const int vp = min(32, (p.W - xw) / 2);
+            const bool act = lane < vp;
+            for (int y = y0; y < y1; ++y, ++t) {
+                const uint32_t sl = t % C::NSLOT;
+                const size_t idx = ((size_t)n * p.H + y) * p.W + xw + 2 * lane + par;
+                float addv = p.bias0;
+                if (p.add_f32 != nullptr && act) addv += p.add_f32[idx];
+                tc::mbar_wait(slot_full + 8 * sl, (t / C::NSLOT) & 1);
+                tc::tc_fence_after();
+                uint32_t v0, v1;
+                tmem_ld2(tmem_base + ((uint32_t)(q * 32) << 16) + par * NC * C::NSLOT + sl * NC, v0, v1);
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(slot_empty + 8 * sl);
+                if (act) p.out_f32[idx] = (__uint_as_float(v0) + __uint_as_float(v1)) + addv;
+            }
         }
     } else {
         // =========================== epilogue ===========================
@@ -351,7 +385,7 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
                 tc::mbar_wait(slot_full + 8 * sl, (t / C::NSLOT) & 1);
                 tc::tc_fence_after();
                 uint32_t v[32];
-                tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + par * 32 * C::NSLOT + sl * 32, v);
+                tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + par * NC * C::NSLOT + sl * NC, v);
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(slot_empty + 8 * sl);
@@ -407,6 +441,44 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
     }
 }
 
+__global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in,
+                                                                           const __grid_constant__ CUtensorMap tmap_out,
+                                                                           const __grid_constant__ CUtensorMap tmap_out2, const ConvTcParams p) {
+    conv3x3_tc_body<32>(tmap_in, tmap_out, tmap_out2, p);
+}
+
+// 32 -> 1 channel 3x3 s1 p1 convolution with an fp32 output plane: the prediction layer prdct.3 (network_exp_msg_chn_adapt.py:289)
+// and, with flipped plane-1 weights, the data gradient of a two-plane stem with respect to its prediction input.  The layer reads
+// 64 B and writes 4 B per pixel: it is bound by the read of the 32-channel map, which the tensor-core form streams through TMA exactly
+// once (the CUDA-core form staged halo tiles and spent 288 shared-memory-fed FMAs per pixel: 22 us at 352x1216).
+__global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_head_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTcParams p) {
+    conv3x3_tc_body<16>(tmap_in, tmap_in, tmap_in, p);
+}
+
+// fp32 [tap][cin] (tap = ky*3 + kx) -> the head kernel's weight image: row = kx*48 + (2-ky)*16 + c, 64 B per row (32 cin), SWIZZLE_64B
+// chunk order; c = 0: bf16(w), c = 1: bf16(w - bf16(w)), c = 2..15: zero
+__global__ void pack_conv_weight_tc_head_kernel(const float* __restrict__ w, bf16* __restrict__ image) {
+    PDL_SYNC();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * 16 * 4) return;
+    const int row = i >> 2, c = i & 3;
+    const int kx = row / 48, rem = row - kx * 48;
+    const int ky = 2 - rem / 16, co = rem & 15;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (co < 2) {
+        uint32_t* u = reinterpret_cast<uint32_t*>(&v);
+        const float* src = w + (ky * 3 + kx) * 32 + c * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = src[2 * j], b = src[2 * j + 1];
+            const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+            if (co == 1) { a -= ah; b -= bh; } else { a = ah; b = bh; }
+            u[j] = pack_bf162(a, b);
+        }
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(image) + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)) = v;
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------
 // NHWC bf16 [N,H,W,C] activation, box = {C, box_w, 1, 1}, SWIZZLE_64B (C = 32) / 128B (C = 64), zero fill outside
 inline int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int N, int H, int W, int Cc, int box_w) {
@@ -455,17 +527,8 @@ inline int conv_tc_tmap(const bf16* in, int N, int H, int W, const CUtensorMap**
     return 0;
 }
 
-inline int launch_conv_tc(const bf16* in, ConvTcParams p, cudaStream_t st) {
-    typedef ConvTcCfg C;
-    static int sms = 0;
-    if (!sms) {
-        PTTA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        int dev = 0;
-        PTTA_CUDA(cudaGetDevice(&dev));
-        PTTA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    PTTA_CHECK(conv_tc_supported(p.N, p.H, p.W), "conv3x3_tc: W=%d must be even", p.W);
-    PTTA_CHECK(!p.relu_in, "conv3x3_tc: ReLU-on-load is not supported (producers store ReLU(x): relu_out)");
+// work split shared by the stride-1 kernels: strips of 256 pixels, a contiguous range of (image, strip, row) per CTA
+inline int conv_tc_split(ConvTcParams& p, int sms) {
     p.strips = cdiv(p.W, 256);
     p.total_rows = p.N * p.strips * p.H;
     // rows per CTA: minimise waves x (rows + halo + fixed cost) over the splits that fill the machine
@@ -478,7 +541,41 @@ inline int launch_conv_tc(const bf16* in, ConvTcParams p, cudaStream_t st) {
         if (ctas <= 1) break;
     }
     p.rows_per_cta = best_rows;
-    const int grid = cdiv(p.total_rows, p.rows_per_cta);
+    return cdiv(p.total_rows, p.rows_per_cta);
+}
+
+// out_f32[n][y][x] = bias0 [+ add_f32[n][y][x]] + sum_taps in[n][y+ky-1][x+kx-1][:] . w[tap][:]   (p.w = image of pack_conv_weight_tc_head_kernel)
+inline int launch_conv_tc_head(const bf16* in, ConvTcParams p, cudaStream_t st) {
+    typedef ConvTcCfg C;
+    static int sms = 0;
+    if (!sms) {
+        PTTA_CUDA(cudaFuncSetAttribute(conv3x3_tc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        int dev = 0;
+        PTTA_CUDA(cudaGetDevice(&dev));
+        PTTA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    PTTA_CHECK(conv_tc_supported(p.N, p.H, p.W), "conv3x3_tc_head: W=%d must be even", p.W);
+    PTTA_CHECK(p.out_f32 != nullptr && p.w != nullptr, "conv3x3_tc_head: output / weight image missing");
+    const int grid = conv_tc_split(p, sms);
+    const CUtensorMap* m = nullptr;
+    PTTA_TRY(conv_tc_tmap(in, p.N, p.H, p.W, &m));
+    const CUtensorMap map_in = *m;
+    launch_k(conv3x3_tc_head_kernel, grid, C::THREADS, C::SMEM, st, map_in, p);
+    return check_launch("conv3x3_tc_head");
+}
+
+inline int launch_conv_tc(const bf16* in, ConvTcParams p, cudaStream_t st) {
+    typedef ConvTcCfg C;
+    static int sms = 0;
+    if (!sms) {
+        PTTA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        int dev = 0;
+        PTTA_CUDA(cudaGetDevice(&dev));
+        PTTA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    PTTA_CHECK(conv_tc_supported(p.N, p.H, p.W), "conv3x3_tc: W=%d must be even", p.W);
+    PTTA_CHECK(!p.relu_in, "conv3x3_tc: ReLU-on-load is not supported (producers store ReLU(x): relu_out)");
+    const int grid = conv_tc_split(p, sms);
     // copies: the cache may be cleared by a later lookup, the kernel takes the maps by value
     const CUtensorMap* m = nullptr;
     PTTA_TRY(conv_tc_tmap(in, p.N, p.H, p.W, &m));

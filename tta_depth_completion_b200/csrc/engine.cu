@@ -97,6 +97,7 @@ struct StemLayer {   // init.0: {1,2,3} -> 32
     float wk[3 * 9 * 32];         // ... re-ordered [ci][tap][co]: passed by value to stem_convc_kernel (constant-bank operands)
     float bk[32];
     float dk[9 * 32];             // host copy of dgrad_ch1 ([9][32]) for head_convc_kernel
+    bf16* img_dgrad1 = nullptr;   // tcgen05 weight image of dgrad_ch1 (conv3x3_tc_head_kernel)
 };
 struct HeadLayer {   // prdct.3: 32 -> 1
     std::string name;
@@ -107,6 +108,7 @@ struct HeadLayer {   // prdct.3: 32 -> 1
     std::vector<float> raw_host;  // host copy of w_dgrad ([32][1][3][3], flipped) ...
     float wdk[9 * 32];            // ... re-ordered [tap][co] for stem_convc_kernel<1>
     float wfk[9 * 32];            // host copy of w_fwd ([9][32]) for head_convc_kernel
+    bf16* img_fwd = nullptr;      // tcgen05 weight image of w_fwd (conv3x3_tc_head_kernel)
 };
 struct BnState {     // per call-site statistics
     float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *uvar = nullptr;
@@ -159,7 +161,7 @@ struct ptta_msgchn {
     cudaEvent_t ev_e3 = nullptr, ev_mlp = nullptr, ev_lossg = nullptr, ev_headb = nullptr, ev_gmg = nullptr, ev_wg2 = nullptr;
     bool two_streams = true;
     bool mlp_on_st3 = false;        // set by forward_impl for the duration of the real cascade
-    bool tc_enabled = true; long long tc_min_pixels = 20000, tc_s2_min_pixels = 16000, tc_t2_min_pixels = 6000;
+    bool tc_enabled = true; long long tc_min_pixels = 6000, tc_s2_min_pixels = 6000, tc_t2_min_pixels = 1500, tc_head_min_pixels = 20000;
     bool fuse_dec_sums = true;      // experiment switches (environment: PTTA_NO_TC, PTTA_NO_FUSE_DEC_SUMS, PTTA_ONE_STREAM)
     Arena arena;
     size_t ws_bytes = 0;
@@ -175,6 +177,8 @@ struct ptta_msgchn {
     ConvLayer meta1, meta2;          // 2layers: 32->128 (no bias), 128->32 ; 1layer: meta1 = 32->32
     BnLayer metaBn1, metaBn2;
     LinearLayer proj0, proj3, pred0, pred3;
+    bf16* projpred_pack = nullptr; float* projpred_bias = nullptr;   // pred.0 o proj.3 as one Linear layer (zero-image rows: emb = pred(proj(z)))
+    bool fuse_projpred = true;
     BnLayer projBn, predBn;
     std::vector<std::string> adapt_names;
 
@@ -308,6 +312,7 @@ struct ptta_msgchn {
     }
     void plan_enc_w(EncW& E) {
         E.init0.dgrad_ch1 = allocv<float>(288);
+        E.init0.img_dgrad1 = allocv<bf16>(9 * 16 * 32);
         plan_conv(E.init2);
         ConvLayer* ls[8] = {&E.e1a, &E.e1b, &E.e2a, &E.e2b, &E.e3a, &E.e3b, &E.e4a, &E.e4b};
         for (int k = 0; k < 2 * E.nenc; ++k) plan_conv(*ls[k]);
@@ -315,6 +320,7 @@ struct ptta_msgchn {
     void plan_dec_w(DecW& D) {
         plan_conv(D.d2a); plan_conv(D.d2b); plan_conv(D.d1a); plan_conv(D.d1b); plan_conv(D.p1);
         D.p3.w_fwd = allocv<float>(288); D.p3.w_dgrad = allocv<float>(288);
+        D.p3.img_fwd = allocv<bf16>(9 * 16 * 32);
     }
     void plan_enc_act(EncAct& A, const std::string& tag, int h, int w) {
         A.a0 = alloc32((tag + ".a0").c_str(), h, w); A.x0 = alloc32((tag + ".x0").c_str(), h, w);
@@ -397,6 +403,7 @@ struct ptta_msgchn {
             plan_branch(zero, "zero", false);
             auto lin = [&](LinearLayer& L) { L.pack = allocv<bf16>((size_t)L.in * L.out); L.pack_t = allocv<bf16>((size_t)L.in * L.out); };
             lin(proj0); lin(proj3); lin(pred0); lin(pred3);
+            projpred_pack = allocv<bf16>((size_t)512 * 512); projpred_bias = allocv<float>(512);
             size_t rm = (size_t)R * 512;
             h_an2 = allocv<bf16>(rm);
             h_a0z = allocv<bf16>(rm); h_a0r = allocv<bf16>(rm); h_an = allocv<bf16>(rm); h_pz = allocv<bf16>(rm); h_q0 = allocv<bf16>(rm);
@@ -527,6 +534,8 @@ struct ptta_msgchn {
         if (E.init0.cin == 2) {
             launch_k(pack_head_weight_kernel, 2, 256, 0, st, E.init0.w + 9, E.init0.dgrad_ch1, 18, 1);
             PTTA_TRY(check_launch("pack_stem_dgrad"));
+            launch_k(pack_conv_weight_tc_head_kernel, cdiv(9 * 16 * 4, 256), 256, 0, st, E.init0.dgrad_ch1, E.init0.img_dgrad1);
+            PTTA_TRY(check_launch("pack_stem_dgrad_tc"));
         }
         PTTA_TRY(pack_conv(E.init2));
         ConvLayer* ls[8] = {&E.e1a, &E.e1b, &E.e2a, &E.e2b, &E.e3a, &E.e3b, &E.e4a, &E.e4b};
@@ -553,6 +562,8 @@ struct ptta_msgchn {
         PTTA_TRY(pack_conv(D.p1));
         launch_k(pack_head_weight_kernel, 2, 256, 0, st, D.p3.w, D.p3.w_fwd, 9, 0);
         PTTA_TRY(check_launch("pack_head"));
+        launch_k(pack_conv_weight_tc_head_kernel, cdiv(9 * 16 * 4, 256), 256, 0, st, D.p3.w_fwd, D.p3.img_fwd);
+        PTTA_TRY(check_launch("pack_head_tc"));
         launch_k(pack_flip9_kernel, 2, 256, 0, st, D.p3.w, D.p3.w_dgrad, 32);
         PTTA_TRY(check_launch("pack_head_dgrad"));
         PTTA_CUDA(cudaMemcpyAsync(&D.p3.bias_host, D.p3.b, sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -582,6 +593,9 @@ struct ptta_msgchn {
         PTTA_TRY(pack_adapted());
         if (has_heads) {
             PTTA_TRY(pack_linear(proj0)); PTTA_TRY(pack_linear(proj3)); PTTA_TRY(pack_linear(pred0)); PTTA_TRY(pack_linear(pred3));
+            launch_k(fuse_linear_kernel, dim3(cdiv(proj3.in, 256), pred0.out), 256, 0, st, pred0.w, pred0.b, proj3.w, proj3.b, projpred_pack,
+                     projpred_bias, pred0.out, proj3.out, proj3.in);
+            PTTA_TRY(check_launch("fuse_linear"));
         }
         PTTA_CUDA(cudaStreamSynchronize(st));   // bias_host / host weight copies
         finish_host_weights(rgbW); finish_host_weights(enc1W); finish_host_weights(enc2W); finish_host_weights(enc3W);
@@ -724,6 +738,15 @@ struct ptta_msgchn {
         launch_stem(p, S.cin, st);
         return check_launch("stem_conv");
     }
+    bool use_tc_head(const Map1& m) const {
+        return tc_enabled && conv_tc_supported(m.n, m.h, m.w) && (long long)m.n * m.h * m.w >= tc_head_min_pixels;
+    }
+    // the 32 -> 1 convolution on the tensor cores (the input already holds ReLU(.) where the layer reads it through one)
+    int head_conv_tc(const bf16* in, const bf16* image, float bias, const float* add, const Map1& out) {
+        ConvTcParams p; memset(&p, 0, sizeof(p));
+        p.w = image; p.N = out.n; p.H = out.h; p.W = out.w; p.out_f32 = out.p; p.add_f32 = add; p.bias0 = bias;
+        return launch_conv_tc_head(in, p, st);
+    }
     // prediction layer: out = conv32->1(relu(h)) + bias [+ add]
     int head_convv(const bf16* in, const float* wk, float bias, const float* add, const Map1& out, int relu_in) {
         HeadCParams c; memset(&c, 0, sizeof(c));
@@ -733,6 +756,7 @@ struct ptta_msgchn {
         return 0;
     }
     int head_fwd(const HeadLayer& Hd, const Map32& h, const float* add, const Map1& out) {
+        if (use_tc_head(out)) return head_conv_tc(h.p, Hd.img_fwd, Hd.bias_host, add, out);      // h is stored as ReLU(h) by prdct.1
         PTTA_TRY(head_convv(h.p, Hd.wfk, Hd.bias_host, add, out, 1));
         return check_launch("head_conv");
     }
@@ -754,6 +778,7 @@ struct ptta_msgchn {
     }
     // gradient wrt input plane 1 of a 2-plane stem: out = conv32->1(g_a0; flipped plane-1 weights) + add
     int stem_dgrad_ch1(const StemLayer& S, const Map32& ga0, const float* add, const Map1& out) {
+        if (use_tc_head(out)) return head_conv_tc(ga0.p, S.img_dgrad1, 0.f, add, out);
         PTTA_TRY(head_convv(ga0.p, S.dk, 0.f, add, out, 0));
         return check_launch("stem_dgrad");
     }
@@ -984,8 +1009,19 @@ struct ptta_msgchn {
         PTTA_TRY(run_meta(zero, true, defer_meta_running));
         if (defer_meta_running && two_layers) PTTA_CUDA(cudaEventRecord(ev_zmeta, st));
         PTTA_TRY(run_cascade(zero, false));
-        PTTA_TRY(mlp(proj0, projBn, bnProjZ, proj3, zero.e3.x2.p, 32, h_a0z, h_pz, true, h_an2, ev_projbn));
-        return mlp(pred0, predBn, bnPred, pred3, h_pz, 512, h_q0, emb, true, h_an2);
+        if (!fuse_projpred) {
+            PTTA_TRY(mlp(proj0, projBn, bnProjZ, proj3, zero.e3.x2.p, 32, h_a0z, h_pz, true, h_an2, ev_projbn));
+            return mlp(pred0, predBn, bnPred, pred3, h_pz, 512, h_q0, emb, true, h_an2);
+        }
+        // proj.3 and pred.0 are two Linear layers with nothing between them: one GEMM with W = W_pred0 W_proj3 (pack time, fp32)
+        PTTA_TRY(gemm(zero.e3.x2.p, proj0.pack, h_a0z, proj0.b, R, proj0.out, 32));
+        PTTA_TRY(bn_forward_stats(projBn, bnProjZ, h_a0z, R, true));
+        PTTA_CUDA(cudaEventRecord(ev_projbn, st));
+        PTTA_TRY(bn_apply(h_a0z, nullptr, h_an2, R, proj0.out, bnProjZ, 1));
+        PTTA_TRY(gemm(h_an2, projpred_pack, h_q0, projpred_bias, R, pred0.out, proj3.in));
+        PTTA_TRY(bn_forward_stats(predBn, bnPred, h_q0, R, true));
+        PTTA_TRY(bn_apply(h_q0, nullptr, h_an2, R, pred0.out, bnPred, 1));
+        return gemm(h_an2, pred3.pack, emb, pred3.b, R, pred3.out, pred3.in);
     }
 
     // ---- losses (src/external_model_adapt.py:371-441) ----------------------------------------------------
@@ -1344,6 +1380,19 @@ int ptta_head_conv_const(const void* in, const float* weight_host_9x32, float bi
     return check_launch("head_conv_const");
 }
 
+int ptta_pack_head_weight_tc(const float* weight_9x32, void* image, ptta_stream_t stream) {
+    PTTA_CHECK(weight_9x32 && image, "pack_head_weight_tc: null argument");
+    launch_k(pack_conv_weight_tc_head_kernel, cdiv(9 * 16 * 4, 256), 256, 0, (cudaStream_t)stream, weight_9x32, (bf16*)image);
+    return check_launch("pack_head_weight_tc");
+}
+
+int ptta_head_conv_tc(const void* in, const void* wimage, float bias, const float* add, float* out, int n, int h, int ww, ptta_stream_t stream) {
+    PTTA_CHECK(in && wimage && out, "head_conv_tc: null argument");
+    ConvTcParams p; memset(&p, 0, sizeof(p));
+    p.w = (const bf16*)wimage; p.N = n; p.H = h; p.W = ww; p.out_f32 = out; p.add_f32 = add; p.bias0 = bias;
+    return launch_conv_tc_head((const bf16*)in, p, (cudaStream_t)stream);
+}
+
 int ptta_up2_1ch(const float* a, const float* b, const float* c, float* out, int n, int h, int w, ptta_stream_t stream) {
     long long tot = (long long)n * h * w * 4;
     launch_k(up2_1ch_kernel, cdiv(tot, 256), 256, 0, (cudaStream_t)stream, a, b, c, out, n, h, w);
@@ -1602,7 +1651,7 @@ int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepa
     if (getenv("PTTA_NO_TC")) e->tc_enabled = false;
     if (getenv("PTTA_NO_FUSE_DEC_SUMS")) e->fuse_dec_sums = false;
     if (getenv("PTTA_ONE_STREAM")) e->two_streams = false;
-    if (const char* v = getenv("PTTA_TC_MIN_PIXELS")) e->tc_min_pixels = e->tc_s2_min_pixels = e->tc_t2_min_pixels = atoll(v);
+    if (const char* v = getenv("PTTA_TC_MIN_PIXELS")) e->tc_min_pixels = e->tc_s2_min_pixels = e->tc_t2_min_pixels = e->tc_head_min_pixels = atoll(v);
     e->define_model();
     e->plan();
     *out = e;
@@ -1614,9 +1663,11 @@ int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value) {
     if (k == "tc_min_pixels") e->tc_min_pixels = value;                 // smallest map (pixels) the stride-1 tcgen05 conv takes
     else if (k == "tc_s2_min_pixels") e->tc_s2_min_pixels = value;      // same for the stride-2 tcgen05 conv
     else if (k == "tc_t2_min_pixels") e->tc_t2_min_pixels = value;      // same for the transposed stride-2 tcgen05 conv (INPUT pixels)
+    else if (k == "tc_head_min_pixels") e->tc_head_min_pixels = value;  // same for the 32 -> 1 tcgen05 conv (prediction layers, stem data gradients)
     else if (k == "tc_enabled") e->tc_enabled = value != 0;
     else if (k == "two_streams") e->two_streams = value != 0;
     else if (k == "fuse_dec_sums") e->fuse_dec_sums = value != 0;
+    else if (k == "fuse_projpred") e->fuse_projpred = value != 0;
     else PTTA_CHECK(false, "set_option: unknown option '%s'", name);
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }   // a captured step bakes the dispatch in
     return 0;

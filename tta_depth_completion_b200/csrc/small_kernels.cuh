@@ -1379,6 +1379,25 @@ __global__ void pack_matrix_kernel(const float* __restrict__ src, bf16* __restri
     dst[idx] = __float2bfloat16_rn(src[(size_t)r * s_r + (size_t)c * s_c]);
 }
 // head conv weights: dst[tap][c] = src[c*s_c + tap'] (fp32)
+// Two Linear layers with nothing between them (proj.3 then pred.0: network_exp_msg_chn_adapt.py:1089-1098, emb = pred(proj(z))) are ONE
+// Linear layer: W = W2 W1, b = W2 b1 + b2.  Computed in fp32 at pack time (both layers are frozen), rounded to bf16 once.
+// out[o][i] = sum_k w2[o][k] w1[k][i];  launch: grid (cdiv(n_in, 256), n_out), block 256
+__global__ void fuse_linear_kernel(const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w1,
+                                   const float* __restrict__ b1, bf16* __restrict__ w_out, float* __restrict__ b_out, int n_out, int n_mid, int n_in) {
+    PDL_SYNC();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, o = blockIdx.y;
+    if (i >= n_in) return;
+    const float* r2 = w2 + (size_t)o * n_mid;
+    float acc = 0.f;
+    for (int k = 0; k < n_mid; ++k) acc = fmaf(__ldg(r2 + k), __ldg(w1 + (size_t)k * n_in + i), acc);
+    w_out[(size_t)o * n_in + i] = __float2bfloat16_rn(acc);
+    if (i == 0) {
+        float bb = b2[o];
+        for (int k = 0; k < n_mid; ++k) bb = fmaf(r2[k], b1[k], bb);
+        b_out[o] = bb;
+    }
+}
+
 __global__ void pack_head_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int s_c, int flip) {
     PDL_SYNC();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;

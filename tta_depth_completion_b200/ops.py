@@ -219,6 +219,19 @@ def head_conv_const(x, weight_9x32, bias=0.0, add=None, relu_in=True, out=None, 
     return out
 
 
+def head_conv_tc(x, weight_9x32, bias=0.0, add=None, out=None):
+    """32 -> 1 conv on tcgen05 (no ReLU-on-load: pass ReLU(x) where the layer reads its input through one)"""
+    _need(x, torch.bfloat16, 'x')
+    _need(weight_9x32, torch.float32, 'weight')
+    n, h, w, _ = x.shape
+    image = torch.empty(9 * 16 * 32, dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().ptta_pack_head_weight_tc(ptr(weight_9x32), ptr(image), _stream()), 'pack_head_weight_tc')
+    if out is None:
+        out = torch.empty((n, h, w), dtype=torch.float32, device=x.device)
+    check(_lib.lib().ptta_head_conv_tc(ptr(x), ptr(image), float(bias), ptr(add), ptr(out), n, h, w, _stream()), 'head_conv_tc')
+    return out
+
+
 def head_conv(x, weight_9x32, bias=0.0, add=None, relu_in=True, out=None, accumulate=False):
     _need(x, torch.bfloat16, 'x')
     _need(weight_9x32, torch.float32, 'weight')
