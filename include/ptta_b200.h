@@ -89,6 +89,12 @@ int ptta_head_conv(const void* in_bf16, const float* weight_9x32, float bias, co
 /* same with the [9][32] weight given as a HOST array (by-value kernel parameters, constant-bank FMA operands) */
 int ptta_head_conv_const(const void* in_bf16, const float* weight_host_9x32, float bias, const float* add, float* out,
                          int n, int h, int w, int relu_in, int accumulate, ptta_stream_t stream);
+/* {1,2,3} -> 32 stem on tcgen05 (stem_tc_kernel: operand tiles built by the CUDA cores as bf16 head + remainder, six MMAs per 128 pixels);
+ * weight: fp32 [32][cin][3][3] device, or NULL when image_scratch still holds the packed weights of an earlier call;
+ * image_scratch: 4 096 bytes of device memory for the packed weights; any h, w */
+int ptta_stem_conv_tc(const float* const* planes, const long long* batch_strides, const float* scale, const float* shift, int cin,
+                      const float* weight, const float* bias, const void* mask_bf16, void* out_bf16, void* image_scratch, int relu_out,
+                      int n, int h, int w, ptta_stream_t stream);
 /* the same layer on tcgen05 (conv3x3_tc_head_kernel; the input must already hold ReLU(.) where the layer reads it through one):
  * pack: fp32 [9][32] device weights -> 9 216-byte weight image (bf16 head + bf16 remainder of every weight);
  * run: out[n][y][x] = bias [+ add[n][y][x]] + conv(in) ; w must be even */

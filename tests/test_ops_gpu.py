@@ -213,6 +213,31 @@ def test_stem_and_head_conv(ops):
     assert torch.allclose(acc.cpu(), want, rtol=1e-4, atol=1e-4), 'head_conv_const accumulate'
 
 
+@pytest.mark.parametrize('n,h,w', [(1, 8, 12), (2, 11, 19), (1, 37, 258), (1, 88, 304), (1, 352, 1216)])
+@pytest.mark.parametrize('cin', [1, 2, 3])
+def test_stem_conv_tc(ops, cin, n, h, w):
+    """{1,2,3} -> 32 stem on tcgen05 (stem_tc_kernel: thread-built bf16 head + remainder operand tiles, six MMAs per 128 pixels, bulk store)
+    vs the fp32 torch conv and vs the CUDA-core kernel it replaces; odd widths, partial last tile, multi-tile CTAs, scale / shift folding,
+    and the masked no-bias form the prediction layers' data gradient uses."""
+    g = torch.Generator().manual_seed(31 + cin + h)
+    x = torch.randn((n, cin, h, w), generator=g) * 20.0                       # depth-like magnitudes: the head/remainder split has to hold
+    wt = torch.randn((32, cin, 3, 3), generator=g) * 0.3
+    b = torch.randn((32,), generator=g) * 0.1
+    scale, shift = [0.5, 2.0, 1.0][:cin], [0.25, -1.0, 0.0][:cin]
+    xn = x * torch.tensor(scale).view(1, cin, 1, 1) + torch.tensor(shift).view(1, cin, 1, 1)
+    want = F.relu(F.conv2d(xn, wt, b, padding=1))
+    planes = [x[:, c].contiguous().to(DEV) for c in range(cin)]
+    got = ops.stem_conv_tc(planes, wt.to(DEV), b.to(DEV), scale=scale, shift=shift, relu_out=True)
+    assert_close_bf16(nchw(got), bf(want), 'stem_tc cin=%d' % cin, ulps=2.0)
+    old = ops.stem_conv(planes, wt.to(DEV), b.to(DEV), scale=scale, shift=shift)
+    assert_close_bf16(nchw(got), torch.relu(nchw(old).float()), 'stem_tc vs stem cin=%d' % cin, ulps=2.0)
+    if cin == 1:                                                             # data-gradient form: mask, no bias, no ReLU
+        mask = bf(torch.randn((n, 32, h, w), generator=g))
+        want = F.conv2d(x, wt, None, padding=1) * (mask > 0).float()
+        got = ops.stem_conv_tc(planes, wt.to(DEV), None, mask=nhwc(mask), relu_out=False)
+        assert_close_bf16(nchw(got), bf(want), 'stem_tc masked', ulps=2.0)
+
+
 @pytest.mark.parametrize('n,h,w', [(1, 8, 12), (2, 24, 40), (1, 37, 258), (2, 9, 600), (1, 88, 304), (1, 352, 1216)])
 def test_head_conv_tc(ops, n, h, w):
     """32 -> 1 conv on tcgen05 (conv3x3_tc_head_kernel: the conv_tc producer / MMA schedule with N = 3 x 16 and weights carried as a

@@ -44,7 +44,28 @@ def stemc(cin, wt, mask):
 
 
 w9h = w9.cpu().contiguous()
+img_tc = {c: torch.empty(2048, dtype=torch.bfloat16, device=dev) for c in (1, 2, 3)}
+head_img = torch.empty(9 * 16 * 32, dtype=torch.bfloat16, device=dev)
+check(L.ptta_pack_head_weight_tc(ptr(w9), ptr(head_img), None), 'pack_head_tc')
+
+
+def stemtc(cin, wt, mask):
+    first = [True]
+    def f(i, s):
+        im = imgs[i % R]
+        planes = (ctypes.c_void_p * 3)(im.data_ptr(), im.data_ptr() + 4 * hw, im.data_ptr() + 8 * hw)
+        strides = (ctypes.c_longlong * 3)(3 * hw, 3 * hw, 3 * hw)
+        check(L.ptta_stem_conv_tc(planes, strides, sc, sh, cin, ptr(wt) if first[0] else None, ptr(b), ptr(maps[(i + 1) % R]) if mask else None, ptr(outs[i % R]),
+                                  ptr(img_tc[cin]), 0 if mask else 1, n, h, w, s), 'stem_tc')
+        first[0] = False
+    return f
+
+
 CASES = [
+    ('stem_tc 3->32 (tcgen05)', stemtc(3, wt3, False), 12 * hw + 64 * hw),
+    ('stem_tc 2->32 (tcgen05)', stemtc(2, wt2, False), 8 * hw + 64 * hw),
+    ('head_dgrad stem_tc (1->32 + ReLU mask)', stemtc(1, wt1, True), 4 * hw + 128 * hw),
+    ('head_conv_tc 32->1 (tcgen05)', lambda i, s: check(L.ptta_head_conv_tc(ptr(maps[i % R]), ptr(head_img), 0.1, None, ptr(o1[i % R]), n, h, w, s), 'head_tc'), 64 * hw + 4 * hw),
     ('stem_conv_const 3->32', stemc(3, wt3, False), 12 * hw + 64 * hw),
     ('stem_conv_const 2->32', stemc(2, wt2, False), 8 * hw + 64 * hw),
     ('head_dgrad const (1->32 + ReLU mask)', stemc(1, wt1, True), 4 * hw + 128 * hw),

@@ -21,6 +21,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc_s2.cuh"
 #include "conv_tc_t2.cuh"
+#include "stem_tc.cuh"
 #include "gemm_tc.cuh"
 #include "nlspn_prop.cuh"
 #include "../../include/ptta_b200.h"
@@ -98,6 +99,7 @@ struct StemLayer {   // init.0: {1,2,3} -> 32
     float bk[32];
     float dk[9 * 32];             // host copy of dgrad_ch1 ([9][32]) for head_convc_kernel
     bf16* img_dgrad1 = nullptr;   // tcgen05 weight image of dgrad_ch1 (conv3x3_tc_head_kernel)
+    bf16* img_tc = nullptr;       // tcgen05 weight image of w (stem_tc_kernel: B_hi | B_lo)
 };
 struct HeadLayer {   // prdct.3: 32 -> 1
     std::string name;
@@ -109,6 +111,7 @@ struct HeadLayer {   // prdct.3: 32 -> 1
     float wdk[9 * 32];            // ... re-ordered [tap][co] for stem_convc_kernel<1>
     float wfk[9 * 32];            // host copy of w_fwd ([9][32]) for head_convc_kernel
     bf16* img_fwd = nullptr;      // tcgen05 weight image of w_fwd (conv3x3_tc_head_kernel)
+    bf16* img_dgrad_tc = nullptr; // tcgen05 weight image of w_dgrad (stem_tc_kernel<1>)
 };
 struct BnState {     // per call-site statistics
     float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr, *uvar = nullptr;
@@ -161,7 +164,7 @@ struct ptta_msgchn {
     cudaEvent_t ev_e3 = nullptr, ev_mlp = nullptr, ev_lossg = nullptr, ev_headb = nullptr, ev_gmg = nullptr, ev_wg2 = nullptr;
     bool two_streams = true;
     bool mlp_on_st3 = false;        // set by forward_impl for the duration of the real cascade
-    bool tc_enabled = true; long long tc_min_pixels = 6000, tc_s2_min_pixels = 6000, tc_t2_min_pixels = 1500, tc_head_min_pixels = 20000;
+    bool tc_enabled = true; long long tc_min_pixels = 6000, tc_s2_min_pixels = 6000, tc_t2_min_pixels = 1500, tc_head_min_pixels = 20000, tc_stem_min_pixels = 20000;
     bool fuse_dec_sums = true;      // experiment switches (environment: PTTA_NO_TC, PTTA_NO_FUSE_DEC_SUMS, PTTA_ONE_STREAM)
     Arena arena;
     size_t ws_bytes = 0;
@@ -313,6 +316,7 @@ struct ptta_msgchn {
     void plan_enc_w(EncW& E) {
         E.init0.dgrad_ch1 = allocv<float>(288);
         E.init0.img_dgrad1 = allocv<bf16>(9 * 16 * 32);
+        E.init0.img_tc = allocv<bf16>(2 * 32 * 32);
         plan_conv(E.init2);
         ConvLayer* ls[8] = {&E.e1a, &E.e1b, &E.e2a, &E.e2b, &E.e3a, &E.e3b, &E.e4a, &E.e4b};
         for (int k = 0; k < 2 * E.nenc; ++k) plan_conv(*ls[k]);
@@ -321,6 +325,7 @@ struct ptta_msgchn {
         plan_conv(D.d2a); plan_conv(D.d2b); plan_conv(D.d1a); plan_conv(D.d1b); plan_conv(D.p1);
         D.p3.w_fwd = allocv<float>(288); D.p3.w_dgrad = allocv<float>(288);
         D.p3.img_fwd = allocv<bf16>(9 * 16 * 32);
+        D.p3.img_dgrad_tc = allocv<bf16>(2 * 32 * 32);
     }
     void plan_enc_act(EncAct& A, const std::string& tag, int h, int w) {
         A.a0 = alloc32((tag + ".a0").c_str(), h, w); A.x0 = alloc32((tag + ".x0").c_str(), h, w);
@@ -537,6 +542,8 @@ struct ptta_msgchn {
             launch_k(pack_conv_weight_tc_head_kernel, cdiv(9 * 16 * 4, 256), 256, 0, st, E.init0.dgrad_ch1, E.init0.img_dgrad1);
             PTTA_TRY(check_launch("pack_stem_dgrad_tc"));
         }
+        launch_k(pack_stem_weight_tc_kernel, 1, 256, 0, st, E.init0.w, E.init0.img_tc, E.init0.cin);
+        PTTA_TRY(check_launch("pack_stem_tc"));
         PTTA_TRY(pack_conv(E.init2));
         ConvLayer* ls[8] = {&E.e1a, &E.e1b, &E.e2a, &E.e2b, &E.e3a, &E.e3b, &E.e4a, &E.e4b};
         for (int k = 0; k < 2 * E.nenc; ++k) PTTA_TRY(pack_conv(*ls[k]));
@@ -566,6 +573,8 @@ struct ptta_msgchn {
         PTTA_TRY(check_launch("pack_head_tc"));
         launch_k(pack_flip9_kernel, 2, 256, 0, st, D.p3.w, D.p3.w_dgrad, 32);
         PTTA_TRY(check_launch("pack_head_dgrad"));
+        launch_k(pack_stem_weight_tc_kernel, 1, 256, 0, st, D.p3.w_dgrad, D.p3.img_dgrad_tc, 1);
+        PTTA_TRY(check_launch("pack_head_dgrad_tc"));
         PTTA_CUDA(cudaMemcpyAsync(&D.p3.bias_host, D.p3.b, sizeof(float), cudaMemcpyDeviceToHost, st));
         PTTA_CUDA(cudaMemcpyAsync(D.p3.wfk, D.p3.w_fwd, sizeof(D.p3.wfk), cudaMemcpyDeviceToHost, st));
         D.p3.raw_host.resize(288);
@@ -718,6 +727,15 @@ struct ptta_msgchn {
     }
     int stem(const StemLayer& S, const float* p0, long long s0, float sc0, float sh0, const float* p1, long long s1, float sc1,
              float sh1, const float* p2, long long s2, float sc2, float sh2, const Map32& out) {
+        if (use_tc_stem(out)) {         // contraction on the tensor cores (stem_tc.cuh)
+            StemTcParams t; memset(&t, 0, sizeof(t));
+            t.relu_out = 1;
+            t.plane[0] = p0; t.plane[1] = p1; t.plane[2] = p2;
+            t.batch_stride[0] = s0; t.batch_stride[1] = s1; t.batch_stride[2] = s2;
+            t.scale[0] = sc0; t.scale[1] = sc1; t.scale[2] = sc2; t.shift[0] = sh0; t.shift[1] = sh1; t.shift[2] = sh2;
+            t.w = S.img_tc; t.bias = S.b; t.out = out.p; t.N = out.n; t.H = out.h; t.W = out.w;
+            return launch_stem_tc(t, S.cin, st);
+        }
         if ((out.w & 1) == 0) {         // weights by value (constant bank): the FMA-only kernel
             StemCParams c; memset(&c, 0, sizeof(c));
             c.relu_out = 1;
@@ -738,6 +756,7 @@ struct ptta_msgchn {
         launch_stem(p, S.cin, st);
         return check_launch("stem_conv");
     }
+    bool use_tc_stem(const Map32& m) const { return tc_enabled && (long long)m.n * m.h * m.w >= tc_stem_min_pixels; }
     bool use_tc_head(const Map1& m) const {
         return tc_enabled && conv_tc_supported(m.n, m.h, m.w) && (long long)m.n * m.h * m.w >= tc_head_min_pixels;
     }
@@ -762,6 +781,12 @@ struct ptta_msgchn {
     }
     // g_h = dgrad_{1->32}(g_out) * [h > 0]
     int head_dgrad(const HeadLayer& Hd, const Map1& gout, const Map32& hmask, const Map32& gh) {
+        if (use_tc_stem(gh)) {
+            StemTcParams t; memset(&t, 0, sizeof(t));
+            t.plane[0] = gout.p; t.batch_stride[0] = (long long)gout.h * gout.w; t.scale[0] = 1.f;
+            t.w = Hd.img_dgrad_tc; t.mask = hmask.p; t.out = gh.p; t.N = gh.n; t.H = gh.h; t.W = gh.w;
+            return launch_stem_tc(t, 1, st);
+        }
         if ((gh.w & 1) == 0) {
             StemCParams c; memset(&c, 0, sizeof(c));
             c.plane[0] = gout.p; c.batch_stride[0] = (long long)gout.h * gout.w; c.scale[0] = 1.f;
@@ -1380,6 +1405,23 @@ int ptta_head_conv_const(const void* in, const float* weight_host_9x32, float bi
     return check_launch("head_conv_const");
 }
 
+int ptta_stem_conv_tc(const float* const* planes, const long long* strides, const float* scale, const float* shift, int cin,
+                      const float* weight, const float* bias, const void* mask, void* out, void* image_scratch, int relu_out, int n, int h, int w,
+                      ptta_stream_t stream) {
+    PTTA_CHECK(cin >= 1 && cin <= 3 && planes && out && image_scratch, "stem_conv_tc: bad arguments");
+    if (weight) {                        // null: image_scratch already holds the packed weights of an earlier call
+        launch_k(pack_stem_weight_tc_kernel, 1, 256, 0, (cudaStream_t)stream, weight, (bf16*)image_scratch, cin);
+        PTTA_TRY(check_launch("pack_stem_tc"));
+    }
+    StemTcParams t; memset(&t, 0, sizeof(t));
+    for (int k = 0; k < 3; ++k) {
+        const int s = k < cin ? k : 0;
+        t.plane[k] = planes[s]; t.batch_stride[k] = strides[s]; t.scale[k] = scale ? scale[s] : 1.f; t.shift[k] = shift ? shift[s] : 0.f;
+    }
+    t.w = (const bf16*)image_scratch; t.bias = bias; t.mask = (const bf16*)mask; t.out = (bf16*)out; t.N = n; t.H = h; t.W = w; t.relu_out = relu_out;
+    return launch_stem_tc(t, cin, (cudaStream_t)stream);
+}
+
 int ptta_pack_head_weight_tc(const float* weight_9x32, void* image, ptta_stream_t stream) {
     PTTA_CHECK(weight_9x32 && image, "pack_head_weight_tc: null argument");
     launch_k(pack_conv_weight_tc_head_kernel, cdiv(9 * 16 * 4, 256), 256, 0, (cudaStream_t)stream, weight_9x32, (bf16*)image);
@@ -1651,7 +1693,7 @@ int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepa
     if (getenv("PTTA_NO_TC")) e->tc_enabled = false;
     if (getenv("PTTA_NO_FUSE_DEC_SUMS")) e->fuse_dec_sums = false;
     if (getenv("PTTA_ONE_STREAM")) e->two_streams = false;
-    if (const char* v = getenv("PTTA_TC_MIN_PIXELS")) e->tc_min_pixels = e->tc_s2_min_pixels = e->tc_t2_min_pixels = e->tc_head_min_pixels = atoll(v);
+    if (const char* v = getenv("PTTA_TC_MIN_PIXELS")) e->tc_min_pixels = e->tc_s2_min_pixels = e->tc_t2_min_pixels = e->tc_head_min_pixels = e->tc_stem_min_pixels = atoll(v);
     e->define_model();
     e->plan();
     *out = e;
@@ -1664,6 +1706,7 @@ int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value) {
     else if (k == "tc_s2_min_pixels") e->tc_s2_min_pixels = value;      // same for the stride-2 tcgen05 conv
     else if (k == "tc_t2_min_pixels") e->tc_t2_min_pixels = value;      // same for the transposed stride-2 tcgen05 conv (INPUT pixels)
     else if (k == "tc_head_min_pixels") e->tc_head_min_pixels = value;  // same for the 32 -> 1 tcgen05 conv (prediction layers, stem data gradients)
+    else if (k == "tc_stem_min_pixels") e->tc_stem_min_pixels = value;  // same for the {1,2,3} -> 32 tcgen05 stem (and the prediction layers' data gradient)
     else if (k == "tc_enabled") e->tc_enabled = value != 0;
     else if (k == "two_streams") e->two_streams = value != 0;
     else if (k == "fuse_dec_sums") e->fuse_dec_sums = value != 0;

@@ -191,6 +191,24 @@ def stem_conv(planes, weight, bias=None, scale=None, shift=None, mask=None):
     return out
 
 
+def stem_conv_tc(planes, weight, bias=None, scale=None, shift=None, mask=None, relu_out=False):
+    """stem_conv on tcgen05 (csrc/stem_tc.cuh); device weights [32, cin, 3, 3]"""
+    cin = len(planes)
+    n, h, w = planes[0].shape
+    for p in planes:
+        _need(p, torch.float32, 'plane')
+    _need(weight, torch.float32, 'weight')
+    pl = (ctypes.c_void_p * 3)(*[planes[min(k, cin - 1)].data_ptr() for k in range(3)])
+    st = (ctypes.c_longlong * 3)(*[h * w] * 3)
+    sc = (ctypes.c_float * 3)(*(list(scale) if scale is not None else [1.0] * cin) + [1.0] * (3 - cin))
+    sh = (ctypes.c_float * 3)(*(list(shift) if shift is not None else [0.0] * cin) + [0.0] * (3 - cin))
+    out = torch.empty((n, h, w, 32), dtype=torch.bfloat16, device=weight.device)
+    image = torch.empty(2048, dtype=torch.bfloat16, device=weight.device)
+    check(_lib.lib().ptta_stem_conv_tc(pl, st, sc, sh, cin, ptr(weight), ptr(bias), ptr(mask), ptr(out), ptr(image), 1 if relu_out else 0,
+                                       n, h, w, _stream()), 'stem_conv_tc')
+    return out
+
+
 def stem_conv_const(planes, weight, bias=None, scale=None, shift=None, mask=None, relu_out=False):
     """stem_conv with HOST weights [32, cin, 3, 3] / bias [32] (CPU tensors): by-value kernel parameters, constant-bank operands"""
     cin = len(planes)
