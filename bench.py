@@ -239,7 +239,7 @@ def workload_config(args):
     h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
     if args.workload.startswith('nlspn'):
         return {'workload': 'NLSPN ProxyTTA continual adaptation (ResNet34 encoder/decoder, 18-step non-local propagation), synthetic ' + dataset.upper() + '-shape '
-                            '%dx3x%dx%d frames, prepare_mode %s, adapt_mode meta_bn (88 tensors), lr %g, w_sd/w_smooth/w_cos %g/%g/%g, '
+                            '%dx3x%dx%d frames, prepare_mode %s, adapt_mode meta_bn after convert_syncbn (94 tensors), lr %g, w_sd/w_smooth/w_cos %g/%g/%g, '
                             'Adam(0.9,0.999,1e-8)' % (args.batch, h, w, mode, lr, W_SD, W_SM, W_COS),
                 'batch_per_gpu': args.batch, 'parallelism': 'independent sequence shard per GPU (no collective)',
                 'l2': 'ring of %d distinct frames; per-step working set (~7 GB of activations) exceeds the 126 MB L2' % RING}

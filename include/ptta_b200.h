@@ -168,6 +168,10 @@ int ptta_tta_loss_backward(const float* pred, const float* image_raw, const floa
                            float max_input_depth, const void* emb_bf16, const void* ref_bf16, long long rows, int dim,
                            float w_sparse_depth, float w_smoothness, void* workspace, float grad_scale, float* g_pred,
                            void* g_ref_bf16, int n, int h, int w, ptta_stream_t stream);
+/* gradient of the cosine loss with respect to `emb` (same workspace, after ptta_tta_loss_forward): needed when the proxy heads hold adapted
+ * tensors (NLSPN adapt mode 'meta_bn' after convert_syncbn: src/nlspn_model_adapt.py:328-337 on SyncBatchNorm-converted BatchNorm1d) */
+int ptta_tta_loss_backward_emb(const void* emb_bf16, const void* ref_bf16, long long rows, int dim, void* workspace, float gscale,
+                               void* g_emb_bf16, int n, int h, int w, ptta_stream_t stream);
 
 /* ---- general-channel convolutions of the NLSPN network (tcgen05, csrc/conv_gen.cuh) ------------------------------
  * external_src/NLSPN/src/model/nlspnmodel_adapt.py:384-448 (resnet34.layer1-4 = torchvision BasicBlock stacks, conv6,

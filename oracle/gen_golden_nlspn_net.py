@@ -6,7 +6,8 @@ the driver's own lines (src/tta_main.py:309-346 construction, :583-633 step) on 
 
 Shims (none touches arithmetic): the ones of oracle/ref_shims.py, a stub for `skimage.restoration.inpaint`
 (src/data_utils.py:24, eval-time only) and `modulated_deform_conv_func` resolved to oracle.nlspn_prop_oracle.MDConvFn (the
-reference's DCN CUDA extension has no CPU path).  convert_syncbn / DDP are skipped (world size 1, CPU).
+reference's DCN CUDA extension has no CPU path) and SyncBatchNorm.forward on CPU (ref_shims.enable_cpu_syncbn: world size 1 = F.batch_norm).
+convert_syncbn() IS called, as the driver does (src/tta_main.py:327): it decides which tensors adapt_parameters('meta_bn') returns.  DDP is skipped.
 
 The checkpoint is NOT stored (26 M parameters): both sides rebuild it from `nlspn_oracle.make_synthetic_checkpoint(seed)`;
 the fixture keeps its digest, the key/shape manifest of the reference's state dict (oracle/nlspn_state_manifest.json), the
@@ -70,6 +71,8 @@ def run_case(case):
     extra = [k for k in sd if k not in manifest]
     assert not missing and not extra, (missing, extra)
     net.load_state_dict(sd, strict=True)                                   # restore_model (W:418-440) minus torch.load
+    ref_shims.enable_cpu_syncbn()
+    model.convert_syncbn()                                                 # T:327 -- BatchNorm2d AND the heads' BatchNorm1d become SyncBatchNorm
     params = model.adapt_parameters('meta_bn')                             # T:339
     named = {id(p): k for k, p in net.named_parameters()}
     names = [named[id(p)] for p in params]

@@ -123,7 +123,12 @@ def encoder(sd, image, sparse_depth, pr=FP32):
 
 
 def _mlp(sd, name, x, training, pr):
-    return O._mlp(sd, name, x, training, pr)
+    """MLP head (M:1396-1402) in the state the driver leaves it in: convert_syncbn() (T:327) makes its BatchNorm1d a SyncBatchNorm, so
+    adapt_parameters('meta_bn') (W:328-337) sets its running statistics to None -- batch statistics in train and eval, nothing to
+    update -- and returns its affine pair among the adapted tensors."""
+    h = pr.act(F.linear(x, pr.wgt(sd[name + '.0.weight']), sd[name + '.0.bias']))
+    h = pr.act(F.relu(F.batch_norm(h, None, None, sd[name + '.1.weight'], sd[name + '.1.bias'], True, 0.1, 1e-5)))
+    return pr.act(F.linear(h, pr.wgt(sd[name + '.3.weight']), sd[name + '.3.bias']))
 
 
 def network_forward(sd, image, sparse_depth, training, pr=FP32, legacy=True, prop_time=18, trace=None):
@@ -174,13 +179,14 @@ def model_forward(sd, image, sparse_depth, training, max_input_depth, pr=FP32, t
 # adapted parameters (W:322-337) and one TTA step (T:583-633)
 # ----------------------------------------------------------------------------------------------------------------
 def adapt_parameter_names(sd, mode='meta_bn'):
-    """'meta_bn': every parameter whose name contains 'meta', then weight and bias of every BatchNorm2d in module order
-    (BatchNorm1d of the heads is not a BatchNorm2d: without convert_syncbn it is not adapted -- SURVEY.md 3.4)."""
+    """'meta_bn' after convert_syncbn() (the driver's sequence, T:327-339): every parameter whose name contains 'meta', then weight and
+    bias of every (Sync)BatchNorm in module order -- the BatchNorm2d layers of the network AND the BatchNorm1d layers of the three heads
+    (the `'pred' not in np and 'proj' not in np` test of W:335 looks at the LOCAL parameter name, 'weight' / 'bias', and excludes nothing)."""
     if mode != 'meta_bn':
         raise NotImplementedError(mode)
     names = [k for k in sd if 'meta' in k and k.rsplit('.', 1)[-1] in ('weight', 'bias')]
     for k in sd:
-        if k.endswith('.running_mean') and not k.startswith(('proj', 'pred')):
+        if k.endswith('.running_mean'):
             base = k[:-len('.running_mean')]
             names += [base + '.weight', base + '.bias']
     return names

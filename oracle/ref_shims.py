@@ -54,6 +54,32 @@ def _neutralise_cuda():
         nn.Module.to = to
 
 
+def enable_cpu_syncbn():
+    """SyncBatchNorm.forward refuses CPU tensors; at world size 1 it is F.batch_norm on the local batch (torch/nn/modules/batchnorm.py:
+    `need_sync` is False without a process group), which is what this replacement calls -- with the module's own buffers, so the
+    `running_mean = None` the reference sets in adapt_parameters('meta_bn') (src/nlspn_model_adapt.py:329-333) selects batch statistics
+    in train AND eval mode exactly as on the GPU.  The driver calls convert_syncbn() before adapt_parameters (src/tta_main.py:327-339),
+    which also turns the heads' BatchNorm1d layers into SyncBatchNorm instances."""
+    import torch.nn.functional as F
+
+    def forward(self, x):
+        if self.momentum is None:
+            eaf = 0.0
+        else:
+            eaf = self.momentum
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+            if self.momentum is None:
+                eaf = 1.0 / float(self.num_batches_tracked)
+        bn_training = self.training or (self.running_mean is None and self.running_var is None)
+        rm = self.running_mean if not self.training or self.track_running_stats else None
+        rv = self.running_var if not self.training or self.track_running_stats else None
+        return F.batch_norm(x, rm, rv, self.weight, self.bias, bn_training, eaf, self.eps)
+    if not getattr(nn.SyncBatchNorm.forward, '_ptta_shim', False):
+        forward._ptta_shim = True
+        nn.SyncBatchNorm.forward = forward
+
+
 def load_reference():
     """Returns a namespace with ExternalModel_Adapt, OutlierRemoval, loss_utils, eval_utils."""
     if _loaded:

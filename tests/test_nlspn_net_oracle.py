@@ -28,7 +28,10 @@ def test_checkpoint_keys_match_reference_manifest():
     for k, shape in manifest.items():
         assert list(sd[k].shape) == shape, k
     names = NO.adapt_parameter_names(sd, 'meta_bn')
-    assert len(names) == 88 and sum(sd[k].numel() for k in names) == 40048          # SURVEY.md 3.4 (probe of the reference)
+    # 88 tensors / 40 048 elements from the meta conv + BatchNorm2d layers + the three heads' BatchNorm1d affine pairs, which
+    # convert_syncbn() (src/tta_main.py:327) turns into SyncBatchNorm instances that adapt_parameters('meta_bn') matches as well
+    assert len(names) == 94 and sum(sd[k].numel() for k in names) == 40048 + 6 * 1024
+    assert names[-6:] == ['proj.1.weight', 'proj.1.bias', 'proj_t.1.weight', 'proj_t.1.bias', 'pred.1.weight', 'pred.1.bias']
 
 
 @pytest.mark.parametrize('name', NAMES)

@@ -1085,7 +1085,7 @@ struct ptta_msgchn {
             launch_k(loss_map_grad_kernel, cdiv(tot, 256), 256, 0, st, padded ? out_u.p : B.output.p, l_d, l_v, l_img, padded ? g_out_u.p : g_out.p, losses,
                                                                Nu, Hu, Wu, l_cap, l_cap > 0.f ? 1 : 0, l_wsd, l_wsm, gscale);
             PTTA_TRY(check_launch("loss_map_grad"));
-            launch_k(loss_cos_grad_kernel, loss_cos_blocks, 256, 0, st, emb, ref, rowstat, losses, g_ref, R, 512, gscale);
+            launch_k(loss_cos_grad_kernel, loss_cos_blocks, 256, 0, st, emb, ref, rowstat, losses, g_ref, R, 512, gscale, 0);
             PTTA_TRY(check_launch("loss_cos_grad"));
         }
         return 0;
@@ -1544,8 +1544,18 @@ int ptta_tta_loss_backward(const float* pred, const float* image_raw, const floa
                                                        cap > 0.f ? 1 : 0, w_sd, w_sm, gscale);
     PTTA_TRY(check_launch("loss_map_grad"));
     launch_k(loss_cos_grad_kernel, L.cos_blocks, 256, 0, st, (const bf16*)emb, (const bf16*)ref, (const float*)(ws + L.rowstat),
-                                                      (const LossScalars*)(ws + L.scalars), (bf16*)g_ref, rows, dim, gscale);
+                                                      (const LossScalars*)(ws + L.scalars), (bf16*)g_ref, rows, dim, gscale, 0);
     return check_launch("loss_cos_grad");
+}
+
+int ptta_tta_loss_backward_emb(const void* emb, const void* ref, long long rows, int dim, void* workspace, float gscale, void* g_emb, int n, int h,
+                               int w, ptta_stream_t stream) {
+    PTTA_CHECK(emb && ref && workspace && g_emb, "tta_loss_backward_emb: null pointer");
+    const TtaLossLayout L = tta_loss_layout(n, h, w, rows);
+    char* ws = (char*)workspace;
+    launch_k(loss_cos_grad_kernel, L.cos_blocks, 256, 0, (cudaStream_t)stream, (const bf16*)emb, (const bf16*)ref, (const float*)(ws + L.rowstat),
+                                                      (const LossScalars*)(ws + L.scalars), (bf16*)g_emb, rows, dim, gscale, 1);
+    return check_launch("loss_cos_grad(emb)");
 }
 
 int ptta_adam_flat(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps, double wd, int step,

@@ -1293,16 +1293,20 @@ __global__ void loss_map_grad_kernel(const float* __restrict__ pred, const float
 }
 
 // d loss / d ref = w_eff * (-2/R) * (ehat - cos*rhat) / max(|r|, eps)
+// wrt_emb = 0: gradient with respect to `ref` (the loss is symmetric in its two arguments: wrt_emb = 1 swaps their roles and writes the
+// gradient with respect to `emb` -- needed when the heads' BatchNorm affine pairs are adapted, NLSPN 'meta_bn' after convert_syncbn)
 __global__ void __launch_bounds__(256) loss_cos_grad_kernel(const bf16* __restrict__ emb, const bf16* __restrict__ ref, const float* __restrict__ rowstat,
-                                                            const LossScalars* __restrict__ ls, bf16* __restrict__ gref, long long R, int D, float gscale) {
+                                                            const LossScalars* __restrict__ ls, bf16* __restrict__ gref, long long R, int D, float gscale,
+                                                            int wrt_emb = 0) {
     PDL_SYNC();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float coef = ls->w_cos_eff * (-2.f / (float)R) * gscale;
     for (long long r = (long long)blockIdx.x * 8 + warp; r < R; r += (long long)gridDim.x * 8) {
         float dot = rowstat[r * 3], ne = fmaxf(sqrtf(rowstat[r * 3 + 1]), 1e-12f), nr = fmaxf(sqrtf(rowstat[r * 3 + 2]), 1e-12f);
+        const bf16* e = emb + (size_t)r * D; const bf16* f = ref + (size_t)r * D;
+        if (wrt_emb) { const float t = ne; ne = nr; nr = t; const bf16* tp = e; e = f; f = tp; }
         float cs = dot / (ne * nr);
         float a = coef / (ne * nr), b = coef * cs / (nr * nr);
-        const bf16* e = emb + (size_t)r * D; const bf16* f = ref + (size_t)r * D;
         bf16* o = gref + (size_t)r * D;
         for (int c = lane * 8; c < D; c += 256) {
             uint4 ev = __ldg(reinterpret_cast<const uint4*>(e + c)), fv = __ldg(reinterpret_cast<const uint4*>(f + c));

@@ -28,25 +28,29 @@ def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def adapt_parameter_names(sd):
-    """src/nlspn_model_adapt.py:322-337 ('meta_bn'): parameters whose name contains 'meta', then weight/bias of every
-    BatchNorm2d in module order (the BatchNorm1d layers of the heads are not BatchNorm2d instances)."""
+def adapt_parameter_names(sd, syncbn=True):
+    """src/nlspn_model_adapt.py:322-337 ('meta_bn'): parameters whose name contains 'meta', then weight/bias of every BatchNorm2d /
+    SyncBatchNorm in module order.  syncbn = True is the driver's sequence (src/tta_main.py:327-339: convert_syncbn() BEFORE
+    adapt_parameters): SyncBatchNorm.convert_sync_batchnorm also converts the BatchNorm1d layers of the three heads, so their affine pairs
+    are adapted too (94 tensors; the `'pred' not in np and 'proj' not in np` test of :335 sees the local names 'weight' / 'bias' and excludes
+    nothing) and their running statistics are set to None.  syncbn = False: adapt_parameters without convert_syncbn (88 tensors)."""
     names = [k for k in sd if 'meta' in k and k.rsplit('.', 1)[-1] in ('weight', 'bias')]
     for k in sd:
-        if k.endswith('.running_mean') and not k.startswith(('proj', 'pred')):
+        if k.endswith('.running_mean') and (syncbn or not k.startswith(('proj', 'pred'))):
             base = k[:-len('.running_mean')]
             names += [base + '.weight', base + '.bias']
     return names
 
 
 class NlspnEngine:
-    def __init__(self, state_dict, n, h, w, device, prop_time=18, legacy=True, share_from=None):
+    def __init__(self, state_dict, n, h, w, device, prop_time=18, legacy=True, share_from=None, syncbn=True):
         if h % 16 or w % 16:
             raise NotImplementedError('NLSPN engine: H and W must be multiples of 16 (got %dx%d)' % (h, w))
         _lib.lib()
         self.dev = torch.device(device)
         self.N, self.H, self.W = n, h, w
         self.prop_time, self.legacy = prop_time, legacy
+        self.syncbn = syncbn if share_from is None else share_from.syncbn      # heads' BatchNorm1d adapted, no running statistics
         self.launches = 0
         self.B = {}            # named activation / gradient buffers
         if share_from is not None:
@@ -91,7 +95,7 @@ class NlspnEngine:
         """Adapted tensors live in ONE flat fp32 buffer (+ gradient, Adam moments); the state-dict entries become views.  The
         three head-decoder BatchNorms are laid out back to back (+32 pad) so the fused 192-channel BatchNorm reads them in place,
         the meta bias is followed by 16 zeros (bias of the 64-channel fused stem convolution)."""
-        names = adapt_parameter_names(sd)
+        names = adapt_parameter_names(sd, self.syncbn)
         self.adapt_names = names
         order, special = [], {}
         fused = ['id_dec1.1', 'gd_dec1.1', 'cf_dec1.1']
@@ -400,7 +404,8 @@ class NlspnEngine:
         h_raw = self.buf(pre + name + '.h_raw', (R, 1024))
         check(_lib.lib().ptta_gemm_bf16_tc(ptr(x), ptr(self.head_w[name + '.0']), ptr(h_raw), ptr(sd[name + '.0.bias']), R, 1024, x.shape[1],
                                            _stream()), 'gemm_tc')
-        running = (sd[name + '.1.running_mean'], sd[name + '.1.running_var'], sd[name + '.1.num_batches_tracked']) if train_running else None
+        # after convert_syncbn + adapt_parameters('meta_bn') the heads' BatchNorm has running_mean = running_var = None: nothing to update
+        running = (sd[name + '.1.running_mean'], sd[name + '.1.running_var'], sd[name + '.1.num_batches_tracked']) if (train_running and not self.syncbn) else None
         st = self.bn_stats(pre + name + '.1', h_raw, sd[name + '.1.weight'], sd[name + '.1.bias'], running)
         h_act = self.bn_act(h_raw, st, ACT_RELU, pre + name + '.h_act')
         out = self.buf(pre + name + '.out', (R, 1024))
@@ -477,6 +482,11 @@ class NlspnEngine:
         check(L.ptta_tta_loss_backward(ptr(B['output']), ptr(image_raw), ptr(sparse), ptr(validity), cap, ptr(self.emb), ptr(self.ref), self.R, 1024,
                                        w_sd, w_sm, ptr(self.loss_ws), gscale, ptr(g_out), ptr(g_ref), N, H, W, _stream()), 'tta_loss_backward')
         self.launches += 2
+        if self.syncbn:          # emb = pred(proj(z_zero.detach())) reaches the adapted BatchNorm affine pairs of proj and pred
+            g_emb = self.buf('g.emb', (self.R, 1024))
+            check(L.ptta_tta_loss_backward_emb(ptr(self.emb), ptr(self.ref), self.R, 1024, ptr(self.loss_ws), gscale, ptr(g_emb), N, H, W, _stream()),
+                  'tta_loss_backward_emb')
+            self.launches += 1
 
     def network_backward(self):
         """from (B['g.out'], B['g.ref']) to the gradients of the 88 adapted tensors (flat_g)"""
@@ -528,7 +538,20 @@ class NlspnEngine:
         d_h = self.buf('g.proj_t.h', (R, 1024))
         check(L.ptta_gemm_bf16_tc(ptr(g_ref), ptr(self.head_w['proj_t.3.T']), ptr(d_h), None, R, 1024, 1024, _stream()), 'gemm_tc')
         d_hraw, _ = self.bn_backward('r.', 'proj_t.1', d_h, 1024, None, 0, B['r.proj_t.h_act'], ACT_RELU, B['r.proj_t.h_raw'], 'g.proj_t.h_raw',
-                                     grads=False)
+                                     grads=self.syncbn)
+        if self.syncbn:
+            # emb = pred(proj(z_zero)), z_zero detached: gradients of pred.1 and proj.1 (weight, bias) only -- pred.3^T, BatchNorm backward,
+            # pred.0^T, proj.3^T, BatchNorm backward; R = N H/16 W/16 rows of 1024, a few microseconds of GEMMs
+            g_emb = B['g.emb']
+            e_h = self.buf('g.pred.h', (R, 1024))
+            check(L.ptta_gemm_bf16_tc(ptr(g_emb), ptr(self.head_w['pred.3.T']), ptr(e_h), None, R, 1024, 1024, _stream()), 'gemm_tc')
+            e_hraw, _ = self.bn_backward('z.', 'pred.1', e_h, 1024, None, 0, B['z.pred.h_act'], ACT_RELU, B['z.pred.h_raw'], 'g.pred.h_raw')
+            e_p = self.buf('g.proj.out', (R, 1024))
+            check(L.ptta_gemm_bf16_tc(ptr(e_hraw), ptr(self.head_w['pred.0.T']), ptr(e_p), None, R, 1024, 1024, _stream()), 'gemm_tc')
+            e_h1 = self.buf('g.proj.h', (R, 1024))
+            check(L.ptta_gemm_bf16_tc(ptr(e_p), ptr(self.head_w['proj.3.T']), ptr(e_h1), None, R, 1024, 1024, _stream()), 'gemm_tc')
+            self.bn_backward('z.', 'proj.1', e_h1, 1024, None, 0, B['z.proj.h_act'], ACT_RELU, B['z.proj.h_raw'], 'g.proj.h_raw')
+            self.launches += 3
         d_fe6_head = self.buf('g.fe6.head', (R, 512))
         check(L.ptta_gemm_bf16_tc(ptr(d_hraw), ptr(self.head_w['proj_t.0.T']), ptr(d_fe6_head), None, R, 512, 1024, _stream()), 'gemm_tc')
         self.launches += 2

@@ -95,7 +95,8 @@ class _NlspnForwardFn(torch.autograd.Function):
         out, emb, ref = eng.forward(image, sparse_depth, training=True)
         ctx.wrapper, ctx.eng = wrapper, eng
         emb_v, ref_v = emb.view(-1, 1024), ref.view(-1, 1024)
-        ctx.mark_non_differentiable(emb_v)       # emb = pred(proj(fe6_zero.detach())): no path to the adapted tensors
+        if not eng.syncbn:
+            ctx.mark_non_differentiable(emb_v)   # emb = pred(proj(fe6_zero.detach())): without convert_syncbn no adapted tensor is on its path
         return out.clone(), emb_v, ref_v
 
     @staticmethod
@@ -107,6 +108,12 @@ class _NlspnForwardFn(torch.autograd.Function):
             go.view(-1).copy_(g_out.reshape(-1))
         if g_ref is not None and g_ref.data_ptr() != gr.data_ptr():
             gr.view(-1).copy_(g_ref.reshape(-1))
+        if eng.syncbn:
+            ge = eng.buf('g.emb', (eng.R, 1024))
+            if g_emb is None:
+                ge.zero_()
+            elif g_emb.data_ptr() != ge.data_ptr():
+                ge.view(-1).copy_(g_emb.reshape(-1))
         eng.network_backward()
         return (None, None, None) + tuple(eng.grads[k].clone() for k in wrapper._adapt_names)
 
@@ -125,7 +132,7 @@ class _NlspnLossFn(torch.autograd.Function):
     def backward(ctx, g_loss, g_parts):
         eng = ctx.eng
         eng.loss_backward(float(g_loss))
-        return (None, eng.B['g.out'], None, eng.B['g.ref'], None, None, None, None, None, None, None)
+        return (None, eng.B['g.out'], eng.B['g.emb'] if eng.syncbn else None, eng.B['g.ref'], None, None, None, None, None, None, None)
 
 
 class NLSPNModel_Adapt(object):
@@ -145,6 +152,7 @@ class NLSPNModel_Adapt(object):
         self._base = None
         self._adapt_names = []
         self._param_objs = OrderedDict()
+        self._syncbn = False                     # set by convert_syncbn()
 
     # -- construction ---------------------------------------------------------------------------------------------------------------
     def _prepare_head(self, mode):
@@ -156,7 +164,7 @@ class NLSPNModel_Adapt(object):
         if self.device.type != 'cuda':
             raise RuntimeError('the TTA step runs on CUDA only (no CPU fallback); got device %s' % self.device)
         self._engines, self._base = {}, None
-        self._adapt_names = adapt_parameter_names(self._sd)
+        self._adapt_names = adapt_parameter_names(self._sd, self._syncbn)
         self._param_objs = OrderedDict()
 
     def _engine_for(self, image):
@@ -166,7 +174,8 @@ class NLSPNModel_Adapt(object):
         eng = self._engines.get(key)
         if eng is None:
             n, h, w = key
-            eng = NlspnEngine(self._sd, n, h, w, self.device, prop_time=self.prop_time, legacy=self.legacy, share_from=self._base)
+            eng = NlspnEngine(self._sd, n, h, w, self.device, prop_time=self.prop_time, legacy=self.legacy, share_from=self._base,
+                              syncbn=self._syncbn)
             if self._base is None:
                 self._base = eng
                 self._sd = eng.sd                      # device tensors; adapted entries are views of the engine's flat buffer
@@ -229,7 +238,16 @@ class NLSPNModel_Adapt(object):
         pass                                      # one adapting model per GPU: nothing to wrap
 
     def convert_syncbn(self, apex=False):
-        pass                                      # world size 1 per model: SyncBatchNorm == BatchNorm
+        """src/nlspn_model_adapt.py:477-486.  One model per process, so the statistics stay local -- but the conversion also decides what
+        adapt_parameters('meta_bn') returns afterwards: SyncBatchNorm.convert_sync_batchnorm turns the heads' BatchNorm1d layers into
+        SyncBatchNorm instances as well, which :329-337 then matches (affine pairs adapted, running statistics None).  The reference
+        driver always converts before it asks for the parameters (src/tta_main.py:327-339)."""
+        if not self._syncbn:
+            self._syncbn = True
+            if self._sd is not None:
+                sd = self.state_dict()
+                self._sd = OrderedDict((k, v.detach().clone()) for k, v in sd.items())
+                self._reset_engines()
 
     def state_dict(self):
         return OrderedDict((k, (v.data if isinstance(v, torch.nn.Parameter) else v)) for k, v in self._sd.items())
