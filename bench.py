@@ -247,8 +247,11 @@ def workload_config(args):
                         'lr %g, w_sd/w_smooth/w_cos %g/%g/%g, Adam(0.9,0.999,1e-8)' % (dataset.upper(), args.batch, h, w, mode, lr, W_SD, W_SM,
                                                                                        W_COS),
             'batch_per_gpu': args.batch,
-            'parallelism': 'independent sequence shard per GPU (no collective)' if getattr(args, 'mode', 'shards') == 'shards' else
-                           'shared model: NCCL mean all-reduce of the flat adapted-gradient buffer, identical fused Adam on every rank',
+            'parallelism': {'shards': 'independent sequence shard per GPU (no collective)',
+                            'shared': 'shared model (DDP + SyncBatchNorm semantics): BatchNorm sums and the mean all-reduce of the flat adapted-gradient buffer '
+                                      'through NVLink peer memory inside the engine kernels, all-reduce fused with Adam, whole step one CUDA graph',
+                            'shared_nccl': 'shared model, round-1 form: local BatchNorm statistics, torch.distributed (NCCL) all-reduce of the gradient buffer, '
+                                           'separate Adam launch, eager'}[getattr(args, 'mode', 'shards')],
             'l2': 'ring of %d distinct frames; per-step working set (~1.5 GB of activations) exceeds the 126 MB L2' % RING}
 
 
@@ -577,14 +580,18 @@ def run_native(args):
     # ---- device-resident throughput (`value`) -------------------------------------------------------------------
     # every step: D2D copy of the next ring frame into the step's fixed input buffers, then the whole step replayed from
     # its CUDA graph (--no-graph: the same kernels launched eagerly)
-    use_graph = args.graph and args.mode == 'shards'
-    if args.mode == 'shared':
-        # BASELINE.json configs[4]: one shared model, every rank adapts on its own batch, the flat adapted-gradient buffer
-        # (74 080 floats) is mean-all-reduced over NCCL before the fused Adam step
+    use_graph = args.graph and args.mode != 'shared_nccl'
+    if args.mode in ('shared', 'shared_nccl'):
+        # BASELINE.json configs[4]: one shared model, every rank adapts on its own batch.  'shared': SyncBatchNorm sums and the mean
+        # all-reduce of the flat adapted-gradient buffer (74 080 floats) go through NVLink peer memory INSIDE the engine's kernels (the
+        # all-reduce fused with Adam), the step replays from one CUDA graph.  'shared_nccl': the round-1 form kept as the baseline --
+        # eager launches, local BatchNorm statistics, torch.distributed all_reduce + div + a separate Adam launch.
         from tta_depth_completion_b200 import sharding
+        if args.mode == 'shared':
+            comm = sharding.enable_shared_model(model)
 
         def run_step(img, sp, graph=False):
-            sharding.shared_model_step(model, img, sp, lr, W_SD, W_SM, W_COS)
+            sharding.shared_model_step(model, img, sp, lr, W_SD, W_SM, W_COS, graph=graph)
     else:
         def run_step(img, sp, graph=False):
             model.tta_step(img, sp, lr, W_SD, W_SM, W_COS, graph=graph)
@@ -652,7 +659,7 @@ def run_native(args):
         # model.forward -> model.compute_loss -> loss.backward() -> torch.optim.Adam.step(), host pinned frames, blocking `.to(device)`
         # and a `.item()` read of the loss every step as the reference's progress bar does -- the "no change to the driver" path
         ms_dropin = None
-        if args.mode == 'shards' and not args.no_extras:
+        if args.mode == 'shards' and not args.no_extras and world == 1:
             ms_dropin = time_dropin_leg(model, pinned, lr, cap, dev, stream, args.steps, barrier)
 
     if world > 1:
@@ -706,7 +713,7 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--workload', default='kitti', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=1)
-    ap.add_argument('--mode', default='shards', choices=['shards', 'shared'], help='shards: independent sequence shard per GPU, no collective (default); shared: one shared model, NCCL all-reduce of the adapted-parameter gradients (BASELINE.json configs[4])')
+    ap.add_argument('--mode', default='shards', choices=['shards', 'shared', 'shared_nccl'], help='shards: independent sequence shard per GPU, no collective (default); shared: one shared model, NCCL all-reduce of the adapted-parameter gradients (BASELINE.json configs[4])')
     ap.add_argument('--no-graph', dest='graph', action='store_false', help='launch the step kernels eagerly instead of replaying the captured CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip the roofline / cpu_baseline legs (profiling runs)')
     ap.add_argument('--engine-opt', action='append', default=[], metavar='NAME=VALUE', help='ptta_msgchn_set_option on the engine (dispatch experiments, e.g. tc_min_pixels=1000); not for headline runs')

@@ -283,6 +283,21 @@ void ptta_msgchn_destroy(ptta_msgchn* e);
  * "tc_min_pixels" / "tc_s2_min_pixels" / "tc_t2_min_pixels": smallest map (N*H*W of the INPUT) the stride-1 / stride-2 /
  * transposed tcgen05 convs take (0 = always),
  * "tc_enabled" 0/1, "two_streams" 0/1, "fuse_dec_sums" 0/1.  Unknown names fail. */
+/* ---- shared-model mode (BASELINE.json configs[4]; the reference: DDP + SyncBatchNorm, src/msg_chn_model_adapt.py:480,555-556) ----
+ * One communicator per rank: a device block mapped into every peer through CUDA IPC.  With a communicator set, the engine's
+ * train-mode BatchNorm layers take their statistics over ALL ranks (forward sums and backward sums exchanged through peer memory
+ * inside the finalize kernels) and the Adam step first mean-all-reduces the flat adapted-gradient buffer (one fused kernel, ranks
+ * summed in rank order: bit-identical replicas).  No NCCL call on the path; the step stays capturable in one CUDA graph.
+ * Train-mode BatchNorm sums: exchanged inside bn_finalize / bn_bwd_finalize.  Host protocol: create -> local_handle -> exchange the handles (any transport, e.g. torch.distributed.all_gather_object) ->
+ * open_peers -> ptta_msgchn_set_comm. */
+typedef struct ptta_comm ptta_comm;
+int ptta_comm_create(ptta_comm** out, int rank, int world, long long grad_floats);
+int ptta_comm_handle_bytes(void);
+int ptta_comm_local_handle(ptta_comm* c, void* handle_out);
+int ptta_comm_open_peers(ptta_comm* c, const void* handles_world_x_bytes);
+int ptta_comm_error(ptta_comm* c);      /* 0 = fine; k > 0 = exchange k-1 timed out waiting for a peer (~4 s): results are void */
+void ptta_comm_destroy(ptta_comm* c);
+int ptta_msgchn_set_comm(ptta_msgchn* e, ptta_comm* c);
 int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value);
 size_t ptta_msgchn_workspace_bytes(const ptta_msgchn* e);
 int ptta_msgchn_bind_workspace(ptta_msgchn* e, void* workspace, size_t bytes, ptta_stream_t stream);

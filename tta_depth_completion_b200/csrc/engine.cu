@@ -182,6 +182,9 @@ struct ptta_msgchn {
     LinearLayer proj0, proj3, pred0, pred3;
     bf16* projpred_pack = nullptr; float* projpred_bias = nullptr;   // pred.0 o proj.3 as one Linear layer (zero-image rows: emb = pred(proj(z)))
     bool fuse_projpred = true;
+    // shared-model mode (ptta_msgchn_set_comm): SyncBatchNorm sums and the gradient all-reduce go through peer memory (peer_comm.cuh)
+    PeerComm comm;
+    int next_xid = 0;                // exchange slots are handed out in call order; every rank runs the same sequence
     BnLayer projBn, predBn;
     std::vector<std::string> adapt_names;
 
@@ -211,6 +214,7 @@ struct ptta_msgchn {
     int loss_map_blocks = 0, loss_cos_blocks = 0;
     AdamHyper* adam_hyper = nullptr;
     AdamChunk* adam_chunks = nullptr; int n_adam_chunks = 0;
+    const float* adam_g_base = nullptr; size_t adam_g_floats = 0;   // extent of the gradient pointers in the chunk table
     float* zero_bias = nullptr;
     // loss inputs remembered for backward
     const float *l_img = nullptr, *l_d = nullptr, *l_v = nullptr; float l_cap = 0, l_wsd = 0, l_wsm = 0;
@@ -631,6 +635,12 @@ struct ptta_msgchn {
             PTTA_CHECK(ext["adam/hyper"].second >= (long long)sizeof(AdamHyper), "'adam/hyper' needs %zu bytes", sizeof(AdamHyper));
             adam_hyper = (AdamHyper*)ext["adam/hyper"].first;
         }
+        adam_g_base = nullptr; adam_g_floats = 0;
+        if (!chunks.empty()) {
+            const float *lo = chunks[0].g, *hi = chunks[0].g + chunks[0].n;
+            for (const AdamChunk& c : chunks) { if (c.g < lo) lo = c.g; if (c.g + c.n > hi) hi = c.g + c.n; }
+            adam_g_base = lo; adam_g_floats = (size_t)(hi - lo);
+        }
         PTTA_CHECK(chunks.size() <= 256, "too many Adam chunks (%zu)", chunks.size());
         n_adam_chunks = (int)chunks.size();
         if (n_adam_chunks) PTTA_CUDA(cudaMemcpyAsync(adam_chunks, chunks.data(), sizeof(AdamChunk) * chunks.size(), cudaMemcpyHostToDevice, st));
@@ -807,6 +817,10 @@ struct ptta_msgchn {
         PTTA_TRY(head_convv(ga0.p, S.dk, 0.f, add, out, 0));
         return check_launch("stem_dgrad");
     }
+    int take_xid() {
+        if (next_xid >= PTTA_COMM_MAX_XID) { set_error("shared-model mode: more than %d peer exchanges in one step", PTTA_COMM_MAX_XID); return -1; }
+        return next_xid++;
+    }
     int stats(const bf16* x, const bf16* dy, long long rows, int C, int mode, const BnState* s, int relu_mask, int& nblk) {
         nblk = cdiv(rows, STATS_ROWS_PER_BLOCK);
         PTTA_CHECK((size_t)nblk * 2 * C <= partial_doubles, "stats partial buffer too small");
@@ -823,7 +837,9 @@ struct ptta_msgchn {
         if (defer_running) { p.running_mean = nullptr; p.running_var = nullptr; p.num_batches_tracked = nullptr; }
         p.uvar = s.uvar;
         p.mean = s.mean; p.invstd = s.invstd; p.scale = s.scale; p.shift = s.shift; p.momentum = 0.1f; p.eps = 1e-5f;
-        launch_k(bn_finalize_kernel, cdiv(L.c, 32), FIN_THREADS, 0, st, partial, nblk, rows, L.c, p, training ? 1 : 0);
+        const int xid = (training && comm.world > 1) ? take_xid() : 0;
+        if (xid < 0) return 1;
+        launch_k(bn_finalize_kernel, cdiv(L.c, 32), FIN_THREADS, 0, st, partial, nblk, rows, L.c, p, training ? 1 : 0, comm, xid);
         return check_launch("bn_finalize");
     }
     int bn_running_update(const BnLayer& L, const BnState& s) {
@@ -839,7 +855,9 @@ struct ptta_msgchn {
                     float* dgamma, float* dbeta) {
         int nblk = 0;
         PTTA_TRY(stats(x, dy, rows, L.c, 1, &s, relu_mask, nblk));
-        launch_k(bn_bwd_finalize_kernel, cdiv(L.c, 32), FIN_THREADS, 0, st, partial, nblk, rows, L.c, L.gamma, s.invstd, dgamma, dbeta, k0, k1, k2);
+        const int xid = comm.world > 1 ? take_xid() : 0;
+        if (xid < 0) return 1;
+        launch_k(bn_bwd_finalize_kernel, cdiv(L.c, 32), FIN_THREADS, 0, st, partial, nblk, rows, L.c, L.gamma, s.invstd, dgamma, dbeta, k0, k1, k2, comm, xid);
         PTTA_TRY(check_launch("bn_bwd_finalize"));
         launch_k(bn_bwd_apply_kernel, cdiv(rows, (256 / (L.c / 8)) * EW_ROWS), 256, 0, st, dy, x, dx, rows, L.c, s.mean, s.invstd, k0, k1, k2, s.scale, s.shift, relu_mask);
         return check_launch("bn_bwd_apply");
@@ -960,6 +978,7 @@ struct ptta_msgchn {
     int forward(const float* image, const float* isc, const float* ish, const float* sparse, float cap, bool training) {
         PTTA_CHECK(bound && packed, "engine not ready: bind a workspace and pack weights first");
         PTTA_CHECK(!training || has_heads, "training forward needs the proxy heads ('selfsup' prepare mode)");
+        next_xid = 0;                   // a step's peer exchanges are numbered from its forward pass on
         if (!padded) return forward_impl(image, isc, ish, sparse, cap, training);
         {
             // the reference pads the NORMALISED image with zeros (msg_chn_model_adapt.py:79-101): fill with the raw value that
@@ -1211,6 +1230,22 @@ struct ptta_msgchn {
 
     int adam_step() {
         PTTA_CHECK(n_adam_chunks > 0, "Adam state not bound (grad/, adam_m/, adam_v/ entries for every adapted tensor)");
+        if (comm.world > 1) {
+            // shared model: one-shot mean all-reduce of the flat gradient buffer fused with the Adam update (identical on every rank)
+            const int xid = take_xid();
+            if (xid < 0) return 1;
+            const float* g_base = nullptr;      // lowest gradient pointer of the chunk table = start of the flat buffer the chunks index into
+            PTTA_CHECK(adam_g_base != nullptr && adam_g_floats <= comm.grad_floats, "shared-model mode: gradient buffer (%zu floats) exceeds the communicator's slot (%zu)",
+                       adam_g_floats, comm.grad_floats);
+            g_base = adam_g_base;
+            launch_k(adam_allreduce_kernel, n_adam_chunks, 256, 0, st, adam_chunks, adam_hyper, comm, xid, g_base);
+            PTTA_TRY(check_launch("adam_allreduce"));
+            launch_k(adam_advance_kernel, 1, 1, 0, st, adam_hyper);
+            PTTA_TRY(check_launch("adam_advance"));
+            launch_k(comm_advance_kernel, 1, 32, 0, st, comm);
+            PTTA_TRY(check_launch("comm_advance"));
+            return pack_adapted();
+        }
         launch_k(adam_kernel, n_adam_chunks, 256, 0, st, adam_chunks, adam_hyper);
         PTTA_TRY(check_launch("adam"));
         launch_k(adam_advance_kernel, 1, 1, 0, st, adam_hyper);
@@ -1709,6 +1744,77 @@ int ptta_msgchn_create(ptta_msgchn** out, int n, int h, int w, const char* prepa
     *out = e;
     return 0;
 }
+// ---- peer communicator of the shared-model mode (peer_comm.cuh) ---------------------------------------------------------
+struct ptta_comm {
+    PeerComm dev;
+    void* local = nullptr;
+    void* opened[PTTA_COMM_MAX_RANKS] = {};
+    size_t bytes = 0;
+};
+int ptta_comm_create(ptta_comm** out, int rank, int world, long long grad_floats) {
+    PTTA_CHECK(out && world >= 1 && world <= PTTA_COMM_MAX_RANKS && rank >= 0 && rank < world && grad_floats > 0, "comm_create: bad arguments (rank %d of %d)", rank, world);
+    ptta_comm* c = new ptta_comm();
+    c->dev.world = world; c->dev.rank = rank; c->dev.grad_floats = (size_t)grad_floats;
+    c->bytes = comm_block_bytes((size_t)grad_floats);
+    if (cudaMalloc(&c->local, c->bytes) != cudaSuccess) { delete c; set_error("comm_create: cudaMalloc(%zu) failed", c->bytes); return 2; }
+    PTTA_CUDA(cudaMemset(c->local, 0, c->bytes));
+    PTTA_CUDA(cudaDeviceSynchronize());
+    c->dev.base[rank] = (unsigned char*)c->local;
+    *out = c;
+    return 0;
+}
+int ptta_comm_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+int ptta_comm_local_handle(ptta_comm* c, void* handle_out) {
+    PTTA_CHECK(c && handle_out, "comm_local_handle: null argument");
+    cudaIpcMemHandle_t h;
+    PTTA_CUDA(cudaIpcGetMemHandle(&h, c->local));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+/* handles: world x ptta_comm_handle_bytes() bytes, rank order (this rank's own entry is ignored) */
+int ptta_comm_open_peers(ptta_comm* c, const void* handles) {
+    PTTA_CHECK(c && handles, "comm_open_peers: null argument");
+    for (int r = 0; r < c->dev.world; ++r) {
+        if (r == c->dev.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        PTTA_CHECK(err == cudaSuccess, "comm_open_peers: cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(err));
+        c->opened[r] = p;
+        c->dev.base[r] = (unsigned char*)p;
+    }
+    return 0;
+}
+/* 0: no exchange ever timed out; k > 0: exchange k-1 of some step gave up waiting for a peer (results since then are void) */
+int ptta_comm_error(ptta_comm* c) {
+    if (!c || !c->local) return -1;
+    uint32_t v = 0;
+    if (cudaMemcpy(&v, (const char*)c->local + comm_error_off(), sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)v;
+}
+void ptta_comm_destroy(ptta_comm* c) {
+    if (!c) return;
+    for (int r = 0; r < PTTA_COMM_MAX_RANKS; ++r) if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
+    if (c->local) cudaFree(c->local);
+    delete c;
+}
+/* shared-model mode on: SyncBatchNorm statistics over all ranks + gradient all-reduce fused with Adam (comm = NULL: off).  Exchange slots
+ * are numbered in host call order, which is the same on every rank; kernels of different streams may reach their exchanges in any
+ * order (each exchange has its own flags, and the spinning kernels are a few blocks that never fill the machine).  Option two_streams = 0
+ * puts the whole step on one stream. */
+int ptta_msgchn_set_comm(ptta_msgchn* e, ptta_comm* c) {
+    PTTA_CHECK(e, "set_comm: null engine");
+    if (c) {
+        for (int r = 0; r < c->dev.world; ++r) PTTA_CHECK(c->dev.base[r] != nullptr, "set_comm: peer %d not opened (ptta_comm_open_peers)", r);
+        e->comm = c->dev;
+    } else {
+        e->comm = PeerComm();
+    }
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    return 0;
+}
+
 int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value) {
     PTTA_CHECK(e && name, "set_option: null argument");
     const std::string k = name;

@@ -3,6 +3,7 @@
 // NHWC bf16, single-channel maps fp32 [N,H,W].
 #pragma once
 #include "common.cuh"
+#include "peer_comm.cuh"
 #include <math_constants.h>
 
 namespace ptta {
@@ -986,11 +987,36 @@ __device__ __forceinline__ bool block_reduce_partials(const double* __restrict__
     return true;
 }
 
-__global__ void __launch_bounds__(FIN_THREADS) bn_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C, BnParams p, int training) {
+// sums of one BatchNorm call over ALL ranks (SyncBatchNorm semantics of the shared-model mode): the owner threads publish the rank's
+// (sum, sum of squares) / (sum dy, sum dy xhat) per channel, wait for every rank, and add the ranks' values in rank order
+__device__ __forceinline__ void bn_sums_all_ranks(const PeerComm& comm, int xid, int C, bool owner, int ch, double& a, double& b) {
+    const uint32_t tag = comm_tag(comm);
+    const size_t off = comm_bn_slot_off((int)(tag & 1u), xid);
+    if (owner) {
+        double* slot = reinterpret_cast<double*>(comm.base[comm.rank] + off);
+        slot[ch] = a; slot[C + ch] = b;
+    }
+    comm_publish_and_wait(comm, xid, tag);
+    if (owner) {
+        a = 0.0; b = 0.0;
+        for (int r = 0; r < comm.world; ++r) {
+            const double* slot = reinterpret_cast<const double*>(comm.base[r] + off);
+            a += ld_volatile_f64(slot + ch); b += ld_volatile_f64(slot + C + ch);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) bn_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C, BnParams p, int training,
+                                                                  const PeerComm comm, int xid) {
     PDL_SYNC();
     int ch; double a, b;
     if (training) {
-        if (!block_reduce_partials(partial, nblk, C, 2, ch, a, b)) return;
+        const bool owner = block_reduce_partials(partial, nblk, C, 2, ch, a, b);
+        if (comm.world > 1) {                                   // batch statistics over the global batch (SyncBatchNorm)
+            bn_sums_all_ranks(comm, xid, C, owner, ch, a, b);
+            count *= comm.world;
+        }
+        if (!owner) return;
         double m = a / (double)count;
         double var = b / (double)count - m * m;
         if (var < 0.0) var = 0.0;
@@ -1074,12 +1100,21 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
 __global__ void __launch_bounds__(FIN_THREADS) bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, long long count, int C,
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ k0, float* __restrict__ k1, float* __restrict__ k2) {
+                                       float* __restrict__ k0, float* __restrict__ k1, float* __restrict__ k2, const PeerComm comm, int xid) {
     PDL_SYNC();
     int ch; double a, b;
-    if (!block_reduce_partials(partial, nblk, C, 2, ch, a, b)) return;
-    if (dbeta) dbeta[ch] = (float)a;
-    if (dgamma) dgamma[ch] = (float)b;
+    const bool owner = block_reduce_partials(partial, nblk, C, 2, ch, a, b);
+    // parameter gradients stay LOCAL sums (the gradient all-reduce averages them, as DDP does); the data gradient uses the means over
+    // the global batch (torch SyncBatchNorm backward: all_reduce of sum_dy / sum_dy_xmu only)
+    if (owner) {
+        if (dbeta) dbeta[ch] = (float)a;
+        if (dgamma) dgamma[ch] = (float)b;
+    }
+    if (comm.world > 1) {
+        bn_sums_all_ranks(comm, xid, C, owner, ch, a, b);
+        count *= comm.world;
+    }
+    if (!owner) return;
     float g = gamma[ch] * invstd[ch];
     k0[ch] = g;
     k1[ch] = (float)((double)g * a / (double)count);
@@ -1359,6 +1394,38 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamChunk* __restrict__
 }
 __global__ void adam_advance_kernel(AdamHyper* hy) {
     PDL_SYNC(); hy->step += 1; }
+
+// Shared-model mode: mean all-reduce of the adapted-parameter gradients FUSED with the Adam update, one launch, one-shot over NVLink
+// peer memory.  Block = one chunk of the chunk table (as adam_kernel): it copies its part of the local gradient into the rank's slot, the
+// ranks rendezvous (peer_comm.cuh), and every block then sums the W copies of its chunk in rank order (bit-identical on all ranks),
+// scales by 1/W, writes the averaged gradient back (what DDP leaves in .grad) and applies Adam.  g_base: start of the flat gradient
+// buffer the chunk pointers point into.
+__global__ void __launch_bounds__(256) adam_allreduce_kernel(const AdamChunk* __restrict__ chunks, const AdamHyper* __restrict__ hy, const PeerComm comm,
+                                                             int xid, const float* __restrict__ g_base) {
+    PDL_SYNC();
+    const AdamChunk ck = chunks[blockIdx.x];
+    const uint32_t tag = comm_tag(comm);
+    const size_t off = comm_grad_off((int)(tag & 1u), comm.grad_floats), idx0 = (size_t)(ck.g - g_base);
+    float* mine = reinterpret_cast<float*>(comm.base[comm.rank] + off) + idx0;
+    for (int i = threadIdx.x; i < ck.n; i += 256) mine[i] = ck.g[i];
+    comm_publish_and_wait(comm, xid, tag);
+    const int t = hy->step + 1;
+    const double bc1 = 1.0 - pow(hy->beta1_d, (double)t);
+    const double bc2 = 1.0 - pow(hy->beta2_d, (double)t);
+    const float step_size = (float)(hy->lr_d / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float b2 = hy->beta2, omb1 = hy->one_minus_beta1, omb2 = hy->one_minus_beta2, eps = hy->eps, wd = hy->weight_decay;
+    const float inv_w = 1.f / (float)comm.world;
+    for (int i = threadIdx.x; i < ck.n; i += 256) {
+        float g = 0.f;
+        for (int r = 0; r < comm.world; ++r) g += ld_volatile_f32(reinterpret_cast<const float*>(comm.base[r] + off) + idx0 + i);
+        g *= inv_w;
+        const_cast<float*>(ck.g)[i] = g;
+        float p = ck.p[i], m = ck.m[i], v = ck.v[i];
+        adam_update(p, g, m, v, b2, omb1, omb2, eps, wd, step_size, bc2_sqrt);
+        ck.p[i] = p; ck.m[i] = m; ck.v[i] = v;
+    }
+}
 
 // -------------------------------------------------------------------------------------------------
 // weight packing: fp32 parameter -> bf16 [tap][O][I] operand of conv3x3_mma

@@ -70,6 +70,12 @@ class MsgChnEngine:
         """Kernel-dispatch options of include/ptta_b200.h (`ptta_msgchn_set_option`)."""
         check(self.L.ptta_msgchn_set_option(self.handle, name.encode(), int(value)), 'set_option')
 
+    def set_comm(self, comm):
+        """Shared-model mode (sharding.PeerCommunicator): SyncBatchNorm statistics over all ranks and the gradient all-reduce fused with
+        the Adam step, through NVLink peer memory inside the engine's own kernels.  None switches it off."""
+        check(self.L.ptta_msgchn_set_comm(self.handle, comm.handle if comm is not None else None), 'set_comm')
+        self._comm = comm               # keep the mapping alive as long as the engine uses it
+
     def close(self):
         if getattr(self, 'handle', None):
             torch.cuda.synchronize(self.device)
