@@ -618,7 +618,8 @@ def run_native(args):
         for i in range(args.steps):
             img, sp = dev_frames[(args.warmup + i) % RING]
             img_d.copy_(img, non_blocking=True); sp_d.copy_(sp, non_blocking=True)
-            run_step(img_d, sp_d, graph=use_graph)
+            for _ in range(args.inner_iter):                # src/tta_main.py:579: `inner_iter` adaptation steps on every batch
+                run_step(img_d, sp_d, graph=use_graph)
         e1.record(stream)
         barrier()
         ms_total = e0.elapsed_time(e1)
@@ -646,7 +647,8 @@ def run_native(args):
             for i in range(i0, i0 + args.steps):
                 pre.take(i)                                 # frame i: staged by the copy stream while step i-1 was running
                 pre.prefetch(i + 1)
-                run_step(img_d, sp_d, graph=use_graph)
+                for _ in range(args.inner_iter):
+                    run_step(img_d, sp_d, graph=use_graph)
                 reader.enqueue(model.last_losses_device(), i)   # D2H of this step's losses; looked at after the next step is launched
             e2e_losses = reader.drain()
             f1.record(stream)
@@ -687,6 +689,10 @@ def run_native(args):
     }
     if args.engine_opt:
         line['engine_options'] = args.engine_opt
+    if args.inner_iter != 1:
+        line['config']['inner_iter'] = args.inner_iter
+        line['config']['workload'] += ', inner_iter %d (TTA steps per frame, src/tta_main.py:579)' % args.inner_iter
+        line['gpu_launches'] *= args.inner_iter
     gflop_step = {'kitti': 210.5, 'void': 152.8}[args.workload] * args.batch
     line['step_tflops'] = gflop_step / (ms_total / args.steps)
     line['step_tflops_note'] = 'work performed per step (%.1f GFLOP: fwd + required dgrad/wgrad, rgb_encoder(0) cached, SURVEY.md 8d) / ms_per_step' % gflop_step
@@ -715,6 +721,7 @@ def main():
     ap.add_argument('--batch', type=int, default=1)
     ap.add_argument('--mode', default='shards', choices=['shards', 'shared', 'shared_nccl'], help='shards: independent sequence shard per GPU, no collective (default); shared: one shared model, NCCL all-reduce of the adapted-parameter gradients (BASELINE.json configs[4])')
     ap.add_argument('--no-graph', dest='graph', action='store_false', help='launch the step kernels eagerly instead of replaying the captured CUDA graph')
+    ap.add_argument('--inner-iter', type=int, default=1, help='adaptation steps per frame (src/tta_main.py:579; the indoor script bash/adapt/adapt_msgchn_scenenet.sh runs 3); a bench "step" is then one FRAME = inner_iter TTA steps')
     ap.add_argument('--no-extras', action='store_true', help='skip the roofline / cpu_baseline legs (profiling runs)')
     ap.add_argument('--engine-opt', action='append', default=[], metavar='NAME=VALUE', help='ptta_msgchn_set_option on the engine (dispatch experiments, e.g. tc_min_pixels=1000); not for headline runs')
     args = ap.parse_args()

@@ -295,7 +295,7 @@ def test_gemm(ops, m, n, k):
     assert_close_bf16(got, want, 'gemm %dx%dx%d' % (m, n, k))
 
 
-@pytest.mark.parametrize('m,n,k', [(300, 256, 64), (1000, 512, 512), (26752, 512, 512), (129, 768, 128)])
+@pytest.mark.parametrize('m,n,k', [(300, 256, 64), (1000, 512, 512), (26752, 512, 512), (129, 768, 128), (26752, 512, 32), (97, 512, 32), (40000, 256, 64)])
 def test_gemm_tcgen05(ops, m, n, k):
     g = torch.Generator().manual_seed(11)
     a = bf(torch.randn((m, k), generator=g))

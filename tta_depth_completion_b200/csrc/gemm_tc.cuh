@@ -1,9 +1,11 @@
 // C[M][N] (bf16) = A[M][K] (bf16, row-major) * B[N][K]^T (bf16, nn.Linear weight layout) + bias[N] on tcgen05:
 // TMA (SWIZZLE_128B boxes of 64 bf16 = 128 B rows) -> 4-stage shared-memory ring -> tcgen05.mma M128 x N256 x K16 with the
-// accumulator in TMEM (2 x 256 columns, double buffered) -> epilogue warps (tcgen05.ld, bias, bf16, 64 B stores).
+// accumulator in TMEM (2 x 256 columns, double buffered) -> four epilogue warps (tcgen05.ld, bias, bf16 into a SWIZZLE_128B staging
+// tile of 32 rows x 64 columns per warp, double buffered) -> TMA stores (whole 128 B lines; the tensor map clips the last row block).
 // Persistent CTAs, tiles ordered so that the two N-halves of one row block run back to back (A stays in L2).
-// Used for the 512 -> 512 Linear layers of the proxy heads (network_exp_msg_chn_adapt.py:1089-1098) and their data
-// gradient; K must be a multiple of 64 and N a multiple of 256 (other shapes stay on gemm_mma.cuh).
+// Used for the Linear layers of the proxy heads (network_exp_msg_chn_adapt.py:1089-1098: 32 -> 512, 512 -> 512) and their data
+// gradient; N must be a multiple of 256 and K a multiple of 64 -- or K = 32: the 64-wide boxes then read past the 32-column rows and TMA
+// zero-fills the upper half of every operand row, so the same kernel runs one K block whose second half contributes nothing.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -20,26 +22,30 @@ struct GemmTcCfg {
     static const int A_BYTES = BM * BK * 2;        // 16 KB
     static const int B_BYTES = BN * BK * 2;        // 32 KB
     static const int STAGE_BYTES = A_BYTES + B_BYTES;
-    static const int SMEM = 1024 + STAGES * STAGE_BYTES + 256;
+    static const int OUT_TILE = 32 * 128;          // one epilogue warp's staging tile: 32 rows x 64 columns of bf16
+    static const int SMEM = 1024 + STAGES * STAGE_BYTES + 4 * 2 * OUT_TILE + 256;
     static const int THREADS = 192;               // warp 0 TMA | warp 1 MMA + TMEM alloc | warps 2-5 epilogue
 };
 
 __global__ void __launch_bounds__(GemmTcCfg::THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                                                                       const __grid_constant__ CUtensorMap tmap_b, const GemmTcParams p) {
+                                                                       const __grid_constant__ CUtensorMap tmap_b,
+                                                                       const __grid_constant__ CUtensorMap tmap_c, const GemmTcParams p) {
     typedef GemmTcCfg C;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bar_s = smem_base + C::STAGES * C::STAGE_BYTES;
+    const uint32_t out_s = smem_base + C::STAGES * C::STAGE_BYTES;
+    const uint32_t bar_s = out_s + 4 * 2 * C::OUT_TILE;
     const uint32_t full = bar_s, empty = bar_s + 8 * C::STAGES, acc_full = bar_s + 16 * C::STAGES, acc_empty = acc_full + 16;
     const uint32_t tmem_slot = acc_empty + 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int num_tiles = p.m_tiles * p.n_tiles, KB = p.K / C::BK;
+    const int num_tiles = p.m_tiles * p.n_tiles, KB = (p.K + C::BK - 1) / C::BK;
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmap_a);
         tc::prefetch_tmap(&tmap_b);
+        tc::prefetch_tmap(&tmap_c);
         for (int i = 0; i < C::STAGES; ++i) { tc::mbar_init(full + 8 * i, 1); tc::mbar_init(empty + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + 8 * i, 1); tc::mbar_init(acc_empty + 8 * i, 128); }
         tc::fence_barrier_init();
@@ -94,35 +100,47 @@ __global__ void __launch_bounds__(GemmTcCfg::THREADS, 1) gemm_tc_kernel(const __
         }
     } else {
         const int q = warp & 3;
-        uint32_t t = 0;
+        unsigned char* stage = smem + (out_s - smem_base) + q * 2 * C::OUT_TILE;
+        const uint32_t stage_s = out_s + q * 2 * C::OUT_TILE;
+        uint32_t t = 0, nst = 0;             // nst: stores issued by this warp (staging buffer = nst & 1)
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
             const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
             const uint32_t as = t & 1;
-            const long long row = (long long)mt * C::BM + q * 32 + lane;
             tc::mbar_wait(acc_full + 8 * as, (t >> 1) & 1);
             tc::tc_fence_after();
 #pragma unroll 1
-            for (int ch = 0; ch < 8; ++ch) {
-                uint32_t v[32];
-                tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + ch * 32, v);
-                if (row < p.M) {
-                    const int col0 = nt * C::BN + ch * 32;
-                    bf16* dst = p.C + (size_t)row * p.N + col0;
+            for (int cp = 0; cp < 4; ++cp, ++nst) {                     // 64 output columns per round: one 128 B staging row per lane
+                const int col0 = nt * C::BN + cp * 64;
+                unsigned char* srow = stage + (nst & 1) * C::OUT_TILE + lane * 128;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");      // the store that used this buffer two rounds ago has read it
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + cp * 64 + h * 32, v);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         float f[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]) + (p.bias ? __ldg(p.bias + col0 + g * 8 + j) : 0.f);
+                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]) + (p.bias ? __ldg(p.bias + col0 + h * 32 + g * 8 + j) : 0.f);
                         uint4 ov;
                         ov.x = pack_bf162(f[0], f[1]); ov.y = pack_bf162(f[2], f[3]);
                         ov.z = pack_bf162(f[4], f[5]); ov.w = pack_bf162(f[6], f[7]);
-                        *reinterpret_cast<uint4*>(dst + g * 8) = ov;
+                        *reinterpret_cast<uint4*>(srow + (((h * 4 + g) ^ (lane & 7)) << 4)) = ov;
                     }
+                }
+                tc::fence_proxy_async();                                // generic-proxy writes -> visible to the TMA store
+                __syncwarp();
+                if (lane == 0 && (long long)mt * C::BM + q * 32 < p.M) {     // (a quarter that lies entirely below the matrix stores nothing)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&tmap_c), "r"(stage_s + (nst & 1) * C::OUT_TILE), "r"(col0), "r"(mt * C::BM + q * 32) : "memory");
+                    tc::bulk_store_commit();
                 }
             }
             tc::tc_fence_before();
             tc::mbar_arrive(acc_empty + 8 * as);
         }
+        if (lane == 0) tc::bulk_store_wait_read_all();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -132,7 +150,7 @@ __global__ void __launch_bounds__(GemmTcCfg::THREADS, 1) gemm_tc_kernel(const __
     }
 }
 
-// row-major [rows][cols] bf16 matrix, box {64, box_rows}, SWIZZLE_128B
+// row-major [rows][cols] bf16 matrix, box {64, box_rows}, SWIZZLE_128B (cols < 64: the box reaches past the row, TMA zero-fills)
 inline int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, int cols, int box_rows) {
     PFN_encodeTiled enc = get_encode_tiled();
     PTTA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
@@ -146,7 +164,7 @@ inline int make_tmap_2d(CUtensorMap* map, const void* ptr, long long rows, int c
     return 0;
 }
 
-inline bool gemm_tc_supported(long long M, int N, int K) { return M > 0 && N % 256 == 0 && K % 64 == 0 && K >= 64; }
+inline bool gemm_tc_supported(long long M, int N, int K) { return M > 0 && N % 256 == 0 && ((K % 64 == 0 && K >= 64) || K == 32); }
 
 inline int launch_gemm_tc(const bf16* A, const bf16* B, bf16* Cout, const float* bias, long long M, int N, int K, cudaStream_t st) {
     typedef GemmTcCfg C;
@@ -158,14 +176,15 @@ inline int launch_gemm_tc(const bf16* A, const bf16* B, bf16* Cout, const float*
         PTTA_CUDA(cudaGetDevice(&dev));
         PTTA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tcm;
     PTTA_TRY(make_tmap_2d(&ta, A, M, K, C::BM));
     PTTA_TRY(make_tmap_2d(&tb, B, N, K, C::BN));
+    PTTA_TRY(make_tmap_2d(&tcm, Cout, M, N, 32));
     GemmTcParams p; p.C = Cout; p.bias = bias; p.M = M; p.N = N; p.K = K;
     p.m_tiles = cdiv(M, C::BM); p.n_tiles = N / C::BN;
     int tiles = p.m_tiles * p.n_tiles;
     int grid = tiles < sms ? tiles : sms;
-    launch_k(gemm_tc_kernel, grid, C::THREADS, C::SMEM, st, ta, tb, p);
+    launch_k(gemm_tc_kernel, grid, C::THREADS, C::SMEM, st, ta, tb, tcm, p);
     return check_launch("gemm_tc");
 }
 
