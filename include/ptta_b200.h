@@ -56,6 +56,10 @@ int ptta_conv3x3_tc(const void* in_bf16, void* out_bf16, const void* wimage_bf16
  * conv reads, or the decoder sum s = ReLU(conv + skip) (network_exp_msg_chn_adapt.py:301-309).  add and add2 are mutually exclusive. */
 int ptta_conv3x3_tc_ex(const void* in_bf16, void* out_bf16, void* out2_bf16, const void* wimage_bf16, const float* bias, int n, int h, int w,
                        int relu_out, const void* mask_bf16, const void* add_bf16, const void* add2_bf16, ptta_stream_t stream);
+/* out = conv(in) + bias + up2(half) with up2 = F.interpolate(scale_factor=2, bilinear, align_corners=True) of the half-resolution map
+ * half [n, h/2, w/2, 32] (the cascade's `x = conv(.) + up(pre_x)`, network_exp_msg_chn_adapt.py:172-186, in ONE pass); out_relu (optional) = ReLU(out) */
+int ptta_conv3x3_tc_up2(const void* in_bf16, void* out_bf16, void* out_relu_bf16, const void* weight_image, const float* bias,
+                        const void* half_bf16, int n, int h, int w, ptta_stream_t stream);
 /* the 32->32 STRIDE-2 case (mode 1 of ptta_conv3x3: Conv2d(s2) forward, ConvTranspose2d(s2) data gradient) on tcgen05.
  * h, w = input size (even); out is [n, h/2, w/2, 32]; out_relu (optional) additionally receives ReLU(out). */
 int ptta_pack_conv_weight_tc_s2(const void* wpack_bf16, void* wimage_bf16, ptta_stream_t stream);

@@ -39,9 +39,20 @@ class Precision:
     fp32 weights).  Identity in the fp32 oracle.  Because the rounding is applied with `.to(dtype)`, autograd rounds the gradient
     arriving at each of these tensors as well -- the stored gradient maps of the native backward."""
 
-    def __init__(self, emulate=None):
+    def __init__(self, emulate=None, fuse_up2_min_pixels=6000):
         self.emulate = emulate
         self.dtype = {'bf16': torch.bfloat16, 'fp16': torch.float16}.get(emulate)
+        # the native path adds the upsampled map of the cascade in the conv epilogue (ONE rounding of the sum) on maps its tcgen05 conv
+        # takes (engine default tc_min_pixels), and in a separate pass (conv output rounded, then the sum rounded) on smaller maps
+        self.fuse_up2_min_pixels = fuse_up2_min_pixels
+
+    def conv_plus(self, y, add):
+        """stored activation of `conv output y + upsampled map add` at the native rounding points"""
+        if add is None:
+            return self.act(y)
+        if y.shape[0] * y.shape[2] * y.shape[3] < self.fuse_up2_min_pixels:
+            y = self.act(y)
+        return self.act(y + add)
 
     def act(self, x):
         if self.dtype is not None:
@@ -102,16 +113,17 @@ def _up2(x):
     return F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True)
 
 
-def _enc_block(sd, prefix, x, pr):
-    # ReLU, conv s2, ReLU, conv  (N:175-186)
+def _enc_block(sd, prefix, x, pr, add=None):
+    # ReLU, conv s2, ReLU, conv  (N:175-186); `add`: the upsampled map the caller adds to the result (N:201-209) -- the native path adds it
+    # in the conv epilogue, BEFORE the one rounding of the stored activation, and the emulation rounds at the same point
     x = pr.act(_conv(sd, prefix + '.1', F.relu(x), pr, stride=2))
-    return pr.act(_conv(sd, prefix + '.3', F.relu(x), pr))
+    return pr.conv_plus(_conv(sd, prefix + '.3', F.relu(x), pr), add)
 
 
-def _init_block(sd, prefix, x, pr):
+def _init_block(sd, prefix, x, pr, add=None):
     # conv, ReLU, conv (N:171-173)
     x = pr.act(_conv(sd, prefix + '.0', x, pr))
-    return pr.act(_conv(sd, prefix + '.2', F.relu(x), pr))
+    return pr.conv_plus(_conv(sd, prefix + '.2', F.relu(x), pr), add)
 
 
 def rgb_encoder(sd, rgb, pr=FP32):
@@ -125,15 +137,9 @@ def rgb_encoder(sd, rgb, pr=FP32):
 
 def depth_encoder(sd, prefix, inp, pre_x2=None, pre_x3=None, pre_x4=None, pr=FP32):
     # N:196-211
-    x0 = _init_block(sd, prefix + '.init', inp, pr)
-    if pre_x4 is not None:
-        x0 = pr.act(x0 + _up2(pre_x4))
-    x1 = _enc_block(sd, prefix + '.enc1', x0, pr)
-    if pre_x3 is not None:
-        x1 = pr.act(x1 + _up2(pre_x3))
-    x2 = _enc_block(sd, prefix + '.enc2', x1, pr)
-    if pre_x2 is not None:
-        x2 = pr.act(x2 + _up2(pre_x2))
+    x0 = _init_block(sd, prefix + '.init', inp, pr, None if pre_x4 is None else _up2(pre_x4))
+    x1 = _enc_block(sd, prefix + '.enc1', x0, pr, None if pre_x3 is None else _up2(pre_x3))
+    x2 = _enc_block(sd, prefix + '.enc2', x1, pr, None if pre_x2 is None else _up2(pre_x2))
     return x0, x1, x2
 
 

@@ -308,6 +308,24 @@ def test_gemm_tcgen05(ops, m, n, k):
     assert float((got - got2).abs().max()) <= 2.0 ** -6 * float(want.abs().max())     # both accumulate in fp32
 
 
+@pytest.mark.parametrize('n,h,w', [(1, 16, 128), (2, 24, 300), (1, 88, 304), (1, 352, 1216)])
+def test_conv_tcgen05_fused_upsampled_addend(ops, n, h, w):
+    """x = conv(a) + up2(pre) in ONE pass (epilogue of conv3x3_tc_kernel gathers the four half-resolution neighbours) vs torch
+    (F.conv2d + F.interpolate align_corners=True on the same bf16 inputs) and vs the two-pass form (conv, then add_up2_c32)"""
+    g = torch.Generator().manual_seed(23 + h)
+    x = bf(torch.relu(torch.randn((n, 32, h, w), generator=g)))
+    half = bf(torch.randn((n, 32, h // 2, w // 2), generator=g))
+    wt = torch.randn((32, 32, 3, 3), generator=g) * (2.0 / 288) ** 0.5
+    b = torch.randn((32,), generator=g) * 0.1
+    want = F.conv2d(x, bf(wt), b, padding=1) + F.interpolate(half, scale_factor=2, mode='bilinear', align_corners=True)
+    wp = ops.pack_conv_weight(wt.to(DEV), 'conv_fwd')
+    out, out_relu = ops.conv3x3_tc_up2(nhwc(x), wp, nhwc(half), b.to(DEV))
+    assert_close_bf16(nchw(out), bf(want), 'conv_tc + up2', ulps=2.0)
+    assert torch.equal(out_relu, torch.relu(out.float()).to(torch.bfloat16))
+    two = ops.add_up2_c32(ops.conv3x3_tc(nhwc(x), wp, b.to(DEV)), nhwc(half))       # rounds twice (<= 2 x 2^-8 each way) vs once
+    assert_close_bf16(nchw(out), nchw(two), 'fused vs two-pass', ulps=3.0)
+
+
 @pytest.mark.parametrize('n,h,w', [(1, 16, 128), (1, 24, 300), (2, 19, 38), (1, 88, 304), (3, 64, 514), (1, 352, 1216)])
 def test_conv_tcgen05_matches_mma(ops, n, h, w):
     """the tcgen05 conv is bit-identical to the mma.sync kernel (same bf16 products, fp32 accumulation of 288 terms)"""

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "conv_mma.cuh"
+#include "small_kernels.cuh"   // up2_coord / up2_scale (bilinear x2, align_corners = True)
 
 namespace ptta {
 
@@ -24,6 +25,8 @@ struct ConvTcParams {
     int relu_out;        // store ReLU(result) (producer-side activation for consumers that only read ReLU(x))
     int strips, segs_y, rows_per_seg, total_segs;      // stride-2 kernel: fixed row segments per strip
     int rows_per_cta, total_rows;                      // stride-1 kernel: contiguous range of the (image, strip, row) sequence per CTA
+    const bf16* up2;     // optional: out = conv + bias + up2(half-resolution map [N][H/2][W/2][32]) (bilinear x2, align_corners = True): the
+                         // cascade's `x = conv(.) + F.interpolate(pre_x)` (network_exp_msg_chn_adapt.py:172-186) without a pass of its own
     // 32 -> 1 channel form (conv3x3_tc_head_kernel): fp32 output plane, optional fp32 addend plane, scalar bias
     float* out_f32; const float* add_f32; float bias0;
 };
@@ -126,10 +129,14 @@ __global__ void pack_conv_weight_tc_kernel(const bf16* __restrict__ pack, bf16* 
 // quarter row (32 pairs x 128 B; the tensor map clips the ragged right edge), double buffered.  Every mbarrier has one
 // arrival per phase except slot_empty (one per epilogue warp).
 __device__ __forceinline__ void conv_tc_pixel(const uint32_t (&v)[32], const float (&bias)[32], const uint4* mk, const uint4* ad, int relu_out,
-                                              uint4 (&ov)[4]) {
+                                              uint4 (&ov)[4], const float* up = nullptr) {
     float f[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]) + bias[c];
+    if (up) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) f[c] += up[c];
+    }
     if (mk) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -369,10 +376,41 @@ __device__ __forceinline__ void conv3x3_tc_body(const CUtensorMap& tmap_in, cons
             const int xw = sx * 256 + q * 64;                                // first pixel of this quarter
             const int vp = min(32, (p.W - xw) / 2);                          // valid pixel pairs of this quarter (may be <= 0)
             const bool act = lane < vp;
+            // bilinear x2 addend: this thread's column pair and weights are the same for every row of the segment
+            int ux0 = 0, ux1 = 0; float ulx0 = 0.f, ulx1 = 0.f;
+            const int uh2 = p.H >> 1, uw2 = p.W >> 1;
+            if (p.up2 && act) up2_coord(xw + 2 * lane + par, uw2, up2_scale(uw2), ux0, ux1, ulx0, ulx1);
             for (int y = y0; y < y1; ++y, ++t) {
                 const uint32_t sl = t % C::NSLOT;
                 // this thread's pixel: 64 contiguous bytes of every NHWC map; mask / add are fetched BEFORE waiting for the accumulators
                 const size_t off = (((size_t)n * p.H + y) * p.W + xw + 2 * lane + par) * 32;
+                float up[32];
+                if (p.up2) {
+                    if (act) {
+                        int uy0, uy1; float uly0, uly1;
+                        up2_coord(y, uh2, up2_scale(uh2), uy0, uy1, uly0, uly1);
+                        const bf16* hb = p.up2 + (size_t)n * uh2 * uw2 * 32;
+                        const uint4* r00 = reinterpret_cast<const uint4*>(hb + ((size_t)uy0 * uw2 + ux0) * 32);
+                        const uint4* r01 = reinterpret_cast<const uint4*>(hb + ((size_t)uy0 * uw2 + ux1) * 32);
+                        const uint4* r10 = reinterpret_cast<const uint4*>(hb + ((size_t)uy1 * uw2 + ux0) * 32);
+                        const uint4* r11 = reinterpret_cast<const uint4*>(hb + ((size_t)uy1 * uw2 + ux1) * 32);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint4 a00 = __ldg(r00 + g), a01 = __ldg(r01 + g), a10 = __ldg(r10 + g), a11 = __ldg(r11 + g);
+                            const uint32_t *u00 = reinterpret_cast<const uint32_t*>(&a00), *u01 = reinterpret_cast<const uint32_t*>(&a01);
+                            const uint32_t *u10 = reinterpret_cast<const uint32_t*>(&a10), *u11 = reinterpret_cast<const uint32_t*>(&a11);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f00 = unpack_bf162(u00[j]), f01 = unpack_bf162(u01[j]), f10 = unpack_bf162(u10[j]), f11 = unpack_bf162(u11[j]);
+                                up[g * 8 + j * 2] = uly0 * (ulx0 * f00.x + ulx1 * f01.x) + uly1 * (ulx0 * f10.x + ulx1 * f11.x);
+                                up[g * 8 + j * 2 + 1] = uly0 * (ulx0 * f00.y + ulx1 * f01.y) + uly1 * (ulx0 * f10.y + ulx1 * f11.y);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) up[c] = 0.f;
+                    }
+                }
                 uint4 mk[4], ad[4];
                 if (p.mask) {
 #pragma unroll
@@ -391,7 +429,7 @@ __device__ __forceinline__ void conv3x3_tc_body(const CUtensorMap& tmap_in, cons
                 if (lane == 0) tc::mbar_arrive(slot_empty + 8 * sl);
                 if (vp <= 0) continue;                   // whole quarter right of the image: both of its warps skip
                 uint4 ov[4];
-                conv_tc_pixel(v, bias, p.mask ? mk : nullptr, p.add ? ad : nullptr, p.relu_out, ov);
+                conv_tc_pixel(v, bias, p.mask ? mk : nullptr, p.add ? ad : nullptr, p.relu_out, ov, p.up2 ? up : nullptr);
                 const uint32_t buf = (t & 1) * C::OUT_TILE;
                 unsigned char* srow = smem + (stage_q - smem_base) + buf + lane * 128;
 #pragma unroll
@@ -575,6 +613,7 @@ inline int launch_conv_tc(const bf16* in, ConvTcParams p, cudaStream_t st) {
     }
     PTTA_CHECK(conv_tc_supported(p.N, p.H, p.W), "conv3x3_tc: W=%d must be even", p.W);
     PTTA_CHECK(!p.relu_in, "conv3x3_tc: ReLU-on-load is not supported (producers store ReLU(x): relu_out)");
+    PTTA_CHECK(!p.up2 || ((p.H & 1) == 0 && (p.W & 1) == 0), "conv3x3_tc: the x2-upsampled addend needs even H, W (got %dx%d)", p.H, p.W);
     const int grid = conv_tc_split(p, sms);
     // copies: the cache may be cleared by a later lookup, the kernel takes the maps by value
     const CUtensorMap* m = nullptr;

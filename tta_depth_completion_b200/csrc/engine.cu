@@ -182,6 +182,7 @@ struct ptta_msgchn {
     LinearLayer proj0, proj3, pred0, pred3;
     bf16* projpred_pack = nullptr; float* projpred_bias = nullptr;   // pred.0 o proj.3 as one Linear layer (zero-image rows: emb = pred(proj(z)))
     bool fuse_projpred = true;
+    bool fuse_up2 = true;            // x = conv(.) + up2(pre_x) in the epilogue of the tcgen05 conv (option fuse_up2 = 0: separate add_up2 pass)
     // shared-model mode (ptta_msgchn_set_comm): SyncBatchNorm sums and the gradient all-reduce go through peer memory (peer_comm.cuh)
     PeerComm comm;
     int next_xid = 0;                // exchange slots are handed out in call order; every rank runs the same sequence
@@ -445,7 +446,7 @@ struct ptta_msgchn {
         partial3 = allocv<double>(partial_doubles);
         losses = (LossScalars*)arena.take(sizeof(LossScalars));
         reg("losses", losses, 0, 5, 1, 1, 1);
-        loss_map_blocks = std::min(cdiv((long long)H * W, LOSS_BLOCK * 4), 256);
+        loss_map_blocks = std::min(cdiv((long long)H * W, LOSS_BLOCK * 4), 1184);
         loss_cos_blocks = (int)std::min<long long>(std::max<long long>(cdiv(R, 8), 1), 1184);
         loss_map_partial = allocv<double>((size_t)N * loss_map_blocks * 4);
         loss_cos_partial = allocv<double>(loss_cos_blocks);
@@ -669,20 +670,26 @@ struct ptta_msgchn {
         return launch_conv_tc_t2(in.p, p, st);
     }
     int conv_tc(const bf16* image, const float* bias, const Map32& in, const Map32& out, int relu_out, const bf16* mask, const bf16* add,
-                bf16* out2 = nullptr, bool stride2 = false, const bf16* add2 = nullptr) {
+                bf16* out2 = nullptr, bool stride2 = false, const bf16* add2 = nullptr, const bf16* up2 = nullptr) {
         ConvTcParams p; memset(&p, 0, sizeof(p));
         p.w = image; p.bias = bias; p.out = out.p; p.out2 = out2; p.add2 = add2; p.mask = mask; p.add = add; p.N = in.n; p.H = in.h; p.W = in.w;
+        p.up2 = up2;
         p.relu_out = relu_out;
         return stride2 ? launch_conv_tc_s2(in.p, p, st) : launch_conv_tc(in.p, p, st);
     }
     // relu_out: the output is only ever read through a ReLU (or as a ReLU mask), so ReLU(x) is what gets stored
     // out2 (optional): a second copy holding ReLU(out), for outputs that are read both raw and through a tensor-core conv
     // add2 (with out2): out2 = ReLU(out + add2) -- the decoder sums s = ReLU(conv(..) + skip) without a separate pass
+    // true when conv_fwd(L, in, ...) runs on the stride-1 tcgen05 kernel, whose epilogue can add a x2-upsampled half-resolution map
+    bool can_fuse_up2(const ConvLayer& L, const Map32& in) const {
+        return fuse_up2 && L.img_fwd && L.mode_fwd == MODE_S1 && use_tc(in) && (in.h & 1) == 0 && (in.w & 1) == 0;
+    }
     int conv_fwd(const ConvLayer& L, const Map32& in, const Map32& out, int pro, const BnState* probn = nullptr, int relu_out = 0,
-                 bf16* out2 = nullptr, const bf16* add2 = nullptr) {
+                 bf16* out2 = nullptr, const bf16* add2 = nullptr, const bf16* up2 = nullptr) {
         if (L.img_fwd && pro == PRO_NONE) {
             if (L.mode_fwd == MODE_S1 && use_tc(in))
-                return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr, out2, false, add2);
+                return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr, out2, false, add2, up2);
+            PTTA_CHECK(up2 == nullptr, "conv_fwd: the upsampled addend is fused by the stride-1 tcgen05 kernel only");
             if (L.mode_fwd == MODE_S2 && use_tc_s2(in) && !add2)
                 return conv_tc(L.img_fwd, L.has_bias ? L.b : nullptr, in, out, relu_out, nullptr, nullptr, out2, true);
             if (L.mode_fwd == MODE_T2 && use_tc_t2(in) && !add2 && !out2)
@@ -904,14 +911,28 @@ struct ptta_msgchn {
         // a0, t1, t2 hold ReLU(.) (stored by their producers): the stride-1 convs need no prologue
         // x0 / x1 are needed raw (decoder sums, masks) AND through ReLU by the stride-2 convs: whoever writes them last also
         // writes the ReLU copy
-        PTTA_TRY(conv_fwd(Wt.init2, A.a0, A.x0, PRO_NONE, nullptr, 0, pre_x4 ? nullptr : A.x0r.p));
-        if (pre_x4) PTTA_TRY(add_up2(A.x0, *pre_x4, A.x0r.p));
+        // x_k = conv(.) + up2(pre_x): the upsampled addend rides in the epilogue of the tcgen05 conv (no pass of its own); maps too small
+        // for that kernel keep the separate add_up2 pass
+        if (pre_x4 && can_fuse_up2(Wt.init2, A.a0)) {
+            PTTA_TRY(conv_fwd(Wt.init2, A.a0, A.x0, PRO_NONE, nullptr, 0, A.x0r.p, nullptr, pre_x4->p));
+        } else {
+            PTTA_TRY(conv_fwd(Wt.init2, A.a0, A.x0, PRO_NONE, nullptr, 0, pre_x4 ? nullptr : A.x0r.p));
+            if (pre_x4) PTTA_TRY(add_up2(A.x0, *pre_x4, A.x0r.p));
+        }
         PTTA_TRY(conv_fwd(Wt.e1a, A.x0r, A.t1, PRO_NONE, nullptr, 1));
-        PTTA_TRY(conv_fwd(Wt.e1b, A.t1, A.x1, PRO_NONE, nullptr, 0, pre_x3 ? nullptr : A.x1r.p));
-        if (pre_x3) PTTA_TRY(add_up2(A.x1, *pre_x3, A.x1r.p));
+        if (pre_x3 && can_fuse_up2(Wt.e1b, A.t1)) {
+            PTTA_TRY(conv_fwd(Wt.e1b, A.t1, A.x1, PRO_NONE, nullptr, 0, A.x1r.p, nullptr, pre_x3->p));
+        } else {
+            PTTA_TRY(conv_fwd(Wt.e1b, A.t1, A.x1, PRO_NONE, nullptr, 0, pre_x3 ? nullptr : A.x1r.p));
+            if (pre_x3) PTTA_TRY(add_up2(A.x1, *pre_x3, A.x1r.p));
+        }
         PTTA_TRY(conv_fwd(Wt.e2a, A.x1r, A.t2, PRO_NONE, nullptr, 1));
-        PTTA_TRY(conv_fwd(Wt.e2b, A.t2, A.x2, PRO_NONE));
-        if (pre_x2) PTTA_TRY(add_up2(A.x2, *pre_x2));
+        if (pre_x2 && can_fuse_up2(Wt.e2b, A.t2)) {
+            PTTA_TRY(conv_fwd(Wt.e2b, A.t2, A.x2, PRO_NONE, nullptr, 0, nullptr, nullptr, pre_x2->p));
+        } else {
+            PTTA_TRY(conv_fwd(Wt.e2b, A.t2, A.x2, PRO_NONE));
+            if (pre_x2) PTTA_TRY(add_up2(A.x2, *pre_x2));
+        }
         return 0;
     }
     // cx0/cx1/cx2: rgb features at the resolutions of x0/x1/x2; out = prediction [+ add]
@@ -1332,6 +1353,14 @@ int ptta_conv3x3_tc_ex(const void* in, void* out, void* out2, const void* wimage
     return launch_conv_tc((const bf16*)in, p, (cudaStream_t)stream);
 }
 
+int ptta_conv3x3_tc_up2(const void* in, void* out, void* out_relu, const void* wimage, const float* bias, const void* half, int n, int h, int w,
+                        ptta_stream_t stream) {
+    PTTA_CHECK(in && out && wimage && half, "conv3x3_tc_up2: null argument");
+    ConvTcParams p; memset(&p, 0, sizeof(p));
+    p.w = (const bf16*)wimage; p.bias = bias; p.out = (bf16*)out; p.out2 = (bf16*)out_relu; p.up2 = (const bf16*)half; p.N = n; p.H = h; p.W = w;
+    return launch_conv_tc((const bf16*)in, p, (cudaStream_t)stream);
+}
+
 int ptta_pack_conv_weight_tc(const void* wpack, void* image, ptta_stream_t stream) {
     PTTA_CHECK(wpack && image, "pack_conv_weight_tc: null argument");
     launch_k(pack_conv_weight_tc_kernel, cdiv(9 * 32 * 4, 256), 256, 0, (cudaStream_t)stream, (const bf16*)wpack, (bf16*)image);
@@ -1537,7 +1566,7 @@ __global__ void adam_flat_dev_kernel(float* p, const float* g, float* m, float* 
 struct TtaLossLayout { size_t scalars, map_partial, cos_partial, rowstat, total; int map_blocks, cos_blocks; };
 static TtaLossLayout tta_loss_layout(int n, int h, int w, long long rows) {
     TtaLossLayout L;
-    L.map_blocks = std::min(cdiv((long long)h * w, LOSS_BLOCK * 4), 256);
+    L.map_blocks = std::min(cdiv((long long)h * w, LOSS_BLOCK * 4), 1184);
     L.cos_blocks = (int)std::min<long long>(std::max<long long>(cdiv(rows, 8), 1), 1184);
     size_t o = 0;
     L.scalars = o; o += 512;
@@ -1827,6 +1856,7 @@ int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value) {
     else if (k == "two_streams") e->two_streams = value != 0;
     else if (k == "fuse_dec_sums") e->fuse_dec_sums = value != 0;
     else if (k == "fuse_projpred") e->fuse_projpred = value != 0;
+    else if (k == "fuse_up2") e->fuse_up2 = value != 0;
     else PTTA_CHECK(false, "set_option: unknown option '%s'", name);
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }   // a captured step bakes the dispatch in
     return 0;

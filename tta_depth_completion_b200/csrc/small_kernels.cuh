@@ -1187,8 +1187,9 @@ __global__ void __launch_bounds__(LOSS_BLOCK) loss_map_reduce_kernel(const float
     const float* pn = pred + n * HW; const float* dn = d + n * HW; const float* vn = v + n * HW;
     const float* in = img + n * HW * 3;
     double s_sd = 0.0, s_v = 0.0, s_x = 0.0, s_y = 0.0;
-    for (long long i = (long long)blockIdx.x * LOSS_BLOCK + threadIdx.x; i < HW; i += (long long)gridDim.x * LOSS_BLOCK) {
-        int x = i % W, y = i / W;
+    const int hw = (int)HW;                 // one image: < 2^31 pixels (32-bit index math: the 64-bit div / mod cost more than the loads)
+    for (int i = blockIdx.x * LOSS_BLOCK + threadIdx.x; i < hw; i += gridDim.x * LOSS_BLOCK) {
+        const int y = i / W, x = i - y * W;
         float p0 = pn[i];
         float dd = dn[i];
         if (do_clamp) dd = fminf(fmaxf(dd, 0.f), cap);

@@ -129,6 +129,17 @@ def conv3x3_tc_ex(x, wpack, bias=None, relu_out=False, mask=None, add=None, add2
     return out, out2
 
 
+def conv3x3_tc_up2(x, wpack, half, bias=None):
+    """(conv(x) + bias + up2(half), ReLU of it) in one pass of the tcgen05 conv; half: [n, h/2, w/2, 32]"""
+    _need(x, torch.bfloat16, 'x')
+    _need(half, torch.bfloat16, 'half')
+    n, h, w, _ = x.shape
+    wimage = pack_conv_weight_tc(wpack)
+    out, out2 = torch.empty_like(x), torch.empty_like(x)
+    check(_lib.lib().ptta_conv3x3_tc_up2(ptr(x), ptr(out), ptr(out2), ptr(wimage), ptr(bias), ptr(half), n, h, w, _stream()), 'conv3x3_tc_up2')
+    return out, out2
+
+
 def conv3x3_tc_s2(x, wpack, bias=None, relu_out=False, mask=None, add=None, want_relu_copy=False):
     """32->32 stride-2 conv on tcgen05 (operand conventions of conv3x3 with MODE_S2, no ReLU-on-load); H, W even.
     Returns out, or (out, relu(out)) with want_relu_copy."""
