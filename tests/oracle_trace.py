@@ -42,6 +42,10 @@ def trace_step(sd, image_raw, sparse_raw, cap, w_sd=1.0, w_sm=1.0, w_cos=0.1, pr
         e2 = O.depth_encoder(sd, 'depth_encoder2', torch.cat((d12, p12), 1), dc1[0], dc1[1], dc1[2], pr)
         for i, t in enumerate(e2):
             keep('%s.e2.x%d' % (tag, i), t)
+        # what the native path stores of x0 / x1 (their raw values are read by nothing): the ReLU copies and the decoder's sums
+        for i in (0, 1):
+            T['%s.e2.x%dr' % (tag, i)] = F.relu(e2[i])
+            T['%s.d2.x%d' % (tag, i)] = pr.act(e2[i] + enc_c[1 + i])
         dc2 = O.depth_decoder(sd, 'depth_decoder2', e2, enc_c[1:4], pr)
         for nm, t in zip(('x2', 'x3', 'x4', 'out'), dc2):
             keep('%s.d2.%s' % (tag, nm), t)
@@ -49,6 +53,10 @@ def trace_step(sd, image_raw, sparse_raw, cap, w_sd=1.0, w_sm=1.0, w_cos=0.1, pr
         e3 = O.depth_encoder(sd, 'depth_encoder3', torch.cat((d, p11), 1), dc2[0], dc2[1], dc2[2], pr)
         for i, t in enumerate(e3):
             keep('%s.e3.x%d' % (tag, i), t)
+        for i in (0, 1):
+            T['%s.e3.x%dr' % (tag, i)] = F.relu(e3[i])
+            if with_dec3:
+                T['%s.d3.x%d' % (tag, i)] = pr.act(e3[i] + enc_c[i])
         if not with_dec3:
             return None, e3
         dc3 = O.depth_decoder(sd, 'depth_decoder3', e3, enc_c[0:3], pr)

@@ -34,8 +34,8 @@ ALIGNED = [n for n in golden_names() if not n.endswith('_pad')]
 
 FWD_NAMES = ['depth_clamped', 'd12', 'd14', 'real.c0', 'real.c1', 'real.c2raw', 'real.c3', 'real.c4', 'real.c2',
              'real.e1.x0', 'real.e1.x1', 'real.e1.x2', 'real.d1.x2', 'real.d1.x3', 'real.d1.x4', 'real.d1.out', 'real.p12',
-             'real.e2.x0', 'real.e2.x1', 'real.e2.x2', 'real.d2.x2', 'real.d2.x3', 'real.d2.x4', 'real.d2.out', 'real.p11',
-             'real.e3.x0', 'real.e3.x1', 'real.e3.x2', 'real.d3.x2', 'real.d3.x3', 'real.d3.x4', 'real.output',
+             'real.e2.x0r', 'real.e2.x1r', 'real.e2.x2', 'real.d2.x0', 'real.d2.x1', 'real.d2.x2', 'real.d2.x3', 'real.d2.x4', 'real.d2.out', 'real.p11',
+             'real.e3.x0r', 'real.e3.x1r', 'real.e3.x2', 'real.d3.x0', 'real.d3.x1', 'real.d3.x2', 'real.d3.x3', 'real.d3.x4', 'real.output',
              'zc1', 'zc2', 'zc3', 'zc4', 'zero.c2', 'zero.d1.out', 'zero.e2.x2', 'zero.d2.out', 'zero.e3.x2', 'emb', 'ref']
 GRAD_NAMES = ('g_output', 'g_ref', 'g_p11', 'g_p12', 'g_out14', 'g_c2')
 

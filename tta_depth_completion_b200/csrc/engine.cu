@@ -130,7 +130,8 @@ struct LinearLayer {
 struct EncW { StemLayer init0; ConvLayer init2, e1a, e1b, e2a, e2b, e3a, e3b, e4a, e4b; int nenc = 2; };
 struct DecW { ConvLayer d2a, d2b, d1a, d1b, p1; HeadLayer p3; };
 
-struct EncAct { Map32 a0, x0, t1, x1, t2, x2; Map32 x0r, x1r; };   // x0r / x1r = ReLU(x0) / ReLU(x1): inputs of the stride-2 convs
+struct EncAct { Map32 a0, x0, t1, x1, t2, x2; Map32 x0r, x1r;    // x0r / x1r = ReLU(x0) / ReLU(x1): inputs of the stride-2 convs
+                bool sum0_done = false, sum1_done = false; };      // the decoder's x0 / x1 sums were already written by this encoder's conv epilogues
 struct DecAct { Map32 x2, x1, x0, u2, x3, s1, u1, x4, s0, h; Map32 x2r; Map1 out; };   // x2r = ReLU(x2): input of the transposed conv dec2.1
 struct Branch {
     Map32 c[5];            // rgb features (c[2] after the meta layer)
@@ -182,6 +183,9 @@ struct ptta_msgchn {
     LinearLayer proj0, proj3, pred0, pred3;
     bf16* projpred_pack = nullptr; float* projpred_bias = nullptr;   // pred.0 o proj.3 as one Linear layer (zero-image rows: emb = pred(proj(z)))
     bool fuse_projpred = true;
+    bool fuse_enc_sums = false;      // decoder sums x0 + c0, x1 + c1 written by the encoder's conv epilogues (needs fuse_up2).  Measured 722 -> 733
+                                     // frames/s: the passes it removes (dec_sums 48 -> 11 us) come back as epilogue time of the tcgen05 conv, and the
+                                     // oracle's bf16 emulation does not round at its points -- off by default, kept as a tested option
     bool fuse_up2 = true;            // x = conv(.) + up2(pre_x) in the epilogue of the tcgen05 conv (option fuse_up2 = 0: separate add_up2 pass)
     // shared-model mode (ptta_msgchn_set_comm): SyncBatchNorm sums and the gradient all-reduce go through peer memory (peer_comm.cuh)
     PeerComm comm;
@@ -336,7 +340,7 @@ struct ptta_msgchn {
         A.a0 = alloc32((tag + ".a0").c_str(), h, w); A.x0 = alloc32((tag + ".x0").c_str(), h, w);
         A.t1 = alloc32((tag + ".t1").c_str(), h / 2, w / 2); A.x1 = alloc32((tag + ".x1").c_str(), h / 2, w / 2);
         A.t2 = alloc32((tag + ".t2").c_str(), h / 4, w / 4); A.x2 = alloc32((tag + ".x2").c_str(), h / 4, w / 4);
-        A.x0r = alloc32(nullptr, h, w); A.x1r = alloc32(nullptr, h / 2, w / 2);
+        A.x0r = alloc32((tag + ".x0r").c_str(), h, w); A.x1r = alloc32((tag + ".x1r").c_str(), h / 2, w / 2);
     }
     void plan_dec_act(DecAct& A, const std::string& tag, int h, int w) {   // h,w = resolution of x0 / out
         A.x2 = alloc32((tag + ".x2").c_str(), h / 4, w / 4); A.x1 = alloc32((tag + ".x1").c_str(), h / 2, w / 2);
@@ -670,10 +674,10 @@ struct ptta_msgchn {
         return launch_conv_tc_t2(in.p, p, st);
     }
     int conv_tc(const bf16* image, const float* bias, const Map32& in, const Map32& out, int relu_out, const bf16* mask, const bf16* add,
-                bf16* out2 = nullptr, bool stride2 = false, const bf16* add2 = nullptr, const bf16* up2 = nullptr) {
+                bf16* out2 = nullptr, bool stride2 = false, const bf16* add2 = nullptr, const bf16* up2 = nullptr, int out2_pre_add = 0) {
         ConvTcParams p; memset(&p, 0, sizeof(p));
         p.w = image; p.bias = bias; p.out = out.p; p.out2 = out2; p.add2 = add2; p.mask = mask; p.add = add; p.N = in.n; p.H = in.h; p.W = in.w;
-        p.up2 = up2;
+        p.up2 = up2; p.out2_pre_add = out2_pre_add;
         p.relu_out = relu_out;
         return stride2 ? launch_conv_tc_s2(in.p, p, st) : launch_conv_tc(in.p, p, st);
     }
@@ -904,24 +908,38 @@ struct ptta_msgchn {
         PTTA_TRY(bn_forward_stats(metaBn2, B.bn2, B.mg.p, rows, training, defer_running));
         return bn_apply(B.mg.p, B.c2raw.p, B.c[2].p, rows, 32, B.bn2, 0);
     }
+    // sum0 / sum1 (optional, with c0 / c1): the decoder that follows needs x0 + c0 and x1 + c1 (rgb features) and nothing else reads x0 / x1
+    // raw, so on the tcgen05 path the conv epilogue writes the SUM as its first output and ReLU(x) as its second (A.sum*_done tells
+    // run_decoder); otherwise x is stored raw and dec_sums adds later
     int run_encoder(const EncW& Wt, EncAct& A, const float* p0, const float* p1, const Map32* pre_x4, const Map32* pre_x3,
-                    const Map32* pre_x2) {
+                    const Map32* pre_x2, const Map32* sum0 = nullptr, const Map32* c0 = nullptr, const Map32* sum1 = nullptr,
+                    const Map32* c1 = nullptr) {
         const long long hw = (long long)A.a0.h * A.a0.w;
         PTTA_TRY(stem(Wt.init0, p0, hw, 1.f, 0.f, p1 ? p1 : p0, hw, 1.f, 0.f, p0, hw, 0.f, 0.f, A.a0));
         // a0, t1, t2 hold ReLU(.) (stored by their producers): the stride-1 convs need no prologue
-        // x0 / x1 are needed raw (decoder sums, masks) AND through ReLU by the stride-2 convs: whoever writes them last also
-        // writes the ReLU copy
+        // x0 / x1 are needed through ReLU by the stride-2 convs (and as ReLU masks in backward): whoever writes them last also writes the ReLU copy
         // x_k = conv(.) + up2(pre_x): the upsampled addend rides in the epilogue of the tcgen05 conv (no pass of its own); maps too small
         // for that kernel keep the separate add_up2 pass
+        A.sum0_done = A.sum1_done = false;
         if (pre_x4 && can_fuse_up2(Wt.init2, A.a0)) {
-            PTTA_TRY(conv_fwd(Wt.init2, A.a0, A.x0, PRO_NONE, nullptr, 0, A.x0r.p, nullptr, pre_x4->p));
+            if (sum0 && fuse_enc_sums) {
+                PTTA_TRY(conv_tc(Wt.init2.img_fwd, Wt.init2.b, A.a0, *sum0, 0, nullptr, c0->p, A.x0r.p, false, nullptr, pre_x4->p, 1));
+                A.sum0_done = true;
+            } else {
+                PTTA_TRY(conv_fwd(Wt.init2, A.a0, A.x0, PRO_NONE, nullptr, 0, A.x0r.p, nullptr, pre_x4->p));
+            }
         } else {
             PTTA_TRY(conv_fwd(Wt.init2, A.a0, A.x0, PRO_NONE, nullptr, 0, pre_x4 ? nullptr : A.x0r.p));
             if (pre_x4) PTTA_TRY(add_up2(A.x0, *pre_x4, A.x0r.p));
         }
         PTTA_TRY(conv_fwd(Wt.e1a, A.x0r, A.t1, PRO_NONE, nullptr, 1));
         if (pre_x3 && can_fuse_up2(Wt.e1b, A.t1)) {
-            PTTA_TRY(conv_fwd(Wt.e1b, A.t1, A.x1, PRO_NONE, nullptr, 0, A.x1r.p, nullptr, pre_x3->p));
+            if (sum1 && fuse_enc_sums) {
+                PTTA_TRY(conv_tc(Wt.e1b.img_fwd, Wt.e1b.b, A.t1, *sum1, 0, nullptr, c1->p, A.x1r.p, false, nullptr, pre_x3->p, 1));
+                A.sum1_done = true;
+            } else {
+                PTTA_TRY(conv_fwd(Wt.e1b, A.t1, A.x1, PRO_NONE, nullptr, 0, A.x1r.p, nullptr, pre_x3->p));
+            }
         } else {
             PTTA_TRY(conv_fwd(Wt.e1b, A.t1, A.x1, PRO_NONE, nullptr, 0, pre_x3 ? nullptr : A.x1r.p));
             if (pre_x3) PTTA_TRY(add_up2(A.x1, *pre_x3, A.x1r.p));
@@ -941,8 +959,8 @@ struct ptta_msgchn {
         {   // x2 = dx2 + cx2 (and ReLU(x2)), x1 = dx1 + cx1, x0 = dx0 + cx0 in one launch
             DecSumsParams dp;
             dp.a[0] = E.x2.p; dp.b[0] = cx2.p; dp.out[0] = A.x2.p; dp.n8[0] = (long long)A.x2.numel() / 8;
-            dp.a[1] = E.x1.p; dp.b[1] = cx1.p; dp.out[1] = A.x1.p; dp.n8[1] = (long long)A.x1.numel() / 8;
-            dp.a[2] = E.x0.p; dp.b[2] = cx0.p; dp.out[2] = A.x0.p; dp.n8[2] = (long long)A.x0.numel() / 8;
+            dp.a[1] = E.x1.p; dp.b[1] = cx1.p; dp.out[1] = A.x1.p; dp.n8[1] = E.sum1_done ? 0 : (long long)A.x1.numel() / 8;
+            dp.a[2] = E.x0.p; dp.b[2] = cx0.p; dp.out[2] = A.x0.p; dp.n8[2] = E.sum0_done ? 0 : (long long)A.x0.numel() / 8;
             dp.out0_relu = A.x2r.p;
             launch_k(dec_sums_kernel, cdiv(dp.n8[0] + dp.n8[1] + dp.n8[2], 256), 256, 0, st, dp);
             PTTA_TRY(check_launch("dec_sums"));
@@ -967,10 +985,11 @@ struct ptta_msgchn {
         if (is_real && !enc1_done) PTTA_TRY(run_encoder(enc1W, B.e1, d14.p, nullptr, nullptr, nullptr, nullptr));
         PTTA_TRY(run_decoder(dec1W, B.d1, B.e1, B.c[2], B.c[3], B.c[4], nullptr, B.d1.out));
         PTTA_TRY(up2_1(B.d1.out, nullptr, nullptr, B.p12));                        // p12 = up2(out14)
-        PTTA_TRY(run_encoder(enc2W, B.e2, d12.p, B.p12.p, &B.d1.x4, &B.d1.x3, &B.d1.x2));
+        PTTA_TRY(run_encoder(enc2W, B.e2, d12.p, B.p12.p, &B.d1.x4, &B.d1.x3, &B.d1.x2, &B.d2.x0, &B.c[1], &B.d2.x1, &B.c[2]));
         PTTA_TRY(run_decoder(dec2W, B.d2, B.e2, B.c[1], B.c[2], B.c[3], nullptr, B.d2.out));
         PTTA_TRY(up2_1(B.d2.out, B.p12.p, nullptr, B.p11));                        // p11 = up2(out12 + p12)
-        PTTA_TRY(run_encoder(enc3W, B.e3, dcl.p, B.p11.p, &B.d2.x4, &B.d2.x3, &B.d2.x2));
+        if (is_real) PTTA_TRY(run_encoder(enc3W, B.e3, dcl.p, B.p11.p, &B.d2.x4, &B.d2.x3, &B.d2.x2, &B.d3.x0, &B.c[0], &B.d3.x1, &B.c[1]));
+        else PTTA_TRY(run_encoder(enc3W, B.e3, dcl.p, B.p11.p, &B.d2.x4, &B.d2.x3, &B.d2.x2));      // no decoder 3 on the zero-image branch
         if (!is_real) return 0;                                                    // zero branch stops after encoder 3
         if (mlp_on_st3) {
             // ref = proj(z_real) needs e3.x2 only: it runs on the second side stream while decoder 3 runs here
@@ -1168,10 +1187,10 @@ struct ptta_msgchn {
         // ---- encoder 3 ----
         PTTA_TRY(up2_adj32(G4b, D8, 0));                                                    // D8 = grad of d2.x2 (skip)
         PTTA_TRY(conv_dgrad(enc3W.e2b, G4b, G4a, B.e3.t2.p, nullptr));                      // G4a = g_t2
-        PTTA_TRY(conv_dgrad(enc3W.e2a, G4a, T2b, B.e3.x1.p, T2a.p));                        // T2b = g_x1 total
+        PTTA_TRY(conv_dgrad(enc3W.e2a, G4a, T2b, B.e3.x1r.p, T2a.p));                        // T2b = g_x1 total
         PTTA_TRY(up2_adj32(T2b, D4, 0));                                                    // D4 = grad of d2.x3 (skip)
         PTTA_TRY(conv_dgrad(enc3W.e1b, T2b, T2a, B.e3.t1.p, nullptr));                      // T2a = g_t1
-        PTTA_TRY(conv_dgrad(enc3W.e1a, T2a, T1a, B.e3.x0.p, T1b.p));                        // T1a = g_x0 total
+        PTTA_TRY(conv_dgrad(enc3W.e1a, T2a, T1a, B.e3.x0r.p, T1b.p));                        // T1a = g_x0 total
         PTTA_TRY(up2_adj32(T1a, D2, 0));                                                    // D2 = grad of d2.x4 (skip)
         PTTA_TRY(conv_dgrad(enc3W.init2, T1a, T1b, B.e3.a0.p, nullptr));                    // T1b = g_a0
         PTTA_TRY(stem_dgrad_ch1(enc3W.init0, T1b, g_out.p, g_p11));                         // g_p11 = g_output + stem grad
@@ -1187,9 +1206,9 @@ struct ptta_msgchn {
         PTTA_TRY(conv_dgrad(dec2W.d2a, G4b, E8, B.d2.x2.p, D8.p));                          // E8 = g_e2x2
         // ---- encoder 2 ----
         PTTA_TRY(conv_dgrad(enc2W.e2b, E8, D8, B.e2.t2.p, nullptr));                        // D8 = g_t2
-        PTTA_TRY(conv_dgrad(enc2W.e2a, D8, G4b, B.e2.x1.p, G4a.p));                         // G4b = g_x1 total
+        PTTA_TRY(conv_dgrad(enc2W.e2a, D8, G4b, B.e2.x1r.p, G4a.p));                         // G4b = g_x1 total
         PTTA_TRY(conv_dgrad(enc2W.e1b, G4b, D4, B.e2.t1.p, nullptr));                       // D4 = g_t1
-        PTTA_TRY(conv_dgrad(enc2W.e1a, D4, T2a, B.e2.x0.p, T2b.p));                         // T2a = g_x0 total
+        PTTA_TRY(conv_dgrad(enc2W.e1a, D4, T2a, B.e2.x0r.p, T2b.p));                         // T2a = g_x0 total
         PTTA_TRY(conv_dgrad(enc2W.init2, T2a, D2, B.e2.a0.p, nullptr));                     // D2 = g_a0
         PTTA_TRY(stem_dgrad_ch1(enc2W.init0, D2, g_q.p, g_p12));                            // g_p12 = g_q + stem grad
         PTTA_TRY(up2_adj1(g_p12, g_o14));                                                   // g_out14
@@ -1857,6 +1876,7 @@ int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value) {
     else if (k == "fuse_dec_sums") e->fuse_dec_sums = value != 0;
     else if (k == "fuse_projpred") e->fuse_projpred = value != 0;
     else if (k == "fuse_up2") e->fuse_up2 = value != 0;
+    else if (k == "fuse_enc_sums") e->fuse_enc_sums = value != 0;
     else PTTA_CHECK(false, "set_option: unknown option '%s'", name);
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }   // a captured step bakes the dispatch in
     return 0;
