@@ -432,9 +432,13 @@ class ExternalModel_Adapt(object):
         `last_losses()` when the values are needed (that read synchronises)."""
         eng = self.model._engine_for(image_raw)
         if self.model_name == 'nlspn':
-            eng.set_image_normalization(getattr(self.model, 'img_scale', None), getattr(self.model, 'img_shift', None))
+            if getattr(self.model, 'img_scale', None) is None:
+                # the network must see the NORMALISED image and the smoothness loss the raw one (src/tta_main.py:595-620): without the folded
+                # normalisation the fused step would feed the raw image to both
+                raise RuntimeError('NLSPN tta_step: call set_image_normalization(scale, shift) first (ImageNet statistics folded into the stem)')
+            eng.set_image_normalization(self.model.img_scale, self.model.img_shift)
             eng.tta_step(image_raw, image_raw, sparse_depth, learning_rate, w_loss_sparse_depth, w_loss_smoothness, w_loss_cos,
-                         self.max_input_depth, graph=graph)
+                         self.max_input_depth, graph=graph, betas=betas, eps=eps, weight_decay=weight_decay)
             self._last_engine = eng
             return
         hyper = (learning_rate, betas, eps, weight_decay)

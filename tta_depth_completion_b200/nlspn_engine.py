@@ -607,13 +607,14 @@ class NlspnEngine:
         self.repack_adapted()
         self.launches += 3
 
-    def tta_step(self, image_norm, image_raw, sparse_depth, lr, w_sd=1.0, w_sm=1.0, w_cos=0.1, cap=80.0, graph=False):
+    def tta_step(self, image_norm, image_raw, sparse_depth, lr, w_sd=1.0, w_sm=1.0, w_cos=0.1, cap=80.0, graph=False,
+                 betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         """src/tta_main.py:583-633 for the NLSPN back-end: outlier removal, forward, losses, backward, Adam.
         image_norm: the image the network sees (normalised by the caller, or raw when set_image_normalization folds the
         normalisation into the stem), image_raw: the [0,255] image the smoothness loss sees.
         graph=True: the step is captured into a CUDA graph the second time it is called with the same input buffers and
         loss weights, and replayed from then on (the inputs are read from those buffers at every replay)."""
-        self.set_adam(lr)
+        self.set_adam(lr, betas, eps, weight_decay)
         if not graph:
             return self._step_body(image_norm, image_raw, sparse_depth, w_sd, w_sm, w_cos, cap)
         key = (image_norm.data_ptr(), image_raw.data_ptr(), sparse_depth.data_ptr(), float(w_sd), float(w_sm), float(w_cos), cap)

@@ -48,6 +48,9 @@ class ModulatedDeformConvFunction(Function):
             raise RuntimeError('Input shape and kernel channels wont match: (%d vs %d).' % (c, cin_k * groups))
         if ctx.stride[0] != ctx.stride[1] or ctx.padding[0] != ctx.padding[1] or ctx.dilation[0] != ctx.dilation[1]:
             raise RuntimeError('anisotropic stride / padding / dilation is not implemented')
+        if ctx.stride[0] != 1 or ctx.dilation[0] != 1:
+            raise NotImplementedError('ModulatedDeformConvFunction: stride / dilation other than 1 are not on the NLSPN path (got %d / %d)' % (
+                ctx.stride[0], ctx.dilation[0]))
         ho, wo = h + 2 * ctx.padding[0] - (kh - 1), w + 2 * ctx.padding[1] - (kw - 1)
         if tuple(offset.shape) != (n, 2 * kh * kw * deformable_groups, ho, wo) or tuple(mask.shape) != (n, kh * kw * deformable_groups, ho, wo):
             raise RuntimeError('offset / mask shape does not match the output size %dx%d' % (ho, wo))
