@@ -106,6 +106,35 @@ __global__ void pack_conv_weight_tc_kernel(const bf16* __restrict__ pack, bf16* 
     *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(image) + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)) = v;
 }
 
+// The epilogue thread of lane l needs its OWN pixel's 64 B (pair l of the quarter, parity `par`) of an NHWC operand row.  Loading them
+// directly (lane l reads 4 x 16 B at a 128 B stride between lanes) makes every request touch 32 cache lines: with mask and add operands
+// the LSU, not HBM, then sets the row time (measured 24 / 30 us against 14 us without operands).  Instead lane l loads chunk (l & 3) of
+// pair 8 j + (l >> 2), j = 0..3 -- four lanes cover one pixel's 64 contiguous bytes, 8 lines per request -- and the values are
+// transposed back with warp shuffles: chunk g of pair l sits in load j = l >> 3 of lane 4 (l & 7) + g.
+struct OperandRows { uint4 r[4]; };
+__device__ __forceinline__ void operand_rows_load(OperandRows& o, const bf16* base /* pixel xw + par of the row */, int vp, int lane, bool nc_load) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int pair = j * 8 + (lane >> 2);
+        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)pair * 64) + (lane & 3);
+        o.r[j] = pair < vp ? (nc_load ? __ldg(src) : *src) : make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+__device__ __forceinline__ void operand_rows_transpose(const OperandRows& o, int lane, uint4 (&out)[4]) {
+    const int jd = lane >> 3;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int src = ((lane & 7) << 2) + g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 t;
+            t.x = __shfl_sync(0xffffffffu, o.r[j].x, src); t.y = __shfl_sync(0xffffffffu, o.r[j].y, src);
+            t.z = __shfl_sync(0xffffffffu, o.r[j].z, src); t.w = __shfl_sync(0xffffffffu, o.r[j].w, src);
+            if (j == jd) out[g] = t;
+        }
+    }
+}
+
 // Scatter-form implicit GEMM over PIXEL PAIRS.
 //
 // Shared-memory / TMA view of the NHWC bf16 input: [N][H][W/2][64] -- one 128 B row per pixel pair, SWIZZLE_128B, the layout
@@ -199,7 +228,9 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) { 
 
 // NC = accumulator columns per output row and pixel parity: 32 = the 32 -> 32 convolution; 16 = the 32 -> 1 prediction-layer form
 // (conv3x3_tc_head_kernel below: same producer and MMA schedule with N = 3 x 16, another epilogue)
-template <int NC>
+// MASK / ADDS / UP2: which epilogue operands this instantiation handles (ADDS: `add` or `add2`).  They are template parameters because the
+// kernel sits at its register cap (168 with 10 warps): every operand path compiled in costs the plain forward conv registers it never uses.
+template <int NC, bool MASK, bool ADDS, bool UP2>
 __device__ __forceinline__ void conv3x3_tc_body(const CUtensorMap& tmap_in, const CUtensorMap& tmap_out, const CUtensorMap& tmap_out2,
                                                 const ConvTcParams& p) {
     typedef ConvTcCfg C;
@@ -378,7 +409,7 @@ __device__ __forceinline__ void conv3x3_tc_body(const CUtensorMap& tmap_in, cons
         float bias[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
-        const bf16* addsrc = p.add ? p.add : p.add2;     // the two are never used together
+        const bf16* addsrc = ADDS ? (p.add ? p.add : p.add2) : nullptr;     // the two are never used together
         uint32_t t = 0;
         for (int lin = lin0; lin < lin1;) {
             const int col = lin / p.H, y0 = lin - col * p.H, y1 = min(p.H, y0 + (lin1 - lin));
@@ -390,13 +421,13 @@ __device__ __forceinline__ void conv3x3_tc_body(const CUtensorMap& tmap_in, cons
             // bilinear x2 addend: this thread's column pair and weights are the same for every row of the segment
             int ux0 = 0, ux1 = 0; float ulx0 = 0.f, ulx1 = 0.f;
             const int uh2 = p.H >> 1, uw2 = p.W >> 1;
-            if (p.up2 && act) up2_coord(xw + 2 * lane + par, uw2, up2_scale(uw2), ux0, ux1, ulx0, ulx1);
+            if (UP2 && act) up2_coord(xw + 2 * lane + par, uw2, up2_scale(uw2), ux0, ux1, ulx0, ulx1);
             for (int y = y0; y < y1; ++y, ++t) {
                 const uint32_t sl = t % C::NSLOT;
                 // this thread's pixel: 64 contiguous bytes of every NHWC map; mask / add are fetched BEFORE waiting for the accumulators
                 const size_t off = (((size_t)n * p.H + y) * p.W + xw + 2 * lane + par) * 32;
                 float up[32];
-                if (p.up2) {
+                if (UP2) {
                     if (act) {
                         int uy0, uy1; float uly0, uly1;
                         up2_coord(y, uh2, up2_scale(uh2), uy0, uy1, uly0, uly1);
@@ -423,14 +454,11 @@ __device__ __forceinline__ void conv3x3_tc_body(const CUtensorMap& tmap_in, cons
                     }
                 }
                 uint4 mk[4], ad[4];
-                if (p.mask) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) mk[g] = act ? __ldg(reinterpret_cast<const uint4*>(p.mask + off) + g) : make_uint4(0, 0, 0, 0);
-                }
-                if (addsrc) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) ad[g] = act ? *(reinterpret_cast<const uint4*>(addsrc + off) + g) : make_uint4(0, 0, 0, 0);   // may alias `out`
-                }
+                OperandRows mrows, arows;
+                // first pixel of this warp's parity in the row: the loads below are issued BEFORE waiting for the accumulators
+                const size_t off_q = (((size_t)n * p.H + y) * p.W + xw + par) * 32;
+                if (MASK) operand_rows_load(mrows, p.mask + off_q, vp, lane, true);
+                if (ADDS) operand_rows_load(arows, addsrc + off_q, vp, lane, false);          // may alias `out`: plain loads
                 tc::mbar_wait(slot_full + 8 * sl, (t / C::NSLOT) & 1);
                 tc::tc_fence_after();
                 uint32_t v[32];
@@ -439,8 +467,10 @@ __device__ __forceinline__ void conv3x3_tc_body(const CUtensorMap& tmap_in, cons
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(slot_empty + 8 * sl);
                 if (vp <= 0) continue;                   // whole quarter right of the image: both of its warps skip
+                if (MASK) operand_rows_transpose(mrows, lane, mk);
+                if (ADDS) operand_rows_transpose(arows, lane, ad);
                 uint4 ov[4], ov_pre[4];
-                conv_tc_pixel(v, bias, p.mask ? mk : nullptr, p.add ? ad : nullptr, p.relu_out, ov, p.up2 ? up : nullptr,
+                conv_tc_pixel(v, bias, MASK ? mk : nullptr, (ADDS && p.add) ? ad : nullptr, p.relu_out, ov, UP2 ? up : nullptr,
                               (p.out2 && p.out2_pre_add) ? ov_pre : nullptr);
                 const uint32_t buf = (t & 1) * C::OUT_TILE;
                 unsigned char* srow = smem + (stage_q - smem_base) + buf + lane * 128;
@@ -451,7 +481,7 @@ __device__ __forceinline__ void conv3x3_tc_body(const CUtensorMap& tmap_in, cons
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint4 val = p.out2_pre_add ? ov_pre[g] : ov[g];
-                        if (p.add2) {
+                        if (ADDS && p.add2) {
                             uint32_t* vu = reinterpret_cast<uint32_t*>(&val);
                             const uint32_t* au = reinterpret_cast<const uint32_t*>(&ad[g]);
 #pragma unroll
@@ -491,10 +521,11 @@ __device__ __forceinline__ void conv3x3_tc_body(const CUtensorMap& tmap_in, cons
     }
 }
 
+template <bool MASK, bool ADDS, bool UP2>
 __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in,
                                                                            const __grid_constant__ CUtensorMap tmap_out,
                                                                            const __grid_constant__ CUtensorMap tmap_out2, const ConvTcParams p) {
-    conv3x3_tc_body<32>(tmap_in, tmap_out, tmap_out2, p);
+    conv3x3_tc_body<32, MASK, ADDS, UP2>(tmap_in, tmap_out, tmap_out2, p);
 }
 
 // 32 -> 1 channel 3x3 s1 p1 convolution with an fp32 output plane: the prediction layer prdct.3 (network_exp_msg_chn_adapt.py:289)
@@ -502,7 +533,7 @@ __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_kernel(const
 // 64 B and writes 4 B per pixel: it is bound by the read of the 32-channel map, which the tensor-core form streams through TMA exactly
 // once (the CUDA-core form staged halo tiles and spent 288 shared-memory-fed FMAs per pixel: 22 us at 352x1216).
 __global__ void __launch_bounds__(ConvTcCfg::THREADS, 1) conv3x3_tc_head_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTcParams p) {
-    conv3x3_tc_body<16>(tmap_in, tmap_in, tmap_in, p);
+    conv3x3_tc_body<16, false, false, false>(tmap_in, tmap_in, tmap_in, p);
 }
 
 // fp32 [tap][cin] (tap = ky*3 + kx) -> the head kernel's weight image: row = kx*48 + (2-ky)*16 + c, 64 B per row (32 cin), SWIZZLE_64B
@@ -618,12 +649,18 @@ inline int launch_conv_tc(const bf16* in, ConvTcParams p, cudaStream_t st) {
     typedef ConvTcCfg C;
     static int sms = 0;
     if (!sms) {
-        PTTA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        PTTA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        PTTA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        PTTA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        PTTA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        PTTA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        PTTA_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         int dev = 0;
         PTTA_CUDA(cudaGetDevice(&dev));
         PTTA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     PTTA_CHECK(conv_tc_supported(p.N, p.H, p.W), "conv3x3_tc: W=%d must be even", p.W);
+    PTTA_CHECK(!(p.up2 && p.mask), "conv3x3_tc: the upsampled addend and a derivative mask are never used together");
     PTTA_CHECK(!p.relu_in, "conv3x3_tc: ReLU-on-load is not supported (producers store ReLU(x): relu_out)");
     PTTA_CHECK(!p.up2 || ((p.H & 1) == 0 && (p.W & 1) == 0), "conv3x3_tc: the x2-upsampled addend needs even H, W (got %dx%d)", p.H, p.W);
     const int grid = conv_tc_split(p, sms);
@@ -635,7 +672,17 @@ inline int launch_conv_tc(const bf16* in, ConvTcParams p, cudaStream_t st) {
     const CUtensorMap map_out = *m;
     CUtensorMap map_out2 = map_out;
     if (p.out2) { PTTA_TRY(conv_tc_tmap(p.out2, p.N, p.H, p.W, &m, 32)); map_out2 = *m; }
-    launch_k(conv3x3_tc_kernel, grid, C::THREADS, C::SMEM, st, map_in, map_out, map_out2, p);
+    const bool mask = p.mask != nullptr, adds = p.add != nullptr || p.add2 != nullptr, up2 = p.up2 != nullptr;
+    if (up2) {
+        if (adds) launch_k(conv3x3_tc_kernel<false, true, true>, grid, C::THREADS, C::SMEM, st, map_in, map_out, map_out2, p);
+        else launch_k(conv3x3_tc_kernel<false, false, true>, grid, C::THREADS, C::SMEM, st, map_in, map_out, map_out2, p);
+    } else if (mask) {
+        if (adds) launch_k(conv3x3_tc_kernel<true, true, false>, grid, C::THREADS, C::SMEM, st, map_in, map_out, map_out2, p);
+        else launch_k(conv3x3_tc_kernel<true, false, false>, grid, C::THREADS, C::SMEM, st, map_in, map_out, map_out2, p);
+    } else {
+        if (adds) launch_k(conv3x3_tc_kernel<false, true, false>, grid, C::THREADS, C::SMEM, st, map_in, map_out, map_out2, p);
+        else launch_k(conv3x3_tc_kernel<false, false, false>, grid, C::THREADS, C::SMEM, st, map_in, map_out, map_out2, p);
+    }
     return check_launch("conv3x3_tc");
 }
 
