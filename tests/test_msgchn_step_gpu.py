@@ -359,30 +359,55 @@ def test_graph_replay_equals_eager():
         assert torch.equal(a.state_dict()[k], b.state_dict()[k]), k
 
 
-def test_continual_adaptation_metrics_track_the_oracle():
-    """100 continual steps at 64x128 (the north-star criterion): MAE and RMSE of the eval-mode prediction after adaptation
-    stay within 0.5 % of the oracle's."""
+@pytest.mark.parametrize('ckpt', [0, 'kitti_2layers_a'], ids=['random', 'fitted'])
+def test_continual_adaptation_metrics_track_the_oracle(ckpt):
+    """100 continual steps at 64x128 (the north-star criterion: MAE / RMSE within 0.5 % of the reference after adaptation).
+
+    random checkpoint: both networks still predict ~0, MAE / RMSE agree to 5e-4 -- the 0.5 % bound holds (and means little).
+    FITTED checkpoint (MAE ~0.7 m): 100 steps of a recurrence whose every step carries the bf16 / L1-sign-flip differences of section 4
+    of DESIGN.md drift apart by a few %: MEASURED 2.5 % (MAE), 2.4 % (RMSE), 5 % (iMAE), 3.7 % (iRMSE) -- the 0.5 % figure is NOT met
+    there, and the oracle's own bf16 emulation (no kernel involved) drifts from the fp32 oracle by the same amount (2.7 % / 2.4 % / 4.6 % /
+    2.8 %).  Asserted: within 8 % of fp32 outright, no further from fp32 than twice the emulation (+1 %), and within 1.5 % of the
+    EMULATION (measured 0.06 - 0.8 %) -- the tight statement: the kernels reproduce the bf16-operand step, the operand type costs the rest."""
     mode, cap, lr, steps = 'meta_selfsup_seq_2layers_ema', 80.0, 1e-4, 100
-    sd = O.make_synthetic_checkpoint(0, mode)
+    fitted = ckpt != 0
+    sd = O.get_checkpoint(ckpt, mode)
     model = make_model(mode, sd, cap)
     sd_o = {k: v.clone() for k, v in sd.items()}
     names = O.adapt_parameter_names(sd_o)
     state = O.AdamState(names, sd_o)
+    sd_e = {k: v.clone() for k, v in sd.items()} if fitted else None
+    state_e = O.AdamState(names, sd_e) if fitted else None
+    pr = O.Precision('bf16')
     for t in range(steps):
         image, sparse, dense = O.synthetic_frame(9, t, 1, 64, 128, 'kitti')
         model.tta_step(image.to(DEV), sparse.to(DEV), lr, W_SD, W_SM, W_COS)
         res = O.tta_step(sd_o, state, image, sparse, lr=lr, max_input_depth=cap)
+        if fitted:
+            O.tta_step(sd_e, state_e, image, sparse, lr=lr, max_input_depth=cap, pr=pr)
         got = model.last_losses()
-        assert rel(got['loss'], res['loss']) < 2e-3, (t, got['loss'], res['loss'])
+        assert rel(got['loss'], res['loss']) < (2e-3 if not fitted else 8e-2), (t, got['loss'], res['loss'])
     model.eval()
     d_f = res['sparse_depth']
     out = model.forward(image=(image / 255.0).to(DEV), sparse_depth=d_f.to(DEV), loss_type='adapt_meta_selfsup_seq_ema_reverse').cpu()
     with torch.no_grad():
         out_o = O.model_forward(sd_o, image / 255.0, d_f, False, cap)
+        out_e = O.model_forward(sd_e, image / 255.0, d_f, False, cap, pr) if fitted else None
     m, mo = O.eval_metrics(out, dense, 0.0, 100.0), O.eval_metrics(out_o, dense, 0.0, 100.0)
-    report('continual %d steps 64x128: native %s oracle %s' % (steps, m, mo))
-    for k in ('mae', 'rmse'):
-        assert rel(m[k], mo[k]) < 5e-3, (k, m[k], mo[k])
+    report('continual %d steps 64x128 (%s checkpoint): native %s oracle %s' % (steps, ckpt, m, mo))
+    if not fitted:
+        for k in ('mae', 'rmse'):
+            assert rel(m[k], mo[k]) < 5e-3, (k, m[k], mo[k])
+    else:
+        me = O.eval_metrics(out_e, dense, 0.0, 100.0)
+        report('continual %d steps 64x128 (%s checkpoint): bf16 emulation %s' % (steps, ckpt, me))
+        for k in ('mae', 'rmse', 'imae', 'irmse'):
+            e_nat, e_emu = rel(m[k], mo[k]), rel(me[k], mo[k])
+            report('continual %s: native-vs-fp32 %.3e  emulation-vs-fp32 %.3e' % (k, e_nat, e_emu))
+            assert e_nat < 8e-2 and e_nat < 2.0 * e_emu + 1e-2, (k, m[k], mo[k], me[k])
+            # ... and the native path lands where the bf16 emulation lands (measured: 0.27 % MAE, 0.06 % RMSE, 0.5 % iMAE, 0.8 % iRMSE):
+            # what separates it from the fp32 reference after 100 steps is the operand type, not the kernels
+            assert rel(m[k], me[k]) < 1.5e-2, (k, m[k], me[k])
     for k in names:
         if k not in ZERO_GRAD:
             report('continual %-44s weight nrel after %d steps: %.3e (update/|w| %.3e)' % (
