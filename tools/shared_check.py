@@ -21,6 +21,9 @@ H, W_, STEPS = 64, 128, 3
 
 def make_model(dev, sd):
     m = ExternalModel_Adapt('msg_chn', 0.0, 100.0, max_input_depth=CAP, device=dev)
+    # the kernel dispatch depends on the pixel count of a map (N x H x W): force the tcgen05 kernels everywhere, so that the per-rank
+    # batch-1 engines and the single-GPU batch-W engine run the SAME kernels and differ by summation order only
+    m.model.engine_options = {'tc_min_pixels': 0, 'tc_s2_min_pixels': 0, 'tc_t2_min_pixels': 0, 'tc_head_min_pixels': 0, 'tc_stem_min_pixels': 0}
     m._prepare_head(MODE)
     m.load_state_dict(sd)
     m.set_image_normalization((1 / 255.0,) * 3, (0.0,) * 3)
@@ -78,6 +81,8 @@ def main():
             sa, sb = model.state_dict(), big.state_dict()
             errs = {}
             for k in model.model._adapt_names:
+                if k == 'conv1_rgb_meta.conv1_meta.1.bias':     # bias in front of a train-mode BatchNorm: analytically zero gradient, pure rounding noise
+                    continue
                 upd = nrel(sd[k].to(dev), sb[k])
                 errs[k] = (nrel(sa[k], sb[k]), upd)
             worst = max(e / max(u, 1e-30) for e, u in errs.values())
