@@ -286,7 +286,8 @@ void ptta_msgchn_destroy(ptta_msgchn* e);
 /* dispatch options (results stay right for every value; used by the parity tests to run ALL kernel families at every size):
  * "tc_min_pixels" / "tc_s2_min_pixels" / "tc_t2_min_pixels": smallest map (N*H*W of the INPUT) the stride-1 / stride-2 /
  * transposed tcgen05 convs take (0 = always),
- * "tc_enabled" 0/1, "two_streams" 0/1, "fuse_dec_sums" 0/1.  Unknown names fail. */
+ * "tc_enabled" 0/1, "two_streams" 0/1, "fuse_dec_sums" 0/1; "trainable_head" / "skip_dec3": see the preparation steps below.
+ * Unknown names fail. */
 /* ---- shared-model mode (BASELINE.json configs[4]; the reference: DDP + SyncBatchNorm, src/msg_chn_model_adapt.py:480,555-556) ----
  * One communicator per rank: a device block mapped into every peer through CUDA IPC.  With a communicator set, the engine's
  * train-mode BatchNorm layers take their statistics over ALL ranks (forward sums and backward sums exchanged through peer memory
@@ -342,6 +343,32 @@ int ptta_msgchn_tta_step(ptta_msgchn* e, const float* image_raw, const float* im
 int ptta_msgchn_tta_step_graph(ptta_msgchn* e, const float* image_raw, const float* img_scale, const float* img_shift,
                                const float* sparse_depth, float max_input_depth,
                                float w_sparse_depth, float w_smoothness, float w_cos, ptta_stream_t stream);
+/* ---- source-domain preparation steps (the reference: src/init_main.py:448-572, src/head_main.py:415-541) ----
+ * The training forward's `training` argument is a mode: 0 eval, 1 train with the zero-image branch and the proxy heads (TTA and
+ * stage 2), 2 train WITHOUT them (stage 1: network_exp_msg_chn_adapt.py:559-607, real branch only, meta BatchNorm in train mode).
+ * Stage 1 (meta-layer initialisation, supervised): forward(mode 2) -> l2_loss = MsgChnModel_Adapt.compute_loss(loss_type='pretrain')
+ * (src/msg_chn_model_adapt.py:224-264: ground truth clamped to [0, max_predict_depth], validity = gt > 0, per-image masked MSE, batch
+ * mean) -> l2_loss_backward -> network_backward -> adam_step; ptta_msgchn_init_step runs the five in one call.
+ * Stage 2 (predictor head, engine option "trainable_head" = 1 before the workspace is bound: Adam then steps pred.{0,1,3}.* instead of
+ * the meta layer): forward(mode 1) -> ema_update_head (proj_t <- tau proj_t + (1 - tau) proj, network_exp_msg_chn_adapt.py:701-703) ->
+ * cos_loss = prepare_loss (src/external_model_adapt.py:524-540, no loss_cos gate) -> head_backward (weight / bias gradients of pred.0 and
+ * pred.3 through ptta_gemm_tn_bf16_tc, BatchNorm1d affine gradients; proj's output is detached, :692) -> adam_step;
+ * ptta_msgchn_head_step runs them in one call.  Option "skip_dec3" = 1 leaves out decoder 3 (stage 2 never reads the prediction).
+ * H and W must be multiples of 16 (the reference pads in 'adapt' mode only). */
+int ptta_msgchn_l2_loss(ptta_msgchn* e, const float* ground_truth, float max_predict_depth, ptta_stream_t stream);
+int ptta_msgchn_l2_loss_backward(ptta_msgchn* e, float grad_scale, ptta_stream_t stream);
+int ptta_msgchn_init_step(ptta_msgchn* e, const float* image_raw, const float* img_scale, const float* img_shift, const float* sparse_depth,
+                          const float* ground_truth, float max_input_depth, float max_predict_depth, ptta_stream_t stream);
+int ptta_msgchn_cos_loss(ptta_msgchn* e, ptta_stream_t stream);
+int ptta_msgchn_ema_update_head(ptta_msgchn* e, float tau, ptta_stream_t stream);
+int ptta_msgchn_head_backward(ptta_msgchn* e, float grad_scale, ptta_stream_t stream);
+int ptta_msgchn_head_step(ptta_msgchn* e, const float* image_raw, const float* img_scale, const float* img_shift, const float* sparse_depth,
+                          float max_input_depth, ptta_stream_t stream);
+/* C[m][n] (fp32) = A[rows][m]^T B[rows][n] (bf16, row-major): the weight gradient of a Linear layer, dW[out][in] = sum_r dY[r][out] X[r][in]
+ * (torch: `grad_output.t().mm(input)` inside loss.backward(), src/head_main.py:479), tcgen05 with MN-major operands and a split over the
+ * rows; m % 128 == 0, n % 256 == 0; workspace: ptta_gemm_tn_workspace_bytes (0 = unsupported shape). */
+size_t ptta_gemm_tn_workspace_bytes(long long rows, int m, int n);
+int ptta_gemm_tn_bf16_tc(const void* a_bf16, const void* b_bf16, float* c, void* workspace, long long rows, int m, int n, ptta_stream_t stream);
 /* named access to engine-owned tensors ("output", "emb", "ref", "filtered_depth", "filtered_validity", any
  * activation by its debug name). dtype: 0 fp32, 1 bf16. dims: up to 4 (NHWC for maps). */
 int ptta_msgchn_get_tensor(ptta_msgchn* e, const char* name, void** ptr, int* dtype, long long* dims4);

@@ -367,6 +367,105 @@ def tta_step(sd, state, image, sparse_depth, *, lr, w_sd=1.0, w_sm=1.0, w_cos=0.
 
 
 # ----------------------------------------------------------------------------------------------
+# source-domain preparation: stage 1 src/init_main.py:448-572, stage 2 src/head_main.py:415-541
+# ----------------------------------------------------------------------------------------------
+def l2_loss(src, tgt, w):
+    # L:266-287
+    loss = (src - tgt) ** 2
+    loss = torch.sum(w * loss, dim=[1, 2, 3]) / torch.sum(w, dim=[1, 2, 3])
+    return torch.mean(loss)
+
+
+def supervised_loss(output_depth, ground_truth, max_predict_depth=100.0):
+    # W:224-264 (w_scale0 = 1, the two coarser scales carry weight 0)
+    gt = torch.clamp(ground_truth, min=0.0, max=max_predict_depth)
+    v = torch.where(gt > 0, torch.ones_like(gt), gt)
+    return l2_loss(output_depth, gt, v)
+
+
+def init_forward(sd, image, sparse_depth, max_input_depth, pr=FP32):
+    """network_adapt._rgbd_meta_contrast_init (N:559-607) behind ExternalModel_Adapt.forward's clamp (E:103-108): the real branch only,
+    meta-layer BatchNorm in train mode; returns output_d11 (the only scale the loss weights, W:240-242)."""
+    if max_input_depth is not None:
+        sparse_depth = torch.clamp(sparse_depth, 0, max_input_depth)
+    d12, d14 = pyramid(sparse_depth)
+    enc_c = rgb_encoder(sd, image, pr)
+    enc_c[2] = meta_layer(sd, enc_c[2], True, pr)
+    output, _ = _cascade(sd, enc_c, sparse_depth, d12, d14, True, pr)
+    return output
+
+
+def init_step(sd, state, image, sparse_depth, ground_truth, *, lr, max_input_depth=80.0, max_predict_depth=100.0,
+              normalize=lambda im: im / 255.0, pr=FP32, weight_decay=0.0, return_grads=False):
+    """One stage-1 step (src/init_main.py:482-522): forward 'init_meta_seq_ema', masked L2 against the ground truth, backward to the
+    meta tensors, Adam.  Mutates `sd` and `state`."""
+    names = list(state.m.keys())
+    work = dict(sd)
+    leaves = {}
+    for k in names:
+        leaves[k] = sd[k].detach().clone().requires_grad_(True)
+        work[k] = leaves[k]
+    out = init_forward(work, normalize(image), sparse_depth, max_input_depth, pr)
+    loss = supervised_loss(out, ground_truth, max_predict_depth)
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(names, grads)}
+    adam_update(sd, grads, state, lr, weight_decay=weight_decay)
+    res = {'loss': float(loss.detach()), 'output_depth': out.detach()}
+    if return_grads:
+        res['grads'] = grads
+    return res
+
+
+HEAD_TRAINED = ('pred.0.weight', 'pred.0.bias', 'pred.1.weight', 'pred.1.bias', 'pred.3.weight', 'pred.3.bias')
+
+
+def head_step(sd, state, image, sparse_depth, *, lr, max_input_depth=80.0, normalize=lambda im: im / 255.0, pr=FP32, tau=0.999,
+              weight_decay=0.0, return_grads=False):
+    """One stage-2 step (src/head_main.py:437-480) with forward 'head_meta_selfsup_seq_ema_reverse' = _rgbd_meta_contrast_head with
+    mode [reverse, seq, ema] (N:609-699): the whole network under no_grad on the frame and on the zero image (meta-layer BatchNorm in
+    train mode: running statistics updated twice), proj_t <- EMA(proj) (N:701-703), emb = pred(proj(z_zero).detach()),
+    ref = proj(z_real).detach(); loss 'prepare' = mean(2 - 2 cos) (E:524-540).  head_main.py:268 gives proj.* and pred.* to Adam, but
+    only pred receives gradients (torch.optim.Adam skips tensors without one).  `state` covers HEAD_TRAINED.  Mutates `sd`, `state`."""
+    names = list(state.m.keys())
+    image = normalize(image)
+    if max_input_depth is not None:
+        sparse_depth = torch.clamp(sparse_depth, 0, max_input_depth)
+    with torch.no_grad():
+        d12, d14 = pyramid(sparse_depth)
+        enc_c = rgb_encoder(sd, image, pr)
+        enc_c[2] = meta_layer(sd, enc_c[2], True, pr)
+        _, enc11 = _cascade(sd, enc_c, sparse_depth, d12, d14, False, pr)
+        enc_z = rgb_encoder(sd, torch.zeros_like(image), pr)
+        enc_z[2] = meta_layer(sd, enc_z[2], True, pr)
+        _, enc11_zero = _cascade(sd, enc_z, sparse_depth, d12, d14, False, pr)
+        for k in [k for k in sd if k.startswith('proj_t.') and k.rsplit('.', 1)[-1] in _FLOAT_STATE]:
+            sd[k].copy_(sd[k] * tau + sd['proj.' + k[7:]] * (1.0 - tau))
+        z_zero = enc11_zero[2].permute(0, 2, 3, 1).reshape(-1, 32)
+        z_real = enc11[2].permute(0, 2, 3, 1).reshape(-1, 32)
+        pz = _mlp(sd, 'proj', z_zero, True, pr)
+    work = dict(sd)
+    leaves = {}
+    for k in names:
+        leaves[k] = sd[k].detach().clone().requires_grad_(True)
+        work[k] = leaves[k]
+    emb = _mlp(work, 'pred', pz.detach(), True, pr)
+    with torch.no_grad():
+        ref = _mlp(sd, 'proj', z_real, True, pr)
+    e = F.normalize(emb, dim=-1, p=2)
+    r = F.normalize(ref, dim=-1, p=2)
+    loss = (2 - 2 * (e * r).sum(-1)).mean()
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(names, grads)}
+    adam_update(sd, grads, state, lr, weight_decay=weight_decay)
+    res = {'loss': float(loss.detach())}
+    if return_grads:
+        res['grads'] = grads
+        res['emb'] = emb.detach()
+        res['ref'] = ref.detach()
+    return res
+
+
+# ----------------------------------------------------------------------------------------------
 # evaluation metrics: V:117-175 (torch variants used by T:760-798), after the depth-range mask
 # ----------------------------------------------------------------------------------------------
 def eval_metrics(output_depth, ground_truth, min_depth, max_depth):

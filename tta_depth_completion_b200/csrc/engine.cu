@@ -23,6 +23,7 @@
 #include "conv_tc_t2.cuh"
 #include "stem_tc.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tn_tc.cuh"
 #include "nlspn_prop.cuh"
 #include "../../include/ptta_b200.h"
 
@@ -192,6 +193,14 @@ struct ptta_msgchn {
     int next_xid = 0;                // exchange slots are handed out in call order; every rank runs the same sequence
     BnLayer projBn, predBn;
     std::vector<std::string> adapt_names;
+    // source-domain preparation: stage 1 = supervised fit of the meta layer (src/init_main.py:448-572, no proxy branch),
+    // stage 2 = fit of the predictor head `pred` on the frozen network (src/head_main.py:415-541)
+    bool train_head = false;         // option "trainable_head": the trained tensors are pred.{0,1,3}.{weight,bias}, not the meta layer
+    bool skip_dec3 = false;          // stage 2 never looks at the prediction: decoder 3 of the real branch is not run
+    bool proxy_in_backward = true;   // false after a stage-1 forward: no gradient arrives through the proxy head
+    float* gw_part = nullptr;        // split-K partial tiles of the Linear weight gradients (gemm_tn_tc.cuh)
+    bf16 *g_q0 = nullptr;            // stage 2: gradient wrt pred.0's output
+    const float* l_gt = nullptr; float l_maxd = 0.f;
 
     // activations
     Branch real, zero;
@@ -310,6 +319,19 @@ struct ptta_msgchn {
             def_linear(proj0, "proj.0", 32, 512); def_bn(projBn, "proj.1", 512); def_linear(proj3, "proj.3", 512, 512);
             def_linear(pred0, "pred.0", 512, 512); def_bn(predBn, "pred.1", 512); def_linear(pred3, "pred.3", 512, 512);
         }
+        return 0;
+    }
+
+    // stage 2 of the source-domain preparation: the trained tensors are the predictor head's
+    int select_trainable_head() {
+        PTTA_CHECK(has_heads, "option trainable_head needs the proxy heads ('selfsup' prepare mode)");
+        PTTA_CHECK(!bound, "option trainable_head must be set before the workspace is bound");
+        // head_main.py:268 hands proj.* and pred.* to Adam, but proj's output is detached on the trained path
+        // (network_exp_msg_chn_adapt.py:692): only pred ever receives a gradient, torch.optim.Adam skips the rest
+        train_head = true;
+        adapt_names = {"pred.0.weight", "pred.0.bias", "pred.1.weight", "pred.1.bias", "pred.3.weight", "pred.3.bias"};
+        fuse_projpred = false;       // pred.0 is trained: it cannot be pre-multiplied with proj.3
+        plan();                      // sizing pass again: the weight-gradient workspace joins the arena
         return 0;
     }
 
@@ -455,7 +477,8 @@ struct ptta_msgchn {
         loss_map_partial = allocv<double>((size_t)N * loss_map_blocks * 4);
         loss_cos_partial = allocv<double>(loss_cos_blocks);
         adam_hyper = (AdamHyper*)arena.take(sizeof(AdamHyper));
-        adam_chunks = (AdamChunk*)arena.take(sizeof(AdamChunk) * 256);
+        adam_chunks = (AdamChunk*)arena.take(sizeof(AdamChunk) * ADAM_MAX_CHUNKS);
+        if (train_head) { gw_part = (float*)arena.take(gemm_tn_workspace_bytes(R, 512, 512)); g_q0 = allocv<bf16>((size_t)R * 512); }
         ws_bytes = arena.off + 256;
     }
 
@@ -599,6 +622,7 @@ struct ptta_msgchn {
         return 0;
     }
     int pack_adapted() {
+        if (train_head) { PTTA_TRY(pack_linear(pred0)); return pack_linear(pred3); }
         PTTA_TRY(pack_conv(meta1));
         if (two_layers) PTTA_TRY(pack_conv(meta2));
         return 0;
@@ -608,7 +632,8 @@ struct ptta_msgchn {
         PTTA_CUDA(cudaMemsetAsync(zero_bias, 0, 512 * sizeof(float), st));
         PTTA_TRY(pack_enc(rgbW)); PTTA_TRY(pack_enc(enc1W)); PTTA_TRY(pack_enc(enc2W)); PTTA_TRY(pack_enc(enc3W));
         PTTA_TRY(pack_dec(dec1W)); PTTA_TRY(pack_dec(dec2W)); PTTA_TRY(pack_dec(dec3W));
-        PTTA_TRY(pack_adapted());
+        PTTA_TRY(pack_conv(meta1));
+        if (two_layers) PTTA_TRY(pack_conv(meta2));
         if (has_heads) {
             PTTA_TRY(pack_linear(proj0)); PTTA_TRY(pack_linear(proj3)); PTTA_TRY(pack_linear(pred0)); PTTA_TRY(pack_linear(pred3));
             launch_k(fuse_linear_kernel, dim3(cdiv(proj3.in, 256), pred0.out), 256, 0, st, pred0.w, pred0.b, proj3.w, proj3.b, projpred_pack,
@@ -646,7 +671,7 @@ struct ptta_msgchn {
             for (const AdamChunk& c : chunks) { if (c.g < lo) lo = c.g; if (c.g + c.n > hi) hi = c.g + c.n; }
             adam_g_base = lo; adam_g_floats = (size_t)(hi - lo);
         }
-        PTTA_CHECK(chunks.size() <= 256, "too many Adam chunks (%zu)", chunks.size());
+        PTTA_CHECK(chunks.size() <= ADAM_MAX_CHUNKS, "too many Adam chunks (%zu)", chunks.size());
         n_adam_chunks = (int)chunks.size();
         if (n_adam_chunks) PTTA_CUDA(cudaMemcpyAsync(adam_chunks, chunks.data(), sizeof(AdamChunk) * chunks.size(), cudaMemcpyHostToDevice, st));
         if (has_heads) {
@@ -1002,6 +1027,7 @@ struct ptta_msgchn {
             st = main; partial = main_partial;
             if (rc3) return rc3;
         }
+        if (skip_dec3) return 0;
         return run_decoder(dec3W, B.d3, B.e3, B.c[0], B.c[1], B.c[2], B.p11.p, B.output);   // output = out11 + p11
     }
     int mlp(const LinearLayer& L0, const BnLayer& bn, const BnState& s, const LinearLayer& L3, const bf16* x, int in_dim, bf16* a0, bf16* out,
@@ -1015,11 +1041,16 @@ struct ptta_msgchn {
     }
 
     // image / sparse are the caller's (Nu, Hu, Wu) tensors; with `padded` the network runs on the flip-padded pair
-    int forward(const float* image, const float* isc, const float* ish, const float* sparse, float cap, bool training) {
+    // mode: 0 = eval, 1 = train with the proxy branch (TTA and the stage-2 head trainer), 2 = train WITHOUT it (stage 1:
+    // network_exp_msg_chn_adapt.py:559-607 `_rgbd_meta_contrast_init` -- real branch only, meta-layer BatchNorm in train mode)
+    int forward(const float* image, const float* isc, const float* ish, const float* sparse, float cap, int mode) {
         PTTA_CHECK(bound && packed, "engine not ready: bind a workspace and pack weights first");
-        PTTA_CHECK(!training || has_heads, "training forward needs the proxy heads ('selfsup' prepare mode)");
+        PTTA_CHECK(mode >= 0 && mode <= 2, "forward: mode %d", mode);
+        PTTA_CHECK(mode != 1 || has_heads, "training forward needs the proxy heads ('selfsup' prepare mode)");
+        PTTA_CHECK(mode != 2 || !skip_dec3, "stage-1 forward needs decoder 3 (option skip_dec3 is set)");
+        proxy_in_backward = mode != 2;
         next_xid = 0;                   // a step's peer exchanges are numbered from its forward pass on
-        if (!padded) return forward_impl(image, isc, ish, sparse, cap, training);
+        if (!padded) return forward_impl(image, isc, ish, sparse, cap, mode);
         {
             // the reference pads the NORMALISED image with zeros (msg_chn_model_adapt.py:79-101): fill with the raw value that
             // normalises to zero, so that the affine folded into the stem reproduces it
@@ -1032,12 +1063,13 @@ struct ptta_msgchn {
             launch_k(pad_pair_kernel, cdiv(tot, 256), 256, 0, st, sparse, psp, Nu, 1, Hu, Wu, H, W, 1.f, 0.f, 0.f, 0.f);
             PTTA_TRY(check_launch("pad_pair(sparse)"));
         }
-        PTTA_TRY(forward_impl(pimg, isc, ish, psp, cap, training));
+        PTTA_TRY(forward_impl(pimg, isc, ish, psp, cap, mode));
         long long tot = (long long)Nu * Hu * Wu;
         launch_k(unpad_mean_kernel, cdiv(tot, 256), 256, 0, st, real.output.p, out_u.p, Nu, Hu, Wu, H, W);
         return check_launch("unpad_mean");
     }
-    int forward_impl(const float* image, const float* isc, const float* ish, const float* sparse, float cap, bool training) {
+    int forward_impl(const float* image, const float* isc, const float* ish, const float* sparse, float cap, int mode) {
+        const bool training = mode == 1;
         {
             long long tot = (long long)N * (H / 4) * (W / 4);
             launch_k(pyramid_kernel, cdiv(tot, 128), 128, 0, st, sparse, dcl.p, d12.p, d14.p, N, H, W, cap, cap > 0.f ? 1 : 0);
@@ -1047,7 +1079,7 @@ struct ptta_msgchn {
         const bool fork = training && two_streams && st2 != nullptr;
         if (!fork) {
             PTTA_TRY(run_rgb_encoder(image, isc, ish, rc, real.cr));
-            PTTA_TRY(run_meta(real, training));
+            PTTA_TRY(run_meta(real, mode != 0));
             PTTA_TRY(run_cascade(real, true));
             if (!training) return 0;
             PTTA_TRY(zero_side(false));
@@ -1151,6 +1183,7 @@ struct ptta_msgchn {
     }
     // from (g_out, g_ref) to the gradients of the adapted tensors
     int network_backward() {
+        PTTA_CHECK(!train_head, "network_backward: this engine trains the predictor head (option trainable_head); use head_backward");
         for (const std::string& k : adapt_names) PTTA_CHECK(grad_of(k) != nullptr, "gradient buffer 'grad/%s' not bound", k.c_str());
         const Branch& B = real;
         if (padded) {   // adjoint of the crop + mean: each copy receives half of the gradient at its crop, zero elsewhere
@@ -1168,9 +1201,14 @@ struct ptta_msgchn {
                 PTTA_CUDA(cudaStreamWaitEvent(st3, ev_lossg, 0));
                 st = st3; partial = partial3;
             }
-            int rc3 = gemm(g_ref, proj3.pack_t, g_a3, nullptr, R, 512, 512);
-            if (!rc3) rc3 = bn_backward(projBn, bnProjR, g_a3, h_a0r, g_a0, R, 1, nullptr, nullptr);
-            if (!rc3) rc3 = gemm(g_a0, proj0.pack_t, GZ.p, nullptr, R, 32, 512);     // g_z (grad wrt e3.x2 from the heads)
+            int rc3 = 0;
+            if (!proxy_in_backward) {      // stage 1 (supervised): nothing arrives through ref = proj(z_real)
+                if (cudaMemsetAsync(GZ.p, 0, GZ.numel() * sizeof(bf16), st) != cudaSuccess) { set_error("cudaMemsetAsync(g_z) failed"); rc3 = 2; }
+            } else {
+                rc3 = gemm(g_ref, proj3.pack_t, g_a3, nullptr, R, 512, 512);
+                if (!rc3) rc3 = bn_backward(projBn, bnProjR, g_a3, h_a0r, g_a0, R, 1, nullptr, nullptr);
+                if (!rc3) rc3 = gemm(g_a0, proj0.pack_t, GZ.p, nullptr, R, 32, 512);     // g_z (grad wrt e3.x2 from the heads)
+            }
             if (side && !rc3 && cudaEventRecord(ev_headb, st3) != cudaSuccess) { set_error("cudaEventRecord failed"); rc3 = 2; }
             st = main; partial = main_partial;
             if (rc3) return rc3;
@@ -1268,6 +1306,98 @@ struct ptta_msgchn {
         return network_backward();
     }
 
+    // ---- source-domain preparation -------------------------------------------------------
+    // stage 1 loss (src/init_main.py:510-517 -> src/msg_chn_model_adapt.py:224-264 -> src/loss_utils.py:266-287): ground truth clamped to
+    // [0, max_predict_depth], v = [gt > 0], loss = mean_n( sum v (pred - gt)^2 / sum v )
+    int l2_loss(const float* gt, float max_predict) {
+        PTTA_CHECK(Nu <= 64, "l2_loss: batch size %d > 64 not supported", Nu);
+        PTTA_CHECK(!padded, "stage-1 / stage-2 training needs H and W that are multiples of 16 (the reference pads in 'adapt' mode only: "
+                            "src/msg_chn_model_adapt.py:54-55)");
+        l_gt = gt; l_maxd = max_predict;
+        dim3 grid(loss_map_blocks, Nu);
+        launch_k(l2_loss_reduce_kernel, grid, LOSS_BLOCK, 0, st, real.output.p, gt, loss_map_partial, Hu * Wu, max_predict);
+        PTTA_TRY(check_launch("l2_loss_reduce"));
+        launch_k(l2_loss_finalize_kernel, 1, 256, 0, st, loss_map_partial, loss_map_blocks, Nu, losses);
+        return check_launch("l2_loss_finalize");
+    }
+    int l2_loss_backward(float gscale) {
+        PTTA_CHECK(l_gt != nullptr, "l2_loss_backward called before l2_loss");
+        const long long tot = (long long)Nu * Hu * Wu;
+        launch_k(l2_loss_grad_kernel, cdiv(tot, 256), 256, 0, st, real.output.p, l_gt, g_out.p, losses, Nu, Hu * Wu, l_maxd, gscale);
+        return check_launch("l2_loss_grad");
+    }
+    // one supervised step on the meta layer: forward without the proxy branch, L2 loss, backward, Adam (src/init_main.py:482-522)
+    int init_step(const float* image_raw, const float* isc, const float* ish, const float* sparse, const float* gt, float cap, float max_predict) {
+        PTTA_CHECK(!train_head, "init_step: this engine trains the predictor head (option trainable_head)");
+        PTTA_TRY(forward(image_raw, isc, ish, sparse, cap, 2));
+        PTTA_TRY(l2_loss(gt, max_predict));
+        PTTA_TRY(l2_loss_backward(1.f));
+        PTTA_TRY(network_backward());
+        return adam_step();
+    }
+
+    // stage 2 loss (src/head_main.py:469-475 -> src/external_model_adapt.py:524-540): mean_r(2 - 2 cos(emb_r, ref_r)), no gate
+    int cos_loss() {
+        launch_k(loss_cos_rows_kernel, loss_cos_blocks, 256, 0, st, emb, ref, rowstat, loss_cos_partial, R, 512);
+        PTTA_TRY(check_launch("loss_cos_rows"));
+        launch_k(cos_loss_finalize_kernel, 1, 256, 0, st, loss_cos_partial, loss_cos_blocks, R, losses);
+        return check_launch("cos_loss_finalize");
+    }
+    // proj_t <- tau proj_t + (1 - tau) proj over the PARAMETERS of proj (network_exp_msg_chn_adapt.py:701-703, called once per stage-2
+    // forward at :689); skipped when the checkpoint has no EMA copy
+    int ema_update_head(float tau) {
+        static const char* names[6] = {"0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias"};
+        EmaParams ep; memset(&ep, 0, sizeof(ep));
+        long long maxn = 0;
+        for (int i = 0; i < 6; ++i) {
+            auto t = ext.find(std::string("proj_t.") + names[i]);
+            auto sidx = ext.find(std::string("proj.") + names[i]);
+            if (t == ext.end()) continue;
+            PTTA_CHECK(sidx != ext.end() && sidx->second.second == t->second.second, "ema_update: proj.%s / proj_t.%s mismatch", names[i], names[i]);
+            ep.t[ep.count] = (float*)t->second.first; ep.s[ep.count] = (const float*)sidx->second.first; ep.n[ep.count] = t->second.second;
+            maxn = std::max(maxn, t->second.second);
+            ++ep.count;
+        }
+        if (!ep.count) return 0;
+        ep.tau = tau; ep.one_minus_tau = (float)(1.0 - (double)tau);
+        launch_k(ema_update_kernel, dim3(cdiv(maxn, 256), ep.count), 256, 0, st, ep);
+        return check_launch("ema_update");
+    }
+    // gradients of pred.{0,1,3}: emb = pred(proj(z_zero).detach()) (network_exp_msg_chn_adapt.py:692)
+    //   emb = a1 W3^T + b3,  a1 = relu(bn(q0)),  q0 = pz W0^T + b0,  pz = proj(z_zero)
+    int head_backward(float gscale) {
+        PTTA_CHECK(train_head, "head_backward: engine was not created with option trainable_head");
+        for (const std::string& k : adapt_names) PTTA_CHECK(grad_of(k) != nullptr, "gradient buffer 'grad/%s' not bound", k.c_str());
+        bf16* g_emb = g_a3; bf16* g_a1 = g_a0;
+        launch_k(loss_cos_grad_kernel, loss_cos_blocks, 256, 0, st, emb, ref, rowstat, losses, g_emb, R, 512, gscale, 1);
+        PTTA_TRY(check_launch("loss_cos_grad(emb)"));
+        int nblk = 0;
+        // pred.3
+        PTTA_TRY(launch_gemm_tn_tc(g_emb, h_an2, grad_of("pred.3.weight"), gw_part, R, 512, 512, st));
+        PTTA_TRY(stats(g_emb, nullptr, R, 512, 0, nullptr, 0, nblk));
+        launch_k(colsum_finalize_kernel, cdiv(512, 32), FIN_THREADS, 0, st, partial, nblk, 512, grad_of("pred.3.bias"));
+        PTTA_TRY(check_launch("colsum_finalize"));
+        PTTA_TRY(gemm(g_emb, pred3.pack_t, g_a1, nullptr, R, 512, 512));
+        // pred.1 (BatchNorm1d, train mode) behind the ReLU
+        PTTA_TRY(bn_backward(predBn, bnPred, g_a1, h_q0, g_q0, R, 1, grad_of("pred.1.weight"), grad_of("pred.1.bias")));
+        // pred.0
+        PTTA_TRY(launch_gemm_tn_tc(g_q0, h_pz, grad_of("pred.0.weight"), gw_part, R, 512, 512, st));
+        PTTA_TRY(stats(g_q0, nullptr, R, 512, 0, nullptr, 0, nblk));
+        launch_k(colsum_finalize_kernel, cdiv(512, 32), FIN_THREADS, 0, st, partial, nblk, 512, grad_of("pred.0.bias"));
+        return check_launch("colsum_finalize");
+    }
+    // one stage-2 step (src/head_main.py:437-480): frozen network on the frame and on the zero image, EMA copy of proj, cosine loss
+    // between pred(proj(z_zero)) and proj(z_real), gradients of pred, Adam
+    int head_step(const float* image_raw, const float* isc, const float* ish, const float* sparse, float cap) {
+        PTTA_CHECK(train_head, "head_step: engine was not created with option trainable_head");
+        PTTA_CHECK(!padded, "stage-2 training needs H and W that are multiples of 16");
+        PTTA_TRY(forward(image_raw, isc, ish, sparse, cap, 1));
+        PTTA_TRY(ema_update_head(0.999f));
+        PTTA_TRY(cos_loss());
+        PTTA_TRY(head_backward(1.f));
+        return adam_step();
+    }
+
     int adam_step() {
         PTTA_CHECK(n_adam_chunks > 0, "Adam state not bound (grad/, adam_m/, adam_v/ entries for every adapted tensor)");
         if (comm.world > 1) {
@@ -1303,7 +1433,7 @@ struct ptta_msgchn {
     int tta_step(const float* image_raw, const float* isc, const float* ish, const float* sparse, float cap, float w_sd, float w_sm,
                  float w_cos) {
         PTTA_TRY(outlier(sparse));                                               // src/tta_main.py:583-590
-        PTTA_TRY(forward(image_raw, isc, ish, fd.p, cap, true));                 // :610-614
+        PTTA_TRY(forward(image_raw, isc, ish, fd.p, cap, 1));                    // :610-614
         PTTA_TRY(loss(image_raw, fd.p, fv.p, cap, w_sd, w_sm, w_cos));           // :619-629
         PTTA_TRY(backward(1.f));                                                 // :631-632
         return adam_step();                                                      // :633
@@ -1877,6 +2007,8 @@ int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value) {
     else if (k == "fuse_projpred") e->fuse_projpred = value != 0;
     else if (k == "fuse_up2") e->fuse_up2 = value != 0;
     else if (k == "fuse_enc_sums") e->fuse_enc_sums = value != 0;
+    else if (k == "trainable_head") { if (value) PTTA_TRY(e->select_trainable_head()); }   // stage-2 trainer: Adam steps pred.*, not the meta layer
+    else if (k == "skip_dec3") e->skip_dec3 = value != 0;                  // stage 2 never reads the prediction of the real branch
     else PTTA_CHECK(false, "set_option: unknown option '%s'", name);
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }   // a captured step bakes the dispatch in
     return 0;
@@ -1946,8 +2078,52 @@ int ptta_msgchn_forward(ptta_msgchn* e, const float* image, const float* isc, co
                         int training, ptta_stream_t stream) {
     PTTA_CHECK(e && image && sparse && isc && ish, "forward: null argument");
     e->st = (cudaStream_t)stream;
-    return e->forward(image, isc, ish, sparse, cap, training != 0);
+    return e->forward(image, isc, ish, sparse, cap, training);
 }
+// ---- source-domain preparation steps -----------------------------------------------------------------------------
+int ptta_msgchn_l2_loss(ptta_msgchn* e, const float* ground_truth, float max_predict_depth, ptta_stream_t stream) {
+    PTTA_CHECK(e && ground_truth, "l2_loss: null argument");
+    e->st = (cudaStream_t)stream;
+    return e->l2_loss(ground_truth, max_predict_depth);
+}
+int ptta_msgchn_l2_loss_backward(ptta_msgchn* e, float gscale, ptta_stream_t stream) {
+    PTTA_CHECK(e, "l2_loss_backward: null engine");
+    e->st = (cudaStream_t)stream;
+    return e->l2_loss_backward(gscale);
+}
+int ptta_msgchn_init_step(ptta_msgchn* e, const float* image_raw, const float* isc, const float* ish, const float* sparse, const float* ground_truth,
+                          float cap, float max_predict_depth, ptta_stream_t stream) {
+    PTTA_CHECK(e && image_raw && sparse && ground_truth && isc && ish, "init_step: null argument");
+    e->st = (cudaStream_t)stream;
+    return e->init_step(image_raw, isc, ish, sparse, ground_truth, cap, max_predict_depth);
+}
+int ptta_msgchn_cos_loss(ptta_msgchn* e, ptta_stream_t stream) {
+    PTTA_CHECK(e && e->has_heads, "cos_loss: engine has no proxy heads");
+    e->st = (cudaStream_t)stream;
+    return e->cos_loss();
+}
+int ptta_msgchn_ema_update_head(ptta_msgchn* e, float tau, ptta_stream_t stream) {
+    PTTA_CHECK(e && e->has_heads, "ema_update_head: engine has no proxy heads");
+    e->st = (cudaStream_t)stream;
+    return e->ema_update_head(tau);
+}
+int ptta_msgchn_head_backward(ptta_msgchn* e, float gscale, ptta_stream_t stream) {
+    PTTA_CHECK(e, "head_backward: null engine");
+    e->st = (cudaStream_t)stream;
+    return e->head_backward(gscale);
+}
+int ptta_msgchn_head_step(ptta_msgchn* e, const float* image_raw, const float* isc, const float* ish, const float* sparse, float cap,
+                          ptta_stream_t stream) {
+    PTTA_CHECK(e && image_raw && sparse && isc && ish, "head_step: null argument");
+    e->st = (cudaStream_t)stream;
+    return e->head_step(image_raw, isc, ish, sparse, cap);
+}
+size_t ptta_gemm_tn_workspace_bytes(long long rows, int m, int n) { return gemm_tn_supported(rows, m, n) ? gemm_tn_workspace_bytes(rows, m, n) : 0; }
+int ptta_gemm_tn_bf16_tc(const void* a, const void* b, float* c, void* workspace, long long rows, int m, int n, ptta_stream_t stream) {
+    PTTA_CHECK(a && b && c && workspace, "gemm_tn_bf16_tc: null argument");
+    return launch_gemm_tn_tc((const bf16*)a, (const bf16*)b, c, (float*)workspace, rows, m, n, (cudaStream_t)stream);
+}
+
 int ptta_msgchn_loss(ptta_msgchn* e, const float* image_raw, const float* sparse, const float* validity, float cap, float w_sd, float w_sm,
                      float w_cos, ptta_stream_t stream) {
     PTTA_CHECK(e && image_raw && sparse && validity, "loss: null argument");

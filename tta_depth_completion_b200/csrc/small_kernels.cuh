@@ -1359,6 +1359,92 @@ __global__ void __launch_bounds__(256) loss_cos_grad_kernel(const bf16* __restri
 }
 
 // -------------------------------------------------------------------------------------------------
+// f3: losses of the source-domain preparation stages
+//   stage 1 (src/msg_chn_model_adapt.py:224-264, src/loss_utils.py:266-287): gt' = clamp(gt, 0, max_predict), v = [gt' > 0],
+//            loss = mean_n( sum v (pred - gt')^2 / sum v );   partial layout (doubles): [N][nblk][4] = {sum v (pred-gt')^2, sum v, -, -}
+//   stage 2 (src/external_model_adapt.py:524-540): mean_r(2 - 2 cos(emb_r, ref_r)) -- loss_cos_rows_kernel + this finalize, no gate
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LOSS_BLOCK) l2_loss_reduce_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                                    double* __restrict__ partial, int HW, float max_predict) {
+    PDL_SYNC();
+    __shared__ double sh[32];
+    const int n = blockIdx.y;
+    const float* pn = pred + (size_t)n * HW; const float* gn = gt + (size_t)n * HW;
+    double s_l = 0.0, s_v = 0.0;
+    for (int i = blockIdx.x * LOSS_BLOCK + threadIdx.x; i < HW; i += gridDim.x * LOSS_BLOCK) {
+        const float g = fminf(fmaxf(gn[i], 0.f), max_predict);
+        if (g > 0.f) {
+            const float d = pn[i] - g;
+            s_l += (double)(d * d);
+            s_v += 1.0;
+        }
+    }
+    double r0 = block_sum_d(s_l, sh), r1 = block_sum_d(s_v, sh);
+    if (threadIdx.x == 0) {
+        double* o = partial + ((size_t)n * gridDim.x + blockIdx.x) * 4;
+        o[0] = r0; o[1] = r1; o[2] = 0.0; o[3] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256) l2_loss_finalize_kernel(const double* __restrict__ partial, int nblk, int N, LossScalars* out) {
+    PDL_SYNC();
+    __shared__ double sh[32];
+    double tot = 0.0;
+    for (int n = 0; n < N; ++n) {
+        double a = 0.0, b = 0.0;
+        for (int k = threadIdx.x; k < nblk; k += 256) {
+            const double* p = partial + ((size_t)n * nblk + k) * 4;
+            a += p[0]; b += p[1];
+        }
+        a = block_sum_d(a, sh); b = block_sum_d(b, sh);
+        if (threadIdx.x == 0) {
+            const float fa = (float)a, fb = (float)b;
+            tot += (double)(fa / fb);                   // no epsilon, as in the reference
+            if (n < 64) out->inv_count[n] = 1.f / fb;
+        }
+    }
+    if (threadIdx.x != 0) return;
+    out->loss = (float)(tot / N);
+    out->loss_sparse_depth = 0.f; out->loss_smooth = 0.f; out->loss_cos = 0.f; out->w_cos_eff = 0.f;
+}
+
+// d loss / d pred = gscale * 2 v (pred - gt') / (N sum_n v)
+__global__ void l2_loss_grad_kernel(const float* __restrict__ pred, const float* __restrict__ gt, float* __restrict__ gpred,
+                                    const LossScalars* __restrict__ ls, int N, int HW, float max_predict, float gscale) {
+    PDL_SYNC();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * HW) return;
+    const int n = (int)(idx / HW);
+    const float g = fminf(fmaxf(gt[idx], 0.f), max_predict);
+    float r = 0.f;
+    if (g > 0.f) r = gscale * 2.f * (pred[idx] - g) * ls->inv_count[n] / (float)N;
+    gpred[idx] = r;
+}
+
+__global__ void __launch_bounds__(256) cos_loss_finalize_kernel(const double* __restrict__ cos_partial, int cos_blocks, long long R, LossScalars* out) {
+    PDL_SYNC();
+    __shared__ double sh[32];
+    double c = 0.0;
+    for (int k = threadIdx.x; k < cos_blocks; k += 256) c += cos_partial[k];
+    c = block_sum_d(c, sh);
+    if (threadIdx.x != 0) return;
+    const float l_cos = R > 0 ? (float)(c / (double)R) : 0.f;
+    out->loss = l_cos; out->loss_cos = l_cos; out->loss_sparse_depth = 0.f; out->loss_smooth = 0.f;
+    out->w_cos_eff = 1.f;                               // loss_cos_grad_kernel scales with it
+}
+
+// EMA copy of the projector (network_exp_msg_chn_adapt.py:701-703): t = t * tau + s * (1 - tau), two products and one sum like the
+// reference's tensor expression (no fused multiply-add, so the result is bit-identical)
+struct EmaParams { float* t[8]; const float* s[8]; long long n[8]; int count; float tau, one_minus_tau; };
+__global__ void __launch_bounds__(256) ema_update_kernel(const EmaParams p) {
+    PDL_SYNC();
+    const int k = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n[k]) return;
+    p.t[k][i] = __fadd_rn(__fmul_rn(p.t[k][i], p.tau), __fmul_rn(p.s[k][i], p.one_minus_tau));
+}
+
+// -------------------------------------------------------------------------------------------------
 // a17: fused multi-tensor Adam (torch.optim.Adam, amsgrad=False; src/tta_main.py:341-346,633).
 // One launch over a chunk table covering every adapted tensor; hyper-parameters and the step count
 // live on the device so the launch is CUDA-graph friendly.
@@ -1366,6 +1452,7 @@ __global__ void __launch_bounds__(256) loss_cos_grad_kernel(const bf16* __restri
 struct AdamHyper { float lr, beta1, beta2, eps, weight_decay, one_minus_beta1, one_minus_beta2; int step; double beta1_d, beta2_d, lr_d; };
 struct AdamChunk { float* p; const float* g; float* m; float* v; int n; };
 #define ADAM_CHUNK 2048
+#define ADAM_MAX_CHUNKS 1024
 
 // torch's single-tensor formulation: exp_avg.lerp_(g, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g, g, value=1-b2);
 // denom = sqrt(v)/sqrt(bc2) + eps; p.addcdiv_(m, denom, value=-lr/bc1)   (1-b computed in double, as torch does)

@@ -111,10 +111,12 @@ def add_head_state(sd, mode):
         if 'seq' not in mode:
             raise NotImplementedError('only the sequential ("seq") meta layer is implemented: %s' % mode)
         if '1layer' in mode:
-            w = torch.empty(32, 32, 3, 3)
+            # nn.Conv2d's own initialisation first (it consumes the RNG), then the Kaiming fan-out draw over the weight (:1066-1068)
+            w = _default_conv_init(torch.empty(32, 32, 3, 3))
+            b = torch.empty(32).uniform_(-1.0 / math.sqrt(288), 1.0 / math.sqrt(288))
             torch.nn.init.kaiming_normal_(w, mode='fan_out', nonlinearity='relu')
             sd['conv1_rgb_meta.weight'] = w
-            sd['conv1_rgb_meta.bias'] = torch.empty(32).uniform_(-1.0 / math.sqrt(288), 1.0 / math.sqrt(288))
+            sd['conv1_rgb_meta.bias'] = b
         elif '2layers' in mode:
             p = 'conv1_rgb_meta.conv1_meta'
             sd[p + '.0.0.weight'] = _default_conv_init(torch.empty(128, 32, 3, 3))
