@@ -278,6 +278,14 @@ int ptta_eval_metrics(const float* output_depth, const float* ground_truth, long
  * payloads -> fp32 image NCHW in [0,255], depth and validity [n,1,h,w]; bit-exact with the numpy code */
 int ptta_input_stage(const void* image_u8_hwc, const void* depth_u16, float* image_nchw, float* depth, float* validity, int n,
                      int h0, int w0, int y0, int x0, int h, int w, float depth_multiplier, ptta_stream_t stream);
+/* Host-side PNG decoding (no device work; plain host pointers, e.g. pinned staging memory): replaces PIL on the reference's loader path --
+ * `np.asarray(Image.open(path).convert('RGB'))` (src/data_utils.py:134-165) and `np.array(Image.open(path))` of the 16-bit depth maps
+ * (src/data_utils.py:167-234).  Container parsing with CRC check, zlib inflate, the five scanline filters, colour-type conversion as
+ * convert('RGB') does it (alpha dropped, grey replicated, palette looked up).  8- and 16-bit non-interlaced files; anything else fails
+ * with a message.  ptta_png_info: channels = 3 for palette files; bit_depth 8 or 16. */
+int ptta_png_info(const void* file_bytes, size_t n, int* width, int* height, int* channels, int* bit_depth);
+int ptta_png_decode_rgb8(const void* file_bytes, size_t n, unsigned char* out_hwc, size_t out_bytes);
+int ptta_png_decode_gray16(const void* file_bytes, size_t n, unsigned short* out_hw, size_t out_bytes);
 
 /* ---- MSG-CHN ProxyTTA engine ------------------------------------------------------------------- */
 /* prepare_mode: the reference's string, e.g. "meta_selfsup_seq_2layers_ema" (network_exp_msg_chn_adapt.py:1022-1087) */
@@ -351,7 +359,7 @@ int ptta_msgchn_tta_step_graph(ptta_msgchn* e, const float* image_raw, const flo
  * mean) -> l2_loss_backward -> network_backward -> adam_step; ptta_msgchn_init_step runs the five in one call.
  * Stage 2 (predictor head, engine option "trainable_head" = 1 before the workspace is bound: Adam then steps pred.{0,1,3}.* instead of
  * the meta layer): forward(mode 1) -> ema_update_head (proj_t <- tau proj_t + (1 - tau) proj, network_exp_msg_chn_adapt.py:701-703) ->
- * cos_loss = prepare_loss (src/external_model_adapt.py:524-540, no loss_cos gate) -> head_backward (weight / bias gradients of pred.0 and
+ * cos_loss = prepare_loss (src/external_model_adapt.py:524-540, no loss_cos gate) -> cos_loss_backward -> head_backward (weight / bias gradients of pred.0 and
  * pred.3 through ptta_gemm_tn_bf16_tc, BatchNorm1d affine gradients; proj's output is detached, :692) -> adam_step;
  * ptta_msgchn_head_step runs them in one call.  Option "skip_dec3" = 1 leaves out decoder 3 (stage 2 never reads the prediction).
  * H and W must be multiples of 16 (the reference pads in 'adapt' mode only). */
@@ -360,8 +368,9 @@ int ptta_msgchn_l2_loss_backward(ptta_msgchn* e, float grad_scale, ptta_stream_t
 int ptta_msgchn_init_step(ptta_msgchn* e, const float* image_raw, const float* img_scale, const float* img_shift, const float* sparse_depth,
                           const float* ground_truth, float max_input_depth, float max_predict_depth, ptta_stream_t stream);
 int ptta_msgchn_cos_loss(ptta_msgchn* e, ptta_stream_t stream);
-int ptta_msgchn_ema_update_head(ptta_msgchn* e, float tau, ptta_stream_t stream);
-int ptta_msgchn_head_backward(ptta_msgchn* e, float grad_scale, ptta_stream_t stream);
+int ptta_msgchn_ema_update_head(ptta_msgchn* e, double tau, ptta_stream_t stream);
+int ptta_msgchn_cos_loss_backward(ptta_msgchn* e, float grad_scale, ptta_stream_t stream);      /* -> "g_emb" (bf16 [R,512]) */
+int ptta_msgchn_head_backward(ptta_msgchn* e, ptta_stream_t stream);                             /* "g_emb" -> "grad/pred.*" */
 int ptta_msgchn_head_step(ptta_msgchn* e, const float* image_raw, const float* img_scale, const float* img_shift, const float* sparse_depth,
                           float max_input_depth, ptta_stream_t stream);
 /* C[m][n] (fp32) = A[rows][m]^T B[rows][n] (bf16, row-major): the weight gradient of a Linear layer, dW[out][in] = sum_r dY[r][out] X[r][in]

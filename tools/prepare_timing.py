@@ -1,0 +1,81 @@
+"""Timing of the source-domain preparation steps on one B200: ptta_msgchn_init_step / ptta_msgchn_head_step at the
+benchmark frame size, and the Linear weight-gradient GEMM (gemm_tn_tc_kernel + reduce) alone.  CUDA events, after warm-up.
+    python tools/prepare_timing.py [--batch 1 4]"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tta_depth_completion_b200 import ExternalModel_Adapt, _lib                          # noqa: E402
+from tta_depth_completion_b200.synthetic import synthetic_frame, get_checkpoint           # noqa: E402
+
+DEV = 'cuda'
+
+
+def timed(fn, iters, warmup=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, nargs='*', default=[1, 4])
+    ap.add_argument('--iters', type=int, default=50)
+    args = ap.parse_args()
+    out = {}
+    L = _lib.lib()
+    for rows in (26752, 4 * 26752):
+        a = torch.randn(rows, 512, device=DEV).bfloat16()
+        b = torch.randn(rows, 512, device=DEV).bfloat16()
+        c = torch.empty(512, 512, device=DEV)
+        ws = torch.empty(L.ptta_gemm_tn_workspace_bytes(rows, 512, 512), dtype=torch.uint8, device=DEV)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ms = timed(lambda: L.ptta_gemm_tn_bf16_tc(_lib.ptr(a), _lib.ptr(b), _lib.ptr(c), _lib.ptr(ws), rows, 512, 512, st), 200)
+        ref = timed(lambda: torch.matmul(a.t(), b), 200)
+        out['gemm_tn_%dx512x512' % rows] = {'us': round(ms * 1e3, 2), 'tflops': round(2.0 * rows * 512 * 512 / ms / 1e9, 1),
+                                            'algorithmic_GBps': round((2 * rows * 512 * 2 + 512 * 512 * 4) / ms / 1e6, 1),
+                                            'cublas_bf16_us': round(ref * 1e3, 2)}
+    for n in args.batch:
+        sd = get_checkpoint('kitti_2layers_a', 'meta_selfsup_seq_2layers_ema')
+        frames = [tuple(t.to(DEV) for t in synthetic_frame(60, k, n, 352, 1216, 'kitti')) for k in range(4)]
+        for stage in ('init', 'head'):
+            model = ExternalModel_Adapt('msg_chn', 0.0, 100.0, max_input_depth=80.0, device=torch.device(DEV))
+            model._prepare_head('meta_selfsup_seq_2layers_ema')
+            model.load_state_dict(sd)
+            torch.manual_seed(1)
+            if stage == 'head':
+                model.prepare_parameters('head_selfsup_ema')
+            model.set_image_normalization((1 / 255.0,) * 3, (0.0,) * 3)
+            model.train()
+            k = [0]
+
+            def step():
+                im, sp, gt = frames[k[0] % 4]
+                k[0] += 1
+                if stage == 'init':
+                    model.init_step(im, sp, gt, 1e-3)
+                else:
+                    model.head_step(im, sp, 1e-3)
+            ms = timed(step, args.iters)
+            eng = model.model._engine_for(frames[0][0])
+            l0 = eng.launch_count()
+            step()
+            out['%s_step_%dx352x1216' % (stage, n)] = {'ms': round(ms, 3), 'frames_per_s': round(n * 1e3 / ms, 1), 'launches': eng.launch_count() - l0,
+                                                       'loss': round(model.last_losses()['loss'], 5)}
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()

@@ -8,7 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.environ.get('PTTA_B200_LIB') or os.path.join(LIB_DIR, 'libptta_b200.so')     # override: A/B experiments with another build
-SOURCES = ['engine.cu', 'nlspn_net.cu']
+SOURCES = ['engine.cu', 'nlspn_net.cu', 'png_host.cu']      # png_host.cu: host-only code (PNG container + zlib inflate), links libz
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 
 
@@ -60,7 +60,7 @@ def build_library(force=False, verbose=False):
             raise RuntimeError('nvcc failed:\n' + out)
         if verbose and out.strip():
             print(out)
-    cmd = [nvcc, '-shared', '-o', LIB_PATH] + [_obj(s) for s in SOURCES]
+    cmd = [nvcc, '-shared', '-o', LIB_PATH] + [_obj(s) for s in SOURCES] + ['-lz']
     if verbose:
         print(' '.join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -73,7 +73,7 @@ def build_stamps_library(verbose=False):
     """Profiling build (-DPTTA_STAMPS): every kernel records its in-situ start time (tools/graph_stamps.py).  Not the product."""
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     out = os.path.join(LIB_DIR, 'libptta_b200_stamps.so')
-    cmd = [nvcc] + NVCC_FLAGS + ['-DPTTA_STAMPS', '-shared', '-o', out] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + ['-DPTTA_STAMPS', '-shared', '-o', out] + [os.path.join(CSRC, s) for s in SOURCES] + ['-lz']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)

@@ -318,6 +318,8 @@ struct ptta_msgchn {
         if (has_heads) {
             def_linear(proj0, "proj.0", 32, 512); def_bn(projBn, "proj.1", 512); def_linear(proj3, "proj.3", 512, 512);
             def_linear(pred0, "pred.0", 512, 512); def_bn(predBn, "pred.1", 512); def_linear(pred3, "pred.3", 512, 512);
+            if (prepare_mode.find("ema") != std::string::npos)      // EMA copy of proj (network_exp_msg_chn_adapt.py:1052-1060): stage 2 updates it
+                for (const char* t : {"0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias"}) need(std::string("proj_t.") + t);
         }
         return 0;
     }
@@ -447,7 +449,7 @@ struct ptta_msgchn {
             reg("emb", emb, 1, R, 512, 1, 1); reg("ref", ref, 1, R, 512, 1, 1);
             reg("heads.a0_real", h_a0r, 1, R, 512, 1, 1);
             g_ref = allocv<bf16>(rm); g_a3 = allocv<bf16>(rm); g_a0 = allocv<bf16>(rm);
-            reg("g_ref", g_ref, 1, R, 512, 1, 1);
+            reg("g_ref", g_ref, 1, R, 512, 1, 1); reg("g_emb", g_a3, 1, R, 512, 1, 1);
             bnProjZ = alloc_bn(512); bnProjR = alloc_bn(512); bnPred = alloc_bn(512);
             rowstat = allocv<float>((size_t)R * 3);
         }
@@ -1345,7 +1347,7 @@ struct ptta_msgchn {
     }
     // proj_t <- tau proj_t + (1 - tau) proj over the PARAMETERS of proj (network_exp_msg_chn_adapt.py:701-703, called once per stage-2
     // forward at :689); skipped when the checkpoint has no EMA copy
-    int ema_update_head(float tau) {
+    int ema_update_head(double tau) {     // tau as the reference's Python float: 1 - tau is formed in double, then both factors are rounded to fp32
         static const char* names[6] = {"0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias"};
         EmaParams ep; memset(&ep, 0, sizeof(ep));
         long long maxn = 0;
@@ -1359,18 +1361,21 @@ struct ptta_msgchn {
             ++ep.count;
         }
         if (!ep.count) return 0;
-        ep.tau = tau; ep.one_minus_tau = (float)(1.0 - (double)tau);
+        ep.tau = (float)tau; ep.one_minus_tau = (float)(1.0 - tau);
         launch_k(ema_update_kernel, dim3(cdiv(maxn, 256), ep.count), 256, 0, st, ep);
         return check_launch("ema_update");
     }
     // gradients of pred.{0,1,3}: emb = pred(proj(z_zero).detach()) (network_exp_msg_chn_adapt.py:692)
     //   emb = a1 W3^T + b3,  a1 = relu(bn(q0)),  q0 = pz W0^T + b0,  pz = proj(z_zero)
-    int head_backward(float gscale) {
+    // d loss / d emb of the stage-2 loss into "g_emb"
+    int cos_loss_backward(float gscale) {
+        launch_k(loss_cos_grad_kernel, loss_cos_blocks, 256, 0, st, emb, ref, rowstat, losses, g_a3, R, 512, gscale, 1);
+        return check_launch("loss_cos_grad(emb)");
+    }
+    int head_backward() {
         PTTA_CHECK(train_head, "head_backward: engine was not created with option trainable_head");
         for (const std::string& k : adapt_names) PTTA_CHECK(grad_of(k) != nullptr, "gradient buffer 'grad/%s' not bound", k.c_str());
         bf16* g_emb = g_a3; bf16* g_a1 = g_a0;
-        launch_k(loss_cos_grad_kernel, loss_cos_blocks, 256, 0, st, emb, ref, rowstat, losses, g_emb, R, 512, gscale, 1);
-        PTTA_TRY(check_launch("loss_cos_grad(emb)"));
         int nblk = 0;
         // pred.3
         PTTA_TRY(launch_gemm_tn_tc(g_emb, h_an2, grad_of("pred.3.weight"), gw_part, R, 512, 512, st));
@@ -1392,9 +1397,10 @@ struct ptta_msgchn {
         PTTA_CHECK(train_head, "head_step: engine was not created with option trainable_head");
         PTTA_CHECK(!padded, "stage-2 training needs H and W that are multiples of 16");
         PTTA_TRY(forward(image_raw, isc, ish, sparse, cap, 1));
-        PTTA_TRY(ema_update_head(0.999f));
+        PTTA_TRY(ema_update_head(0.999));
         PTTA_TRY(cos_loss());
-        PTTA_TRY(head_backward(1.f));
+        PTTA_TRY(cos_loss_backward(1.f));
+        PTTA_TRY(head_backward());
         return adam_step();
     }
 
@@ -2102,15 +2108,20 @@ int ptta_msgchn_cos_loss(ptta_msgchn* e, ptta_stream_t stream) {
     e->st = (cudaStream_t)stream;
     return e->cos_loss();
 }
-int ptta_msgchn_ema_update_head(ptta_msgchn* e, float tau, ptta_stream_t stream) {
+int ptta_msgchn_ema_update_head(ptta_msgchn* e, double tau, ptta_stream_t stream) {
     PTTA_CHECK(e && e->has_heads, "ema_update_head: engine has no proxy heads");
     e->st = (cudaStream_t)stream;
     return e->ema_update_head(tau);
 }
-int ptta_msgchn_head_backward(ptta_msgchn* e, float gscale, ptta_stream_t stream) {
+int ptta_msgchn_cos_loss_backward(ptta_msgchn* e, float gscale, ptta_stream_t stream) {
+    PTTA_CHECK(e && e->has_heads, "cos_loss_backward: engine has no proxy heads");
+    e->st = (cudaStream_t)stream;
+    return e->cos_loss_backward(gscale);
+}
+int ptta_msgchn_head_backward(ptta_msgchn* e, ptta_stream_t stream) {
     PTTA_CHECK(e, "head_backward: null engine");
     e->st = (cudaStream_t)stream;
-    return e->head_backward(gscale);
+    return e->head_backward();
 }
 int ptta_msgchn_head_step(ptta_msgchn* e, const float* image_raw, const float* isc, const float* ish, const float* sparse, float cap,
                           ptta_stream_t stream) {

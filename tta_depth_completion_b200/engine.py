@@ -111,10 +111,48 @@ class MsgChnEngine:
         return _FLOAT3(*[float(x) for x in v])
 
     def forward(self, image, sparse_depth, max_input_depth, training, img_scale=(1.0, 1.0, 1.0), img_shift=(0.0, 0.0, 0.0)):
+        """training: False / 0 eval, True / 1 train with the zero-image branch and the proxy heads, 2 train without them (stage 1)"""
         self._check_inputs(image, sparse_depth)
         cap = float(max_input_depth) if max_input_depth is not None else -1.0
         check(self.L.ptta_msgchn_forward(self.handle, ptr(image), self._f3(img_scale), self._f3(img_shift), ptr(sparse_depth), cap,
-                                         1 if training else 0, _stream()), 'forward')
+                                         int(training), _stream()), 'forward')
+
+    # -- source-domain preparation (include/ptta_b200.h, "source-domain preparation steps") -----------------
+    def l2_loss(self, ground_truth, max_predict_depth):
+        self._check_map(ground_truth)
+        check(self.L.ptta_msgchn_l2_loss(self.handle, ptr(ground_truth), float(max_predict_depth), _stream()), 'l2_loss')
+
+    def l2_loss_backward(self, grad_scale=1.0):
+        check(self.L.ptta_msgchn_l2_loss_backward(self.handle, grad_scale, _stream()), 'l2_loss_backward')
+
+    def init_step(self, image_raw, sparse_depth, ground_truth, max_input_depth, max_predict_depth, img_scale, img_shift):
+        self._check_inputs(image_raw, sparse_depth)
+        self._check_map(ground_truth)
+        cap = float(max_input_depth) if max_input_depth is not None else -1.0
+        check(self.L.ptta_msgchn_init_step(self.handle, ptr(image_raw), self._f3(img_scale), self._f3(img_shift), ptr(sparse_depth),
+                                           ptr(ground_truth), cap, float(max_predict_depth), _stream()), 'init_step')
+
+    def cos_loss(self):
+        check(self.L.ptta_msgchn_cos_loss(self.handle, _stream()), 'cos_loss')
+
+    def cos_loss_backward(self, grad_scale=1.0):
+        check(self.L.ptta_msgchn_cos_loss_backward(self.handle, grad_scale, _stream()), 'cos_loss_backward')
+
+    def ema_update_head(self, tau=0.999):
+        check(self.L.ptta_msgchn_ema_update_head(self.handle, tau, _stream()), 'ema_update_head')
+
+    def head_backward(self):
+        check(self.L.ptta_msgchn_head_backward(self.handle, _stream()), 'head_backward')
+
+    def head_step(self, image_raw, sparse_depth, max_input_depth, img_scale, img_shift):
+        self._check_inputs(image_raw, sparse_depth)
+        cap = float(max_input_depth) if max_input_depth is not None else -1.0
+        check(self.L.ptta_msgchn_head_step(self.handle, ptr(image_raw), self._f3(img_scale), self._f3(img_shift), ptr(sparse_depth), cap,
+                                           _stream()), 'head_step')
+
+    def _check_map(self, t):
+        if tuple(t.shape) != (self.n, 1, self.h, self.w) or t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise TypeError('expected a contiguous fp32 CUDA tensor of shape %s' % ((self.n, 1, self.h, self.w),))
 
     def loss(self, image_raw, sparse_depth, validity, max_input_depth, w_sd, w_sm, w_cos):
         cap = float(max_input_depth) if max_input_depth is not None else -1.0

@@ -181,6 +181,87 @@ class _LossFn(torch.autograd.Function):
                 None, None, None, None, None, None, None)
 
 
+class _InitForwardFn(torch.autograd.Function):
+    """stage-1 forward (loss_type 'init_meta...': network_exp_msg_chn_adapt.py:559-607): the real branch with the meta layer in train mode"""
+
+    @staticmethod
+    def forward(ctx, wrapper, image, sparse_depth, *params):
+        eng = wrapper._engine_for(image)
+        eng.pack_adapted()
+        eng.forward(image, sparse_depth, None, 2)
+        ctx.wrapper, ctx.eng = wrapper, eng
+        return eng.tensor('output').view(eng.n, 1, eng.h, eng.w).clone()
+
+    @staticmethod
+    def backward(ctx, g_out):
+        eng, wrapper = ctx.eng, ctx.wrapper
+        go = eng.tensor('g_output')
+        if g_out.data_ptr() != go.data_ptr():
+            go.view(-1).copy_(g_out.reshape(-1))
+        eng.network_backward()
+        return (None, None, None) + tuple(wrapper._grad_views[k].clone() for k in wrapper._adapt_names)
+
+
+class _L2LossFn(torch.autograd.Function):
+    """MsgChnModel_Adapt.compute_loss(loss_type='pretrain') (src/msg_chn_model_adapt.py:224-264) on the engine's last prediction"""
+
+    @staticmethod
+    def forward(ctx, eng, output_depth, ground_truth, max_predict_depth):
+        eng.l2_loss(ground_truth, max_predict_depth)
+        ctx.eng = eng
+        return eng.tensor('losses').view(-1)[0].clone()
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        eng = ctx.eng
+        eng.l2_loss_backward(float(g_loss))
+        return None, eng.tensor('g_output').view(eng.n, 1, eng.h, eng.w), None, None
+
+
+class _HeadForwardFn(torch.autograd.Function):
+    """stage-2 forward (loss_type 'head_meta_selfsup_seq_ema_reverse': network_exp_msg_chn_adapt.py:609-699, mode [reverse, seq, ema]):
+    frozen network on the frame and on the zero image, EMA copy of proj, emb = pred(proj(z_zero).detach()), ref = proj(z_real).detach()"""
+
+    @staticmethod
+    def forward(ctx, wrapper, image, sparse_depth, *params):
+        eng = wrapper._engine_for(image)
+        eng.pack_adapted()
+        eng.forward(image, sparse_depth, None, 1)
+        eng.ema_update_head(0.999)
+        ctx.wrapper, ctx.eng = wrapper, eng
+        emb, ref = eng.tensor('emb').view(-1, 512), eng.tensor('ref').view(-1, 512)
+        ctx.mark_non_differentiable(ref)
+        return emb, ref
+
+    @staticmethod
+    def backward(ctx, g_emb, g_ref):
+        eng, wrapper = ctx.eng, ctx.wrapper
+        ge = eng.tensor('g_emb')
+        if g_emb.data_ptr() != ge.data_ptr():
+            ge.view(-1).copy_(g_emb.reshape(-1))
+        eng.head_backward()
+        return (None, None, None) + tuple(wrapper._grad_views[k].clone() for k in wrapper._adapt_names)
+
+
+class _CosLossFn(torch.autograd.Function):
+    """ExternalModel_Adapt.prepare_loss (src/external_model_adapt.py:524-540) on the engine's last (emb, ref)"""
+
+    @staticmethod
+    def forward(ctx, eng, embedding, reference):
+        eng.cos_loss()
+        ctx.eng = eng
+        return eng.tensor('losses').view(-1)[0].clone()
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        eng = ctx.eng
+        eng.cos_loss_backward(float(g_loss))
+        return None, eng.tensor('g_emb').view(-1, 512), None
+
+
+HEAD_TRAINED = ('pred.0.weight', 'pred.0.bias', 'pred.1.weight', 'pred.1.bias', 'pred.3.weight', 'pred.3.bias')
+
+
 class MsgChnModel_Adapt(object):
     """src/msg_chn_model_adapt.py -- MSG-CHN wrapper (state dict, adapted-parameter selection, checkpoints)."""
 
@@ -199,6 +280,7 @@ class MsgChnModel_Adapt(object):
         self.img_shift = (0.0, 0.0, 0.0)
         self._adam_step = 0
         self.engine_options = {}       # ptta_msgchn_set_option(name, value) applied to every engine this wrapper creates
+        self._trainable = 'meta'       # which tensors the flat parameter / gradient / Adam buffers cover: 'meta' (TTA, stage 1) or 'head' (stage 2)
 
     # -- construction ---------------------------------------------------------------------------------
     def _prepare_head(self, mode=''):
@@ -214,7 +296,10 @@ class MsgChnModel_Adapt(object):
         for k, v in list(self._sd.items()):
             want = torch.int64 if k.endswith('num_batches_tracked') else torch.float32
             self._sd[k] = v.detach().to(self.device, want).contiguous()
-        self._adapt_names = [k for k in self._sd if 'meta' in k and k.endswith(_PARAM_SUFFIX)]   # msg_chn_model_adapt.py:392-396
+        if self._trainable == 'head':           # stage 2: of the tensors head_main.py:268 hands to Adam only pred.* ever gets a gradient
+            self._adapt_names = [k for k in HEAD_TRAINED if k in self._sd]
+        else:
+            self._adapt_names = [k for k in self._sd if 'meta' in k and k.endswith(_PARAM_SUFFIX)]   # msg_chn_model_adapt.py:392-396
         total = sum(self._sd[k].numel() for k in self._adapt_names)
         self._flat = {name: torch.zeros(total, dtype=torch.float32, device=self.device) for name in ('param', 'grad', 'm', 'v')}
         # Adam step counter + hyper-parameters: ONE device block per wrapper, bound into every engine (all shapes share the
@@ -243,12 +328,16 @@ class MsgChnModel_Adapt(object):
         if self.prepare_mode is None:
             raise RuntimeError('_prepare_head(mode) must be called before forward (src/tta_main.py:322)')
         key = (image.shape[0], image.shape[2], image.shape[3])
+        self._last_key = key
         eng = self._engines.get(key)
         if eng is None:
             n, h, w = key          # H, W need not be multiples of 16: the engine pads and flip-ensembles (src/msg_chn_model_adapt.py:58-125)
             state = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in self._sd.items()}
+            options = dict(self.engine_options)
+            if self._trainable == 'head':
+                options.update(trainable_head=1, skip_dec3=1)
             eng = MsgChnEngine(n, h, w, self.prepare_mode, state, self._grad_views, self._m_views, self._v_views,
-                               options=self.engine_options, adam_hyper=self._adam_hyper)
+                               options=options, adam_hyper=self._adam_hyper)
             self._engines[key] = eng
         return eng
 
@@ -258,7 +347,26 @@ class MsgChnModel_Adapt(object):
             raise RuntimeError('_prepare_head(mode) must be called before forward (src/tta_main.py:322)')
         image = image.contiguous()
         sparse_depth = sparse_depth.contiguous()
+        if self.training and 'init_meta' in loss_type:           # stage 1 (network_exp_msg_chn_adapt.py:344-360)
+            if self._trainable != 'meta':
+                raise RuntimeError('stage-1 forward after prepare_parameters(\'head...\'): the trained set is the predictor head')
+            out = _InitForwardFn.apply(self, image, sparse_depth, *self._param_objs.values())
+            eng = self._engine_for(image)
+            with torch.no_grad():                                  # the two coarser scales carry weight 0 in the loss (W:240-242): detached copies
+                p11 = eng.tensor('real.p11').view(eng.n, 1, eng.h, eng.w).clone()
+                o14 = eng.tensor('real.d1.out').view(eng.n, 1, eng.h // 4, eng.w // 4)
+                o14 = torch.nn.functional.interpolate(o14, scale_factor=4, mode='bilinear', align_corners=True)
+            return [out, p11, o14]
+        if self.training and 'head' in loss_type and 'adapt' not in loss_type:      # stage 2 (:362-376)
+            if self._trainable != 'head':
+                raise RuntimeError('stage-2 forward needs prepare_parameters(\'head_selfsup_ema\') first (src/head_main.py:268)')
+            if not all(s in loss_type for s in ('reverse', 'seq', 'ema')):
+                raise NotImplementedError('stage-2 forward: only the [reverse, seq, ema] mode of the shipped scripts is implemented: %s' % loss_type)
+            emb, ref = _HeadForwardFn.apply(self, image, sparse_depth, *self._param_objs.values())
+            return None, emb, ref
         if self.training and 'adapt' in loss_type:
+            if self._trainable != 'meta':
+                raise RuntimeError('adaptation forward after prepare_parameters(\'head...\'): call adapt_parameters on a fresh model')
             out, emb, ref = _ForwardFn.apply(self, image, sparse_depth, *self._param_objs.values())
             return out, emb, ref
         eng = self._engine_for(image)
@@ -274,7 +382,44 @@ class MsgChnModel_Adapt(object):
     def adapt_parameters(self, mode=''):
         if mode != 'meta':
             raise NotImplementedError('adapt mode %r: only "meta" is on the native path (msg_chn_model_adapt.py:392-396)' % mode)
+        if self._trainable != 'meta':
+            raise RuntimeError('adapt_parameters after prepare_parameters(\'head...\'): build a fresh model for adaptation')
         return torch.nn.ParameterList(list(self._param_objs.values()))
+
+    def prepare_parameters(self, mode=''):
+        """src/msg_chn_model_adapt.py:287-339 -- the tensors a preparation stage trains.  As in the reference, the call (re)creates
+        the layers `mode` names from torch's global RNG: 'head_selfsup_ema' (src/head_main.py:268) draws new proj / proj_t / pred heads
+        (twice, W:295-298) and returns proj.* and pred.*; 'meta_seq_<k>' (src/init_main.py:288) draws a new meta layer and returns it."""
+        if 'head' in mode:
+            if self.prepare_mode is None:
+                raise RuntimeError('_prepare_head(mode) must be called before prepare_parameters(%r) (src/head_main.py:259)' % mode)
+            fresh = {}
+            add_head_state(fresh, mode)
+            add_head_state(fresh, mode)
+            self._sd.update(fresh)
+            self._trainable = 'head'
+            self._materialise()
+            handed = [k for k in self._sd if k.startswith(('proj.', 'pred.')) and k.endswith(_PARAM_SUFFIX)]
+            return [self._param_objs[k] if k in self._param_objs else torch.nn.Parameter(self._sd[k], requires_grad=True) for k in handed]
+        if 'selfsup' in mode:
+            raise NotImplementedError('prepare mode %r (joint meta + head training) is not used by the shipped scripts' % mode)
+        if 'meta' in mode:
+            self._trainable = 'meta'
+            if self.prepare_mode is None or 'selfsup' not in self.prepare_mode:
+                self.prepare_mode = mode
+            add_head_state(self._sd, mode)
+            self._materialise()
+            return list(self._param_objs.values())
+        raise NotImplementedError('prepare mode %r' % mode)
+
+    def compute_loss(self, input_rgb=None, output_depth=None, validity_map=None, ground_truth=None, l1_weight=1.0, l2_weight=1.0,
+                     loss_type='pretrain'):
+        """src/msg_chn_model_adapt.py:203-264: masked L2 against the ground truth on output_depth[0] (evaluated by the engine on the
+        prediction of its last stage-1 forward)"""
+        out0 = output_depth[0] if isinstance(output_depth, (list, tuple)) else output_depth
+        eng = self._engine_for(out0)
+        loss = _L2LossFn.apply(eng, out0, ground_truth.contiguous(), float(self.max_predict_depth))
+        return loss, {'loss': loss}
 
     def train(self):
         self.training = True
@@ -407,7 +552,52 @@ class ExternalModel_Adapt(object):
                                    validity_map=validity_map, embedding=embedding, reference=reference,
                                    w_loss_sparse_depth=w_loss_sparse_depth, w_loss_smoothness=w_loss_smoothness,
                                    w_loss_cos=w_loss_cos)
+        if 'prepare' in loss_type:                                  # src/external_model_adapt.py:155-158
+            return self.prepare_loss(embedding=embedding, reference=reference)
+        if self.model_name == 'msg_chn' and ('init' in loss_type or loss_type == 'pretrain') and ground_truth is not None:   # :174-180, :225-230
+            if w_loss_smoothness != 0.0:
+                raise NotImplementedError('supervised loss with a smoothness term (src/external_model_adapt.py:232-234)')
+            return self.model.compute_loss(input_rgb=input_rgb, output_depth=output_depth, validity_map=validity_map,
+                                           ground_truth=ground_truth, loss_type=loss_type)
         raise NotImplementedError('loss_type %r is outside the TTA hot path (DESIGN.md, scope table)' % loss_type)
+
+    def prepare_loss(self, embedding, reference):
+        """src/external_model_adapt.py:524-540 -- cosine distance between the stage-2 forward's emb and ref"""
+        if self.model_name != 'msg_chn':
+            raise NotImplementedError('stage-2 head training is implemented for msg_chn')
+        eng = self.model._engines.get(getattr(self.model, '_last_key', None))
+        if eng is None:
+            raise RuntimeError('prepare_loss called before a stage-2 forward')
+        loss = _CosLossFn.apply(eng, embedding, reference)
+        return loss, {'loss': loss}
+
+    def prepare_parameters(self, mode=''):
+        return self.model.prepare_parameters(mode)
+
+    def init_step(self, image_raw, sparse_depth, ground_truth, learning_rate, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        """One whole stage-1 step (src/init_main.py:482-522: forward 'init_meta...', supervised loss, backward, Adam) in one library
+        call; `last_losses()['loss']` reads the loss."""
+        eng = self._prep_engine(image_raw, 'meta', (learning_rate, betas, eps, weight_decay))
+        eng.init_step(image_raw, sparse_depth, ground_truth.contiguous(), self.max_input_depth, self.max_predict_depth,
+                      self.model.img_scale, self.model.img_shift)
+        self._last_engine = eng
+
+    def head_step(self, image_raw, sparse_depth, learning_rate, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        """One whole stage-2 step (src/head_main.py:437-480) in one library call."""
+        eng = self._prep_engine(image_raw, 'head', (learning_rate, betas, eps, weight_decay))
+        eng.head_step(image_raw, sparse_depth, self.max_input_depth, self.model.img_scale, self.model.img_shift)
+        self._last_engine = eng
+
+    def _prep_engine(self, image_raw, trainable, hyper):
+        if self.model_name != 'msg_chn':
+            raise NotImplementedError('the source-domain preparation steps are implemented for msg_chn')
+        if self.model._trainable != trainable:
+            raise RuntimeError('call prepare_parameters(...) for the %s stage first' % trainable)
+        eng = self.model._engine_for(image_raw)
+        if getattr(eng, '_hyper', None) != hyper:
+            eng.set_adam(hyper[0], hyper[1], hyper[2], hyper[3], step_count=-1)
+            eng._hyper = hyper
+        return eng
 
     def adapt_loss(self, input_rgb, output_depth, sparse_depth, validity_map, embedding, reference, w_loss_sparse_depth=1.0,
                    w_loss_smoothness=1.0, w_loss_cos=1.0):

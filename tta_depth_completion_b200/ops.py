@@ -369,3 +369,51 @@ def input_stage(image_u8_hwc, depth_u16, crop_shape=None, crop_type=('bottom',),
     check(_lib.lib().ptta_input_stage(ptr(image_u8_hwc), ptr(depth_u16), ptr(image), ptr(depth), ptr(validity), n, h0, w0, y0, x0, h, w,
                                       float(depth_multiplier), _stream()), 'input_stage')
     return image, depth, validity
+
+
+# ---- host-side PNG decoding (csrc/png_host.cu) --------------------------------------------------------------
+def _file_bytes(src):
+    if isinstance(src, (bytes, bytearray, memoryview)):
+        return bytes(src)
+    with open(src, 'rb') as f:
+        return f.read()
+
+
+def png_info(src):
+    """(width, height, channels, bit_depth) of a PNG file (path or bytes) -- header only"""
+    data = _file_bytes(src)
+    w, h, c, d = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(_lib.lib().ptta_png_info(data, len(data), ctypes.byref(w), ctypes.byref(h), ctypes.byref(c), ctypes.byref(d)), 'png_info')
+    return w.value, h.value, c.value, d.value
+
+
+def _decode_png(src, out, fn_name, dtype, channels):
+    import numpy as np
+    data = _file_bytes(src)
+    w, h, _, _ = png_info(data)
+    shape = (h, w, channels) if channels > 1 else (h, w)
+    if out is None:
+        out = np.empty(shape, dtype=dtype)
+    if isinstance(out, torch.Tensor):            # e.g. a pinned staging buffer: decoded in place, no intermediate copy
+        if out.is_cuda or not out.is_contiguous() or tuple(out.shape) != shape or out.element_size() != np.dtype(dtype).itemsize:
+            raise TypeError('out must be a contiguous host tensor of shape %s' % (shape,))
+        p, nbytes = out.data_ptr(), out.numel() * out.element_size()
+    else:
+        if out.dtype != dtype or not out.flags['C_CONTIGUOUS'] or out.shape != shape:
+            raise TypeError('out must be a C-contiguous %s array of shape %s' % (np.dtype(dtype).name, shape))
+        p, nbytes = out.ctypes.data, out.nbytes
+    check(getattr(_lib.lib(), fn_name)(data, len(data), c_void_p(p), nbytes), fn_name)
+    return out
+
+
+def decode_png_rgb8(src, out=None):
+    """what `np.asarray(Image.open(path).convert('RGB'))` holds (src/data_utils.py:149-152): uint8 [H, W, 3]; `out` may be a numpy array or a
+    (pinned) host torch tensor to decode into"""
+    import numpy as np
+    return _decode_png(src, out, 'ptta_png_decode_rgb8', np.uint8, 3)
+
+
+def decode_png_gray16(src, out=None):
+    """what `np.array(Image.open(path))` holds for a 16-bit (or 8-bit) grey depth map (src/data_utils.py:186, 219): uint16 [H, W]"""
+    import numpy as np
+    return _decode_png(src, out, 'ptta_png_decode_gray16', np.uint16, 1)
