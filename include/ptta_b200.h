@@ -278,6 +278,22 @@ int ptta_eval_metrics(const float* output_depth, const float* ground_truth, long
  * payloads -> fp32 image NCHW in [0,255], depth and validity [n,1,h,w]; bit-exact with the numpy code */
 int ptta_input_stage(const void* image_u8_hwc, const void* depth_u16, float* image_nchw, float* depth, float* validity, int n,
                      int h0, int w0, int y0, int x0, int h, int w, float depth_multiplier, ptta_stream_t stream);
+/* On-device augmentations of the adaptation / preparation loops (src/transforms.py; the drop-in mirror with the reference's RNG draw
+ * order is tta_depth_completion_b200/transforms.py).
+ * ptta_augment_photometric: src/transforms.py:236-333 + :669-712 on an fp32 [N,3,H,W] image in [0,255]: uint8 truncation, per-sample
+ * brightness / contrast / saturation as torchvision's tensor ops compute them (`_blend`, `rgb_to_grayscale`; every product and sum rounded
+ * separately, uint8 truncation after each transform), `.float()`, normalisation (norm_mode 0: none, 1: /255, 2: 2x/255-1,
+ * 3: (x/255 - mean[c]) / std[c] with HOST arrays mean3 / std3).  Flag arrays: device uint8 [N] (NULL = transform not configured), factor
+ * arrays: device fp32 [N].  quantize = 1 whenever any photometric transform is configured (the reference then casts to uint8 even for
+ * samples that draw no transform).  workspace: 8 * n bytes, needed for the contrast transform (exact integer sum of the grey image).
+ * ptta_augment_flip: src/transforms.py:990-1034, per-sample horizontal / vertical mirror of an fp32 [N,C,H,W] map (out != in). */
+int ptta_augment_photometric(const float* image, float* out, int n, int h, int w, const unsigned char* do_brightness,
+                             const float* f_brightness, const unsigned char* do_contrast, const float* f_contrast,
+                             const unsigned char* do_saturation, const float* f_saturation, int quantize, int norm_mode,
+                             const float* mean3, const float* std3, void* workspace, ptta_stream_t stream);
+int ptta_augment_flip(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_hflip,
+                      const unsigned char* do_vflip, ptta_stream_t stream);
+
 /* Host-side PNG decoding (no device work; plain host pointers, e.g. pinned staging memory): replaces PIL on the reference's loader path --
  * `np.asarray(Image.open(path).convert('RGB'))` (src/data_utils.py:134-165) and `np.array(Image.open(path))` of the 16-bit depth maps
  * (src/data_utils.py:167-234).  Container parsing with CRC check, zlib inflate, the five scanline filters, colour-type conversion as

@@ -1,0 +1,69 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/transforms.pt by running the REAL reference's `Transforms` class
+(/root/reference/src/transforms.py, CPU tensors) on seeded inputs.  Each case stores the constructor arguments, the seed (inputs and
+draws come from it: torch.manual_seed(seed); inputs first, then the class's own torch.rand calls) and the outputs.
+    python oracle/gen_golden_transforms.py"""
+import importlib
+import os
+import sys
+
+import torch
+from PIL import Image
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+REFERENCE_SRC = '/root/reference/src'
+IMAGENET = [[0.485, 0.456, 0.406], [0.229, 0.224, 0.225]]
+
+CASES = [
+    dict(name='photo_all_p1', seed=11, n=4, h=24, w=40, prob=1.0, kinds=['image'],
+         ctor=dict(normalized_image_range=[0, 1], random_brightness=[0.6, 1.4], random_contrast=[0.6, 1.4], random_saturation=[0.6, 1.4])),
+    dict(name='photo_all_p05', seed=12, n=8, h=16, w=48, prob=0.5, kinds=['image'],
+         ctor=dict(normalized_image_range=[0, 1], random_brightness=[0.5, 1.5], random_contrast=[0.5, 1.5], random_saturation=[0.5, 1.5])),
+    dict(name='photo_sat_imagenet', seed=13, n=3, h=20, w=28, prob=1.0, kinds=['image'],
+         ctor=dict(normalized_image_range=IMAGENET, random_saturation=[0.6, 1.4])),
+    dict(name='photo_bright_pm1', seed=14, n=5, h=12, w=36, prob=1.0, kinds=['image'],
+         ctor=dict(normalized_image_range=[-1, 1], random_brightness=[0.6, 1.4])),
+    dict(name='norm_only', seed=15, n=2, h=12, w=20, prob=1.0, kinds=['image'], ctor=dict(normalized_image_range=[0, 1])),
+    dict(name='flip_hv', seed=16, n=6, h=14, w=22, prob=1.0, kinds=['image', 'depth', 'depth', 'depth'],
+         ctor=dict(random_flip_type=['horizontal', 'vertical'])),
+    dict(name='flip_h_p05', seed=17, n=8, h=10, w=18, prob=0.5, kinds=['image', 'depth'], ctor=dict(random_flip_type=['horizontal'])),
+]
+
+
+def case_inputs(case):
+    """seeded inputs: smooth + textured [0,255] images (so that grey means are not all alike), sparse-ish depth maps"""
+    torch.manual_seed(case['seed'])
+    n, h, w = case['n'], case['h'], case['w']
+    out = []
+    for kind in case['kinds']:
+        if kind == 'image':
+            y = torch.linspace(0, 1, h).view(1, 1, h, 1)
+            x = torch.linspace(0, 1, w).view(1, 1, 1, w)
+            base = 255 * torch.stack([x.expand(n, 1, h, w), y.expand(n, 1, h, w), (x * y).expand(n, 1, h, w)], 1).squeeze(2)
+            scale = torch.rand(n, 3, 1, 1) * 0.8 + 0.2
+            out.append((base * scale + 40 * torch.rand(n, 3, h, w)).clamp(0, 255))
+        else:
+            out.append(torch.rand(n, 1, h, w) * 80 * (torch.rand(n, 1, h, w) < 0.3).float())
+    return out
+
+
+def main():
+    if not hasattr(Image, 'ANTIALIAS'):
+        Image.ANTIALIAS = Image.LANCZOS          # the reference's constructor names the pre-Pillow-10 constant (src/transforms.py:187)
+    sys.path.insert(0, REFERENCE_SRC)
+    T = importlib.import_module('transforms')
+    fixtures = {}
+    for case in CASES:
+        inputs = case_inputs(case)
+        tr = T.Transforms(**case['ctor'])
+        outs = tr.transform(images_arr=[t.clone() for t in inputs], random_transform_probability=case['prob'])
+        fixtures[case['name']] = {'case': case, 'outputs': [o.clone() for o in outs]}
+        print('%-20s %s' % (case['name'], ' '.join('%.6f' % float(o.mean()) for o in outs)))
+    path = os.path.join(ROOT, 'tests', 'golden', 'transforms.pt')
+    torch.save({'fixtures': fixtures, 'torch_version': torch.__version__}, path)
+    print('%s  %.0f KB' % (os.path.relpath(path, ROOT), os.path.getsize(path) / 1024))
+
+
+if __name__ == '__main__':
+    main()

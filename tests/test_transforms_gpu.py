@@ -1,0 +1,105 @@
+"""GPU: the native augmentations (csrc/augment.cuh through tta_depth_completion_b200.transforms.Transforms, the drop-in mirror of
+src/transforms.py) against (a) the fixtures produced by the reference's own class and (b) the CPU oracle at the benchmark frame size.
+The draws are made on the CPU generator here (`rand_device`), so that both sides see the same random numbers.
+
+Stated tolerance: flips, brightness, saturation and every normalisation are BIT-EXACT.  The contrast transform blends with the mean of
+the grey image: the native path sums the grey values exactly (integers), torch.mean accumulates in fp32 in an order of its own -- the two
+means differ by ~1e-7 relative, which moves a pixel by one uint8 step only when the blended value lands within ~1e-5 of an integer:
+at most 1e-4 of the values may differ, each by exactly one grey level."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from golden_util import GOLDEN_DIR
+from oracle import transforms_oracle as TO
+from oracle.gen_golden_transforms import case_inputs, IMAGENET
+from test_transforms_oracle import FIX, case_cfg
+
+DEV = 'cuda'
+
+
+def level(rng):
+    """size of one uint8 step after normalisation"""
+    if rng == [0, 1]:
+        return 1 / 255.0
+    if rng == [-1, 1]:
+        return 2 / 255.0
+    if rng is None or rng == [0, 255]:
+        return 1.0
+    return 1 / 255.0 / min(rng[1])
+
+
+def compare(got, want, contrast, rng, what):
+    got = got.cpu()
+    assert got.shape == want.shape and got.dtype == want.dtype, what
+    if not contrast:
+        assert torch.equal(got, want), (what, float((got - want).abs().max()))
+        return 0.0
+    diff = (got - want).abs()
+    frac = float((diff > 0).float().mean())
+    assert frac <= 1e-4 and float(diff.max()) <= level(rng) * 1.0001 + 1e-6, (what, frac, float(diff.max()))
+    return frac
+
+
+@pytest.mark.parametrize('name', sorted(FIX))
+def test_native_transforms_match_reference_fixture(name):
+    from tta_depth_completion_b200.transforms import Transforms
+    fx = FIX[name]
+    case = fx['case']
+    inputs = case_inputs(case)
+    tr = Transforms(**case['ctor'])
+    tr.rand_device = 'cpu'
+    outs = tr.transform(images_arr=[t.to(DEV) for t in inputs], random_transform_probability=case['prob'])
+    assert len(outs) == len(fx['outputs'])
+    for k, (got, want) in enumerate(zip(outs, fx['outputs'])):
+        compare(got, want, 'random_contrast' in case['ctor'], case['ctor'].get('normalized_image_range'), '%s[%d]' % (name, k))
+
+
+@pytest.mark.parametrize('n,h,w', [(1, 352, 1216), (4, 240, 1216), (2, 480, 640)])
+@pytest.mark.parametrize('rng', [[0, 1], IMAGENET])
+def test_native_photometric_at_frame_size(n, h, w, rng):
+    """the shipped adaptation scripts' jitter (bash/adapt/adapt_msgchn_vkitti.sh: brightness / contrast / saturation 0.6 .. 1.4,
+    probability 1) on full frames, against the CPU oracle on the same draws"""
+    from tta_depth_completion_b200.transforms import Transforms
+    from tta_depth_completion_b200.synthetic import synthetic_frame
+    image = synthetic_frame(3, 0, n, h, w, 'kitti')[0]
+    ctor = dict(normalized_image_range=rng, random_brightness=[0.6, 1.4], random_contrast=[0.6, 1.4], random_saturation=[0.6, 1.4])
+    cfg = {'brightness': [0.6, 1.4], 'contrast': [0.6, 1.4], 'saturation': [0.6, 1.4]}
+    worst = 0.0
+    for seed in range(3):
+        torch.manual_seed(100 + seed)
+        d = TO.draws(n, cfg, 1.0)
+        want = TO.apply([image], cfg, d, rng)[0]
+        tr = Transforms(**ctor)
+        tr.rand_device = 'cpu'
+        torch.manual_seed(100 + seed)
+        got = tr.transform(images_arr=[image.to(DEV)], random_transform_probability=1.0)[0]
+        worst = max(worst, compare(got, want, True, rng, 'seed %d' % seed))
+    print('fraction of values off by one grey level (contrast mean): %.2e' % worst)
+
+
+def test_native_flips_at_frame_size():
+    from tta_depth_completion_b200.transforms import Transforms
+    from tta_depth_completion_b200.synthetic import synthetic_frame
+    image, sparse, dense = synthetic_frame(4, 1, 4, 240, 1216, 'kitti')
+    cfg = {'flip': ('horizontal', 'vertical')}
+    torch.manual_seed(7)
+    d = TO.draws(4, cfg, 1.0)
+    want = TO.apply([image, sparse, dense], cfg, d, None)
+    tr = Transforms(random_flip_type=['horizontal', 'vertical'])
+    tr.rand_device = 'cpu'
+    torch.manual_seed(7)
+    got = tr.transform(images_arr=[image.to(DEV), sparse.to(DEV), dense.to(DEV)], random_transform_probability=1.0)
+    for g, w_ in zip(got, want):
+        assert torch.equal(g.cpu(), w_)
+
+
+def test_unsupported_options_fail_loudly():
+    from tta_depth_completion_b200.transforms import Transforms
+    with pytest.raises(NotImplementedError, match='random_rotate_max'):
+        Transforms(random_rotate_max=5)
+    with pytest.raises(NotImplementedError, match='random_resize_and_crop'):
+        Transforms(random_resize_and_crop=[1.0, 1.5])

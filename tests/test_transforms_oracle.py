@@ -1,0 +1,36 @@
+"""CPU: oracle/transforms_oracle.py (restatement of the reference's Transforms for the natively implemented options) against the
+fixtures produced by the reference's own class (oracle/gen_golden_transforms.py) -- bit-exact: same torch / torchvision CPU ops, same draws."""
+import os
+
+import pytest
+import torch
+
+from golden_util import GOLDEN_DIR
+from oracle import transforms_oracle as TO
+from oracle.gen_golden_transforms import case_inputs
+
+FIX = torch.load(os.path.join(GOLDEN_DIR, 'transforms.pt'), weights_only=False)['fixtures']
+
+
+def case_cfg(case):
+    c = case['ctor']
+    cfg = {}
+    for k in ('brightness', 'contrast', 'saturation'):
+        if 'random_' + k in c:
+            cfg[k] = c['random_' + k]
+    if 'random_flip_type' in c:
+        cfg['flip'] = tuple(c['random_flip_type'])
+    return cfg
+
+
+@pytest.mark.parametrize('name', sorted(FIX))
+def test_oracle_equals_reference_transforms(name):
+    fx = FIX[name]
+    case = fx['case']
+    inputs = case_inputs(case)                      # seeds the generator; the draws continue from there, as in the generator script
+    cfg = case_cfg(case)
+    d = TO.draws(case['n'], cfg, case['prob'])
+    outs = TO.apply(inputs, cfg, d, case['ctor'].get('normalized_image_range'))
+    assert len(outs) == len(fx['outputs'])
+    for got, want in zip(outs, fx['outputs']):
+        assert got.dtype == want.dtype and torch.equal(got, want)

@@ -47,6 +47,21 @@ def main():
         out['gemm_tn_%dx512x512' % rows] = {'us': round(ms * 1e3, 2), 'tflops': round(2.0 * rows * 512 * 512 / ms / 1e9, 1),
                                             'algorithmic_GBps': round((2 * rows * 512 * 2 + 512 * 512 * 4) / ms / 1e6, 1),
                                             'cublas_bf16_us': round(ref * 1e3, 2)}
+    # on-device augmentations (csrc/augment.cuh): all three photometric transforms on, [0,1] normalisation; and one flip pass of the image
+    for n in args.batch:
+        h, w = 352, 1216
+        img = (torch.rand(n, 3, h, w, device=DEV) * 255).contiguous()
+        o = torch.empty_like(img)
+        on = torch.ones(n, dtype=torch.uint8, device=DEV)
+        f = torch.full((n,), 1.2, device=DEV)
+        ws = torch.empty(n, dtype=torch.int64, device=DEV)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = _lib.ptr
+        ms = timed(lambda: L.ptta_augment_photometric(P(img), P(o), n, h, w, P(on), P(f), P(on), P(f), P(on), P(f), 1, 1, None, None, P(ws), st), 200)
+        alg = 3 * img.numel() * 4          # grey-sum pass reads the image, the apply pass reads it again and writes the result
+        out['augment_photometric_%dx352x1216' % n] = {'us': round(ms * 1e3, 2), 'algorithmic_GBps': round(alg / ms / 1e6, 1)}
+        ms = timed(lambda: L.ptta_augment_flip(P(img), P(o), n, 3, h, w, P(on), None, st), 200)
+        out['augment_flip_%dx3x352x1216' % n] = {'us': round(ms * 1e3, 2), 'algorithmic_GBps': round(2 * img.numel() * 4 / ms / 1e6, 1)}
     for n in args.batch:
         sd = get_checkpoint('kitti_2layers_a', 'meta_selfsup_seq_2layers_ema')
         frames = [tuple(t.to(DEV) for t in synthetic_frame(60, k, n, 352, 1216, 'kitti')) for k in range(4)]

@@ -25,6 +25,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tn_tc.cuh"
 #include "nlspn_prop.cuh"
+#include "augment.cuh"
 #include "../../include/ptta_b200.h"
 
 namespace ptta {
@@ -1775,6 +1776,44 @@ int ptta_tta_loss_backward_emb(const void* emb, const void* ref, long long rows,
     launch_k(loss_cos_grad_kernel, L.cos_blocks, 256, 0, (cudaStream_t)stream, (const bf16*)emb, (const bf16*)ref, (const float*)(ws + L.rowstat),
                                                       (const LossScalars*)(ws + L.scalars), (bf16*)g_emb, rows, dim, gscale, 1);
     return check_launch("loss_cos_grad(emb)");
+}
+
+// ---- on-device augmentations (augment.cuh) ----------------------------------------------------------------------
+int ptta_augment_photometric(const float* image, float* out, int n, int h, int w, const unsigned char* do_brightness, const float* f_brightness,
+                             const unsigned char* do_contrast, const float* f_contrast, const unsigned char* do_saturation,
+                             const float* f_saturation, int quantize, int norm_mode, const float* mean3, const float* std3, void* workspace,
+                             ptta_stream_t stream) {
+    PTTA_CHECK(image && out && n >= 1 && h >= 1 && w >= 1, "augment_photometric: bad argument");
+    PTTA_CHECK(norm_mode >= 0 && norm_mode <= 3, "augment_photometric: normalisation mode %d", norm_mode);
+    PTTA_CHECK(norm_mode != 3 || (mean3 && std3), "augment_photometric: standard normalisation needs mean and std");
+    PTTA_CHECK((!do_brightness || f_brightness) && (!do_contrast || f_contrast) && (!do_saturation || f_saturation),
+               "augment_photometric: a flag array without its factor array");
+    PTTA_CHECK(!do_contrast || workspace, "augment_photometric: the contrast transform needs a workspace of 8 * n bytes");
+    PTTA_CHECK(quantize || !(do_brightness || do_contrast || do_saturation), "augment_photometric: the photometric transforms work on the uint8 image");
+    PTTA_CHECK((long long)h * w < (1ll << 31) / 3 && n <= 65535, "augment_photometric: image too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    PhotoParams p; memset(&p, 0, sizeof(p));
+    p.in = image; p.out = out; p.do_b = do_brightness; p.do_c = do_contrast; p.do_s = do_saturation;
+    p.f_b = f_brightness; p.f_c = f_contrast; p.f_s = f_saturation; p.gray_sum = (unsigned long long*)workspace;
+    p.N = n; p.HW = h * w; p.quantize = quantize; p.norm_mode = norm_mode;
+    for (int k = 0; k < 3; ++k) { p.mean[k] = mean3 ? mean3[k] : 0.f; p.std[k] = std3 ? std3[k] : 1.f; }
+    const int bx = std::min(cdiv(p.HW, 256 * 4), 1184);
+    if (do_contrast) {
+        PTTA_CUDA(cudaMemsetAsync(workspace, 0, sizeof(unsigned long long) * n, st));
+        launch_k(photo_gray_sum_kernel, dim3(bx, n), 256, 0, st, p);
+        PTTA_TRY(check_launch("photo_gray_sum"));
+    }
+    launch_k(photo_apply_kernel, dim3(bx, n), 256, 0, st, p);
+    return check_launch("photo_apply");
+}
+
+int ptta_augment_flip(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_hflip, const unsigned char* do_vflip,
+                      ptta_stream_t stream) {
+    PTTA_CHECK(in && out && in != out && n >= 1 && c >= 1 && h >= 1 && w >= 1, "augment_flip: bad argument (in-place is not supported)");
+    PTTA_CHECK((long long)c * h * w < (1ll << 31) && n <= 65535, "augment_flip: map too large");
+    const int bx = std::min(cdiv((long long)c * h * w, 256 * 4), 1184);
+    launch_k(flip_kernel, dim3(bx, n), 256, 0, (cudaStream_t)stream, in, out, c, h, w, do_hflip, do_vflip);
+    return check_launch("flip");
 }
 
 int ptta_adam_flat(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps, double wd, int step,
