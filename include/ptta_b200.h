@@ -293,6 +293,17 @@ int ptta_augment_photometric(const float* image, float* out, int n, int h, int w
                              const float* mean3, const float* std3, void* workspace, ptta_stream_t stream);
 int ptta_augment_flip(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_hflip,
                       const unsigned char* do_vflip, ptta_stream_t stream);
+/* ptta_augment_rotate: src/transforms.py:406-423, 1036-1070 (torchvision functional.rotate, expand=False, fill=None = affine grid +
+ * grid_sample with zero padding, align_corners=False).  theta_n_x_6: device fp32 [N][6], the 3 x 2 matrix torchvision multiplies its
+ * base grid with (theta^T / (0.5 w, 0.5 h); x column first), prepared on the host as torchvision does.  mode 0 nearest, 1 bilinear.
+ * ptta_augment_resize_crop: src/transforms.py:425-502, 1222-1283 (functional.resize to (resize_h, resize_w) >= (h, w), then the crop
+ * [start_y, start_y + h) x [start_x, start_x + w)): device int32 [N] arrays; only the surviving h x w pixels are computed.
+ * Both: fp32 [N,C,H,W], out != in, samples whose flag is clear are copied. */
+int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate,
+                        const float* theta_n_x_6, int mode, ptta_stream_t stream);
+int ptta_augment_resize_crop(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_resize,
+                             const int* resize_h, const int* resize_w, const int* start_y, const int* start_x, int mode,
+                             ptta_stream_t stream);
 
 /* Host-side PNG decoding (no device work; plain host pointers, e.g. pinned staging memory): replaces PIL on the reference's loader path --
  * `np.asarray(Image.open(path).convert('RGB'))` (src/data_utils.py:134-165) and `np.array(Image.open(path))` of the 16-bit depth maps

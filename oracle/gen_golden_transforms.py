@@ -6,6 +6,7 @@ import importlib
 import os
 import sys
 
+import numpy as np
 import torch
 from PIL import Image
 
@@ -27,6 +28,15 @@ CASES = [
     dict(name='norm_only', seed=15, n=2, h=12, w=20, prob=1.0, kinds=['image'], ctor=dict(normalized_image_range=[0, 1])),
     dict(name='flip_hv', seed=16, n=6, h=14, w=22, prob=1.0, kinds=['image', 'depth', 'depth', 'depth'],
          ctor=dict(random_flip_type=['horizontal', 'vertical'])),
+    dict(name='rotate5', seed=18, n=6, h=20, w=32, prob=1.0, kinds=['image', 'depth', 'depth', 'depth'], modes=['bilinear', 'nearest', 'nearest', 'nearest'],
+         ctor=dict(random_rotate_max=5)),
+    dict(name='rotate25_p05', seed=19, n=8, h=16, w=16, prob=0.5, kinds=['image', 'depth'], modes=['bilinear', 'nearest'], ctor=dict(random_rotate_max=25)),
+    dict(name='resize_crop', seed=20, n=6, h=16, w=24, prob=1.0, kinds=['image', 'depth', 'depth', 'depth'], modes=['bilinear', 'nearest', 'nearest', 'nearest'],
+         intrinsics=True, ctor=dict(random_resize_and_crop=[1.0, 1.5])),
+    # the geometric set of the shipped adaptation scripts (bash/adapt/adapt_msgchn_vkitti.sh:37-41)
+    dict(name='adapt_script_geometric', seed=21, n=8, h=24, w=40, prob=1.0, kinds=['image', 'depth', 'depth', 'depth'],
+         modes=['bilinear', 'nearest', 'nearest', 'nearest'], intrinsics=True,
+         ctor=dict(random_flip_type=['horizontal'], random_rotate_max=5, random_resize_and_crop=[1.0, 1.5])),
     dict(name='flip_h_p05', seed=17, n=8, h=10, w=18, prob=0.5, kinds=['image', 'depth'], ctor=dict(random_flip_type=['horizontal'])),
 ]
 
@@ -48,6 +58,13 @@ def case_inputs(case):
     return out
 
 
+def case_intrinsics(case):
+    K = torch.eye(3).repeat(case['n'], 1, 1)
+    K[:, 0, 0] = 700.0 + torch.arange(case['n']); K[:, 1, 1] = 710.0
+    K[:, 0, 2] = case['w'] / 2.0; K[:, 1, 2] = case['h'] / 2.0
+    return K
+
+
 def main():
     if not hasattr(Image, 'ANTIALIAS'):
         Image.ANTIALIAS = Image.LANCZOS          # the reference's constructor names the pre-Pillow-10 constant (src/transforms.py:187)
@@ -56,9 +73,18 @@ def main():
     fixtures = {}
     for case in CASES:
         inputs = case_inputs(case)
+        np.random.seed(case['seed'])
         tr = T.Transforms(**case['ctor'])
-        outs = tr.transform(images_arr=[t.clone() for t in inputs], random_transform_probability=case['prob'])
-        fixtures[case['name']] = {'case': case, 'outputs': [o.clone() for o in outs]}
+        kw = {}
+        if 'modes' in case:
+            kw['interpolation_modes'] = tr.map_interpolation_mode_names_to_enums(case['modes'])
+        Ks = None
+        if case.get('intrinsics'):
+            kw['intrinsics_arr'] = [case_intrinsics(case)]
+        outs = tr.transform(images_arr=[t.clone() for t in inputs], random_transform_probability=case['prob'], **kw)
+        if case.get('intrinsics'):
+            outs, Ks = outs
+        fixtures[case['name']] = {'case': case, 'outputs': [o.clone() for o in outs], 'intrinsics': [k.clone() for k in Ks] if Ks else None}
         print('%-20s %s' % (case['name'], ' '.join('%.6f' % float(o.mean()) for o in outs)))
     path = os.path.join(ROOT, 'tests', 'golden', 'transforms.pt')
     torch.save({'fixtures': fixtures, 'torch_version': torch.__version__}, path)

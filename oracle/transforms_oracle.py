@@ -1,11 +1,15 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's `Transforms.transform` (src/transforms.py:192-668) for the options
 the native path implements: brightness / contrast / saturation jitter (:236-301, per-sample torchvision tensor ops, :714-837), image
-normalisation (:669-712) and per-sample flips (:386-407, 990-1034).  The third-party arithmetic is torchvision's
+normalisation (:669-712), per-sample flips (:386-407, 990-1034), rotation (:406-423, 1036-1070) and resize-and-crop (:425-502, 1222-1283).  The third-party arithmetic is torchvision's
 (`torchvision.transforms.functional.adjust_*`, pinned 0.10.1 by the reference's README.md:74; 0.26 here -- the tensor code path
 `_blend` / `rgb_to_grayscale` is unchanged between the two) and is called as the reference calls it.  Pinned against fixtures produced by
 the reference's own class: oracle/gen_golden_transforms.py, tests/test_transforms_oracle.py."""
+import numpy as np
 import torch
 from torchvision.transforms import functional
+from torchvision.transforms import InterpolationMode
+
+_MODE = {'nearest': InterpolationMode.NEAREST, 'bilinear': InterpolationMode.BILINEAR, 0: InterpolationMode.NEAREST, 2: InterpolationMode.BILINEAR}
 
 
 def draws(n_batch, cfg, probability, rand=lambda n: torch.rand(n)):
@@ -21,10 +25,25 @@ def draws(n_batch, cfg, probability, rand=lambda n: torch.rand(n)):
     for name in ('horizontal', 'vertical'):
         if name in cfg.get('flip', ()):
             d['do_' + name] = torch.logical_and(d['do'], rand(n_batch) <= 0.50)
+    if 'rotate' in cfg:                                                         # T:406-416 (angles from numpy's global generator)
+        d['do_rotate'] = torch.logical_and(d['do'], rand(n_batch) <= 0.50)
+        m = cfg['rotate']
+        d['angles'] = (m - (-m)) * np.random.rand(n_batch) + (-m)
+    if 'resize_and_crop' in cfg:                                                # T:425-480
+        lo, hi = cfg['resize_and_crop']
+        h, w = cfg['shape']
+        d['do_resize_and_crop'] = torch.logical_and(d['do'], rand(n_batch) <= 0.50)
+        d['r_height'] = torch.randint(low=int(lo * h), high=int(hi * h), size=(n_batch,))
+        d['r_width'] = torch.randint(low=int(lo * w), high=int(hi * w), size=(n_batch,))
+        sy, sx = [], []
+        for b in range(n_batch):
+            sy.append(torch.randint(low=0, high=int(d['r_height'][b]) - h + 1, size=(1,)))
+            sx.append(torch.randint(low=0, high=int(d['r_width'][b]) - w + 1, size=(1,)))
+        d['start_y'], d['start_x'] = torch.cat(sy), torch.cat(sx)
     return d
 
 
-def apply(images_arr, cfg, d, normalized_image_range=None):
+def apply(images_arr, cfg, d, normalized_image_range=None, interpolation_modes=('nearest',)):
     images_arr = [im.clone() for im in images_arr]
     photometric = any(k in cfg for k in ('brightness', 'contrast', 'saturation'))
     if photometric:
@@ -53,4 +72,43 @@ def apply(images_arr, cfg, d, normalized_image_range=None):
                 for b in range(images.shape[0]):
                     if d['do_' + name][b]:
                         images[b, ...] = torch.flip(images[b], dims=[dim])                                       # T:990-1034
+    if 'do_rotate' in d:                                                        # T:1036-1070
+        modes = list(interpolation_modes) + [interpolation_modes[-1]] * (len(images_arr) - len(interpolation_modes))
+        for images, mode in zip(images_arr, modes):
+            for b in range(images.shape[0]):
+                if d['do_rotate'][b]:
+                    images[b, ...] = functional.rotate(images[b], angle=d['angles'][b], interpolation=_MODE[mode], expand=False)
+    if 'do_resize_and_crop' in d:                                               # T:1222-1283
+        modes = list(interpolation_modes) + [interpolation_modes[-1]] * (len(images_arr) - len(interpolation_modes))
+        h, w = images_arr[0].shape[-2:]
+        for i, (images, mode) in enumerate(zip(images_arr, modes)):
+            out = []
+            for b in range(images.shape[0]):
+                image = images[b]
+                if d['do_resize_and_crop'][b]:
+                    image = functional.resize(image, size=(int(d['r_height'][b]), int(d['r_width'][b])), interpolation=_MODE[mode])
+                    y0, x0 = int(d['start_y'][b]), int(d['start_x'][b])
+                    image = image[..., y0:y0 + h, x0:x0 + w]
+                out.append(image)
+            images_arr[i] = torch.stack(out, dim=0)
     return images_arr
+
+
+def adjust_intrinsics(intrinsics_arr, d, shape):
+    """T:449-453, 498-502 with T:1330-1378: every sample's intrinsics are rescaled and shifted, also those the transform skipped"""
+    if 'do_resize_and_crop' not in d:
+        return [K.clone() for K in intrinsics_arr]
+    h, w = shape
+    out = []
+    for K in intrinsics_arr:
+        K = K.clone()
+        for b in range(len(K)):
+            xs, ys = d['r_width'][b] / w, d['r_height'][b] / h
+            K[b, 0, 0] = K[b, 0, 0] * xs
+            K[b, 0, 2] = K[b, 0, 2] * xs
+            K[b, 1, 1] = K[b, 1, 1] * ys
+            K[b, 1, 2] = K[b, 1, 2] * ys
+            K[b, 0, 2] = K[b, 0, 2] * 1.0 - (d['r_width'][b] - w)
+            K[b, 1, 2] = K[b, 1, 2] * 1.0 - (d['r_height'][b] - h)
+        out.append(K)
+    return out

@@ -5,9 +5,11 @@ The draws are made on the CPU generator here (`rand_device`), so that both sides
 Stated tolerance: flips, brightness, saturation and every normalisation are BIT-EXACT.  The contrast transform blends with the mean of
 the grey image: the native path sums the grey values exactly (integers), torch.mean accumulates in fp32 in an order of its own -- the two
 means differ by ~1e-7 relative, which moves a pixel by one uint8 step only when the blended value lands within ~1e-5 of an integer:
-at most 1e-4 of the values may differ, each by exactly one grey level."""
+at most 1e-4 of the values may differ, each by exactly one grey level.  Rotation / resize-and-crop resample in fp32: see
+`compare_resampled`."""
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -52,10 +54,61 @@ def test_native_transforms_match_reference_fixture(name):
     inputs = case_inputs(case)
     tr = Transforms(**case['ctor'])
     tr.rand_device = 'cpu'
-    outs = tr.transform(images_arr=[t.to(DEV) for t in inputs], random_transform_probability=case['prob'])
+    np.random.seed(case['seed'])
+    kw = {}
+    if 'modes' in case:
+        kw['interpolation_modes'] = tr.map_interpolation_mode_names_to_enums(case['modes'])
+    if case.get('intrinsics'):
+        from oracle.gen_golden_transforms import case_intrinsics
+        kw['intrinsics_arr'] = [case_intrinsics(case).to(DEV)]
+    outs = tr.transform(images_arr=[t.to(DEV) for t in inputs], random_transform_probability=case['prob'], **kw)
+    if case.get('intrinsics'):
+        outs, Ks = outs
+        assert torch.equal(Ks[0].cpu(), fx['intrinsics'][0])
     assert len(outs) == len(fx['outputs'])
+    resampled = 'random_rotate_max' in case['ctor'] or 'random_resize_and_crop' in case['ctor']
     for k, (got, want) in enumerate(zip(outs, fx['outputs'])):
-        compare(got, want, 'random_contrast' in case['ctor'], case['ctor'].get('normalized_image_range'), '%s[%d]' % (name, k))
+        if resampled:
+            compare_resampled(got, want, '%s[%d]' % (name, k))
+        else:
+            compare(got, want, 'random_contrast' in case['ctor'], case['ctor'].get('normalized_image_range'), '%s[%d]' % (name, k))
+
+
+def compare_resampled(got, want, what, max_bad=2e-3):
+    """rotation / resize: the source coordinate of every output pixel is a chain of fp32 operations that torch evaluates through a batched
+    matrix product (rotation) or in another association (resize); a coordinate that differs in its last bit picks another source pixel
+    only when it sits on a rounding boundary (nearest) or moves a bilinear weight by ~1e-6.  Stated tolerance: values equal to 1e-4 of the
+    value range everywhere except at most 0.2 % of the pixels (the boundary cases)."""
+    got = got.cpu()
+    assert got.shape == want.shape and got.dtype == want.dtype, what
+    scale = max(float(want.abs().max()), 1e-6)
+    bad = float(((got - want).abs() > 1e-4 * scale).float().mean())
+    assert bad <= max_bad, (what, bad)
+    return bad
+
+
+@pytest.mark.parametrize('n,h,w', [(4, 240, 1216), (1, 352, 1216)])
+def test_native_geometric_at_frame_size(n, h, w):
+    """the geometric set of the shipped adaptation scripts (horizontal flip, rotate 5, resize-and-crop 1.0 .. 1.5; image bilinear, sparse depth /
+    validity / ground truth nearest) on full frames, against the CPU oracle (torchvision on the same draws)"""
+    from tta_depth_completion_b200.transforms import Transforms
+    from tta_depth_completion_b200.synthetic import synthetic_frame
+    image, sparse, dense = synthetic_frame(5, 2, n, h, w, 'kitti')
+    validity = (sparse > 0).float()
+    cfg = {'flip': ('horizontal',), 'rotate': 5, 'resize_and_crop': [1.0, 1.5], 'shape': (h, w)}
+    modes = ['bilinear', 'nearest', 'nearest', 'nearest']
+    worst = 0.0
+    for seed in range(3):
+        torch.manual_seed(200 + seed); np.random.seed(200 + seed)
+        d = TO.draws(n, cfg, 1.0)
+        want = TO.apply([image, sparse, validity, dense], cfg, d, None, modes)
+        tr = Transforms(random_flip_type=['horizontal'], random_rotate_max=5, random_resize_and_crop=[1.0, 1.5])
+        tr.rand_device = 'cpu'
+        torch.manual_seed(200 + seed); np.random.seed(200 + seed)
+        got = tr.transform(images_arr=[t.to(DEV) for t in (image, sparse, validity, dense)], interpolation_modes=modes, random_transform_probability=1.0)
+        for k, (g, w_) in enumerate(zip(got, want)):
+            worst = max(worst, compare_resampled(g, w_, 'seed %d tensor %d' % (seed, k)))
+    print('fraction of pixels beyond 1e-4 of the range (rounding-boundary source pixels): %.2e' % worst)
 
 
 @pytest.mark.parametrize('n,h,w', [(1, 352, 1216), (4, 240, 1216), (2, 480, 640)])
@@ -99,7 +152,9 @@ def test_native_flips_at_frame_size():
 
 def test_unsupported_options_fail_loudly():
     from tta_depth_completion_b200.transforms import Transforms
-    with pytest.raises(NotImplementedError, match='random_rotate_max'):
-        Transforms(random_rotate_max=5)
-    with pytest.raises(NotImplementedError, match='random_resize_and_crop'):
-        Transforms(random_resize_and_crop=[1.0, 1.5])
+    with pytest.raises(NotImplementedError, match='random_resize_and_pad'):
+        Transforms(random_resize_and_pad=[0.5, 1.0])
+    with pytest.raises(NotImplementedError, match='random_hue'):
+        Transforms(random_hue=[-0.1, 0.1])
+    with pytest.raises(NotImplementedError, match='random_crop_to_shape'):
+        Transforms(random_crop_to_shape=[32, 64])

@@ -2,6 +2,7 @@
 fixtures produced by the reference's own class (oracle/gen_golden_transforms.py) -- bit-exact: same torch / torchvision CPU ops, same draws."""
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -20,6 +21,11 @@ def case_cfg(case):
             cfg[k] = c['random_' + k]
     if 'random_flip_type' in c:
         cfg['flip'] = tuple(c['random_flip_type'])
+    if c.get('random_rotate_max', 0) > 0:
+        cfg['rotate'] = c['random_rotate_max']
+    if 'random_resize_and_crop' in c:
+        cfg['resize_and_crop'] = c['random_resize_and_crop']
+        cfg['shape'] = (case['h'], case['w'])
     return cfg
 
 
@@ -29,8 +35,13 @@ def test_oracle_equals_reference_transforms(name):
     case = fx['case']
     inputs = case_inputs(case)                      # seeds the generator; the draws continue from there, as in the generator script
     cfg = case_cfg(case)
+    np.random.seed(case['seed'])
     d = TO.draws(case['n'], cfg, case['prob'])
-    outs = TO.apply(inputs, cfg, d, case['ctor'].get('normalized_image_range'))
+    outs = TO.apply(inputs, cfg, d, case['ctor'].get('normalized_image_range'), case.get('modes', ('nearest',)))
     assert len(outs) == len(fx['outputs'])
     for got, want in zip(outs, fx['outputs']):
         assert got.dtype == want.dtype and torch.equal(got, want)
+    if fx.get('intrinsics'):
+        from oracle.gen_golden_transforms import case_intrinsics
+        Ks = TO.adjust_intrinsics([case_intrinsics(case)], d, (case['h'], case['w']))
+        assert torch.equal(Ks[0], fx['intrinsics'][0])

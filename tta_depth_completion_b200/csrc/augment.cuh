@@ -9,6 +9,7 @@
 //   normalisation of :669-712.  One reduction pass (only for samples with the contrast flag: exact integer sum of the grey values)
 //   and ONE elementwise pass instead of ~15 tensor ops and three host syncs per sample (`float(factors[b])`).
 //   flips (src/transforms.py:386-407, 990-1034): per-sample horizontal / vertical mirror of an N x C x H x W map.
+//   rotation (:406-423) and resize-and-crop (:425-502): per-sample resampling, nearest or bilinear (see the kernels).
 // The random draws stay where the reference makes them (torch.rand on the device, same order): tta_depth_completion_b200/transforms.py.
 #pragma once
 #include "common.cuh"
@@ -113,6 +114,90 @@ __global__ void __launch_bounds__(256) flip_kernel(const float* __restrict__ in,
         const int c = i / plane, r = i - c * plane, y = r / W, x = r - y * W;
         const int sy = fv ? H - 1 - y : y, sx = fh ? W - 1 - x : x;
         out[off + i] = in[off + (size_t)c * plane + sy * W + sx];
+    }
+}
+
+// Per-sample rotation about the image centre (src/transforms.py:406-423, 1036-1070 -> torchvision functional.rotate, expand=False,
+// fill=None -> affine grid + grid_sample(padding_mode='zeros', align_corners=False)).  theta: [N][6] = the 3 x 2 matrix
+// `theta^T / (0.5 w, 0.5 h)` torchvision multiplies the base grid with (row-major: x-column then y-column), prepared on the host exactly
+// as torchvision does (double-precision matrix -> fp32 -> fp32 division).  Base grid = pixel centres relative to the image centre.
+// mode 0: nearest (round half to even, as grid_sample), 1: bilinear.  Samples whose flag is clear are copied.
+__global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+                                                     const unsigned char* __restrict__ do_rot, const float* __restrict__ theta, int mode) {
+    PDL_SYNC();
+    const int n = blockIdx.y;
+    const int plane = H * W;
+    const float* ib = in + (size_t)n * C * plane;
+    float* ob = out + (size_t)n * C * plane;
+    if (!do_rot[n]) {
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < C * plane; i += gridDim.x * 256) ob[i] = ib[i];
+        return;
+    }
+    const float t0 = theta[n * 6 + 0], t1 = theta[n * 6 + 1], t2 = theta[n * 6 + 2], t3 = theta[n * 6 + 3], t4 = theta[n * 6 + 4], t5 = theta[n * 6 + 5];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < plane; i += gridDim.x * 256) {
+        const int y = i / W, x = i - y * W;
+        const float xb = (float)x - 0.5f * (float)W + 0.5f, yb = (float)y - 0.5f * (float)H + 0.5f;
+        const float gx = __fadd_rn(__fadd_rn(__fmul_rn(xb, t0), __fmul_rn(yb, t1)), t2);
+        const float gy = __fadd_rn(__fadd_rn(__fmul_rn(xb, t3), __fmul_rn(yb, t4)), t5);
+        const float ix = ((gx + 1.f) * (float)W - 1.f) / 2.f, iy = ((gy + 1.f) * (float)H - 1.f) / 2.f;
+        if (mode == 0) {
+            const float fx = nearbyintf(ix), fy = nearbyintf(iy);
+            const bool inb = fx >= 0.f && fx <= (float)(W - 1) && fy >= 0.f && fy <= (float)(H - 1);
+            const int src = inb ? (int)fy * W + (int)fx : 0;
+            for (int c = 0; c < C; ++c) ob[c * plane + i] = inb ? ib[c * plane + src] : 0.f;
+        } else {
+            const float x0 = floorf(ix), y0 = floorf(iy);
+            const float wx1 = ix - x0, wx0 = (x0 + 1.f) - ix, wy1 = iy - y0, wy0 = (y0 + 1.f) - iy;
+            const int xi = (int)x0, yi = (int)y0;
+            const bool vx0 = xi >= 0 && xi < W, vx1 = xi + 1 >= 0 && xi + 1 < W, vy0 = yi >= 0 && yi < H, vy1 = yi + 1 >= 0 && yi + 1 < H;
+            for (int c = 0; c < C; ++c) {
+                const float* pc = ib + c * plane;
+                float v = 0.f;
+                if (vy0 && vx0) v += pc[yi * W + xi] * (wx0 * wy0);
+                if (vy0 && vx1) v += pc[yi * W + xi + 1] * (wx1 * wy0);
+                if (vy1 && vx0) v += pc[(yi + 1) * W + xi] * (wx0 * wy1);
+                if (vy1 && vx1) v += pc[(yi + 1) * W + xi + 1] * (wx1 * wy1);
+                ob[c * plane + i] = v;
+            }
+        }
+    }
+}
+
+// Per-sample enlargement to (rh, rw) >= (H, W) followed by the crop [sy, sy + H) x [sx, sx + W) (src/transforms.py:425-502, 1222-1283 ->
+// torchvision functional.resize -> F.interpolate, align_corners=False): only the H x W pixels that survive the crop are computed.
+// mode 0: nearest (source index floor(dst * in / out)), 1: bilinear (source coordinate max(in / out * (dst + 0.5) - 0.5, 0)).
+__global__ void __launch_bounds__(256) resize_crop_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+                                                          const unsigned char* __restrict__ do_rs, const int* __restrict__ rh,
+                                                          const int* __restrict__ rw, const int* __restrict__ sy, const int* __restrict__ sx,
+                                                          int mode) {
+    PDL_SYNC();
+    const int n = blockIdx.y;
+    const int plane = H * W;
+    const float* ib = in + (size_t)n * C * plane;
+    float* ob = out + (size_t)n * C * plane;
+    if (!do_rs[n]) {
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < C * plane; i += gridDim.x * 256) ob[i] = ib[i];
+        return;
+    }
+    const float sh = (float)H / (float)rh[n], sw = (float)W / (float)rw[n];
+    const int oy = sy[n], ox = sx[n];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < plane; i += gridDim.x * 256) {
+        const int y = i / W, x = i - y * W;
+        const int Y = y + oy, X = x + ox;                  // position in the enlarged image
+        if (mode == 0) {
+            const int ys = min((int)floorf((float)Y * sh), H - 1), xs = min((int)floorf((float)X * sw), W - 1);
+            for (int c = 0; c < C; ++c) ob[c * plane + i] = ib[c * plane + ys * W + xs];
+        } else {
+            const float yr = fmaxf(sh * ((float)Y + 0.5f) - 0.5f, 0.f), xr = fmaxf(sw * ((float)X + 0.5f) - 0.5f, 0.f);
+            const int y1 = (int)yr, x1 = (int)xr;
+            const int yp = y1 < H - 1 ? 1 : 0, xp = x1 < W - 1 ? 1 : 0;
+            const float ly1 = yr - (float)y1, ly0 = 1.f - ly1, lx1 = xr - (float)x1, lx0 = 1.f - lx1;
+            for (int c = 0; c < C; ++c) {
+                const float* pc = ib + c * plane;
+                ob[c * plane + i] = ly0 * (lx0 * pc[y1 * W + x1] + lx1 * pc[y1 * W + x1 + xp]) +
+                                    ly1 * (lx0 * pc[(y1 + yp) * W + x1] + lx1 * pc[(y1 + yp) * W + x1 + xp]);
+            }
+        }
     }
 }
 

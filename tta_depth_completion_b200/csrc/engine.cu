@@ -1816,6 +1816,27 @@ int ptta_augment_flip(const float* in, float* out, int n, int c, int h, int w, c
     return check_launch("flip");
 }
 
+int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate, const float* theta_n_x_6,
+                        int mode, ptta_stream_t stream) {
+    PTTA_CHECK(in && out && in != out && do_rotate && theta_n_x_6 && n >= 1 && c >= 1 && h >= 1 && w >= 1, "augment_rotate: bad argument");
+    PTTA_CHECK(mode == 0 || mode == 1, "augment_rotate: interpolation mode %d (0 nearest, 1 bilinear)", mode);
+    PTTA_CHECK((long long)c * h * w < (1ll << 31) && n <= 65535, "augment_rotate: map too large");
+    const int bx = std::min(cdiv((long long)h * w, 256 * 2), 2368);
+    launch_k(rotate_kernel, dim3(bx, n), 256, 0, (cudaStream_t)stream, in, out, c, h, w, do_rotate, theta_n_x_6, mode);
+    return check_launch("rotate");
+}
+
+int ptta_augment_resize_crop(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_resize, const int* resize_h,
+                             const int* resize_w, const int* start_y, const int* start_x, int mode, ptta_stream_t stream) {
+    PTTA_CHECK(in && out && in != out && do_resize && resize_h && resize_w && start_y && start_x && n >= 1 && c >= 1 && h >= 1 && w >= 1,
+               "augment_resize_crop: bad argument");
+    PTTA_CHECK(mode == 0 || mode == 1, "augment_resize_crop: interpolation mode %d (0 nearest, 1 bilinear)", mode);
+    PTTA_CHECK((long long)c * h * w < (1ll << 31) && n <= 65535, "augment_resize_crop: map too large");
+    const int bx = std::min(cdiv((long long)h * w, 256 * 2), 2368);
+    launch_k(resize_crop_kernel, dim3(bx, n), 256, 0, (cudaStream_t)stream, in, out, c, h, w, do_resize, resize_h, resize_w, start_y, start_x, mode);
+    return check_launch("resize_crop");
+}
+
 int ptta_adam_flat(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps, double wd, int step,
                    ptta_stream_t stream) {
     PTTA_CHECK(step >= 1, "adam: step must be >= 1");

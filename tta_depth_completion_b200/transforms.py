@@ -8,10 +8,15 @@ equal generator state both implementations augment every sample identically.  Wh
 reduction + one elementwise kernel for the whole photometric chain (csrc/augment.cuh) instead of ~15 tensor ops and a host sync per
 sample and transform (`float(factors[b])`).
 
-Options that resample the image (rotate, resize-and-crop / -pad, crop-and-pad, random crop to shape), gamma / hue jitter, noise and
-point removal are not implemented: configuring one raises NotImplementedError at construction (no silent fallback)."""
+Also native: the per-sample rotation (torchvision `functional.rotate` = affine grid + grid_sample; the angle comes from
+`np.random.rand`, as in the reference) and resize-and-crop (`functional.resize` + crop) -- with these, every augmentation the shipped
+adaptation scripts enable (bash/adapt/adapt_msgchn_*.sh: brightness, contrast, saturation, horizontal flip, rotate 5, resize-and-crop
+1.0 .. 1.5) runs in the library.  Crop-and-pad, resize-and-pad, random crop to shape, gamma / hue jitter, noise and point removal are
+not implemented: configuring one raises NotImplementedError at construction (no silent fallback)."""
 import ctypes
+import math
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -41,9 +46,9 @@ class Transforms(object):
             'random_gamma': -1 not in random_gamma, 'random_hue': -1 not in random_hue,
             'random_noise': random_noise_type != 'none' and random_noise_spread > -1,
             'random_remove_patch_percent_range': -1 not in random_remove_patch_percent_range,
-            'random_crop_to_shape': -1 not in random_crop_to_shape, 'random_rotate_max': random_rotate_max > 0,
-            'random_crop_and_pad': -1 not in random_crop_and_pad, 'random_resize_and_crop': -1 not in random_resize_and_crop,
+            'random_crop_to_shape': -1 not in random_crop_to_shape, 'random_crop_and_pad': -1 not in random_crop_and_pad,
             'random_resize_and_pad': -1 not in random_resize_and_pad,
+            'resize_scaling_depth': bool(resize_scaling_depth) and -1 not in random_resize_and_crop,
         }
         bad = [k for k, v in unsupported.items() if v]
         if bad:
@@ -52,6 +57,13 @@ class Transforms(object):
         self.do_image_normalization = normalized_image_range is not None
         self.do_random_horizontal_flip = 'horizontal' in random_flip_type
         self.do_random_vertical_flip = 'vertical' in random_flip_type
+        self.do_random_rotate = random_rotate_max > 0
+        self.random_rotate_max = random_rotate_max
+        self.do_random_resize_and_crop = -1 not in random_resize_and_crop
+        self.random_resize_and_crop_min, self.random_resize_and_crop_max = random_resize_and_crop[0], random_resize_and_crop[1]
+        if self.do_random_resize_and_crop:
+            assert self.random_resize_and_crop_min < self.random_resize_and_crop_max
+            assert self.random_resize_and_crop_min >= 1.0
         self._norm = self._normalisation(normalized_image_range)
         self.rand_device = None        # where the draws are made; None = the images' device, as in the reference
 
@@ -106,12 +118,100 @@ class Transforms(object):
             do_v = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8).contiguous()
         if do_h is not None or do_v is not None:
             images_arr = [self._flip(im, do_h, do_v) for im in images_arr]
+        n_height, n_width = images_arr[0].shape[-2:]
+        intrinsics_arr = list(intrinsics_arr)
+        modes = self._modes(interpolation_modes, len(images_arr))
+        if self.do_random_rotate:                                                                                # :406-423
+            do_rotate = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8).contiguous()
+            values = np.random.rand(n_batch)                                # the reference draws the angles from numpy's global generator
+            angles = (2 * self.random_rotate_max) * values + (-self.random_rotate_max)
+            theta = torch.from_numpy(self._rotation_grid_matrix(angles, n_height, n_width)).to(device)
+            images_arr = [self._resample('rotate', im, m, do_rotate, theta) for im, m in zip(images_arr, modes)]
+        if self.do_random_resize_and_crop:                                                                       # :425-502
+            do_rs = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8).contiguous()
+            rdev = self.rand_device if self.rand_device is not None else device
+            r_height = torch.randint(low=int(self.random_resize_and_crop_min * n_height), high=int(self.random_resize_and_crop_max * n_height),
+                                     size=(n_batch,), device=rdev)
+            r_width = torch.randint(low=int(self.random_resize_and_crop_min * n_width), high=int(self.random_resize_and_crop_max * n_width),
+                                    size=(n_batch,), device=rdev)
+            intrinsics_arr = self._adjust_intrinsics(intrinsics_arr, x_scales=(r_width / n_width), y_scales=(r_height / n_height))
+            rh, rw = r_height.tolist(), r_width.tolist()                   # one host read (the reference makes 2 N of them, :463-477)
+            start_y, start_x = [], []
+            for b in range(n_batch):
+                start_y.append(torch.randint(low=0, high=rh[b] - n_height + 1, size=(1,), device=rdev))
+                start_x.append(torch.randint(low=0, high=rw[b] - n_width + 1, size=(1,), device=rdev))
+            start_y, start_x = torch.cat(start_y, dim=0), torch.cat(start_x, dim=0)
+            args = [t.to(device=device, dtype=torch.int32).contiguous() for t in (r_height, r_width, start_y, start_x)]
+            images_arr = [self._resample('resize_crop', im, m, do_rs, *args) for im, m in zip(images_arr, modes)]
+            intrinsics_arr = self._adjust_intrinsics(intrinsics_arr, x_offsets=(r_width - n_width), y_offsets=(r_height - n_height))
         outputs = []
         if len(images_arr) > 0:
             outputs.append(images_arr)
         if len(intrinsics_arr) > 0:
             outputs.append(list(intrinsics_arr))
         return outputs[0] if len(outputs) == 1 else outputs
+
+    # -- geometric helpers -----------------------------------------------------------------------------------
+    @staticmethod
+    def _modes(interpolation_modes, n):
+        """per-tensor interpolation (0 nearest, 1 bilinear) from the reference's names or PIL enums (NEAREST = 0, BILINEAR = 2), the last
+        entry repeated for the remaining tensors (src/transforms.py:1056-1059)"""
+        out = []
+        for m in list(interpolation_modes) + [interpolation_modes[-1]] * max(0, n - len(interpolation_modes)):
+            if m in (0, 'nearest'):
+                out.append(0)
+            elif m in (2, 'bilinear'):
+                out.append(1)
+            else:
+                raise NotImplementedError('interpolation mode %r (nearest and bilinear are native)' % (m,))
+        return out[:n]
+
+    @staticmethod
+    def _rotation_grid_matrix(angles, h, w):
+        """fp32 [N, 6]: what torchvision multiplies its base grid with for `rotate(img, angle)` -- the inverse rotation about the centre
+        (double precision, `_get_inverse_affine_matrix` with angle -> -angle, no shear / scale / translation), cast to fp32, transposed and
+        divided by (0.5 w, 0.5 h) in fp32 (`_gen_affine_grid`)"""
+        out = np.zeros((len(angles), 6), dtype=np.float32)
+        half = np.array([0.5 * w, 0.5 * h], dtype=np.float32)
+        for b, angle in enumerate(angles):
+            rot = math.radians(-float(angle))
+            a, bb, c, d = math.cos(rot), -math.sin(rot), math.sin(rot), math.cos(rot)
+            theta = np.array([[d, -bb, 0.0], [-c, a, 0.0]], dtype=np.float32)
+            resc = theta.T / half                                              # [3, 2]
+            out[b, :3], out[b, 3:] = resc[:, 0], resc[:, 1]
+        return out
+
+    @staticmethod
+    def _resample(kind, images, mode, flags, *args):
+        images = images.float().contiguous()
+        n, c, h, w = images.shape
+        out = torch.empty_like(images)
+        L = _lib.lib()
+        if kind == 'rotate':
+            check(L.ptta_augment_rotate(ptr(images), ptr(out), n, c, h, w, ptr(flags), ptr(args[0].contiguous()), mode, _stream()), 'augment_rotate')
+        else:
+            check(L.ptta_augment_resize_crop(ptr(images), ptr(out), n, c, h, w, ptr(flags), ptr(args[0]), ptr(args[1]), ptr(args[2]), ptr(args[3]),
+                                             mode, _stream()), 'augment_resize_crop')
+        return out
+
+    @staticmethod
+    def _adjust_intrinsics(intrinsics_arr, x_scales=None, y_scales=None, x_offsets=None, y_offsets=None):
+        """src/transforms.py:1330-1378: focal lengths and optical centres scaled, offsets subtracted -- for EVERY sample of the batch, also the
+        ones the transform skipped (the reference's behaviour)"""
+        out = []
+        for K in intrinsics_arr:
+            K = K.clone()
+            dev = K.device
+            xs = torch.ones(len(K), device=dev) if x_scales is None else x_scales.to(dev)
+            ys = torch.ones(len(K), device=dev) if y_scales is None else y_scales.to(dev)
+            xo = torch.zeros(len(K), device=dev) if x_offsets is None else x_offsets.to(dev)
+            yo = torch.zeros(len(K), device=dev) if y_offsets is None else y_offsets.to(dev)
+            K[:, 0, 0] = K[:, 0, 0] * xs
+            K[:, 0, 2] = K[:, 0, 2] * xs - xo
+            K[:, 1, 1] = K[:, 1, 1] * ys
+            K[:, 1, 2] = K[:, 1, 2] * ys - yo
+            out.append(K)
+        return out
 
     def _photometric(self, images, flags, factors):
         if images.shape[1] != 3:
