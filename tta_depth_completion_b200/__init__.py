@@ -6,6 +6,7 @@ from .external_model_adapt import ExternalModel_Adapt, MsgChnModel_Adapt, Outlie
 from .engine import MsgChnEngine  # noqa: F401
 from .nlspn_model_adapt import NLSPNModel_Adapt  # noqa: F401
 from .nlspn_engine import NlspnEngine  # noqa: F401
+from .transforms import Transforms  # noqa: F401
 from . import ops  # noqa: F401
 
-__all__ = ['ExternalModel_Adapt', 'MsgChnModel_Adapt', 'NLSPNModel_Adapt', 'NlspnEngine', 'OutlierRemoval', 'MsgChnEngine', 'ops', 'ADAPT_LOSS_TYPE']
+__all__ = ['ExternalModel_Adapt', 'MsgChnModel_Adapt', 'NLSPNModel_Adapt', 'NlspnEngine', 'OutlierRemoval', 'Transforms', 'MsgChnEngine', 'ops', 'ADAPT_LOSS_TYPE']

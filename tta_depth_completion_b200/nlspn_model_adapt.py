@@ -145,6 +145,7 @@ class NLSPNModel_Adapt(object):
         self.legacy = bool(offset)               # src/nlspn_model_adapt.py:62: args.legacy = offset
         self.prop_time = 18
         self.training = True
+        self.warn_on_holes = True               # eval forward: one device->host read to report holes the reference would inpaint (False: skip the check)
         self.prepare_mode = None
         self.adapt = False
         self._sd = None
@@ -201,9 +202,18 @@ class NLSPNModel_Adapt(object):
         eng.repack_adapted()
         with torch.no_grad():
             out = eng.forward(image, sparse_depth, training=False)
-        # the reference fills holes with skimage's inpaint_biharmonic on the CPU here (src/nlspn_model_adapt.py:124-127): eval-time
-        # post-processing outside the adaptation step, not reproduced
-        return out.clone()
+        # the reference fills holes (pixels that are exactly 0) with skimage's inpaint_biharmonic on the CPU here
+        # (src/nlspn_model_adapt.py:124-127 -> src/data_utils.py:327-354) and returns the map untouched when there is none.  The solver is
+        # not reproduced: a prediction without holes is identical to the reference's, one WITH holes is reported instead of passing silently
+        out = out.clone()
+        if self.warn_on_holes and 'head' not in loss_type:
+            holes = int((out == 0).sum())
+            if holes:
+                import warnings
+                warnings.warn('NLSPN eval forward: %d of %d predicted depths are exactly 0; the reference would fill them with '
+                              'skimage.restoration.inpaint_biharmonic (src/data_utils.py:327-354), this path returns them as they are'
+                              % (holes, out.numel()), RuntimeWarning)
+        return out
 
     def parameters(self):
         self._materialise()
