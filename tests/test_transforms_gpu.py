@@ -134,6 +134,32 @@ def test_native_photometric_at_frame_size(n, h, w, rng):
     print('fraction of values off by one grey level (contrast mean): %.2e' % worst)
 
 
+@pytest.mark.parametrize('n,h,w', [(3, 15, 21), (2, 16, 24), (5, 9, 12)])
+def test_scalar_and_vector_paths(n, h, w):
+    """odd sizes take the 4-byte path of the photometric / flip kernels, multiples of four the 16-byte path: both against the oracle"""
+    from tta_depth_completion_b200.transforms import Transforms
+    torch.manual_seed(h * w)
+    image = torch.rand(n, 3, h, w) * 255
+    depth = torch.rand(n, 1, h, w)
+    cfg = {'brightness': [0.5, 1.5], 'contrast': [0.5, 1.5], 'saturation': [0.5, 1.5]}
+    torch.manual_seed(5)
+    want = TO.apply([image], cfg, TO.draws(n, cfg, 1.0), [0, 1])[0]
+    tr = Transforms(normalized_image_range=[0, 1], random_brightness=[0.5, 1.5], random_contrast=[0.5, 1.5], random_saturation=[0.5, 1.5])
+    tr.rand_device = 'cpu'
+    torch.manual_seed(5)
+    got = tr.transform(images_arr=[image.to(DEV)], random_transform_probability=1.0)[0]
+    compare(got, want, True, [0, 1], 'photometric %dx%d' % (h, w))
+    cfg = {'flip': ('horizontal', 'vertical')}
+    torch.manual_seed(6)
+    want = TO.apply([image, depth], cfg, TO.draws(n, cfg, 1.0), None)
+    tr = Transforms(random_flip_type=['horizontal', 'vertical'])
+    tr.rand_device = 'cpu'
+    torch.manual_seed(6)
+    got = tr.transform(images_arr=[image.to(DEV), depth.to(DEV)], random_transform_probability=1.0)
+    for g, w_ in zip(got, want):
+        assert torch.equal(g.cpu(), w_)
+
+
 def test_native_flips_at_frame_size():
     from tta_depth_completion_b200.transforms import Transforms
     from tta_depth_completion_b200.synthetic import synthetic_frame

@@ -31,26 +31,37 @@ __device__ __forceinline__ float photo_trunc(float v) { return truncf(fminf(fmax
 __device__ __forceinline__ float photo_gray(float r, float g, float b) {
     return truncf(__fadd_rn(__fadd_rn(__fmul_rn(0.2989f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b)));
 }
-// ratio u + (1 - ratio) other, the two products and the sum rounded separately (torchvision `_blend`); 1 - ratio is formed in double
-__device__ __forceinline__ float photo_blend(float u, float other, float ratio) {
-    const float omr = (float)(1.0 - (double)ratio);
+// ratio u + (1 - ratio) other, the two products and the sum rounded separately (torchvision `_blend`); omr = 1 - ratio, formed in double
+__device__ __forceinline__ float photo_one_minus(float ratio) { return (float)(1.0 - (double)ratio); }      // per sample, outside the pixel loops
+__device__ __forceinline__ float photo_blend(float u, float other, float ratio, float omr) {
     return photo_trunc(__fadd_rn(__fmul_rn(ratio, u), __fmul_rn(omr, other)));
 }
 __device__ __forceinline__ float photo_quant(float x) { return truncf(fminf(fmaxf(x, 0.f), 255.f)); }     // float -> uint8 cast of an in-range value
 
-// exact sum of the grey values of every sample whose contrast flag is set, taken AFTER its brightness step
+// exact sum of the grey values of every sample whose contrast flag is set, taken AFTER its brightness step.
+// VEC = 4: four consecutive pixels per thread through 16-byte loads of each colour plane (HW % 4 == 0, 16-byte aligned planes)
+template <int VEC>
 __global__ void __launch_bounds__(256) photo_gray_sum_kernel(const PhotoParams p) {
     PDL_SYNC();
     const int n = blockIdx.y;
     if (!p.do_c || !p.do_c[n]) return;
     const float* base = p.in + (size_t)n * 3 * p.HW;
     const bool bright = p.do_b && p.do_b[n];
-    const float fb = bright ? p.f_b[n] : 1.f;
+    const float fb = bright ? p.f_b[n] : 1.f, ob_ = photo_one_minus(fb);
     unsigned int local = 0;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < p.HW; i += gridDim.x * 256) {
-        float r = photo_quant(base[i]), g = photo_quant(base[p.HW + i]), b = photo_quant(base[2 * p.HW + i]);
-        if (bright) { r = photo_blend(r, 0.f, fb); g = photo_blend(g, 0.f, fb); b = photo_blend(b, 0.f, fb); }
-        local += (unsigned int)photo_gray(r, g, b);
+    for (int i = (blockIdx.x * 256 + threadIdx.x) * VEC; i < p.HW; i += gridDim.x * 256 * VEC) {
+        float c[3][VEC];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (VEC == 4) *reinterpret_cast<float4*>(c[k]) = __ldg(reinterpret_cast<const float4*>(base + (size_t)k * p.HW + i));
+            else c[k][0] = base[(size_t)k * p.HW + i];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float r = photo_quant(c[0][v]), g = photo_quant(c[1][v]), b = photo_quant(c[2][v]);
+            if (bright) { r = photo_blend(r, 0.f, fb, ob_); g = photo_blend(g, 0.f, fb, ob_); b = photo_blend(b, 0.f, fb, ob_); }
+            local += (unsigned int)photo_gray(r, g, b);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
@@ -64,6 +75,7 @@ __global__ void __launch_bounds__(256) photo_gray_sum_kernel(const PhotoParams p
     }
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(256) photo_apply_kernel(const PhotoParams p) {
     PDL_SYNC();
     const int n = blockIdx.y;
@@ -72,37 +84,70 @@ __global__ void __launch_bounds__(256) photo_apply_kernel(const PhotoParams p) {
     const bool bright = p.do_b && p.do_b[n], contrast = p.do_c && p.do_c[n], sat = p.do_s && p.do_s[n];
     const float fb = bright ? p.f_b[n] : 1.f, fc = contrast ? p.f_c[n] : 1.f, fs = sat ? p.f_s[n] : 1.f;
     const float mean = contrast ? (float)((double)p.gray_sum[n] / (double)p.HW) : 0.f;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < p.HW; i += gridDim.x * 256) {
-        float c[3] = {base[i], base[p.HW + i], base[2 * p.HW + i]};
-        if (p.quantize) {
+    const float omb = photo_one_minus(fb), omc = photo_one_minus(fc), oms = photo_one_minus(fs);
+    // after the uint8 truncation a channel holds one of 256 values: the normalisation (IEEE divisions, as torch's `/ 255.0` and
+    // `normalize`) is tabulated once per block instead of being evaluated 12 times per thread and iteration
+    __shared__ float lut[3][256];
+    const bool use_lut = p.quantize && p.norm_mode != 0;
+    if (use_lut) {
+        const float v = (float)threadIdx.x;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) c[k] = photo_quant(c[k]);
-            if (bright) {
+        for (int k = 0; k < 3; ++k) {
+            float x = __fdiv_rn(v, 255.f);
+            if (p.norm_mode == 2) x = __fsub_rn(__fmul_rn(2.f, x), 1.f);
+            else if (p.norm_mode == 3) x = __fdiv_rn(__fsub_rn(x, p.mean[k]), p.std[k]);
+            lut[k][threadIdx.x] = x;
+        }
+        __syncthreads();
+    }
+    for (int i = (blockIdx.x * 256 + threadIdx.x) * VEC; i < p.HW; i += gridDim.x * 256 * VEC) {
+        float c[3][VEC];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) c[k] = photo_blend(c[k], 0.f, fb);
+        for (int k = 0; k < 3; ++k) {
+            if (VEC == 4) *reinterpret_cast<float4*>(c[k]) = __ldg(reinterpret_cast<const float4*>(base + (size_t)k * p.HW + i));
+            else c[k][0] = base[(size_t)k * p.HW + i];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            if (p.quantize) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) c[k][v] = photo_quant(c[k][v]);
+                if (bright) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) c[k][v] = photo_blend(c[k][v], 0.f, fb, omb);
+                }
+                if (contrast) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) c[k][v] = photo_blend(c[k][v], mean, fc, omc);
+                }
+                if (sat) {
+                    const float gr = photo_gray(c[0][v], c[1][v], c[2][v]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) c[k][v] = photo_blend(c[k][v], gr, fs, oms);
+                }
             }
-            if (contrast) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) c[k] = photo_blend(c[k], mean, fc);
-            }
-            if (sat) {
-                const float gr = photo_gray(c[0], c[1], c[2]);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) c[k] = photo_blend(c[k], gr, fs);
+            for (int k = 0; k < 3; ++k) {
+                float x = c[k][v];
+                if (use_lut) x = lut[k][(int)x];
+                else if (p.norm_mode == 1) x = __fdiv_rn(x, 255.f);
+                else if (p.norm_mode == 2) x = __fsub_rn(__fmul_rn(2.f, __fdiv_rn(x, 255.f)), 1.f);
+                else if (p.norm_mode == 3) x = __fdiv_rn(__fsub_rn(__fdiv_rn(x, 255.f), p.mean[k]), p.std[k]);
+                c[k][v] = x;
             }
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            float v = c[k];
-            if (p.norm_mode == 1) v = __fdiv_rn(v, 255.f);
-            else if (p.norm_mode == 2) v = __fsub_rn(__fmul_rn(2.f, __fdiv_rn(v, 255.f)), 1.f);
-            else if (p.norm_mode == 3) v = __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.f), p.mean[k]), p.std[k]);
-            ob[k * p.HW + i] = v;
+            if (VEC == 4) *reinterpret_cast<float4*>(ob + (size_t)k * p.HW + i) = *reinterpret_cast<const float4*>(c[k]);
+            else ob[(size_t)k * p.HW + i] = c[k][0];
         }
     }
 }
 
 // out[n][c][y][x] = in[n][c][vflip ? H-1-y : y][hflip ? W-1-x : x]
+// VEC = 4: four consecutive output pixels per thread (W % 4 == 0, 16-byte aligned rows): one 16-byte load (of the mirrored quad when
+// hflip) and one 16-byte store
+template <int VEC>
 __global__ void __launch_bounds__(256) flip_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
                                                    const unsigned char* __restrict__ do_h, const unsigned char* __restrict__ do_v) {
     PDL_SYNC();
@@ -110,10 +155,17 @@ __global__ void __launch_bounds__(256) flip_kernel(const float* __restrict__ in,
     const bool fh = do_h && do_h[n], fv = do_v && do_v[n];
     const int plane = H * W;
     const size_t off = (size_t)n * C * plane;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < C * plane; i += gridDim.x * 256) {
+    for (int i = (blockIdx.x * 256 + threadIdx.x) * VEC; i < C * plane; i += gridDim.x * 256 * VEC) {
         const int c = i / plane, r = i - c * plane, y = r / W, x = r - y * W;
-        const int sy = fv ? H - 1 - y : y, sx = fh ? W - 1 - x : x;
-        out[off + i] = in[off + (size_t)c * plane + sy * W + sx];
+        const int sy = fv ? H - 1 - y : y;
+        const float* row = in + off + (size_t)c * plane + (size_t)sy * W;
+        if (VEC == 4) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(row + (fh ? W - 4 - x : x)));
+            if (fh) v = make_float4(v.w, v.z, v.y, v.x);
+            *reinterpret_cast<float4*>(out + off + i) = v;
+        } else {
+            out[off + i] = row[fh ? W - 1 - x : x];
+        }
     }
 }
 

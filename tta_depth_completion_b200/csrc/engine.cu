@@ -1797,13 +1797,18 @@ int ptta_augment_photometric(const float* image, float* out, int n, int h, int w
     p.f_b = f_brightness; p.f_c = f_contrast; p.f_s = f_saturation; p.gray_sum = (unsigned long long*)workspace;
     p.N = n; p.HW = h * w; p.quantize = quantize; p.norm_mode = norm_mode;
     for (int k = 0; k < 3; ++k) { p.mean[k] = mean3 ? mean3[k] : 0.f; p.std[k] = std3 ? std3[k] : 1.f; }
-    const int bx = std::min(cdiv(p.HW, 256 * 4), 1184);
+    // 16-byte accesses when every colour plane starts on a 16-byte boundary; ~2 waves of blocks over the whole batch
+    const bool vec = (p.HW % 4 == 0) && (((uintptr_t)image | (uintptr_t)out) & 15) == 0;
+    const int per_block = 256 * (vec ? 4 : 1) * 2;
+    const int bx = std::max(1, std::min(cdiv(p.HW, per_block), cdiv(2368, n)));
     if (do_contrast) {
         PTTA_CUDA(cudaMemsetAsync(workspace, 0, sizeof(unsigned long long) * n, st));
-        launch_k(photo_gray_sum_kernel, dim3(bx, n), 256, 0, st, p);
+        if (vec) launch_k(photo_gray_sum_kernel<4>, dim3(bx, n), 256, 0, st, p);
+        else launch_k(photo_gray_sum_kernel<1>, dim3(bx, n), 256, 0, st, p);
         PTTA_TRY(check_launch("photo_gray_sum"));
     }
-    launch_k(photo_apply_kernel, dim3(bx, n), 256, 0, st, p);
+    if (vec) launch_k(photo_apply_kernel<4>, dim3(bx, n), 256, 0, st, p);
+    else launch_k(photo_apply_kernel<1>, dim3(bx, n), 256, 0, st, p);
     return check_launch("photo_apply");
 }
 
@@ -1811,8 +1816,10 @@ int ptta_augment_flip(const float* in, float* out, int n, int c, int h, int w, c
                       ptta_stream_t stream) {
     PTTA_CHECK(in && out && in != out && n >= 1 && c >= 1 && h >= 1 && w >= 1, "augment_flip: bad argument (in-place is not supported)");
     PTTA_CHECK((long long)c * h * w < (1ll << 31) && n <= 65535, "augment_flip: map too large");
-    const int bx = std::min(cdiv((long long)c * h * w, 256 * 4), 1184);
-    launch_k(flip_kernel, dim3(bx, n), 256, 0, (cudaStream_t)stream, in, out, c, h, w, do_hflip, do_vflip);
+    const bool vec = (w % 4 == 0) && (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    const int bx = std::max(1, std::min(cdiv((long long)c * h * w, 256 * (vec ? 4 : 1) * 2), cdiv(2368, n)));
+    if (vec) launch_k(flip_kernel<4>, dim3(bx, n), 256, 0, (cudaStream_t)stream, in, out, c, h, w, do_hflip, do_vflip);
+    else launch_k(flip_kernel<1>, dim3(bx, n), 256, 0, (cudaStream_t)stream, in, out, c, h, w, do_hflip, do_vflip);
     return check_launch("flip");
 }
 
