@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the ProxyTTA per-frame adaptation step (BASELINE.json: adapted frames/s, fwd+bwd+update, 352x1216).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload kitti|void] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload kitti|void|nlspn|prepare_init|prepare_head] [--batch B]
 
 One "step" = src/tta_main.py:583-633 of the reference for one batch: outlier removal, forward (real + zero-image
 branch + proxy heads), the three losses, backward to the adapted meta layer, Adam.  Workload at N=1 = BASELINE.json
@@ -39,6 +39,10 @@ WORKLOADS = {
     # the NLSPN back-end on synthetic VOID-shape indoor frames (480x640, ~0.5 % density, depth cap 8 m)
     'nlspn_void': (480, 640, 'void', 'meta_selfsup_seq_1layer_ema', 3e-4, 8.0),
 }
+# the source-domain preparation stages on the KITTI-shape workload (src/init_main.py / src/head_main.py steps)
+PREPARE = {'prepare_init': 'init', 'prepare_head': 'head'}
+for _k in PREPARE:
+    WORKLOADS[_k] = (352, 1216, 'kitti', 'meta_selfsup_seq_2layers_ema', 1e-3, 80.0)
 NLSPN_GFLOP_STEP = 3445.9        # forward 2 227.0 + required dgrad 1 201.1 + wgrad 17.8 at 1x352x1216
 W_SD, W_SM, W_COS = 1.0, 1.0, 0.1
 RING = 8                      # distinct frames cycled through (device-resident for `value`, pinned host for `e2e`)
@@ -191,11 +195,64 @@ def nlspn_cpu_sample(args, steps, warmup):
                                  'workload, %.1f s/step, throughput scaled by 1/4' % (steps, torch.__version__, args.batch, hs, ws, dt / steps)}
 
 
+def prepare_state(workload):
+    """(state dict the stage trains from, names of the trained tensors): the seeded synthetic checkpoint; stage 1 starts from a freshly
+    drawn meta layer (prepare_parameters), stage 2 from freshly drawn heads -- here the checkpoint's own (equivalent for timing)"""
+    sd = make_checkpoint(workload)
+    if PREPARE[workload] == 'init':
+        names = [k for k in sd if 'meta' in k and k.endswith(('weight', 'bias'))]
+    else:
+        names = ['pred.0.weight', 'pred.0.bias', 'pred.1.weight', 'pred.1.bias', 'pred.3.weight', 'pred.3.bias']
+    return sd, names
+
+
+def prepare_frames(workload, batch, count, seq_seed):
+    from tta_depth_completion_b200 import synthetic
+    h, w, dataset = WORKLOADS[workload][:3]
+    return [tuple(t.contiguous() for t in synthetic.synthetic_frame(seq_seed, t, batch, h, w, dataset)) for t in range(count)]
+
+
+def prepare_cpu_steps(args, steps, warmup):
+    """oracle port of the stage's step (oracle/msgchn_oracle.py: init_step / head_step) on all host cores; returns seconds per step"""
+    from oracle import msgchn_oracle as O
+    h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd, names = prepare_state(args.workload)
+    state = O.AdamState(names, sd)
+    frames = prepare_frames(args.workload, args.batch, 2, 1)
+
+    def one(i):
+        image, sparse, dense = frames[i % 2]
+        if PREPARE[args.workload] == 'init':
+            O.init_step(sd, state, image, sparse, dense, lr=lr, max_input_depth=cap)
+        else:
+            O.head_step(sd, state, image, sparse, lr=lr, max_input_depth=cap)
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    return (time.perf_counter() - t0) / steps
+
+
 def run_reference(args):
     """CPU arm: the oracle port of the reference step on all host cores."""
     from oracle import msgchn_oracle as O
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
+        return
+    if args.workload in PREPARE:
+        steps, warm = min(args.steps, 5), min(args.warmup, 1)
+        dt = prepare_cpu_steps(args, steps, warm)
+        value = args.batch / dt
+        h, w = WORKLOADS[args.workload][:2]
+        cb = {'value': value, 'unit': 'frames/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+              'sample': '%d full-size %s steps (%dx3x%dx%d) of oracle/msgchn_oracle.py, torch %s CPU fp32, %.2f s/step' % (
+                  steps, PREPARE[args.workload], args.batch, h, w, torch.__version__, dt)}
+        print(json.dumps({'impl': 'reference', 'metric': 'trained_frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus,
+                          'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * dt, 'higher_is_better': True, 'scaling': 'weak',
+                          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args), 'cpu_baseline': cb,
+                          'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
         return
     if args.workload.startswith('nlspn'):
         steps = min(args.steps, 3)
@@ -237,6 +294,14 @@ def run_reference(args):
 
 def workload_config(args):
     h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
+    if args.workload in PREPARE:
+        what = {'init': 'stage-1 meta-layer initialisation (src/init_main.py:482-522: forward init_meta_seq_ema, masked L2 against the ground truth, '
+                        'backward to the meta layer, Adam)',
+                'head': 'stage-2 predictor-head training (src/head_main.py:437-480: frozen network on the frame and on the zero image, EMA copy of '
+                        'proj, cosine loss, backward to pred.*, Adam)'}[PREPARE[args.workload]]
+        return {'workload': 'MSG-CHN source-domain preparation, %s, synthetic %s-shape %dx3x%dx%d frames, prepare_mode %s, lr %g, one step per '
+                            'batch, %d-frame ring (per-step working set >> L2)' % (what, dataset.upper(), args.batch, h, w, mode, lr, RING),
+                'batch': args.batch, 'height': h, 'width': w}
     if args.workload.startswith('nlspn'):
         return {'workload': 'NLSPN ProxyTTA continual adaptation (ResNet34 encoder/decoder, 18-step non-local propagation), synthetic ' + dataset.upper() + '-shape '
                             '%dx3x%dx%d frames, prepare_mode %s, adapt_mode meta_bn after convert_syncbn (94 tensors), lr %g, w_sd/w_smooth/w_cos %g/%g/%g, '
@@ -544,9 +609,163 @@ def gpu_eager_baseline(args, dev, steps=10):
     return out
 
 
+def time_gemm_tn_kernel(dev, peaks, rows, iters=40):
+    """the Linear weight gradient dW = dY^T X (rows x 512 x 512) of the stage-2 step on tcgen05 (csrc/gemm_tn_tc.cuh), timed alone"""
+    import ctypes
+    from tta_depth_completion_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(0)
+    As = [torch.randn(rows, 512, generator=g).to(dev, torch.bfloat16) for _ in range(4)]
+    Bs = [torch.randn(rows, 512, generator=g).to(dev, torch.bfloat16) for _ in range(4)]
+    c = torch.empty(512, 512, device=dev)
+    ws = torch.empty(L.ptta_gemm_tn_workspace_bytes(rows, 512, 512), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(dev)
+    with torch.cuda.stream(stream):
+        st = ctypes.c_void_p(stream.cuda_stream)
+
+        def launch(i):
+            _lib.check(L.ptta_gemm_tn_bf16_tc(_lib.ptr(As[i % 4]), _lib.ptr(Bs[i % 4]), _lib.ptr(c), _lib.ptr(ws), rows, 512, 512, st), 'gemm_tn')
+        for i in range(3):
+            launch(i)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for i in range(iters):
+                launch(i)
+        graph.replay()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        graph.replay()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    gflop = 2.0 * rows * 512 * 512 / 1e9
+    tflops = gflop / ms
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'gemm_tn_kernel_traffic.json')) as f:
+            traffic = json.load(f).get('dram_bytes_per_launch')
+    except Exception:
+        pass
+    return {'kernel': 'gemm_tn_tc_kernel + gemm_tn_reduce_kernel: dW[512][512] = dY^T X over %d rows (bf16 operands MN-major, tcgen05 + TMEM, '
+                      'TMA-fed, fp32 split-K partial tiles)' % rows,
+            'bound': 'tensor', 'achieved': tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': tflops / peaks['bf16_tflops'],
+            'traffic': traffic, 'us_per_launch': 1e3 * ms, 'gflop_per_launch': gflop,
+            'algorithmic_bytes_per_launch': 2 * rows * 512 * 2 + 512 * 512 * 4,
+            'note': 'bounded by the L2 -> SM operand traffic (each operand is read by every tile of the other dimension: 164 MB for 54.8 MB of '
+                    'DRAM reads, profiles/r2_gemm_tn_ncu_details.txt), not by the tensor pipe',
+            'peak_source': peaks['source'] + ', burst figures (kernel timed alone, 40 launches replayed from a CUDA graph)'}
+
+
+def run_native_prepare(args):
+    """`--workload prepare_init | prepare_head`: the source-domain preparation steps in the same harness as the TTA
+    step -- device-resident graph replays for `value`, pinned host frames + H2D + a blocking loss read every step for `e2e`."""
+    from tta_depth_completion_b200 import ExternalModel_Adapt
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the preparation steps have no CPU fallback (use --impl reference for the CPU arm)')
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    stage = PREPARE[args.workload]
+    h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
+    peaks = load_peaks()
+    model = ExternalModel_Adapt('msg_chn', 0.0, 100.0, max_input_depth=cap, device=dev)
+    model._prepare_head(mode)
+    model.load_state_dict(make_checkpoint(args.workload))
+    torch.manual_seed(0)
+    if stage == 'head':
+        model.prepare_parameters('head_selfsup_ema')            # src/head_main.py:268 (draws fresh heads)
+    model.set_image_normalization((1 / 255.0,) * 3, (0.0,) * 3)
+    model.train()
+    frames = prepare_frames(args.workload, args.batch, RING, 1 + rank)
+    dev_frames = [tuple(t.to(dev) for t in f) for f in frames]
+    pinned = [tuple(t.pin_memory() for t in f) for f in frames]
+    stream = torch.cuda.Stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run_step(f, graph):
+        if stage == 'init':
+            model.init_step(f[0], f[1], f[2], lr, graph=graph)
+        else:
+            model.head_step(f[0], f[1], lr, graph=graph)
+    with torch.cuda.stream(stream):
+        run_step(dev_frames[0], False)
+        eng = model._last_engine
+        l0 = eng.launch_count()
+        run_step(dev_frames[0], False)
+        launches_per_step = eng.launch_count() - l0
+        for i in range(max(3, args.warmup)):
+            run_step(dev_frames[i % RING], args.graph)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            run_step(dev_frames[(args.warmup + i) % RING], args.graph)
+        e1.record(stream)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        sampler.stop_flag = True
+        losses = model.last_losses()
+        # end to end: pinned host frames -> H2D -> step -> D2H loss read (synchronising), every step
+        passes = []
+        for _ in range(E2E_PASSES):
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for i in range(args.steps):
+                f = tuple(t.to(dev, non_blocking=True) for t in pinned[i % RING])
+                run_step(f, args.graph)
+                model.last_losses()
+            f1.record(stream)
+            barrier()
+            passes.append(f0.elapsed_time(f1))
+        ms_e2e = sorted(passes)[len(passes) // 2]
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    frames_total = world * args.batch * args.steps
+    h2d = sum(t.numel() * 4 for t in (frames[0] if stage == 'init' else frames[0][:2]))
+    line = {'metric': 'trained_frames_per_sec', 'value': frames_total / (ms_total / 1e3), 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(args),
+            'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 20,
+                    'ms_per_step': ms_e2e / args.steps, 'passes_ms': passes,
+                    'input_staging': 'pinned host frames copied H2D on the compute stream every step, blocking loss read every step'},
+            'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step, 'cuda_graph': bool(args.graph),
+            'clocks': sampler.summary(), 'last_losses': losses}
+    if world == 1 and not args.no_extras:
+        line['roofline'] = time_gemm_tn_kernel(dev, peaks, args.batch * (h // 4) * (w // 4)) if stage == 'head' else time_dominant_kernel(dev, peaks)
+        dt = prepare_cpu_steps(args, 2, 1)
+        line['cpu_baseline'] = {'value': args.batch / dt, 'unit': 'frames/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+                                'sample': '2 full-size %s steps (%dx3x%dx%d) of oracle/msgchn_oracle.py (torch %s CPU fp32) after 1 warm-up, %.2f s/step' % (
+                                    stage, args.batch, h, w, torch.__version__, dt)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_native(args):
     if args.workload.startswith('nlspn'):
         return run_native_nlspn(args)
+    if args.workload in PREPARE:
+        return run_native_prepare(args)
     from tta_depth_completion_b200 import ExternalModel_Adapt
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

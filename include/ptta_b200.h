@@ -198,13 +198,14 @@ int ptta_convg_run(int kind, int role, const void* x0_bf16, const void* x1_bf16,
  * {start, count, out_c, out_py} per class, then {c_inner, dx, dy, py, src, wsel, tap, k0} per item; returns the ints written */
 int ptta_convg_plan_describe(int kind, int role, int n, int h, int w, int cin0, int cin1, int cout, int has_short, int* out,
                              int capacity);
-/* timing experiments only: 1 one MMA per K-item, 2 no epilogue work, 4 no epilogue fence / store, 8 / 16 no A / B loads (results are
- * then wrong); 32 (results stay right): streamed weight tiles multicast over clusters of two CTAs; 64: cycle stamps (read_ts) */
+/* mask 32: streamed weight tiles multicast over clusters of two CTAs (results unchanged; a tested option, off by default); mask 0: off.
+ * Every other bit fails in this library: the work-skipping timing switches (1, 2, 4, 8, 16: results wrong by construction) and the cycle
+ * stamps (64, read back through the two functions below) are compiled into the experiments build only (-DPTTA_EXPERIMENTS ->
+ * lib/libptta_b200_experiments.so, used by tools/convg_experiment.py / convg_trace.py, never by the package): the product kernel
+ * contains none of their branches. */
 int ptta_convg_debug_set(int mask);
-/* mask & 64: CTA 0 records clock64() stamps per tile ([tile][16 events]: issue thread 0-3, epilogue 4-7, producer 8-9); synchronises */
-int ptta_convg_debug_read_ts(long long* out_host, int n);
-/* mask & 64: %globaltimer (ns) at entry / exit of every CTA ([cta][2]) */
-int ptta_convg_debug_read_cta(unsigned long long* out_host, int n);
+int ptta_convg_debug_read_ts(long long* out_host, int n);                /* experiments build only */
+int ptta_convg_debug_read_cta(unsigned long long* out_host, int n);      /* experiments build only */
 /* thin heads id_dec0 / gd_dec0 / cf_dec0 (nlspnmodel_adapt.py:430-448, 883-895) as ONE 16-output-channel conv over the concat
  * (x0 | x1): fp32 planar outputs through per-channel plane pointers (host arrays of n_real entries), activation per channel
  * (0 none, 1 LeakyReLU(0.2), 2 sigmoid).  Weights packed by ptta_convg_pack(kind 0, role 0, ..., cout = 16). */
@@ -394,6 +395,12 @@ int ptta_msgchn_l2_loss(ptta_msgchn* e, const float* ground_truth, float max_pre
 int ptta_msgchn_l2_loss_backward(ptta_msgchn* e, float grad_scale, ptta_stream_t stream);
 int ptta_msgchn_init_step(ptta_msgchn* e, const float* image_raw, const float* img_scale, const float* img_shift, const float* sparse_depth,
                           const float* ground_truth, float max_input_depth, float max_predict_depth, ptta_stream_t stream);
+/* the same two steps captured once into a CUDA graph and replayed (inputs copied into engine-owned staging buffers inside the call, so a
+ * fresh tensor may be passed every step; needs a non-default stream) */
+int ptta_msgchn_init_step_graph(ptta_msgchn* e, const float* image_raw, const float* img_scale, const float* img_shift, const float* sparse_depth,
+                                const float* ground_truth, float max_input_depth, float max_predict_depth, ptta_stream_t stream);
+int ptta_msgchn_head_step_graph(ptta_msgchn* e, const float* image_raw, const float* img_scale, const float* img_shift,
+                                const float* sparse_depth, float max_input_depth, ptta_stream_t stream);
 int ptta_msgchn_cos_loss(ptta_msgchn* e, ptta_stream_t stream);
 int ptta_msgchn_ema_update_head(ptta_msgchn* e, double tau, ptta_stream_t stream);
 int ptta_msgchn_cos_loss_backward(ptta_msgchn* e, float grad_scale, ptta_stream_t stream);      /* -> "g_emb" (bf16 [R,512]) */

@@ -230,3 +230,38 @@ def test_head_training_converges():
             losses.append(model.last_losses()['loss'])
     report('head training, 60 steps: loss_cos ' + ' '.join('%.3f' % l for l in losses))
     assert losses[0] > 1.5 and losses[-1] < 0.5 * losses[0], losses
+
+
+@pytest.mark.parametrize('stage', ['init', 'head'])
+def test_graph_replay_equals_eager(stage):
+    """the captured step (ptta_msgchn_init_step_graph / _head_step_graph: staged inputs, side streams inside the capture) against the eager
+    one: losses and every trained tensor bit for bit over 4 steps with a fresh input tensor each step"""
+    case = dict(stage=stage, prepare_mode='meta_selfsup_seq_2layers_ema', init_mode='meta_seq_2layers', ckpt='kitti_2layers_a', dataset='kitti',
+                n=2, h=48, w=80, lr=1e-3, max_input_depth=80.0, seq_seed=61, seed=5)
+    sd0, fresh = prep_initial_state(case)
+    models = []
+    for _ in range(2):
+        m, _p = make_prep_model(case, sd0)
+        if stage == 'init':
+            m.load_state_dict({k: v for k, v in sd0.items() if k not in fresh}, strict=False)
+        models.append(m)
+    a, b = models
+    stream = torch.cuda.Stream()
+    for t in range(4):
+        image, sparse, dense = prep_frame(case, t)
+        im, sp, gt = image.to(DEV), sparse.to(DEV), dense.to(DEV)
+        if stage == 'init':
+            a.init_step(im, sp, gt, case['lr'])
+        else:
+            a.head_step(im, sp, case['lr'])
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            if stage == 'init':
+                b.init_step(im.clone(), sp.clone(), gt.clone(), case['lr'], graph=True)
+            else:
+                b.head_step(im.clone(), sp.clone(), case['lr'], graph=True)
+        stream.synchronize()
+        assert a.last_losses()['loss'] == b.last_losses()['loss'], t
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k

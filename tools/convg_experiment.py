@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Where does the time of the general-channel tcgen05 conv go?  Times the 64->64 and 256->256 stride-1 layers with parts of the
+"""[needs the experiments build: python -m tta_depth_completion_b200.build experiments, then run with
+PTTA_B200_LIB=tta_depth_completion_b200/lib/libptta_b200_experiments.so -- the product library contains none of these switches]
+Where does the time of the general-channel tcgen05 conv go?  Times the 64->64 and 256->256 stride-1 layers with parts of the
 kernel switched off (ptta_convg_debug_set)."""
 import os
 import sys

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Per-tile cycle trace of CTA 0 of the general-channel conv (64->64 3x3 s1 @352x1216): where does a tile's time go?
+"""[needs the experiments build: python -m tta_depth_completion_b200.build experiments, then run with
+PTTA_B200_LIB=tta_depth_completion_b200/lib/libptta_b200_experiments.so -- the product library contains none of these switches]
+Per-tile cycle trace of CTA 0 of the general-channel conv (64->64 3x3 s1 @352x1216): where does a tile's time go?
 events: issue thread 0 loop top | 1 accumulator free | 2 A tile landed | 3 36 MMAs issued + commits;
 epilogue 4 waiting | 5 accumulator full | 6 tile staged in smem | 7 accumulator released; producer 8 loop top | 9 TMA issued"""
 import ctypes

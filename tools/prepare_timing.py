@@ -84,10 +84,21 @@ def main():
                 else:
                     model.head_step(im, sp, 1e-3)
             ms = timed(step, args.iters)
+            stream = torch.cuda.Stream()
+
+            def gstep():
+                im, sp, gt = frames[k[0] % 4]
+                k[0] += 1
+                if stage == 'init':
+                    model.init_step(im, sp, gt, 1e-3, graph=True)
+                else:
+                    model.head_step(im, sp, 1e-3, graph=True)
+            with torch.cuda.stream(stream):
+                ms_graph = timed(gstep, args.iters)
             eng = model.model._engine_for(frames[0][0])
             l0 = eng.launch_count()
             step()
-            out['%s_step_%dx352x1216' % (stage, n)] = {'ms': round(ms, 3), 'frames_per_s': round(n * 1e3 / ms, 1), 'launches': eng.launch_count() - l0,
+            out['%s_step_%dx352x1216' % (stage, n)] = {'ms': round(ms, 3), 'frames_per_s': round(n * 1e3 / ms, 1), 'ms_graph': round(ms_graph, 3), 'launches': eng.launch_count() - l0,
                                                        'loss': round(model.last_losses()['loss'], 5)}
     print(json.dumps(out))
 

@@ -80,9 +80,23 @@ def build_stamps_library(verbose=False):
     return out
 
 
+def build_experiments_library(verbose=False):
+    """Experiments build (-DPTTA_EXPERIMENTS): convg_kernel with the work-skipping timing switches and cycle stamps of
+    tools/convg_experiment.py / tools/convg_trace.py (PTTA_B200_LIB=.../libptta_b200_experiments.so).  Not the product."""
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    out = os.path.join(LIB_DIR, 'libptta_b200_experiments.so')
+    cmd = [nvcc] + NVCC_FLAGS + ['-DPTTA_EXPERIMENTS', '-shared', '-o', out] + [os.path.join(CSRC, s) for s in SOURCES] + ['-lz']
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == '__main__':
     import sys
     if 'stamps' in sys.argv:
         print(build_stamps_library(verbose=True))
+    elif 'experiments' in sys.argv:
+        print(build_experiments_library(verbose=True))
     else:
         print(build_library(force=True, verbose=True))

@@ -128,7 +128,12 @@ __device__ __forceinline__ void fast_divmod(int x, int d, unsigned mul, unsigned
         fast_divmod(r_, p.tiles_y, p.div_mul[2], p.div_shr[2], n, ty);                \
     }
 
-__device__ long long g_convg_ts[64 * 16];   // timing experiments (dbg & 64): clock64() stamps of CTA 0, [tile][event]
+// Timing experiments (tools/convg_experiment.py, tools/convg_trace.py) exist only in the experiments build (-DPTTA_EXPERIMENTS ->
+// lib/libptta_b200_experiments.so, never loaded by the package): switches that skip work (1 one MMA per K-item, 2 no epilogue work,
+// 4 no epilogue fence / store, 8 / 16 no A / B loads -- results are then wrong) and cycle stamps (64).  In the product build `dbg` is the
+// constant 0: every branch below folds away and the kernel reads no switch.
+#ifdef PTTA_EXPERIMENTS
+__device__ long long g_convg_ts[64 * 16];   // dbg & 64: clock64() stamps of CTA 0, [tile][event]
 #define CONVG_TS(tl, k) do { if ((dbg & 64) && blockIdx.x == 0 && (tl) < 64) g_convg_ts[(tl) * 16 + (k)] = clock64(); } while (0)
 __device__ unsigned long long g_convg_cta[256 * 2];   // dbg & 64: %globaltimer (ns) at entry / exit of every CTA
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -136,7 +141,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ int g_convg_dbg = 0;   // timing experiments only (ptta_convg_debug_set): 1 one MMA per item, 2 no epilogue work, 4 no fence/store
+__device__ int g_convg_dbg = 0;
+#define CONVG_DBG_LOAD() g_convg_dbg
+#define CONVG_CTA_STAMP(slot) do { if ((dbg & 64) && tid == 0 && blockIdx.x < 256) g_convg_cta[blockIdx.x * 2 + (slot)] = globaltimer_ns(); } while (0)
+#else
+#define CONVG_TS(tl, k) do { } while (0)
+#define CONVG_DBG_LOAD() 0
+#define CONVG_CTA_STAMP(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(ConvGCfg::THREADS, 1)
 convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
@@ -156,9 +168,9 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     const uint32_t ACC_LOG = p.BN <= 64 ? 3u : (p.BN <= 128 ? 2u : 1u), NACC = 1u << ACC_LOG, ACC_STRIDE = 512u >> ACC_LOG;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int dbg = g_convg_dbg;
+    const int dbg = CONVG_DBG_LOAD();
     if (tid == 0) CONVG_TS(63, 0);                   // kernel entry
-    if ((dbg & 64) && tid == 0 && blockIdx.x < 256) g_convg_cta[blockIdx.x * 2] = globaltimer_ns();
+    CONVG_CTA_STAMP(0);
     const uint32_t NA = p.n_a, NB = p.n_b, A_SLOT = p.a_slot_bytes, B_SLOT = p.b_slot_bytes;
     const uint32_t b_base = smem_base + NA * A_SLOT;            // B ring, or the resident weights
     const uint32_t b_tx = (uint32_t)p.BN * 128u;
@@ -412,7 +424,7 @@ convg_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     tc::tc_fence_before();
     __syncthreads();
     if (tid == 0) CONVG_TS(63, 2);                   // all roles finished (stores drained)
-    if ((dbg & 64) && tid == 0 && blockIdx.x < 256) g_convg_cta[blockIdx.x * 2 + 1] = globaltimer_ns();
+    CONVG_CTA_STAMP(1);
     if (p.mcast) tc::cluster_sync();        // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc::tc_fence_after();
@@ -632,7 +644,7 @@ inline int convg_make_plan(ConvGPlan& pl, int kind, int role, int n, int h, int 
     }
     // weight-tile multicast over clusters of two CTAs: implemented and parity-tested, but it does not shorten the streamed-weight layers
     // (128->128: 29.3 us with and without: the per-tile trace shows them MMA-bound at ~75 cycles per N = 128 MMA with 8 us of
-    // prologue / tail per launch, not L2-bound), so it stays an experiment switch: convg_multicast_enabled() <- ptta_convg_debug_set(32)
+    // prologue / tail per launch, not L2-bound), so it stays a tested option, off by default: convg_multicast_enabled() <- ptta_convg_debug_set(32)
     pl.p.mcast = (convg_multicast_enabled() && pl.p.halo && !pl.p.b_resident && pl.p.n_tiles == 1 && BN % 16 == 0 && pl.p.total_tiles >= 2) ? 1 : 0;
     if (pl.p.n_a > ConvGCfg::MAX_STAGES) pl.p.n_a = ConvGCfg::MAX_STAGES;
     if (pl.p.n_b > ConvGCfg::MAX_STAGES) pl.p.n_b = ConvGCfg::MAX_STAGES;

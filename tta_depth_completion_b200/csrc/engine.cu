@@ -236,6 +236,13 @@ struct ptta_msgchn {
     // graph
     cudaGraphExec_t graph_exec = nullptr;
     struct GraphKey { float isc[3], ish[3], cap, w_sd, w_sm, w_cos; } graph_key;   // everything a capture bakes in (inputs are staged)
+    cudaGraphExec_t prep_graph_exec = nullptr;      // captured stage-1 / stage-2 step (an engine runs one of the two)
+    GraphKey prep_graph_key;
+    float* stage_gt = nullptr;                      // engine-owned copy of the ground truth the captured stage-1 step reads
+    void drop_graphs() {
+        if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+        if (prep_graph_exec) { cudaGraphExecDestroy(prep_graph_exec); prep_graph_exec = nullptr; }
+    }
 
     // ---------------------------------------------------------------------------------------------
     Map32 alloc32(const char* name, int h, int w, int c = 32) {
@@ -422,6 +429,7 @@ struct ptta_msgchn {
         fd = alloc_user("filtered_depth"); fv = alloc_user("filtered_validity");
         stage_img = allocv<float>((size_t)Nu * 3 * Hu * Wu); reg("stage_image", stage_img, 0, Nu, 3, Hu, Wu);
         stage_sp = allocv<float>((size_t)Nu * Hu * Wu); reg("stage_sparse", stage_sp, 0, Nu, 1, Hu, Wu);
+        stage_gt = allocv<float>((size_t)Nu * Hu * Wu); reg("stage_ground_truth", stage_gt, 0, Nu, 1, Hu, Wu);
         if (padded) {
             pimg = allocv<float>((size_t)N * 3 * H * W);
             psp = allocv<float>((size_t)N * H * W);
@@ -683,7 +691,7 @@ struct ptta_msgchn {
         }
         PTTA_CUDA(cudaStreamSynchronize(st));
         packed = true;
-        if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+        drop_graphs();
         return 0;
     }
 
@@ -1405,6 +1413,33 @@ struct ptta_msgchn {
         return adam_step();
     }
 
+    // captured stage-1 / stage-2 steps (same scheme as ptta_msgchn_tta_step_graph: inputs staged into engine-owned buffers, one eager step to
+    // set the function attributes and validate, then capture-without-execute and replay)
+    template <class Body>
+    int prep_step_graphed(const GraphKey& key, cudaStream_t stream_, Body body) {
+        ptta_msgchn* e = this; cudaStream_t st = stream_;
+        if (e->prep_graph_exec && memcmp(&key, &e->prep_graph_key, sizeof(key)) != 0) { cudaGraphExecDestroy(e->prep_graph_exec); e->prep_graph_exec = nullptr; }
+        if (!e->prep_graph_exec) {
+            e->st = st;
+            PTTA_TRY(body());
+            PTTA_CUDA(cudaStreamSynchronize(st));
+            cudaGraph_t graph = nullptr;
+            PTTA_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int rc = body();
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            PTTA_CHECK(ce == cudaSuccess, "graph capture failed: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&e->prep_graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            PTTA_CHECK(ce == cudaSuccess, "graph instantiate failed: %s", cudaGetErrorString(ce));
+            memcpy(&e->prep_graph_key, &key, sizeof(key));
+            return 0;   // the eager step above WAS this call's step
+        }
+        PTTA_CUDA(cudaGraphLaunch(e->prep_graph_exec, st));
+        return 0;
+    }
+
+
     int adam_step() {
         PTTA_CHECK(n_adam_chunks > 0, "Adam state not bound (grad/, adam_m/, adam_v/ entries for every adapted tensor)");
         if (comm.world > 1) {
@@ -2083,12 +2118,12 @@ int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value) {
     else if (k == "trainable_head") { if (value) PTTA_TRY(e->select_trainable_head()); }   // stage-2 trainer: Adam steps pred.*, not the meta layer
     else if (k == "skip_dec3") e->skip_dec3 = value != 0;                  // stage 2 never reads the prediction of the real branch
     else PTTA_CHECK(false, "set_option: unknown option '%s'", name);
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }   // a captured step bakes the dispatch in
+    e->drop_graphs();   // a captured step bakes the dispatch in
     return 0;
 }
 void ptta_msgchn_destroy(ptta_msgchn* e) {
     if (!e) return;
-    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    e->drop_graphs();
     if (e->st2) { cudaStreamDestroy(e->st2); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaEventDestroy(e->ev_projbn);
                  cudaEventDestroy(e->ev_enc1); cudaEventDestroy(e->ev_zmeta); }
     if (e->st3) { cudaStreamDestroy(e->st3); cudaEventDestroy(e->ev_e3); cudaEventDestroy(e->ev_mlp); cudaEventDestroy(e->ev_lossg);
@@ -2298,6 +2333,35 @@ int ptta_msgchn_tta_step_graph(ptta_msgchn* e, const float* image_raw, const flo
     }
     PTTA_CUDA(cudaGraphLaunch(e->graph_exec, st));
     return 0;
+}
+
+int ptta_msgchn_init_step_graph(ptta_msgchn* e, const float* image_raw, const float* isc, const float* ish, const float* sparse,
+                                const float* ground_truth, float cap, float max_predict_depth, ptta_stream_t stream) {
+    PTTA_CHECK(e && image_raw && sparse && ground_truth && isc && ish, "init_step_graph: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    PTTA_CHECK(st != nullptr, "init_step_graph: needs a non-default stream (legacy stream 0 cannot be captured)");
+    ptta_msgchn::GraphKey key; memset(&key, 0, sizeof(key));
+    key.cap = cap; key.w_sd = max_predict_depth; key.w_sm = 1.f;        // w_sm = 1: stage 1
+    for (int c = 0; c < 3; ++c) { key.isc[c] = isc[c]; key.ish[c] = ish[c]; }
+    const size_t px = (size_t)e->Nu * e->Hu * e->Wu;
+    if (image_raw != e->stage_img) PTTA_CUDA(cudaMemcpyAsync(e->stage_img, image_raw, 3 * px * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (sparse != e->stage_sp) PTTA_CUDA(cudaMemcpyAsync(e->stage_sp, sparse, px * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (ground_truth != e->stage_gt) PTTA_CUDA(cudaMemcpyAsync(e->stage_gt, ground_truth, px * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return e->prep_step_graphed(key, st, [&]() { return e->init_step(e->stage_img, isc, ish, e->stage_sp, e->stage_gt, cap, max_predict_depth); });
+}
+
+int ptta_msgchn_head_step_graph(ptta_msgchn* e, const float* image_raw, const float* isc, const float* ish, const float* sparse, float cap,
+                                ptta_stream_t stream) {
+    PTTA_CHECK(e && image_raw && sparse && isc && ish, "head_step_graph: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    PTTA_CHECK(st != nullptr, "head_step_graph: needs a non-default stream (legacy stream 0 cannot be captured)");
+    ptta_msgchn::GraphKey key; memset(&key, 0, sizeof(key));
+    key.cap = cap; key.w_sm = 2.f;                                       // w_sm = 2: stage 2
+    for (int c = 0; c < 3; ++c) { key.isc[c] = isc[c]; key.ish[c] = ish[c]; }
+    const size_t px = (size_t)e->Nu * e->Hu * e->Wu;
+    if (image_raw != e->stage_img) PTTA_CUDA(cudaMemcpyAsync(e->stage_img, image_raw, 3 * px * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (sparse != e->stage_sp) PTTA_CUDA(cudaMemcpyAsync(e->stage_sp, sparse, px * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return e->prep_step_graphed(key, st, [&]() { return e->head_step(e->stage_img, isc, ish, e->stage_sp, cap); });
 }
 
 int ptta_msgchn_get_tensor(ptta_msgchn* e, const char* name, void** ptr, int* dtype, long long* dims4) {

@@ -34,23 +34,41 @@ int ptta_convg_run(int kind, int role, const void* x0, const void* x1, const voi
 }
 
 int ptta_convg_debug_set(int mask) {
-    convg_multicast_flag() = (mask & 32) ? 1 : 0;          // host-side switch: weight-tile multicast over 2-CTA clusters
+#ifdef PTTA_EXPERIMENTS
+    convg_multicast_flag() = (mask & 32) ? 1 : 0;
     PTTA_CUDA(cudaMemcpyToSymbol(g_convg_dbg, &mask, sizeof(int)));
     return 0;
+#else
+    // product build: the only switch is 32 (weight-tile multicast over 2-CTA clusters; results unchanged, tested).  The work-skipping
+    // timing switches and the cycle stamps are compiled into the experiments build only
+    PTTA_CHECK((mask & ~32) == 0, "convg_debug_set: mask %d needs the experiments build (-DPTTA_EXPERIMENTS); this library accepts 0 and 32", mask);
+    convg_multicast_flag() = (mask & 32) ? 1 : 0;
+    return 0;
+#endif
 }
 
 int ptta_convg_debug_read_cta(unsigned long long* out_host, int n) {
+#ifdef PTTA_EXPERIMENTS
     PTTA_CHECK(out_host && n > 0 && n <= 512, "convg_debug_read_cta: bad arguments");
     PTTA_CUDA(cudaDeviceSynchronize());
     PTTA_CUDA(cudaMemcpyFromSymbol(out_host, g_convg_cta, (size_t)n * sizeof(unsigned long long)));
     return 0;
+#else
+    (void)out_host; (void)n;
+    PTTA_CHECK(false, "convg_debug_read_cta: experiments build only (-DPTTA_EXPERIMENTS)");
+#endif
 }
 
 int ptta_convg_debug_read_ts(long long* out_host, int n) {
+#ifdef PTTA_EXPERIMENTS
     PTTA_CHECK(out_host && n > 0 && n <= 64 * 16, "convg_debug_read_ts: bad arguments");
     PTTA_CUDA(cudaDeviceSynchronize());
     PTTA_CUDA(cudaMemcpyFromSymbol(out_host, g_convg_ts, (size_t)n * sizeof(long long)));
     return 0;
+#else
+    (void)out_host; (void)n;
+    PTTA_CHECK(false, "convg_debug_read_ts: experiments build only (-DPTTA_EXPERIMENTS)");
+#endif
 }
 
 int ptta_convg_run_thin(const void* x0, const void* x1, const void* packed, const float* bias, float* const* planes, const long long* nstrides,

@@ -125,11 +125,12 @@ class MsgChnEngine:
     def l2_loss_backward(self, grad_scale=1.0):
         check(self.L.ptta_msgchn_l2_loss_backward(self.handle, grad_scale, _stream()), 'l2_loss_backward')
 
-    def init_step(self, image_raw, sparse_depth, ground_truth, max_input_depth, max_predict_depth, img_scale, img_shift):
+    def init_step(self, image_raw, sparse_depth, ground_truth, max_input_depth, max_predict_depth, img_scale, img_shift, graph=False):
         self._check_inputs(image_raw, sparse_depth)
         self._check_map(ground_truth)
         cap = float(max_input_depth) if max_input_depth is not None else -1.0
-        check(self.L.ptta_msgchn_init_step(self.handle, ptr(image_raw), self._f3(img_scale), self._f3(img_shift), ptr(sparse_depth),
+        fn = self.L.ptta_msgchn_init_step_graph if graph else self.L.ptta_msgchn_init_step
+        check(fn(self.handle, ptr(image_raw), self._f3(img_scale), self._f3(img_shift), ptr(sparse_depth),
                                            ptr(ground_truth), cap, float(max_predict_depth), _stream()), 'init_step')
 
     def cos_loss(self):
@@ -144,10 +145,11 @@ class MsgChnEngine:
     def head_backward(self):
         check(self.L.ptta_msgchn_head_backward(self.handle, _stream()), 'head_backward')
 
-    def head_step(self, image_raw, sparse_depth, max_input_depth, img_scale, img_shift):
+    def head_step(self, image_raw, sparse_depth, max_input_depth, img_scale, img_shift, graph=False):
         self._check_inputs(image_raw, sparse_depth)
         cap = float(max_input_depth) if max_input_depth is not None else -1.0
-        check(self.L.ptta_msgchn_head_step(self.handle, ptr(image_raw), self._f3(img_scale), self._f3(img_shift), ptr(sparse_depth), cap,
+        fn = self.L.ptta_msgchn_head_step_graph if graph else self.L.ptta_msgchn_head_step
+        check(fn(self.handle, ptr(image_raw), self._f3(img_scale), self._f3(img_shift), ptr(sparse_depth), cap,
                                            _stream()), 'head_step')
 
     def _check_map(self, t):

@@ -574,18 +574,18 @@ class ExternalModel_Adapt(object):
     def prepare_parameters(self, mode=''):
         return self.model.prepare_parameters(mode)
 
-    def init_step(self, image_raw, sparse_depth, ground_truth, learning_rate, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def init_step(self, image_raw, sparse_depth, ground_truth, learning_rate, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, graph=False):
         """One whole stage-1 step (src/init_main.py:482-522: forward 'init_meta...', supervised loss, backward, Adam) in one library
         call; `last_losses()['loss']` reads the loss."""
         eng = self._prep_engine(image_raw, 'meta', (learning_rate, betas, eps, weight_decay))
         eng.init_step(image_raw, sparse_depth, ground_truth.contiguous(), self.max_input_depth, self.max_predict_depth,
-                      self.model.img_scale, self.model.img_shift)
+                      self.model.img_scale, self.model.img_shift, graph=graph)
         self._last_engine = eng
 
-    def head_step(self, image_raw, sparse_depth, learning_rate, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def head_step(self, image_raw, sparse_depth, learning_rate, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, graph=False):
         """One whole stage-2 step (src/head_main.py:437-480) in one library call."""
         eng = self._prep_engine(image_raw, 'head', (learning_rate, betas, eps, weight_decay))
-        eng.head_step(image_raw, sparse_depth, self.max_input_depth, self.model.img_scale, self.model.img_shift)
+        eng.head_step(image_raw, sparse_depth, self.max_input_depth, self.model.img_scale, self.model.img_shift, graph=graph)
         self._last_engine = eng
 
     def _prep_engine(self, image_raw, trainable, hyper):
