@@ -188,6 +188,10 @@ struct ptta_msgchn {
     bool fuse_enc_sums = false;      // decoder sums x0 + c0, x1 + c1 written by the encoder's conv epilogues (needs fuse_up2).  Measured 722 -> 733
                                      // frames/s: the passes it removes (dec_sums 48 -> 11 us) come back as epilogue time of the tcgen05 conv, and the
                                      // oracle's bf16 emulation does not round at its points -- off by default, kept as a tested option
+    bool fuse_bn_finalize = false;   // BatchNorm finalize inside col_stats (the blocks holding the last tickets finalise; single-GPU path): bit-identical
+                                     // to the separate bn_finalize / bn_bwd_finalize launches and 10 launches fewer per step, but MEASURED SLOWER
+                                     // (721 vs 731 frames/s): with programmatic dependent launch the finalize kernel's launch is already hidden, and the
+                                     // tail -- 16 blocks of 256 threads after every other block has finished -- costs more than it saves.  Tested option, off
     bool fuse_up2 = true;            // x = conv(.) + up2(pre_x) in the epilogue of the tcgen05 conv (option fuse_up2 = 0: separate add_up2 pass)
     // shared-model mode (ptta_msgchn_set_comm): SyncBatchNorm sums and the gradient all-reduce go through peer memory (peer_comm.cuh)
     PeerComm comm;
@@ -475,12 +479,12 @@ struct ptta_msgchn {
         k0 = allocv<float>(512); k1 = allocv<float>(512); k2 = allocv<float>(512);
         long long max_rows = std::max<long long>(R, 1);
         partial_doubles = (size_t)cdiv(max_rows, STATS_ROWS_PER_BLOCK) * 2 * 512;
-        partial = allocv<double>(partial_doubles);
-        partial2 = allocv<double>(partial_doubles);
+        partial = allocv<double>(partial_doubles + 2);           // + the two counters of the fused finalize (StatsFin)
+        partial2 = allocv<double>(partial_doubles + 2);
         size_t wg = std::max(wgrad_partial_bytes(N, H / 4, W / 4, 32, 128), wgrad_partial_bytes(N, H / 4, W / 4, 128, 32));
         wgrad_ws = (float*)arena.take(wg);
         wgrad_ws2 = (float*)arena.take(wg);
-        partial3 = allocv<double>(partial_doubles);
+        partial3 = allocv<double>(partial_doubles + 2);
         losses = (LossScalars*)arena.take(sizeof(LossScalars));
         reg("losses", losses, 0, 5, 1, 1, 1);
         loss_map_blocks = std::min(cdiv((long long)H * W, LOSS_BLOCK * 4), 1184);
@@ -868,22 +872,30 @@ struct ptta_msgchn {
         if (next_xid >= PTTA_COMM_MAX_XID) { set_error("shared-model mode: more than %d peer exchanges in one step", PTTA_COMM_MAX_XID); return -1; }
         return next_xid++;
     }
-    int stats(const bf16* x, const bf16* dy, long long rows, int C, int mode, const BnState* s, int relu_mask, int& nblk) {
+    // fin: optional fused finalize (single-GPU path; its counters sit behind the partial buffer of the stream the call runs on)
+    int stats(const bf16* x, const bf16* dy, long long rows, int C, int mode, const BnState* s, int relu_mask, int& nblk, const StatsFin* fin = nullptr) {
         nblk = cdiv(rows, STATS_ROWS_PER_BLOCK);
         PTTA_CHECK((size_t)nblk * 2 * C <= partial_doubles, "stats partial buffer too small");
+        StatsFin f; memset(&f, 0, sizeof(f));
+        if (fin) { f = *fin; f.counters = reinterpret_cast<unsigned int*>(partial + partial_doubles); }
         launch_k(col_stats_kernel, nblk, 256, 2 * 2048 * sizeof(double), st, x, dy, partial, rows, C, mode, s ? s->mean : nullptr,
                                                                       s ? s->invstd : nullptr, s ? s->scale : nullptr,
-                                                                      s ? s->shift : nullptr, relu_mask);
+                                                                      s ? s->shift : nullptr, relu_mask, f);
         return check_launch("col_stats");
     }
     // defer_running: compute the batch statistics now, leave the running-statistics update to bn_running_update (ordering)
     int bn_forward_stats(const BnLayer& L, const BnState& s, const bf16* x, long long rows, bool training, bool defer_running = false) {
         int nblk = 0;
-        if (training) PTTA_TRY(stats(x, nullptr, rows, L.c, 0, nullptr, 0, nblk));
         BnParams p; p.gamma = L.gamma; p.beta = L.beta; p.running_mean = L.rm; p.running_var = L.rv; p.num_batches_tracked = L.nbt;
         if (defer_running) { p.running_mean = nullptr; p.running_var = nullptr; p.num_batches_tracked = nullptr; }
         p.uvar = s.uvar;
         p.mean = s.mean; p.invstd = s.invstd; p.scale = s.scale; p.shift = s.shift; p.momentum = 0.1f; p.eps = 1e-5f;
+        if (training && comm.world == 1 && fuse_bn_finalize) {     // the last blocks of col_stats finalise: no second launch
+            StatsFin fin; memset(&fin, 0, sizeof(fin));
+            fin.kind = 1; fin.count = rows; fin.p = p;
+            return stats(x, nullptr, rows, L.c, 0, nullptr, 0, nblk, &fin);
+        }
+        if (training) PTTA_TRY(stats(x, nullptr, rows, L.c, 0, nullptr, 0, nblk));
         const int xid = (training && comm.world > 1) ? take_xid() : 0;
         if (xid < 0) return 1;
         launch_k(bn_finalize_kernel, cdiv(L.c, 32), FIN_THREADS, 0, st, partial, nblk, rows, L.c, p, training ? 1 : 0, comm, xid);
@@ -901,6 +913,14 @@ struct ptta_msgchn {
     int bn_backward(const BnLayer& L, const BnState& s, const bf16* dy, const bf16* x, bf16* dx, long long rows, int relu_mask,
                     float* dgamma, float* dbeta) {
         int nblk = 0;
+        if (comm.world == 1 && fuse_bn_finalize) {
+            StatsFin fin; memset(&fin, 0, sizeof(fin));
+            fin.kind = 2; fin.count = rows; fin.gamma = L.gamma; fin.invstd = s.invstd; fin.dgamma = dgamma; fin.dbeta = dbeta;
+            fin.k0 = k0; fin.k1 = k1; fin.k2 = k2;
+            PTTA_TRY(stats(x, dy, rows, L.c, 1, &s, relu_mask, nblk, &fin));
+            launch_k(bn_bwd_apply_kernel, cdiv(rows, (256 / (L.c / 8)) * EW_ROWS), 256, 0, st, dy, x, dx, rows, L.c, s.mean, s.invstd, k0, k1, k2, s.scale, s.shift, relu_mask);
+            return check_launch("bn_bwd_apply");
+        }
         PTTA_TRY(stats(x, dy, rows, L.c, 1, &s, relu_mask, nblk));
         const int xid = comm.world > 1 ? take_xid() : 0;
         if (xid < 0) return 1;
@@ -2114,6 +2134,7 @@ int ptta_msgchn_set_option(ptta_msgchn* e, const char* name, long long value) {
     else if (k == "fuse_dec_sums") e->fuse_dec_sums = value != 0;
     else if (k == "fuse_projpred") e->fuse_projpred = value != 0;
     else if (k == "fuse_up2") e->fuse_up2 = value != 0;
+    else if (k == "fuse_bn_finalize") e->fuse_bn_finalize = value != 0;
     else if (k == "fuse_enc_sums") e->fuse_enc_sums = value != 0;
     else if (k == "trainable_head") { if (value) PTTA_TRY(e->select_trainable_head()); }   // stage-2 trainer: Adam steps pred.*, not the meta layer
     else if (k == "skip_dec3") e->skip_dec3 = value != 0;                  // stage 2 never reads the prediction of the real branch
