@@ -300,6 +300,10 @@ int ptta_augment_flip(const float* in, float* out, int n, int c, int h, int w, c
  * ptta_augment_resize_crop: src/transforms.py:425-502, 1222-1283 (functional.resize to (resize_h, resize_w) >= (h, w), then the crop
  * [start_y, start_y + h) x [start_x, start_x + w)): device int32 [N] arrays; only the surviving h x w pixels are computed.
  * Both: fp32 [N,C,H,W], out != in, samples whose flag is clear are copied. */
+/* ptta_augment_crop: src/transforms.py:337-383, 955-988 -- every sample cropped to the same (crop_h, crop_w) window at its own offset
+ * (device int32 [N] arrays; the caller guarantees start + crop <= size, as torch.randint's bounds do); out is [N,C,crop_h,crop_w]. */
+int ptta_augment_crop(const float* in, float* out, int n, int c, int h, int w, int crop_h, int crop_w, const int* start_y,
+                      const int* start_x, ptta_stream_t stream);
 int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate,
                         const float* theta_n_x_6, int mode, ptta_stream_t stream);
 int ptta_augment_resize_crop(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_resize,

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's `Transforms.transform` (src/transforms.py:192-668) for the options
 the native path implements: brightness / contrast / saturation jitter (:236-301, per-sample torchvision tensor ops, :714-837), image
-normalisation (:669-712), per-sample flips (:386-407, 990-1034), rotation (:406-423, 1036-1070) and resize-and-crop (:425-502, 1222-1283).  The third-party arithmetic is torchvision's
+normalisation (:669-712), random crop to a common shape (:337-383, 955-988), per-sample flips (:386-407, 990-1034), rotation (:406-423, 1036-1070) and resize-and-crop (:425-502, 1222-1283).  The third-party arithmetic is torchvision's
 (`torchvision.transforms.functional.adjust_*`, pinned 0.10.1 by the reference's README.md:74; 0.26 here -- the tensor code path
 `_blend` / `rgb_to_grayscale` is unchanged between the two) and is called as the reference calls it.  Pinned against fixtures produced by
 the reference's own class: oracle/gen_golden_transforms.py, tests/test_transforms_oracle.py."""
@@ -22,6 +22,20 @@ def draws(n_batch, cfg, probability, rand=lambda n: torch.rand(n)):
             d['do_' + name] = torch.logical_and(d['do'], roll >= 0.50 if ge else roll <= 0.50)
             lo, hi = cfg[name]
             d['f_' + name] = (hi - lo) * rand(n_batch) + lo
+    if 'crop_to_shape' in cfg:                                                  # T:337-366
+        spec = cfg['crop_to_shape']
+        h, w = cfg['shape']
+        roll = bool(torch.rand(1) <= 0.50)
+        if len(spec) == 2:
+            d['do_crop'], (d['crop_h'], d['crop_w']) = roll, spec
+        else:
+            d['do_crop'] = True
+            d['crop_h'] = int(np.random.randint(low=spec[0], high=spec[2] + 1))
+            d['crop_w'] = int(np.random.randint(low=spec[1], high=spec[3] + 1))
+        if d['do_crop']:
+            d['crop_y'] = torch.randint(low=0, high=h - d['crop_h'] + 1, size=(n_batch,))
+            d['crop_x'] = torch.randint(low=0, high=w - d['crop_w'] + 1, size=(n_batch,))
+            cfg = dict(cfg, shape=(d['crop_h'], d['crop_w']))                   # later transforms see the cropped size (T:381-383)
     for name in ('horizontal', 'vertical'):
         if name in cfg.get('flip', ()):
             d['do_' + name] = torch.logical_and(d['do'], rand(n_batch) <= 0.50)
@@ -66,6 +80,10 @@ def apply(images_arr, cfg, d, normalized_image_range=None, interpolation_modes=(
             images_arr = [2.0 * (im / 255.0) - 1.0 for im in images_arr]
         elif rng != [0, 255]:
             raise ValueError(rng)
+    if d.get('do_crop'):                                                        # T:955-988
+        ch, cw = d['crop_h'], d['crop_w']
+        images_arr = [torch.stack([im[b, :, int(d['crop_y'][b]):int(d['crop_y'][b]) + ch, int(d['crop_x'][b]):int(d['crop_x'][b]) + cw]
+                                   for b in range(im.shape[0])], dim=0) for im in images_arr]
     for name, dim in (('horizontal', -1), ('vertical', -2)):
         if 'do_' + name in d:
             for images in images_arr:
@@ -96,13 +114,19 @@ def apply(images_arr, cfg, d, normalized_image_range=None, interpolation_modes=(
 
 def adjust_intrinsics(intrinsics_arr, d, shape):
     """T:449-453, 498-502 with T:1330-1378: every sample's intrinsics are rescaled and shifted, also those the transform skipped"""
-    if 'do_resize_and_crop' not in d:
-        return [K.clone() for K in intrinsics_arr]
     h, w = shape
     out = []
     for K in intrinsics_arr:
         K = K.clone()
         for b in range(len(K)):
+            if d.get('do_crop'):                                                # T:372-379: the full size difference, for every sample
+                K[b, 0, 2] = K[b, 0, 2] * 1.0 - float(w - d['crop_w'])
+                K[b, 1, 2] = K[b, 1, 2] * 1.0 - float(h - d['crop_h'])
+        if d.get('do_crop'):
+            h, w = d['crop_h'], d['crop_w']
+        for b in range(len(K)):
+            if 'do_resize_and_crop' not in d:
+                continue
             xs, ys = d['r_width'][b] / w, d['r_height'][b] / h
             K[b, 0, 0] = K[b, 0, 0] * xs
             K[b, 0, 2] = K[b, 0, 2] * xs

@@ -182,5 +182,5 @@ def test_unsupported_options_fail_loudly():
         Transforms(random_resize_and_pad=[0.5, 1.0])
     with pytest.raises(NotImplementedError, match='random_hue'):
         Transforms(random_hue=[-0.1, 0.1])
-    with pytest.raises(NotImplementedError, match='random_crop_to_shape'):
-        Transforms(random_crop_to_shape=[32, 64])
+    with pytest.raises(NotImplementedError, match='random_crop_and_pad'):
+        Transforms(random_crop_and_pad=[0.5, 1.0])

@@ -21,6 +21,9 @@ def case_cfg(case):
             cfg[k] = c['random_' + k]
     if 'random_flip_type' in c:
         cfg['flip'] = tuple(c['random_flip_type'])
+    if 'random_crop_to_shape' in c:
+        cfg['crop_to_shape'] = c['random_crop_to_shape']
+        cfg['shape'] = (case['h'], case['w'])
     if c.get('random_rotate_max', 0) > 0:
         cfg['rotate'] = c['random_rotate_max']
     if 'random_resize_and_crop' in c:

@@ -10,6 +10,7 @@
 //   and ONE elementwise pass instead of ~15 tensor ops and three host syncs per sample (`float(factors[b])`).
 //   flips (src/transforms.py:386-407, 990-1034): per-sample horizontal / vertical mirror of an N x C x H x W map.
 //   rotation (:406-423) and resize-and-crop (:425-502): per-sample resampling, nearest or bilinear (see the kernels).
+//   random crop to a common shape (:337-383): per-sample window copy.
 // The random draws stay where the reference makes them (torch.rand on the device, same order): tta_depth_completion_b200/transforms.py.
 #pragma once
 #include "common.cuh"
@@ -250,6 +251,20 @@ __global__ void __launch_bounds__(256) resize_crop_kernel(const float* __restric
                                     ly1 * (lx0 * pc[(y1 + yp) * W + x1] + lx1 * pc[(y1 + yp) * W + x1 + xp]);
             }
         }
+    }
+}
+
+// Per-sample crop to a common (ch, cw) window (src/transforms.py:337-383, 955-988): out[n][c][y][x] = in[n][c][sy[n] + y][sx[n] + x]
+__global__ void __launch_bounds__(256) crop_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W, int ch, int cw,
+                                                   const int* __restrict__ sy, const int* __restrict__ sx) {
+    PDL_SYNC();
+    const int n = blockIdx.y;
+    const int oplane = ch * cw, oy = sy[n], ox = sx[n];
+    const float* ib = in + (size_t)n * C * H * W;
+    float* ob = out + (size_t)n * C * oplane;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < C * oplane; i += gridDim.x * 256) {
+        const int c = i / oplane, r = i - c * oplane, y = r / cw, x = r - y * cw;
+        ob[i] = ib[(size_t)c * H * W + (size_t)(oy + y) * W + ox + x];
     }
 }
 

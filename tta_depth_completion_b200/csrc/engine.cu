@@ -1878,6 +1878,16 @@ int ptta_augment_flip(const float* in, float* out, int n, int c, int h, int w, c
     return check_launch("flip");
 }
 
+int ptta_augment_crop(const float* in, float* out, int n, int c, int h, int w, int crop_h, int crop_w, const int* start_y, const int* start_x,
+                      ptta_stream_t stream) {
+    PTTA_CHECK(in && out && in != out && start_y && start_x && n >= 1 && c >= 1, "augment_crop: bad argument");
+    PTTA_CHECK(crop_h >= 1 && crop_w >= 1 && crop_h <= h && crop_w <= w, "augment_crop: window %dx%d does not fit %dx%d", crop_h, crop_w, h, w);
+    PTTA_CHECK((long long)c * h * w < (1ll << 31) && n <= 65535, "augment_crop: map too large");
+    const int bx = std::max(1, std::min(cdiv((long long)c * crop_h * crop_w, 256 * 4), cdiv(2368, n)));
+    launch_k(crop_kernel, dim3(bx, n), 256, 0, (cudaStream_t)stream, in, out, c, h, w, crop_h, crop_w, start_y, start_x);
+    return check_launch("crop");
+}
+
 int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate, const float* theta_n_x_6,
                         int mode, ptta_stream_t stream) {
     PTTA_CHECK(in && out && in != out && do_rotate && theta_n_x_6 && n >= 1 && c >= 1 && h >= 1 && w >= 1, "augment_rotate: bad argument");

@@ -883,6 +883,40 @@ struct BnParams {
     float momentum, eps;
 };
 
+// The per-channel arithmetic of the two finalize steps, written with explicit roundings (no fused multiply-add left to the compiler) so that
+// the stand-alone finalize kernels and the finalize fused into col_stats give bit-identical vectors.
+__device__ __forceinline__ void bn_forward_channel(const BnParams& p, int ch, double a, double b, long long count) {
+    const double cnt = (double)count;
+    const double m = __ddiv_rn(a, cnt);
+    double var = __dsub_rn(__ddiv_rn(b, cnt), __dmul_rn(m, m));
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)__ddiv_rn(1.0, sqrt(__dadd_rn(var, (double)p.eps)));
+    const float mf = (float)m;
+    p.mean[ch] = mf;
+    p.invstd[ch] = invstd;
+    const float sc = __fmul_rn(p.gamma[ch], invstd);
+    p.scale[ch] = sc;
+    p.shift[ch] = __fsub_rn(p.beta[ch], __fmul_rn(mf, sc));
+    const double unbiased = count > 1 ? __ddiv_rn(__dmul_rn(var, cnt), (double)(count - 1)) : var;
+    if (p.uvar) p.uvar[ch] = (float)unbiased;
+    if (p.running_mean) {
+        const float keep = __fsub_rn(1.f, p.momentum);
+        p.running_mean[ch] = __fadd_rn(__fmul_rn(keep, p.running_mean[ch]), __fmul_rn(p.momentum, mf));
+        p.running_var[ch] = __fadd_rn(__fmul_rn(keep, p.running_var[ch]), __fmul_rn(p.momentum, (float)unbiased));
+    }
+    if (ch == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+}
+// a, b: the sums over the batch the data gradient uses (all ranks in shared-model mode); count likewise
+__device__ __forceinline__ void bn_backward_channel(int ch, double a, double b, long long count, const float* __restrict__ gamma,
+                                                    const float* __restrict__ invstd, float* __restrict__ k0, float* __restrict__ k1,
+                                                    float* __restrict__ k2) {
+    const float g = __fmul_rn(gamma[ch], invstd[ch]);
+    const double cnt = (double)count;
+    k0[ch] = g;
+    k1[ch] = (float)__ddiv_rn(__dmul_rn((double)g, a), cnt);
+    k2[ch] = (float)__ddiv_rn(__dmul_rn((double)g, b), cnt);
+}
+
 // sum of partial[k][slot][ch] over k for 32 channels per block: thread (cx = tid & 31, ks = tid >> 5) adds slice ks of the
 // partial list (256 B coalesced reads, four independent loads in flight), the FIN_SLICES slices are combined through shared
 // memory in a fixed order (deterministic).  Returns the totals (a: slot 0, b: slot 1) in the threads with ks == 0; launch
@@ -1062,32 +1096,12 @@ __device__ __forceinline__ void stats_fused_finalize(const StatsFin& fin, const 
         int ch; double a, b;
         const bool owner = group_reduce_partials_256(partial, nblk, C, g, ch, a, b, fsh);
         if (!owner) continue;
-        const long long count = fin.count;
         if (fin.kind == 1) {
-            const BnParams& p = fin.p;
-            double m = a / (double)count;
-            double var = b / (double)count - m * m;
-            if (var < 0.0) var = 0.0;
-            float invstd = (float)(1.0 / sqrt(var + (double)p.eps));
-            p.mean[ch] = (float)m;
-            p.invstd[ch] = invstd;
-            float sc = p.gamma[ch] * invstd;
-            p.scale[ch] = sc;
-            p.shift[ch] = p.beta[ch] - (float)m * sc;
-            double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
-            if (p.uvar) p.uvar[ch] = (float)unbiased;
-            if (p.running_mean) {
-                p.running_mean[ch] = (1.f - p.momentum) * p.running_mean[ch] + p.momentum * (float)m;
-                p.running_var[ch] = (1.f - p.momentum) * p.running_var[ch] + p.momentum * (float)unbiased;
-            }
-            if (ch == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+            bn_forward_channel(fin.p, ch, a, b, fin.count);
         } else {
             if (fin.dbeta) fin.dbeta[ch] = (float)a;
             if (fin.dgamma) fin.dgamma[ch] = (float)b;
-            float gk = fin.gamma[ch] * fin.invstd[ch];
-            fin.k0[ch] = gk;
-            fin.k1[ch] = (float)((double)gk * a / (double)count);
-            fin.k2[ch] = (float)((double)gk * b / (double)count);
+            bn_backward_channel(ch, a, b, fin.count, fin.gamma, fin.invstd, fin.k0, fin.k1, fin.k2);
         }
     }
     __syncthreads();
@@ -1127,22 +1141,7 @@ __global__ void __launch_bounds__(FIN_THREADS) bn_finalize_kernel(const double* 
             count *= comm.world;
         }
         if (!owner) return;
-        double m = a / (double)count;
-        double var = b / (double)count - m * m;
-        if (var < 0.0) var = 0.0;
-        float invstd = (float)(1.0 / sqrt(var + (double)p.eps));
-        p.mean[ch] = (float)m;
-        p.invstd[ch] = invstd;
-        float sc = p.gamma[ch] * invstd;
-        p.scale[ch] = sc;
-        p.shift[ch] = p.beta[ch] - (float)m * sc;
-        double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
-        if (p.uvar) p.uvar[ch] = (float)unbiased;
-        if (p.running_mean) {
-            p.running_mean[ch] = (1.f - p.momentum) * p.running_mean[ch] + p.momentum * (float)m;
-            p.running_var[ch] = (1.f - p.momentum) * p.running_var[ch] + p.momentum * (float)unbiased;
-        }
-        if (ch == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+        bn_forward_channel(p, ch, a, b, count);
     } else {
         ch = blockIdx.x * 32 + (threadIdx.x & 31);
         if ((threadIdx.x >> 5) != 0 || ch >= C) return;
@@ -1225,10 +1224,7 @@ __global__ void __launch_bounds__(FIN_THREADS) bn_bwd_finalize_kernel(const doub
         count *= comm.world;
     }
     if (!owner) return;
-    float g = gamma[ch] * invstd[ch];
-    k0[ch] = g;
-    k1[ch] = (float)((double)g * a / (double)count);
-    k2[ch] = (float)((double)g * b / (double)count);
+    bn_backward_channel(ch, a, b, count, gamma, invstd, k0, k1, k2);
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, long long rows, int C,

@@ -338,6 +338,8 @@ class MsgChnModel_Adapt(object):
                 options.update(trainable_head=1, skip_dec3=1)
             eng = MsgChnEngine(n, h, w, self.prepare_mode, state, self._grad_views, self._m_views, self._v_views,
                                options=options, adam_hyper=self._adam_hyper)
+            if getattr(self, '_comm', None) is not None:      # shared-model mode (sharding.enable_shared_model): every engine joins it
+                eng.set_comm(self._comm)
             self._engines[key] = eng
         return eng
 

@@ -11,7 +11,7 @@ sample and transform (`float(factors[b])`).
 Also native: the per-sample rotation (torchvision `functional.rotate` = affine grid + grid_sample; the angle comes from
 `np.random.rand`, as in the reference) and resize-and-crop (`functional.resize` + crop) -- with these, every augmentation the shipped
 adaptation scripts enable (bash/adapt/adapt_msgchn_*.sh: brightness, contrast, saturation, horizontal flip, rotate 5, resize-and-crop
-1.0 .. 1.5) runs in the library.  Crop-and-pad, resize-and-pad, random crop to shape, gamma / hue jitter, noise and point removal are
+1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Crop-and-pad, resize-and-pad, gamma / hue jitter, noise and point removal are
 not implemented: configuring one raises NotImplementedError at construction (no silent fallback)."""
 import ctypes
 import math
@@ -46,7 +46,7 @@ class Transforms(object):
             'random_gamma': -1 not in random_gamma, 'random_hue': -1 not in random_hue,
             'random_noise': random_noise_type != 'none' and random_noise_spread > -1,
             'random_remove_patch_percent_range': -1 not in random_remove_patch_percent_range,
-            'random_crop_to_shape': -1 not in random_crop_to_shape, 'random_crop_and_pad': -1 not in random_crop_and_pad,
+            'random_crop_and_pad': -1 not in random_crop_and_pad,
             'random_resize_and_pad': -1 not in random_resize_and_pad,
             'resize_scaling_depth': bool(resize_scaling_depth) and -1 not in random_resize_and_crop,
         }
@@ -57,6 +57,10 @@ class Transforms(object):
         self.do_image_normalization = normalized_image_range is not None
         self.do_random_horizontal_flip = 'horizontal' in random_flip_type
         self.do_random_vertical_flip = 'vertical' in random_flip_type
+        self.do_random_crop_to_shape = -1 not in random_crop_to_shape
+        self.random_crop_to_shape = list(random_crop_to_shape)
+        if self.do_random_crop_to_shape and len(random_crop_to_shape) not in (2, 4):
+            raise ValueError('Unsupported input for random crop to shape: {}'.format(random_crop_to_shape))
         self.do_random_rotate = random_rotate_max > 0
         self.random_rotate_max = random_rotate_max
         self.do_random_resize_and_crop = -1 not in random_resize_and_crop
@@ -111,6 +115,26 @@ class Transforms(object):
             images_arr = [im.float() for im in images_arr]
         if n_channel == 1:
             images_arr = [im[..., 0:1, :, :] for im in images_arr]
+        intrinsics_arr = list(intrinsics_arr)
+        if self.do_random_crop_to_shape:                                                                         # :337-383
+            rdev = self.rand_device if self.rand_device is not None else device
+            # `do and rand(1) <= 0.5 or range`: the roll is drawn in both forms; two numbers = crop to that shape half of the time, four = always
+            roll = bool(torch.rand(1, device=rdev) <= 0.50)
+            if len(self.random_crop_to_shape) == 2:
+                do_crop = roll
+                ch, cw = self.random_crop_to_shape
+            else:
+                do_crop = True
+                ch = int(np.random.randint(low=self.random_crop_to_shape[0], high=self.random_crop_to_shape[2] + 1))
+                cw = int(np.random.randint(low=self.random_crop_to_shape[1], high=self.random_crop_to_shape[3] + 1))
+            if do_crop:
+                n_height, n_width = images_arr[0].shape[-2:]
+                start_y = torch.randint(low=0, high=n_height - ch + 1, size=(n_batch,), device=rdev)
+                start_x = torch.randint(low=0, high=n_width - cw + 1, size=(n_batch,), device=rdev)
+                sy, sx = (t.to(device=device, dtype=torch.int32).contiguous() for t in (start_y, start_x))
+                images_arr = [self._crop(im, ch, cw, sy, sx) for im in images_arr]
+                off = torch.ones(n_batch)
+                intrinsics_arr = self._adjust_intrinsics(intrinsics_arr, x_offsets=off * float(n_width - cw), y_offsets=off * float(n_height - ch))
         do_h = do_v = None
         if self.do_random_horizontal_flip:                                                                       # :386-394
             do_h = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8).contiguous()
@@ -119,7 +143,6 @@ class Transforms(object):
         if do_h is not None or do_v is not None:
             images_arr = [self._flip(im, do_h, do_v) for im in images_arr]
         n_height, n_width = images_arr[0].shape[-2:]
-        intrinsics_arr = list(intrinsics_arr)
         modes = self._modes(interpolation_modes, len(images_arr))
         if self.do_random_rotate:                                                                                # :406-423
             do_rotate = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8).contiguous()
@@ -179,6 +202,14 @@ class Transforms(object):
             theta = np.array([[d, -bb, 0.0], [-c, a, 0.0]], dtype=np.float32)
             resc = theta.T / half                                              # [3, 2]
             out[b, :3], out[b, 3:] = resc[:, 0], resc[:, 1]
+        return out
+
+    @staticmethod
+    def _crop(images, ch, cw, sy, sx):
+        images = images.float().contiguous()
+        n, c, h, w = images.shape
+        out = torch.empty((n, c, ch, cw), dtype=torch.float32, device=images.device)
+        check(_lib.lib().ptta_augment_crop(ptr(images), ptr(out), n, c, h, w, ch, cw, ptr(sy), ptr(sx), _stream()), 'augment_crop')
         return out
 
     @staticmethod
