@@ -25,6 +25,11 @@ CASES = [
          ctor=dict(normalized_image_range=IMAGENET, random_saturation=[0.6, 1.4])),
     dict(name='photo_bright_pm1', seed=14, n=5, h=12, w=36, prob=1.0, kinds=['image'],
          ctor=dict(normalized_image_range=[-1, 1], random_brightness=[0.6, 1.4])),
+    dict(name='photo_gamma', seed=25, n=6, h=16, w=24, prob=1.0, kinds=['image'],
+         ctor=dict(normalized_image_range=[0, 1], random_brightness=[0.6, 1.4], random_contrast=[0.6, 1.4], random_gamma=[0.6, 1.6],
+                   random_saturation=[0.6, 1.4])),
+    dict(name='photo_flat_imagenet', seed=26, n=3, h=12, w=20, prob=1.0, kinds=['image'],
+         ctor=dict(normalized_image_range=[0.485, 0.456, 0.406, 0.229, 0.224, 0.225], random_contrast=[0.6, 1.4])),
     dict(name='norm_only', seed=15, n=2, h=12, w=20, prob=1.0, kinds=['image'], ctor=dict(normalized_image_range=[0, 1])),
     dict(name='flip_hv', seed=16, n=6, h=14, w=22, prob=1.0, kinds=['image', 'depth', 'depth', 'depth'],
          ctor=dict(random_flip_type=['horizontal', 'vertical'])),

@@ -16,7 +16,7 @@ def draws(n_batch, cfg, probability, rand=lambda n: torch.rand(n)):
     """the reference's random draws, in its order (T:229-331, 386-404); cfg: dict with optional 'brightness' / 'contrast' /
     'saturation' ranges and 'flip' = subset of ('horizontal', 'vertical')"""
     d = {'do': rand(n_batch) <= probability}
-    for name, ge in (('brightness', True), ('contrast', False), ('saturation', False)):
+    for name, ge in (('brightness', True), ('contrast', False), ('gamma', False), ('saturation', False)):       # T:242-301 (hue would sit before saturation)
         if name in cfg:
             roll = rand(n_batch)
             d['do_' + name] = torch.logical_and(d['do'], roll >= 0.50 if ge else roll <= 0.50)
@@ -59,10 +59,10 @@ def draws(n_batch, cfg, probability, rand=lambda n: torch.rand(n)):
 
 def apply(images_arr, cfg, d, normalized_image_range=None, interpolation_modes=('nearest',)):
     images_arr = [im.clone() for im in images_arr]
-    photometric = any(k in cfg for k in ('brightness', 'contrast', 'saturation'))
+    photometric = any(k in cfg for k in ('brightness', 'contrast', 'saturation'))        # gamma alone does not trigger the cast (T:102-106)
     if photometric:
         images_arr = [im.to(torch.uint8) if torch.is_floating_point(im) else im for im in images_arr]          # T:236-240
-    for name, fn in (('brightness', functional.adjust_brightness), ('contrast', functional.adjust_contrast),
+    for name, fn in (('brightness', functional.adjust_brightness), ('contrast', functional.adjust_contrast), ('gamma', functional.adjust_gamma),
                      ('saturation', functional.adjust_saturation)):
         if name in cfg:
             for images in images_arr:

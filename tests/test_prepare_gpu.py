@@ -265,3 +265,47 @@ def test_graph_replay_equals_eager(stage):
     sa, sb = a.state_dict(), b.state_dict()
     for k in sa:
         assert torch.equal(sa[k], sb[k]), k
+
+
+@pytest.mark.parametrize('stage', ['init', 'head'])
+def test_checkpoint_round_trip_of_a_preparation_run(stage, tmp_path):
+    """save_model / restore_model in the middle of a stage (the reference's checkpoint format, src/msg_chn_model_adapt.py:482-545, with the
+    optimiser state of the stage's parameter list -- proj.* + pred.* for stage 2, of which only pred.* carries moments): 2 steps, save,
+    restore into a fresh model, 2 more steps == 4 uninterrupted steps, bit for bit; the file also loads into torch.optim.Adam"""
+    case = dict(stage=stage, prepare_mode='meta_selfsup_seq_2layers_ema', init_mode='meta_seq_2layers', ckpt='kitti_2layers_a', dataset='kitti',
+                n=1, h=48, w=80, lr=1e-3, max_input_depth=80.0, seq_seed=71, seed=9)
+    sd0, fresh = prep_initial_state(case)
+
+    def new_model():
+        m, params = make_prep_model(case, sd0)
+        if stage == 'init':
+            m.load_state_dict({k: v for k, v in sd0.items() if k not in fresh}, strict=False)
+        return m, params
+
+    def step(m, t):
+        image, sparse, dense = prep_frame(case, t)
+        if stage == 'init':
+            m.init_step(image.to(DEV), sparse.to(DEV), dense.to(DEV), case['lr'])
+        else:
+            m.head_step(image.to(DEV), sparse.to(DEV), case['lr'])
+    a, _ = new_model()
+    for t in range(4):
+        step(a, t)
+    b, _ = new_model()
+    for t in range(2):
+        step(b, t)
+    path = str(tmp_path / 'prep.pth')
+    b.save_model(path, 2, None)
+    ckpt = torch.load(path, map_location='cpu', weights_only=False)
+    n_handed = 12 if stage == 'head' else len(b.model._adapt_names)
+    assert len(ckpt['optimizer']['param_groups'][0]['params']) == n_handed
+    assert len(ckpt['optimizer']['state']) == len(b.model._adapt_names)          # moments only for the tensors that were stepped
+    c, params = new_model()
+    opt = torch.optim.Adam(params, lr=case['lr'])
+    _, train_step = c.restore_model(path, opt)                                   # loads into the driver's optimiser as well
+    assert train_step == 2 and c.model.adam_step_count() == 2
+    for t in range(2, 4):
+        step(c, t)
+    sa, sc = a.state_dict(), c.state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sc[k]), k

@@ -13,10 +13,18 @@ from oracle.gen_golden_transforms import case_inputs
 FIX = torch.load(os.path.join(GOLDEN_DIR, 'transforms.pt'), weights_only=False)['fixtures']
 
 
+def nested_range(rng):
+    """the constructor's own re-shaping of a flat mean..., std... list (src/transforms.py:73-80)"""
+    if rng is not None and len(rng) > 2:
+        k = len(rng) // 2
+        return [tuple(rng[:k]), tuple(rng[k:])]
+    return rng
+
+
 def case_cfg(case):
     c = case['ctor']
     cfg = {}
-    for k in ('brightness', 'contrast', 'saturation'):
+    for k in ('brightness', 'contrast', 'gamma', 'saturation'):
         if 'random_' + k in c:
             cfg[k] = c['random_' + k]
     if 'random_flip_type' in c:
@@ -40,7 +48,7 @@ def test_oracle_equals_reference_transforms(name):
     cfg = case_cfg(case)
     np.random.seed(case['seed'])
     d = TO.draws(case['n'], cfg, case['prob'])
-    outs = TO.apply(inputs, cfg, d, case['ctor'].get('normalized_image_range'), case.get('modes', ('nearest',)))
+    outs = TO.apply(inputs, cfg, d, nested_range(case['ctor'].get('normalized_image_range')), case.get('modes', ('nearest',)))
     assert len(outs) == len(fx['outputs'])
     for got, want in zip(outs, fx['outputs']):
         assert got.dtype == want.dtype and torch.equal(got, want)

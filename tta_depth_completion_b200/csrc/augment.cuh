@@ -3,6 +3,7 @@
 //   sample with python-float factors): the fp32 [0,255] image is truncated to uint8 (`images.to(torch.uint8)`, :240), then
 //       brightness  u <- trunc(clamp(f u))
 //       contrast    u <- trunc(clamp(f u + (1 - f) mean(gray(u))))        gray = trunc(0.2989 r + 0.587 g + 0.114 b)
+//       gamma       u <- trunc(255.999 clamp((u / 255) ^ g, 0, 1))          (torchvision adjust_gamma: uint8 -> float -> pow -> uint8)
 //       saturation  u <- trunc(clamp(f u + (1 - f) gray(u)))
 //   each only for the samples whose flag is set, each on the uint8 result of the previous one (the reference runs them as separate
 //   tensor ops: every product and sum below is rounded on its own, no fused multiply-add), then `.float()` and the image
@@ -21,6 +22,7 @@ struct PhotoParams {
     const float* in; float* out;
     const unsigned char *do_b, *do_c, *do_s;      // [N] flags (nullptr = transform not configured)
     const float *f_b, *f_c, *f_s;                 // [N] factors, fp32 as drawn
+    const unsigned char* do_g; const float* f_g;  // gamma jitter (between contrast and saturation, as in the reference)
     unsigned long long* gray_sum;                 // [N] (contrast only)
     int N, HW;
     int quantize;                                 // images.to(uint8) happens whenever any photometric transform is configured
@@ -88,6 +90,14 @@ __global__ void __launch_bounds__(256) photo_apply_kernel(const PhotoParams p) {
     const float omb = photo_one_minus(fb), omc = photo_one_minus(fc), oms = photo_one_minus(fs);
     // after the uint8 truncation a channel holds one of 256 values: the normalisation (IEEE divisions, as torch's `/ 255.0` and
     // `normalize`) is tabulated once per block instead of being evaluated 12 times per thread and iteration
+    // gamma acts on one of 256 channel values: tabulated per block (one powf per entry instead of three per pixel)
+    __shared__ float glut[256];
+    const bool gamma = p.do_g && p.do_g[n];
+    if (gamma) {
+        const float x = __fdiv_rn((float)threadIdx.x, 255.f);
+        const float y = fminf(fmaxf(powf(x, p.f_g[n]), 0.f), 1.f);
+        glut[threadIdx.x] = truncf(__fmul_rn(y, 255.999f));
+    }
     __shared__ float lut[3][256];
     const bool use_lut = p.quantize && p.norm_mode != 0;
     if (use_lut) {
@@ -99,8 +109,8 @@ __global__ void __launch_bounds__(256) photo_apply_kernel(const PhotoParams p) {
             else if (p.norm_mode == 3) x = __fdiv_rn(__fsub_rn(x, p.mean[k]), p.std[k]);
             lut[k][threadIdx.x] = x;
         }
-        __syncthreads();
     }
+    __syncthreads();
     for (int i = (blockIdx.x * 256 + threadIdx.x) * VEC; i < p.HW; i += gridDim.x * 256 * VEC) {
         float c[3][VEC];
 #pragma unroll
@@ -120,6 +130,10 @@ __global__ void __launch_bounds__(256) photo_apply_kernel(const PhotoParams p) {
                 if (contrast) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) c[k][v] = photo_blend(c[k][v], mean, fc, omc);
+                }
+                if (gamma) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) c[k][v] = glut[(int)c[k][v]];
                 }
                 if (sat) {
                     const float gr = photo_gray(c[0][v], c[1][v], c[2][v]);

@@ -453,14 +453,25 @@ class MsgChnModel_Adapt(object):
         """number of optimiser steps the fused Adam has taken (device-resident counter shared by the engines of all shapes)"""
         return int(self._adam_hyper.view(torch.int32)[self._ADAM_STEP_WORD].item())
 
+    def _optimizer_names(self):
+        """state-dict keys of the tensors the reference hands to torch.optim.Adam in this stage, in its order"""
+        if self._trainable == 'head':
+            return [k for k in self._sd if k.startswith(('proj.', 'pred.')) and k.endswith(_PARAM_SUFFIX)]
+        return list(self._adapt_names)
+
     def load_adam_state(self, opt_sd):
         """torch.optim.Adam state dict (as written by the reference's save_model) -> the fused Adam's flat moment buffers and step
         counter, so that `tta_step` continues the checkpointed run exactly as `optimizer.step()` would"""
         ids = [i for g in opt_sd['param_groups'] for i in g['params']]
-        if len(ids) != len(self._adapt_names):
-            raise RuntimeError('optimizer state covers %d tensors, the adapted set has %d' % (len(ids), len(self._adapt_names)))
+        names = self._optimizer_names()
+        if len(ids) != len(names):
+            raise RuntimeError('optimizer state covers %d tensors, this stage hands %d to Adam' % (len(ids), len(names)))
         step = 0
-        for i, k in zip(ids, self._adapt_names):
+        for i, k in zip(ids, names):
+            if k not in self._m_views:          # stage 2: proj.* is handed to Adam but never receives a gradient (no state, never stepped)
+                if opt_sd['state'].get(i) is not None:
+                    raise RuntimeError('optimizer state holds moments for %s, which the native stage-2 step does not train' % k)
+                continue
             st = opt_sd['state'].get(i)
             if st is None:                      # tensor never stepped
                 self._m_views[k].zero_(); self._v_views[k].zero_()
@@ -476,7 +487,9 @@ class MsgChnModel_Adapt(object):
     def adam_state_dict(self, lr=0.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         """the fused Adam's state in torch.optim.Adam's own state_dict format (built by a real torch.optim.Adam, so every key the
         installed torch expects is there)"""
-        params = list(self._param_objs.values())
+        # the parameter list the reference's optimiser was built over: the adapted tensors, or proj.* + pred.* for stage 2 (src/head_main.py:268)
+        params = [self._param_objs[k] if k in self._param_objs else torch.nn.Parameter(self._sd[k], requires_grad=True)
+                  for k in self._optimizer_names()]
         opt = torch.optim.Adam(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         step = self.adam_step_count()
         if step > 0:

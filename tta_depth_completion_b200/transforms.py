@@ -1,5 +1,6 @@
 """Drop-in mirror of the reference's `Transforms` (src/transforms.py:8-668) for the augmentations whose arithmetic runs in
-libptta_b200.so: the photometric chain (brightness / contrast / saturation + image normalisation) and the per-sample flips.
+libptta_b200.so: the photometric chain (brightness / contrast / gamma / saturation + image normalisation) and the geometric transforms
+listed below.
 
 Same constructor arguments, same `transform(images_arr, intrinsics_arr, padding_modes, interpolation_modes,
 random_transform_probability)` call and return convention, and -- the part that keeps runs comparable -- the SAME random draws: every
@@ -11,7 +12,7 @@ sample and transform (`float(factors[b])`).
 Also native: the per-sample rotation (torchvision `functional.rotate` = affine grid + grid_sample; the angle comes from
 `np.random.rand`, as in the reference) and resize-and-crop (`functional.resize` + crop) -- with these, every augmentation the shipped
 adaptation scripts enable (bash/adapt/adapt_msgchn_*.sh: brightness, contrast, saturation, horizontal flip, rotate 5, resize-and-crop
-1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Crop-and-pad, resize-and-pad, gamma / hue jitter, noise and point removal are
+1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Gamma jitter is native too.  Crop-and-pad, resize-and-pad, hue jitter, noise and point removal are
 not implemented: configuring one raises NotImplementedError at construction (no silent fallback)."""
 import ctypes
 import math
@@ -35,6 +36,9 @@ class Transforms(object):
                  random_remove_patch_percent_range=[-1, -1], random_remove_patch_size=[1, 1], random_crop_to_shape=[-1, -1],
                  random_flip_type=['none'], random_rotate_max=0, random_crop_and_pad=[-1, -1], random_resize_and_crop=[-1, -1],
                  random_resize_and_pad=[-1, -1], resize_scaling_depth=False):
+        if normalized_image_range is not None and len(normalized_image_range) > 2:       # flat mean..., std... list (src/transforms.py:73-80)
+            k = len(normalized_image_range) // 2
+            normalized_image_range = [tuple(normalized_image_range[:k]), tuple(normalized_image_range[k:])]
         self.normalized_image_range = normalized_image_range
         self.do_random_brightness = -1 not in random_brightness
         self.random_brightness = random_brightness
@@ -42,8 +46,10 @@ class Transforms(object):
         self.random_contrast = random_contrast
         self.do_random_saturation = -1 not in random_saturation
         self.random_saturation = random_saturation
+        self.do_random_gamma = -1 not in random_gamma
+        self.random_gamma = random_gamma
         unsupported = {
-            'random_gamma': -1 not in random_gamma, 'random_hue': -1 not in random_hue,
+            'random_hue': -1 not in random_hue,
             'random_noise': random_noise_type != 'none' and random_noise_spread > -1,
             'random_remove_patch_percent_range': -1 not in random_remove_patch_percent_range,
             'random_crop_and_pad': -1 not in random_crop_and_pad,
@@ -53,6 +59,7 @@ class Transforms(object):
         bad = [k for k, v in unsupported.items() if v]
         if bad:
             raise NotImplementedError('Transforms options without a native kernel: %s (DESIGN.md, scope table f2)' % ', '.join(bad))
+        # as in the reference, gamma alone does not trigger the uint8 cast (src/transforms.py:74-78 leaves it out of do_photometric_transforms)
         self.do_photometric_transforms = self.do_random_brightness or self.do_random_contrast or self.do_random_saturation
         self.do_image_normalization = normalized_image_range is not None
         self.do_random_horizontal_flip = 'horizontal' in random_flip_type
@@ -100,6 +107,7 @@ class Transforms(object):
         flags, factors = {}, {}
         for name, enabled, rng, ge in (('b', self.do_random_brightness, self.random_brightness, True),
                                        ('c', self.do_random_contrast, self.random_contrast, False),
+                                       ('g', self.do_random_gamma, self.random_gamma, False),          # (hue would be drawn here)
                                        ('s', self.do_random_saturation, self.random_saturation, False)):
             if not enabled:
                 continue
@@ -260,7 +268,7 @@ class Transforms(object):
         ws = torch.empty(n, dtype=torch.int64, device=images.device) if 'c' in flags else None
         check(_lib.lib().ptta_augment_photometric(
             ptr(images), ptr(out), n, h, w, ptr(flags.get('b')), ptr(factors.get('b')), ptr(flags.get('c')), ptr(factors.get('c')),
-            ptr(flags.get('s')), ptr(factors.get('s')), 1 if self.do_photometric_transforms else 0, mode,
+            ptr(flags.get('s')), ptr(factors.get('s')), ptr(flags.get('g')), ptr(factors.get('g')), 1 if self.do_photometric_transforms else 0, mode,
             _FLOAT3(*mean) if mean else None, _FLOAT3(*std) if std else None, ptr(ws), _stream()), 'augment_photometric')
         return out
 
