@@ -77,6 +77,7 @@ class Transforms(object):
             assert self.random_resize_and_crop_min >= 1.0
         self._norm = self._normalisation(normalized_image_range)
         self.rand_device = None        # where the draws are made; None = the images' device, as in the reference
+        self._streams = {}
 
     @staticmethod
     def _normalisation(rng):
@@ -94,6 +95,15 @@ class Transforms(object):
     def _rand(self, n, device):
         return torch.rand(n, device=self.rand_device if self.rand_device is not None else device).to(device)
 
+    def _rng_stream(self, device):
+        """The draws (tiny tensors, two host reads for the resize sizes) run on a stream of their own: the host then waits for THEM, not
+        for whatever the caller's stream still has queued (the previous frame's adaptation step).  The generator is advanced on the host
+        at call time, so the values do not depend on the stream."""
+        st = self._streams.get(device)
+        if st is None:
+            st = self._streams[device] = torch.cuda.Stream(device)
+        return st
+
     def transform(self, images_arr, intrinsics_arr=[], padding_modes=['constant'], interpolation_modes=['nearest'],
                   random_transform_probability=0.00):
         images_arr = list(images_arr)
@@ -103,76 +113,36 @@ class Transforms(object):
         if images_arr[0].ndim != 4:
             raise ValueError('Unsupported number of dimensions: {}'.format(images_arr[0].ndim))
         n_batch, n_channel = images_arr[0].shape[:2]
-        do_random_transform = self._rand(n_batch, device) <= random_transform_probability                       # :229-230
-        flags, factors = {}, {}
-        for name, enabled, rng, ge in (('b', self.do_random_brightness, self.random_brightness, True),
-                                       ('c', self.do_random_contrast, self.random_contrast, False),
-                                       ('g', self.do_random_gamma, self.random_gamma, False),          # (hue would be drawn here)
-                                       ('s', self.do_random_saturation, self.random_saturation, False)):
-            if not enabled:
-                continue
-            roll = self._rand(n_batch, device)
-            # brightness is applied when its roll is >= 0.5 (:243-245), the others when it is <= 0.5 (:256-258, :295-297)
-            flags[name] = torch.logical_and(do_random_transform, roll >= 0.50 if ge else roll <= 0.50).to(torch.uint8).contiguous()
-            values = self._rand(n_batch, device)
-            lo, hi = rng
-            factors[name] = ((hi - lo) * values + lo).contiguous()
+        n_height, n_width = images_arr[0].shape[-2:]
+        rdev = self.rand_device if self.rand_device is not None else device
+        cur = torch.cuda.current_stream(device)
+        plan = self._draw(n_batch, n_height, n_width, device, rdev, random_transform_probability)
+        for t in plan['device_tensors']:
+            t.record_stream(cur)                       # allocated on the draw stream, read by kernels on the caller's stream
+        cur.wait_stream(self._rng_stream(device))
+        # ---- kernels, in the reference's order ----
         if self.do_photometric_transforms or self.do_image_normalization:
-            images_arr = [self._photometric(im, flags, factors) for im in images_arr]
+            images_arr = [self._photometric(im, plan['flags'], plan['factors']) for im in images_arr]
         else:
             images_arr = [im.float() for im in images_arr]
         if n_channel == 1:
             images_arr = [im[..., 0:1, :, :] for im in images_arr]
         intrinsics_arr = list(intrinsics_arr)
-        if self.do_random_crop_to_shape:                                                                         # :337-383
-            rdev = self.rand_device if self.rand_device is not None else device
-            # `do and rand(1) <= 0.5 or range`: the roll is drawn in both forms; two numbers = crop to that shape half of the time, four = always
-            roll = bool(torch.rand(1, device=rdev) <= 0.50)
-            if len(self.random_crop_to_shape) == 2:
-                do_crop = roll
-                ch, cw = self.random_crop_to_shape
-            else:
-                do_crop = True
-                ch = int(np.random.randint(low=self.random_crop_to_shape[0], high=self.random_crop_to_shape[2] + 1))
-                cw = int(np.random.randint(low=self.random_crop_to_shape[1], high=self.random_crop_to_shape[3] + 1))
-            if do_crop:
-                n_height, n_width = images_arr[0].shape[-2:]
-                start_y = torch.randint(low=0, high=n_height - ch + 1, size=(n_batch,), device=rdev)
-                start_x = torch.randint(low=0, high=n_width - cw + 1, size=(n_batch,), device=rdev)
-                sy, sx = (t.to(device=device, dtype=torch.int32).contiguous() for t in (start_y, start_x))
-                images_arr = [self._crop(im, ch, cw, sy, sx) for im in images_arr]
-                off = torch.ones(n_batch)
-                intrinsics_arr = self._adjust_intrinsics(intrinsics_arr, x_offsets=off * float(n_width - cw), y_offsets=off * float(n_height - ch))
-        do_h = do_v = None
-        if self.do_random_horizontal_flip:                                                                       # :386-394
-            do_h = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8).contiguous()
-        if self.do_random_vertical_flip:                                                                         # :396-404
-            do_v = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8).contiguous()
-        if do_h is not None or do_v is not None:
-            images_arr = [self._flip(im, do_h, do_v) for im in images_arr]
-        n_height, n_width = images_arr[0].shape[-2:]
+        if plan.get('crop'):                                                                                     # :337-383
+            ch, cw, sy, sx = plan['crop']
+            images_arr = [self._crop(im, ch, cw, sy, sx) for im in images_arr]
+            off = torch.ones(n_batch)
+            intrinsics_arr = self._adjust_intrinsics(intrinsics_arr, x_offsets=off * float(n_width - cw), y_offsets=off * float(n_height - ch))
+            n_height, n_width = ch, cw
+        if plan.get('do_h') is not None or plan.get('do_v') is not None:                                         # :386-404
+            images_arr = [self._flip(im, plan.get('do_h'), plan.get('do_v')) for im in images_arr]
         modes = self._modes(interpolation_modes, len(images_arr))
-        if self.do_random_rotate:                                                                                # :406-423
-            do_rotate = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8).contiguous()
-            values = np.random.rand(n_batch)                                # the reference draws the angles from numpy's global generator
-            angles = (2 * self.random_rotate_max) * values + (-self.random_rotate_max)
-            theta = torch.from_numpy(self._rotation_grid_matrix(angles, n_height, n_width)).to(device)
+        if 'rotate' in plan:                                                                                     # :406-423
+            do_rotate, theta = plan['rotate']
             images_arr = [self._resample('rotate', im, m, do_rotate, theta) for im, m in zip(images_arr, modes)]
-        if self.do_random_resize_and_crop:                                                                       # :425-502
-            do_rs = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8).contiguous()
-            rdev = self.rand_device if self.rand_device is not None else device
-            r_height = torch.randint(low=int(self.random_resize_and_crop_min * n_height), high=int(self.random_resize_and_crop_max * n_height),
-                                     size=(n_batch,), device=rdev)
-            r_width = torch.randint(low=int(self.random_resize_and_crop_min * n_width), high=int(self.random_resize_and_crop_max * n_width),
-                                    size=(n_batch,), device=rdev)
+        if 'resize' in plan:                                                                                     # :425-502
+            do_rs, r_height, r_width, args = plan['resize']
             intrinsics_arr = self._adjust_intrinsics(intrinsics_arr, x_scales=(r_width / n_width), y_scales=(r_height / n_height))
-            rh, rw = r_height.tolist(), r_width.tolist()                   # one host read (the reference makes 2 N of them, :463-477)
-            start_y, start_x = [], []
-            for b in range(n_batch):
-                start_y.append(torch.randint(low=0, high=rh[b] - n_height + 1, size=(1,), device=rdev))
-                start_x.append(torch.randint(low=0, high=rw[b] - n_width + 1, size=(1,), device=rdev))
-            start_y, start_x = torch.cat(start_y, dim=0), torch.cat(start_x, dim=0)
-            args = [t.to(device=device, dtype=torch.int32).contiguous() for t in (r_height, r_width, start_y, start_x)]
             images_arr = [self._resample('resize_crop', im, m, do_rs, *args) for im, m in zip(images_arr, modes)]
             intrinsics_arr = self._adjust_intrinsics(intrinsics_arr, x_offsets=(r_width - n_width), y_offsets=(r_height - n_height))
         outputs = []
@@ -181,6 +151,70 @@ class Transforms(object):
         if len(intrinsics_arr) > 0:
             outputs.append(list(intrinsics_arr))
         return outputs[0] if len(outputs) == 1 else outputs
+
+    def _draw(self, n_batch, n_height, n_width, device, rdev, probability):
+        """every random number of one `transform` call, drawn in the reference's order (src/transforms.py:229-480) on the draw stream;
+        none of them depends on image data, only on the shapes"""
+        plan = {'flags': {}, 'factors': {}, 'device_tensors': []}
+
+        def keep(t):
+            t = t.contiguous()
+            if t.is_cuda:
+                plan['device_tensors'].append(t)
+            return t
+        with torch.cuda.stream(self._rng_stream(device)):
+            do_random_transform = self._rand(n_batch, device) <= probability                                     # :229-230
+            for name, enabled, rng, ge in (('b', self.do_random_brightness, self.random_brightness, True),
+                                           ('c', self.do_random_contrast, self.random_contrast, False),
+                                           ('g', self.do_random_gamma, self.random_gamma, False),      # (hue would be drawn here)
+                                           ('s', self.do_random_saturation, self.random_saturation, False)):
+                if not enabled:
+                    continue
+                roll = self._rand(n_batch, device)
+                # brightness is applied when its roll is >= 0.5 (:243-245), the others when it is <= 0.5 (:256-258, :295-297)
+                plan['flags'][name] = keep(torch.logical_and(do_random_transform, roll >= 0.50 if ge else roll <= 0.50).to(torch.uint8))
+                values = self._rand(n_batch, device)
+                lo, hi = rng
+                plan['factors'][name] = keep((hi - lo) * values + lo)
+            if self.do_random_crop_to_shape:                                                                     # :337-366
+                # `do and rand(1) <= 0.5 or range`: the roll is drawn in both forms; two numbers = crop to that shape half of the time, four = always
+                roll = bool(torch.rand(1, device=rdev) <= 0.50)
+                if len(self.random_crop_to_shape) == 2:
+                    do_crop = roll
+                    ch, cw = self.random_crop_to_shape
+                else:
+                    do_crop = True
+                    ch = int(np.random.randint(low=self.random_crop_to_shape[0], high=self.random_crop_to_shape[2] + 1))
+                    cw = int(np.random.randint(low=self.random_crop_to_shape[1], high=self.random_crop_to_shape[3] + 1))
+                if do_crop:
+                    start_y = torch.randint(low=0, high=n_height - ch + 1, size=(n_batch,), device=rdev)
+                    start_x = torch.randint(low=0, high=n_width - cw + 1, size=(n_batch,), device=rdev)
+                    plan['crop'] = (ch, cw, keep(start_y.to(device=device, dtype=torch.int32)), keep(start_x.to(device=device, dtype=torch.int32)))
+                    n_height, n_width = ch, cw
+            if self.do_random_horizontal_flip:                                                                   # :386-394
+                plan['do_h'] = keep(torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8))
+            if self.do_random_vertical_flip:                                                                     # :396-404
+                plan['do_v'] = keep(torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8))
+            if self.do_random_rotate:                                                                            # :406-416
+                do_rotate = keep(torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8))
+                values = np.random.rand(n_batch)                            # the reference draws the angles from numpy's global generator
+                angles = (2 * self.random_rotate_max) * values + (-self.random_rotate_max)
+                plan['rotate'] = (do_rotate, keep(torch.from_numpy(self._rotation_grid_matrix(angles, n_height, n_width)).to(device)))
+            if self.do_random_resize_and_crop:                                                                   # :425-480
+                do_rs = keep(torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8))
+                r_height = torch.randint(low=int(self.random_resize_and_crop_min * n_height), high=int(self.random_resize_and_crop_max * n_height),
+                                         size=(n_batch,), device=rdev)
+                r_width = torch.randint(low=int(self.random_resize_and_crop_min * n_width), high=int(self.random_resize_and_crop_max * n_width),
+                                        size=(n_batch,), device=rdev)
+                rh, rw = r_height.tolist(), r_width.tolist()               # one host read (the reference makes 2 N of them, :463-477)
+                start_y, start_x = [], []
+                for b in range(n_batch):
+                    start_y.append(torch.randint(low=0, high=rh[b] - n_height + 1, size=(1,), device=rdev))
+                    start_x.append(torch.randint(low=0, high=rw[b] - n_width + 1, size=(1,), device=rdev))
+                start_y, start_x = torch.cat(start_y, dim=0), torch.cat(start_x, dim=0)
+                args = [keep(t.to(device=device, dtype=torch.int32)) for t in (r_height, r_width, start_y, start_x)]
+                plan['resize'] = (do_rs, keep(r_height), keep(r_width), args)
+        return plan
 
     # -- geometric helpers -----------------------------------------------------------------------------------
     @staticmethod
