@@ -282,8 +282,10 @@ int ptta_input_stage(const void* image_u8_hwc, const void* depth_u16, float* ima
 /* On-device augmentations of the adaptation / preparation loops (src/transforms.py; the drop-in mirror with the reference's RNG draw
  * order is tta_depth_completion_b200/transforms.py).
  * ptta_augment_photometric: src/transforms.py:236-333 + :669-712 on an fp32 [N,3,H,W] image in [0,255]: uint8 truncation, per-sample
- * brightness / contrast / gamma / saturation (the reference's order) as torchvision's tensor ops compute them (`_blend`, `rgb_to_grayscale`,
- * `adjust_gamma`; every product and sum rounded separately, uint8 truncation after each transform), `.float()`, normalisation (norm_mode 0: none, 1: /255, 2: 2x/255-1,
+ * brightness / contrast / gamma / hue / saturation (the reference's order) as torchvision's tensor ops compute them (`_blend`,
+ * `rgb_to_grayscale`, `adjust_gamma`, `adjust_hue`; every product and sum rounded separately, uint8 truncation after each transform),
+ * `.float()`, additive noise (`noise`: fp32 [N,3,H,W] drawn by the caller -- torch.randn / torch.rand, so the generator contract holds --
+ * added as x + spread * n, or spread * (n - 0.5) when noise_uniform), normalisation (norm_mode 0: none, 1: /255, 2: 2x/255-1,
  * 3: (x/255 - mean[c]) / std[c] with HOST arrays mean3 / std3).  Flag arrays: device uint8 [N] (NULL = transform not configured), factor
  * arrays: device fp32 [N].  quantize = 1 whenever any photometric transform is configured (the reference then casts to uint8 even for
  * samples that draw no transform).  workspace: 8 * n bytes, needed for the contrast transform (exact integer sum of the grey image).
@@ -291,8 +293,9 @@ int ptta_input_stage(const void* image_u8_hwc, const void* depth_u16, float* ima
 int ptta_augment_photometric(const float* image, float* out, int n, int h, int w, const unsigned char* do_brightness,
                              const float* f_brightness, const unsigned char* do_contrast, const float* f_contrast,
                              const unsigned char* do_saturation, const float* f_saturation, const unsigned char* do_gamma,
-                             const float* f_gamma, int quantize, int norm_mode, const float* mean3, const float* std3, void* workspace,
-                             ptta_stream_t stream);
+                             const float* f_gamma, const unsigned char* do_hue, const float* f_hue, const unsigned char* do_noise,
+                             const float* noise, float noise_spread, int noise_uniform, int quantize, int norm_mode,
+                             const float* mean3, const float* std3, void* workspace, ptta_stream_t stream);
 int ptta_augment_flip(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_hflip,
                       const unsigned char* do_vflip, ptta_stream_t stream);
 /* ptta_augment_rotate: src/transforms.py:406-423, 1036-1070 (torchvision functional.rotate, expand=False, fill=None = affine grid +

@@ -30,6 +30,15 @@ CASES = [
                    random_saturation=[0.6, 1.4])),
     dict(name='photo_flat_imagenet', seed=26, n=3, h=12, w=20, prob=1.0, kinds=['image'],
          ctor=dict(normalized_image_range=[0.485, 0.456, 0.406, 0.229, 0.224, 0.225], random_contrast=[0.6, 1.4])),
+    dict(name='photo_hue', seed=27, n=6, h=16, w=24, prob=1.0, kinds=['image'],
+         ctor=dict(normalized_image_range=[0, 1], random_hue=[-0.1, 0.1])),
+    dict(name='photo_all5', seed=28, n=8, h=16, w=24, prob=1.0, kinds=['image'],
+         ctor=dict(normalized_image_range=[0, 1], random_brightness=[0.6, 1.4], random_contrast=[0.6, 1.4], random_gamma=[0.7, 1.4],
+                   random_hue=[-0.5, 0.5], random_saturation=[0.6, 1.4])),
+    dict(name='noise_gaussian', seed=29, n=6, h=12, w=20, prob=1.0, kinds=['image'],
+         ctor=dict(normalized_image_range=[0, 1], random_noise_type='gaussian', random_noise_spread=4.0, random_saturation=[0.8, 1.2])),
+    dict(name='noise_uniform', seed=30, n=6, h=12, w=20, prob=1.0, kinds=['image'],
+         ctor=dict(normalized_image_range=[0, 255], random_noise_type='uniform', random_noise_spread=10.0)),
     dict(name='norm_only', seed=15, n=2, h=12, w=20, prob=1.0, kinds=['image'], ctor=dict(normalized_image_range=[0, 1])),
     dict(name='flip_hv', seed=16, n=6, h=14, w=22, prob=1.0, kinds=['image', 'depth', 'depth', 'depth'],
          ctor=dict(random_flip_type=['horizontal', 'vertical'])),

@@ -16,12 +16,22 @@ def draws(n_batch, cfg, probability, rand=lambda n: torch.rand(n)):
     """the reference's random draws, in its order (T:229-331, 386-404); cfg: dict with optional 'brightness' / 'contrast' /
     'saturation' ranges and 'flip' = subset of ('horizontal', 'vertical')"""
     d = {'do': rand(n_batch) <= probability}
-    for name, ge in (('brightness', True), ('contrast', False), ('gamma', False), ('saturation', False)):       # T:242-301 (hue would sit before saturation)
+    for name, ge in (('brightness', True), ('contrast', False), ('gamma', False), ('hue', False), ('saturation', False)):       # T:242-301
         if name in cfg:
             roll = rand(n_batch)
             d['do_' + name] = torch.logical_and(d['do'], roll >= 0.50 if ge else roll <= 0.50)
             lo, hi = cfg[name]
             d['f_' + name] = (hi - lo) * rand(n_batch) + lo
+    if 'noise' in cfg:                                                          # T:320-331, 839-875: one draw per tensor and flagged sample
+        kind, spread = cfg['noise']
+        d['do_noise'] = torch.logical_and(d['do'], rand(n_batch) <= 0.50)
+        d['noise'] = []
+        for shape in cfg['tensor_shapes']:
+            per = {}
+            for b in range(n_batch):
+                if d['do_noise'][b]:
+                    per[b] = torch.randn(*shape[1:]) if kind == 'gaussian' else torch.rand(*shape[1:])
+            d['noise'].append(per)
     if 'crop_to_shape' in cfg:                                                  # T:337-366
         spec = cfg['crop_to_shape']
         h, w = cfg['shape']
@@ -59,17 +69,22 @@ def draws(n_batch, cfg, probability, rand=lambda n: torch.rand(n)):
 
 def apply(images_arr, cfg, d, normalized_image_range=None, interpolation_modes=('nearest',)):
     images_arr = [im.clone() for im in images_arr]
-    photometric = any(k in cfg for k in ('brightness', 'contrast', 'saturation'))        # gamma alone does not trigger the cast (T:102-106)
+    photometric = any(k in cfg for k in ('brightness', 'contrast', 'hue', 'saturation'))        # gamma alone does not trigger the cast (T:102-106)
     if photometric:
         images_arr = [im.to(torch.uint8) if torch.is_floating_point(im) else im for im in images_arr]          # T:236-240
     for name, fn in (('brightness', functional.adjust_brightness), ('contrast', functional.adjust_contrast), ('gamma', functional.adjust_gamma),
-                     ('saturation', functional.adjust_saturation)):
+                     ('hue', functional.adjust_hue), ('saturation', functional.adjust_saturation)):
         if name in cfg:
             for images in images_arr:
                 for b in range(images.shape[0]):
                     if d['do_' + name][b]:
                         images[b, ...] = fn(images[b], d['f_' + name][b])                                        # T:714-837
     images_arr = [im.float() for im in images_arr]
+    if 'noise' in cfg:
+        kind, spread = cfg['noise']
+        for images, per in zip(images_arr, d['noise']):
+            for b, nz in per.items():
+                images[b, ...] = images[b] + spread * nz if kind == 'gaussian' else images[b] + spread * (nz - 0.5)
     rng = normalized_image_range
     if rng is not None:                                                                                            # T:669-712
         if rng == [0, 1]:

@@ -2,7 +2,7 @@
 src/transforms.py) against (a) the fixtures produced by the reference's own class and (b) the CPU oracle at the benchmark frame size.
 The draws are made on the CPU generator here (`rand_device`), so that both sides see the same random numbers.
 
-Stated tolerance: flips, brightness, saturation and every normalisation are BIT-EXACT.  The contrast transform blends with the mean of
+Stated tolerance: flips, crops, brightness, hue, saturation, additive noise and every normalisation are BIT-EXACT.  The contrast transform blends with the mean of
 the grey image: the native path sums the grey values exactly (integers), torch.mean accumulates in fp32 in an order of its own -- the two
 means differ by ~1e-7 relative, which moves a pixel by one uint8 step only when the blended value lands within ~1e-5 of an integer:
 at most 1e-4 of the values may differ, each by exactly one grey level.  Rotation / resize-and-crop resample in fp32: see
@@ -34,7 +34,7 @@ def level(rng):
     return 1 / 255.0 / min(rng[1])
 
 
-def compare(got, want, contrast, rng, what, max_frac=1e-4):
+def compare(got, want, contrast, rng, what, max_frac=1e-4, max_levels=1):
     got = got.cpu()
     assert got.shape == want.shape and got.dtype == want.dtype, what
     if not contrast:
@@ -42,7 +42,7 @@ def compare(got, want, contrast, rng, what, max_frac=1e-4):
         return 0.0
     diff = (got - want).abs()
     frac = float((diff > 0).float().mean())
-    assert frac <= max_frac and float(diff.max()) <= level(rng) * 1.0001 + 1e-6, (what, frac, float(diff.max()))
+    assert frac <= max_frac and float(diff.max()) <= max_levels * level(rng) * 1.0001 + 1e-6, (what, frac, float(diff.max()))
     return frac
 
 
@@ -73,8 +73,9 @@ def test_native_transforms_match_reference_fixture(name):
         else:
             # contrast (grey mean) and gamma (powf of the CPU fixture vs the device's) may move a value by one grey level
             soft = 'random_contrast' in case['ctor'] or 'random_gamma' in case['ctor']
+            # a one-level difference that enters the hue transform (RGB -> HSV -> RGB) can leave it as up to three levels
             compare(got, want, soft, nested_range(case['ctor'].get('normalized_image_range')), '%s[%d]' % (name, k),
-                    max_frac=2e-3 if 'random_gamma' in case['ctor'] else 1e-4)
+                    max_frac=2e-3 if 'random_gamma' in case['ctor'] else 1e-4, max_levels=3 if (soft and 'random_hue' in case['ctor']) else 1)
 
 
 def compare_resampled(got, want, what, max_bad=2e-3):
@@ -208,7 +209,7 @@ def test_unsupported_options_fail_loudly():
     from tta_depth_completion_b200.transforms import Transforms
     with pytest.raises(NotImplementedError, match='random_resize_and_pad'):
         Transforms(random_resize_and_pad=[0.5, 1.0])
-    with pytest.raises(NotImplementedError, match='random_hue'):
-        Transforms(random_hue=[-0.1, 0.1])
+    with pytest.raises(NotImplementedError, match='random_remove_patch_percent_range'):
+        Transforms(random_remove_patch_percent_range=[0.1, 0.2])
     with pytest.raises(NotImplementedError, match='random_crop_and_pad'):
         Transforms(random_crop_and_pad=[0.5, 1.0])

@@ -24,7 +24,10 @@ def nested_range(rng):
 def case_cfg(case):
     c = case['ctor']
     cfg = {}
-    for k in ('brightness', 'contrast', 'gamma', 'saturation'):
+    if c.get('random_noise_type', 'none') != 'none':
+        cfg['noise'] = (c['random_noise_type'], c['random_noise_spread'])
+        cfg['tensor_shapes'] = [(case['n'], 3 if kind == 'image' else 1, case['h'], case['w']) for kind in case['kinds']]
+    for k in ('brightness', 'contrast', 'gamma', 'hue', 'saturation'):
         if 'random_' + k in c:
             cfg[k] = c['random_' + k]
     if 'random_flip_type' in c:

@@ -4,7 +4,9 @@
 //       brightness  u <- trunc(clamp(f u))
 //       contrast    u <- trunc(clamp(f u + (1 - f) mean(gray(u))))        gray = trunc(0.2989 r + 0.587 g + 0.114 b)
 //       gamma       u <- trunc(255.999 clamp((u / 255) ^ g, 0, 1))          (torchvision adjust_gamma: uint8 -> float -> pow -> uint8)
+//       hue         (r, g, b) / 255 -> HSV -> h <- (h + f) mod 1 -> RGB -> trunc(255.999 x)  (torchvision adjust_hue: `_rgb2hsv`, `_hsv2rgb`)
 //       saturation  u <- trunc(clamp(f u + (1 - f) gray(u)))
+//   and, on the float image, additive noise (:839-875): x + spread * n with n drawn by torch (gaussian) or spread * (u - 0.5) (uniform)
 //   each only for the samples whose flag is set, each on the uint8 result of the previous one (the reference runs them as separate
 //   tensor ops: every product and sum below is rounded on its own, no fused multiply-add), then `.float()` and the image
 //   normalisation of :669-712.  One reduction pass (only for samples with the contrast flag: exact integer sum of the grey values)
@@ -23,6 +25,8 @@ struct PhotoParams {
     const unsigned char *do_b, *do_c, *do_s;      // [N] flags (nullptr = transform not configured)
     const float *f_b, *f_c, *f_s;                 // [N] factors, fp32 as drawn
     const unsigned char* do_g; const float* f_g;  // gamma jitter (between contrast and saturation, as in the reference)
+    const unsigned char* do_h; const float* f_h;  // hue jitter (after gamma, before saturation)
+    const unsigned char* do_n; const float* noise; float noise_spread; int noise_uniform;   // additive noise on the float image (before normalisation)
     unsigned long long* gray_sum;                 // [N] (contrast only)
     int N, HW;
     int quantize;                                 // images.to(uint8) happens whenever any photometric transform is configured
@@ -40,6 +44,50 @@ __device__ __forceinline__ float photo_blend(float u, float other, float ratio, 
     return photo_trunc(__fadd_rn(__fmul_rn(ratio, u), __fmul_rn(omr, other)));
 }
 __device__ __forceinline__ float photo_quant(float x) { return truncf(fminf(fmaxf(x, 0.f), 255.f)); }     // float -> uint8 cast of an in-range value
+
+// torchvision.transforms.functional_tensor.adjust_hue on one uint8 pixel, operation by operation (every elementwise tensor op of
+// `_rgb2hsv` / `_hsv2rgb` is one separately rounded fp32 operation here; the one-hot einsum of `_hsv2rgb` selects one value exactly)
+__device__ __forceinline__ float photo_remainder1(float x) {       // torch.remainder(x, 1.0)
+    float m = fmodf(x, 1.f);
+    if (m != 0.f && m < 0.f) m = __fadd_rn(m, 1.f);
+    return m;
+}
+__device__ __forceinline__ void photo_hue(float& r8, float& g8, float& b8, float hue) {
+    const float r = __fdiv_rn(r8, 255.f), g = __fdiv_rn(g8, 255.f), b = __fdiv_rn(b8, 255.f);
+    const float maxc = fmaxf(fmaxf(r, g), b), minc = fminf(fminf(r, g), b);
+    const bool eqc = maxc == minc;
+    const float cr = __fsub_rn(maxc, minc);
+    const float s = __fdiv_rn(cr, eqc ? 1.f : maxc);
+    const float div = eqc ? 1.f : cr;
+    const float rc = __fdiv_rn(__fsub_rn(maxc, r), div), gc = __fdiv_rn(__fsub_rn(maxc, g), div), bc = __fdiv_rn(__fsub_rn(maxc, b), div);
+    const float hr = (maxc == r ? 1.f : 0.f) * __fsub_rn(bc, gc);
+    const float hg = ((maxc == g && maxc != r) ? 1.f : 0.f) * __fsub_rn(__fadd_rn(2.f, rc), bc);
+    const float hb = ((maxc != g && maxc != r) ? 1.f : 0.f) * __fsub_rn(__fadd_rn(4.f, gc), rc);
+    float h = __fadd_rn(__fadd_rn(hr, hg), hb);
+    h = fmodf(__fadd_rn(__fdiv_rn(h, 6.f), 1.f), 1.f);
+    h = photo_remainder1(__fadd_rn(h, hue));
+    const float v = maxc;
+    const float h6 = __fmul_rn(h, 6.f);
+    const float fi = floorf(h6);
+    const float f = __fsub_rn(h6, fi);
+    int i = (int)fi % 6;
+    if (i < 0) i += 6;
+    const float p = fminf(fmaxf(__fmul_rn(v, __fsub_rn(1.f, s)), 0.f), 1.f);
+    const float q = fminf(fmaxf(__fmul_rn(v, __fsub_rn(1.f, __fmul_rn(f, s))), 0.f), 1.f);
+    const float t = fminf(fmaxf(__fmul_rn(v, __fsub_rn(1.f, __fmul_rn(__fsub_rn(1.f, f), s))), 0.f), 1.f);
+    float ro, go, bo;
+    switch (i) {
+        case 0: ro = v; go = t; bo = p; break;
+        case 1: ro = q; go = v; bo = p; break;
+        case 2: ro = p; go = v; bo = t; break;
+        case 3: ro = p; go = q; bo = v; break;
+        case 4: ro = t; go = p; bo = v; break;
+        default: ro = v; go = p; bo = q; break;
+    }
+    // back to uint8 as torchvision's convert_image_dtype does it: trunc(x * (255 + 1 - 1e-3)).  (The release the reference pins, 0.10.1, is
+    // believed to multiply by 255.0 at this one place; parity here is pinned on the installed release, 0.26, by running the reference's class.)
+    r8 = truncf(__fmul_rn(ro, 255.999f)); g8 = truncf(__fmul_rn(go, 255.999f)); b8 = truncf(__fmul_rn(bo, 255.999f));
+}
 
 // exact sum of the grey values of every sample whose contrast flag is set, taken AFTER its brightness step.
 // VEC = 4: four consecutive pixels per thread through 16-byte loads of each colour plane (HW % 4 == 0, 16-byte aligned planes)
@@ -92,6 +140,10 @@ __global__ void __launch_bounds__(256) photo_apply_kernel(const PhotoParams p) {
     // `normalize`) is tabulated once per block instead of being evaluated 12 times per thread and iteration
     // gamma acts on one of 256 channel values: tabulated per block (one powf per entry instead of three per pixel)
     __shared__ float glut[256];
+    const bool hue_on = p.do_h && p.do_h[n];
+    const float fh = hue_on ? p.f_h[n] : 0.f;
+    const bool noisy = p.do_n && p.do_n[n];
+    const float* nz = p.noise ? p.noise + (size_t)n * 3 * p.HW : nullptr;
     const bool gamma = p.do_g && p.do_g[n];
     if (gamma) {
         const float x = __fdiv_rn((float)threadIdx.x, 255.f);
@@ -135,6 +187,7 @@ __global__ void __launch_bounds__(256) photo_apply_kernel(const PhotoParams p) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) c[k][v] = glut[(int)c[k][v]];
                 }
+                if (hue_on) photo_hue(c[0][v], c[1][v], c[2][v], fh);
                 if (sat) {
                     const float gr = photo_gray(c[0][v], c[1][v], c[2][v]);
 #pragma unroll
@@ -144,7 +197,12 @@ __global__ void __launch_bounds__(256) photo_apply_kernel(const PhotoParams p) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 float x = c[k][v];
-                if (use_lut) x = lut[k][(int)x];
+                if (noisy) {
+                    float nv = nz[(size_t)k * p.HW + i + v];
+                    if (p.noise_uniform) nv = __fsub_rn(nv, 0.5f);
+                    x = __fadd_rn(x, __fmul_rn(p.noise_spread, nv));
+                }
+                if (use_lut && !noisy) x = lut[k][(int)x];
                 else if (p.norm_mode == 1) x = __fdiv_rn(x, 255.f);
                 else if (p.norm_mode == 2) x = __fsub_rn(__fmul_rn(2.f, __fdiv_rn(x, 255.f)), 1.f);
                 else if (p.norm_mode == 3) x = __fdiv_rn(__fsub_rn(__fdiv_rn(x, 255.f), p.mean[k]), p.std[k]);

@@ -1836,21 +1836,24 @@ int ptta_tta_loss_backward_emb(const void* emb, const void* ref, long long rows,
 // ---- on-device augmentations (augment.cuh) ----------------------------------------------------------------------
 int ptta_augment_photometric(const float* image, float* out, int n, int h, int w, const unsigned char* do_brightness, const float* f_brightness,
                              const unsigned char* do_contrast, const float* f_contrast, const unsigned char* do_saturation,
-                             const float* f_saturation, const unsigned char* do_gamma, const float* f_gamma, int quantize, int norm_mode,
-                             const float* mean3, const float* std3, void* workspace, ptta_stream_t stream) {
+                             const float* f_saturation, const unsigned char* do_gamma, const float* f_gamma, const unsigned char* do_hue,
+                             const float* f_hue, const unsigned char* do_noise, const float* noise, float noise_spread, int noise_uniform,
+                             int quantize, int norm_mode, const float* mean3, const float* std3, void* workspace, ptta_stream_t stream) {
     PTTA_CHECK(image && out && n >= 1 && h >= 1 && w >= 1, "augment_photometric: bad argument");
     PTTA_CHECK(norm_mode >= 0 && norm_mode <= 3, "augment_photometric: normalisation mode %d", norm_mode);
     PTTA_CHECK(norm_mode != 3 || (mean3 && std3), "augment_photometric: standard normalisation needs mean and std");
     PTTA_CHECK((!do_brightness || f_brightness) && (!do_contrast || f_contrast) && (!do_saturation || f_saturation) && (!do_gamma || f_gamma),
                "augment_photometric: a flag array without its factor array");
     PTTA_CHECK(!do_contrast || workspace, "augment_photometric: the contrast transform needs a workspace of 8 * n bytes");
-    PTTA_CHECK(quantize || !(do_brightness || do_contrast || do_saturation || do_gamma), "augment_photometric: the photometric transforms work on the uint8 image");
+    PTTA_CHECK(quantize || !(do_brightness || do_contrast || do_saturation || do_gamma || do_hue), "augment_photometric: the photometric transforms work on the uint8 image");
+    PTTA_CHECK((!do_hue || f_hue) && (!do_noise || noise), "augment_photometric: a flag array without its factor / noise array");
     PTTA_CHECK((long long)h * w < (1ll << 31) / 3 && n <= 65535, "augment_photometric: image too large");
     cudaStream_t st = (cudaStream_t)stream;
     PhotoParams p; memset(&p, 0, sizeof(p));
     p.in = image; p.out = out; p.do_b = do_brightness; p.do_c = do_contrast; p.do_s = do_saturation;
     p.f_b = f_brightness; p.f_c = f_contrast; p.f_s = f_saturation; p.gray_sum = (unsigned long long*)workspace;
-    p.do_g = do_gamma; p.f_g = f_gamma;
+    p.do_g = do_gamma; p.f_g = f_gamma; p.do_h = do_hue; p.f_h = f_hue;
+    p.do_n = do_noise; p.noise = noise; p.noise_spread = noise_spread; p.noise_uniform = noise_uniform;
     p.N = n; p.HW = h * w; p.quantize = quantize; p.norm_mode = norm_mode;
     for (int k = 0; k < 3; ++k) { p.mean[k] = mean3 ? mean3[k] : 0.f; p.std[k] = std3 ? std3[k] : 1.f; }
     // 16-byte accesses when every colour plane starts on a 16-byte boundary; ~2 waves of blocks over the whole batch

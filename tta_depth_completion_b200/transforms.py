@@ -12,7 +12,7 @@ sample and transform (`float(factors[b])`).
 Also native: the per-sample rotation (torchvision `functional.rotate` = affine grid + grid_sample; the angle comes from
 `np.random.rand`, as in the reference) and resize-and-crop (`functional.resize` + crop) -- with these, every augmentation the shipped
 adaptation scripts enable (bash/adapt/adapt_msgchn_*.sh: brightness, contrast, saturation, horizontal flip, rotate 5, resize-and-crop
-1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Gamma jitter is native too.  Crop-and-pad, resize-and-pad, hue jitter, noise and point removal are
+1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Gamma and hue jitter and the additive noise are native too.  Crop-and-pad, resize-and-pad and point removal are
 not implemented: configuring one raises NotImplementedError at construction (no silent fallback)."""
 import ctypes
 import math
@@ -48,9 +48,13 @@ class Transforms(object):
         self.random_saturation = random_saturation
         self.do_random_gamma = -1 not in random_gamma
         self.random_gamma = random_gamma
+        self.do_random_hue = -1 not in random_hue
+        self.random_hue = random_hue
+        self.do_random_noise = random_noise_type != 'none' and random_noise_spread > -1
+        self.random_noise_type, self.random_noise_spread = random_noise_type, random_noise_spread
+        if self.do_random_noise and random_noise_type not in ('gaussian', 'uniform'):
+            raise ValueError('Unsupported noise type: {}'.format(random_noise_type))
         unsupported = {
-            'random_hue': -1 not in random_hue,
-            'random_noise': random_noise_type != 'none' and random_noise_spread > -1,
             'random_remove_patch_percent_range': -1 not in random_remove_patch_percent_range,
             'random_crop_and_pad': -1 not in random_crop_and_pad,
             'random_resize_and_pad': -1 not in random_resize_and_pad,
@@ -60,7 +64,7 @@ class Transforms(object):
         if bad:
             raise NotImplementedError('Transforms options without a native kernel: %s (DESIGN.md, scope table f2)' % ', '.join(bad))
         # as in the reference, gamma alone does not trigger the uint8 cast (src/transforms.py:74-78 leaves it out of do_photometric_transforms)
-        self.do_photometric_transforms = self.do_random_brightness or self.do_random_contrast or self.do_random_saturation
+        self.do_photometric_transforms = self.do_random_brightness or self.do_random_contrast or self.do_random_hue or self.do_random_saturation
         self.do_image_normalization = normalized_image_range is not None
         self.do_random_horizontal_flip = 'horizontal' in random_flip_type
         self.do_random_vertical_flip = 'vertical' in random_flip_type
@@ -116,13 +120,14 @@ class Transforms(object):
         n_height, n_width = images_arr[0].shape[-2:]
         rdev = self.rand_device if self.rand_device is not None else device
         cur = torch.cuda.current_stream(device)
-        plan = self._draw(n_batch, n_height, n_width, device, rdev, random_transform_probability)
+        plan = self._draw(n_batch, n_height, n_width, device, rdev, random_transform_probability, [tuple(im.shape) for im in images_arr])
         for t in plan['device_tensors']:
             t.record_stream(cur)                       # allocated on the draw stream, read by kernels on the caller's stream
         cur.wait_stream(self._rng_stream(device))
         # ---- kernels, in the reference's order ----
-        if self.do_photometric_transforms or self.do_image_normalization:
-            images_arr = [self._photometric(im, plan['flags'], plan['factors']) for im in images_arr]
+        if self.do_photometric_transforms or self.do_image_normalization or self.do_random_noise:
+            images_arr = [self._photometric(im, plan['flags'], plan['factors'], plan.get('do_n'), plan['noise'][k] if 'noise' in plan else None)
+                          for k, im in enumerate(images_arr)]
         else:
             images_arr = [im.float() for im in images_arr]
         if n_channel == 1:
@@ -152,7 +157,7 @@ class Transforms(object):
             outputs.append(list(intrinsics_arr))
         return outputs[0] if len(outputs) == 1 else outputs
 
-    def _draw(self, n_batch, n_height, n_width, device, rdev, probability):
+    def _draw(self, n_batch, n_height, n_width, device, rdev, probability, shapes):
         """every random number of one `transform` call, drawn in the reference's order (src/transforms.py:229-480) on the draw stream;
         none of them depends on image data, only on the shapes"""
         plan = {'flags': {}, 'factors': {}, 'device_tensors': []}
@@ -166,7 +171,8 @@ class Transforms(object):
             do_random_transform = self._rand(n_batch, device) <= probability                                     # :229-230
             for name, enabled, rng, ge in (('b', self.do_random_brightness, self.random_brightness, True),
                                            ('c', self.do_random_contrast, self.random_contrast, False),
-                                           ('g', self.do_random_gamma, self.random_gamma, False),      # (hue would be drawn here)
+                                           ('g', self.do_random_gamma, self.random_gamma, False),
+                                           ('h', self.do_random_hue, self.random_hue, False),
                                            ('s', self.do_random_saturation, self.random_saturation, False)):
                 if not enabled:
                     continue
@@ -176,6 +182,18 @@ class Transforms(object):
                 values = self._rand(n_batch, device)
                 lo, hi = rng
                 plan['factors'][name] = keep((hi - lo) * values + lo)
+            if self.do_random_noise:                                                                             # :320-331, 839-875
+                do_n = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50)
+                plan['do_n'] = keep(do_n.to(torch.uint8))
+                host = do_n.tolist()
+                plan['noise'] = []
+                for shape in shapes:                        # per tensor, per flagged sample: one draw of the sample's shape, in the reference's order
+                    nz = torch.zeros(shape, dtype=torch.float32, device=device)
+                    for b in range(n_batch):
+                        if host[b]:
+                            draw = torch.randn(*shape[1:], device=rdev) if self.random_noise_type == 'gaussian' else torch.rand(*shape[1:], device=rdev)
+                            nz[b] = draw.to(device)
+                    plan['noise'].append(keep(nz))
             if self.do_random_crop_to_shape:                                                                     # :337-366
                 # `do and rand(1) <= 0.5 or range`: the roll is drawn in both forms; two numbers = crop to that shape half of the time, four = always
                 roll = bool(torch.rand(1, device=rdev) <= 0.50)
@@ -286,13 +304,15 @@ class Transforms(object):
             out.append(K)
         return out
 
-    def _photometric(self, images, flags, factors):
+    def _photometric(self, images, flags, factors, do_noise=None, noise=None):
         if images.shape[1] != 3:
             if self.do_photometric_transforms:
                 raise NotImplementedError('photometric transforms of %d-channel tensors' % images.shape[1])
         images = images.float().contiguous()
         n, c, h, w = images.shape
         if c != 3:                                  # normalisation only (single-channel input to a Transforms without jitter)
+            if noise is not None:
+                raise NotImplementedError('noise on %d-channel tensors' % c)
             mode, mean, std = self._norm
             if mode == 3:
                 raise NotImplementedError('standard normalisation of %d-channel tensors' % c)
@@ -302,7 +322,9 @@ class Transforms(object):
         ws = torch.empty(n, dtype=torch.int64, device=images.device) if 'c' in flags else None
         check(_lib.lib().ptta_augment_photometric(
             ptr(images), ptr(out), n, h, w, ptr(flags.get('b')), ptr(factors.get('b')), ptr(flags.get('c')), ptr(factors.get('c')),
-            ptr(flags.get('s')), ptr(factors.get('s')), ptr(flags.get('g')), ptr(factors.get('g')), 1 if self.do_photometric_transforms else 0, mode,
+            ptr(flags.get('s')), ptr(factors.get('s')), ptr(flags.get('g')), ptr(factors.get('g')), ptr(flags.get('h')), ptr(factors.get('h')),
+            ptr(do_noise), ptr(noise), float(self.random_noise_spread), 1 if self.random_noise_type == 'uniform' else 0,
+            1 if self.do_photometric_transforms else 0, mode,
             _FLOAT3(*mean) if mean else None, _FLOAT3(*std) if std else None, ptr(ws), _stream()), 'augment_photometric')
         return out
 
