@@ -308,6 +308,10 @@ int ptta_augment_flip(const float* in, float* out, int n, int c, int h, int w, c
  * (device int32 [N] arrays; the caller guarantees start + crop <= size, as torch.randint's bounds do); out is [N,C,crop_h,crop_w]. */
 int ptta_augment_crop(const float* in, float* out, int n, int c, int h, int w, int crop_h, int crop_w, const int* start_y,
                       const int* start_x, ptta_stream_t stream);
+/* ptta_augment_crop_pad: src/transforms.py:508-566, 1072-1135 with constant (zero) padding -- per sample the window
+ * {start_y, start_x, crop_h, crop_w} is placed at {pad_top, pad_left} of an h x w map of zeros (device int32 [N][6] in that order). */
+int ptta_augment_crop_pad(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_crop_pad,
+                          const int* window_n_x_6, ptta_stream_t stream);
 int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate,
                         const float* theta_n_x_6, int mode, ptta_stream_t stream);
 int ptta_augment_resize_crop(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_resize,

@@ -57,6 +57,8 @@ CASES = [
     dict(name='crop_range_resize', seed=24, n=5, h=24, w=40, prob=1.0, kinds=['image', 'depth', 'depth', 'depth'],
          modes=['bilinear', 'nearest', 'nearest', 'nearest'], intrinsics=True,
          ctor=dict(random_crop_to_shape=[12, 20, 20, 32], random_resize_and_crop=[1.0, 1.5], random_rotate_max=10)),
+    dict(name='crop_and_pad', seed=31, n=8, h=20, w=32, prob=1.0, kinds=['image', 'depth', 'depth'],
+         ctor=dict(random_crop_and_pad=[0.5, 1.0], random_flip_type=['horizontal'])),
     dict(name='flip_h_p05', seed=17, n=8, h=10, w=18, prob=0.5, kinds=['image', 'depth'], ctor=dict(random_flip_type=['horizontal'])),
 ]
 

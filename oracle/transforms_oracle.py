@@ -64,6 +64,22 @@ def draws(n_batch, cfg, probability, rand=lambda n: torch.rand(n)):
             sy.append(torch.randint(low=0, high=int(d['r_height'][b]) - h + 1, size=(1,)))
             sx.append(torch.randint(low=0, high=int(d['r_width'][b]) - w + 1, size=(1,)))
         d['start_y'], d['start_x'] = torch.cat(sy), torch.cat(sx)
+    if 'crop_and_pad' in cfg:                                                   # T:508-557
+        lo, hi = cfg['crop_and_pad']
+        h, w = cfg['shape']
+        d['do_crop_and_pad'] = torch.logical_and(d['do'], rand(n_batch) <= 0.50)
+        max_h, min_h, max_w, min_w = int(hi * h), int(lo * h), int(hi * w), int(lo * w)
+        rand_h = torch.randint(low=min_h, high=max_h, size=(n_batch,))
+        rand_w = torch.randint(low=min_w, high=max_w, size=(n_batch,))
+        sy = torch.cat([torch.randint(low=0, high=max_h - int(v), size=(1,)) for v in rand_h])
+        sx = torch.cat([torch.randint(low=0, high=max_w - int(v), size=(1,)) for v in rand_w])
+        ey = torch.minimum(sy + rand_h, torch.full_like(sy, h))
+        ex = torch.minimum(sx + rand_w, torch.full_like(sx, w))
+        dh = (h - (ey - sy)).int()
+        pt = (dh * torch.rand(n_batch)).int()
+        dw = (w - (ex - sx)).int()
+        pl = (dw * torch.rand(n_batch)).int()
+        d['cp'] = (sy, sx, ey, ex, pt, dh - pt, pl, dw - pl)
     return d
 
 
@@ -124,6 +140,13 @@ def apply(images_arr, cfg, d, normalized_image_range=None, interpolation_modes=(
                     image = image[..., y0:y0 + h, x0:x0 + w]
                 out.append(image)
             images_arr[i] = torch.stack(out, dim=0)
+    if 'do_crop_and_pad' in d:                                                  # T:1072-1135 (constant padding)
+        sy, sx, ey, ex, pt, pb, pl, pr = d['cp']
+        for images in images_arr:
+            for b in range(images.shape[0]):
+                if d['do_crop_and_pad'][b]:
+                    image = images[b][..., int(sy[b]):int(ey[b]), int(sx[b]):int(ex[b])]
+                    images[b, ...] = functional.pad(image, (int(pl[b]), int(pt[b]), int(pr[b]), int(pb[b])), padding_mode='constant', fill=0)
     return images_arr
 
 

@@ -211,5 +211,3 @@ def test_unsupported_options_fail_loudly():
         Transforms(random_resize_and_pad=[0.5, 1.0])
     with pytest.raises(NotImplementedError, match='random_remove_patch_percent_range'):
         Transforms(random_remove_patch_percent_range=[0.1, 0.2])
-    with pytest.raises(NotImplementedError, match='random_crop_and_pad'):
-        Transforms(random_crop_and_pad=[0.5, 1.0])

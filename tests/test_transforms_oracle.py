@@ -35,6 +35,9 @@ def case_cfg(case):
     if 'random_crop_to_shape' in c:
         cfg['crop_to_shape'] = c['random_crop_to_shape']
         cfg['shape'] = (case['h'], case['w'])
+    if 'random_crop_and_pad' in c:
+        cfg['crop_and_pad'] = c['random_crop_and_pad']
+        cfg.setdefault('shape', (case['h'], case['w']))
     if c.get('random_rotate_max', 0) > 0:
         cfg['rotate'] = c['random_rotate_max']
     if 'random_resize_and_crop' in c:

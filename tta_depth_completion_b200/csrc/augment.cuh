@@ -340,4 +340,25 @@ __global__ void __launch_bounds__(256) crop_kernel(const float* __restrict__ in,
     }
 }
 
+// Per-sample crop-and-pad (src/transforms.py:508-566, 1072-1135, constant padding): the window [sy, sy + ch) x [sx, sx + cw) of the sample is
+// placed at (pad_top, pad_left) of an H x W map of zeros.  win: [N][6] = {sy, sx, ch, cw, pad_top, pad_left}.  Flag clear: copy.
+__global__ void __launch_bounds__(256) crop_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+                                                       const unsigned char* __restrict__ do_cp, const int* __restrict__ win) {
+    PDL_SYNC();
+    const int n = blockIdx.y;
+    const int plane = H * W;
+    const float* ib = in + (size_t)n * C * plane;
+    float* ob = out + (size_t)n * C * plane;
+    if (!do_cp[n]) {
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < C * plane; i += gridDim.x * 256) ob[i] = ib[i];
+        return;
+    }
+    const int sy = win[n * 6], sx = win[n * 6 + 1], ch = win[n * 6 + 2], cw = win[n * 6 + 3], pt = win[n * 6 + 4], pl = win[n * 6 + 5];
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < C * plane; i += gridDim.x * 256) {
+        const int c = i / plane, r = i - c * plane, y = r / W, x = r - y * W;
+        const int yy = y - pt, xx = x - pl;
+        ob[i] = (yy >= 0 && yy < ch && xx >= 0 && xx < cw) ? ib[(size_t)c * plane + (size_t)(sy + yy) * W + sx + xx] : 0.f;
+    }
+}
+
 }  // namespace ptta

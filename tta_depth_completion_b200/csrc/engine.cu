@@ -1892,6 +1892,15 @@ int ptta_augment_crop(const float* in, float* out, int n, int c, int h, int w, i
     return check_launch("crop");
 }
 
+int ptta_augment_crop_pad(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_crop_pad, const int* window_n_x_6,
+                          ptta_stream_t stream) {
+    PTTA_CHECK(in && out && in != out && do_crop_pad && window_n_x_6 && n >= 1 && c >= 1 && h >= 1 && w >= 1, "augment_crop_pad: bad argument");
+    PTTA_CHECK((long long)c * h * w < (1ll << 31) && n <= 65535, "augment_crop_pad: map too large");
+    const int bx = std::max(1, std::min(cdiv((long long)c * h * w, 256 * 4), cdiv(2368, n)));
+    launch_k(crop_pad_kernel, dim3(bx, n), 256, 0, (cudaStream_t)stream, in, out, c, h, w, do_crop_pad, window_n_x_6);
+    return check_launch("crop_pad");
+}
+
 int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate, const float* theta_n_x_6,
                         int mode, ptta_stream_t stream) {
     PTTA_CHECK(in && out && in != out && do_rotate && theta_n_x_6 && n >= 1 && c >= 1 && h >= 1 && w >= 1, "augment_rotate: bad argument");

@@ -12,7 +12,7 @@ sample and transform (`float(factors[b])`).
 Also native: the per-sample rotation (torchvision `functional.rotate` = affine grid + grid_sample; the angle comes from
 `np.random.rand`, as in the reference) and resize-and-crop (`functional.resize` + crop) -- with these, every augmentation the shipped
 adaptation scripts enable (bash/adapt/adapt_msgchn_*.sh: brightness, contrast, saturation, horizontal flip, rotate 5, resize-and-crop
-1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Gamma and hue jitter and the additive noise are native too.  Crop-and-pad, resize-and-pad and point removal are
+1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Gamma and hue jitter and the additive noise are native too.  Crop-and-pad (constant padding) is native; resize-and-pad and point removal are
 not implemented: configuring one raises NotImplementedError at construction (no silent fallback)."""
 import ctypes
 import math
@@ -56,7 +56,6 @@ class Transforms(object):
             raise ValueError('Unsupported noise type: {}'.format(random_noise_type))
         unsupported = {
             'random_remove_patch_percent_range': -1 not in random_remove_patch_percent_range,
-            'random_crop_and_pad': -1 not in random_crop_and_pad,
             'random_resize_and_pad': -1 not in random_resize_and_pad,
             'resize_scaling_depth': bool(resize_scaling_depth) and -1 not in random_resize_and_crop,
         }
@@ -72,6 +71,11 @@ class Transforms(object):
         self.random_crop_to_shape = list(random_crop_to_shape)
         if self.do_random_crop_to_shape and len(random_crop_to_shape) not in (2, 4):
             raise ValueError('Unsupported input for random crop to shape: {}'.format(random_crop_to_shape))
+        self.do_random_crop_and_pad = -1 not in random_crop_and_pad
+        self.random_crop_and_pad_min, self.random_crop_and_pad_max = random_crop_and_pad[0], random_crop_and_pad[1]
+        if self.do_random_crop_and_pad:
+            assert self.random_crop_and_pad_min < self.random_crop_and_pad_max
+            assert self.random_crop_and_pad_max <= 1
         self.do_random_rotate = random_rotate_max > 0
         self.random_rotate_max = random_rotate_max
         self.do_random_resize_and_crop = -1 not in random_resize_and_crop
@@ -150,6 +154,11 @@ class Transforms(object):
             intrinsics_arr = self._adjust_intrinsics(intrinsics_arr, x_scales=(r_width / n_width), y_scales=(r_height / n_height))
             images_arr = [self._resample('resize_crop', im, m, do_rs, *args) for im, m in zip(images_arr, modes)]
             intrinsics_arr = self._adjust_intrinsics(intrinsics_arr, x_offsets=(r_width - n_width), y_offsets=(r_height - n_height))
+        if 'crop_pad' in plan:                                                                                   # :508-566
+            if any(m != 'constant' for m in padding_modes):
+                raise NotImplementedError('crop-and-pad with padding modes other than constant')
+            do_cp, win = plan['crop_pad']
+            images_arr = [self._crop_pad(im, do_cp, win) for im in images_arr]
         outputs = []
         if len(images_arr) > 0:
             outputs.append(images_arr)
@@ -232,6 +241,23 @@ class Transforms(object):
                 start_y, start_x = torch.cat(start_y, dim=0), torch.cat(start_x, dim=0)
                 args = [keep(t.to(device=device, dtype=torch.int32)) for t in (r_height, r_width, start_y, start_x)]
                 plan['resize'] = (do_rs, keep(r_height), keep(r_width), args)
+            if self.do_random_crop_and_pad:                                                                      # :508-557
+                do_cp = keep(torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8))
+                max_h, min_h = int(self.random_crop_and_pad_max * n_height), int(self.random_crop_and_pad_min * n_height)
+                max_w, min_w = int(self.random_crop_and_pad_max * n_width), int(self.random_crop_and_pad_min * n_width)
+                rand_h = torch.randint(low=min_h, high=max_h, size=(n_batch,), device=rdev)
+                rand_w = torch.randint(low=min_w, high=max_w, size=(n_batch,), device=rdev)
+                rh, rw = rand_h.tolist(), rand_w.tolist()
+                start_y = torch.cat([torch.randint(low=0, high=max_h - v, size=(1,), device=rdev) for v in rh])
+                start_x = torch.cat([torch.randint(low=0, high=max_w - v, size=(1,), device=rdev) for v in rw])
+                end_y = torch.minimum(start_y + rand_h, torch.full_like(start_y, n_height))
+                end_x = torch.minimum(start_x + rand_w, torch.full_like(start_x, n_width))
+                d_h = (n_height - (end_y - start_y)).int()
+                pad_top = (d_h * torch.rand(n_batch, device=rdev)).int()
+                d_w = (n_width - (end_x - start_x)).int()
+                pad_left = (d_w * torch.rand(n_batch, device=rdev)).int()
+                win = torch.stack([start_y.int(), start_x.int(), (end_y - start_y).int(), (end_x - start_x).int(), pad_top, pad_left], dim=1)
+                plan['crop_pad'] = (do_cp, keep(win.to(device=device, dtype=torch.int32)))
         return plan
 
     # -- geometric helpers -----------------------------------------------------------------------------------
@@ -270,6 +296,14 @@ class Transforms(object):
         n, c, h, w = images.shape
         out = torch.empty((n, c, ch, cw), dtype=torch.float32, device=images.device)
         check(_lib.lib().ptta_augment_crop(ptr(images), ptr(out), n, c, h, w, ch, cw, ptr(sy), ptr(sx), _stream()), 'augment_crop')
+        return out
+
+    @staticmethod
+    def _crop_pad(images, do_cp, win):
+        images = images.float().contiguous()
+        n, c, h, w = images.shape
+        out = torch.empty_like(images)
+        check(_lib.lib().ptta_augment_crop_pad(ptr(images), ptr(out), n, c, h, w, ptr(do_cp), ptr(win), _stream()), 'augment_crop_pad')
         return out
 
     @staticmethod
