@@ -312,6 +312,10 @@ int ptta_augment_crop(const float* in, float* out, int n, int c, int h, int w, i
  * {start_y, start_x, crop_h, crop_w} is placed at {pad_top, pad_left} of an h x w map of zeros (device int32 [N][6] in that order). */
 int ptta_augment_crop_pad(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_crop_pad,
                           const int* window_n_x_6, ptta_stream_t stream);
+/* ptta_augment_remove_patches: src/transforms.py:625-652, 878-953 -- every selected pixel (`selected`: device uint8 [N,H,W], chosen by the
+ * caller from the sample's non-zero pixels as the reference does, torch.randperm) erases the {ph, pw} patch around it (device int32 [N][2], odd). */
+int ptta_augment_remove_patches(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_remove,
+                                const unsigned char* selected, const int* patch_n_x_2, ptta_stream_t stream);
 int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate,
                         const float* theta_n_x_6, int mode, ptta_stream_t stream);
 int ptta_augment_resize_crop(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_resize,

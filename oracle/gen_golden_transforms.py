@@ -4,6 +4,7 @@ draws come from it: torch.manual_seed(seed); inputs first, then the class's own 
     python oracle/gen_golden_transforms.py"""
 import importlib
 import os
+import random
 import sys
 
 import numpy as np
@@ -59,6 +60,8 @@ CASES = [
          ctor=dict(random_crop_to_shape=[12, 20, 20, 32], random_resize_and_crop=[1.0, 1.5], random_rotate_max=10)),
     dict(name='crop_and_pad', seed=31, n=8, h=20, w=32, prob=1.0, kinds=['image', 'depth', 'depth'],
          ctor=dict(random_crop_and_pad=[0.5, 1.0], random_flip_type=['horizontal'])),
+    dict(name='remove_points', seed=32, n=8, h=24, w=40, prob=1.0, kinds=['depth'],
+         ctor=dict(random_remove_patch_percent_range=[0.2, 0.6], random_remove_patch_size=[1, 1, 5, 7])),
     dict(name='flip_h_p05', seed=17, n=8, h=10, w=18, prob=0.5, kinds=['image', 'depth'], ctor=dict(random_flip_type=['horizontal'])),
 ]
 
@@ -96,6 +99,7 @@ def main():
     for case in CASES:
         inputs = case_inputs(case)
         np.random.seed(case['seed'])
+        random.seed(case['seed'])
         tr = T.Transforms(**case['ctor'])
         kw = {}
         if 'modes' in case:

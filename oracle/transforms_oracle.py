@@ -4,6 +4,8 @@ normalisation (:669-712), random crop to a common shape (:337-383, 955-988), per
 (`torchvision.transforms.functional.adjust_*`, pinned 0.10.1 by the reference's README.md:74; 0.26 here -- the tensor code path
 `_blend` / `rgb_to_grayscale` is unchanged between the two) and is called as the reference calls it.  Pinned against fixtures produced by
 the reference's own class: oracle/gen_golden_transforms.py, tests/test_transforms_oracle.py."""
+import random
+
 import numpy as np
 import torch
 from torchvision.transforms import functional
@@ -80,6 +82,11 @@ def draws(n_batch, cfg, probability, rand=lambda n: torch.rand(n)):
         dw = (w - (ex - sx)).int()
         pl = (dw * torch.rand(n_batch)).int()
         d['cp'] = (sy, sx, ey, ex, pt, dh - pt, pl, dw - pl)
+    if 'remove_patch' in cfg:                                                   # T:625-643 (patch sizes from python's global generator)
+        (lo, hi), heights, widths = cfg['remove_patch']
+        d['do_remove'] = torch.logical_and(d['do'], rand(n_batch) <= 0.50)
+        d['densities'] = (hi - lo) * rand(n_batch) + lo
+        d['patch'] = [[random.choice(heights), random.choice(widths)] for _ in range(n_batch)]
     return d
 
 
@@ -147,6 +154,21 @@ def apply(images_arr, cfg, d, normalized_image_range=None, interpolation_modes=(
                 if d['do_crop_and_pad'][b]:
                     image = images[b][..., int(sy[b]):int(ey[b]), int(sx[b]):int(ex[b])]
                     images[b, ...] = functional.pad(image, (int(pl[b]), int(pt[b]), int(pr[b]), int(pb[b])), padding_mode='constant', fill=0)
+    if 'do_remove' in d:                                                        # T:878-953 (the subset is drawn here: it depends on the data)
+        for images in images_arr:
+            for b in range(images.shape[0]):
+                if d['do_remove'][b]:
+                    image = images[b]
+                    mask = torch.sum(torch.abs(image), dim=0, keepdim=True)
+                    mask = torch.where(mask > 0, torch.ones_like(mask), torch.zeros_like(mask))
+                    nz = (mask > 0).nonzero(as_tuple=True)
+                    subset = torch.randperm(nz[0].shape[0])
+                    subset = subset[0:int(d['densities'][b] * subset.shape[0])]
+                    mask[tuple(idx[subset] for idx in nz)] = float('inf')
+                    ps = d['patch'][b]
+                    mask = torch.nn.functional.max_pool2d(input=mask, kernel_size=ps, stride=1, padding=[int(k // 2) for k in ps])
+                    mask[mask == float('inf')] = 0.0
+                    images[b, ...] = mask * image
     return images_arr
 
 

@@ -9,6 +9,8 @@ at most 1e-4 of the values may differ, each by exactly one grey level.  Rotation
 `compare_resampled`."""
 import os
 
+import random
+
 import numpy as np
 import pytest
 import torch
@@ -55,6 +57,7 @@ def test_native_transforms_match_reference_fixture(name):
     tr = Transforms(**case['ctor'])
     tr.rand_device = 'cpu'
     np.random.seed(case['seed'])
+    random.seed(case['seed'])
     kw = {}
     if 'modes' in case:
         kw['interpolation_modes'] = tr.map_interpolation_mode_names_to_enums(case['modes'])
@@ -209,5 +212,3 @@ def test_unsupported_options_fail_loudly():
     from tta_depth_completion_b200.transforms import Transforms
     with pytest.raises(NotImplementedError, match='random_resize_and_pad'):
         Transforms(random_resize_and_pad=[0.5, 1.0])
-    with pytest.raises(NotImplementedError, match='random_remove_patch_percent_range'):
-        Transforms(random_remove_patch_percent_range=[0.1, 0.2])

@@ -2,6 +2,8 @@
 fixtures produced by the reference's own class (oracle/gen_golden_transforms.py) -- bit-exact: same torch / torchvision CPU ops, same draws."""
 import os
 
+import random
+
 import numpy as np
 import pytest
 import torch
@@ -38,6 +40,11 @@ def case_cfg(case):
     if 'random_crop_and_pad' in c:
         cfg['crop_and_pad'] = c['random_crop_and_pad']
         cfg.setdefault('shape', (case['h'], case['w']))
+    if 'random_remove_patch_percent_range' in c:
+        sz = c.get('random_remove_patch_size', [1, 1])
+        hs = list(range(sz[0], sz[2] + 2, 2)) if len(sz) == 4 else [sz[0]]
+        ws = list(range(sz[1], sz[3] + 2, 2)) if len(sz) == 4 else [sz[1]]
+        cfg['remove_patch'] = (c['random_remove_patch_percent_range'], hs, ws)
     if c.get('random_rotate_max', 0) > 0:
         cfg['rotate'] = c['random_rotate_max']
     if 'random_resize_and_crop' in c:
@@ -53,6 +60,7 @@ def test_oracle_equals_reference_transforms(name):
     inputs = case_inputs(case)                      # seeds the generator; the draws continue from there, as in the generator script
     cfg = case_cfg(case)
     np.random.seed(case['seed'])
+    random.seed(case['seed'])
     d = TO.draws(case['n'], cfg, case['prob'])
     outs = TO.apply(inputs, cfg, d, nested_range(case['ctor'].get('normalized_image_range')), case.get('modes', ('nearest',)))
     assert len(outs) == len(fx['outputs'])

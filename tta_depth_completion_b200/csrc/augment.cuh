@@ -361,4 +361,31 @@ __global__ void __launch_bounds__(256) crop_pad_kernel(const float* __restrict__
     }
 }
 
+// Random point removal (src/transforms.py:625-652, 878-953): every SELECTED pixel of a sample (uint8 map `sel`, chosen by the caller from the
+// sample's non-zero pixels with torch.randperm, as the reference does) erases the ph x pw patch around it (the reference marks the point
+// with inf, max-pools with the patch and zeroes what became inf).  out = 0 inside a patch, the input elsewhere.  patch: [N][2] = {ph, pw} (odd).
+__global__ void __launch_bounds__(256) remove_patches_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+                                                             const unsigned char* __restrict__ do_rm, const unsigned char* __restrict__ sel,
+                                                             const int* __restrict__ patch) {
+    PDL_SYNC();
+    const int n = blockIdx.y;
+    const int plane = H * W;
+    const float* ib = in + (size_t)n * C * plane;
+    float* ob = out + (size_t)n * C * plane;
+    if (!do_rm[n]) {
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < C * plane; i += gridDim.x * 256) ob[i] = ib[i];
+        return;
+    }
+    const unsigned char* sb = sel + (size_t)n * plane;
+    const int ry = patch[n * 2] / 2, rx = patch[n * 2 + 1] / 2;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < plane; i += gridDim.x * 256) {
+        const int y = i / W, x = i - y * W;
+        bool hit = false;
+        for (int yy = max(y - ry, 0); yy <= min(y + ry, H - 1) && !hit; ++yy)
+            for (int xx = max(x - rx, 0); xx <= min(x + rx, W - 1); ++xx)
+                if (sb[yy * W + xx]) { hit = true; break; }
+        for (int c = 0; c < C; ++c) ob[c * plane + i] = hit ? 0.f : ib[c * plane + i];
+    }
+}
+
 }  // namespace ptta

@@ -1901,6 +1901,15 @@ int ptta_augment_crop_pad(const float* in, float* out, int n, int c, int h, int 
     return check_launch("crop_pad");
 }
 
+int ptta_augment_remove_patches(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_remove, const unsigned char* selected,
+                                const int* patch_n_x_2, ptta_stream_t stream) {
+    PTTA_CHECK(in && out && in != out && do_remove && selected && patch_n_x_2 && n >= 1 && c >= 1 && h >= 1 && w >= 1, "augment_remove_patches: bad argument");
+    PTTA_CHECK((long long)c * h * w < (1ll << 31) && n <= 65535, "augment_remove_patches: map too large");
+    const int bx = std::max(1, std::min(cdiv((long long)h * w, 256 * 2), cdiv(2368, n)));
+    launch_k(remove_patches_kernel, dim3(bx, n), 256, 0, (cudaStream_t)stream, in, out, c, h, w, do_remove, selected, patch_n_x_2);
+    return check_launch("remove_patches");
+}
+
 int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate, const float* theta_n_x_6,
                         int mode, ptta_stream_t stream) {
     PTTA_CHECK(in && out && in != out && do_rotate && theta_n_x_6 && n >= 1 && c >= 1 && h >= 1 && w >= 1, "augment_rotate: bad argument");

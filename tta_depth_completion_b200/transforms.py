@@ -12,10 +12,11 @@ sample and transform (`float(factors[b])`).
 Also native: the per-sample rotation (torchvision `functional.rotate` = affine grid + grid_sample; the angle comes from
 `np.random.rand`, as in the reference) and resize-and-crop (`functional.resize` + crop) -- with these, every augmentation the shipped
 adaptation scripts enable (bash/adapt/adapt_msgchn_*.sh: brightness, contrast, saturation, horizontal flip, rotate 5, resize-and-crop
-1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Gamma and hue jitter and the additive noise are native too.  Crop-and-pad (constant padding) is native; resize-and-pad and point removal are
+1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Gamma and hue jitter and the additive noise are native too.  Crop-and-pad (constant padding) and the random point removal are native; resize-and-pad is
 not implemented: configuring one raises NotImplementedError at construction (no silent fallback)."""
 import ctypes
 import math
+import random
 
 import numpy as np
 import torch
@@ -55,7 +56,6 @@ class Transforms(object):
         if self.do_random_noise and random_noise_type not in ('gaussian', 'uniform'):
             raise ValueError('Unsupported noise type: {}'.format(random_noise_type))
         unsupported = {
-            'random_remove_patch_percent_range': -1 not in random_remove_patch_percent_range,
             'random_resize_and_pad': -1 not in random_resize_and_pad,
             'resize_scaling_depth': bool(resize_scaling_depth) and -1 not in random_resize_and_crop,
         }
@@ -76,6 +76,14 @@ class Transforms(object):
         if self.do_random_crop_and_pad:
             assert self.random_crop_and_pad_min < self.random_crop_and_pad_max
             assert self.random_crop_and_pad_max <= 1
+        self.do_random_remove_patch = -1 not in random_remove_patch_percent_range
+        self.random_remove_patch_percent_range = random_remove_patch_percent_range
+        if len(random_remove_patch_size) == 4:          # a range of (odd) sizes to choose from, src/transforms.py:131-137
+            self.random_remove_patch_size_height = list(range(random_remove_patch_size[0], random_remove_patch_size[2] + 2, 2))
+            self.random_remove_patch_size_width = list(range(random_remove_patch_size[1], random_remove_patch_size[3] + 2, 2))
+        else:
+            self.random_remove_patch_size_height = [random_remove_patch_size[0]]
+            self.random_remove_patch_size_width = [random_remove_patch_size[1]]
         self.do_random_rotate = random_rotate_max > 0
         self.random_rotate_max = random_rotate_max
         self.do_random_resize_and_crop = -1 not in random_resize_and_crop
@@ -159,6 +167,8 @@ class Transforms(object):
                 raise NotImplementedError('crop-and-pad with padding modes other than constant')
             do_cp, win = plan['crop_pad']
             images_arr = [self._crop_pad(im, do_cp, win) for im in images_arr]
+        if 'remove' in plan:                                                                                     # :644-652, 878-953
+            images_arr = [self._remove_patches(im, plan['remove'], rdev) for im in images_arr]
         outputs = []
         if len(images_arr) > 0:
             outputs.append(images_arr)
@@ -258,6 +268,14 @@ class Transforms(object):
                 pad_left = (d_w * torch.rand(n_batch, device=rdev)).int()
                 win = torch.stack([start_y.int(), start_x.int(), (end_y - start_y).int(), (end_x - start_x).int(), pad_top, pad_left], dim=1)
                 plan['crop_pad'] = (do_cp, keep(win.to(device=device, dtype=torch.int32)))
+            if self.do_random_remove_patch:                                                                      # :625-643
+                do_rm = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50)
+                values = self._rand(n_batch, device)
+                lo, hi = self.random_remove_patch_percent_range
+                patch = [[random.choice(self.random_remove_patch_size_height), random.choice(self.random_remove_patch_size_width)]
+                         for _ in range(n_batch)]                             # python's global generator, as the reference
+                plan['remove'] = (keep(do_rm.to(torch.uint8)), do_rm.tolist(), (hi - lo) * values + lo,
+                                  keep(torch.tensor(patch, dtype=torch.int32).to(device)))
         return plan
 
     # -- geometric helpers -----------------------------------------------------------------------------------
@@ -296,6 +314,27 @@ class Transforms(object):
         n, c, h, w = images.shape
         out = torch.empty((n, c, ch, cw), dtype=torch.float32, device=images.device)
         check(_lib.lib().ptta_augment_crop(ptr(images), ptr(out), n, c, h, w, ch, cw, ptr(sy), ptr(sx), _stream()), 'augment_crop')
+        return out
+
+    @staticmethod
+    def _remove_patches(images, plan, rdev):
+        """the selection is data dependent (a random subset of the sample's non-zero pixels, torch.randperm over their count: src/transforms.py
+        :926-953), so it is drawn here, after the tensor exists -- in the reference's order: per tensor, per flagged sample"""
+        do_rm, host, densities, patch = plan
+        images = images.float().contiguous()
+        n, c, h, w = images.shape
+        sel = torch.zeros((n, h, w), dtype=torch.uint8, device=images.device)
+        for b in range(n):
+            if not host[b]:
+                continue
+            ys, xs = (images[b].abs().sum(dim=0) > 0).nonzero(as_tuple=True)
+            k = ys.shape[0]
+            perm = torch.randperm(k, device=rdev)
+            chosen = perm[0:int(densities[b] * k)].to(images.device)
+            sel[b, ys[chosen], xs[chosen]] = 1
+        out = torch.empty_like(images)
+        check(_lib.lib().ptta_augment_remove_patches(ptr(images), ptr(out), n, c, h, w, ptr(do_rm), ptr(sel), ptr(patch), _stream()),
+              'augment_remove_patches')
         return out
 
     @staticmethod
