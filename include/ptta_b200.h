@@ -316,6 +316,11 @@ int ptta_augment_crop_pad(const float* in, float* out, int n, int c, int h, int 
  * caller from the sample's non-zero pixels as the reference does, torch.randperm) erases the {ph, pw} patch around it (device int32 [N][2], odd). */
 int ptta_augment_remove_patches(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_remove,
                                 const unsigned char* selected, const int* patch_n_x_2, ptta_stream_t stream);
+/* ptta_augment_resize_pad: src/transforms.py:578-622, 1137-1220 -- per sample a reduction to {resize_h, resize_w} <= (h, w) placed at {pad_top,
+ * pad_left} of an h x w map of zeros (device int32 [N][4] in that order); nearest or bilinear WITHOUT anti-aliasing (torchvision 0.10.1, the
+ * release the reference pins; later releases filter a bilinear reduction by default). */
+int ptta_augment_resize_pad(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_resize_pad,
+                            const int* geometry_n_x_4, int mode, ptta_stream_t stream);
 int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate,
                         const float* theta_n_x_6, int mode, ptta_stream_t stream);
 int ptta_augment_resize_crop(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_resize,

@@ -62,6 +62,10 @@ CASES = [
          ctor=dict(random_crop_and_pad=[0.5, 1.0], random_flip_type=['horizontal'])),
     dict(name='remove_points', seed=32, n=8, h=24, w=40, prob=1.0, kinds=['depth'],
          ctor=dict(random_remove_patch_percent_range=[0.2, 0.6], random_remove_patch_size=[1, 1, 5, 7])),
+    # resize-and-pad: the installed torchvision (0.26) low-pass filters a BILINEAR reduction by default, the release the reference pins (0.10.1)
+    # has no such option -- the fixture holds what the class produces HERE; the nearest-neighbour tensors are release independent
+    dict(name='resize_and_pad', seed=33, n=8, h=24, w=40, prob=1.0, kinds=['image', 'depth', 'depth'], modes=['bilinear', 'nearest', 'nearest'],
+         ctor=dict(random_resize_and_pad=[0.6, 1.0])),
     dict(name='flip_h_p05', seed=17, n=8, h=10, w=18, prob=0.5, kinds=['image', 'depth'], ctor=dict(random_flip_type=['horizontal'])),
 ]
 

@@ -82,6 +82,18 @@ def draws(n_batch, cfg, probability, rand=lambda n: torch.rand(n)):
         dw = (w - (ex - sx)).int()
         pl = (dw * torch.rand(n_batch)).int()
         d['cp'] = (sy, sx, ey, ex, pt, dh - pt, pl, dw - pl)
+    if 'resize_and_pad' in cfg:                                                 # T:578-612
+        lo, hi = cfg['resize_and_pad']
+        h, w = cfg['shape']
+        d['do_resize_and_pad'] = torch.logical_and(d['do'], rand(n_batch) <= 0.50)
+        rh = torch.randint(low=int(lo * h), high=int(hi * h), size=(n_batch,))
+        rw = torch.randint(low=int(lo * w), high=int(hi * w), size=(n_batch,))
+        dh = (h - rh).int()
+        pt = (dh * torch.rand(n_batch)).int()
+        dw = (w - rw).int()
+        pl = (dw * torch.rand(n_batch)).int()
+        zero = torch.zeros_like(pt)
+        d['rp'] = (rh, rw, torch.maximum(pt, zero), torch.maximum(dh - pt, zero), torch.maximum(pl, zero), torch.maximum(dw - pl, zero))
     if 'remove_patch' in cfg:                                                   # T:625-643 (patch sizes from python's global generator)
         (lo, hi), heights, widths = cfg['remove_patch']
         d['do_remove'] = torch.logical_and(d['do'], rand(n_batch) <= 0.50)
@@ -90,7 +102,7 @@ def draws(n_batch, cfg, probability, rand=lambda n: torch.rand(n)):
     return d
 
 
-def apply(images_arr, cfg, d, normalized_image_range=None, interpolation_modes=('nearest',)):
+def apply(images_arr, cfg, d, normalized_image_range=None, interpolation_modes=('nearest',), antialias=False):
     images_arr = [im.clone() for im in images_arr]
     photometric = any(k in cfg for k in ('brightness', 'contrast', 'hue', 'saturation'))        # gamma alone does not trigger the cast (T:102-106)
     if photometric:
@@ -153,6 +165,14 @@ def apply(images_arr, cfg, d, normalized_image_range=None, interpolation_modes=(
             for b in range(images.shape[0]):
                 if d['do_crop_and_pad'][b]:
                     image = images[b][..., int(sy[b]):int(ey[b]), int(sx[b]):int(ex[b])]
+                    images[b, ...] = functional.pad(image, (int(pl[b]), int(pt[b]), int(pr[b]), int(pb[b])), padding_mode='constant', fill=0)
+    if 'do_resize_and_pad' in d:                                                # T:1137-1220; antialias=False = the pinned torchvision 0.10.1 (no such option there)
+        modes = list(interpolation_modes) + [interpolation_modes[-1]] * (len(images_arr) - len(interpolation_modes))
+        rh, rw, pt, pb, pl, pr = d['rp']
+        for images, mode in zip(images_arr, modes):
+            for b in range(images.shape[0]):
+                if d['do_resize_and_pad'][b]:
+                    image = functional.resize(images[b], size=(int(rh[b]), int(rw[b])), interpolation=_MODE[mode], antialias=antialias)
                     images[b, ...] = functional.pad(image, (int(pl[b]), int(pt[b]), int(pr[b]), int(pb[b])), padding_mode='constant', fill=0)
     if 'do_remove' in d:                                                        # T:878-953 (the subset is drawn here: it depends on the data)
         for images in images_arr:

@@ -45,6 +45,9 @@ def case_cfg(case):
         hs = list(range(sz[0], sz[2] + 2, 2)) if len(sz) == 4 else [sz[0]]
         ws = list(range(sz[1], sz[3] + 2, 2)) if len(sz) == 4 else [sz[1]]
         cfg['remove_patch'] = (c['random_remove_patch_percent_range'], hs, ws)
+    if 'random_resize_and_pad' in c:
+        cfg['resize_and_pad'] = c['random_resize_and_pad']
+        cfg.setdefault('shape', (case['h'], case['w']))
     if c.get('random_rotate_max', 0) > 0:
         cfg['rotate'] = c['random_rotate_max']
     if 'random_resize_and_crop' in c:
@@ -62,7 +65,8 @@ def test_oracle_equals_reference_transforms(name):
     np.random.seed(case['seed'])
     random.seed(case['seed'])
     d = TO.draws(case['n'], cfg, case['prob'])
-    outs = TO.apply(inputs, cfg, d, nested_range(case['ctor'].get('normalized_image_range')), case.get('modes', ('nearest',)))
+    # the fixtures hold what the reference's class produces under the INSTALLED torchvision: anti-aliased bilinear reductions (resize-and-pad)
+    outs = TO.apply(inputs, cfg, d, nested_range(case['ctor'].get('normalized_image_range')), case.get('modes', ('nearest',)), antialias=True)
     assert len(outs) == len(fx['outputs'])
     for got, want in zip(outs, fx['outputs']):
         assert got.dtype == want.dtype and torch.equal(got, want)

@@ -388,4 +388,43 @@ __global__ void __launch_bounds__(256) remove_patches_kernel(const float* __rest
     }
 }
 
+// Per-sample reduction to (rh, rw) <= (H, W) placed at (pad_top, pad_left) of an H x W map of zeros (src/transforms.py:578-622, 1137-1220:
+// functional.resize + functional.pad, constant padding).  Source coordinates as F.interpolate computes them (align_corners = False, NO
+// anti-aliasing: the behaviour of the torchvision release the reference pins, 0.10.1; later releases low-pass filter a bilinear reduction
+// by default).  mode 0 nearest, 1 bilinear.  geo: [N][4] = {rh, rw, pad_top, pad_left}.
+__global__ void __launch_bounds__(256) resize_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+                                                         const unsigned char* __restrict__ do_rp, const int* __restrict__ geo, int mode) {
+    PDL_SYNC();
+    const int n = blockIdx.y;
+    const int plane = H * W;
+    const float* ib = in + (size_t)n * C * plane;
+    float* ob = out + (size_t)n * C * plane;
+    if (!do_rp[n]) {
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < C * plane; i += gridDim.x * 256) ob[i] = ib[i];
+        return;
+    }
+    const int rh = geo[n * 4], rw = geo[n * 4 + 1], pt = geo[n * 4 + 2], pl = geo[n * 4 + 3];
+    const float sh = (float)H / (float)rh, sw = (float)W / (float)rw;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < plane; i += gridDim.x * 256) {
+        const int y = i / W, x = i - y * W;
+        const int Y = y - pt, X = x - pl;                  // position in the reduced image
+        if (Y < 0 || Y >= rh || X < 0 || X >= rw) {
+            for (int c = 0; c < C; ++c) ob[c * plane + i] = 0.f;
+        } else if (mode == 0) {
+            const int ys = min((int)floorf((float)Y * sh), H - 1), xs = min((int)floorf((float)X * sw), W - 1);
+            for (int c = 0; c < C; ++c) ob[c * plane + i] = ib[c * plane + ys * W + xs];
+        } else {
+            const float yr = fmaxf(sh * ((float)Y + 0.5f) - 0.5f, 0.f), xr = fmaxf(sw * ((float)X + 0.5f) - 0.5f, 0.f);
+            const int y1 = (int)yr, x1 = (int)xr;
+            const int yp = y1 < H - 1 ? 1 : 0, xp = x1 < W - 1 ? 1 : 0;
+            const float ly1 = yr - (float)y1, ly0 = 1.f - ly1, lx1 = xr - (float)x1, lx0 = 1.f - lx1;
+            for (int c = 0; c < C; ++c) {
+                const float* pc = ib + c * plane;
+                ob[c * plane + i] = ly0 * (lx0 * pc[y1 * W + x1] + lx1 * pc[y1 * W + x1 + xp]) +
+                                    ly1 * (lx0 * pc[(y1 + yp) * W + x1] + lx1 * pc[(y1 + yp) * W + x1 + xp]);
+            }
+        }
+    }
+}
+
 }  // namespace ptta

@@ -1910,6 +1910,16 @@ int ptta_augment_remove_patches(const float* in, float* out, int n, int c, int h
     return check_launch("remove_patches");
 }
 
+int ptta_augment_resize_pad(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_resize_pad, const int* geometry_n_x_4,
+                            int mode, ptta_stream_t stream) {
+    PTTA_CHECK(in && out && in != out && do_resize_pad && geometry_n_x_4 && n >= 1 && c >= 1 && h >= 1 && w >= 1, "augment_resize_pad: bad argument");
+    PTTA_CHECK(mode == 0 || mode == 1, "augment_resize_pad: interpolation mode %d (0 nearest, 1 bilinear)", mode);
+    PTTA_CHECK((long long)c * h * w < (1ll << 31) && n <= 65535, "augment_resize_pad: map too large");
+    const int bx = std::max(1, std::min(cdiv((long long)h * w, 256 * 2), cdiv(2368, n)));
+    launch_k(resize_pad_kernel, dim3(bx, n), 256, 0, (cudaStream_t)stream, in, out, c, h, w, do_resize_pad, geometry_n_x_4, mode);
+    return check_launch("resize_pad");
+}
+
 int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate, const float* theta_n_x_6,
                         int mode, ptta_stream_t stream) {
     PTTA_CHECK(in && out && in != out && do_rotate && theta_n_x_6 && n >= 1 && c >= 1 && h >= 1 && w >= 1, "augment_rotate: bad argument");

@@ -12,8 +12,9 @@ sample and transform (`float(factors[b])`).
 Also native: the per-sample rotation (torchvision `functional.rotate` = affine grid + grid_sample; the angle comes from
 `np.random.rand`, as in the reference) and resize-and-crop (`functional.resize` + crop) -- with these, every augmentation the shipped
 adaptation scripts enable (bash/adapt/adapt_msgchn_*.sh: brightness, contrast, saturation, horizontal flip, rotate 5, resize-and-crop
-1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Gamma and hue jitter and the additive noise are native too.  Crop-and-pad (constant padding) and the random point removal are native; resize-and-pad is
-not implemented: configuring one raises NotImplementedError at construction (no silent fallback)."""
+1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Gamma and hue jitter and the additive noise are native too.  Crop-and-pad and resize-and-pad (constant padding; bilinear reductions WITHOUT anti-aliasing, as the torchvision release the reference
+pins computes them) and the random point removal are native.  What stays without a kernel raises NotImplementedError (no silent
+fallback): `resize_scaling_depth`, padding modes other than 'constant', interpolation modes other than nearest / bilinear."""
 import ctypes
 import math
 import random
@@ -55,8 +56,13 @@ class Transforms(object):
         self.random_noise_type, self.random_noise_spread = random_noise_type, random_noise_spread
         if self.do_random_noise and random_noise_type not in ('gaussian', 'uniform'):
             raise ValueError('Unsupported noise type: {}'.format(random_noise_type))
+        self.do_random_resize_and_pad = -1 not in random_resize_and_pad
+        self.random_resize_and_pad_min, self.random_resize_and_pad_max = random_resize_and_pad[0], random_resize_and_pad[1]
+        if self.do_random_resize_and_pad:
+            assert self.random_resize_and_pad_min < self.random_resize_and_pad_max
+            assert self.random_resize_and_pad_min > 0
+            assert self.random_resize_and_pad_max <= 1.0
         unsupported = {
-            'random_resize_and_pad': -1 not in random_resize_and_pad,
             'resize_scaling_depth': bool(resize_scaling_depth) and -1 not in random_resize_and_crop,
         }
         bad = [k for k, v in unsupported.items() if v]
@@ -167,6 +173,11 @@ class Transforms(object):
                 raise NotImplementedError('crop-and-pad with padding modes other than constant')
             do_cp, win = plan['crop_pad']
             images_arr = [self._crop_pad(im, do_cp, win) for im in images_arr]
+        if 'resize_pad' in plan:                                                                                 # :578-622
+            if any(m != 'constant' for m in padding_modes):
+                raise NotImplementedError('resize-and-pad with padding modes other than constant')
+            do_rp, geo = plan['resize_pad']
+            images_arr = [self._resize_pad(im, m, do_rp, geo) for im, m in zip(images_arr, modes)]
         if 'remove' in plan:                                                                                     # :644-652, 878-953
             images_arr = [self._remove_patches(im, plan['remove'], rdev) for im in images_arr]
         outputs = []
@@ -268,6 +279,19 @@ class Transforms(object):
                 pad_left = (d_w * torch.rand(n_batch, device=rdev)).int()
                 win = torch.stack([start_y.int(), start_x.int(), (end_y - start_y).int(), (end_x - start_x).int(), pad_top, pad_left], dim=1)
                 plan['crop_pad'] = (do_cp, keep(win.to(device=device, dtype=torch.int32)))
+            if self.do_random_resize_and_pad:                                                                    # :578-612
+                do_rp = keep(torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50).to(torch.uint8))
+                r_height = torch.randint(low=int(self.random_resize_and_pad_min * n_height), high=int(self.random_resize_and_pad_max * n_height),
+                                         size=(n_batch,), device=rdev)
+                r_width = torch.randint(low=int(self.random_resize_and_pad_min * n_width), high=int(self.random_resize_and_pad_max * n_width),
+                                        size=(n_batch,), device=rdev)
+                d_h = (n_height - r_height).int()
+                pad_top = (d_h * torch.rand(n_batch, device=rdev)).int()
+                d_w = (n_width - r_width).int()
+                pad_left = (d_w * torch.rand(n_batch, device=rdev)).int()
+                pad_top, pad_left = torch.clamp(pad_top, min=0), torch.clamp(pad_left, min=0)
+                geo = torch.stack([r_height.int(), r_width.int(), pad_top, pad_left], dim=1)
+                plan['resize_pad'] = (do_rp, keep(geo.to(device=device, dtype=torch.int32)))
             if self.do_random_remove_patch:                                                                      # :625-643
                 do_rm = torch.logical_and(do_random_transform, self._rand(n_batch, device) <= 0.50)
                 values = self._rand(n_batch, device)
@@ -335,6 +359,14 @@ class Transforms(object):
         out = torch.empty_like(images)
         check(_lib.lib().ptta_augment_remove_patches(ptr(images), ptr(out), n, c, h, w, ptr(do_rm), ptr(sel), ptr(patch), _stream()),
               'augment_remove_patches')
+        return out
+
+    @staticmethod
+    def _resize_pad(images, mode, do_rp, geo):
+        images = images.float().contiguous()
+        n, c, h, w = images.shape
+        out = torch.empty_like(images)
+        check(_lib.lib().ptta_augment_resize_pad(ptr(images), ptr(out), n, c, h, w, ptr(do_rp), ptr(geo), mode, _stream()), 'augment_resize_pad')
         return out
 
     @staticmethod
