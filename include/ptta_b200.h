@@ -321,6 +321,9 @@ int ptta_augment_remove_patches(const float* in, float* out, int n, int c, int h
  * release the reference pins; later releases filter a bilinear reduction by default). */
 int ptta_augment_resize_pad(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_resize_pad,
                             const int* geometry_n_x_4, int mode, ptta_stream_t stream);
+/* ptta_augment_divide_samples: src/transforms.py:1274-1275 (`resize_scaling_depth`) -- in place, data[n][:] /= divisor[n] (IEEE fp32 division)
+ * for the samples whose flag is set; the caller passes float32(r_width / n_width) of the resize-and-crop draw. */
+int ptta_augment_divide_samples(float* data, int n, long long per_sample, const unsigned char* do_divide, const float* divisor_n, ptta_stream_t stream);
 int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate,
                         const float* theta_n_x_6, int mode, ptta_stream_t stream);
 int ptta_augment_resize_crop(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_resize,

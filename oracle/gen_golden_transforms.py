@@ -48,6 +48,8 @@ CASES = [
     dict(name='rotate25_p05', seed=19, n=8, h=16, w=16, prob=0.5, kinds=['image', 'depth'], modes=['bilinear', 'nearest'], ctor=dict(random_rotate_max=25)),
     dict(name='resize_crop', seed=20, n=6, h=16, w=24, prob=1.0, kinds=['image', 'depth', 'depth', 'depth'], modes=['bilinear', 'nearest', 'nearest', 'nearest'],
          intrinsics=True, ctor=dict(random_resize_and_crop=[1.0, 1.5])),
+    dict(name='resize_crop_scaled', seed=34, n=6, h=16, w=24, prob=1.0, kinds=['image', 'depth', 'depth'], modes=['bilinear', 'nearest', 'nearest'],
+         intrinsics=True, ctor=dict(random_resize_and_crop=[1.0, 1.5], resize_scaling_depth=True)),
     # the geometric set of the shipped adaptation scripts (bash/adapt/adapt_msgchn_vkitti.sh:37-41)
     dict(name='adapt_script_geometric', seed=21, n=8, h=24, w=40, prob=1.0, kinds=['image', 'depth', 'depth', 'depth'],
          modes=['bilinear', 'nearest', 'nearest', 'nearest'], intrinsics=True,

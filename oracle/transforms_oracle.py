@@ -157,6 +157,8 @@ def apply(images_arr, cfg, d, normalized_image_range=None, interpolation_modes=(
                     image = functional.resize(image, size=(int(d['r_height'][b]), int(d['r_width'][b])), interpolation=_MODE[mode])
                     y0, x0 = int(d['start_y'][b]), int(d['start_x'][b])
                     image = image[..., y0:y0 + h, x0:x0 + w]
+                    if i != 0 and cfg.get('resize_scaling_depth'):              # T:1274-1275: int64 0-d tensor / int -> float32 0-d tensor
+                        image = image / (d['r_width'][b] / w)
                 out.append(image)
             images_arr[i] = torch.stack(out, dim=0)
     if 'do_crop_and_pad' in d:                                                  # T:1072-1135 (constant padding)

@@ -221,8 +221,6 @@ def test_native_flips_at_frame_size():
 
 def test_unsupported_options_fail_loudly():
     from tta_depth_completion_b200.transforms import Transforms
-    with pytest.raises(NotImplementedError, match='resize_scaling_depth'):
-        Transforms(random_resize_and_crop=[1.0, 1.5], resize_scaling_depth=True)
     with pytest.raises(NotImplementedError, match='padding modes'):
         t = Transforms(random_crop_and_pad=[0.5, 1.0])
         t.rand_device = 'cpu'

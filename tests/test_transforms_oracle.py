@@ -53,6 +53,8 @@ def case_cfg(case):
     if 'random_resize_and_crop' in c:
         cfg['resize_and_crop'] = c['random_resize_and_crop']
         cfg['shape'] = (case['h'], case['w'])
+        if c.get('resize_scaling_depth'):
+            cfg['resize_scaling_depth'] = True
     return cfg
 
 

@@ -291,6 +291,18 @@ __global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ i
 // Per-sample enlargement to (rh, rw) >= (H, W) followed by the crop [sy, sy + H) x [sx, sx + W) (src/transforms.py:425-502, 1222-1283 ->
 // torchvision functional.resize -> F.interpolate, align_corners=False): only the H x W pixels that survive the crop are computed.
 // mode 0: nearest (source index floor(dst * in / out)), 1: bilinear (source coordinate max(in / out * (dst + 0.5) - 0.5, 0)).
+// src/transforms.py:1274-1275 (`resize_scaling_depth`): after resize-and-crop every tensor but the first is divided, per sample the transform
+// touched, by float32(r_width / n_width) -- an IEEE fp32 division per element, in place, as `image /= (r_width / n_width)` does
+__global__ void __launch_bounds__(256) divide_samples_kernel(float* __restrict__ data, long long per_sample, const unsigned char* __restrict__ flags,
+                                                             const float* __restrict__ divisor) {
+    PDL_SYNC();
+    const int n = blockIdx.y;
+    if (!flags[n]) return;
+    const float d = divisor[n];
+    float* p = data + (size_t)n * per_sample;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < per_sample; i += gridDim.x * 256ll) p[i] = __fdiv_rn(p[i], d);
+}
+
 __global__ void __launch_bounds__(256) resize_crop_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
                                                           const unsigned char* __restrict__ do_rs, const int* __restrict__ rh,
                                                           const int* __restrict__ rw, const int* __restrict__ sy, const int* __restrict__ sx,

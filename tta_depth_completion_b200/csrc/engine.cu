@@ -1920,6 +1920,13 @@ int ptta_augment_resize_pad(const float* in, float* out, int n, int c, int h, in
     return check_launch("resize_pad");
 }
 
+int ptta_augment_divide_samples(float* data, int n, long long per_sample, const unsigned char* do_divide, const float* divisor_n, ptta_stream_t stream) {
+    PTTA_CHECK(data && do_divide && divisor_n && n >= 1 && n <= 65535 && per_sample >= 1, "augment_divide_samples: bad argument");
+    const int bx = (int)std::max(1ll, std::min((per_sample + 511) / 512, (long long)cdiv(2368, n)));
+    launch_k(divide_samples_kernel, dim3(bx, n), 256, 0, (cudaStream_t)stream, data, per_sample, do_divide, divisor_n);
+    return check_launch("divide_samples");
+}
+
 int ptta_augment_rotate(const float* in, float* out, int n, int c, int h, int w, const unsigned char* do_rotate, const float* theta_n_x_6,
                         int mode, ptta_stream_t stream) {
     PTTA_CHECK(in && out && in != out && do_rotate && theta_n_x_6 && n >= 1 && c >= 1 && h >= 1 && w >= 1, "augment_rotate: bad argument");

@@ -14,7 +14,8 @@ Also native: the per-sample rotation (torchvision `functional.rotate` = affine g
 adaptation scripts enable (bash/adapt/adapt_msgchn_*.sh: brightness, contrast, saturation, horizontal flip, rotate 5, resize-and-crop
 1.0 .. 1.5) runs in the library; the random crop to a common shape is native as well.  Gamma and hue jitter and the additive noise are native too.  Crop-and-pad and resize-and-pad (constant padding; bilinear reductions WITHOUT anti-aliasing, as the torchvision release the reference
 pins computes them) and the random point removal are native.  What stays without a kernel raises NotImplementedError (no silent
-fallback): `resize_scaling_depth`, padding modes other than 'constant', interpolation modes other than nearest / bilinear."""
+fallback): padding modes other than 'constant', interpolation modes other than nearest / bilinear.  `resize_scaling_depth` (the depth tensors
+divided by the width ratio of the enlargement) is native."""
 import ctypes
 import math
 import random
@@ -62,12 +63,7 @@ class Transforms(object):
             assert self.random_resize_and_pad_min < self.random_resize_and_pad_max
             assert self.random_resize_and_pad_min > 0
             assert self.random_resize_and_pad_max <= 1.0
-        unsupported = {
-            'resize_scaling_depth': bool(resize_scaling_depth) and -1 not in random_resize_and_crop,
-        }
-        bad = [k for k, v in unsupported.items() if v]
-        if bad:
-            raise NotImplementedError('Transforms options without a native kernel: %s (DESIGN.md, scope table f2)' % ', '.join(bad))
+        self.resize_scaling_depth = resize_scaling_depth                                                        # :183
         # as in the reference, gamma alone does not trigger the uint8 cast (src/transforms.py:74-78 leaves it out of do_photometric_transforms)
         self.do_photometric_transforms = self.do_random_brightness or self.do_random_contrast or self.do_random_hue or self.do_random_saturation
         self.do_image_normalization = normalized_image_range is not None
@@ -167,6 +163,11 @@ class Transforms(object):
             do_rs, r_height, r_width, args = plan['resize']
             intrinsics_arr = self._adjust_intrinsics(intrinsics_arr, x_scales=(r_width / n_width), y_scales=(r_height / n_height))
             images_arr = [self._resample('resize_crop', im, m, do_rs, *args) for im, m in zip(images_arr, modes)]
+            if self.resize_scaling_depth:                                                                        # :1274-1275: every tensor but the first
+                divisor = (r_width / n_width).to(device=images_arr[0].device, dtype=torch.float32)
+                for im in images_arr[1:]:
+                    check(_lib.lib().ptta_augment_divide_samples(ptr(im), im.shape[0], im[0].numel(), ptr(do_rs), ptr(divisor), _stream()),
+                          'augment_divide_samples')
             intrinsics_arr = self._adjust_intrinsics(intrinsics_arr, x_offsets=(r_width - n_width), y_offsets=(r_height - n_height))
         if 'crop_pad' in plan:                                                                                   # :508-566
             if any(m != 'constant' for m in padding_modes):
