@@ -176,6 +176,14 @@ int ptta_tta_loss_backward(const float* pred, const float* image_raw, const floa
  * tensors (NLSPN adapt mode 'meta_bn' after convert_syncbn: src/nlspn_model_adapt.py:328-337 on SyncBatchNorm-converted BatchNorm1d) */
 int ptta_tta_loss_backward_emb(const void* emb_bf16, const void* ref_bf16, long long rows, int dim, void* workspace, float gscale,
                                void* g_emb_bf16, int n, int h, int w, ptta_stream_t stream);
+/* stage-2 loss of the source-domain preparation on stand-alone buffers: mean(2 - 2 cos(emb, ref)), no loss_cos gate
+ * (src/external_model_adapt.py:524-540 `prepare_loss`); workspace as ptta_tta_loss_forward (float 0 = the loss), followed by
+ * ptta_tta_loss_backward_emb for d loss / d emb. */
+int ptta_cos_loss_forward(const void* emb_bf16, const void* ref_bf16, long long rows, int dim, void* workspace, int n, int h, int w,
+                          ptta_stream_t stream);
+/* EMA copy of a head tensor: target <- target * tau + source * (1 - tau) in the reference's operation order
+ * (external_src/NLSPN/src/model/nlspnmodel_adapt.py:1314-1316 `_update_head`). */
+int ptta_ema_update(float* target, const float* source, long long count, double tau, ptta_stream_t stream);
 
 /* ---- general-channel convolutions of the NLSPN network (tcgen05, csrc/conv_gen.cuh) ------------------------------
  * external_src/NLSPN/src/model/nlspnmodel_adapt.py:384-448 (resnet34.layer1-4 = torchvision BasicBlock stacks, conv6,

@@ -57,9 +57,24 @@ from tta_depth_completion_b200.synthetic import (make_nlspn_checkpoint as make_s
 # ----------------------------------------------------------------------------------------------------------------
 # network pieces
 # ----------------------------------------------------------------------------------------------------------------
+_BN_RUNNING = [False]
+
+
+class running_batchnorm:
+    """stage 2 (src/head_main.py): `train_prepare()` (W:360-368) puts every BatchNorm outside proj / pred into eval mode and nothing has
+    removed the running statistics there (adapt_parameters is not called), so the frozen encoder normalises with them"""
+    def __enter__(self):
+        _BN_RUNNING[0] = True
+
+    def __exit__(self, *a):
+        _BN_RUNNING[0] = False
+
+
 def _bn2d(sd, name, x):
     """Every BatchNorm2d after adapt_parameters('meta_bn') (W:322-337): batch statistics in train AND eval, no running
     statistics (track_running_stats False, buffers None)."""
+    if _BN_RUNNING[0]:
+        return F.batch_norm(x, sd[name + '.running_mean'], sd[name + '.running_var'], sd[name + '.weight'], sd[name + '.bias'], False, 0.1, BN_EPS)
     return F.batch_norm(x, None, None, sd[name + '.weight'], sd[name + '.bias'], True, 0.1, BN_EPS)
 
 
@@ -212,6 +227,58 @@ def tta_step(sd, state, image, sparse_depth, *, lr=3e-4, w_sd=1.0, w_sm=1.0, w_c
     res = {'validity': v_f, 'sparse_depth': d_f, 'output_depth': out.detach(), 'loss': float(loss),
            'loss_smooth': float(info['loss_smooth']), 'loss_sparse_depth': float(info['loss_sparse_depth']),
            'loss_cos': float(info['loss_cos'])}
+    if return_grads:
+        res['grads'] = grads
+        res['emb'] = emb.detach()
+        res['ref'] = ref.detach()
+    return res
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# stage 2 of the source-domain preparation on the NLSPN back-end: the predictor heads (src/head_main.py:259-275, 437-480)
+# ----------------------------------------------------------------------------------------------------------------
+HEAD_TRAINED = tuple('%s.%s.%s' % (m, i, q) for m in ('proj', 'pred') for i in ('0', '1', '3') for q in ('weight', 'bias'))   # W:261-265
+_HEAD_FLOAT = ('0.weight', '0.bias', '1.weight', '1.bias', '3.weight', '3.bias')
+
+
+def _mlp_stage2(sd, name, x, train_bn, pr):
+    """MLP head with its BatchNorm1d as stage 2 leaves it: running statistics present; train mode (batch statistics, running statistics
+    and num_batches_tracked updated) for proj / pred, eval mode for proj_t (W:360-368 after convert_syncbn, head_main.py:275)"""
+    h = pr.act(F.linear(x, pr.wgt(sd[name + '.0.weight']), sd[name + '.0.bias']))
+    if train_bn:
+        sd[name + '.1.num_batches_tracked'] += 1
+    h = F.batch_norm(h, sd[name + '.1.running_mean'], sd[name + '.1.running_var'], sd[name + '.1.weight'], sd[name + '.1.bias'], train_bn, 0.1, 1e-5)
+    return pr.act(F.linear(pr.act(F.relu(h)), pr.wgt(sd[name + '.3.weight']), sd[name + '.3.bias']))
+
+
+def head_step(sd, state, image, sparse_depth, *, lr, pr=FP32, tau=0.999, weight_decay=0.0, return_grads=False):
+    """One stage-2 step with forward 'head_meta_selfsup_seq_ema_reverse' = _rgbd_meta_contrast_prepare, mode [seq, reverse, ema]
+    (M:1014-1060): both encoders under no_grad (BatchNorm2d in eval mode), proj_t <- EMA(proj) over its parameters (M:1314-1316),
+    emb = pred(proj(fe6 of the zero image)), ref = proj_t(fe6 of the frame).detach(); loss 'prepare' = mean(2 - 2 cos) (E:524-540);
+    Adam over proj.* and pred.* -- unlike MSG-CHN's variant only the INPUT of proj is detached (M:1057), so both heads train.
+    `image` is the normalised network input (head_main.py:457-467 feeds the augmented image).  Mutates `sd`, `state`."""
+    names = list(state.m.keys())
+    with torch.no_grad():
+        with running_batchnorm():
+            fe6 = encoder(sd, image, sparse_depth, pr)[-1]
+            fe6_z = encoder(sd, torch.zeros_like(image), sparse_depth, pr)[-1]
+        for k in _HEAD_FLOAT:
+            sd['proj_t.' + k].copy_(sd['proj_t.' + k] * tau + sd['proj.' + k] * (1.0 - tau))
+    work = dict(sd)
+    leaves = {}
+    for k in names:
+        leaves[k] = sd[k].detach().clone().requires_grad_(True)
+        work[k] = leaves[k]
+    emb = _mlp_stage2(work, 'pred', _mlp_stage2(work, 'proj', fe6_z.permute(0, 2, 3, 1).reshape(-1, 512), True, pr), True, pr)
+    with torch.no_grad():
+        ref = _mlp_stage2(sd, 'proj_t', fe6.permute(0, 2, 3, 1).reshape(-1, 512), False, pr)
+    e = F.normalize(emb, dim=-1, p=2)
+    r = F.normalize(ref, dim=-1, p=2)
+    loss = (2 - 2 * (e * r).sum(-1)).mean()
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(names, grads)}
+    O.adam_update(sd, grads, state, lr, weight_decay=weight_decay)
+    res = {'loss': float(loss.detach())}
     if return_grads:
         res['grads'] = grads
         res['emb'] = emb.detach()

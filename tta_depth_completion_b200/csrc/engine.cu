@@ -1833,6 +1833,31 @@ int ptta_tta_loss_backward_emb(const void* emb, const void* ref, long long rows,
     return check_launch("loss_cos_grad(emb)");
 }
 
+// stage-2 loss on stand-alone buffers (the NLSPN head trainer, driven from Python): mean(2 - 2 cos(emb, ref)) with no gate
+// (src/external_model_adapt.py:524-540); same workspace layout as ptta_tta_loss_forward, so ptta_tta_loss_backward_emb follows it
+int ptta_cos_loss_forward(const void* emb, const void* ref, long long rows, int dim, void* workspace, int n, int h, int w, ptta_stream_t stream) {
+    PTTA_CHECK(emb && ref && workspace && rows >= 1, "cos_loss_forward: bad argument");
+    PTTA_CHECK(dim % 256 == 0, "cos_loss_forward: row length %d not a multiple of 256", dim);
+    const TtaLossLayout L = tta_loss_layout(n, h, w, rows);
+    char* ws = (char*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    launch_k(loss_cos_rows_kernel, L.cos_blocks, 256, 0, st, (const bf16*)emb, (const bf16*)ref, (float*)(ws + L.rowstat), (double*)(ws + L.cos_partial), rows, dim);
+    PTTA_TRY(check_launch("loss_cos_rows"));
+    launch_k(cos_loss_finalize_kernel, 1, 256, 0, st, (const double*)(ws + L.cos_partial), L.cos_blocks, rows, (LossScalars*)(ws + L.scalars));
+    return check_launch("cos_loss_finalize");
+}
+
+// target <- target * tau + source * (1 - tau), two products and one sum (no FMA) like the reference's tensor expression
+// (nlspnmodel_adapt.py:1314-1316, network_exp_msg_chn_adapt.py:701-703); 1 - tau is formed in double like the Python float
+int ptta_ema_update(float* target, const float* source, long long count, double tau, ptta_stream_t stream) {
+    PTTA_CHECK(target && source && count >= 1, "ema_update: bad argument");
+    EmaParams ep; memset(&ep, 0, sizeof(ep));
+    ep.t[0] = target; ep.s[0] = source; ep.n[0] = count; ep.count = 1;
+    ep.tau = (float)tau; ep.one_minus_tau = (float)(1.0 - tau);
+    launch_k(ema_update_kernel, dim3(cdiv(count, 256), 1), 256, 0, (cudaStream_t)stream, ep);
+    return check_launch("ema_update");
+}
+
 // ---- on-device augmentations (augment.cuh) ----------------------------------------------------------------------
 int ptta_augment_photometric(const float* image, float* out, int n, int h, int w, const unsigned char* do_brightness, const float* f_brightness,
                              const unsigned char* do_contrast, const float* f_contrast, const unsigned char* do_saturation,

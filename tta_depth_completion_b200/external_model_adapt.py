@@ -599,6 +599,13 @@ class ExternalModel_Adapt(object):
 
     def head_step(self, image_raw, sparse_depth, learning_rate, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, graph=False):
         """One whole stage-2 step (src/head_main.py:437-480) in one library call."""
+        if self.model_name == 'nlspn':                    # orchestrated from Python over the C ABI (nlspn_prepare.NlspnHeadTrainer)
+            if getattr(self.model, 'img_scale', None) is None:
+                raise RuntimeError('NLSPN head_step: call set_image_normalization(scale, shift) first (ImageNet statistics folded into the stem)')
+            self._last_engine = self.model.head_step(image_raw.contiguous(), sparse_depth.contiguous(), learning_rate, betas, eps, weight_decay,
+                                                     max_input_depth=self.max_input_depth, img_scale=self.model.img_scale,
+                                                     img_shift=self.model.img_shift)
+            return
         eng = self._prep_engine(image_raw, 'head', (learning_rate, betas, eps, weight_decay))
         eng.head_step(image_raw, sparse_depth, self.max_input_depth, self.model.img_scale, self.model.img_shift, graph=graph)
         self._last_engine = eng
@@ -657,6 +664,8 @@ class ExternalModel_Adapt(object):
         self._last_engine = eng
 
     def last_losses(self):
+        if hasattr(self._last_engine, 'read_loss'):       # NLSPN stage-2 trainer: one scalar
+            return {'loss': self._last_engine.read_loss()}
         return self._last_engine.read_losses()
 
     def last_losses_device(self):

@@ -217,6 +217,18 @@ class NlspnEngine:
 
     def bn_stats(self, bn, x, gamma, beta, running=None):
         rows, c = x.numel() // x.shape[-1], x.shape[-1]
+        if getattr(self, 'bn_running', False):
+            # eval-mode BatchNorm2d (stage 2 of the preparation, src/nlspn_model_adapt.py:360-368): scale / shift from the running
+            # statistics, computed once per layer -- the encoder is frozen there
+            key = bn.split('.', 1)[1]
+            st = self.bn_eval_state.get(key) if hasattr(self, 'bn_eval_state') else None
+            if st is None:
+                if not hasattr(self, 'bn_eval_state'):
+                    self.bn_eval_state = {}
+                scale = gamma / torch.sqrt(self.sd[key + '.running_var'] + BN_EPS)
+                st = {'scale': scale.contiguous(), 'shift': (beta - self.sd[key + '.running_mean'] * scale).contiguous()}
+                self.bn_eval_state[key] = st
+            return st
         st = self.bn_state.get(bn)
         if st is None:
             st = {k: torch.empty(c, dtype=torch.float32, device=self.dev) for k in ('mean', 'rstd', 'scale', 'shift')}

@@ -227,6 +227,47 @@ class NLSPNModel_Adapt(object):
         self.adapt = True
         return torch.nn.ParameterList(list(self._param_objs.values()))
 
+    def prepare_parameters(self, mode=''):
+        """src/nlspn_model_adapt.py:242-285.  'head...' (src/head_main.py:268 passes 'head_selfsup_ema'): proj / proj_t / pred are re-created
+        from torch's global generator exactly as the reference's `_prepare_head(mode)` does, and the parameters of proj and pred are returned
+        (proj_t is the EMA copy) in the reference, which hands them to torch.optim.Adam.  Here the whole step incl. Adam is the library call
+        `head_step` (the trained tensors live in its flat buffer, created when the first frame fixes the input shape), so the returned list
+        is empty; the trained tensors are read through `state_dict()` / `save_model`.  Other modes raise."""
+        if 'head' not in mode:
+            raise NotImplementedError('NLSPN native back-end: prepare_parameters(%r) (stage 2, "head...", is implemented)' % (mode,))
+        if self._sd is None:
+            raise RuntimeError('_prepare_head(mode) and restore_model(...) come first (src/head_main.py:259-266)')
+        from .nlspn_prepare import fresh_head_state
+        sd = OrderedDict((k, v.detach().clone().cpu()) for k, v in self.state_dict().items())
+        sd.update(fresh_head_state())
+        self._sd = sd
+        self._reset_engines()
+        self._trainable, self._head_trainer, self._head_key = 'head', None, None
+        return []
+
+    def _head_trainer_for(self, image):
+        if getattr(self, '_trainable', None) != 'head':
+            raise RuntimeError("call prepare_parameters('head_selfsup_ema') first")
+        key = (image.shape[0], image.shape[2], image.shape[3])
+        if self._head_trainer is None:
+            from .nlspn_prepare import NlspnHeadTrainer
+            n, h, w = key
+            eng = NlspnEngine(self._sd, n, h, w, self.device, prop_time=self.prop_time, legacy=self.legacy, syncbn=False)
+            self._base, self._engines[key], self._sd = eng, eng, eng.sd
+            self._head_trainer, self._head_key = NlspnHeadTrainer(eng), key
+        elif key != self._head_key:
+            raise NotImplementedError('stage-2 training keeps one input shape (the reference crops every batch to n_height x n_width)')
+        return self._head_trainer
+
+    def head_step(self, image, sparse_depth, learning_rate, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_input_depth=None,
+                  img_scale=None, img_shift=None):
+        """One whole stage-2 step (src/head_main.py:437-480) through the library; `image` is the network input unless a normalisation is folded
+        into the stem (img_scale / img_shift)."""
+        tr = self._head_trainer_for(image)
+        tr.eng.set_image_normalization(img_scale, img_shift)
+        tr.head_step(image, sparse_depth, learning_rate, betas, eps, weight_decay, max_input_depth=max_input_depth)
+        return tr
+
     def train(self):
         self.training = True
 
