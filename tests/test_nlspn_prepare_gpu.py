@@ -165,3 +165,25 @@ def test_head_training_through_the_wrapper():
         assert float((got - sd0[k].flatten()[::S]).norm()) > 0.5 * upd, k                # and it did move
     with pytest.raises(NotImplementedError):
         m.prepare_parameters('init_meta')
+
+
+def test_captured_head_step_equals_eager():
+    """graph=True (frame copied into trainer-owned staging buffers, step captured on the second call and replayed) against the eager
+    launches, a fresh input tensor every step: same losses and the same trained tensors bit for bit"""
+    dev = torch.device('cuda:0')
+    case = dict(ckpt_seed=2, seed=77, n=1, h=64, w=128, dataset='kitti', cap=80.0, lr=1e-3, seq=9)
+    trainers = [make_trainer(initial_state(case), 1, 64, 128, dev) for _ in range(2)]
+    stream = torch.cuda.Stream()
+    for t in range(5):
+        image, sparse, _ = NO.synthetic_frame(case['seq'], t, 1, 64, 128, 'kitti')
+        image, sparse = NO.normalize_image(image).to(dev), sparse.to(dev)
+        trainers[0].head_step(image, sparse, case['lr'], max_input_depth=case['cap'])
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            trainers[1].head_step(image.clone(), sparse.clone(), case['lr'], max_input_depth=case['cap'], graph=True)
+        torch.cuda.current_stream().wait_stream(stream)
+        assert trainers[0].read_loss() == trainers[1].read_loss(), t
+    assert trainers[1]._graph is not None
+    for k in trainers[0].params:
+        assert torch.equal(trainers[0].params[k], trainers[1].params[k]), k
+        assert torch.equal(trainers[0].eng.sd['proj_t.0.weight'], trainers[1].eng.sd['proj_t.0.weight'])

@@ -57,7 +57,8 @@ def main():
         ws = torch.empty(n, dtype=torch.int64, device=DEV)
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         P = _lib.ptr
-        ms = timed(lambda: L.ptta_augment_photometric(P(img), P(o), n, h, w, P(on), P(f), P(on), P(f), P(on), P(f), 1, 1, None, None, P(ws), st), 200)
+        ms = timed(lambda: L.ptta_augment_photometric(P(img), P(o), n, h, w, P(on), P(f), P(on), P(f), P(on), P(f), None, None, None, None, None, None, 0.0, 0,
+                                                          1, 1, None, None, P(ws), st), 200)
         alg = 3 * img.numel() * 4          # grey-sum pass reads the image, the apply pass reads it again and writes the result
         out['augment_photometric_%dx352x1216' % n] = {'us': round(ms * 1e3, 2), 'algorithmic_GBps': round(alg / ms / 1e6, 1)}
         ms = timed(lambda: L.ptta_augment_flip(P(img), P(o), n, 3, h, w, P(on), None, st), 200)
@@ -100,6 +101,40 @@ def main():
             step()
             out['%s_step_%dx352x1216' % (stage, n)] = {'ms': round(ms, 3), 'frames_per_s': round(n * 1e3 / ms, 1), 'ms_graph': round(ms_graph, 3), 'launches': eng.launch_count() - l0,
                                                        'loss': round(model.last_losses()['loss'], 5)}
+    # stage 2 on the NLSPN back-end (nlspn_prepare.NlspnHeadTrainer: Python-orchestrated launches over the C ABI, eager)
+    from tta_depth_completion_b200.synthetic import make_nlspn_checkpoint, IMAGENET_MEAN, IMAGENET_STD
+    for n in args.batch:
+        model = ExternalModel_Adapt('nlspn', 0.0, 100.0, max_input_depth=80.0, offset=True, device=torch.device(DEV))
+        model._prepare_head('meta_selfsup_seq_1layer_ema')
+        model.load_state_dict(make_nlspn_checkpoint(0))
+        torch.manual_seed(1)
+        model.prepare_parameters('head_selfsup_ema')
+        model.set_image_normalization([1.0 / (255.0 * s_) for s_ in IMAGENET_STD], [-m_ / s_ for m_, s_ in zip(IMAGENET_MEAN, IMAGENET_STD)])
+        frames = [tuple(t.to(DEV) for t in synthetic_frame(60, k, n, 352, 1216, 'kitti')) for k in range(4)]
+        k = [0]
+
+        def nstep():
+            im, sp, gt = frames[k[0] % 4]
+            k[0] += 1
+            model.head_step(im, sp, 1e-3)
+        ms = timed(nstep, args.iters)
+        tr = model._last_engine
+        l0 = tr.launches + tr.eng.launches
+        nstep()
+        n_launch = tr.launches + tr.eng.launches - l0
+        stream = torch.cuda.Stream()
+
+        def ngstep():
+            im, sp, gt = frames[k[0] % 4]
+            k[0] += 1
+            model.head_step(im, sp, 1e-3, graph=True)
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            ms_graph = timed(ngstep, args.iters)
+        torch.cuda.current_stream().wait_stream(stream)
+        out['nlspn_head_step_%dx352x1216' % n] = {'ms': round(ms, 3), 'frames_per_s': round(n * 1e3 / ms, 1), 'ms_graph': round(ms_graph, 3),
+                                                   'frames_per_s_graph': round(n * 1e3 / ms_graph, 1), 'launches': n_launch,
+                                                   'loss': round(model.last_losses()['loss'], 5)}
     print(json.dumps(out))
 
 

@@ -604,7 +604,7 @@ class ExternalModel_Adapt(object):
                 raise RuntimeError('NLSPN head_step: call set_image_normalization(scale, shift) first (ImageNet statistics folded into the stem)')
             self._last_engine = self.model.head_step(image_raw.contiguous(), sparse_depth.contiguous(), learning_rate, betas, eps, weight_decay,
                                                      max_input_depth=self.max_input_depth, img_scale=self.model.img_scale,
-                                                     img_shift=self.model.img_shift)
+                                                     img_shift=self.model.img_shift, graph=graph)
             return
         eng = self._prep_engine(image_raw, 'head', (learning_rate, betas, eps, weight_decay))
         eng.head_step(image_raw, sparse_depth, self.max_input_depth, self.model.img_scale, self.model.img_shift, graph=graph)

@@ -260,12 +260,12 @@ class NLSPNModel_Adapt(object):
         return self._head_trainer
 
     def head_step(self, image, sparse_depth, learning_rate, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_input_depth=None,
-                  img_scale=None, img_shift=None):
+                  img_scale=None, img_shift=None, graph=False):
         """One whole stage-2 step (src/head_main.py:437-480) through the library; `image` is the network input unless a normalisation is folded
         into the stem (img_scale / img_shift)."""
         tr = self._head_trainer_for(image)
         tr.eng.set_image_normalization(img_scale, img_shift)
-        tr.head_step(image, sparse_depth, learning_rate, betas, eps, weight_decay, max_input_depth=max_input_depth)
+        tr.head_step(image, sparse_depth, learning_rate, betas, eps, weight_decay, max_input_depth=max_input_depth, graph=graph)
         return tr
 
     def train(self):

@@ -88,6 +88,7 @@ class NlspnHeadTrainer:
         for name in ('proj', 'proj_t', 'pred'):
             self._repack(name)
         self.launches = 0
+        self._graph, self._graph_key, self._seen_key = None, None, None
 
     # ---- helpers ------------------------------------------------------------------------------------------------------------------
     def _repack(self, name):
@@ -161,30 +162,64 @@ class NlspnHeadTrainer:
         return dx
 
     # ---- one step --------------------------------------------------------------------------------------------------------------------
-    def head_step(self, image_norm, sparse_depth, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_input_depth=None, tau=0.999):
-        """image_norm: the normalised network input (fp32 NCHW); sparse_depth fp32 [N,1,H,W].  Returns nothing; `read_loss()` reads the loss."""
-        L, e = _lib.lib(), self.eng
-        sd = e.sd
+    def head_step(self, image_norm, sparse_depth, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_input_depth=None, tau=0.999, graph=False):
+        """image_norm: the normalised network input (fp32 NCHW); sparse_depth fp32 [N,1,H,W].  Returns nothing; `read_loss()` reads the loss.
+        graph=True: the frame is copied into trainer-owned staging buffers and the step is captured into a CUDA graph the second time it is
+        called, then replayed (a fresh tensor may be passed every step; needs a non-default stream)."""
         self.set_adam(lr, betas, eps, weight_decay)
         image_norm, sparse_depth = image_norm.contiguous(), sparse_depth.contiguous()
+        if not graph:
+            return self._step_body(image_norm, sparse_depth, max_input_depth, tau)
+        e = self.eng
+        img_in = e.buf('head.stage.image', tuple(image_norm.shape), torch.float32)
+        dep_in = e.buf('head.stage.depth', tuple(sparse_depth.shape), torch.float32)
+        img_in.copy_(image_norm, non_blocking=True)
+        dep_in.copy_(sparse_depth, non_blocking=True)
+        key = (max_input_depth, float(tau), e.img_scale is None)
+        if self._graph is not None and self._graph_key == key:
+            self._graph.replay()
+            return
+        if self._seen_key != key:
+            self._seen_key = key                               # first call: eager (allocates every buffer, sets kernel attributes)
+            return self._step_body(img_in, dep_in, max_input_depth, tau)
+        g = torch.cuda.CUDAGraph()
+        l0 = self.launches + e.launches
+        torch.cuda.synchronize(self.dev)
+        with torch.cuda.graph(g):
+            self._step_body(img_in, dep_in, max_input_depth, tau)
+        self.launches_per_step = self.launches + e.launches - l0
+        self._graph, self._graph_key = g, key
+        g.replay()
+
+    def _step_body(self, image_norm, sparse_depth, max_input_depth, tau):
+        L, e = _lib.lib(), self.eng
+        sd = e.sd
+        R = e.R
         if max_input_depth is not None:                                  # src/external_model_adapt.py:103-108
             d_c = e.buf('head.depth', tuple(sparse_depth.shape), torch.float32)
             check(L.ptta_nl_clamp(ptr(sparse_depth), ptr(d_c), 0.0, float(max_input_depth), d_c.numel(), _stream()), 'nl_clamp')
             sparse_depth = d_c
+        # the zero-image encoder and the two trained heads on top of it depend only on the sparse depth: they run on a second stream beside
+        # the frame's encoder (fork / join through events, also inside a CUDA-graph capture), as NlspnEngine.forward does for the TTA step
+        main, side = torch.cuda.current_stream(), e.side_stream
         e.bn_running = True                                              # frozen encoder: eval-mode BatchNorm2d (running statistics)
         try:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                fe6_z = e.encoder('z.', None, sparse_depth)[-1]
+                e.bn_running = False
+                p_out, p_saved = self._mlp_forward('z.head.proj', 'proj', fe6_z.reshape(R, 512), True)
+                emb, q_saved = self._mlp_forward('z.head.pred', 'pred', p_out, True)
+                e.bn_running = True
             fe6 = e.encoder('r.', image_norm, sparse_depth)[-1]
-            fe6_z = e.encoder('z.', None, sparse_depth)[-1]
         finally:
             e.bn_running = False
-        R = e.R
         for k in _EMA_KEYS:                                              # nlspnmodel_adapt.py:1055 -> :1314-1316
             t = sd['proj_t.' + k]
             check(L.ptta_ema_update(ptr(t), ptr(sd['proj.' + k]), t.numel(), float(tau), _stream()), 'ema_update')
         self._repack('proj_t')
-        p_out, p_saved = self._mlp_forward('head.proj', 'proj', fe6_z.reshape(R, 512), True)
-        emb, q_saved = self._mlp_forward('head.pred', 'pred', p_out, True)
         ref, _ = self._mlp_forward('head.proj_t', 'proj_t', fe6.reshape(R, 512), False)
+        main.wait_stream(side)
         check(L.ptta_cos_loss_forward(ptr(emb), ptr(ref), R, 1024, ptr(self.loss_ws), e.N, e.H, e.W, _stream()), 'cos_loss_forward')
         g_emb = e.buf('head.g_emb', (R, 1024))
         check(L.ptta_tta_loss_backward_emb(ptr(emb), ptr(ref), R, 1024, ptr(self.loss_ws), 1.0, ptr(g_emb), e.N, e.H, e.W, _stream()), 'loss_backward_emb')
