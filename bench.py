@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the ProxyTTA per-frame adaptation step (BASELINE.json: adapted frames/s, fwd+bwd+update, 352x1216).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload kitti|void|nlspn|prepare_init|prepare_head] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload kitti|void|nlspn|prepare_init|prepare_head|prepare_head_nlspn] [--batch B]
 
 One "step" = src/tta_main.py:583-633 of the reference for one batch: outlier removal, forward (real + zero-image
 branch + proxy heads), the three losses, backward to the adapted meta layer, Adam.  Workload at N=1 = BASELINE.json
@@ -40,9 +40,11 @@ WORKLOADS = {
     'nlspn_void': (480, 640, 'void', 'meta_selfsup_seq_1layer_ema', 3e-4, 8.0),
 }
 # the source-domain preparation stages on the KITTI-shape workload (src/init_main.py / src/head_main.py steps)
-PREPARE = {'prepare_init': 'init', 'prepare_head': 'head'}
+PREPARE = {'prepare_init': 'init', 'prepare_head': 'head', 'prepare_head_nlspn': 'head'}
 for _k in PREPARE:
     WORKLOADS[_k] = (352, 1216, 'kitti', 'meta_selfsup_seq_2layers_ema', 1e-3, 80.0)
+# stage 2 on the NLSPN back-end (tta_depth_completion_b200/nlspn_prepare.py)
+WORKLOADS['prepare_head_nlspn'] = (352, 1216, 'kitti', 'meta_selfsup_seq_1layer_ema', 1e-3, 80.0)
 NLSPN_GFLOP_STEP = 3445.9        # forward 2 227.0 + required dgrad 1 201.1 + wgrad 17.8 at 1x352x1216
 W_SD, W_SM, W_COS = 1.0, 1.0, 0.1
 RING = 8                      # distinct frames cycled through (device-resident for `value`, pinned host for `e2e`)
@@ -217,6 +219,17 @@ def prepare_cpu_steps(args, steps, warmup):
     from oracle import msgchn_oracle as O
     h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
     torch.set_num_threads(os.cpu_count() or 1)
+    if args.workload == 'prepare_head_nlspn':
+        from oracle import nlspn_oracle as NO
+        sd = NO.make_synthetic_checkpoint(0)
+        state = O.AdamState(list(NO.HEAD_TRAINED), sd)
+        frames = prepare_frames(args.workload, args.batch, 2, 1)
+        for i in range(warmup):
+            NO.head_step(sd, state, NO.normalize_image(frames[i % 2][0]), torch.clamp(frames[i % 2][1], 0, cap), lr=lr)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            NO.head_step(sd, state, NO.normalize_image(frames[i % 2][0]), torch.clamp(frames[i % 2][1], 0, cap), lr=lr)
+        return (time.perf_counter() - t0) / steps
     sd, names = prepare_state(args.workload)
     state = O.AdamState(names, sd)
     frames = prepare_frames(args.workload, args.batch, 2, 1)
@@ -247,8 +260,8 @@ def run_reference(args):
         value = args.batch / dt
         h, w = WORKLOADS[args.workload][:2]
         cb = {'value': value, 'unit': 'frames/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
-              'sample': '%d full-size %s steps (%dx3x%dx%d) of oracle/msgchn_oracle.py, torch %s CPU fp32, %.2f s/step' % (
-                  steps, PREPARE[args.workload], args.batch, h, w, torch.__version__, dt)}
+              'sample': '%d full-size %s steps (%dx3x%dx%d) of oracle/%s_oracle.py, torch %s CPU fp32, %.2f s/step' % (
+                  steps, PREPARE[args.workload], args.batch, h, w, 'nlspn' if args.workload == 'prepare_head_nlspn' else 'msgchn', torch.__version__, dt)}
         print(json.dumps({'impl': 'reference', 'metric': 'trained_frames_per_sec', 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus,
                           'steps': steps, 'warmup': warm, 'ms_per_step': 1e3 * dt, 'higher_is_better': True, 'scaling': 'weak',
                           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args), 'cpu_baseline': cb,
@@ -299,8 +312,12 @@ def workload_config(args):
                         'backward to the meta layer, Adam)',
                 'head': 'stage-2 predictor-head training (src/head_main.py:437-480: frozen network on the frame and on the zero image, EMA copy of '
                         'proj, cosine loss, backward to pred.*, Adam)'}[PREPARE[args.workload]]
-        return {'workload': 'MSG-CHN source-domain preparation, %s, synthetic %s-shape %dx3x%dx%d frames, prepare_mode %s, lr %g, one step per '
-                            'batch, %d-frame ring (per-step working set >> L2)' % (what, dataset.upper(), args.batch, h, w, mode, lr, RING),
+        if args.workload == 'prepare_head_nlspn':
+            what = ('stage-2 predictor-head training on the NLSPN back-end (src/head_main.py:437-480 with nlspnmodel_adapt.py:1014-1060: both ResNet34 '
+                    'encoders with eval-mode BatchNorm on the frame and on the zero image, EMA copy of proj, cosine loss, backward to proj.* and pred.*, Adam)')
+        return {'workload': '%s source-domain preparation, %s, synthetic %s-shape %dx3x%dx%d frames, prepare_mode %s, lr %g, one step per '
+                            'batch, %d-frame ring (per-step working set >> L2)' % ('NLSPN' if args.workload == 'prepare_head_nlspn' else 'MSG-CHN', what,
+                                                                                  dataset.upper(), args.batch, h, w, mode, lr, RING),
                 'batch': args.batch, 'height': h, 'width': w}
     if args.workload.startswith('nlspn'):
         return {'workload': 'NLSPN ProxyTTA continual adaptation (ResNet34 encoder/decoder, 18-step non-local propagation), synthetic ' + dataset.upper() + '-shape '
@@ -675,13 +692,23 @@ def run_native_prepare(args):
     stage = PREPARE[args.workload]
     h, w, dataset, mode, lr, cap = WORKLOADS[args.workload]
     peaks = load_peaks()
-    model = ExternalModel_Adapt('msg_chn', 0.0, 100.0, max_input_depth=cap, device=dev)
+    nlspn = args.workload == 'prepare_head_nlspn'
+    model = ExternalModel_Adapt('nlspn' if nlspn else 'msg_chn', 0.0, 100.0, max_input_depth=cap, offset=True, device=dev)
     model._prepare_head(mode)
-    model.load_state_dict(make_checkpoint(args.workload))
+    if nlspn:
+        from tta_depth_completion_b200 import synthetic
+        model.load_state_dict(synthetic.make_nlspn_checkpoint(0))
+    else:
+        model.load_state_dict(make_checkpoint(args.workload))
     torch.manual_seed(0)
     if stage == 'head':
         model.prepare_parameters('head_selfsup_ema')            # src/head_main.py:268 (draws fresh heads)
-    model.set_image_normalization((1 / 255.0,) * 3, (0.0,) * 3)
+    if nlspn:
+        model.convert_syncbn()                                  # :278
+        model.set_image_normalization([1.0 / (255.0 * s_) for s_ in synthetic.IMAGENET_STD],
+                                      [-m_ / s_ for m_, s_ in zip(synthetic.IMAGENET_MEAN, synthetic.IMAGENET_STD)])
+    else:
+        model.set_image_normalization((1 / 255.0,) * 3, (0.0,) * 3)
     model.train()
     frames = prepare_frames(args.workload, args.batch, RING, 1 + rank)
     dev_frames = [tuple(t.to(dev) for t in f) for f in frames]
@@ -701,9 +728,10 @@ def run_native_prepare(args):
     with torch.cuda.stream(stream):
         run_step(dev_frames[0], False)
         eng = model._last_engine
-        l0 = eng.launch_count()
+        count = (lambda: eng.launches + eng.eng.launches) if nlspn else eng.launch_count
+        l0 = count()
         run_step(dev_frames[0], False)
-        launches_per_step = eng.launch_count() - l0
+        launches_per_step = count() - l0
         for i in range(max(3, args.warmup)):
             run_step(dev_frames[i % RING], args.graph)
         barrier()
@@ -745,17 +773,20 @@ def run_native_prepare(args):
     line = {'metric': 'trained_frames_per_sec', 'value': frames_total / (ms_total / 1e3), 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(3, args.warmup), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(args),
-            'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 20,
+            'e2e': {'value': frames_total / (ms_e2e / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 if nlspn else 20,
                     'ms_per_step': ms_e2e / args.steps, 'passes_ms': passes,
                     'input_staging': 'pinned host frames copied H2D on the compute stream every step, blocking loss read every step'},
             'gpu_launches': launches_per_step * args.steps, 'launches_per_step': launches_per_step, 'cuda_graph': bool(args.graph),
             'clocks': sampler.summary(), 'last_losses': losses}
     if world == 1 and not args.no_extras:
-        line['roofline'] = time_gemm_tn_kernel(dev, peaks, args.batch * (h // 4) * (w // 4)) if stage == 'head' else time_dominant_kernel(dev, peaks)
+        if nlspn:
+            line['roofline'] = time_convg_kernel(dev, peaks)        # the encoders' 64->64 convolutions: the step's dominant kernel
+        else:
+            line['roofline'] = time_gemm_tn_kernel(dev, peaks, args.batch * (h // 4) * (w // 4)) if stage == 'head' else time_dominant_kernel(dev, peaks)
         dt = prepare_cpu_steps(args, 2, 1)
         line['cpu_baseline'] = {'value': args.batch / dt, 'unit': 'frames/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
-                                'sample': '2 full-size %s steps (%dx3x%dx%d) of oracle/msgchn_oracle.py (torch %s CPU fp32) after 1 warm-up, %.2f s/step' % (
-                                    stage, args.batch, h, w, torch.__version__, dt)}
+                                'sample': '2 full-size %s steps (%dx3x%dx%d) of oracle/%s_oracle.py (torch %s CPU fp32) after 1 warm-up, %.2f s/step' % (
+                                    stage, args.batch, h, w, 'nlspn' if nlspn else 'msgchn', torch.__version__, dt)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
