@@ -187,3 +187,19 @@ def test_captured_head_step_equals_eager():
     for k in trainers[0].params:
         assert torch.equal(trainers[0].params[k], trainers[1].params[k]), k
         assert torch.equal(trainers[0].eng.sd['proj_t.0.weight'], trainers[1].eng.sd['proj_t.0.weight'])
+
+
+def test_preparation_forwards_without_a_kernel_path_fail_loudly():
+    from tta_depth_completion_b200.external_model_adapt import ExternalModel_Adapt
+    dev = torch.device('cuda:0')
+    m = ExternalModel_Adapt(model_name='nlspn', min_predict_depth=0.0, max_predict_depth=100.0, max_input_depth=80.0, offset=True,
+                            dataset_name='kitti', device=dev)
+    m._prepare_head(NO.PREPARE_MODE)
+    m.load_state_dict(NO.make_synthetic_checkpoint(0))
+    image, sparse, _ = NO.synthetic_frame(3, 0, 1, 32, 64, 'kitti')
+    for lt in ('head_meta_selfsup_seq_ema_reverse', 'init_meta_selfsup_seq_ema'):
+        with pytest.raises(NotImplementedError):
+            m.forward(image=NO.normalize_image(image).to(dev), sparse_depth=sparse.to(dev), intrinsics=None, loss_type=lt)
+    with pytest.raises(RuntimeError, match='prepare_parameters'):
+        m.set_image_normalization((1.0,) * 3, (0.0,) * 3)
+        m.head_step(image.to(dev), sparse.to(dev), 1e-3)

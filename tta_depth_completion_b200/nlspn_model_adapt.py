@@ -195,6 +195,10 @@ class NLSPNModel_Adapt(object):
         if loss_type is None:
             raise TypeError("argument of type 'NoneType' is not iterable")      # the reference evaluates `'time' in loss_type`
         image, sparse_depth = image.contiguous(), sparse_depth.contiguous()
+        if 'head' in loss_type or 'init_meta' in loss_type:
+            # the preparation forwards (nlspnmodel_adapt.py:511-585) return embeddings / a supervised prediction, not this path's eval depth
+            raise NotImplementedError('NLSPN native back-end: forward(loss_type=%r) -- stage 2 runs as the fused `head_step` '
+                                      '(nlspn_prepare.NlspnHeadTrainer), stage 1 is not built' % (loss_type,))
         if self.training and 'adapt' in loss_type:
             self._materialise(image.shape[0], image.shape[2], image.shape[3])
             return _NlspnForwardFn.apply(self, image, sparse_depth, *self._param_objs.values())
