@@ -35,6 +35,11 @@ offset, aff = NP.offset_affinity(offset_aff, conf, 4.0, True)
 px = n * h * w
 us = graph_time(lambda: NP.offset_affinity(offset_aff, conf, 4.0, True))
 print('offset_affinity fwd        %8.1f us   %6.0f GB/s (212 B/px)' % (us, px * 212 / us / 1e3))
+oa_r, cf_r = offset_aff.clone().requires_grad_(True), conf.clone().requires_grad_(True)
+o_r, a_r = NP.offset_affinity(oa_r, cf_r, 4.0, True)
+g_o, g_a = torch.randn_like(o_r), torch.randn_like(a_r)
+us = graph_time(lambda: torch.autograd.grad((o_r, a_r), (oa_r, cf_r), (g_o, g_a), retain_graph=True))
+print('offset_affinity bwd        %8.1f us   %6.0f GB/s (312 B/px + the confidence scatter)' % (us, px * 312 / us / 1e3))
 us = graph_time(lambda: NP.propagate(feat_init, offset, aff, sparse, T))
 print('propagate fwd (18 steps)   %8.1f us   %6.0f GB/s (116 B/px/step)  %.1f us/step' % (us, px * 116 * T / us / 1e3, us / T))
 fi, of, af = (t.clone().requires_grad_(True) for t in (feat_init, offset, aff))
